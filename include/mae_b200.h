@@ -1,0 +1,205 @@
+/*
+ * mae_b200.h — C ABI of libmae_b200.so: the B200 (sm_100a) implementation of the loss-and-evaluation
+ * hot path of XuezheMax/mae.
+ *
+ * The reference has no FFI / plugin API of its own (it is pure Python): its seam is
+ * the Python class interface in mae/modules.  Every entry point below therefore cites the Python
+ * function (reference file:line) whose arithmetic it replaces; the Python host layer in
+ * mae_b200/ops.py binds these symbols with ctypes and mae_b200/modules mirrors the class interface.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to fp32 data unless stated otherwise; sizes are int64_t;
+ *     "stride" arguments are ROW strides in elements (the reference's mu is a chunk(2,1) view with
+ *     row stride 2*D, encoder_cores/resnet.py:43); the innermost dimension is always contiguous.
+ *   - no allocation, no synchronisation and no global state inside: the caller owns every buffer,
+ *     including workspaces and outputs; all work is enqueued on `stream` (a cudaStream_t), so every
+ *     call can be captured into a CUDA graph.
+ *   - workspaces must be zero-filled once when allocated (they carry self-resetting tickets) and
+ *     must not be shared by calls that may run concurrently.
+ *   - return value: 0 on success, a negative MAE_ERR_* code for an argument error, or a positive
+ *     cudaError_t from the launch.  mae_strerror() maps either to text.
+ *   - "nullable" pointers may be NULL; the documented default is used instead.
+ */
+#ifndef MAE_B200_H
+#define MAE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* mae_stream_t; /* cudaStream_t */
+
+#define MAE_ABI_VERSION 1
+
+enum {
+    MAE_OK = 0,
+    MAE_ERR_NULL = -1,      /* a required pointer is NULL */
+    MAE_ERR_SHAPE = -2,     /* a size is <= 0, too large, or inconsistent (e.g. MPD with B < 2) */
+    MAE_ERR_STRIDE = -3,    /* a row stride is smaller than the row length */
+    MAE_ERR_WORKSPACE = -4, /* workspace too small for the given sizes */
+    MAE_ERR_ALIGN = -5,     /* a pointer is not 16-byte aligned where the kernel needs it */
+    MAE_ERR_UNSUPPORTED = -6
+};
+
+int mae_abi_version(void);
+const char* mae_strerror(int code);
+/* SM count / compute capability of the current device; used by the host layer to refuse non-sm_100 parts. */
+int mae_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------------------------------
+ * A1 + A2  reparameterised sample and analytic KL
+ *   replaces GaussianEncoder.reparameterize  (mae/modules/encoders/gaussian_encoder.py:56-62)
+ *        and the analytic KL of encode()     (mae/modules/encoders/gaussian_encoder.py:219)
+ *   z[b,s,d]  = eps[b,s,d] * exp(0.5*logvar[b,d]) + mu[b,d]
+ *   kl[b]     = 0.5 * sum_d (mu^2 + exp(logvar) - logvar - 1)            (kl nullable: skipped)
+ *   eps is drawn by the caller (torch Philox) so RNG parity with the reference is exact.
+ * bwd: gz [B,ns,D] nullable, gkl [B] nullable ->
+ *   dmu[b,d] (+)= sum_s gz + gkl[b]*mu ;  dlogvar[b,d] (+)= 0.5*exp(0.5*logvar)*sum_s(gz*eps) + 0.5*gkl[b]*(exp(logvar)-1)
+ *   accumulate != 0 adds into dmu/dlogvar instead of overwriting (dmu/dlogvar are dense [B,D]).
+ * ---------------------------------------------------------------------------------------------- */
+int mae_reparam_kl_fwd(const float* mu, int64_t mu_stride, const float* logvar, int64_t logvar_stride,
+                       const float* eps, int64_t B, int64_t ns, int64_t D,
+                       float* z, float* kl, mae_stream_t stream);
+int mae_reparam_kl_bwd(const float* mu, int64_t mu_stride, const float* logvar, int64_t logvar_stride,
+                       const float* eps, const float* gz, const float* gkl,
+                       int64_t B, int64_t ns, int64_t D,
+                       float* dmu, float* dlogvar, int accumulate, mae_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * A3  mutual posterior divergence (MPD) regulariser
+ *   replaces GaussianEncoder._postKL (mae/modules/encoders/gaussian_encoder.py:162-188)
+ *
+ *   KL_ij = 0.5 * sum_d [ v_i r_j + (mu_i-mu_j)^2 r_j - (lv_i - lv_j) - 1 ],  v = exp(lv), r = 1/(v+1e-12)
+ *   m_d   = sum_{i!=j} KL_ij,d / (B(B-1))                      (per latent dimension, [D])
+ *   S     = sqrt( sum_{i!=j} (KL_ij - m)^2 / (B(B-1) - 1) ),   m = sum_d m_d
+ *   (this is what the Eye*mean fill, unbiased .std() and the cc/dd factors at :181-187 reduce to.)
+ *
+ * The B x B matrix is never formed by the large path: tiles of 2*KL_ij = x~_i . y~_j + c_j - l_i - D with
+ * x~ = [v+mu^2, mu], y~ = [r, -2 mu r] (K = 2D) are produced in shared memory / registers.
+ *
+ * mae_mpd_prepare : O(B*D) pre-pass over ALL B posteriors (after an all-gather in multi-GPU runs):
+ *                   packed panels, per-dimension column statistics, m_d (written to m_d[D]) and m.
+ * mae_mpd_fwd     : tiles for rows [row0,row0+nrows) x all B columns.  Writes sumsq[0] (double) =
+ *                   sum over those rows and all j != i of (KL_ij - m)^2, and, if S is non-NULL,
+ *                   S[0] = sqrt(sumsq/(B(B-1)-1)) (meaningful when the row range covers all rows).
+ *                   store_kl != 0 additionally keeps the KL tiles in the workspace for the small-B
+ *                   backward (requires B <= MAE_MPD_SMALL_B and the full row range).
+ * mae_mpd_finalize: S[0] = sqrt(sumsq[0]/(B(B-1)-1)) after sumsq has been all-reduced across ranks.
+ * mae_mpd_bwd     : gradient of  sum_d g_m[d]*m_d + g_S*S  w.r.t. mu and logvar of rows
+ *                   [row0,row0+nrows): dmu/dlogvar are dense [nrows,D].  Each row's contribution both
+ *                   as the "i" and as the "j" argument of KL_ij is included, so no cross-rank
+ *                   reduce-scatter of column gradients is needed.  g_S and S are device scalars.
+ *                   path: 0 = choose automatically, 1 = stored-KL path, 2 = recompute-tile path.
+ * ---------------------------------------------------------------------------------------------- */
+#define MAE_MPD_SMALL_B 2048
+int64_t mae_mpd_workspace_bytes(int64_t B, int64_t D);
+int mae_mpd_prepare(const float* mu, int64_t mu_stride, const float* logvar, int64_t logvar_stride,
+                    int64_t B, int64_t D, void* workspace, int64_t workspace_bytes,
+                    float* m_d, mae_stream_t stream);
+int mae_mpd_fwd(void* workspace, int64_t workspace_bytes, int64_t B, int64_t D,
+                int64_t row0, int64_t nrows, int store_kl,
+                double* sumsq, float* S, mae_stream_t stream);
+int mae_mpd_finalize(const double* sumsq, int64_t B, float* S, mae_stream_t stream);
+int mae_mpd_bwd(const float* mu, int64_t mu_stride, const float* logvar, int64_t logvar_stride,
+                void* workspace, int64_t workspace_bytes, int64_t B, int64_t D,
+                int64_t row0, int64_t nrows,
+                const float* g_m, const float* g_S, const float* S,
+                float* dmu, float* dlogvar, int accumulate, int path, mae_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * A4a  Bernoulli reconstruction error
+ *   replaces BinaryImageDecoder.reconstruct_error (.../image_decoders/binary_image_decoder.py:84-93)
+ *        and its duplicate in PixelCNNDecoderBinaryImage28x28 (.../image_decoders/pixelcnn.py:136-139)
+ *   err[b,s] = - sum_p [ log(probs[b,s,p] + 1e-12) * x[b,p] + log(1 - probs[b,s,p] + 1e-12) * (1 - x[b,p]) ]
+ *   probs are post-sigmoid probabilities [B,ns,P]; x is [B,P].
+ * bwd: dprobs[b,s,p] = g[b,s] * ( (1-x)/(1-probs+1e-12) - x/(probs+1e-12) )
+ * ---------------------------------------------------------------------------------------------- */
+int mae_bernoulli_fwd(const float* probs, const float* x, int64_t B, int64_t ns, int64_t P,
+                      float* err, mae_stream_t stream);
+int mae_bernoulli_bwd(const float* probs, const float* x, const float* g, int64_t B, int64_t ns, int64_t P,
+                      float* dprobs, mae_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * A4b + A4c  discretized mixture of logistics, from the RAW decoder output
+ *   replaces ColorImageDecoder.execute            (.../image_decoders/color_image_decoder.py:38-52)
+ *            ColorImageDecoder.reconstruct_error  (.../image_decoders/color_image_decoder.py:91-125)
+ *            discretized_mix_logistic_loss        (mae/modules/utils.py:61-123)
+ *   raw [B*ns, 10*nmix, HW] (NCHW: logits | means | log-scales | coefficients, mixture-major and
+ *   colour-minor inside each group), x [B,3,HW] in [-1,1]; err [B,ns].
+ *   log-softmax of the logits, clamp(min=-7) of the log-scales and tanh of the coefficients happen
+ *   inside the kernel.  bin 1/255, lower 1/255-1, upper 1-1/255 as in the reference.
+ *   workspace: mae_dmol_workspace_bytes(B*ns, HW) bytes (per-CTA partial sums + tickets).
+ * bwd: draw [B*ns,10*nmix,HW] = g[b,s] * d err[b,s] / d raw   (clamp gate passes at equality).
+ * ---------------------------------------------------------------------------------------------- */
+int64_t mae_dmol_workspace_bytes(int64_t N, int64_t HW);
+int mae_dmol_fwd(const float* raw, const float* x, int64_t B, int64_t ns, int64_t nmix, int64_t HW,
+                 float* err, void* workspace, int64_t workspace_bytes, mae_stream_t stream);
+int mae_dmol_bwd(const float* raw, const float* x, const float* g, int64_t B, int64_t ns, int64_t nmix, int64_t HW,
+                 float* draw, mae_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * A5 / A6  Gaussian log densities
+ *   replaces GaussianEncoder.log_probability_prior     (gaussian_encoder.py:231-260, lines 256-258)
+ *            GaussianEncoder.log_probability_posterior (gaussian_encoder.py:262-301, lines 297-299)
+ *   prior:     out[n]   = -0.5 * sum_d (z[n,d]^2 + log 2pi) + logdet[n]                (logdet nullable = 0)
+ *   posterior: out[b,k] = -0.5 * sum_d (lv + (z-mu)^2/(exp(lv)+1e-12) + log 2pi) + logdet[b,k]
+ *   the flow transforms that produce z_normal/logdet stay in PyTorch.
+ * bwd (for the Monte-Carlo KL branch of encode(), gaussian_encoder.py:220-225):
+ *   prior:     dz = -g[n]*z
+ *   posterior: dz = -g*(z-mu)*r ; dmu = sum_k g*(z-mu)*r ; dlogvar = sum_k -0.5*g*(1 - (z-mu)^2 r^2 v)
+ *   (d logdet = g is a pass-through done by the host layer).
+ * ---------------------------------------------------------------------------------------------- */
+int mae_log_prob_prior_fwd(const float* z_normal, const float* logdet, int64_t N, int64_t D,
+                           float* out, mae_stream_t stream);
+int mae_log_prob_prior_bwd(const float* z_normal, const float* g, int64_t N, int64_t D,
+                           float* dz, mae_stream_t stream);
+int mae_log_prob_posterior_fwd(const float* z_normal, const float* logdet,
+                               const float* mu, int64_t mu_stride, const float* logvar, int64_t logvar_stride,
+                               int64_t B, int64_t K, int64_t D, float* out, mae_stream_t stream);
+int mae_log_prob_posterior_bwd(const float* z_normal, const float* g,
+                               const float* mu, int64_t mu_stride, const float* logvar, int64_t logvar_stride,
+                               int64_t B, int64_t K, int64_t D,
+                               float* dz, float* dmu, float* dlogvar, mae_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * A5 + A6 + A7  fused importance-weighted NLL estimator
+ *   replaces the tail of MAE.nll (mae/modules/mae.py:203-215) and logsumexp (mae/modules/utils.py:23-38)
+ *   log_gen [B,K] (= -reconstruct_error), z_prior_normal [B,K,D] + logdet_prior [B,K] (nullable = 0),
+ *   z_post_normal [B,K,D] + logdet_post [B,K] (nullable = 0), mu/logvar [B,D]  ->
+ *   nll_elbo[b] = -mean_k log_iw ; recon[b] = -mean_k log_gen ; kl[b] = mean_k (log q - log p) ;
+ *   nll_iw[b]   = -(max_k log_iw + log sum_k exp(log_iw - max)) + log K ,  log_iw = log_gen + log p - log q
+ * ---------------------------------------------------------------------------------------------- */
+int mae_iw_nll(const float* log_gen, const float* z_prior_normal, const float* logdet_prior,
+               const float* z_post_normal, const float* logdet_post,
+               const float* mu, int64_t mu_stride, const float* logvar, int64_t logvar_stride,
+               int64_t B, int64_t K, int64_t D,
+               float* nll_elbo, float* recon, float* kl, float* nll_iw, mae_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * A3' + A8  objective assembly
+ *   replaces MAE.loss lines mae/modules/mae.py:132-140
+ *   err [B,ns], kl [B], m_d [D] (nullable), S [1] (nullable) ->
+ *   recon[b] = mean_s err[b,s]
+ *   scalars[0] = loss = mean_b recon + max(mean_b kl, free_bits) + loss_mean + loss_std
+ *   scalars[1] = postKL_mean = sum_d m_d         scalars[2] = loss_mean = -eta * sum_d logsigmoid(m_d)  (0 if eta<=0)
+ *   scalars[3] = loss_std = gamma * S (0 if gamma<=0)      scalars[4] = mean_b kl       scalars[5] = mean_b recon
+ *   inv_batch: 1/B_global (>0) lets multi-GPU callers pass local partial tensors; 0 -> 1/B.
+ * bwd, given gloss (device scalar, nullable = 1):
+ *   derr[b,s] = gloss*inv_batch/ns ; dkl[b] = gloss*inv_batch*[mean kl >= free_bits] ;
+ *   dm_d[d] = -gloss*eta*sigmoid(-m_d) ; dS = gloss*gamma
+ *   kl_mean is read from scalars[4] written by the forward.
+ * ---------------------------------------------------------------------------------------------- */
+int mae_loss_assemble_fwd(const float* err, const float* kl, const float* m_d, const float* S,
+                          int64_t B, int64_t ns, int64_t D, float eta, float gamma, float free_bits, float inv_batch,
+                          float* scalars, float* recon, mae_stream_t stream);
+int mae_loss_assemble_bwd(const float* gloss, const float* scalars, const float* m_d,
+                          int64_t B, int64_t ns, int64_t D, float eta, float gamma, float free_bits, float inv_batch,
+                          float* derr, float* dkl, float* dm_d, float* dS, mae_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAE_B200_H */

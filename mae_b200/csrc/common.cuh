@@ -1,0 +1,78 @@
+// Shared helpers for the sm_100a kernels of libmae_b200.so.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/mae_b200.h"
+
+#define MAE_REQUIRE(cond, code) \
+    do {                        \
+        if (!(cond)) return (code); \
+    } while (0)
+
+namespace mae {
+
+constexpr float kEps = 1e-12f;           // the reference's eps everywhere on the path
+constexpr float kLog2Pi = 1.8378770664093453f;
+constexpr int kWarp = 32;
+
+static inline int launch_status() {
+    cudaError_t e = cudaPeekAtLastError();
+    return e == cudaSuccess ? MAE_OK : static_cast<int>(e);
+}
+
+static inline cudaStream_t as_stream(mae_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
+
+// Number of SMs of the current device (cached per process; 148 on B200).
+int sm_count();
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Block-wide sum; every thread returns the total.  `scratch` holds >= 32 elements of T.
+// Fixed reduction order -> deterministic.
+template <typename T>
+__device__ __forceinline__ T block_sum(T v, T* scratch) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();  // scratch may still be in use by a previous call
+    if (lane == 0) scratch[w] = v;
+    __syncthreads();
+    T t = (lane < nw) ? scratch[lane] : T(0);
+    t = warp_sum(t);
+    return t;
+}
+
+// Streaming (read-once) global load that does not allocate in L1.
+__device__ __forceinline__ float ldg_stream(const float* p) {
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float4 ldg_stream4(const float* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void stg_stream(float* p, float v) {
+    asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(p), "f"(v));
+}
+
+}  // namespace mae

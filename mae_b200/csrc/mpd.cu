@@ -1,0 +1,640 @@
+// A3: mutual posterior divergence regulariser (gaussian_encoder.py:162-188) without the [B,B,D] tensor.
+//
+//   2*KL_ij = x~_i . y~_j + c_j - l_i - D        (K = 2D contraction, FP32 FFMA, register-tiled)
+//     x~_i = [v_i + mu_i^2, mu_i]  (interleaved per latent dim: k = 2d, 2d+1)
+//     y~_j = [r_j, -2 mu_j r_j]    v = exp(lv), r = 1/(v + 1e-12)
+//     c_j  = sum_d (mu_j^2 r_j + lv_j),  l_i = sum_d lv_i
+//   mu is taken relative to row 0 (KL is translation invariant per dimension), which removes the
+//   cancellation a common offset would cause in the expanded square.
+//
+// Kernels
+//   mpd_prepare_kernel   O(B*D): panels X~, Y~ (row-major [Bp][Kp]), V (float4 {mu,v,r,lv}), c, l, per-dimension
+//                        column sums in fp64, m_d and m = sum_d m_d (closed form, SURVEY.md §8a "A3-alg").
+//   mpd_fwd_kernel       64x64 tiles of KL over rows [row0,row1) x all columns; accumulates sum (KL_ij - m)^2
+//                        (m is known beforehand, so no E[x^2]-E[x]^2 cancellation); optional KL / KL^T store.
+//   mpd_bwd_small_kernel B <= 2048: per-(i,d) gradient from the stored KL and KL^T (L2-resident).
+//   mpd_bwd_tile_kernel  large B: flash-attention-style recompute; per row block, for every column block
+//                        recompute KL_ij and KL_ji tiles, form the weights W, and contract W with the
+//                        column panels (two more FFMA GEMMs); the row owner receives its complete gradient
+//                        (as the i and as the j argument), so there are no atomics and no reduce-scatter.
+// All cross-CTA reductions are ticketed and summed in a fixed order -> bit-reproducible results.
+#include "common.cuh"
+
+namespace mae {
+namespace {
+
+constexpr int kT = 64;         // tile edge (rows and columns per CTA tile)
+constexpr int kKC = 16;        // K chunk staged in shared memory per step
+constexpr int kNT = 256;       // threads per CTA: 16 x 16 threads, 4 x 4 micro-tile each
+constexpr int kLd = kT + 4;    // padded leading dimension (keeps float4 alignment)
+constexpr int kOC = 128;       // K columns (= 64 latent dims) of gradient owned by one CTA of the tile backward
+constexpr int kLdP = kOC + 4;
+constexpr int kMaxFwdCtas = 592;  // 4 x 148; fixed so partial-sum order does not depend on the device
+
+struct Hdr {  // first 256 bytes of the workspace
+    unsigned int ticket_prep;
+    unsigned int ticket_fwd;
+    unsigned int pad[2];
+    double m;      // sum_d m_d
+    double sumsq;  // last forward result
+};
+
+struct Layout {
+    int64_t Bp, Kp, nblk;
+    int64_t hdr, colstats, c, l, xp, yp, vp, part_prep, part_fwd, kl, klt, total;
+};
+
+Layout make_layout(int64_t B, int64_t D) {
+    Layout L;
+    L.Bp = round_up(B, kT);
+    L.Kp = round_up(2 * D, kKC);
+    L.nblk = L.Bp / kT;
+    int64_t off = 0;
+    auto take = [&](int64_t bytes) {
+        int64_t o = off;
+        off += round_up(bytes, 256);
+        return o;
+    };
+    L.hdr = take(256);
+    L.colstats = take(8 * D * 8);
+    L.c = take(L.Bp * 4);
+    L.l = take(L.Bp * 4);
+    L.xp = take(L.Bp * L.Kp * 4);
+    L.yp = take(L.Bp * L.Kp * 4);
+    L.vp = take(L.Bp * D * 16);
+    L.part_prep = take(L.nblk * 7 * D * 8);
+    L.part_fwd = take(kMaxFwdCtas * 8);
+    if (B <= MAE_MPD_SMALL_B) {
+        L.kl = take(L.Bp * L.Bp * 4);
+        L.klt = take(L.Bp * L.Bp * 4);
+    } else {
+        L.kl = L.klt = -1;
+    }
+    L.total = off;
+    return L;
+}
+
+template <typename T>
+T* at(void* ws, int64_t off) {
+    return reinterpret_cast<T*>(static_cast<char*>(ws) + off);
+}
+
+// ---------------------------------------------------------------------------------------------- prepare
+__global__ void __launch_bounds__(kNT)
+mpd_prepare_kernel(const float* __restrict__ mu, int64_t mu_stride, const float* __restrict__ lv, int64_t lv_stride, int B,
+                   int D, int Kp, float* __restrict__ Xp, float* __restrict__ Yp, float4* __restrict__ Vp,
+                   float* __restrict__ cvec, float* __restrict__ lvec, double* part, double* __restrict__ colstats, Hdr* hdr,
+                   float* __restrict__ m_d_out) {
+    __shared__ double scratch[32];
+    __shared__ bool is_last;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int blk = blockIdx.x;
+    const int i0 = blk * kT;
+
+    // phase A: one warp per row; lanes strided over latent dims (coalesced reads and panel writes)
+    for (int r = w; r < kT; r += kNT / 32) {
+        const int i = i0 + r;
+        float* xr = Xp + (int64_t)i * Kp;
+        float* yr = Yp + (int64_t)i * Kp;
+        float cs = 0.f, ls = 0.f;
+        if (i < B) {
+            const float* mr = mu + (int64_t)i * mu_stride;
+            const float* lr = lv + (int64_t)i * lv_stride;
+            for (int d = lane; d < D; d += 32) {
+                const float l = lr[d];
+                const float mc = mr[d] - mu[d];  // relative to row 0
+                const float v = expf(l);
+                const float rr = 1.0f / (v + kEps);
+                *reinterpret_cast<float2*>(xr + 2 * d) = make_float2(v + mc * mc, mc);
+                *reinterpret_cast<float2*>(yr + 2 * d) = make_float2(rr, -2.0f * mc * rr);
+                Vp[(int64_t)i * D + d] = make_float4(mc, v, rr, l);
+                cs += mc * mc * rr + l;
+                ls += l;
+            }
+            for (int k = 2 * D + lane; k < Kp; k += 32) {
+                xr[k] = 0.f;
+                yr[k] = 0.f;
+            }
+        } else {
+            for (int k = lane; k < Kp; k += 32) {
+                xr[k] = 0.f;
+                yr[k] = 0.f;
+            }
+        }
+        cs = warp_sum(cs);
+        ls = warp_sum(ls);
+        if (lane == 0) {
+            cvec[i] = cs;
+            lvec[i] = ls;
+        }
+    }
+
+    // phase B: per-dimension partial column sums over this CTA's rows, fp64
+    for (int d = tid; d < D; d += kNT) {
+        double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0, a6 = 0;
+        const float pivot = mu[d];
+        for (int r = 0; r < kT; ++r) {
+            const int i = i0 + r;
+            if (i >= B) break;
+            const float l = lv[(int64_t)i * lv_stride + d];
+            const float mc = mu[(int64_t)i * mu_stride + d] - pivot;
+            const float v = expf(l);
+            const float rr = 1.0f / (v + kEps);
+            a0 += v;
+            a1 += rr;
+            a2 += (double)v * rr;
+            a3 += mc;
+            a4 += (double)mc * mc;
+            a5 += (double)rr * mc;
+            a6 += (double)rr * mc * mc;
+        }
+        double* p = part + (int64_t)blk * 7 * D + d;
+        p[0 * (int64_t)D] = a0;
+        p[1 * (int64_t)D] = a1;
+        p[2 * (int64_t)D] = a2;
+        p[3 * (int64_t)D] = a3;
+        p[4 * (int64_t)D] = a4;
+        p[5 * (int64_t)D] = a5;
+        p[6 * (int64_t)D] = a6;
+    }
+
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned int t = atomicAdd(&hdr->ticket_prep, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+
+    // last CTA: ordered sum of the partials, closed-form m_d
+    const double nb = (double)B;
+    double msum = 0.0;
+    for (int d = tid; d < D; d += kNT) {
+        double s[7] = {0, 0, 0, 0, 0, 0, 0};
+        for (int bk = 0; bk < (int)gridDim.x; ++bk) {
+            const double* p = part + (int64_t)bk * 7 * D + d;
+#pragma unroll
+            for (int q = 0; q < 7; ++q) s[q] += __ldcg(p + q * (int64_t)D);
+        }
+#pragma unroll
+        for (int q = 0; q < 7; ++q) colstats[q * (int64_t)D + d] = s[q];
+        // sum_{i!=j} [v_i r_j + (mu_i-mu_j)^2 r_j] = Sv*R0 - Svr + S2*R0 - 2*S1*R1 + B*R2
+        const double tn = s[0] * s[1] - s[2] + s[4] * s[1] - 2.0 * s[3] * s[5] + nb * s[6];
+        const double md = 0.5 * tn / (nb * (nb - 1.0)) - 0.5;
+        m_d_out[d] = (float)md;
+        msum += md;
+    }
+    msum = block_sum(msum, scratch);
+    if (tid == 0) {
+        hdr->m = msum;
+        hdr->ticket_prep = 0u;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ tile helpers
+// Stage a 64-row x 16-k slab of a row-major panel into shared memory, transposed to [k][row].
+__device__ __forceinline__ void stage_slab(const float* __restrict__ panel, int64_t row_base, int Kp, int k0,
+                                           float (*dst)[kLd], int tid) {
+    const int r = tid >> 2, kq = (tid & 3) * 4;
+    const float4 a = *reinterpret_cast<const float4*>(panel + (row_base + r) * Kp + k0 + kq);
+    dst[kq + 0][r] = a.x;
+    dst[kq + 1][r] = a.y;
+    dst[kq + 2][r] = a.z;
+    dst[kq + 3][r] = a.w;
+}
+
+__device__ __forceinline__ void fma_tile(const float (*A)[kLd], const float (*Bm)[kLd], int ty, int tx, float acc[4][4]) {
+#pragma unroll
+    for (int k = 0; k < kKC; ++k) {
+        const float4 a = *reinterpret_cast<const float4*>(&A[k][ty * 4]);
+        const float4 b = *reinterpret_cast<const float4*>(&Bm[k][tx * 4]);
+        const float av[4] = {a.x, a.y, a.z, a.w};
+        const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- forward
+__global__ void __launch_bounds__(kNT)
+mpd_fwd_kernel(const float* __restrict__ Xp, const float* __restrict__ Yp, const float* __restrict__ cvec,
+               const float* __restrict__ lvec, Hdr* hdr, double* part, int B, int D, int Kp, int row0, int row1, int tr0,
+               int ntr, int ntc, float* __restrict__ KL, float* __restrict__ KLT, int Bp, double* __restrict__ sumsq_out,
+               float* __restrict__ S_out) {
+    __shared__ __align__(16) float As[kKC][kLd];
+    __shared__ __align__(16) float Bs[kKC][kLd];
+    __shared__ double scratch[32];
+    __shared__ bool is_last;
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    const float m = (float)hdr->m;
+    const float fd = (float)D;
+    double total = 0.0;
+    const int ntiles = ntr * ntc;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int ti = tr0 + tile / ntc, tj = tile % ntc;
+        float acc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        for (int k0 = 0; k0 < Kp; k0 += kKC) {
+            stage_slab(Xp, (int64_t)ti * kT, Kp, k0, As, tid);
+            stage_slab(Yp, (int64_t)tj * kT, Kp, k0, Bs, tid);
+            __syncthreads();
+            fma_tile(As, Bs, ty, tx, acc);
+            __syncthreads();
+        }
+        float psum = 0.f;
+        const int jb = tj * kT + tx * 4;
+        const float4 c4 = *reinterpret_cast<const float4*>(cvec + jb);
+        const float cj[4] = {c4.x, c4.y, c4.z, c4.w};
+        float klv[4][4];
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii) {
+            const int i = ti * kT + ty * 4 + ii;
+            const float li = lvec[i];
+            const bool row_ok = (i >= row0) && (i < row1);
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                const int j = jb + jj;
+                const float kl = 0.5f * (acc[ii][jj] + cj[jj] - li - fd);
+                klv[ii][jj] = kl;
+                if (row_ok && j < B && j != i) {
+                    const float dev = kl - m;
+                    psum = fmaf(dev, dev, psum);
+                }
+            }
+            if (KL != nullptr)
+                *reinterpret_cast<float4*>(KL + (int64_t)i * Bp + jb) = make_float4(klv[ii][0], klv[ii][1], klv[ii][2], klv[ii][3]);
+        }
+        if (KLT != nullptr) {
+            const int ib = ti * kT + ty * 4;
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj)
+                *reinterpret_cast<float4*>(KLT + (int64_t)(jb + jj) * Bp + ib) =
+                    make_float4(klv[0][jj], klv[1][jj], klv[2][jj], klv[3][jj]);
+        }
+        total += (double)psum;
+    }
+    total = block_sum(total, scratch);
+    if (tid == 0) {
+        part[blockIdx.x] = total;
+        __threadfence();
+        const unsigned int t = atomicAdd(&hdr->ticket_fwd, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last && tid == 0) {
+        __threadfence();
+        double s = 0.0;
+        for (int i = 0; i < (int)gridDim.x; ++i) s += __ldcg(part + i);
+        hdr->sumsq = s;
+        sumsq_out[0] = s;
+        if (S_out != nullptr) {
+            const double nb = (double)B;
+            S_out[0] = (float)sqrt(s / (nb * (nb - 1.0) - 1.0));
+        }
+        hdr->ticket_fwd = 0u;
+    }
+}
+
+__global__ void mpd_finalize_kernel(const double* __restrict__ sumsq, double nb, float* __restrict__ S) {
+    S[0] = (float)sqrt(sumsq[0] / (nb * (nb - 1.0) - 1.0));
+}
+
+// --------------------------------------------------------------------------------- backward: common parts
+// weight scale of (KL - m): g_S / ((B^2 - B - 1) * S)     (SURVEY.md §8a "A3-bwd")
+__device__ __forceinline__ float weight_scale(const float* g_S, const float* S, int B) {
+    if (g_S == nullptr) return 0.f;
+    const double s = (double)S[0];
+    if (!(s > 0.0)) return 0.f;
+    const double nb = (double)B;
+    return (float)((double)g_S[0] / ((nb * nb - nb - 1.0) * s));
+}
+
+// closed-form gradient of sum_d g_m[d]*m_d w.r.t. (mu_k,d ; lv_k,d), fp64, O(1) per element.
+__device__ __forceinline__ void mean_part(const double* __restrict__ cs, const float* __restrict__ g_m, int B, int D, int d,
+                                          float mc_f, float v_f, float r_f, float& gmu, float& glv) {
+    if (g_m == nullptr) return;
+    const double nb = (double)B;
+    const double a = (double)g_m[d] / (nb * (nb - 1.0));
+    const double Sv = cs[0 * (int64_t)D + d], R0 = cs[1 * (int64_t)D + d], S1 = cs[3 * (int64_t)D + d],
+                 S2 = cs[4 * (int64_t)D + d], R1 = cs[5 * (int64_t)D + d];
+    const double mc = mc_f, v = v_f, r = r_f;
+    const double dT_dmu = 2.0 * ((mc * R0 - R1) + r * (nb * mc - S1));
+    const double dT_dlv = v * ((R0 - r) - r * r * (Sv - v + S2 - 2.0 * S1 * mc + nb * mc * mc));
+    gmu += (float)(0.5 * a * dT_dmu);
+    glv += (float)(0.5 * a * dT_dlv);
+}
+
+// ------------------------------------------------------------------------- backward, stored-KL (small B)
+// one warp per (row i, 32 latent dims); walks all partners j.
+__global__ void __launch_bounds__(kNT)
+mpd_bwd_small_kernel(const float4* __restrict__ Vp, const float* __restrict__ KL, const float* __restrict__ KLT, int Bp,
+                     const double* __restrict__ colstats, const Hdr* __restrict__ hdr, const float* __restrict__ g_m,
+                     const float* __restrict__ g_S, const float* __restrict__ S, int B, int D, int row0, int nrows,
+                     float* __restrict__ dmu, float* __restrict__ dlv, int accumulate) {
+    const int lane = threadIdx.x & 31;
+    const int nd32 = (D + 31) / 32;
+    const int64_t wg = (int64_t)blockIdx.x * (kNT / 32) + (threadIdx.x >> 5);
+    if (wg >= (int64_t)nrows * nd32) return;
+    const int i = row0 + (int)(wg / nd32);
+    const int d = (int)(wg % nd32) * 32 + lane;
+    const bool active = d < D;
+    const float m = (float)hdr->m;
+    const float beta = weight_scale(g_S, S, B);
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 pi = active ? Vp[(int64_t)i * D + d] : zero4;  // {mu, v, r, lv} of row i
+    float gmu = 0.f, glv = 0.f;
+    if (beta != 0.f) {
+        const float* kl_row = KL + (int64_t)i * Bp;    // KL_ij
+        const float* klt_row = KLT + (int64_t)i * Bp;  // KL_ji
+        const float riv = pi.z * pi.z * pi.y;          // r_i^2 v_i
+        for (int j = 0; j < B; ++j) {
+            if (j == i) continue;
+            const float w1 = beta * (kl_row[j] - m);
+            const float w2 = beta * (klt_row[j] - m);
+            const float4 pj = active ? Vp[(int64_t)j * D + d] : zero4;
+            const float dl = pi.x - pj.x;
+            gmu = fmaf(dl, fmaf(w1, pj.z, w2 * pi.z), gmu);
+            glv += w1 * (pi.y * pj.z - 1.0f) + w2 * (1.0f - (pj.y + dl * dl) * riv);
+        }
+        glv *= 0.5f;
+    }
+    if (!active) return;
+    mean_part(colstats, g_m, B, D, d, pi.x, pi.y, pi.z, gmu, glv);
+    const int64_t o = (int64_t)(i - row0) * D + d;
+    if (accumulate) {
+        dmu[o] += gmu;
+        dlv[o] += glv;
+    } else {
+        dmu[o] = gmu;
+        dlv[o] = glv;
+    }
+}
+
+// ----------------------------------------------------------------------- backward, recompute tiles (large B)
+struct BwdSmem {
+    float XI[kKC][kLd], YI[kKC][kLd], XJ[kKC][kLd], YJ[kKC][kLd];
+    float W1T[kT][kLd], W2T[kT][kLd];  // [j][i]
+    float PY[kT][kLdP], PX[kT][kLdP];  // column panels of block J, this CTA's K chunk
+};
+
+// grid: (row tiles, K chunks of kOC columns).  CTA owns rows [i0,i0+64) and gradient dims of its chunk.
+__global__ void __launch_bounds__(kNT)
+mpd_bwd_tile_kernel(const float* __restrict__ Xp, const float* __restrict__ Yp, const float* __restrict__ cvec,
+                    const float* __restrict__ lvec, const float4* __restrict__ Vp, const double* __restrict__ colstats,
+                    const Hdr* __restrict__ hdr, const float* __restrict__ g_m, const float* __restrict__ g_S,
+                    const float* __restrict__ S, int B, int D, int Kp, int row0, int row1, int tr0, int ntc,
+                    float* __restrict__ dmu, float* __restrict__ dlv, int accumulate) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    BwdSmem& sm = *reinterpret_cast<BwdSmem*>(smem_raw);
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    const int ti = tr0 + blockIdx.x;
+    const int i0 = ti * kT;
+    const int kbase = blockIdx.y * kOC;
+    const float m = (float)hdr->m;
+    const float beta = weight_scale(g_S, S, B);
+    const float fd = (float)D;
+
+    float G1[4][8], G2[4][8], rs1[4], rs2[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        rs1[i] = rs2[i] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) G1[i][j] = G2[i][j] = 0.f;
+    }
+    float ci[4], li[4];
+#pragma unroll
+    for (int ii = 0; ii < 4; ++ii) {
+        ci[ii] = cvec[i0 + ty * 4 + ii];
+        li[ii] = lvec[i0 + ty * 4 + ii];
+    }
+
+    if (beta != 0.f) {
+        for (int tj = 0; tj < ntc; ++tj) {
+            const int j0 = tj * kT;
+            float a1[4][4], a2[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) a1[i][j] = a2[i][j] = 0.f;
+            for (int k0 = 0; k0 < Kp; k0 += kKC) {
+                stage_slab(Xp, (int64_t)i0, Kp, k0, sm.XI, tid);
+                stage_slab(Yp, (int64_t)i0, Kp, k0, sm.YI, tid);
+                stage_slab(Xp, (int64_t)j0, Kp, k0, sm.XJ, tid);
+                stage_slab(Yp, (int64_t)j0, Kp, k0, sm.YJ, tid);
+                __syncthreads();
+                fma_tile(sm.XI, sm.YJ, ty, tx, a1);  // x~_i . y~_j  -> KL_ij
+                fma_tile(sm.YI, sm.XJ, ty, tx, a2);  // y~_i . x~_j  -> KL_ji
+                __syncthreads();
+            }
+            // weights; W1T/W2T stored [j][i]
+            const int jb = j0 + tx * 4;
+            const float4 c4 = *reinterpret_cast<const float4*>(cvec + jb);
+            const float4 l4 = *reinterpret_cast<const float4*>(lvec + jb);
+            const float cj[4] = {c4.x, c4.y, c4.z, c4.w};
+            const float lj[4] = {l4.x, l4.y, l4.z, l4.w};
+            float w1[4][4], w2[4][4];
+#pragma unroll
+            for (int ii = 0; ii < 4; ++ii) {
+                const int i = i0 + ty * 4 + ii;
+                const bool row_ok = (i >= row0) && (i < row1);
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    const int j = jb + jj;
+                    const bool ok = row_ok && j < B && j != i;
+                    const float kij = 0.5f * (a1[ii][jj] + cj[jj] - li[ii] - fd);
+                    const float kji = 0.5f * (a2[ii][jj] + ci[ii] - lj[jj] - fd);
+                    w1[ii][jj] = ok ? beta * (kij - m) : 0.f;
+                    w2[ii][jj] = ok ? beta * (kji - m) : 0.f;
+                    rs1[ii] += w1[ii][jj];
+                    rs2[ii] += w2[ii][jj];
+                }
+            }
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                *reinterpret_cast<float4*>(&sm.W1T[tx * 4 + jj][ty * 4]) = make_float4(w1[0][jj], w1[1][jj], w1[2][jj], w1[3][jj]);
+                *reinterpret_cast<float4*>(&sm.W2T[tx * 4 + jj][ty * 4]) = make_float4(w2[0][jj], w2[1][jj], w2[2][jj], w2[3][jj]);
+            }
+            // column panels of block J restricted to this CTA's K chunk: 64 rows x 128 columns each
+            for (int q = tid; q < kT * (kOC / 4); q += kNT) {
+                const int r = q / (kOC / 4), c = (q % (kOC / 4)) * 4;
+                float4 y = make_float4(0.f, 0.f, 0.f, 0.f), x = y;
+                if (kbase + c < Kp) {
+                    y = *reinterpret_cast<const float4*>(Yp + (int64_t)(j0 + r) * Kp + kbase + c);
+                    x = *reinterpret_cast<const float4*>(Xp + (int64_t)(j0 + r) * Kp + kbase + c);
+                }
+                *reinterpret_cast<float4*>(&sm.PY[r][c]) = y;
+                *reinterpret_cast<float4*>(&sm.PX[r][c]) = x;
+            }
+            __syncthreads();
+            // G1[i][k] += sum_j W1[i][j] * y~_j[k];  G2[i][k] += sum_j W2[i][j] * x~_j[k]
+#pragma unroll 4
+            for (int j = 0; j < kT; ++j) {
+                const float4 wa = *reinterpret_cast<const float4*>(&sm.W1T[j][ty * 4]);
+                const float4 wb = *reinterpret_cast<const float4*>(&sm.W2T[j][ty * 4]);
+                const float4 y0 = *reinterpret_cast<const float4*>(&sm.PY[j][tx * 4]);
+                const float4 y1 = *reinterpret_cast<const float4*>(&sm.PY[j][64 + tx * 4]);
+                const float4 x0 = *reinterpret_cast<const float4*>(&sm.PX[j][tx * 4]);
+                const float4 x1 = *reinterpret_cast<const float4*>(&sm.PX[j][64 + tx * 4]);
+                const float wav[4] = {wa.x, wa.y, wa.z, wa.w};
+                const float wbv[4] = {wb.x, wb.y, wb.z, wb.w};
+                const float yv[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
+                const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+                for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        G1[ii][c] = fmaf(wav[ii], yv[c], G1[ii][c]);
+                        G2[ii][c] = fmaf(wbv[ii], xv[c], G2[ii][c]);
+                    }
+            }
+            __syncthreads();
+        }
+        // row sums of W: reduce the per-thread partials over the 16 threads (tx) that share a row group
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii) {
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) {
+                rs1[ii] += __shfl_xor_sync(0xffffffffu, rs1[ii], o);
+                rs2[ii] += __shfl_xor_sync(0xffffffffu, rs2[ii], o);
+            }
+        }
+    }
+
+    // epilogue: this thread holds, for 4 rows, K columns {tx*4..tx*4+3} and {64+tx*4..}: 4 latent dims per row
+#pragma unroll
+    for (int ii = 0; ii < 4; ++ii) {
+        const int i = i0 + ty * 4 + ii;
+        if (i < row0 || i >= row1) continue;
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            const int cb = (h >> 1) * 4 + (h & 1) * 2;           // register column of the pair (2d, 2d+1)
+            const int kcol = kbase + (h >> 1) * 64 + tx * 4 + (h & 1) * 2;
+            const int d = kcol >> 1;
+            if (d >= D) continue;
+            const float4 pi = Vp[(int64_t)i * D + d];  // {mu, v, r, lv}
+            const float g1r = G1[ii][cb], g1m = G1[ii][cb + 1], g2x = G2[ii][cb], g2m = G2[ii][cb + 1];
+            float gmu = pi.x * g1r + 0.5f * g1m - pi.z * (g2m - pi.x * rs2[ii]);
+            float glv = 0.5f * (pi.y * g1r - rs1[ii]) +
+                        0.5f * (rs2[ii] - pi.z * pi.z * pi.y * (g2x - 2.0f * pi.x * g2m + pi.x * pi.x * rs2[ii]));
+            mean_part(colstats, g_m, B, D, d, pi.x, pi.y, pi.z, gmu, glv);
+            const int64_t o = (int64_t)(i - row0) * D + d;
+            if (accumulate) {
+                dmu[o] += gmu;
+                dlv[o] += glv;
+            } else {
+                dmu[o] = gmu;
+                dlv[o] = glv;
+            }
+        }
+    }
+}
+
+int check_common(int64_t B, int64_t D, const void* ws, int64_t ws_bytes, Layout& L) {
+    MAE_REQUIRE(ws != nullptr, MAE_ERR_NULL);
+    MAE_REQUIRE(B >= 2 && D >= 1 && B <= (1ll << 22) && D <= (1ll << 20), MAE_ERR_SHAPE);
+    MAE_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 255) == 0, MAE_ERR_ALIGN);
+    L = make_layout(B, D);
+    MAE_REQUIRE(ws_bytes >= L.total, MAE_ERR_WORKSPACE);
+    return MAE_OK;
+}
+
+}  // namespace
+}  // namespace mae
+
+extern "C" int64_t mae_mpd_workspace_bytes(int64_t B, int64_t D) {
+    if (B < 2 || D < 1) return 0;
+    return mae::make_layout(B, D).total;
+}
+
+extern "C" int mae_mpd_prepare(const float* mu, int64_t mu_stride, const float* logvar, int64_t logvar_stride, int64_t B,
+                               int64_t D, void* workspace, int64_t workspace_bytes, float* m_d, mae_stream_t stream) {
+    using namespace mae;
+    MAE_REQUIRE(mu && logvar && m_d, MAE_ERR_NULL);
+    Layout L;
+    int rc = check_common(B, D, workspace, workspace_bytes, L);
+    if (rc != MAE_OK) return rc;
+    MAE_REQUIRE(mu_stride >= D && logvar_stride >= D, MAE_ERR_STRIDE);
+    mpd_prepare_kernel<<<(unsigned)L.nblk, kNT, 0, as_stream(stream)>>>(
+        mu, mu_stride, logvar, logvar_stride, (int)B, (int)D, (int)L.Kp, at<float>(workspace, L.xp), at<float>(workspace, L.yp),
+        at<float4>(workspace, L.vp), at<float>(workspace, L.c), at<float>(workspace, L.l), at<double>(workspace, L.part_prep),
+        at<double>(workspace, L.colstats), at<Hdr>(workspace, L.hdr), m_d);
+    return launch_status();
+}
+
+extern "C" int mae_mpd_fwd(void* workspace, int64_t workspace_bytes, int64_t B, int64_t D, int64_t row0, int64_t nrows,
+                           int store_kl, double* sumsq, float* S, mae_stream_t stream) {
+    using namespace mae;
+    MAE_REQUIRE(sumsq, MAE_ERR_NULL);
+    Layout L;
+    int rc = check_common(B, D, workspace, workspace_bytes, L);
+    if (rc != MAE_OK) return rc;
+    MAE_REQUIRE(row0 >= 0 && nrows >= 1 && row0 + nrows <= B, MAE_ERR_SHAPE);
+    if (store_kl) MAE_REQUIRE(B <= MAE_MPD_SMALL_B && row0 == 0 && nrows == B, MAE_ERR_UNSUPPORTED);
+    const int tr0 = (int)(row0 / kT);
+    const int ntr = (int)(ceil_div(row0 + nrows, kT) - tr0);
+    const int ntc = (int)L.nblk;
+    const int64_t ntiles = (int64_t)ntr * ntc;
+    const int grid = (int)(ntiles < kMaxFwdCtas ? ntiles : kMaxFwdCtas);
+    mpd_fwd_kernel<<<grid, kNT, 0, as_stream(stream)>>>(
+        at<float>(workspace, L.xp), at<float>(workspace, L.yp), at<float>(workspace, L.c), at<float>(workspace, L.l),
+        at<Hdr>(workspace, L.hdr), at<double>(workspace, L.part_fwd), (int)B, (int)D, (int)L.Kp, (int)row0, (int)(row0 + nrows),
+        tr0, ntr, ntc, store_kl ? at<float>(workspace, L.kl) : nullptr, store_kl ? at<float>(workspace, L.klt) : nullptr,
+        (int)L.Bp, sumsq, S);
+    return launch_status();
+}
+
+extern "C" int mae_mpd_finalize(const double* sumsq, int64_t B, float* S, mae_stream_t stream) {
+    using namespace mae;
+    MAE_REQUIRE(sumsq && S, MAE_ERR_NULL);
+    MAE_REQUIRE(B >= 2, MAE_ERR_SHAPE);
+    mpd_finalize_kernel<<<1, 1, 0, as_stream(stream)>>>(sumsq, (double)B, S);
+    return launch_status();
+}
+
+extern "C" int mae_mpd_bwd(const float* mu, int64_t mu_stride, const float* logvar, int64_t logvar_stride, void* workspace,
+                           int64_t workspace_bytes, int64_t B, int64_t D, int64_t row0, int64_t nrows, const float* g_m,
+                           const float* g_S, const float* S, float* dmu, float* dlogvar, int accumulate, int path,
+                           mae_stream_t stream) {
+    using namespace mae;
+    (void)mu; (void)mu_stride; (void)logvar; (void)logvar_stride;  // everything needed was packed by mae_mpd_prepare
+    MAE_REQUIRE(dmu && dlogvar, MAE_ERR_NULL);
+    MAE_REQUIRE(g_S == nullptr || S != nullptr, MAE_ERR_NULL);
+    Layout L;
+    int rc = check_common(B, D, workspace, workspace_bytes, L);
+    if (rc != MAE_OK) return rc;
+    MAE_REQUIRE(row0 >= 0 && nrows >= 1 && row0 + nrows <= B, MAE_ERR_SHAPE);
+    MAE_REQUIRE(path >= 0 && path <= 2, MAE_ERR_SHAPE);
+    if (path == 0) path = (B <= MAE_MPD_SMALL_B) ? 1 : 2;
+    if (path == 1) {
+        MAE_REQUIRE(B <= MAE_MPD_SMALL_B, MAE_ERR_UNSUPPORTED);
+        const int64_t warps = nrows * ceil_div(D, 32);
+        const int64_t blocks = ceil_div(warps, kNT / 32);
+        MAE_REQUIRE(blocks < (1ll << 31), MAE_ERR_SHAPE);
+        mpd_bwd_small_kernel<<<(unsigned)blocks, kNT, 0, as_stream(stream)>>>(
+            at<float4>(workspace, L.vp), at<float>(workspace, L.kl), at<float>(workspace, L.klt), (int)L.Bp,
+            at<double>(workspace, L.colstats), at<Hdr>(workspace, L.hdr), g_m, g_S, S, (int)B, (int)D, (int)row0, (int)nrows, dmu,
+            dlogvar, accumulate);
+        return launch_status();
+    }
+    {
+        cudaError_t e = cudaFuncSetAttribute(mpd_bwd_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdSmem));
+        if (e != cudaSuccess) return (int)e;
+    }
+    const int tr0 = (int)(row0 / kT);
+    const int ntr = (int)(ceil_div(row0 + nrows, kT) - tr0);
+    const int nchunks = (int)ceil_div(L.Kp, kOC);
+    MAE_REQUIRE(nchunks <= 65535, MAE_ERR_SHAPE);
+    dim3 grid((unsigned)ntr, (unsigned)nchunks);
+    mpd_bwd_tile_kernel<<<grid, kNT, sizeof(BwdSmem), as_stream(stream)>>>(
+        at<float>(workspace, L.xp), at<float>(workspace, L.yp), at<float>(workspace, L.c), at<float>(workspace, L.l),
+        at<float4>(workspace, L.vp), at<double>(workspace, L.colstats), at<Hdr>(workspace, L.hdr), g_m, g_S, S, (int)B, (int)D,
+        (int)L.Kp, (int)row0, (int)(row0 + nrows), tr0, (int)L.nblk, dmu, dlogvar, accumulate);
+    return launch_status();
+}

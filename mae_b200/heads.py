@@ -1,0 +1,41 @@
+"""The loss / evaluation heads as single calls on synthetic encoder/decoder outputs.
+
+These compose the operators exactly the way ``MAE.loss`` / ``MAE.nll`` do (mae/modules/mae.py:100-140,
+179-216) but take the conv stacks' outputs as arguments, which is what benchmarks and the smoke test need
+(BASELINE.json: the conv stacks stay in PyTorch and are not part of the measured path)."""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import ops
+
+
+def loss_head_binary(mu, logvar, eps, probs, x, eta=0.0, gamma=0.0, free_bits=0.0):
+    """C1/C2: reparam + analytic KL, MPD, Bernoulli likelihood, assembly.  Returns (loss, recon, KL, stats, z)."""
+    z, kl = ops.reparam_kl(mu, logvar, eps)
+    m_d, s = ops.mpd(mu, logvar)
+    err = ops.bernoulli_recon_error(probs, x)
+    loss, stats, recon = ops.assemble_loss(err, kl, m_d, s, eta, gamma, free_bits)
+    return loss, recon, kl, stats, z
+
+
+def loss_head_color(mu, logvar, eps, raw, x, nmix=10, eta=0.0, gamma=0.0, free_bits=0.0):
+    """C3: reparam + analytic KL, MPD, discretized-logistic-mixture likelihood, assembly."""
+    z, kl = ops.reparam_kl(mu, logvar, eps)
+    m_d, s = ops.mpd(mu, logvar)
+    err = ops.dmol_recon_error(raw, x, eps.size(1), nmix)
+    loss, stats, recon = ops.assemble_loss(err, kl, m_d, s, eta, gamma, free_bits)
+    return loss, recon, kl, stats, z
+
+
+def iw_eval_color(raw, x, z, mu, logvar, nmix=10, z_prior_normal: Optional[torch.Tensor] = None,
+                  logdet_prior: Optional[torch.Tensor] = None, logdet_post: Optional[torch.Tensor] = None):
+    """C4: importance-weighted NLL of a batch of images from K posterior samples each.
+    raw [B*K,10*nmix,H,W], x [B,3,H,W], z [B,K,D] -> ((nll_elbo, recon, kl), nll_iw), each [B]."""
+    with torch.no_grad():
+        k = z.size(1)
+        log_gen = ops.dmol_recon_error(raw, x, k, nmix).neg_()
+        zp = z if z_prior_normal is None else z_prior_normal
+        return ops.iw_nll(log_gen, zp, logdet_prior, z, logdet_post, mu, logvar)

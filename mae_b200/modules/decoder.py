@@ -1,0 +1,130 @@
+"""Decoder side of the drop-in: ``Decoder`` interface + registry (mae/modules/decoders/decoder.py:7-101) and the
+two likelihood heads, ``BinaryImageDecoder`` (image_decoders/binary_image_decoder.py) and ``ColorImageDecoder``
+(image_decoders/color_image_decoder.py).  Sub-classes supply the conv stack as ``forward``; the likelihood
+itself runs on the sm_100a kernels."""
+from __future__ import annotations
+
+from typing import Dict, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import ops
+
+
+class Decoder(nn.Module):
+    _registry: Dict[str, type] = dict()
+
+    def z_shape(self) -> Tuple:
+        raise NotImplementedError
+
+    def output_size(self) -> Tuple:
+        raise NotImplementedError
+
+    def initialize(self, x, z, init_scale=1.0):
+        raise NotImplementedError
+
+    def decode(self, z, random_sample):
+        raise NotImplementedError
+
+    def reconstruct_error(self, x, z):
+        raise NotImplementedError
+
+    def log_probability(self, x, z):
+        raise NotImplementedError
+
+    @classmethod
+    def register(cls, name: str):
+        Decoder._registry[name] = cls
+
+    @classmethod
+    def by_name(cls, name: str):
+        return Decoder._registry[name]
+
+    @classmethod
+    def from_params(cls, params: Dict) -> "Decoder":
+        raise NotImplementedError
+
+
+class BinaryImageDecoder(Decoder):
+    """Pixel-wise independent Bernoulli.  ``forward(z)`` of a sub-class returns post-sigmoid probabilities."""
+
+    def __init__(self, nz, ngpu=1):
+        super().__init__()
+        self.nz = nz
+        self.ngpu = ngpu
+
+    def z_shape(self) -> Tuple:
+        return self.nz, 1, 1
+
+    def decode(self, z, random_sample):
+        """Reference: binary_image_decoder.py:52-68."""
+        img_probs = self(z)
+        img = torch.bernoulli(img_probs) if random_sample else torch.ge(img_probs, 0.5).float()
+        return img, img_probs
+
+    def bernoulli_error(self, recon_x, x):
+        """probabilities [B,ns,P] (any trailing shape) and x [B,*] -> [B,ns] on the CUDA kernel."""
+        b, ns = recon_x.size(0), recon_x.size(1)
+        return ops.bernoulli_recon_error(recon_x.reshape(b, ns, -1), x.reshape(b, -1))
+
+    def reconstruct_error(self, x, z):
+        """x [B,*], z [B,ns,*z] -> [B,ns].  Reference: binary_image_decoder.py:71-93."""
+        size = z.size()
+        b, ns = size[:2]
+        recon_x = self(z.view(b * ns, *size[2:])).view(b, ns, -1)
+        return self.bernoulli_error(recon_x, x)
+
+    def log_probability(self, x, z):
+        return self.reconstruct_error(x, z) * -1.
+
+
+class ColorImageDecoder(Decoder):
+    """Discretized mixture of logistics for 3-channel images.  ``forward(x, z)`` of a sub-class returns the raw
+    conv output [N, 10*nmix, H, W]."""
+
+    def __init__(self, nmix, ngpu=1):
+        super().__init__()
+        self.nc = 3
+        self.nmix = nmix
+        self.ngpu = ngpu
+
+    def execute(self, z, x):
+        """Post-processed mixture parameters (used by ``decode``; the likelihood kernel does this itself).
+        Reference: color_image_decoder.py:38-52."""
+        output = self(x, z)
+        nmix, nc = self.nmix, self.nc
+        logit_probs = output[:, :nmix]
+        batch, _, H, W = logit_probs.size()
+        mu = output[:, nmix:(nc + 1) * nmix].view(batch, nmix, nc, H, W)
+        log_scale = output[:, (nc + 1) * nmix:(nc * 2 + 1) * nmix].view(batch, nmix, nc, H, W)
+        coeffs = output[:, (nc * 2 + 1) * nmix:(nc * 2 + 4) * nmix].view(batch, nmix, nc, H, W)
+        return mu, log_scale.clamp(min=-7.), F.log_softmax(logit_probs, dim=1), coeffs.tanh()
+
+    def decode(self, z, random_sample):
+        """Reference: color_image_decoder.py:71-88 + utils.py:127-160 (sampling; not on the hot path)."""
+        mu, log_scale, logit_probs, coeffs = self.execute(z, None)
+        index = logit_probs.argmax(dim=1, keepdim=True).unsqueeze(2).expand(-1, 1, mu.size(2), -1, -1)
+        mu = mu.gather(1, index).squeeze(1)
+        log_scale = log_scale.gather(1, index).squeeze(1)
+        coeffs = coeffs.gather(1, index).squeeze(1)
+        x = mu
+        if random_sample:
+            u = torch.empty_like(mu).uniform_(1e-5, 1 - 1e-5)
+            x = x + log_scale.exp() * (torch.log(u) - torch.log(1.0 - u))
+        x0 = x[:, 0].clamp(min=-1., max=1.)
+        x1 = (x[:, 1] + coeffs[:, 0] * x0).clamp(min=-1., max=1.)
+        x2 = (x[:, 2] + coeffs[:, 1] * x0 + coeffs[:, 2] * x1).clamp(min=-1., max=1.)
+        return torch.stack([x0, x1, x2], dim=1), None
+
+    def reconstruct_error(self, x, z):
+        """x [B,3,H,W] in [-1,1], z [B,ns,*z] -> [B,ns].  Reference: color_image_decoder.py:91-125."""
+        size = z.size()
+        b, ns = size[:2]
+        x_expand = x.repeat_interleave(ns, dim=0) if ns > 1 else x
+        raw = self(x_expand, z.view(b * ns, *size[2:]))
+        return ops.dmol_recon_error(raw, x, ns, self.nmix)
+
+    def log_probability(self, x, z):
+        return self.reconstruct_error(x, z) * -1.

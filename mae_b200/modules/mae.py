@@ -1,0 +1,93 @@
+"""``MAE`` facade: same constructor, methods and return types as mae/modules/mae.py, with the bodies of
+``loss`` (:100-140) and ``nll`` (:179-216) running on the fused kernels."""
+from __future__ import annotations
+
+import json
+import os
+from typing import Dict, Tuple
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import ops
+from .decoder import Decoder
+from .encoder import Encoder
+
+
+class MAE(nn.Module):
+    def __init__(self, encoder: Encoder, decoder: Decoder):
+        super().__init__()
+        if int(np.prod(encoder.z_shape())) != int(np.prod(decoder.z_shape())):
+            raise ValueError('encoder latent z shape %s does not match decoder input shape %s'
+                             % (encoder.z_shape(), decoder.z_shape()))
+        self.encoder = encoder
+        self.decoder = decoder
+
+    def z_shape(self) -> Tuple:
+        return self.encoder.z_shape()
+
+    def sample_from_proir(self, nsamples=1, device=torch.device('cpu')):
+        return self.encoder.sample_from_proir(nsamples, device=device)
+
+    def sample_from_posterior(self, x, nsamples=1):
+        return self.encoder.sample_from_posterior(x, nsamples)
+
+    def encode(self, x, nsamples):
+        return self.encoder.encode(x, nsamples)
+
+    def decode(self, z, random_sample):
+        return self.decoder.decode(z.view(z.size(0), *self.decoder.z_shape()), random_sample)
+
+    def loss(self, x, nsamples, eta=0.0, gamma=0.0, free_bits=0.0):
+        """-> (loss [], recon [B], KL [B], postKL_mean [], postKL_std [], loss_postKL_mean [] | 0., loss_postKL_std [] | 0.)
+
+        Reference: mae/modules/mae.py:100-140.  ``loss`` carries the gradient; the other entries are logging
+        values (the reference's training loops only ``.sum()``/print them)."""
+        z, KL, (m_d, S) = self.encode(x, nsamples)
+        err = self.decoder.reconstruct_error(x, z.view(z.size(0), z.size(1), *self.decoder.z_shape()))
+        loss, stats, recon = ops.assemble_loss(err, KL, m_d, S, eta, gamma, free_bits)
+        loss_mean = stats[1] if eta > 0. else 0.
+        loss_std = stats[2] if gamma > 0. else 0.
+        return loss, recon, KL, stats[0], S.detach(), loss_mean, loss_std
+
+    def reconstruct(self, x, k=50, random_sample=False):
+        z, _ = self.sample_from_posterior(x, nsamples=k)
+        return self.decode(z.mean(dim=1), random_sample=random_sample)
+
+    def initialize(self, x, init_scale=1.0):
+        z = self.encoder.initialize(x, init_scale=init_scale)
+        return self.decoder.initialize(x, z.view(z.size(0), *self.decoder.z_shape()), init_scale=init_scale)
+
+    def nll(self, x, k):
+        """Importance-weighted NLL: -> ((nll_elbo [B], recon [B], kl [B]), nll_iw [B]).
+
+        Reference: mae/modules/mae.py:179-216.  Evaluation-only (the reference calls it under no_grad)."""
+        batch = x.size(0)
+        with torch.no_grad():
+            z, (mu, logvar, z_post_normal, logdet_post) = self.sample_from_posterior(x, nsamples=k)
+            enc = self.encoder
+            prior_flow = getattr(enc, 'prior_flow', None)
+            if prior_flow is None:
+                z_prior_normal, logdet_prior = z, None
+            else:
+                z_prior_normal, logdet_prior = prior_flow.backward(z.view(batch * k, *prior_flow.input_size()))
+            post_flow = getattr(enc, 'posterior_flow', None)
+            log_gen = self.decoder.log_probability(x, z.view(batch, k, *self.decoder.z_shape()))
+            return ops.iw_nll(log_gen, z_prior_normal, logdet_prior, z_post_normal,
+                              logdet_post if post_flow is not None else None, mu, logvar)
+
+    @classmethod
+    def from_params(cls, params: Dict) -> "MAE":
+        encoder_params = params.pop('encoder')
+        encoder = Encoder.by_name(encoder_params.pop('type')).from_params(encoder_params)
+        decoder_params = params.pop('decoder')
+        decoder = Decoder.by_name(decoder_params.pop('type')).from_params(decoder_params)
+        return MAE(encoder, decoder)
+
+    @classmethod
+    def load(cls, model_path, device) -> "MAE":
+        params = json.load(open(os.path.join(model_path, 'config.json'), 'r'))
+        mae = MAE.from_params(params)
+        mae.load_state_dict(torch.load(os.path.join(model_path, 'model.pt'), map_location=device))
+        return mae.to(device)

@@ -1,0 +1,477 @@
+"""Autograd-aware PyTorch operators over the C ABI of libmae_b200.so.
+
+PyTorch is plumbing here (device memory, streams, autograd bookkeeping); all arithmetic of the hot path
+runs in the hand-written sm_100a kernels.  Every op raises on non-CUDA tensors: there is no CPU or eager
+fallback.  Launches go to ``torch.cuda.current_stream()`` so the ops compose with CUDA-graph capture.
+"""
+from __future__ import annotations
+
+import threading
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import _lib
+
+__all__ = [
+    "reparam_kl", "mpd", "mpd_forward_only", "bernoulli_recon_error", "dmol_recon_error", "log_prob_prior",
+    "log_prob_posterior", "iw_nll", "assemble_loss", "launch_count", "reset_launch_count",
+]
+
+_launches = 0  # number of kernels of ours enqueued since the last reset (bench.py reports it)
+
+
+def launch_count() -> int:
+    return _launches
+
+
+def reset_launch_count() -> None:
+    global _launches
+    _launches = 0
+
+
+def _count(n: int = 1) -> None:
+    global _launches
+    _launches += n
+
+
+def _lib_():
+    return _lib.load()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _req_cuda(*tensors: Optional[torch.Tensor]) -> None:
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("mae_b200 ops run on CUDA tensors only (got %s): there is no CPU fallback" % t.device)
+        if t.dtype != torch.float32:
+            raise RuntimeError("mae_b200 ops compute in float32 (got %s)" % t.dtype)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _rows(t: torch.Tensor) -> Tuple[torch.Tensor, int]:
+    """View ``t`` [B,*] as rows of a strided matrix without copying when possible (the reference's mu/logvar
+    are ``chunk(2,1)`` views, encoder_cores/resnet.py:43).  Returns (2-D tensor, row stride in elements)."""
+    b = t.size(0)
+    d = t.numel() // max(b, 1)
+    try:
+        v = t.view(b, d)
+    except RuntimeError:
+        v = t.reshape(b, d)
+    if d > 1 and v.stride(1) != 1:
+        v = v.contiguous()
+    if v.data_ptr() % 4 != 0:
+        v = v.contiguous()
+    stride = v.stride(0) if b > 1 else d
+    if stride < d:
+        v = v.contiguous()
+        stride = d
+    return v, stride
+
+
+# ------------------------------------------------------------------------------------------------
+# workspace pool: zero-filled once (tickets are self-resetting), reused across steps per stream
+# ------------------------------------------------------------------------------------------------
+class _Pool:
+    def __init__(self) -> None:
+        self._free: Dict[tuple, List[torch.Tensor]] = {}
+        self._lock = threading.Lock()
+
+    def take(self, nbytes: int, device: torch.device) -> torch.Tensor:
+        key = (device.index, _stream(), int(nbytes))
+        with self._lock:
+            lst = self._free.get(key)
+            if lst:
+                return lst.pop()
+        return torch.zeros(int(nbytes), dtype=torch.uint8, device=device)
+
+    def give(self, ws: torch.Tensor) -> None:
+        key = (ws.device.index, _stream(), ws.numel())
+        with self._lock:
+            self._free.setdefault(key, []).append(ws)
+
+
+_pool = _Pool()
+
+
+# ------------------------------------------------------------------------------------------------
+# A1 + A2
+# ------------------------------------------------------------------------------------------------
+class _ReparamKL(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mu, logvar, eps, want_kl):
+        ctx.set_materialize_grads(False)
+        _req_cuda(mu, logvar, eps)
+        b, ns = eps.size(0), eps.size(1)
+        mu2, ms = _rows(mu)
+        lv2, ls = _rows(logvar)
+        d = mu2.size(1)
+        eps_c = eps.contiguous()
+        z = torch.empty_like(eps_c)
+        kl = torch.empty(b, device=mu.device, dtype=torch.float32) if want_kl else None
+        _lib.check(_lib_().mae_reparam_kl_fwd(mu2.data_ptr(), ms, lv2.data_ptr(), ls, eps_c.data_ptr(), b, ns, d,
+                                              z.data_ptr(), _ptr(kl), _stream()), "mae_reparam_kl_fwd")
+        _count()
+        ctx.save_for_backward(mu2, lv2, eps_c)
+        ctx.meta = (ms, ls, b, ns, d, mu.shape, logvar.shape)
+        if kl is None:
+            kl = torch.zeros(0, device=mu.device)
+            ctx.mark_non_differentiable(kl)
+        return z, kl
+
+    @staticmethod
+    def backward(ctx, gz, gkl):
+        mu2, lv2, eps_c = ctx.saved_tensors
+        ms, ls, b, ns, d, mu_shape, lv_shape = ctx.meta
+        if gz is None and gkl is None:
+            return None, None, None, None
+        gz = gz.contiguous() if gz is not None else None
+        gkl = gkl.contiguous() if (gkl is not None and gkl.numel() == b) else None
+        dmu = torch.empty(b, d, device=mu2.device, dtype=torch.float32)
+        dlv = torch.empty_like(dmu)
+        _lib.check(_lib_().mae_reparam_kl_bwd(mu2.data_ptr(), ms, lv2.data_ptr(), ls, eps_c.data_ptr(), _ptr(gz), _ptr(gkl),
+                                              b, ns, d, dmu.data_ptr(), dlv.data_ptr(), 0, _stream()), "mae_reparam_kl_bwd")
+        _count()
+        return dmu.view(mu_shape), dlv.view(lv_shape), None, None
+
+
+def reparam_kl(mu: torch.Tensor, logvar: torch.Tensor, eps: torch.Tensor, want_kl: bool = True):
+    """z = eps*exp(0.5*logvar)+mu  [B,ns,*z]  and the analytic KL [B] (or None).
+    Reference: gaussian_encoder.py:56-62 and :219."""
+    z, kl = _ReparamKL.apply(mu, logvar, eps, want_kl)
+    return z, (kl if want_kl else None)
+
+
+# ------------------------------------------------------------------------------------------------
+# A3
+# ------------------------------------------------------------------------------------------------
+def _mpd_launch_fwd(mu2, ms, lv2, ls, b, d, ws, store_kl, row0=0, nrows=None):
+    lib = _lib_()
+    dev = mu2.device
+    m_d = torch.empty(d, device=dev, dtype=torch.float32)
+    sumsq = torch.empty(1, device=dev, dtype=torch.float64)
+    s = torch.empty((), device=dev, dtype=torch.float32)
+    nrows = b if nrows is None else nrows
+    _lib.check(lib.mae_mpd_prepare(mu2.data_ptr(), ms, lv2.data_ptr(), ls, b, d, ws.data_ptr(), ws.numel(), m_d.data_ptr(),
+                                   _stream()), "mae_mpd_prepare")
+    _lib.check(lib.mae_mpd_fwd(ws.data_ptr(), ws.numel(), b, d, row0, nrows, int(store_kl), sumsq.data_ptr(), s.data_ptr(),
+                               _stream()), "mae_mpd_fwd")
+    _count(2)
+    return m_d, s, sumsq
+
+
+class _MPD(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mu, logvar, bwd_path):
+        ctx.set_materialize_grads(False)
+        _req_cuda(mu, logvar)
+        b = mu.size(0)
+        if b < 2:
+            raise RuntimeError("the MPD regulariser needs a batch of at least 2 posteriors (gaussian_encoder.py:181)")
+        mu2, ms = _rows(mu)
+        lv2, ls = _rows(logvar)
+        d = mu2.size(1)
+        lib = _lib_()
+        ws = _pool.take(lib.mae_mpd_workspace_bytes(b, d), mu.device)
+        need_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        small = b <= 2048 and bwd_path != 2
+        m_d, s, _ = _mpd_launch_fwd(mu2, ms, lv2, ls, b, d, ws, store_kl=need_grad and small)
+        if need_grad:
+            ctx.ws = ws
+            ctx.save_for_backward(mu2, lv2, s)
+            ctx.meta = (ms, ls, b, d, mu.shape, logvar.shape, 1 if small else 2)
+        else:
+            _pool.give(ws)
+        return m_d.view(mu.shape[1:]), s
+
+    @staticmethod
+    def backward(ctx, g_m, g_s):
+        mu2, lv2, s = ctx.saved_tensors
+        ms, ls, b, d, mu_shape, lv_shape, path = ctx.meta
+        ws = ctx.ws
+        if g_m is None and g_s is None:
+            ctx.ws = None
+            _pool.give(ws)
+            return None, None, None
+        g_m = g_m.contiguous().view(-1) if g_m is not None else None
+        g_s = g_s.contiguous() if g_s is not None else None
+        dmu = torch.empty(b, d, device=mu2.device, dtype=torch.float32)
+        dlv = torch.empty_like(dmu)
+        _lib.check(_lib_().mae_mpd_bwd(mu2.data_ptr(), ms, lv2.data_ptr(), ls, ws.data_ptr(), ws.numel(), b, d, 0, b,
+                                       _ptr(g_m), _ptr(g_s), s.data_ptr(), dmu.data_ptr(), dlv.data_ptr(), 0, path, _stream()),
+                   "mae_mpd_bwd")
+        _count()
+        ctx.ws = None
+        _pool.give(ws)
+        return dmu.view(mu_shape), dlv.view(lv_shape), None
+
+
+def mpd(mu: torch.Tensor, logvar: torch.Tensor, bwd_path: int = 0):
+    """Mutual posterior divergence: (m_d with the shape of one latent, S scalar).
+    Reference: GaussianEncoder._postKL, gaussian_encoder.py:162-188.  ``bwd_path``: 0 auto, 1 stored-KL, 2 tiles."""
+    return _MPD.apply(mu, logvar, bwd_path)
+
+
+def mpd_forward_only(mu: torch.Tensor, logvar: torch.Tensor, row0: int = 0, nrows: Optional[int] = None):
+    """Forward on a row block: returns (m_d, S_of_block_as_if_complete, sumsq[1] fp64).  For multi-GPU
+    row-blocked evaluation: all-reduce ``sumsq`` and call :func:`mpd_finalize`."""
+    _req_cuda(mu, logvar)
+    mu2, ms = _rows(mu)
+    lv2, ls = _rows(logvar)
+    b, d = mu2.shape
+    ws = _pool.take(_lib_().mae_mpd_workspace_bytes(b, d), mu.device)
+    m_d, s, sumsq = _mpd_launch_fwd(mu2, ms, lv2, ls, b, d, ws, False, row0, nrows)
+    _pool.give(ws)
+    return m_d.view(mu.shape[1:]), s, sumsq
+
+
+def mpd_finalize(sumsq: torch.Tensor, batch: int) -> torch.Tensor:
+    s = torch.empty((), device=sumsq.device, dtype=torch.float32)
+    _lib.check(_lib_().mae_mpd_finalize(sumsq.data_ptr(), batch, s.data_ptr(), _stream()), "mae_mpd_finalize")
+    _count()
+    return s
+
+
+# ------------------------------------------------------------------------------------------------
+# A4a
+# ------------------------------------------------------------------------------------------------
+class _Bernoulli(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, probs, x):
+        _req_cuda(probs, x)
+        b, ns, p = probs.shape
+        probs_c = probs.contiguous()
+        x_c = x.reshape(b, -1).contiguous()
+        if x_c.size(1) != p:
+            raise RuntimeError("x has %d pixels per image, probabilities have %d" % (x_c.size(1), p))
+        err = torch.empty(b, ns, device=probs.device, dtype=torch.float32)
+        _lib.check(_lib_().mae_bernoulli_fwd(probs_c.data_ptr(), x_c.data_ptr(), b, ns, p, err.data_ptr(), _stream()),
+                   "mae_bernoulli_fwd")
+        _count()
+        ctx.save_for_backward(probs_c, x_c)
+        return err
+
+    @staticmethod
+    def backward(ctx, g):
+        probs_c, x_c = ctx.saved_tensors
+        b, ns, p = probs_c.shape
+        g = g.contiguous()
+        d = torch.empty_like(probs_c)
+        _lib.check(_lib_().mae_bernoulli_bwd(probs_c.data_ptr(), x_c.data_ptr(), g.data_ptr(), b, ns, p, d.data_ptr(), _stream()),
+                   "mae_bernoulli_bwd")
+        _count()
+        return d, None
+
+
+def bernoulli_recon_error(probs: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    """probs [B,ns,P] post-sigmoid, x [B,*] -> reconstruction error [B,ns].
+    Reference: binary_image_decoder.py:84-93 / pixelcnn.py:136-139."""
+    return _Bernoulli.apply(probs, x)
+
+
+# ------------------------------------------------------------------------------------------------
+# A4b + A4c
+# ------------------------------------------------------------------------------------------------
+class _Dmol(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, raw, x, ns, nmix):
+        _req_cuda(raw, x)
+        n, ch = raw.size(0), raw.size(1)
+        hw = raw[0, 0].numel()
+        b = x.size(0)
+        if ch != 10 * nmix or n != b * ns or x.size(1) != 3 or x[0, 0].numel() != hw:
+            raise RuntimeError("dmol: raw %s / x %s inconsistent with ns=%d nmix=%d" % (tuple(raw.shape), tuple(x.shape), ns, nmix))
+        raw_c = raw.contiguous()
+        x_c = x.contiguous()
+        lib = _lib_()
+        ws = _pool.take(max(int(lib.mae_dmol_workspace_bytes(n, hw)), 256), raw.device)
+        err = torch.empty(b, ns, device=raw.device, dtype=torch.float32)
+        _lib.check(lib.mae_dmol_fwd(raw_c.data_ptr(), x_c.data_ptr(), b, ns, nmix, hw, err.data_ptr(), ws.data_ptr(), ws.numel(),
+                                    _stream()), "mae_dmol_fwd")
+        _count()
+        _pool.give(ws)
+        ctx.save_for_backward(raw_c, x_c)
+        ctx.meta = (b, ns, nmix, hw)
+        return err
+
+    @staticmethod
+    def backward(ctx, g):
+        raw_c, x_c = ctx.saved_tensors
+        b, ns, nmix, hw = ctx.meta
+        g = g.contiguous()
+        d = torch.empty_like(raw_c)
+        _lib.check(_lib_().mae_dmol_bwd(raw_c.data_ptr(), x_c.data_ptr(), g.data_ptr(), b, ns, nmix, hw, d.data_ptr(), _stream()),
+                   "mae_dmol_bwd")
+        _count()
+        return d, None, None, None
+
+
+def dmol_recon_error(raw: torch.Tensor, x: torch.Tensor, ns: int, nmix: int) -> torch.Tensor:
+    """raw [B*ns,10*nmix,H,W] decoder output, x [B,3,H,W] in [-1,1] -> reconstruction error [B,ns].
+    Reference: color_image_decoder.py:38-52,91-125 + utils.py:61-123."""
+    return _Dmol.apply(raw, x, int(ns), int(nmix))
+
+
+# ------------------------------------------------------------------------------------------------
+# A5 / A6
+# ------------------------------------------------------------------------------------------------
+class _LogPrior(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z, logdet):
+        _req_cuda(z, logdet)
+        n = z.size(0)
+        z_c = z.reshape(n, -1).contiguous()
+        d = z_c.size(1)
+        ld = logdet.contiguous() if logdet is not None else None
+        out = torch.empty(n, device=z.device, dtype=torch.float32)
+        _lib.check(_lib_().mae_log_prob_prior_fwd(z_c.data_ptr(), _ptr(ld), n, d, out.data_ptr(), _stream()),
+                   "mae_log_prob_prior_fwd")
+        _count()
+        ctx.save_for_backward(z_c)
+        ctx.meta = (z.shape, logdet is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (z_c,) = ctx.saved_tensors
+        shape, has_ld = ctx.meta
+        g = g.contiguous()
+        dz = None
+        if ctx.needs_input_grad[0]:
+            dz = torch.empty_like(z_c)
+            _lib.check(_lib_().mae_log_prob_prior_bwd(z_c.data_ptr(), g.data_ptr(), z_c.size(0), z_c.size(1), dz.data_ptr(),
+                                                      _stream()), "mae_log_prob_prior_bwd")
+            _count()
+            dz = dz.view(shape)
+        return dz, (g if has_ld else None)
+
+
+def log_prob_prior(z_normal: torch.Tensor, logdet: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """log N(z_normal; 0, I) + logdet, [N].  Reference: gaussian_encoder.py:256-258."""
+    return _LogPrior.apply(z_normal, logdet)
+
+
+class _LogPosterior(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z, mu, logvar, logdet):
+        _req_cuda(z, mu, logvar, logdet)
+        b, k = z.size(0), z.size(1)
+        z_c = z.reshape(b, k, -1).contiguous()
+        d = z_c.size(2)
+        mu2, ms = _rows(mu)
+        lv2, ls = _rows(logvar)
+        ld = logdet.contiguous() if logdet is not None else None
+        out = torch.empty(b, k, device=z.device, dtype=torch.float32)
+        _lib.check(_lib_().mae_log_prob_posterior_fwd(z_c.data_ptr(), _ptr(ld), mu2.data_ptr(), ms, lv2.data_ptr(), ls, b, k, d,
+                                                      out.data_ptr(), _stream()), "mae_log_prob_posterior_fwd")
+        _count()
+        ctx.save_for_backward(z_c, mu2, lv2)
+        ctx.meta = (ms, ls, z.shape, mu.shape, logvar.shape, logdet is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        z_c, mu2, lv2 = ctx.saved_tensors
+        ms, ls, z_shape, mu_shape, lv_shape, has_ld = ctx.meta
+        b, k, d = z_c.shape
+        g = g.contiguous()
+        dz = torch.empty_like(z_c)
+        dmu = torch.empty(b, d, device=z_c.device, dtype=torch.float32)
+        dlv = torch.empty_like(dmu)
+        _lib.check(_lib_().mae_log_prob_posterior_bwd(z_c.data_ptr(), g.data_ptr(), mu2.data_ptr(), ms, lv2.data_ptr(), ls, b, k, d,
+                                                      dz.data_ptr(), dmu.data_ptr(), dlv.data_ptr(), _stream()),
+                   "mae_log_prob_posterior_bwd")
+        _count()
+        return dz.view(z_shape), dmu.view(mu_shape), dlv.view(lv_shape), (g if has_ld else None)
+
+
+def log_prob_posterior(z_normal: torch.Tensor, mu: torch.Tensor, logvar: torch.Tensor,
+                       logdet: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """log q(z|x) for z_normal [B,K,*z], [B,K].  Reference: gaussian_encoder.py:297-299."""
+    return _LogPosterior.apply(z_normal, mu, logvar, logdet)
+
+
+# ------------------------------------------------------------------------------------------------
+# A5 + A6 + A7 fused (evaluation only: outputs carry no autograd graph, like calc_nll's no_grad use)
+# ------------------------------------------------------------------------------------------------
+@torch.no_grad()
+def iw_nll(log_gen: torch.Tensor, z_prior_normal: torch.Tensor, logdet_prior: Optional[torch.Tensor],
+           z_post_normal: torch.Tensor, logdet_post: Optional[torch.Tensor], mu: torch.Tensor, logvar: torch.Tensor):
+    """Returns ((nll_elbo, recon, kl), nll_iw), each [B].  Reference: mae.py:203-215 + utils.py:23-38."""
+    _req_cuda(log_gen, z_prior_normal, logdet_prior, z_post_normal, logdet_post, mu, logvar)
+    b, k = log_gen.shape
+    zq = z_post_normal.reshape(b, k, -1).contiguous()
+    zp = z_prior_normal.reshape(b, k, -1).contiguous()
+    d = zq.size(2)
+    mu2, ms = _rows(mu)
+    lv2, ls = _rows(logvar)
+    lg = log_gen.contiguous()
+    ldp = logdet_prior.reshape(b, k).contiguous() if logdet_prior is not None else None
+    ldq = logdet_post.reshape(b, k).contiguous() if logdet_post is not None else None
+    out = torch.empty(4, b, device=lg.device, dtype=torch.float32)
+    _lib.check(_lib_().mae_iw_nll(lg.data_ptr(), zp.data_ptr(), _ptr(ldp), zq.data_ptr(), _ptr(ldq), mu2.data_ptr(), ms,
+                                  lv2.data_ptr(), ls, b, k, d, out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(),
+                                  out[3].data_ptr(), _stream()), "mae_iw_nll")
+    _count()
+    return (out[0], out[1], out[2]), out[3]
+
+
+# ------------------------------------------------------------------------------------------------
+# A3' + A8
+# ------------------------------------------------------------------------------------------------
+class _Assemble(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, err, kl, m_d, s, eta, gamma, free_bits, inv_batch):
+        ctx.set_materialize_grads(False)
+        _req_cuda(err, kl, m_d, s)
+        b, ns = err.shape
+        err_c, kl_c = err.contiguous(), kl.contiguous()
+        m_c = m_d.contiguous().view(-1) if m_d is not None else None
+        d = m_c.numel() if m_c is not None else 0
+        scalars = torch.empty(6, device=err.device, dtype=torch.float32)
+        recon = torch.empty(b, device=err.device, dtype=torch.float32)
+        _lib.check(_lib_().mae_loss_assemble_fwd(err_c.data_ptr(), kl_c.data_ptr(), _ptr(m_c), _ptr(s), b, ns, d, eta, gamma,
+                                                 free_bits, inv_batch, scalars.data_ptr(), recon.data_ptr(), _stream()),
+                   "mae_loss_assemble_fwd")
+        _count()
+        ctx.save_for_backward(scalars, m_c if m_c is not None else scalars)
+        ctx.meta = (b, ns, d, eta, gamma, free_bits, inv_batch, m_d.shape if m_d is not None else None, s is not None)
+        loss = scalars[0]
+        stats = scalars[1:]
+        ctx.mark_non_differentiable(stats, recon)
+        return loss, stats, recon
+
+    @staticmethod
+    def backward(ctx, gloss, _gstats, _grecon):
+        scalars, m_c = ctx.saved_tensors
+        b, ns, d, eta, gamma, free_bits, inv_batch, m_shape, has_s = ctx.meta
+        dev = scalars.device
+        if gloss is None:
+            return (None,) * 8
+        gloss = gloss.contiguous()
+        derr = torch.empty(b, ns, device=dev, dtype=torch.float32)
+        dkl = torch.empty(b, device=dev, dtype=torch.float32)
+        dm = torch.empty(d, device=dev, dtype=torch.float32) if m_shape is not None else None
+        ds = torch.empty((), device=dev, dtype=torch.float32) if has_s else None
+        _lib.check(_lib_().mae_loss_assemble_bwd(gloss.data_ptr(), scalars.data_ptr(), _ptr(m_c) if m_shape is not None else None,
+                                                 b, ns, d, eta, gamma, free_bits, inv_batch, derr.data_ptr(), dkl.data_ptr(),
+                                                 _ptr(dm), _ptr(ds), _stream()), "mae_loss_assemble_bwd")
+        _count()
+        return derr, dkl, (dm.view(m_shape) if dm is not None else None), ds, None, None, None, None
+
+
+def assemble_loss(err: torch.Tensor, kl: torch.Tensor, m_d: Optional[torch.Tensor], s: Optional[torch.Tensor],
+                  eta: float = 0.0, gamma: float = 0.0, free_bits: float = 0.0, inv_batch: float = 0.0):
+    """Objective of MAE.loss (mae.py:132-140) in one launch.
+
+    Returns (loss [], stats [5] = (postKL_mean, loss_postKL_mean, loss_postKL_std, mean KL, mean recon), recon [B]).
+    Only ``loss`` carries a gradient; ``stats`` and ``recon`` are logging outputs."""
+    return _Assemble.apply(err, kl, m_d, s, float(eta), float(gamma), float(free_bits), float(inv_batch))

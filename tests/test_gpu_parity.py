@@ -1,0 +1,393 @@
+"""Parity of the CUDA path (through the C ABI, via mae_b200.ops / mae_b200.modules) against
+
+  * the committed golden fixtures generated from the live reference (tests/golden/*.pt), and
+  * the CPU oracle (oracle/mae_oracle.py) on seeded inputs at sizes it finishes in seconds, and
+  * size-independent properties at BASELINE.json's full sizes.
+
+Tolerances (tests/tolerance.py): 1e-5 relative to the tensor scale for loss terms and gradients, with the
+fp64-anchored escape max(1e-5*scale, 4*|ref32-ref64|); 1e-4 bits/dim for the evaluation NLL.
+Run on the B200 box:  python -m pytest tests -m gpu -q
+"""
+import math
+
+import pytest
+import torch
+
+from tolerance import check_bpd, check_close
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from mae_b200 import _lib, ops as _ops
+    _lib.load()
+    return _ops
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import mae_oracle
+    torch.set_num_threads(max(1, torch.get_num_threads()))
+    return mae_oracle
+
+
+def cu(t):
+    return t.to(DEV)
+
+
+# ---------------------------------------------------------------------------------------------- A1 + A2
+def test_reparam_kl_golden(ops, golden):
+    for name, c in golden("reparam_kl").items():
+        mu, lv = cu(c["mu"]).requires_grad_(), cu(c["logvar"]).requires_grad_()
+        z, kl = ops.reparam_kl(mu, lv, cu(c["eps"]))
+        ((z * cu(c["gz"])).sum() + (kl * cu(c["gKL"])).sum()).backward()
+        r64, r32 = c["ref64"], c["ref32"]
+        check_close(z, r64["z"], r32["z"], what=name + " z")
+        check_close(kl, r64["KL"], r32["KL"], what=name + " KL")
+        check_close(mu.grad, r64["dmu"], r32["dmu"], what=name + " dmu")
+        check_close(lv.grad, r64["dlogvar"], r32["dlogvar"], what=name + " dlogvar")
+
+
+def test_reparam_strided_chunk_views(ops, O):
+    torch.manual_seed(1)
+    out = torch.randn(37, 2 * 24, device=DEV, requires_grad=True)
+    mu, lv = out.chunk(2, 1)                      # row stride 48, like encoder_cores/resnet.py:43
+    eps = torch.randn(37, 3, 24, device=DEV)
+    z, kl = ops.reparam_kl(mu, lv, eps)
+    (z.sum() * 0.3 + kl.sum()).backward()
+    o = out.detach().double().cpu().requires_grad_()
+    m, l = o.chunk(2, 1)
+    zr = O.reparameterize(m, l, eps.double().cpu())
+    (zr.sum() * 0.3 + O.analytic_kl(m, l).sum()).backward()
+    check_close(z, zr, what="z")
+    check_close(out.grad, o.grad, what="grad through chunk views")
+
+
+# ---------------------------------------------------------------------------------------------------- A3
+@pytest.mark.parametrize("path", [1, 2])
+def test_mpd_golden(ops, golden, path):
+    for name, c in golden("mpd").items():
+        mu, lv = cu(c["mu"]).requires_grad_(), cu(c["logvar"]).requires_grad_()
+        m_d, s = ops.mpd(mu, lv, bwd_path=path)
+        r64, r32 = c["ref64"], c["ref32"]
+        assert m_d.shape == r64["m_d"].shape, name
+        check_close(m_d, r64["m_d"], r32["m_d"], what="%s m_d" % name)
+        check_close(s, r64["S"], r32["S"], what="%s S" % name)
+        loss = -c["eta"] * torch.nn.functional.logsigmoid(m_d).sum() + c["gamma"] * s
+        loss.backward()
+        check_close(mu.grad, r64["dmu"], r32.get("dmu"), what="%s dmu (path %d)" % (name, path))
+        check_close(lv.grad, r64["dlogvar"], r32.get("dlogvar"), what="%s dlogvar (path %d)" % (name, path))
+
+
+def test_mpd_partial_upstream_grads(ops, O):
+    """only g_S, only g_m, and a non-uniform g_m"""
+    torch.manual_seed(3)
+    mu0, lv0 = torch.randn(21, 13), torch.randn(21, 13)
+    w = torch.randn(13)
+    for mode in ("S", "m", "both"):
+        for path in (1, 2):
+            mu, lv = cu(mu0).requires_grad_(), cu(lv0).requires_grad_()
+            m_d, s = ops.mpd(mu, lv, bwd_path=path)
+            f = {"S": lambda m, s_: 2.0 * s_, "m": lambda m, s_: (m * w.to(m)).sum(),
+                 "both": lambda m, s_: (m * w.to(m)).sum() - 0.5 * s_}[mode]
+            f(m_d, s).backward()
+            a, b = mu0.double().requires_grad_(), lv0.double().requires_grad_()
+            mr, sr = O.post_kl(a, b)
+            f(mr, sr).backward()
+            check_close(mu.grad, a.grad, what="dmu %s path %d" % (mode, path))
+            check_close(lv.grad, b.grad, what="dlv %s path %d" % (mode, path))
+
+
+def test_mpd_tile_backward_multi_chunk(ops, O):
+    """D > 64 -> several K chunks per row block; B not a multiple of the tile; strided inputs."""
+    torch.manual_seed(4)
+    out = torch.randn(150, 2 * 70)
+    g = torch.randn(70)
+    o_gpu = cu(out).requires_grad_()
+    mu, lv = o_gpu.chunk(2, 1)
+    m_d, s = ops.mpd(mu, lv, bwd_path=2)
+    ((m_d * cu(g)).sum() + 0.7 * s).backward()
+    o = out.double().requires_grad_()
+    a, b = o.chunk(2, 1)
+    mr, sr = O.post_kl(a, b)
+    ((mr * g.double()).sum() + 0.7 * sr).backward()
+    check_close(m_d, mr, what="m_d")
+    check_close(s, sr, what="S")
+    check_close(o_gpu.grad, o.grad, what="grad (tile path, 3 chunks)")
+
+
+def test_mpd_large_vs_chunked_oracle(ops, O):
+    from mae_b200 import synth
+    mu, lv = synth.posterior_params(3000, (32,), seed=11)
+    m_ref, s_ref = O.post_kl_chunked(mu, lv, rows_per_chunk=100)
+    m_d, s = ops.mpd(cu(mu), cu(lv))
+    check_close(m_d, m_ref, what="m_d B=3000")
+    check_close(s, s_ref, what="S B=3000")
+
+
+def test_mpd_row_blocks_add_up_and_deterministic(ops):
+    """sum of row-block partial sums == full sum (the multi-GPU decomposition); bitwise repeatability."""
+    from mae_b200 import synth
+    mu, lv = synth.posterior_params(1000, (64,), seed=12)
+    mu, lv = cu(mu), cu(lv)
+    m_full, s_full, ss_full = ops.mpd_forward_only(mu, lv)
+    parts = []
+    for r0, n in ((0, 125), (125, 125), (250, 250), (500, 499), (999, 1)):
+        m_p, _, ss = ops.mpd_forward_only(mu, lv, r0, n)
+        assert torch.equal(m_p, m_full)
+        parts.append(ss)
+    tot = torch.stack(parts).sum()
+    assert abs(float(tot) - float(ss_full)) <= 1e-9 * abs(float(ss_full))
+    s2 = ops.mpd_finalize(tot.reshape(1), 1000)
+    check_close(s2, s_full, rel=1e-6, what="S from row blocks")
+    m2, s_again, ss2 = ops.mpd_forward_only(mu, lv)
+    assert torch.equal(ss2, ss_full) and torch.equal(s_again, s_full)
+
+
+def test_mpd_full_size_properties(ops):
+    """BASELINE C5 size (B=16384, D=64; the [B,B,D] tensor would be 69 GB): permutation and translation
+    invariance of (m_d, S), and gradients summing to zero along the batch for mu (translation invariance)."""
+    from mae_b200 import synth
+    mu, lv = synth.posterior_params(16384, (64,), seed=13)
+    mu, lv = cu(mu), cu(lv)
+    m1, s1, _ = ops.mpd_forward_only(mu, lv)
+    perm = torch.randperm(16384, device=DEV, generator=torch.Generator(DEV).manual_seed(5))
+    m2, s2, _ = ops.mpd_forward_only(mu[perm], lv[perm])
+    check_close(m2, m1, rel=2e-6, what="m_d permutation")
+    check_close(s2, s1, rel=2e-6, what="S permutation")
+    m3, s3, _ = ops.mpd_forward_only(mu + 3.0, lv)
+    check_close(m3, m1, rel=1e-5, what="m_d translation")
+    check_close(s3, s1, rel=1e-5, what="S translation")
+
+
+def test_mpd_backward_translation_property_tile_path(ops):
+    from mae_b200 import synth
+    mu, lv = synth.posterior_params(2500, (64,), seed=14)   # > 2048 -> recompute-tile path automatically
+    mu, lv = cu(mu).requires_grad_(), cu(lv).requires_grad_()
+    m_d, s = ops.mpd(mu, lv)
+    (torch.nn.functional.logsigmoid(m_d).sum() * -1.0 + s).backward()
+    col = mu.grad.sum(dim=0)                                  # d/d(common shift) == 0
+    assert float(col.abs().max()) <= 1e-4 * float(mu.grad.abs().sum(dim=0).max())
+    # and the two backward paths agree on a sub-problem that both can run
+    mu_s, lv_s = mu.detach()[:700].clone().requires_grad_(), lv.detach()[:700].clone().requires_grad_()
+    g = {}
+    for path in (1, 2):
+        mu_s.grad = lv_s.grad = None
+        m_d, s = ops.mpd(mu_s, lv_s, bwd_path=path)
+        (torch.nn.functional.logsigmoid(m_d).sum() * -1.0 + s).backward()
+        g[path] = (mu_s.grad.clone(), lv_s.grad.clone())
+    check_close(g[2][0], g[1][0].double(), rel=2e-5, what="dmu path2 vs path1")
+    check_close(g[2][1], g[1][1].double(), rel=2e-5, what="dlv path2 vs path1")
+
+
+def test_mpd_rejects_batch_of_one(ops):
+    with pytest.raises(RuntimeError, match="at least 2"):
+        ops.mpd(torch.zeros(1, 4, device=DEV), torch.zeros(1, 4, device=DEV))
+
+
+# --------------------------------------------------------------------------------------------------- A4a
+def test_bernoulli_golden(ops, golden):
+    for name, c in golden("bernoulli").items():
+        pr = cu(c["probs"]).requires_grad_()
+        err = ops.bernoulli_recon_error(pr, cu(c["x"]))
+        (err * cu(c["g"])).sum().backward()
+        check_close(err, c["ref64"]["err"], c["ref32"]["err"], what=name + " err")
+        check_close(pr.grad, c["ref64"]["dprobs"], c["ref32"]["dprobs"], what=name + " dprobs")
+
+
+def test_bernoulli_nll_eval_shape(ops, O):
+    """[1,4096,784]: the shape calc_nll drives (experiments/binary_image.py:49,271)."""
+    from mae_b200 import synth
+    d = synth.binary_head(1, 4096, 784, seed=21)
+    err = ops.bernoulli_recon_error(cu(d["probs"]), cu(d["x"]))
+    ref = O.bernoulli_recon_error(d["probs"].double(), d["x"].double())
+    check_close(err, ref, what="bernoulli K=4096")
+
+
+# --------------------------------------------------------------------------------------------- A4b + A4c
+def test_dmol_golden(ops, golden):
+    for name, c in golden("dmol").items():
+        raw = cu(c["raw"]).requires_grad_()
+        err = ops.dmol_recon_error(raw, cu(c["x"]), c["ns"], c["nmix"])
+        (err * cu(c["g"])).sum().backward()
+        check_close(err, c["ref64"]["err"], c["ref32"]["err"], what=name + " err")
+        check_close(raw.grad, c["ref64"]["draw"], c["ref32"]["draw"], what=name + " draw")
+
+
+def test_dmol_c3_full_size_digest(ops, golden):
+    from mae_b200 import synth
+    d = golden("dmol_c3_digest")
+    inp = synth.color_head(64, 1, 10, 32, 32, seed=int(d["seed"]))
+    assert float(inp["raw"].double().sum()) == float(d["input_checksum"])
+    raw = cu(inp["raw"]).requires_grad_()
+    err = ops.dmol_recon_error(raw, cu(inp["x"]), 1, 10)
+    (err / 64.0).sum().backward()
+    check_close(err, d["err64"], d["err32"], what="C3 err")
+    g = raw.grad
+    sc = float(d["draw64_abs_sum"]) / g.numel()          # mean |grad|
+    check_close(g.double().sum(dim=(0, 2, 3)), d["draw64_channel_sums"], rel=1e-5, floor=1e-5 * sc * 64 * 1024 ** 0.5,
+                what="C3 per-channel gradient sums")
+    got = torch.stack([g[:, :, int(h), int(w)] for h, w in d["pixels"]], dim=0)
+    check_close(got, d["draw64_pixels"], d["draw32_pixels"], what="C3 gradient pixels")
+    # deterministic
+    err2 = ops.dmol_recon_error(raw.detach(), cu(inp["x"]), 1, 10)
+    assert torch.equal(err2, err.detach())
+
+
+def test_dmol_iw_shape_vs_oracle(ops, O):
+    """one C4 image: K=512 samples of [100,32,32] (209.7 MB) against the CPU oracle in fp64 (a few seconds)."""
+    from mae_b200 import synth
+    inp = synth.color_head(1, 512, 10, 32, 32, seed=31)
+    err = ops.dmol_recon_error(cu(inp["raw"]), cu(inp["x"]), 512, 10)
+    ref = O.dmol_recon_error(inp["raw"].double(), inp["x"].double(), 512, 10)
+    check_close(err, ref, what="dmol K=512")
+    check_bpd(err, ref, 3072, what="dmol K=512 bits/dim")
+
+
+def test_dmol_shape_errors(ops):
+    with pytest.raises(RuntimeError, match="inconsistent"):
+        ops.dmol_recon_error(torch.zeros(2, 99, 4, 4, device=DEV), torch.zeros(2, 3, 4, 4, device=DEV), 1, 10)
+
+
+# ------------------------------------------------------------------------------------------- A5, A6, A7
+def test_log_probs_and_iw_golden(ops, golden):
+    for name, c in golden("iw").items():
+        r64, r32 = c["ref64"], c["ref32"]
+        zn = cu(c["z_normal"])
+        b, k = zn.shape[:2]
+        lp0 = ops.log_prob_prior(zn.reshape(b * k, *zn.shape[2:]))
+        lp1 = ops.log_prob_prior(cu(c["z_prior_normal"]), cu(c["logdet_prior"]))
+        lq = ops.log_prob_posterior(zn, cu(c["mu"]), cu(c["logvar"]), cu(c["logdet_post"]))
+        check_close(lp0, r32["log_prior_noflow"].double(), rel=1e-5, what=name + " log prior")
+        check_close(lp1, r64["log_prior_flow"], r32["log_prior_flow"], what=name + " log prior (flow)")
+        check_close(lq, r32["log_post"].double(), rel=1e-5, what=name + " log posterior")
+        (e, r, kl), iw = ops.iw_nll(cu(c["log_gen"]), cu(c["z_prior_normal"]).view(b, k, -1), cu(c["logdet_prior"]).view(b, k),
+                                    zn, cu(c["logdet_post"]), cu(c["mu"]), cu(c["logvar"]))
+        # reference fp32 chain as the anchor (its z_normal is the fp32 tensor we feed)
+        for got, key in ((e, "nll_elbo"), (r, "recon"), (kl, "kl"), (iw, "nll_iw")):
+            check_close(got, r32[key].double(), rel=1e-5, floor=2e-3 if key == "kl" else 0.0, what="%s %s" % (name, key))
+
+
+def test_log_prob_gradients(ops, O):
+    torch.manual_seed(7)
+    b, k, d = 6, 5, 9
+    z0, mu0, lv0 = torch.randn(b, k, d), torch.randn(b, d), torch.randn(b, d)
+    ld0, g = torch.randn(b, k), torch.randn(b, k)
+    z, mu, lv, ld = (cu(t).requires_grad_() for t in (z0, mu0, lv0, ld0))
+    (ops.log_prob_posterior(z, mu, lv, ld) * cu(g)).sum().backward()
+    zr, mr, lr, ldr = (t.double().requires_grad_() for t in (z0, mu0, lv0, ld0))
+    (O.log_prob_posterior(zr, mr, lr, ldr) * g.double()).sum().backward()
+    for got, ref, n in ((z, zr, "dz"), (mu, mr, "dmu"), (lv, lr, "dlv"), (ld, ldr, "dlogdet")):
+        check_close(got.grad, ref.grad, what="posterior " + n)
+    zp = cu(z0.reshape(b * k, d)).requires_grad_()
+    ldp = cu(ld0.reshape(-1)).requires_grad_()
+    (ops.log_prob_prior(zp, ldp) * cu(g.reshape(-1))).sum().backward()
+    zpr = z0.reshape(b * k, d).double().requires_grad_()
+    (O.log_prob_prior(zpr, ld0.reshape(-1).double()) * g.reshape(-1).double()).sum().backward()
+    check_close(zp.grad, zpr.grad, what="prior dz")
+    check_close(ldp.grad, g.reshape(-1), what="prior dlogdet")
+
+
+def test_iw_eval_color_end_to_end(ops, O):
+    """C4 head for 2 images x K=64 on 16x16: DMOL fwd + fused IW kernel vs oracle; bits/dim tolerance."""
+    from mae_b200 import synth
+    b, k, d = 2, 64, 64
+    inp = synth.color_head(b, k, 10, 16, 16, seed=41)
+    mu, lv = synth.posterior_params(b, (d,), seed=42, clamp=True)
+    z = O.reparameterize(mu, lv, synth.noise(b, k, (d,), seed=43))
+    log_gen = -ops.dmol_recon_error(cu(inp["raw"]), cu(inp["x"]), k, 10)
+    (e, r, kl), iw = ops.iw_nll(log_gen, cu(z), None, cu(z), None, cu(mu), cu(lv))
+    (e_r, r_r, kl_r), iw_r = O.iw_eval_color(inp["raw"].double(), inp["x"].double(), z.double(), mu.double(), lv.double(), 10)
+    nx = 3 * 16 * 16
+    for got, ref, n in ((e, e_r, "elbo"), (r, r_r, "recon"), (iw, iw_r, "iw")):
+        check_close(got, ref, what="C4 " + n)
+        check_bpd(got, ref, nx, what="C4 bits/dim " + n)
+    check_close(kl, kl_r, rel=1e-5, what="C4 kl")
+
+
+# ---------------------------------------------------------------------------------------------- A3' + A8
+@pytest.mark.parametrize("eta,gamma,free_bits", [(1.0, 1.0, 0.0), (0.0, 0.0, 0.0), (2.0, 0.0, 1e6), (0.0, 0.5, 3.0)])
+def test_assemble_loss(ops, O, eta, gamma, free_bits):
+    torch.manual_seed(9)
+    b, ns, d = 37, 3, 20
+    err0, kl0, m0, s0 = torch.rand(b, ns) * 100, torch.rand(b) * 5, torch.randn(d) * 3, torch.rand(()) * 10
+    err, kl, m, s = (cu(t).requires_grad_() for t in (err0, kl0, m0, s0))
+    loss, stats, recon = ops.assemble_loss(err, kl, m, s, eta, gamma, free_bits)
+    (loss * 1.7).backward()
+    er, kr, mr, sr = (t.double().requires_grad_() for t in (err0, kl0, m0, s0))
+    ref = O.assemble_loss(er, kr, mr, sr, eta, gamma, free_bits)
+    (ref[0] * 1.7).backward()
+    check_close(loss, ref[0], what="loss")
+    check_close(recon, ref[1], what="recon")
+    check_close(stats[0], ref[3], what="postKL_mean")
+    check_close(stats[1], torch.as_tensor(ref[5]), what="loss_postKL_mean", floor=1e-12)
+    check_close(stats[2], torch.as_tensor(ref[6]), what="loss_postKL_std", floor=1e-12)
+    zero = lambda t: torch.zeros_like(t) if t.grad is None else t.grad
+    check_close(err.grad, zero(er), what="derr")
+    check_close(kl.grad, zero(kr), what="dkl", floor=1e-12)
+    check_close(zero(m), zero(mr), what="dm_d", floor=1e-12)
+    check_close(zero(s), zero(sr), what="dS", floor=1e-12)
+
+
+# --------------------------------------------------------------------------------- drop-in: whole MAE
+def _build(case, name):
+    import stubs
+    from mae_b200.modules import MAE, GaussianEncoder
+    if name.startswith("binary"):
+        flow = stubs.AffineFlow(case["nz"]) if "priorflow" in name else None
+        enc = GaussianEncoder(stubs.LinearCore(case["npix"], case["nz"], False), prior_flow=flow)
+        dec = stubs.BinaryLinearDecoder(case["nz"], case["npix"])
+    else:
+        enc = GaussianEncoder(stubs.LinearCore(3 * case["h"] * case["w"], case["nz"], True))
+        dec = stubs.ColorLinearDecoder(case["nz"], case["nmix"], case["h"], case["w"])
+    mae = MAE(enc, dec)
+    mae.load_state_dict(case["state"])
+    return mae.to(DEV)
+
+
+def test_mae_dropin_matches_reference_mae(golden, monkeypatch):
+    """Same 7-tuple, parameter gradients and IW-NLL as the reference's MAE driven with identical stand-in conv
+    stacks, weights, inputs and noise (tests/golden/make_golden.py::golden_mae)."""
+    from mae_b200.modules import GaussianEncoder
+    for name, c in golden("mae_stub").items():
+        mae = _build(c, name)
+        x = cu(c["x"])
+        r64, r32 = c["ref64"], c["ref32"]
+        monkeypatch.setattr(GaussianEncoder, "_draw_eps", staticmethod(lambda mu, ns, e=c["eps_loss"]: cu(e)))
+        out = mae.loss(x, c["ns"], eta=c["eta"], gamma=c["gamma"], free_bits=c["free_bits"])
+        assert len(out) == 7
+        out[0].backward()
+        for i, key in enumerate(["loss", "recon", "KL", "postKL_mean", "postKL_std", "loss_mean", "loss_std"]):
+            if not torch.is_tensor(out[i]):
+                assert out[i] == 0.0 and float(r64["loss7"][i]) == 0.0, "%s %s" % (name, key)   # mae.py:134-135
+                continue
+            check_close(out[i], r64["loss7"][i], r32["loss7"][i], what="%s %s" % (name, key))
+        for pname, p in mae.named_parameters():
+            check_close(p.grad, r64["grads"][pname], r32["grads"][pname], what="%s grad %s" % (name, pname))
+        monkeypatch.setattr(GaussianEncoder, "_draw_eps", staticmethod(lambda mu, ns, e=c["eps_nll"]: cu(e)))
+        (e, r, kl), iw = mae.nll(x, c["k"])
+        nx = c["x"][0].numel()
+        for got, key in ((e, "nll_elbo"), (r, "nll_recon"), (iw, "nll_iw")):
+            check_close(got, r64[key], r32[key], what="%s %s" % (name, key))
+            check_bpd(got, r64[key], nx, what="%s %s bits/dim" % (name, key))
+        check_close(kl, r64["nll_kl"], r32["nll_kl"], what="%s nll kl" % name, floor=1e-4)
+
+
+def test_sampling_api_shapes():
+    import stubs
+    from mae_b200.modules import MAE, GaussianEncoder
+    torch.manual_seed(0)
+    mae = MAE(GaussianEncoder(stubs.LinearCore(48, 6, True)), stubs.ColorLinearDecoder(6, 3, 4, 4)).to(DEV)
+    x = torch.rand(5, 3, 4, 4, device=DEV) * 2 - 1
+    z, (mu, lv, zn, ld) = mae.sample_from_posterior(x, 4)
+    assert z.shape == (5, 4, 6) and ld.shape == (5, 4) and mu.shape == (5, 6)
+    zp, _ = mae.sample_from_proir(7, device=torch.device(DEV))
+    img, _ = mae.decode(zp, random_sample=True)
+    assert img.shape == (7, 3, 4, 4) and float(img.abs().max()) <= 1.0
+    rec, _ = mae.reconstruct(x, k=3)
+    assert rec.shape == (5, 3, 4, 4)
+    z2, kl, (m_d, s) = mae.encode(x, 2)
+    assert z2.shape == (5, 2, 6) and kl.shape == (5,) and m_d.shape == (6,) and s.dim() == 0
