@@ -1,0 +1,507 @@
+#!/usr/bin/env python
+"""Benchmark of the MAE loss-and-evaluation hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c1|c4|c5]
+
+Default workload (N=1):  C3 = BASELINE.json configs[2], "CIFAR-10 32x32x3, discretized logistic mixture (10 comps)
+decoder, latent 64, batch 64, full MAE loss fwd+bwd" — the loss-head configuration with a real HBM roofline
+(configs[1], OMNIGLOT, is 1.6 MB / 10 MFLOP per step and purely launch-latency-bound; it is reported under
+"workloads" together with C4 = IW-NLL eval and C5 = MPD microbench).  One step = reparam+KL, MPD, DMOL likelihood,
+objective assembly, forward AND backward, on synthetic encoder/decoder outputs (the conv stacks stay in PyTorch
+and are not part of the measured path).  Prints ONE JSON line on rank 0.
+
+Timing rules followed: >= 3 warm-up steps; a ring of input slabs larger than L2 is cycled so every step reads
+from HBM; CUDA events on the launching stream; max over ranks; nvidia-smi clocks sampled during the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+ETA, GAMMA, FREE_BITS = 1.0, 1.0, 0.0
+L2_BYTES = 126e6
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+# ----------------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples nvidia-smi SM clocks / throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------- synthetic inputs
+def c3_host_inputs(slab: int, batch=64, latent=64):
+    """One slab of C3 inputs on the host (pinned): encoder outputs, noise, decoder output, images."""
+    from mae_b200 import synth
+    seed = synth.SEED + 1000 * slab
+    mu, lv = synth.posterior_params(batch, (latent,), seed=seed, clamp=True)
+    enc = torch.cat([mu, lv], dim=1)                       # [B, 2D]: mu/logvar are chunk views of it
+    eps = synth.noise(batch, 1, (latent,), seed=seed)
+    head = synth.color_head(batch, 1, 10, 32, 32, seed=seed)
+    return {k: v.contiguous().pin_memory() if torch.cuda.is_available() else v
+            for k, v in dict(enc=enc, eps=eps, raw=head["raw"], x=head["x"]).items()}
+
+
+def c3_bytes(batch=64, ns=1, nmix=10, hw=1024):
+    fwd = 4 * (10 * nmix * hw * batch * ns + 3 * hw * batch + batch * ns)
+    bwd = 4 * (2 * 10 * nmix * hw * batch * ns + 3 * hw * batch + batch * ns)
+    return fwd, bwd
+
+
+# -------------------------------------------------------------------------------------------------- our arm
+class C3Step:
+    """One slab's fwd+bwd of the colour loss head, captured into a CUDA graph."""
+
+    def __init__(self, host, dev, dist_ctx=None):
+        from mae_b200 import heads
+        self.heads = heads
+        self.dist = dist_ctx
+        self.enc = host["enc"].to(dev).requires_grad_()
+        self.eps = host["eps"].to(dev)
+        self.raw = host["raw"].to(dev).requires_grad_()
+        self.x = host["x"].to(dev)
+        self.graph = None
+        self.loss = None
+        self.launches = 0
+
+    def eager(self):
+        from mae_b200 import ops
+        self.enc.grad = None
+        self.raw.grad = None
+        mu, lv = self.enc.chunk(2, 1)
+        if self.dist is None:
+            loss, recon, kl, stats, z = self.heads.loss_head_color(mu, lv, self.eps, self.raw, self.x, 10, ETA, GAMMA, FREE_BITS)
+        else:
+            loss, recon, kl, stats, z = self.dist.loss_head_color(mu, lv, self.eps, self.raw, self.x, 10, ETA, GAMMA, FREE_BITS)
+        loss.backward()
+        return loss
+
+    def capture(self):
+        from mae_b200 import ops
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(3):
+                self.eager()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        ops.reset_launch_count()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = self.eager()
+        self.launches = ops.launch_count()
+
+    def run(self):
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self.loss = self.eager()
+        return self.loss
+
+
+def time_kernel(fn, n_iter, stream):
+    """average device time of fn() over n_iter back-to-back launches, CUDA events on the launching stream"""
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for i in range(3):
+        fn(i)
+    torch.cuda.synchronize()
+    e0.record(stream)
+    for i in range(n_iter):
+        fn(i)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n_iter * 1e-3
+
+
+def bench_ours(args):
+    import torch.distributed as dist
+    from mae_b200 import _lib, ops
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    _lib.load()
+    dist_ctx = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        from mae_b200.distributed import ShardedHead
+        dist_ctx = ShardedHead()
+    hbm_gbs, peak_src = measured_peaks()
+    batch, latent = 64, 64
+    fwd_b, bwd_b = c3_bytes(batch)
+    step_bytes = fwd_b + bwd_b
+    ring = max(4, int(L2_BYTES * 3 / step_bytes) + 1)                     # > 3x L2 of distinct data in flight
+    hosts = [c3_host_inputs(i + 17 * rank, batch, latent) for i in range(min(ring, 4))]
+    steps_obj = []
+    for i in range(ring):
+        st = C3Step(hosts[i % len(hosts)], dev, dist_ctx)
+        if not args.no_graph:
+            st.capture()
+        steps_obj.append(st)
+    launches_per_step = steps_obj[0].launches if not args.no_graph else None
+    if launches_per_step is None:
+        ops.reset_launch_count()
+        steps_obj[0].run()
+        launches_per_step = ops.launch_count()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    stream = torch.cuda.current_stream()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    # warm-up: at least W (>= 3) steps and at least ~0.4 s of replay so that clocks have ramped and nvidia-smi
+    # (100 ms period) sees the load
+    n_warm = 0
+    t_w = time.perf_counter()
+    while n_warm < max(args.warmup, 3) or time.perf_counter() - t_w < 0.4:
+        for i in range(50):
+            steps_obj[(n_warm + i) % ring].run()
+        n_warm += 50
+        torch.cuda.synchronize()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for i in range(args.steps):
+        steps_obj[i % ring].run()
+    e1.record(stream)
+    barrier()
+    dt = e0.elapsed_time(e1) * 1e-3
+    loss_val = float(steps_obj[(args.steps - 1) % ring].loss)
+    if world > 1:
+        t = torch.tensor([dt], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t)
+
+    # ---- end to end through the public API with HOST buffers: H2D of the step's inputs, step, D2H of the loss
+    e2e_steps = max(3, min(args.steps, 50))
+    st = steps_obj[0]
+    h = hosts[0]
+    h2d = sum(v.numel() * 4 for v in h.values())
+    host_loss = torch.empty((), dtype=torch.float32).pin_memory()
+
+    def e2e_once():
+        with torch.no_grad():
+            st.enc.copy_(h["enc"], non_blocking=True)
+            st.eps.copy_(h["eps"], non_blocking=True)
+            st.raw.copy_(h["raw"], non_blocking=True)
+            st.x.copy_(h["x"], non_blocking=True)
+        st.run()
+        host_loss.copy_(st.loss.detach(), non_blocking=True)
+
+    for _ in range(3):
+        e2e_once()
+    barrier()
+    e0.record(stream)
+    for _ in range(e2e_steps):
+        e2e_once()
+    e1.record(stream)
+    barrier()
+    dt_e2e = e0.elapsed_time(e1) * 1e-3
+    if world > 1:
+        t = torch.tensor([dt_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt_e2e = float(t)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- roofline of the dominant kernel (DMOL backward: 53.2 MB per launch), timed alone on the launching stream
+    lib = _lib.load()
+    raws = [s_.raw.detach() for s_ in steps_obj]
+    xs = [s_.x for s_ in steps_obj]
+    g = torch.full((batch, 1), 1.0 / batch, device=dev)
+    draw = [torch.empty_like(r) for r in raws[:2]]
+    err = torch.empty(batch, 1, device=dev)
+    ws = torch.zeros(max(int(lib.mae_dmol_workspace_bytes(batch, 1024)), 256), dtype=torch.uint8, device=dev)
+    sp = stream.cuda_stream
+
+    def k_bwd(i):
+        j = i % ring
+        lib.mae_dmol_bwd(raws[j].data_ptr(), xs[j].data_ptr(), g.data_ptr(), batch, 1, 10, 1024, draw[i % 2].data_ptr(), sp)
+
+    def k_fwd(i):
+        j = i % ring
+        lib.mae_dmol_fwd(raws[j].data_ptr(), xs[j].data_ptr(), batch, 1, 10, 1024, err.data_ptr(), ws.data_ptr(), ws.numel(), sp)
+
+    n_k = max(20, min(200, args.steps))
+    t_bwd = time_kernel(k_bwd, n_k, stream)
+    t_fwd = time_kernel(k_fwd, n_k, stream)
+    roof = {"bound": "hbm", "kernel": "dmol_bwd_kernel", "achieved": bwd_b / t_bwd / 1e9, "peak": hbm_gbs, "unit": "GB/s",
+            "frac": bwd_b / t_bwd / 1e9 / hbm_gbs, "traffic": None, "peak_source": peak_src,
+            "bytes_per_launch": bwd_b, "us_per_launch": t_bwd * 1e6,
+            "dmol_fwd": {"achieved": fwd_b / t_fwd / 1e9, "frac": fwd_b / t_fwd / 1e9 / hbm_gbs, "bytes_per_launch": fwd_b,
+                         "us_per_launch": t_fwd * 1e6},
+            "step": {"bytes": step_bytes, "us": dt / args.steps * 1e6, "frac": step_bytes / (dt / args.steps) / 1e9 / hbm_gbs}}
+
+    out = None
+    if rank == 0:
+        extra = {}
+        if world == 1 and not args.no_extra:
+            extra = bench_extra(dev, hbm_gbs)
+        cpu = cpu_baseline_c3(budget_s=12.0) if not args.no_cpu else None
+        value = world * batch * args.steps / dt
+        out = {
+            "metric": "mae_loss_head_fwd_bwd_samples_per_s", "value": value, "unit": "samples/s", "n_gpus": world,
+            "steps": args.steps, "warmup": n_warm, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "C3: CIFAR-10 32x32x3 head, DMOL nmix=10, latent 64, batch 64/GPU, MPD on (eta=gamma=1), "
+                                   "full MAE loss fwd+bwd on synthetic encoder/decoder outputs",
+                       "global_batch": world * batch, "parallelism": "dp%d (batch-sharded; MPD over the all-gathered batch)" % world,
+                       "l2": "ring of %d input slabs (%.0f MB) cycled > 126 MB L2" % (ring, ring * step_bytes / 1e6),
+                       "cuda_graph": not args.no_graph},
+            "e2e": {"value": world * batch * e2e_steps / dt_e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": 4, "ms_per_step": dt_e2e / e2e_steps * 1e3},
+            "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
+            "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "loss": loss_val, "workloads": extra,
+        }
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return out
+
+
+# ------------------------------------------------------------------------------- secondary workloads (N=1)
+def bench_extra(dev, hbm_gbs):
+    """C4 (IW-NLL eval), C1/C2 (binary head) and C5 (MPD microbench) as secondary numbers with their own rooflines."""
+    from mae_b200 import heads, ops, synth
+    res = {}
+    stream = torch.cuda.current_stream()
+    # ---- C4: K=512 samples per image, 2 images per launch, ring of 4 slabs (4 x 419 MB) > L2
+    k, nimg, d = 512, 2, 64
+    slabs = []
+    g = torch.Generator(device=dev).manual_seed(524287)
+    for i in range(4):
+        raw = torch.randn(nimg * k, 100, 32, 32, device=dev, generator=g)
+        x = (torch.randint(0, 256, (nimg, 3, 32, 32), device=dev, generator=g).float() / 127.5 - 1.0)
+        mu = torch.randn(nimg, d, device=dev, generator=g)
+        lv = torch.randn(nimg, d, device=dev, generator=g).clamp(-7, 7)
+        z = mu[:, None] + torch.randn(nimg, k, d, device=dev, generator=g) * (0.5 * lv).exp()[:, None]
+        slabs.append((raw, x, z, mu, lv))
+    per_img = 4 * (k * 100 * 1024 + 3 * 1024 + k * (2 * d + 3) + 2 * d)
+
+    def c4(i):
+        raw, x, z, mu, lv = slabs[i % 4]
+        return heads.iw_eval_color(raw, x, z, mu, lv, 10)
+
+    t = time_kernel(c4, 24, stream)
+    res["c4_iw_nll_eval"] = {"metric": "iw_nll_eval_images_per_s", "value": nimg / t, "unit": "images/s",
+                             "config": "CIFAR shapes, K=512, %d images/launch, ring of 4 slabs (1.7 GB) > L2" % nimg,
+                             "roofline": {"bound": "hbm", "achieved": nimg * per_img / t / 1e9, "peak": hbm_gbs,
+                                          "frac": nimg * per_img / t / 1e9 / hbm_gbs, "bytes_per_image": per_img}}
+    del slabs
+    torch.cuda.empty_cache()
+    # ---- C1/C2: binary head fwd+bwd, B=100, D=64 (launch-latency-bound: 1.57 MB / 10 MFLOP per step)
+    h = synth.binary_head(100, 1, 784)
+    mu0, lv0 = synth.posterior_params(100, (64,))
+    enc = torch.cat([mu0, lv0], 1).to(dev).requires_grad_()
+    eps = synth.noise(100, 1, (64,)).to(dev)
+    probs = h["probs"].to(dev).requires_grad_()
+    xb = h["x"].to(dev)
+
+    def c1_step():
+        enc.grad = None
+        probs.grad = None
+        mu, lv = enc.chunk(2, 1)
+        loss = heads.loss_head_binary(mu, lv, eps, probs, xb, ETA, GAMMA, FREE_BITS)[0]
+        loss.backward()
+        return loss
+
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(3):
+            c1_step()
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    ops.reset_launch_count()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        c1_step()
+    n_launch = ops.launch_count()
+    t = time_kernel(lambda i: graph.replay(), 200, stream)
+    c1_bytes = 4 * (100 * 784 + 100 * 784 + 100) + 4 * (2 * 100 * 784 + 100 * 784 + 100)
+    res["c1_binary_head"] = {"metric": "mae_loss_head_fwd_bwd_samples_per_s", "value": 100 / t, "unit": "samples/s",
+                             "config": "MNIST/OMNIGLOT 28x28 head, B=100, latent 64, Bernoulli + MPD fwd+bwd, CUDA graph",
+                             "us_per_step": t * 1e6, "launches_per_step": n_launch,
+                             "roofline": {"bound": "launch-latency", "hbm_floor_us": c1_bytes / (hbm_gbs * 1e9) * 1e6,
+                                          "frac": c1_bytes / t / 1e9 / hbm_gbs}}
+    # ---- C5: MPD microbench fwd+bwd, B=8192, D=64 (16*B^2*D flop algorithmic)
+    for b5, d5 in ((8192, 64),):
+        mu5, lv5 = synth.posterior_params(b5, (d5,), seed=5)
+        mu5, lv5 = mu5.to(dev).requires_grad_(), lv5.to(dev).requires_grad_()
+
+        def c5(i):
+            mu5.grad = None
+            lv5.grad = None
+            m_d, s_ = ops.mpd(mu5, lv5)
+            (-torch.nn.functional.logsigmoid(m_d).sum() + s_).backward()
+
+        t = time_kernel(c5, 5, stream)
+        flop = 16.0 * b5 * b5 * d5
+        res["c5_mpd_b%d_d%d" % (b5, d5)] = {"metric": "mpd_fwd_bwd_pairs_per_s", "value": b5 * b5 / t, "unit": "pairs/s",
+                                            "ms": t * 1e3, "tflops_algorithmic": flop / t / 1e12,
+                                            "roofline": {"bound": "fp32 ffma", "peak_tflops_nominal": 148 * 128 * 2 * 1.965e-3,
+                                                         "frac": flop / t / 1e12 / (148 * 128 * 2 * 1.965e-3)}}
+    return res
+
+
+# ------------------------------------------------------------------------------------------- CPU / reference
+def cpu_c3_step_fn(batch=64, latent=64):
+    """The oracle port of the reference's CPU path for one C3 step (fwd+bwd) on host cores."""
+    from mae_b200 import synth
+    from oracle import mae_oracle as O
+    h = c3_host_inputs(0, batch, latent)
+    enc = h["enc"].clone().requires_grad_()
+    raw = h["raw"].clone().requires_grad_()
+
+    def step():
+        enc.grad = None
+        raw.grad = None
+        mu, lv = enc.chunk(2, 1)
+        out, _ = O.loss_head_color(mu, lv, h["eps"], lambda z: raw, h["x"], 10, ETA, GAMMA, FREE_BITS)
+        out[0].backward()
+        return float(out[0])
+
+    return step
+
+
+def cpu_baseline_c3(budget_s=12.0):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    step = cpu_c3_step_fn()
+    step()
+    t0 = time.perf_counter()
+    n = 0
+    while n < 3 or (time.perf_counter() - t0 < budget_s and n < 200):
+        step()
+        n += 1
+    dt = (time.perf_counter() - t0) / n
+    return {"value": 64 / dt, "unit": "samples/s", "cores": cores, "kind": "port",
+            "sample": "%d full C3 steps (B=64) of oracle/mae_oracle.py (torch CPU restatement of the reference's ATen path), "
+                      "%.1f ms/step" % (n, dt * 1e3)}
+
+
+def bench_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path (oracle port: the reference is pure
+    Python/ATen and /root/reference does not exist on the GPU box) on all host cores, same config and metric."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return None
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    step = cpu_c3_step_fn()
+    warm = max(1, min(args.warmup, 3))
+    for _ in range(warm):
+        step()
+    steps = max(1, min(args.steps, 40))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        loss = step()
+    dt = time.perf_counter() - t0
+    value = 64 * steps / dt
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    return {
+        "impl": "reference", "metric": "mae_loss_head_fwd_bwd_samples_per_s", "value": value, "unit": "samples/s",
+        "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C3: CIFAR-10 32x32x3 head, DMOL nmix=10, latent 64, batch 64, MPD on (eta=gamma=1), full MAE "
+                               "loss fwd+bwd on synthetic encoder/decoder outputs", "global_batch": 64, "parallelism": "host cpu"},
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port",
+                         "sample": "%d C3 steps (B=64) of the oracle port on %d host threads" % (steps, cores)},
+        "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "loss": loss,
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying CUDA graphs")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads (C1, C4, C5)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        out = bench_reference(args)
+    else:
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device (the hot path has no CPU fallback); use --impl reference for the CPU arm")
+        out = bench_ours(args)
+    if out is not None:
+        print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

@@ -12,8 +12,8 @@ __device__ __forceinline__ float logsigmoid(float x) { return fminf(x, 0.f) - lo
 
 __global__ void __launch_bounds__(kThreads)
 assemble_fwd_kernel(const float* __restrict__ err, const float* __restrict__ kl, const float* __restrict__ m_d,
-                    const float* __restrict__ S, int B, int ns, int D, float eta, float gamma, float free_bits,
-                    float inv_batch, float* __restrict__ scalars, float* __restrict__ recon) {
+                    const float* __restrict__ S, const float* __restrict__ ext_sums, int B, int ns, int D, float eta,
+                    float gamma, float free_bits, float inv_batch, float* __restrict__ scalars, float* __restrict__ recon) {
     __shared__ float scratch[32];
     float s_rec = 0.f, s_kl = 0.f, s_m = 0.f, s_ls = 0.f;
     const float inv_ns = 1.0f / (float)ns;
@@ -37,6 +37,10 @@ assemble_fwd_kernel(const float* __restrict__ err, const float* __restrict__ kl,
     s_m = block_sum(s_m, scratch);
     s_ls = block_sum(s_ls, scratch);
     if (threadIdx.x == 0) {
+        if (ext_sums != nullptr) {
+            s_rec += ext_sums[0];
+            s_kl += ext_sums[1];
+        }
         const float mean_rec = s_rec * inv_batch, mean_kl = s_kl * inv_batch;
         const float l_mean = (eta > 0.f && m_d != nullptr) ? -eta * s_ls : 0.f;
         const float l_std = (gamma > 0.f && S != nullptr) ? gamma * S[0] : 0.f;
@@ -70,15 +74,15 @@ assemble_bwd_kernel(const float* __restrict__ gloss, const float* __restrict__ s
 }  // namespace
 }  // namespace mae
 
-extern "C" int mae_loss_assemble_fwd(const float* err, const float* kl, const float* m_d, const float* S, int64_t B, int64_t ns,
-                                     int64_t D, float eta, float gamma, float free_bits, float inv_batch, float* scalars,
+extern "C" int mae_loss_assemble_fwd(const float* err, const float* kl, const float* m_d, const float* S,
+                                     const float* ext_sums, int64_t B, int64_t ns, int64_t D, float eta, float gamma, float free_bits, float inv_batch, float* scalars,
                                      float* recon, mae_stream_t stream) {
     using namespace mae;
     MAE_REQUIRE(err && kl && scalars && recon, MAE_ERR_NULL);
     MAE_REQUIRE(B > 0 && ns > 0 && D >= 0 && B < (1ll << 31) && ns < (1ll << 31) && D < (1ll << 31), MAE_ERR_SHAPE);
     if (inv_batch <= 0.f) inv_batch = 1.0f / (float)B;
-    assemble_fwd_kernel<<<1, kThreads, 0, as_stream(stream)>>>(err, kl, m_d, S, (int)B, (int)ns, (int)D, eta, gamma, free_bits,
-                                                              inv_batch, scalars, recon);
+    assemble_fwd_kernel<<<1, kThreads, 0, as_stream(stream)>>>(err, kl, m_d, S, ext_sums, (int)B, (int)ns, (int)D, eta, gamma,
+                                                              free_bits, inv_batch, scalars, recon);
     return launch_status();
 }
 

@@ -1,15 +1,20 @@
 // A3: mutual posterior divergence regulariser (gaussian_encoder.py:162-188) without the [B,B,D] tensor.
 //
-//   2*KL_ij = x~_i . y~_j + c_j - l_i - D        (K = 2D contraction, FP32 FFMA, register-tiled)
-//     x~_i = [v_i + mu_i^2, mu_i]  (interleaved per latent dim: k = 2d, 2d+1)
-//     y~_j = [r_j, -2 mu_j r_j]    v = exp(lv), r = 1/(v + 1e-12)
-//     c_j  = sum_d (mu_j^2 r_j + lv_j),  l_i = sum_d lv_i
-//   mu is taken relative to row 0 (KL is translation invariant per dimension), which removes the
-//   cancellation a common offset would cause in the expanded square.
+// Pivoted GEMM decomposition (K = 2D contraction, FP32 FFMA, register-tiled).  With per-dimension pivots
+// mu_bar, l_bar (mean of the first <=32 rows; KL is invariant to a common shift of mu and a common scale of v),
+// v_bar = exp(l_bar), alpha = lv - l_bar, a = expm1(alpha) = v/v_bar - 1, b = v_bar*r - 1, r = 1/(v + 1e-12),
+// mc = mu - mu_bar, s = mc^2/v_bar:
+//   2*KL_ij = x~_i . y~_j + E_i + F_j
+//     x~_i = [a_i + s_i, mc_i]        (interleaved per latent dim: k = 2d, 2d+1)
+//     y~_j = [b_j, -2 mc_j r_j]
+//     E_i  = sum_d (a_i - alpha_i + s_i),   F_j = sum_d (b_j + alpha_j + mc_j^2 r_j)
+//   Every term is small when the posteriors are alike, so the tiles keep full relative precision in the
+//   posterior-collapse regime where the reference's own (A + B - C - 1) cancels (hard part 3).
+//   The O(B*D) pre-pass evaluates the per-element quantities in fp64.
 //
 // Kernels
-//   mpd_prepare_kernel   O(B*D): panels X~, Y~ (row-major [Bp][Kp]), V (float4 {mu,v,r,lv}), c, l, per-dimension
-//                        column sums in fp64, m_d and m = sum_d m_d (closed form, SURVEY.md §8a "A3-alg").
+//   mpd_prepare_kernel   O(B*D): pivots, panels X~, Y~ (row-major [Bp][Kp]), V (float4 {mc,a,b,t}), E, F,
+//                        per-dimension column sums in fp64, m_d and m = sum_d m_d (closed form, SURVEY.md §8a "A3-alg").
 //   mpd_fwd_kernel       64x64 tiles of KL over rows [row0,row1) x all columns; accumulates sum (KL_ij - m)^2
 //                        (m is known beforehand, so no E[x^2]-E[x]^2 cancellation); optional KL / KL^T store.
 //   mpd_bwd_small_kernel B <= 2048: per-(i,d) gradient from the stored KL and KL^T (L2-resident).
@@ -30,6 +35,8 @@ constexpr int kLd = kT + 4;    // padded leading dimension (keeps float4 alignme
 constexpr int kOC = 128;       // K columns (= 64 latent dims) of gradient owned by one CTA of the tile backward
 constexpr int kLdP = kOC + 4;
 constexpr int kMaxFwdCtas = 592;  // 4 x 148; fixed so partial-sum order does not depend on the device
+constexpr int kPivotRows = 32;    // pivots = mean of the first min(B,32) rows
+constexpr double kEpsD = 1e-12;
 
 struct Hdr {  // first 256 bytes of the workspace
     unsigned int ticket_prep;
@@ -41,7 +48,7 @@ struct Hdr {  // first 256 bytes of the workspace
 
 struct Layout {
     int64_t Bp, Kp, nblk;
-    int64_t hdr, colstats, c, l, xp, yp, vp, part_prep, part_fwd, kl, klt, total;
+    int64_t hdr, colstats, pivots, c, l, xp, yp, vp, part_prep, part_fwd, kl, klt, total;
 };
 
 Layout make_layout(int64_t B, int64_t D) {
@@ -57,6 +64,7 @@ Layout make_layout(int64_t B, int64_t D) {
     };
     L.hdr = take(256);
     L.colstats = take(8 * D * 8);
+    L.pivots = take(3 * D * 8);  // double mu_bar[D], l_bar[D], v_bar[D]
     L.c = take(L.Bp * 4);
     L.l = take(L.Bp * 4);
     L.xp = take(L.Bp * L.Kp * 4);
@@ -80,36 +88,69 @@ T* at(void* ws, int64_t off) {
 }
 
 // ---------------------------------------------------------------------------------------------- prepare
+// per-element quantities of the pivoted decomposition, fp64
+struct Elem {
+    double mc, alpha, a, v, r, b;
+};
+__device__ __forceinline__ Elem make_elem(float mu, float lv, double mu_bar, double l_bar, double v_bar) {
+    Elem e;
+    e.mc = (double)mu - mu_bar;
+    e.alpha = (double)lv - l_bar;
+    e.a = expm1(e.alpha);
+    e.v = v_bar * (1.0 + e.a);
+    e.r = 1.0 / (e.v + kEpsD);
+    e.b = -(e.a * v_bar + kEpsD) * e.r;  // v_bar * r - 1 without cancellation
+    return e;
+}
+
 __global__ void __launch_bounds__(kNT)
 mpd_prepare_kernel(const float* __restrict__ mu, int64_t mu_stride, const float* __restrict__ lv, int64_t lv_stride, int B,
                    int D, int Kp, float* __restrict__ Xp, float* __restrict__ Yp, float4* __restrict__ Vp,
-                   float* __restrict__ cvec, float* __restrict__ lvec, double* part, double* __restrict__ colstats, Hdr* hdr,
-                   float* __restrict__ m_d_out) {
+                   float* __restrict__ evec, float* __restrict__ fvec, double* part, double* __restrict__ colstats,
+                   double* pivots, Hdr* hdr, float* __restrict__ m_d_out) {
     __shared__ double scratch[32];
     __shared__ bool is_last;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int blk = blockIdx.x;
     const int i0 = blk * kT;
 
+    // phase 0: pivots.  Every CTA computes the same values and writes the same bits (benign), then reads its own.
+    {
+        const int P = B < kPivotRows ? B : kPivotRows;
+        for (int d = tid; d < D; d += kNT) {
+            double sm = 0.0, sl = 0.0;
+            for (int i = 0; i < P; ++i) {
+                sm += (double)mu[(int64_t)i * mu_stride + d];
+                sl += (double)lv[(int64_t)i * lv_stride + d];
+            }
+            sm /= (double)P;
+            sl /= (double)P;
+            pivots[d] = sm;
+            pivots[(int64_t)D + d] = sl;
+            pivots[2 * (int64_t)D + d] = exp(sl);
+        }
+    }
+    __syncthreads();
+
     // phase A: one warp per row; lanes strided over latent dims (coalesced reads and panel writes)
     for (int r = w; r < kT; r += kNT / 32) {
         const int i = i0 + r;
         float* xr = Xp + (int64_t)i * Kp;
         float* yr = Yp + (int64_t)i * Kp;
-        float cs = 0.f, ls = 0.f;
+        double es = 0.0, fs = 0.0;
         if (i < B) {
             const float* mr = mu + (int64_t)i * mu_stride;
             const float* lr = lv + (int64_t)i * lv_stride;
             for (int d = lane; d < D; d += 32) {
-                const float l = lr[d];
-                const float mc = mr[d] - mu[d];  // relative to row 0
-                const float v = expf(l);
-                const float rr = 1.0f / (v + kEps);
-                *reinterpret_cast<float2*>(xr + 2 * d) = make_float2(v + mc * mc, mc);
-                *reinterpret_cast<float2*>(yr + 2 * d) = make_float2(rr, -2.0f * mc * rr);
-                Vp[(int64_t)i * D + d] = make_float4(mc, v, rr, l);
-                cs += mc * mc * rr + l;
-                ls += l;
+                const double v_bar = pivots[2 * (int64_t)D + d];
+                const Elem e = make_elem(mr[d], lr[d], pivots[d], pivots[(int64_t)D + d], v_bar);
+                const double s = e.mc * e.mc / v_bar;
+                const double t = e.a + (2.0 * e.b + e.b * e.b) * (1.0 + e.a);  // r^2 v v_bar - 1
+                *reinterpret_cast<float2*>(xr + 2 * d) = make_float2((float)(e.a + s), (float)e.mc);
+                *reinterpret_cast<float2*>(yr + 2 * d) = make_float2((float)e.b, (float)(-2.0 * e.mc * e.r));
+                Vp[(int64_t)i * D + d] = make_float4((float)e.mc, (float)e.a, (float)e.b, (float)t);
+                es += (e.a - e.alpha) + s;
+                fs += (e.b + e.alpha) + e.mc * e.mc * e.r;
             }
             for (int k = 2 * D + lane; k < Kp; k += 32) {
                 xr[k] = 0.f;
@@ -121,32 +162,29 @@ mpd_prepare_kernel(const float* __restrict__ mu, int64_t mu_stride, const float*
                 yr[k] = 0.f;
             }
         }
-        cs = warp_sum(cs);
-        ls = warp_sum(ls);
+        es = warp_sum(es);
+        fs = warp_sum(fs);
         if (lane == 0) {
-            cvec[i] = cs;
-            lvec[i] = ls;
+            evec[i] = (float)es;
+            fvec[i] = (float)fs;
         }
     }
 
     // phase B: per-dimension partial column sums over this CTA's rows, fp64
     for (int d = tid; d < D; d += kNT) {
         double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0, a6 = 0;
-        const float pivot = mu[d];
+        const double mu_bar = pivots[d], l_bar = pivots[(int64_t)D + d], v_bar = pivots[2 * (int64_t)D + d];
         for (int r = 0; r < kT; ++r) {
             const int i = i0 + r;
             if (i >= B) break;
-            const float l = lv[(int64_t)i * lv_stride + d];
-            const float mc = mu[(int64_t)i * mu_stride + d] - pivot;
-            const float v = expf(l);
-            const float rr = 1.0f / (v + kEps);
-            a0 += v;
-            a1 += rr;
-            a2 += (double)v * rr;
-            a3 += mc;
-            a4 += (double)mc * mc;
-            a5 += (double)rr * mc;
-            a6 += (double)rr * mc * mc;
+            const Elem e = make_elem(mu[(int64_t)i * mu_stride + d], lv[(int64_t)i * lv_stride + d], mu_bar, l_bar, v_bar);
+            a0 += e.v;
+            a1 += e.r;
+            a2 += e.v * e.r;
+            a3 += e.mc;
+            a4 += e.mc * e.mc;
+            a5 += e.r * e.mc;
+            a6 += e.r * e.mc * e.mc;
         }
         double* p = part + (int64_t)blk * 7 * D + d;
         p[0 * (int64_t)D] = a0;
@@ -221,8 +259,8 @@ __device__ __forceinline__ void fma_tile(const float (*A)[kLd], const float (*Bm
 
 // ---------------------------------------------------------------------------------------------- forward
 __global__ void __launch_bounds__(kNT)
-mpd_fwd_kernel(const float* __restrict__ Xp, const float* __restrict__ Yp, const float* __restrict__ cvec,
-               const float* __restrict__ lvec, Hdr* hdr, double* part, int B, int D, int Kp, int row0, int row1, int tr0,
+mpd_fwd_kernel(const float* __restrict__ Xp, const float* __restrict__ Yp, const float* __restrict__ evec,
+               const float* __restrict__ fvec, Hdr* hdr, double* part, int B, int D, int Kp, int row0, int row1, int tr0,
                int ntr, int ntc, float* __restrict__ KL, float* __restrict__ KLT, int Bp, double* __restrict__ sumsq_out,
                float* __restrict__ S_out) {
     __shared__ __align__(16) float As[kKC][kLd];
@@ -231,7 +269,6 @@ mpd_fwd_kernel(const float* __restrict__ Xp, const float* __restrict__ Yp, const
     __shared__ bool is_last;
     const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
     const float m = (float)hdr->m;
-    const float fd = (float)D;
     double total = 0.0;
     const int ntiles = ntr * ntc;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -250,18 +287,18 @@ mpd_fwd_kernel(const float* __restrict__ Xp, const float* __restrict__ Yp, const
         }
         float psum = 0.f;
         const int jb = tj * kT + tx * 4;
-        const float4 c4 = *reinterpret_cast<const float4*>(cvec + jb);
-        const float cj[4] = {c4.x, c4.y, c4.z, c4.w};
+        const float4 f4 = *reinterpret_cast<const float4*>(fvec + jb);
+        const float fj[4] = {f4.x, f4.y, f4.z, f4.w};
         float klv[4][4];
 #pragma unroll
         for (int ii = 0; ii < 4; ++ii) {
             const int i = ti * kT + ty * 4 + ii;
-            const float li = lvec[i];
+            const float ei = evec[i];
             const bool row_ok = (i >= row0) && (i < row1);
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {
                 const int j = jb + jj;
-                const float kl = 0.5f * (acc[ii][jj] + cj[jj] - li - fd);
+                const float kl = 0.5f * (acc[ii][jj] + ei + fj[jj]);
                 klv[ii][jj] = kl;
                 if (row_ok && j < B && j != i) {
                     const float dev = kl - m;
@@ -317,14 +354,16 @@ __device__ __forceinline__ float weight_scale(const float* g_S, const float* S, 
 }
 
 // closed-form gradient of sum_d g_m[d]*m_d w.r.t. (mu_k,d ; lv_k,d), fp64, O(1) per element.
-__device__ __forceinline__ void mean_part(const double* __restrict__ cs, const float* __restrict__ g_m, int B, int D, int d,
-                                          float mc_f, float v_f, float r_f, float& gmu, float& glv) {
+__device__ __forceinline__ void mean_part(const double* __restrict__ cs, const double* __restrict__ pivots,
+                                          const float* __restrict__ g_m, int B, int D, int d, float mu_f, float lv_f,
+                                          float& gmu, float& glv) {
     if (g_m == nullptr) return;
     const double nb = (double)B;
     const double a = (double)g_m[d] / (nb * (nb - 1.0));
     const double Sv = cs[0 * (int64_t)D + d], R0 = cs[1 * (int64_t)D + d], S1 = cs[3 * (int64_t)D + d],
                  S2 = cs[4 * (int64_t)D + d], R1 = cs[5 * (int64_t)D + d];
-    const double mc = mc_f, v = v_f, r = r_f;
+    const Elem e = make_elem(mu_f, lv_f, pivots[d], pivots[(int64_t)D + d], pivots[2 * (int64_t)D + d]);
+    const double mc = e.mc, v = e.v, r = e.r;
     const double dT_dmu = 2.0 * ((mc * R0 - R1) + r * (nb * mc - S1));
     const double dT_dlv = v * ((R0 - r) - r * r * (Sv - v + S2 - 2.0 * S1 * mc + nb * mc * mc));
     gmu += (float)(0.5 * a * dT_dmu);
@@ -332,12 +371,16 @@ __device__ __forceinline__ void mean_part(const double* __restrict__ cs, const f
 }
 
 // ------------------------------------------------------------------------- backward, stored-KL (small B)
-// one warp per (row i, 32 latent dims); walks all partners j.
+// one warp per (row i, 32 latent dims); walks all partners j.  V = {mc, a, b, t} (see the header comment):
+//   d KL_ij/d mu_i = dl*r_j,  d KL_ji/d mu_i = dl*r_i,                        r = (1+b)/v_bar
+//   2 d KL_ij/d lv_i = v_i r_j - 1 = a_i b_j + a_i + b_j
+//   2 d KL_ji/d lv_i = 1 - (v_j + dl^2) r_i^2 v_i = -(a_j + t_i + a_j t_i) - dl^2 (1+t_i)/v_bar
 __global__ void __launch_bounds__(kNT)
-mpd_bwd_small_kernel(const float4* __restrict__ Vp, const float* __restrict__ KL, const float* __restrict__ KLT, int Bp,
-                     const double* __restrict__ colstats, const Hdr* __restrict__ hdr, const float* __restrict__ g_m,
-                     const float* __restrict__ g_S, const float* __restrict__ S, int B, int D, int row0, int nrows,
-                     float* __restrict__ dmu, float* __restrict__ dlv, int accumulate) {
+mpd_bwd_small_kernel(const float* __restrict__ mu, int64_t mu_stride, const float* __restrict__ lv, int64_t lv_stride,
+                     const float4* __restrict__ Vp, const float* __restrict__ KL, const float* __restrict__ KLT, int Bp,
+                     const double* __restrict__ colstats, const double* __restrict__ pivots, const Hdr* __restrict__ hdr,
+                     const float* __restrict__ g_m, const float* __restrict__ g_S, const float* __restrict__ S, int B, int D,
+                     int row0, int nrows, float* __restrict__ dmu, float* __restrict__ dlv, int accumulate) {
     const int lane = threadIdx.x & 31;
     const int nd32 = (D + 31) / 32;
     const int64_t wg = (int64_t)blockIdx.x * (kNT / 32) + (threadIdx.x >> 5);
@@ -348,25 +391,27 @@ mpd_bwd_small_kernel(const float4* __restrict__ Vp, const float* __restrict__ KL
     const float m = (float)hdr->m;
     const float beta = weight_scale(g_S, S, B);
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float4 pi = active ? Vp[(int64_t)i * D + d] : zero4;  // {mu, v, r, lv} of row i
+    const float4 pi = active ? Vp[(int64_t)i * D + d] : zero4;  // {mc, a, b, t} of row i
     float gmu = 0.f, glv = 0.f;
     if (beta != 0.f) {
+        const float ivb = active ? (float)(1.0 / pivots[2 * (int64_t)D + d]) : 0.f;
         const float* kl_row = KL + (int64_t)i * Bp;    // KL_ij
         const float* klt_row = KLT + (int64_t)i * Bp;  // KL_ji
-        const float riv = pi.z * pi.z * pi.y;          // r_i^2 v_i
+        const float opb_i = 1.0f + pi.z, opt_i = 1.0f + pi.w;
         for (int j = 0; j < B; ++j) {
             if (j == i) continue;
             const float w1 = beta * (kl_row[j] - m);
             const float w2 = beta * (klt_row[j] - m);
             const float4 pj = active ? Vp[(int64_t)j * D + d] : zero4;
             const float dl = pi.x - pj.x;
-            gmu = fmaf(dl, fmaf(w1, pj.z, w2 * pi.z), gmu);
-            glv += w1 * (pi.y * pj.z - 1.0f) + w2 * (1.0f - (pj.y + dl * dl) * riv);
+            gmu = fmaf(dl, fmaf(w1, 1.0f + pj.z, w2 * opb_i), gmu);
+            glv += w1 * (fmaf(pi.y, pj.z, pi.y) + pj.z) - w2 * (fmaf(pj.y, pi.w, pj.y) + pi.w + dl * dl * opt_i * ivb);
         }
+        gmu *= ivb;
         glv *= 0.5f;
     }
     if (!active) return;
-    mean_part(colstats, g_m, B, D, d, pi.x, pi.y, pi.z, gmu, glv);
+    mean_part(colstats, pivots, g_m, B, D, d, mu[(int64_t)i * mu_stride + d], lv[(int64_t)i * lv_stride + d], gmu, glv);
     const int64_t o = (int64_t)(i - row0) * D + d;
     if (accumulate) {
         dmu[o] += gmu;
@@ -386,9 +431,10 @@ struct BwdSmem {
 
 // grid: (row tiles, K chunks of kOC columns).  CTA owns rows [i0,i0+64) and gradient dims of its chunk.
 __global__ void __launch_bounds__(kNT)
-mpd_bwd_tile_kernel(const float* __restrict__ Xp, const float* __restrict__ Yp, const float* __restrict__ cvec,
-                    const float* __restrict__ lvec, const float4* __restrict__ Vp, const double* __restrict__ colstats,
-                    const Hdr* __restrict__ hdr, const float* __restrict__ g_m, const float* __restrict__ g_S,
+mpd_bwd_tile_kernel(const float* __restrict__ mu, int64_t mu_stride, const float* __restrict__ lv, int64_t lv_stride,
+                    const float* __restrict__ Xp, const float* __restrict__ Yp, const float* __restrict__ evec,
+                    const float* __restrict__ fvec, const float4* __restrict__ Vp, const double* __restrict__ colstats,
+                    const double* __restrict__ pivots, const Hdr* __restrict__ hdr, const float* __restrict__ g_m, const float* __restrict__ g_S,
                     const float* __restrict__ S, int B, int D, int Kp, int row0, int row1, int tr0, int ntc,
                     float* __restrict__ dmu, float* __restrict__ dlv, int accumulate) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -399,7 +445,6 @@ mpd_bwd_tile_kernel(const float* __restrict__ Xp, const float* __restrict__ Yp, 
     const int kbase = blockIdx.y * kOC;
     const float m = (float)hdr->m;
     const float beta = weight_scale(g_S, S, B);
-    const float fd = (float)D;
 
     float G1[4][8], G2[4][8], rs1[4], rs2[4];
 #pragma unroll
@@ -408,11 +453,11 @@ mpd_bwd_tile_kernel(const float* __restrict__ Xp, const float* __restrict__ Yp, 
 #pragma unroll
         for (int j = 0; j < 8; ++j) G1[i][j] = G2[i][j] = 0.f;
     }
-    float ci[4], li[4];
+    float ei[4], fi[4];
 #pragma unroll
     for (int ii = 0; ii < 4; ++ii) {
-        ci[ii] = cvec[i0 + ty * 4 + ii];
-        li[ii] = lvec[i0 + ty * 4 + ii];
+        ei[ii] = evec[i0 + ty * 4 + ii];
+        fi[ii] = fvec[i0 + ty * 4 + ii];
     }
 
     if (beta != 0.f) {
@@ -435,10 +480,10 @@ mpd_bwd_tile_kernel(const float* __restrict__ Xp, const float* __restrict__ Yp, 
             }
             // weights; W1T/W2T stored [j][i]
             const int jb = j0 + tx * 4;
-            const float4 c4 = *reinterpret_cast<const float4*>(cvec + jb);
-            const float4 l4 = *reinterpret_cast<const float4*>(lvec + jb);
-            const float cj[4] = {c4.x, c4.y, c4.z, c4.w};
-            const float lj[4] = {l4.x, l4.y, l4.z, l4.w};
+            const float4 e4 = *reinterpret_cast<const float4*>(evec + jb);
+            const float4 f4 = *reinterpret_cast<const float4*>(fvec + jb);
+            const float ej[4] = {e4.x, e4.y, e4.z, e4.w};
+            const float fj[4] = {f4.x, f4.y, f4.z, f4.w};
             float w1[4][4], w2[4][4];
 #pragma unroll
             for (int ii = 0; ii < 4; ++ii) {
@@ -448,8 +493,8 @@ mpd_bwd_tile_kernel(const float* __restrict__ Xp, const float* __restrict__ Yp, 
                 for (int jj = 0; jj < 4; ++jj) {
                     const int j = jb + jj;
                     const bool ok = row_ok && j < B && j != i;
-                    const float kij = 0.5f * (a1[ii][jj] + cj[jj] - li[ii] - fd);
-                    const float kji = 0.5f * (a2[ii][jj] + ci[ii] - lj[jj] - fd);
+                    const float kij = 0.5f * (a1[ii][jj] + ei[ii] + fj[jj]);
+                    const float kji = 0.5f * (a2[ii][jj] + ej[jj] + fi[ii]);
                     w1[ii][jj] = ok ? beta * (kij - m) : 0.f;
                     w2[ii][jj] = ok ? beta * (kji - m) : 0.f;
                     rs1[ii] += w1[ii][jj];
@@ -518,12 +563,15 @@ mpd_bwd_tile_kernel(const float* __restrict__ Xp, const float* __restrict__ Yp, 
             const int kcol = kbase + (h >> 1) * 64 + tx * 4 + (h & 1) * 2;
             const int d = kcol >> 1;
             if (d >= D) continue;
-            const float4 pi = Vp[(int64_t)i * D + d];  // {mu, v, r, lv}
+            const float4 pi = Vp[(int64_t)i * D + d];  // {mc, a, b, t}
+            const float ivb = (float)(1.0 / pivots[2 * (int64_t)D + d]);
             const float g1r = G1[ii][cb], g1m = G1[ii][cb + 1], g2x = G2[ii][cb], g2m = G2[ii][cb + 1];
-            float gmu = pi.x * g1r + 0.5f * g1m - pi.z * (g2m - pi.x * rs2[ii]);
-            float glv = 0.5f * (pi.y * g1r - rs1[ii]) +
-                        0.5f * (rs2[ii] - pi.z * pi.z * pi.y * (g2x - 2.0f * pi.x * g2m + pi.x * pi.x * rs2[ii]));
-            mean_part(colstats, g_m, B, D, d, pi.x, pi.y, pi.z, gmu, glv);
+            const float mc = pi.x, a = pi.y, ri = (1.0f + pi.z) * ivb, t = pi.w;
+            // row side: mu_i sum_j W r_j - sum_j W mu_j r_j ; column side: -r_i (sum_j W' mu_j - mu_i sum_j W')
+            float gmu = mc * (g1r + rs1[ii]) * ivb + 0.5f * g1m - ri * (g2m - mc * rs2[ii]);
+            float glv = 0.5f * ((1.0f + a) * g1r + a * rs1[ii]) +
+                        0.5f * (-t * rs2[ii] - (1.0f + t) * (g2x - (2.0f * mc * g2m - mc * mc * rs2[ii]) * ivb));
+            mean_part(colstats, pivots, g_m, B, D, d, mu[(int64_t)i * mu_stride + d], lv[(int64_t)i * lv_stride + d], gmu, glv);
             const int64_t o = (int64_t)(i - row0) * D + d;
             if (accumulate) {
                 dmu[o] += gmu;
@@ -564,7 +612,7 @@ extern "C" int mae_mpd_prepare(const float* mu, int64_t mu_stride, const float* 
     mpd_prepare_kernel<<<(unsigned)L.nblk, kNT, 0, as_stream(stream)>>>(
         mu, mu_stride, logvar, logvar_stride, (int)B, (int)D, (int)L.Kp, at<float>(workspace, L.xp), at<float>(workspace, L.yp),
         at<float4>(workspace, L.vp), at<float>(workspace, L.c), at<float>(workspace, L.l), at<double>(workspace, L.part_prep),
-        at<double>(workspace, L.colstats), at<Hdr>(workspace, L.hdr), m_d);
+        at<double>(workspace, L.colstats), at<double>(workspace, L.pivots), at<Hdr>(workspace, L.hdr), m_d);
     return launch_status();
 }
 
@@ -603,8 +651,8 @@ extern "C" int mae_mpd_bwd(const float* mu, int64_t mu_stride, const float* logv
                            const float* g_S, const float* S, float* dmu, float* dlogvar, int accumulate, int path,
                            mae_stream_t stream) {
     using namespace mae;
-    (void)mu; (void)mu_stride; (void)logvar; (void)logvar_stride;  // everything needed was packed by mae_mpd_prepare
-    MAE_REQUIRE(dmu && dlogvar, MAE_ERR_NULL);
+    MAE_REQUIRE(mu && logvar && dmu && dlogvar, MAE_ERR_NULL);
+    MAE_REQUIRE(mu_stride >= D && logvar_stride >= D, MAE_ERR_STRIDE);
     MAE_REQUIRE(g_S == nullptr || S != nullptr, MAE_ERR_NULL);
     Layout L;
     int rc = check_common(B, D, workspace, workspace_bytes, L);
@@ -618,8 +666,9 @@ extern "C" int mae_mpd_bwd(const float* mu, int64_t mu_stride, const float* logv
         const int64_t blocks = ceil_div(warps, kNT / 32);
         MAE_REQUIRE(blocks < (1ll << 31), MAE_ERR_SHAPE);
         mpd_bwd_small_kernel<<<(unsigned)blocks, kNT, 0, as_stream(stream)>>>(
-            at<float4>(workspace, L.vp), at<float>(workspace, L.kl), at<float>(workspace, L.klt), (int)L.Bp,
-            at<double>(workspace, L.colstats), at<Hdr>(workspace, L.hdr), g_m, g_S, S, (int)B, (int)D, (int)row0, (int)nrows, dmu,
+            mu, mu_stride, logvar, logvar_stride, at<float4>(workspace, L.vp), at<float>(workspace, L.kl),
+            at<float>(workspace, L.klt), (int)L.Bp, at<double>(workspace, L.colstats), at<double>(workspace, L.pivots),
+            at<Hdr>(workspace, L.hdr), g_m, g_S, S, (int)B, (int)D, (int)row0, (int)nrows, dmu,
             dlogvar, accumulate);
         return launch_status();
     }
@@ -633,8 +682,9 @@ extern "C" int mae_mpd_bwd(const float* mu, int64_t mu_stride, const float* logv
     MAE_REQUIRE(nchunks <= 65535, MAE_ERR_SHAPE);
     dim3 grid((unsigned)ntr, (unsigned)nchunks);
     mpd_bwd_tile_kernel<<<grid, kNT, sizeof(BwdSmem), as_stream(stream)>>>(
-        at<float>(workspace, L.xp), at<float>(workspace, L.yp), at<float>(workspace, L.c), at<float>(workspace, L.l),
-        at<float4>(workspace, L.vp), at<double>(workspace, L.colstats), at<Hdr>(workspace, L.hdr), g_m, g_S, S, (int)B, (int)D,
+        mu, mu_stride, logvar, logvar_stride, at<float>(workspace, L.xp), at<float>(workspace, L.yp), at<float>(workspace, L.c),
+        at<float>(workspace, L.l), at<float4>(workspace, L.vp), at<double>(workspace, L.colstats),
+        at<double>(workspace, L.pivots), at<Hdr>(workspace, L.hdr), g_m, g_S, S, (int)B, (int)D,
         (int)L.Kp, (int)row0, (int)(row0 + nrows), tr0, (int)L.nblk, dmu, dlogvar, accumulate);
     return launch_status();
 }

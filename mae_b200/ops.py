@@ -429,16 +429,16 @@ def iw_nll(log_gen: torch.Tensor, z_prior_normal: torch.Tensor, logdet_prior: Op
 # ------------------------------------------------------------------------------------------------
 class _Assemble(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, err, kl, m_d, s, eta, gamma, free_bits, inv_batch):
+    def forward(ctx, err, kl, m_d, s, eta, gamma, free_bits, inv_batch, ext_sums):
         ctx.set_materialize_grads(False)
-        _req_cuda(err, kl, m_d, s)
+        _req_cuda(err, kl, m_d, s, ext_sums)
         b, ns = err.shape
         err_c, kl_c = err.contiguous(), kl.contiguous()
         m_c = m_d.contiguous().view(-1) if m_d is not None else None
         d = m_c.numel() if m_c is not None else 0
         scalars = torch.empty(6, device=err.device, dtype=torch.float32)
         recon = torch.empty(b, device=err.device, dtype=torch.float32)
-        _lib.check(_lib_().mae_loss_assemble_fwd(err_c.data_ptr(), kl_c.data_ptr(), _ptr(m_c), _ptr(s), b, ns, d, eta, gamma,
+        _lib.check(_lib_().mae_loss_assemble_fwd(err_c.data_ptr(), kl_c.data_ptr(), _ptr(m_c), _ptr(s), _ptr(ext_sums), b, ns, d, eta, gamma,
                                                  free_bits, inv_batch, scalars.data_ptr(), recon.data_ptr(), _stream()),
                    "mae_loss_assemble_fwd")
         _count()
@@ -455,7 +455,7 @@ class _Assemble(torch.autograd.Function):
         b, ns, d, eta, gamma, free_bits, inv_batch, m_shape, has_s = ctx.meta
         dev = scalars.device
         if gloss is None:
-            return (None,) * 8
+            return (None,) * 9
         gloss = gloss.contiguous()
         derr = torch.empty(b, ns, device=dev, dtype=torch.float32)
         dkl = torch.empty(b, device=dev, dtype=torch.float32)
@@ -465,13 +465,15 @@ class _Assemble(torch.autograd.Function):
                                                  b, ns, d, eta, gamma, free_bits, inv_batch, derr.data_ptr(), dkl.data_ptr(),
                                                  _ptr(dm), _ptr(ds), _stream()), "mae_loss_assemble_bwd")
         _count()
-        return derr, dkl, (dm.view(m_shape) if dm is not None else None), ds, None, None, None, None
+        return derr, dkl, (dm.view(m_shape) if dm is not None else None), ds, None, None, None, None, None
 
 
 def assemble_loss(err: torch.Tensor, kl: torch.Tensor, m_d: Optional[torch.Tensor], s: Optional[torch.Tensor],
-                  eta: float = 0.0, gamma: float = 0.0, free_bits: float = 0.0, inv_batch: float = 0.0):
+                  eta: float = 0.0, gamma: float = 0.0, free_bits: float = 0.0, inv_batch: float = 0.0,
+                  ext_sums: Optional[torch.Tensor] = None):
     """Objective of MAE.loss (mae.py:132-140) in one launch.
 
     Returns (loss [], stats [5] = (postKL_mean, loss_postKL_mean, loss_postKL_std, mean KL, mean recon), recon [B]).
-    Only ``loss`` carries a gradient; ``stats`` and ``recon`` are logging outputs."""
-    return _Assemble.apply(err, kl, m_d, s, float(eta), float(gamma), float(free_bits), float(inv_batch))
+    Only ``loss`` carries a gradient; ``stats`` and ``recon`` are logging outputs.  ``inv_batch`` (1/global batch)
+    and ``ext_sums`` (device float[2]: recon and KL sums of the other ranks) serve batch-sharded runs."""
+    return _Assemble.apply(err, kl, m_d, s, float(eta), float(gamma), float(free_bits), float(inv_batch), ext_sums)

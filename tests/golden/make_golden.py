@@ -329,18 +329,40 @@ class _RefColorLinearDecoder(RefColorDecoder):
         return self.linear(z).view(z.size(0), 10 * self.nmix, self.h, self.w)
 
 
-def _run_ref_mae(mae, x, ns, eta, gamma, free_bits, seed, k_nll):
+class _InjectNoise:
+    """Feeds a fixed fp32 noise tensor to the reference's ``new_empty(...).normal_()`` draw
+    (gaussian_encoder.py:61) so that the fp32 and the fp64 runs of the UNMODIFIED reference consume the same eps
+    (CPU normal_() yields different streams for float and double)."""
+
+    def __init__(self, eps):
+        self.eps = eps
+
+    def __enter__(self):
+        self._orig = torch.Tensor.normal_
+        eps = self.eps
+
+        def fake(t, *a, **k):
+            assert t.shape == eps.shape, (t.shape, eps.shape)
+            return t.copy_(eps)
+
+        torch.Tensor.normal_ = fake
+        return self
+
+    def __exit__(self, *exc):
+        torch.Tensor.normal_ = self._orig
+
+
+def _run_ref_mae(mae, x, ns, eta, gamma, free_bits, eps_loss, eps_nll, k_nll):
     res = {}
     for tag in ("ref32", "ref64"):
         m = mae if tag == "ref32" else mae.double()
         xx = x if tag == "ref32" else x.double()
         m.zero_grad()
-        torch.manual_seed(seed)
-        out = m.loss(xx, ns, eta=eta, gamma=gamma, free_bits=free_bits)
+        with _InjectNoise(eps_loss):
+            out = m.loss(xx, ns, eta=eta, gamma=gamma, free_bits=free_bits)
         out[0].backward()
         grads = {n: p.grad.clone() for n, p in m.named_parameters()}
-        torch.manual_seed(seed)
-        with torch.no_grad():
+        with _InjectNoise(eps_nll), torch.no_grad():
             (nll_elbo, recon, kl), nll_iw = m.nll(xx, k_nll)
         res[tag] = {"loss7": [o.detach() if torch.is_tensor(o) else torch.tensor(o) for o in out],
                     "grads": grads, "nll_elbo": nll_elbo, "nll_recon": recon, "nll_kl": kl, "nll_iw": nll_iw}
@@ -362,14 +384,14 @@ def golden_mae():
     torch.manual_seed(seed); eps_nll = torch.empty(b, k, nz).normal_()
     out["binary_noflow"] = {"x": x, "state": state, "ns": ns, "k": k, "eta": 1.0, "gamma": 0.5, "free_bits": 0.0,
                             "eps_loss": eps_loss, "eps_nll": eps_nll, "nz": nz, "npix": npix,
-                            **_run_ref_mae(mae, x, ns, 1.0, 0.5, 0.0, seed, k)}
+                            **_run_ref_mae(mae, x, ns, 1.0, 0.5, 0.0, eps_loss, eps_nll, k)}
     # binary, prior flow (MC KL branch, :220-225) + free bits above the KL mean (clamp active)
     enc = RefGaussianEncoder(_RefLinearCore(npix, nz, False), prior_flow=_RefAffineFlow(nz))
     mae = RefMAE(enc, _RefBinaryLinearDecoder(nz, npix))
     state = {n: p.detach().clone() for n, p in mae.state_dict().items()}
     out["binary_priorflow"] = {"x": x, "state": state, "ns": ns, "k": k, "eta": 0.0, "gamma": 1.0, "free_bits": 1e4,
                                "eps_loss": eps_loss, "eps_nll": eps_nll, "nz": nz, "npix": npix,
-                               **_run_ref_mae(mae, x, ns, 0.0, 1.0, 1e4, seed, k)}
+                               **_run_ref_mae(mae, x, ns, 0.0, 1.0, 1e4, eps_loss, eps_nll, k)}
     # colour, no flows
     b, nz, nmix, h, w, ns, k = 5, 6, 4, 4, 4, 2, 16
     enc = RefGaussianEncoder(_RefLinearCore(3 * h * w, nz, True))
@@ -380,7 +402,7 @@ def golden_mae():
     torch.manual_seed(seed); eps_nll = torch.empty(b, k, nz).normal_()
     out["color_noflow"] = {"x": x, "state": state, "ns": ns, "k": k, "eta": 2.0, "gamma": 1.0, "free_bits": 0.0,
                            "eps_loss": eps_loss, "eps_nll": eps_nll, "nz": nz, "nmix": nmix, "h": h, "w": w,
-                           **_run_ref_mae(mae, x, ns, 2.0, 1.0, 0.0, seed, k)}
+                           **_run_ref_mae(mae, x, ns, 2.0, 1.0, 0.0, eps_loss, eps_nll, k)}
     save("mae_stub", out)
 
 

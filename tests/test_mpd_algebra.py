@@ -1,23 +1,34 @@
 """CPU check (fp64, torch) of the closed forms the MPD kernels implement (mae_b200/csrc/mpd.cu):
-GEMM decomposition of KL_ij, O(B*D) formula for m_d, and the own-row backward (row side + column side +
-rank-1 mean part).  Compared with autograd through the oracle.  This validates the algebra only; the CUDA
-code itself is checked by tests/test_gpu_parity.py on a B200."""
+pivoted GEMM decomposition of KL_ij, O(B*D) formula for m_d, and the own-row backward (row side + column
+side + rank-1 mean part) in both the tile form and the stored-KL per-pair form.  Compared with autograd
+through the oracle.  This validates the algebra only; the CUDA code itself is checked by
+tests/test_gpu_parity.py on a B200."""
 import torch
 
 from oracle import mae_oracle as O
 
 
-def kernel_algebra(mu, lv, g_m, g_S):
+def kernel_algebra(mu, lv, g_m, g_S, npivot=32):
     B, D = mu.shape
     eps = 1e-12
-    mc = mu - mu[0:1]                       # pivot on row 0
-    v = lv.exp()
+    P = min(B, npivot)
+    mu_bar = mu[:P].mean(0, keepdim=True)            # pivots: mean of the first P rows
+    l_bar = lv[:P].mean(0, keepdim=True)
+    v_bar = l_bar.exp()
+    ivb = 1.0 / v_bar
+    mc = mu - mu_bar
+    alpha = lv - l_bar
+    a = torch.expm1(alpha)                           # v_i / v_bar - 1
+    v = v_bar * (1 + a)
     r = 1.0 / (v + eps)
-    X = torch.stack([v + mc * mc, mc], dim=2).reshape(B, 2 * D)         # interleaved (2d, 2d+1)
-    Y = torch.stack([r, -2.0 * mc * r], dim=2).reshape(B, 2 * D)
-    c = (mc * mc * r + lv).sum(1)
-    l = lv.sum(1)
-    KL = 0.5 * (X @ Y.t() + c[None, :] - l[:, None] - D)
+    b = -(a * v_bar + eps) * r                       # v_bar * r_j - 1
+    s = mc * mc * ivb
+    t = a + (2 * b + b * b) * (1 + a)                # (1+b)^2 (1+a) - 1 = r^2 v v_bar - 1
+    X = torch.stack([a + s, mc], dim=2).reshape(B, 2 * D)            # interleaved (2d, 2d+1)
+    Y = torch.stack([b, -2.0 * mc * r], dim=2).reshape(B, 2 * D)
+    E = (a - alpha + s).sum(1)
+    F = (b + alpha + mc * mc * r).sum(1)
+    KL = 0.5 * (X @ Y.t() + E[:, None] + F[None, :])
     # column statistics and closed-form m_d
     Sv, R0, Svr, S1, S2, R1, R2 = v.sum(0), r.sum(0), (v * r).sum(0), mc.sum(0), (mc * mc).sum(0), (r * mc).sum(0), (r * mc * mc).sum(0)
     tn = Sv * R0 - Svr + S2 * R0 - 2 * S1 * R1 + B * R2
@@ -26,34 +37,37 @@ def kernel_algebra(mu, lv, g_m, g_S):
     off = ~torch.eye(B, dtype=torch.bool)
     sumsq = ((KL - m)[off] ** 2).sum()
     S = torch.sqrt(sumsq / (B * (B - 1) - 1))
-    # backward
+    # backward, tile form
     beta = g_S / ((B * B - B - 1) * S)
     W1 = beta * (KL - m) * off          # weight of KL_ij, row i
     W2 = beta * (KL.t() - m) * off      # weight of KL_ji seen from row i
-    G1 = W1 @ Y                         # [B,2D]
+    G1 = W1 @ Y
     G2 = W2 @ X
     rs1, rs2 = W1.sum(1, keepdim=True), W2.sum(1, keepdim=True)
     g1r, g1m = G1[:, 0::2], G1[:, 1::2]
     g2x, g2m = G2[:, 0::2], G2[:, 1::2]
-    gmu = mc * g1r + 0.5 * g1m - r * (g2m - mc * rs2)
-    glv = 0.5 * (v * g1r - rs1) + 0.5 * (rs2 - r * r * v * (g2x - 2 * mc * g2m + mc * mc * rs2))
-    a = g_m / (B * (B - 1))
+    ri = (1 + b) * ivb
+    gmu = mc * (g1r + rs1) * ivb + 0.5 * g1m - ri * (g2m - mc * rs2)
+    glv = 0.5 * ((1 + a) * g1r + a * rs1) + 0.5 * (-t * rs2 - (1 + t) * (g2x - (2 * mc * g2m - mc * mc * rs2) * ivb))
+    aa = g_m / (B * (B - 1))
     dT_dmu = 2 * ((mc * R0 - R1) + r * (B * mc - S1))
     dT_dlv = v * ((R0 - r) - r * r * (Sv - v + S2 - 2 * S1 * mc + B * mc * mc))
-    gmu = gmu + 0.5 * a * dT_dmu
-    glv = glv + 0.5 * a * dT_dlv
-    # direct per-pair form used by the stored-KL kernel
+    gmu = gmu + 0.5 * aa * dT_dmu
+    glv = glv + 0.5 * aa * dT_dlv
+    # per-pair form used by the stored-KL kernel
     dl = mc[:, None, :] - mc[None, :, :]
-    gmu2 = (dl * (W1[:, :, None] * r[None] + W2[:, :, None] * r[:, None])).sum(1)
-    glv2 = 0.5 * (W1[:, :, None] * (v[:, None] * r[None] - 1) + W2[:, :, None] * (1 - (v[None] + dl * dl) * (r * r * v)[:, None])).sum(1)
-    gmu2 = gmu2 + 0.5 * a * dT_dmu
-    glv2 = glv2 + 0.5 * a * dT_dlv
+    ai, aj, bi, bj, ti = a[:, None], a[None], b[:, None], b[None], t[:, None]
+    w1, w2 = W1[:, :, None], W2[:, :, None]
+    gmu2 = (dl * (w1 * (1 + bj) + w2 * (1 + bi)) * ivb).sum(1)
+    glv2 = 0.5 * (w1 * (ai * bj + ai + bj) + w2 * (-(aj + ti + aj * ti) - dl * dl * (1 + ti) * ivb)).sum(1)
+    gmu2 = gmu2 + 0.5 * aa * dT_dmu
+    glv2 = glv2 + 0.5 * aa * dT_dlv
     return m_d, S, gmu, glv, gmu2, glv2
 
 
 def test_mpd_kernel_algebra_matches_oracle_autograd():
     torch.manual_seed(0)
-    for B, D, off in [(2, 3, 0.0), (5, 1, 0.0), (9, 4, 20.0), (33, 17, -3.0)]:
+    for B, D, off in [(2, 3, 0.0), (5, 1, 0.0), (9, 4, 20.0), (33, 17, -3.0), (40, 6, 0.5)]:
         mu = (torch.randn(B, D, dtype=torch.float64) + off).requires_grad_()
         lv = torch.randn(B, D, dtype=torch.float64).clamp(-7, 7).requires_grad_()
         g_m = torch.randn(D, dtype=torch.float64)
