@@ -25,72 +25,66 @@ constexpr float kLog2Bin = -4.848116181284444f;  // log(2/255)            (utils
 constexpr float kDeltaMin = 1e-5f;               // cdf_delta threshold   (utils.py:113)
 constexpr float kLogScaleMin = -7.0f;            // log_scale.clamp(min=-7) (color_image_decoder.py:52)
 
-// exp(-|x|) and 1/(1+exp(-|x|)): the two quantities every sigmoid/softplus below is built from.
-struct SigParts {
-    float e;  // exp(-|x|)  in (0,1]
-    float r;  // 1/(1+e)    in [0.5,1)
-};
-MAE_HD SigParts sig_parts(float x) {
-    SigParts s;
-    s.e = expf(-fabsf(x));
-    s.r = 1.0f / (1.0f + s.e);
-    return s;
-}
-MAE_HD float sigmoid_from(const SigParts& s, float x) { return x >= 0.f ? s.r : s.e * s.r; }   // sigma(x)
-MAE_HD float sigmoid_neg_from(const SigParts& s, float x) { return x >= 0.f ? s.e * s.r : s.r; }  // sigma(-x) = 1-sigma(x)
-// softplus(x) = log(1+e^x) = max(x,0) + log1p(e^{-|x|}); F.softplus' threshold-20 shortcut is the same
-// number in fp32 (log1p(e^-20) = 2e-9 < ulp(20)/2).
-MAE_HD float softplus_from(const SigParts& s, float x) { return fmaxf(x, 0.f) + log1pf(s.e); }
+// ---- MUFU primitives -------------------------------------------------------------------------------
+// On the device these are single SFU instructions (ex2/lg2/rcp.approx.ftz, <= 2^-22 relative error);
+// the host versions exist only for tests/hostcheck.
+#if defined(__CUDA_ARCH__)
+MAE_HD float fast_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+MAE_HD float fast_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+MAE_HD float fast_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+#else
+MAE_HD float fast_ex2(float x) { return exp2f(x); }
+MAE_HD float fast_lg2(float x) { return log2f(x); }
+MAE_HD float fast_rcp(float x) { return 1.0f / x; }
+#endif
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
 
 // log of the probability mass a logistic(mean, exp(ls)) puts on the bin of x, with the reference's
 // four-way selection (utils.py:94-118).  cx = x - mean (centred), ls = clamped log-scale.
 // When GRAD, also returns d/dcx and d/dls of the selected branch.
+//
+// Formulation (5 MUFU ops per call on the common path: 3 ex2, 1 rcp, 1 lg2; all selects are branch-free):
+//   s = e^-ls, u = s*cx, hi = u + s/255 ("plus_in"), lo = u - s/255 ("min_in")
+//   eh = e^-|hi|, el = e^-|lo|, a = 1+eh, b = 1+el, r = 1/(a*b)
+//   cdf(hi)-cdf(lo) = num*r with num = el-eh (both > 0), eh-el (both < 0), 1-el*eh (opposite signs):
+//     always a difference of SMALL numbers, so no cancellation near cdf = 1 (the reference loses digits there)
+//   x == 255:  -softplus(lo)    = log(a*r) - max(lo,0)          x == 0:  hi - softplus(hi) = log(b*r) + min(hi,0)
+//   so every non-"approx" case is  log(Q) + lin  with one lg2.
+//   "approx" (delta <= 1e-5, rare): u - ls - 2*softplus(u) + log(2/255), taken as a real branch.
 template <bool GRAD>
 MAE_HD float logistic_bin_logprob(float cx, float ls, float x, float& d_cx, float& d_ls) {
-    const float s = expf(-ls);
-    const float hi = s * (cx + kBin);  // "plus_in"
-    const float lo = s * (cx - kBin);  // "min_in"
-    float L;
-    if (x > kUpper) {  // x == 255: everything above the last bin edge, -softplus(min_in)
-        const SigParts a = sig_parts(lo);
-        L = -softplus_from(a, lo);
+    const float s = fast_ex2(-kLog2e * ls);
+    const float u = s * cx;
+    const float sh = s * kBin;
+    const float hi = u + sh, lo = u - sh;
+    const float eh = fast_ex2(-kLog2e * fabsf(hi)), el = fast_ex2(-kLog2e * fabsf(lo));
+    const float a = 1.0f + eh, b = 1.0f + el;
+    const float r = fast_rcp(a * b);
+    const float num = lo > 0.f ? (el - eh) : (hi < 0.f ? (eh - el) : (1.0f - el * eh));
+    const float delta = num * r;
+    const bool is_up = x > kUpper, is_low = x < kLower;
+    const float q = is_up ? a * r : (is_low ? b * r : fmaxf(delta, kEpsF));
+    const float lin = is_up ? -fmaxf(lo, 0.f) : (is_low ? fminf(hi, 0.f) : 0.f);
+    float L = fmaf(fast_lg2(q), kLn2, lin);
+    if (GRAD) {
+        // d/dhi and d/dlo of the selected branch
+        const float rinv = fast_rcp(num);
+        const float dp_mid = eh * b * b * r * rinv;   // sigma'(hi)/delta
+        const float dq_mid = -el * a * a * r * rinv;  // -sigma'(lo)/delta
+        const float dp = is_up ? 0.f : (is_low ? (hi >= 0.f ? eh : 1.0f) * b * r : dp_mid);   // low: sigma(-hi)
+        const float dq = is_up ? -(lo >= 0.f ? 1.0f : el) * a * r : (is_low ? 0.f : dq_mid);  // up: -sigma(lo)
+        d_cx = s * (dp + dq);
+        d_ls = -(hi * dp + lo * dq);
+    }
+    if (!is_up && !is_low && !(delta > kDeltaMin)) {  // very wide / very far component: density * bin width
+        const float eu = fast_ex2(-kLog2e * fabsf(u));
+        const float sp = fmaxf(u, 0.f) + kLn2 * fast_lg2(1.0f + eu);  // softplus(u)
+        L = u - ls - 2.0f * sp + kLog2Bin;
         if (GRAD) {
-            const float dq = -sigmoid_from(a, lo);
-            d_cx = s * dq;
-            d_ls = -lo * dq;
-        }
-    } else if (x < kLower) {  // x == 0: everything below the first bin edge, plus_in - softplus(plus_in)
-        const SigParts a = sig_parts(hi);
-        L = hi - softplus_from(a, hi);
-        if (GRAD) {
-            const float dp = sigmoid_neg_from(a, hi);
-            d_cx = s * dp;
-            d_ls = -hi * dp;
-        }
-    } else {
-        const SigParts a = sig_parts(hi), b = sig_parts(lo);
-        // cdf(hi) - cdf(lo); evaluated through the complements when both arguments are positive so the
-        // difference of two numbers near 1 does not cancel (hi > lo always).
-        const float delta = lo > 0.f ? (sigmoid_neg_from(b, lo) - sigmoid_neg_from(a, hi))
-                                     : (sigmoid_from(a, hi) - sigmoid_from(b, lo));
-        if (delta > kDeltaMin) {
-            L = logf(fmaxf(delta, kEpsF));
-            if (GRAD) {
-                const float inv = 1.0f / delta;
-                const float dp = a.e * a.r * a.r * inv;    // sigma'(hi)/delta
-                const float dq = -b.e * b.r * b.r * inv;   // -sigma'(lo)/delta
-                d_cx = s * (dp + dq);
-                d_ls = -(hi * dp + lo * dq);
-            }
-        } else {  // very wide component: density at the bin centre times the bin width
-            const float u = s * cx;
-            const SigParts c = sig_parts(u);
-            L = u - ls - 2.0f * softplus_from(c, u) + kLog2Bin;
-            if (GRAD) {
-                const float du = 1.0f - 2.0f * sigmoid_from(c, u);
-                d_cx = s * du;
-                d_ls = -u * du - 1.0f;
-            }
+            const float du = (u >= 0.f ? (eu - 1.0f) : (1.0f - eu)) * fast_rcp(1.0f + eu);  // 1 - 2*sigma(u)
+            d_cx = s * du;
+            d_ls = -u * du - 1.0f;
         }
     }
     return L;
@@ -101,14 +95,24 @@ MAE_HD float logistic_bin_logprob(float cx, float ls, float x, float& d_cx, floa
 // post-processing of ColorImageDecoder.execute (tanh of coefficients, clamp of log-scales).
 //   mu, rho, kap: raw means / log-scales / coefficients of this component; x: the 3 sub-pixels.
 // When GRAD, g_mu/g_rho/g_kap receive d T / d raw for this component.
+// tanh(k) = sign(k)(1-e)/(1+e), e = e^-2|k|; the three reciprocals share one rcp; 1-tanh^2 = 4e/(1+e)^2.
 template <bool GRAD>
 MAE_HD float dmol_component(const float mu[3], const float rho[3], const float kap[3], const float x[3],
                             float g_mu[3], float g_rho[3], float g_kap[3]) {
-    const float c0 = tanhf(kap[0]), c1 = tanhf(kap[1]), c2 = tanhf(kap[2]);
+    const float e0 = fast_ex2(-2.0f * kLog2e * fabsf(kap[0]));
+    const float e1 = fast_ex2(-2.0f * kLog2e * fabsf(kap[1]));
+    const float e2 = fast_ex2(-2.0f * kLog2e * fabsf(kap[2]));
+    const float p0 = 1.0f + e0, p1 = 1.0f + e1, p2 = 1.0f + e2;
+    const float p01 = p0 * p1;
+    const float r3 = fast_rcp(p01 * p2);
+    const float i0 = r3 * p1 * p2, i1 = r3 * p0 * p2, i2 = r3 * p01;  // 1/(1+e_k)
+    const float c0 = copysignf((1.0f - e0) * i0, kap[0]);
+    const float c1 = copysignf((1.0f - e1) * i1, kap[1]);
+    const float c2 = copysignf((1.0f - e2) * i2, kap[2]);
     float mean[3];
     mean[0] = mu[0];
-    mean[1] = mu[1] + c0 * x[0];
-    mean[2] = mu[2] + c1 * x[0] + c2 * x[1];
+    mean[1] = fmaf(c0, x[0], mu[1]);
+    mean[2] = fmaf(c2, x[1], fmaf(c1, x[0], mu[2]));
     float T = 0.f;
     float d_cx[3], d_ls[3];
 #pragma unroll
@@ -122,9 +126,9 @@ MAE_HD float dmol_component(const float mu[3], const float rho[3], const float k
             g_mu[c] = -d_cx[c];                                     // d/d mean = -d/d cx
             g_rho[c] = rho[c] >= kLogScaleMin ? d_ls[c] : 0.f;      // clamp passes the gradient at equality
         }
-        g_kap[0] = x[0] * g_mu[1] * (1.0f - c0 * c0);
-        g_kap[1] = x[0] * g_mu[2] * (1.0f - c1 * c1);
-        g_kap[2] = x[1] * g_mu[2] * (1.0f - c2 * c2);
+        g_kap[0] = x[0] * g_mu[1] * (4.0f * e0 * i0 * i0);
+        g_kap[1] = x[0] * g_mu[2] * (4.0f * e1 * i1 * i1);
+        g_kap[2] = x[1] * g_mu[2] * (4.0f * e2 * i2 * i2);
     }
     return T;
 }
@@ -144,9 +148,9 @@ struct Lse {
     MAE_HD void init() { m = -INFINITY; s = 0.f; }
     MAE_HD void push(float v) {
         if (v <= m) {
-            s += expf(v - m);
+            s += fast_ex2(kLog2e * (v - m));
         } else {
-            s = s * expf(m - v) + 1.0f;
+            s = s * fast_ex2(kLog2e * (m - v)) + 1.0f;
             m = v;
         }
     }
@@ -156,7 +160,7 @@ struct Lse {
         if (o.m <= m) s += o.s * expf(o.m - m);
         else { s = s * expf(m - o.m) + o.s; m = o.m; }
     }
-    MAE_HD float value() const { return m + logf(s); }
+    MAE_HD float value() const { return fmaf(fast_lg2(s), kLn2, m); }
 };
 
 
@@ -211,8 +215,8 @@ MAE_HD void dmol_pixel_bwd(const float* base, float* out, long long cs, int nmix
         float logit, mu[3], rho[3], kap[3], gmu[3], grho[3], gkap[3];
         dmol_load_component<Ld>(base, cs, nmix, m, logit, mu, rho, kap);
         const float T = dmol_component<true>(mu, rho, kap, xs, gmu, grho, gkap);
-        const float w = expf(T + logit - zt);  // responsibility of component m
-        const float pi = expf(logit - zl);     // softmax(logits)_m
+        const float w = fast_ex2(kLog2e * (T + logit - zt));  // responsibility of component m
+        const float pi = fast_ex2(kLog2e * (logit - zl));     // softmax(logits)_m
         const float a = -g * w;                // d err / d T_m
         St::st(out + (long long)m * cs, g * (pi - w));
 #pragma unroll

@@ -48,6 +48,7 @@ struct Hdr {  // first 256 bytes of the workspace
 
 struct Layout {
     int64_t Bp, Kp, nblk;
+    int64_t prep_rows, prep_grid;  // rows per CTA / CTAs of mpd_prepare_kernel
     int64_t hdr, colstats, pivots, c, l, xp, yp, vp, part_prep, part_fwd, kl, klt, total;
 };
 
@@ -56,6 +57,13 @@ Layout make_layout(int64_t B, int64_t D) {
     L.Bp = round_up(B, kT);
     L.Kp = round_up(2 * D, kKC);
     L.nblk = L.Bp / kT;
+    // prepare: 8 rows per CTA for small batches (latency), at most ~1184 CTAs for large ones, <= 512 rows per CTA
+    {
+        int64_t rows = round_up(ceil_div(L.Bp, 1184), 8);
+        if (rows > 512) rows = 512;
+        L.prep_rows = rows;
+        L.prep_grid = ceil_div(L.Bp, rows);
+    }
     int64_t off = 0;
     auto take = [&](int64_t bytes) {
         int64_t o = off;
@@ -70,7 +78,7 @@ Layout make_layout(int64_t B, int64_t D) {
     L.xp = take(L.Bp * L.Kp * 4);
     L.yp = take(L.Bp * L.Kp * 4);
     L.vp = take(L.Bp * D * 16);
-    L.part_prep = take(L.nblk * 7 * D * 8);
+    L.part_prep = take(L.prep_grid * 7 * D * 8);
     L.part_fwd = take(kMaxFwdCtas * 8);
     if (B <= MAE_MPD_SMALL_B) {
         L.kl = take(L.Bp * L.Bp * 4);
@@ -103,97 +111,116 @@ __device__ __forceinline__ Elem make_elem(float mu, float lv, double mu_bar, dou
     return e;
 }
 
+// grid: G CTAs; CTA `blk` owns rows [blk*R, blk*R+R) (R a multiple of 8, so one warp owns whole rows).  Work is
+// organised in chunks of 32 latent dims: lane = dim inside the chunk, warp = row (stride 8).  Every element is
+// evaluated once in fp64 and feeds the panels, the row sums E_i/F_i and the per-dimension column partials.
 __global__ void __launch_bounds__(kNT)
 mpd_prepare_kernel(const float* __restrict__ mu, int64_t mu_stride, const float* __restrict__ lv, int64_t lv_stride, int B,
-                   int D, int Kp, float* __restrict__ Xp, float* __restrict__ Yp, float4* __restrict__ Vp,
+                   int D, int Kp, int R, int Bp, float* __restrict__ Xp, float* __restrict__ Yp, float4* __restrict__ Vp,
                    float* __restrict__ evec, float* __restrict__ fvec, double* part, double* __restrict__ colstats,
                    double* pivots, Hdr* hdr, float* __restrict__ m_d_out) {
+    extern __shared__ __align__(16) unsigned char prep_smem[];
+    double* row_e = reinterpret_cast<double*>(prep_smem);  // [R]
+    double* row_f = row_e + R;                             // [R]
+    __shared__ double col_part[kNT / 32][7][32];
     __shared__ double scratch[32];
     __shared__ bool is_last;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int blk = blockIdx.x;
-    const int i0 = blk * kT;
+    const int i0 = blk * R;
+    constexpr int kWarps = kNT / 32;
 
-    // phase 0: pivots.  Every CTA computes the same values and writes the same bits (benign), then reads its own.
-    {
-        const int P = B < kPivotRows ? B : kPivotRows;
-        for (int d = tid; d < D; d += kNT) {
-            double sm = 0.0, sl = 0.0;
+    for (int r = tid; r < R; r += kNT) {
+        row_e[r] = 0.0;
+        row_f[r] = 0.0;
+    }
+    const int P = B < kPivotRows ? B : kPivotRows;
+    const int nchunk = (D + 31) / 32;
+    for (int ch = 0; ch < nchunk; ++ch) {
+        const int d = ch * 32 + lane;
+        const bool dok = d < D;
+        // pivots of this chunk: mean of the first P rows (every CTA computes the same values)
+        double mu_bar = 0.0, l_bar = 0.0, v_bar = 1.0;
+        if (dok) {
             for (int i = 0; i < P; ++i) {
-                sm += (double)mu[(int64_t)i * mu_stride + d];
-                sl += (double)lv[(int64_t)i * lv_stride + d];
+                mu_bar += (double)mu[(int64_t)i * mu_stride + d];
+                l_bar += (double)lv[(int64_t)i * lv_stride + d];
             }
-            sm /= (double)P;
-            sl /= (double)P;
-            pivots[d] = sm;
-            pivots[(int64_t)D + d] = sl;
-            pivots[2 * (int64_t)D + d] = exp(sl);
-        }
-    }
-    __syncthreads();
-
-    // phase A: one warp per row; lanes strided over latent dims (coalesced reads and panel writes)
-    for (int r = w; r < kT; r += kNT / 32) {
-        const int i = i0 + r;
-        float* xr = Xp + (int64_t)i * Kp;
-        float* yr = Yp + (int64_t)i * Kp;
-        double es = 0.0, fs = 0.0;
-        if (i < B) {
-            const float* mr = mu + (int64_t)i * mu_stride;
-            const float* lr = lv + (int64_t)i * lv_stride;
-            for (int d = lane; d < D; d += 32) {
-                const double v_bar = pivots[2 * (int64_t)D + d];
-                const Elem e = make_elem(mr[d], lr[d], pivots[d], pivots[(int64_t)D + d], v_bar);
-                const double s = e.mc * e.mc / v_bar;
-                const double t = e.a + (2.0 * e.b + e.b * e.b) * (1.0 + e.a);  // r^2 v v_bar - 1
-                *reinterpret_cast<float2*>(xr + 2 * d) = make_float2((float)(e.a + s), (float)e.mc);
-                *reinterpret_cast<float2*>(yr + 2 * d) = make_float2((float)e.b, (float)(-2.0 * e.mc * e.r));
-                Vp[(int64_t)i * D + d] = make_float4((float)e.mc, (float)e.a, (float)e.b, (float)t);
-                es += (e.a - e.alpha) + s;
-                fs += (e.b + e.alpha) + e.mc * e.mc * e.r;
-            }
-            for (int k = 2 * D + lane; k < Kp; k += 32) {
-                xr[k] = 0.f;
-                yr[k] = 0.f;
-            }
-        } else {
-            for (int k = lane; k < Kp; k += 32) {
-                xr[k] = 0.f;
-                yr[k] = 0.f;
+            mu_bar /= (double)P;
+            l_bar /= (double)P;
+            v_bar = exp(l_bar);
+            if (blk == 0 && w == 0) {
+                pivots[d] = mu_bar;
+                pivots[(int64_t)D + d] = l_bar;
+                pivots[2 * (int64_t)D + d] = v_bar;
             }
         }
-        es = warp_sum(es);
-        fs = warp_sum(fs);
-        if (lane == 0) {
-            evec[i] = (float)es;
-            fvec[i] = (float)fs;
-        }
-    }
-
-    // phase B: per-dimension partial column sums over this CTA's rows, fp64
-    for (int d = tid; d < D; d += kNT) {
         double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0, a6 = 0;
-        const double mu_bar = pivots[d], l_bar = pivots[(int64_t)D + d], v_bar = pivots[2 * (int64_t)D + d];
-        for (int r = 0; r < kT; ++r) {
+        for (int r = w; r < R; r += kWarps) {
             const int i = i0 + r;
-            if (i >= B) break;
-            const Elem e = make_elem(mu[(int64_t)i * mu_stride + d], lv[(int64_t)i * lv_stride + d], mu_bar, l_bar, v_bar);
-            a0 += e.v;
-            a1 += e.r;
-            a2 += e.v * e.r;
-            a3 += e.mc;
-            a4 += e.mc * e.mc;
-            a5 += e.r * e.mc;
-            a6 += e.r * e.mc * e.mc;
+            if (i >= Bp) break;
+            double es = 0.0, fs = 0.0;
+            if (dok) {
+                float2 xv = make_float2(0.f, 0.f), yv = xv;
+                if (i < B) {
+                    const Elem e = make_elem(mu[(int64_t)i * mu_stride + d], lv[(int64_t)i * lv_stride + d], mu_bar, l_bar, v_bar);
+                    const double sq = e.mc * e.mc;
+                    const double s = sq / v_bar;
+                    const double t = e.a + (2.0 * e.b + e.b * e.b) * (1.0 + e.a);  // r^2 v v_bar - 1
+                    xv = make_float2((float)(e.a + s), (float)e.mc);
+                    yv = make_float2((float)e.b, (float)(-2.0 * e.mc * e.r));
+                    Vp[(int64_t)i * D + d] = make_float4((float)e.mc, (float)e.a, (float)e.b, (float)t);
+                    es = (e.a - e.alpha) + s;
+                    fs = (e.b + e.alpha) + sq * e.r;
+                    a0 += e.v;
+                    a1 += e.r;
+                    a2 += e.v * e.r;
+                    a3 += e.mc;
+                    a4 += sq;
+                    a5 += e.r * e.mc;
+                    a6 += e.r * sq;
+                }
+                *reinterpret_cast<float2*>(Xp + (int64_t)i * Kp + 2 * d) = xv;
+                *reinterpret_cast<float2*>(Yp + (int64_t)i * Kp + 2 * d) = yv;
+            }
+            es = warp_sum(es);
+            fs = warp_sum(fs);
+            if (lane == 0) {
+                row_e[r] += es;
+                row_f[r] += fs;
+            }
         }
-        double* p = part + (int64_t)blk * 7 * D + d;
-        p[0 * (int64_t)D] = a0;
-        p[1 * (int64_t)D] = a1;
-        p[2 * (int64_t)D] = a2;
-        p[3 * (int64_t)D] = a3;
-        p[4 * (int64_t)D] = a4;
-        p[5 * (int64_t)D] = a5;
-        p[6 * (int64_t)D] = a6;
+        col_part[w][0][lane] = a0;
+        col_part[w][1][lane] = a1;
+        col_part[w][2][lane] = a2;
+        col_part[w][3][lane] = a3;
+        col_part[w][4][lane] = a4;
+        col_part[w][5][lane] = a5;
+        col_part[w][6][lane] = a6;
+        __syncthreads();
+        if (tid < 7 * 32) {
+            const int q = tid >> 5, l = tid & 31;
+            if (ch * 32 + l < D) {
+                double t = 0.0;
+#pragma unroll
+                for (int ww = 0; ww < kWarps; ++ww) t += col_part[ww][q][l];
+                part[((int64_t)blk * 7 + q) * D + ch * 32 + l] = t;
+            }
+        }
+        __syncthreads();
+    }
+    // zero the K padding of the panels and publish the row sums
+    for (int r = w; r < R; r += kWarps) {
+        const int i = i0 + r;
+        if (i >= Bp) break;
+        for (int k = 2 * D + lane; k < Kp; k += 32) {
+            Xp[(int64_t)i * Kp + k] = 0.f;
+            Yp[(int64_t)i * Kp + k] = 0.f;
+        }
+        if (lane == 0) {
+            evec[i] = (float)row_e[r];
+            fvec[i] = (float)row_f[r];
+        }
     }
 
     __threadfence();
@@ -609,8 +636,9 @@ extern "C" int mae_mpd_prepare(const float* mu, int64_t mu_stride, const float* 
     int rc = check_common(B, D, workspace, workspace_bytes, L);
     if (rc != MAE_OK) return rc;
     MAE_REQUIRE(mu_stride >= D && logvar_stride >= D, MAE_ERR_STRIDE);
-    mpd_prepare_kernel<<<(unsigned)L.nblk, kNT, 0, as_stream(stream)>>>(
-        mu, mu_stride, logvar, logvar_stride, (int)B, (int)D, (int)L.Kp, at<float>(workspace, L.xp), at<float>(workspace, L.yp),
+    mpd_prepare_kernel<<<(unsigned)L.prep_grid, kNT, (size_t)(2 * L.prep_rows * sizeof(double)), as_stream(stream)>>>(
+        mu, mu_stride, logvar, logvar_stride, (int)B, (int)D, (int)L.Kp, (int)L.prep_rows, (int)L.Bp,
+        at<float>(workspace, L.xp), at<float>(workspace, L.yp),
         at<float4>(workspace, L.vp), at<float>(workspace, L.c), at<float>(workspace, L.l), at<double>(workspace, L.part_prep),
         at<double>(workspace, L.colstats), at<double>(workspace, L.pivots), at<Hdr>(workspace, L.hdr), m_d);
     return launch_status();
