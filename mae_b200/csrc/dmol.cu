@@ -1,18 +1,30 @@
 // A4b + A4c: discretized mixture of logistics straight from the raw NCHW decoder output
 // (color_image_decoder.py:38-52, 91-125; utils.py:61-123).
 //
-// Layout: raw [N, 10*nmix, HW].  One thread owns one pixel of one sample and walks the nmix
-// components; for a fixed channel the 32 lanes of a warp read 32 consecutive pixels (one 128 B line),
-// so every global access is fully coalesced and each byte of `raw` is read exactly once by the
-// forward (HBM-bound; SURVEY.md §8d: 4*(10*nmix*HW*N + 3*HW*B + N) bytes).  The backward recomputes
-// the forward (second read of `raw` is served by L1/L2) and writes d raw once.
+// Layout: raw [N, 10*nmix, HW].  For a fixed channel the 32 lanes of a warp read 32 consecutive pixels
+// (one 128 B line), so every global access is fully coalesced and each byte of `raw` is read exactly
+// once by the forward (HBM-bound; SURVEY.md §8d: 4*(10*nmix*HW*N + 3*HW*B + N) bytes).
+//
+// Work decomposition (templated kernels, nmix = 10 and HW in {1024, 4096} so that every channel offset
+// is an immediate):  a CTA owns G groups of 32 consecutive pixels of one sample; each group is served
+// by SPLIT warps, warp `part` evaluating mixture components part, part+SPLIT, ...  The per-part
+// log-sum-exp states are merged through shared memory.  SPLIT is chosen from the amount of work:
+//   SPLIT = 1 (one thread per pixel, no merge)      large launches: IW-NLL evaluation, >= 512 Ki pixels
+//   SPLIT = 2 / 5                                   training batches: B = 64 gives only 64 Ki pixels, one
+//                                                   thread per pixel would leave 3/4 of the SM's warp slots
+//                                                   empty and expose DRAM + MUFU latency
+// All component parameters of a thread are loaded before any arithmetic (memory-level parallelism).
+// The backward keeps the per-component local gradients in registers when a thread owns <= 5 components
+// (SPLIT >= 2) and recomputes them otherwise; d raw is written exactly once with streaming stores.
+// Any other (nmix, HW) runs on the generic one-thread-per-pixel kernels.
 #include "common.cuh"
 #include "hot_math.cuh"
 
 namespace mae {
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 256;   // generic kernels
+constexpr int kMinPixPerCta = 64;
 
 // Load/store policies for hot_math.cuh's pixel routines (host branch only exists so the shared
 // __host__ __device__ templates instantiate cleanly; it is never executed).
@@ -44,12 +56,35 @@ struct StStream {
     }
 };
 
-// grid: (N, chunks) with chunks = ceil(HW / kThreads).  err[n] = -sum_pix [ LSE_m(T_m + logit_m) - LSE_m(logit_m) ].
-// Cross-CTA reduction of the per-chunk partials is ordered (ticket; the last CTA of a sample adds the
-// partials in chunk order), so the result is bit-reproducible.
+// Ordered cross-CTA reduction of per-CTA partial sums of one sample (ticket; the last CTA of the sample adds
+// the partials in chunk order) -> bit-reproducible err[n].
+__device__ __forceinline__ void publish_partial(float val, int64_t n, int chunk, int chunks, float* __restrict__ err,
+                                                float* partial, unsigned int* tickets, bool* is_last_smem) {
+    if (chunks == 1) {
+        if (threadIdx.x == 0) err[n] = val;
+        return;
+    }
+    if (threadIdx.x == 0) {
+        partial[n * chunks + chunk] = val;
+        __threadfence();
+        const unsigned int t = atomicAdd(&tickets[n], 1u);
+        *is_last_smem = (t == (unsigned int)(chunks - 1));
+    }
+    __syncthreads();
+    if (*is_last_smem && threadIdx.x == 0) {
+        __threadfence();
+        float tot = 0.f;
+        for (int c = 0; c < chunks; ++c) tot += __ldcg(partial + n * chunks + c);
+        err[n] = tot;
+        tickets[n] = 0u;  // self-reset for the next call
+    }
+}
+
+// ------------------------------------------------------------------------------------ generic kernels
+// grid: (N, chunks) with chunks = ceil(HW / kThreads); one thread per pixel walks all components.
 __global__ void __launch_bounds__(kThreads)
-dmol_fwd_kernel(const float* __restrict__ raw, const float* __restrict__ x, int ns, int nmix, int HW, int chunks,
-                float* __restrict__ err, float* partial, unsigned int* tickets) {
+dmol_fwd_generic_kernel(const float* __restrict__ raw, const float* __restrict__ x, int ns, int nmix, int HW, int chunks,
+                        float* __restrict__ err, float* partial, unsigned int* tickets) {
     __shared__ float scratch[32];
     __shared__ bool is_last;
     const int64_t n = blockIdx.x;
@@ -64,31 +99,12 @@ dmol_fwd_kernel(const float* __restrict__ raw, const float* __restrict__ x, int 
         val = hm::dmol_pixel_fwd<LdStream>(base, HW, nmix, xs, nullptr, nullptr);
     }
     val = block_sum(val, scratch);
-    if (chunks == 1) {
-        if (threadIdx.x == 0) err[n] = val;
-        return;
-    }
-    if (threadIdx.x == 0) {
-        partial[n * chunks + blockIdx.y] = val;
-        __threadfence();
-        const unsigned int t = atomicAdd(&tickets[n], 1u);
-        is_last = (t == (unsigned int)(chunks - 1));
-    }
-    __syncthreads();
-    if (is_last && threadIdx.x == 0) {
-        __threadfence();
-        float tot = 0.f;
-        for (int c = 0; c < chunks; ++c) tot += __ldcg(partial + n * chunks + c);
-        err[n] = tot;
-        tickets[n] = 0u;  // self-reset for the next call
-    }
+    publish_partial(val, n, blockIdx.y, chunks, err, partial, tickets, &is_last);
 }
 
-// d raw = g[n] * d err[n] / d raw.  Pass 1 recomputes both log-sum-exps, pass 2 recomputes each component
-// with its local gradient and scales it by the component's responsibility.
 __global__ void __launch_bounds__(kThreads)
-dmol_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ x, const float* __restrict__ g, int ns, int nmix,
-                int HW, float* __restrict__ draw) {
+dmol_bwd_generic_kernel(const float* __restrict__ raw, const float* __restrict__ x, const float* __restrict__ g, int ns,
+                        int nmix, int HW, float* __restrict__ draw) {
     const int64_t n = blockIdx.x;
     const int64_t b = n / ns;
     const int pix = blockIdx.y * kThreads + threadIdx.x;
@@ -100,11 +116,220 @@ dmol_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ x, cons
     hm::dmol_pixel_bwd<LdCached, StStream>(raw + off, draw + off, HW, nmix, xs, g[n]);
 }
 
+// ---------------------------------------------------------------------------------- specialised kernels
+template <int NMIX, int SPLIT>
+struct Geo {
+    static constexpr int kK = (NMIX + SPLIT - 1) / SPLIT;             // components per thread (upper bound)
+    static constexpr int kG = SPLIT == 1 ? 8 : (SPLIT == 2 ? 4 : 2);  // pixel groups per CTA
+    static constexpr int kThreadsCta = 32 * SPLIT * kG;
+    static constexpr int kPix = 32 * kG;                              // pixels per CTA
+};
+
+struct Comp {
+    float logit, mu[3], rho[3], kap[3];
+};
+
+// the 10 parameters of component m = part + k*SPLIT of this thread's pixel: independent coalesced loads at
+// immediate offsets from  lg = pbase + part*HW  and  pr = pbase + 3*part*HW  (pbase = raw + n*10*NMIX*HW + pix)
+template <int NMIX, int HW, int SPLIT>
+__device__ __forceinline__ void load_component(const float* __restrict__ lg, const float* __restrict__ pr, int k, Comp& cp) {
+    cp.logit = ldg_stream(lg + k * SPLIT * HW);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float* q = pr + (3 * k * SPLIT + c) * HW;
+        cp.mu[c] = ldg_stream(q + NMIX * HW);
+        cp.rho[c] = ldg_stream(q + 4 * NMIX * HW);
+        cp.kap[c] = ldg_stream(q + 7 * NMIX * HW);
+    }
+}
+
+// all parameters of the K components of this thread, issued back to back (K*10 independent loads in flight)
+template <int NMIX, int HW, int SPLIT>
+__device__ __forceinline__ void load_components(const float* __restrict__ pbase, int part, Comp (&cp)[Geo<NMIX, SPLIT>::kK]) {
+    const float* lg = pbase + part * HW;
+    const float* pr = pbase + 3 * part * HW;
+#pragma unroll
+    for (int k = 0; k < Geo<NMIX, SPLIT>::kK; ++k) {
+        if (NMIX % SPLIT != 0 && part + k * SPLIT >= NMIX) continue;
+        load_component<NMIX, HW, SPLIT>(lg, pr, k, cp[k]);
+    }
+}
+
+// two-pass log-sum-exp over <= K values held in registers: returns (max, sum of exp(v - max))
+template <int K>
+__device__ __forceinline__ void lse_local(const float (&v)[K], int count, float& mx, float& sm) {
+    mx = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+        if (k < count) mx = fmaxf(mx, v[k]);
+    sm = 0.f;
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+        if (k < count) sm += hm::fast_ex2(hm::kLog2e * (v[k] - mx));
+}
+
+// merge the SPLIT partial (max,sum) pairs of a pixel, published in shared memory as st[part][lane]
+template <int SPLIT>
+__device__ __forceinline__ float lse_merge(const float (*mxs)[32], const float (*sms)[32], int lane) {
+    float mx = mxs[0][lane];
+#pragma unroll
+    for (int p = 1; p < SPLIT; ++p) mx = fmaxf(mx, mxs[p][lane]);
+    float sm = 0.f;
+#pragma unroll
+    for (int p = 0; p < SPLIT; ++p) sm = fmaf(sms[p][lane], hm::fast_ex2(hm::kLog2e * (mxs[p][lane] - mx)), sm);
+    return fmaf(hm::fast_lg2(sm), hm::kLn2, mx);
+}
+
+template <int NMIX, int SPLIT>
+struct MergeSmem {
+    float mt[Geo<NMIX, SPLIT>::kG][SPLIT][32], st[Geo<NMIX, SPLIT>::kG][SPLIT][32];
+    float ml[Geo<NMIX, SPLIT>::kG][SPLIT][32], sl[Geo<NMIX, SPLIT>::kG][SPLIT][32];
+};
+
+// grid: (N, HW / kPix).  HW is a multiple of kPix (static_assert in the launcher).
+template <int NMIX, int HW, int SPLIT>
+__global__ void __launch_bounds__(Geo<NMIX, SPLIT>::kThreadsCta, SPLIT == 1 ? 4 : 1)
+dmol_fwd_kernel(const float* __restrict__ raw, const float* __restrict__ x, int ns, int chunks, float* __restrict__ err,
+                float* partial, unsigned int* tickets) {
+    using G = Geo<NMIX, SPLIT>;
+    __shared__ MergeSmem<NMIX, SPLIT> ms;
+    __shared__ float scratch[32];
+    __shared__ bool is_last;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int part = w % SPLIT, grp = w / SPLIT;
+    const int64_t n = blockIdx.x;
+    const int64_t b = n / ns;
+    const int pix = blockIdx.y * G::kPix + grp * 32 + lane;
+    const int count = (NMIX - part + SPLIT - 1) / SPLIT;
+
+    const float* pbase = raw + n * (int64_t)(10 * NMIX * HW) + pix;
+    float xs[3];
+    float tl[G::kK], lg[G::kK];
+    if (G::kK <= 5) {  // few components per thread: every load in flight before the arithmetic starts
+        Comp cp[G::kK];
+        load_components<NMIX, HW, SPLIT>(pbase, part, cp);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) xs[c] = __ldg(x + (b * 3 + c) * HW + pix);
+#pragma unroll
+        for (int k = 0; k < G::kK; ++k) {
+            if (k < count) {
+                lg[k] = cp[k].logit;
+                tl[k] = hm::dmol_component<false>(cp[k].mu, cp[k].rho, cp[k].kap, xs, nullptr, nullptr, nullptr) + cp[k].logit;
+            }
+        }
+    } else {  // one thread per pixel: rolling window, component k+2 is loaded while component k is evaluated
+        const float* plg = pbase + part * HW;
+        const float* ppr = pbase + 3 * part * HW;
+        Comp c0, c1, c2;
+        load_component<NMIX, HW, SPLIT>(plg, ppr, 0, c0);
+        load_component<NMIX, HW, SPLIT>(plg, ppr, 1, c1);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) xs[c] = __ldg(x + (b * 3 + c) * HW + pix);
+#pragma unroll
+        for (int k = 0; k < G::kK; ++k) {
+            if (k + 2 < G::kK) load_component<NMIX, HW, SPLIT>(plg, ppr, k + 2, c2);
+            lg[k] = c0.logit;
+            tl[k] = hm::dmol_component<false>(c0.mu, c0.rho, c0.kap, xs, nullptr, nullptr, nullptr) + c0.logit;
+            c0 = c1;
+            c1 = c2;
+        }
+    }
+    float mt, st, ml, sl;
+    lse_local<G::kK>(tl, count, mt, st);
+    lse_local<G::kK>(lg, count, ml, sl);
+    float val = 0.f;
+    if (SPLIT == 1) {
+        val = fmaf(hm::fast_lg2(sl), hm::kLn2, ml) - fmaf(hm::fast_lg2(st), hm::kLn2, mt);
+    } else {
+        ms.mt[grp][part][lane] = mt;
+        ms.st[grp][part][lane] = st;
+        ms.ml[grp][part][lane] = ml;
+        ms.sl[grp][part][lane] = sl;
+        __syncthreads();
+        if (part == 0) val = lse_merge<SPLIT>(ms.ml[grp], ms.sl[grp], lane) - lse_merge<SPLIT>(ms.mt[grp], ms.st[grp], lane);
+    }
+    val = block_sum(val, scratch);
+    publish_partial(val, n, blockIdx.y, chunks, err, partial, tickets, &is_last);
+}
+
+template <int NMIX, int HW, int SPLIT>
+__global__ void __launch_bounds__(Geo<NMIX, SPLIT>::kThreadsCta)
+dmol_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ x, const float* __restrict__ g, int ns,
+                float* __restrict__ draw) {
+    using G = Geo<NMIX, SPLIT>;
+    constexpr bool kCache = G::kK <= 5;  // keep local gradients in registers instead of recomputing
+    __shared__ MergeSmem<NMIX, SPLIT> ms;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int part = w % SPLIT, grp = w / SPLIT;
+    const int64_t n = blockIdx.x;
+    const int64_t b = n / ns;
+    const int pix = blockIdx.y * G::kPix + grp * 32 + lane;
+    const int count = (NMIX - part + SPLIT - 1) / SPLIT;
+    const int64_t off = n * (int64_t)(10 * NMIX * HW) + pix;
+
+    Comp cp[G::kK];
+    load_components<NMIX, HW, SPLIT>(raw + off, part, cp);
+    float xs[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) xs[c] = __ldg(x + (b * 3 + c) * HW + pix);
+    const float gn = __ldg(g + n);
+
+    float tl[G::kK], lg[G::kK];
+    float gmu[kCache ? G::kK : 1][3], grho[kCache ? G::kK : 1][3], gkap[kCache ? G::kK : 1][3];
+#pragma unroll
+    for (int k = 0; k < G::kK; ++k) {
+        if (k < count) {
+            lg[k] = cp[k].logit;
+            float T;
+            if (kCache) T = hm::dmol_component<true>(cp[k].mu, cp[k].rho, cp[k].kap, xs, gmu[kCache ? k : 0], grho[kCache ? k : 0], gkap[kCache ? k : 0]);
+            else T = hm::dmol_component<false>(cp[k].mu, cp[k].rho, cp[k].kap, xs, nullptr, nullptr, nullptr);
+            tl[k] = T + cp[k].logit;
+        }
+    }
+    float mt, st, ml, sl, zt, zl;
+    lse_local<G::kK>(tl, count, mt, st);
+    lse_local<G::kK>(lg, count, ml, sl);
+    if (SPLIT == 1) {
+        zt = fmaf(hm::fast_lg2(st), hm::kLn2, mt);
+        zl = fmaf(hm::fast_lg2(sl), hm::kLn2, ml);
+    } else {
+        ms.mt[grp][part][lane] = mt;
+        ms.st[grp][part][lane] = st;
+        ms.ml[grp][part][lane] = ml;
+        ms.sl[grp][part][lane] = sl;
+        __syncthreads();
+        zt = lse_merge<SPLIT>(ms.mt[grp], ms.st[grp], lane);
+        zl = lse_merge<SPLIT>(ms.ml[grp], ms.sl[grp], lane);
+    }
+
+    float* ob = draw + off;
+    float* olg = ob + part * HW;
+    float* opr = ob + 3 * part * HW;
+#pragma unroll
+    for (int k = 0; k < G::kK; ++k) {
+        if (k < count) {
+            float lmu[3], lrho[3], lkap[3];
+            if (!kCache) hm::dmol_component<true>(cp[k].mu, cp[k].rho, cp[k].kap, xs, lmu, lrho, lkap);
+            const float wgt = hm::fast_ex2(hm::kLog2e * (tl[k] - zt));  // responsibility of the component
+            const float pri = hm::fast_ex2(hm::kLog2e * (lg[k] - zl));  // softmax(logits)
+            const float a = -gn * wgt;                                  // d err / d T_m
+            stg_stream(olg + k * SPLIT * HW, gn * (pri - wgt));
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                float* q = opr + (3 * k * SPLIT + c) * HW;
+                stg_stream(q + NMIX * HW, a * (kCache ? gmu[kCache ? k : 0][c] : lmu[c]));
+                stg_stream(q + 4 * NMIX * HW, a * (kCache ? grho[kCache ? k : 0][c] : lrho[c]));
+                stg_stream(q + 7 * NMIX * HW, a * (kCache ? gkap[kCache ? k : 0][c] : lkap[c]));
+            }
+        }
+    }
+}
+
 struct DmolWs {
     int64_t partial_off, ticket_off, total;
 };
 DmolWs dmol_ws(int64_t N, int64_t HW) {
-    const int64_t chunks = ceil_div(HW, kThreads);
+    const int64_t chunks = ceil_div(HW, kMinPixPerCta);  // upper bound over every kernel variant
     DmolWs w;
     w.partial_off = 0;
     w.ticket_off = round_up(N * chunks * (int64_t)sizeof(float), 256);
@@ -115,8 +340,50 @@ DmolWs dmol_ws(int64_t N, int64_t HW) {
 int check_dmol(int64_t B, int64_t ns, int64_t nmix, int64_t HW) {
     MAE_REQUIRE(B > 0 && ns > 0 && nmix > 0 && HW > 0, MAE_ERR_SHAPE);
     MAE_REQUIRE(B * ns < (1ll << 31) && nmix <= 1024 && HW < (1ll << 24), MAE_ERR_SHAPE);
-    MAE_REQUIRE(ceil_div(HW, kThreads) <= 65535, MAE_ERR_SHAPE);
+    MAE_REQUIRE(ceil_div(HW, kMinPixPerCta) <= 65535, MAE_ERR_SHAPE);
     return MAE_OK;
+}
+
+// SPLIT from the number of pixel-threads a launch would have: fill ~2 waves of the 148 x 2048 thread slots
+int pick_split(int64_t pixels) {
+    if (pixels >= (1ll << 19)) return 1;
+    if (pixels >= (1ll << 17)) return 2;
+    return 5;
+}
+
+template <int NMIX, int HW, int SPLIT>
+int launch_fwd(const float* raw, const float* x, int64_t N, int ns, float* err, float* partial, unsigned int* tickets,
+               cudaStream_t s) {
+    using G = Geo<NMIX, SPLIT>;
+    static_assert(HW % G::kPix == 0, "HW must be a multiple of the CTA pixel count");
+    const int chunks = HW / G::kPix;
+    dim3 grid((unsigned)N, (unsigned)chunks);
+    dmol_fwd_kernel<NMIX, HW, SPLIT><<<grid, G::kThreadsCta, 0, s>>>(raw, x, ns, chunks, err, partial, tickets);
+    return launch_status();
+}
+
+template <int NMIX, int HW, int SPLIT>
+int launch_bwd(const float* raw, const float* x, const float* g, int64_t N, int ns, float* draw, cudaStream_t s) {
+    using G = Geo<NMIX, SPLIT>;
+    dim3 grid((unsigned)N, (unsigned)(HW / G::kPix));
+    dmol_bwd_kernel<NMIX, HW, SPLIT><<<grid, G::kThreadsCta, 0, s>>>(raw, x, g, ns, draw);
+    return launch_status();
+}
+
+template <int HW>
+int dispatch_fwd(int split, const float* raw, const float* x, int64_t N, int ns, float* err, float* partial,
+                 unsigned int* tickets, cudaStream_t s) {
+    switch (split) {
+        case 1: return launch_fwd<10, HW, 1>(raw, x, N, ns, err, partial, tickets, s);
+        case 2: return launch_fwd<10, HW, 2>(raw, x, N, ns, err, partial, tickets, s);
+        default: return launch_fwd<10, HW, 5>(raw, x, N, ns, err, partial, tickets, s);
+    }
+}
+template <int HW>
+int dispatch_bwd(int split, const float* raw, const float* x, const float* g, int64_t N, int ns, float* draw, cudaStream_t s) {
+    // the backward always splits a pixel over >= 2 warps so the local gradients stay in registers
+    if (split <= 2) return launch_bwd<10, HW, 2>(raw, x, g, N, ns, draw, s);
+    return launch_bwd<10, HW, 5>(raw, x, g, N, ns, draw, s);
 }
 
 }  // namespace
@@ -134,19 +401,20 @@ extern "C" int mae_dmol_fwd(const float* raw, const float* x, int64_t B, int64_t
     int rc = check_dmol(B, ns, nmix, HW);
     if (rc != MAE_OK) return rc;
     const int64_t N = B * ns;
-    const int64_t chunks = ceil_div(HW, kThreads);
     const DmolWs w = dmol_ws(N, HW);
-    float* partial = nullptr;
-    unsigned int* tickets = nullptr;
-    if (chunks > 1) {
-        MAE_REQUIRE(workspace != nullptr, MAE_ERR_NULL);
-        MAE_REQUIRE(workspace_bytes >= w.total, MAE_ERR_WORKSPACE);
-        partial = reinterpret_cast<float*>(static_cast<char*>(workspace) + w.partial_off);
-        tickets = reinterpret_cast<unsigned int*>(static_cast<char*>(workspace) + w.ticket_off);
+    MAE_REQUIRE(workspace != nullptr, MAE_ERR_NULL);
+    MAE_REQUIRE(workspace_bytes >= w.total, MAE_ERR_WORKSPACE);
+    float* partial = reinterpret_cast<float*>(static_cast<char*>(workspace) + w.partial_off);
+    unsigned int* tickets = reinterpret_cast<unsigned int*>(static_cast<char*>(workspace) + w.ticket_off);
+    cudaStream_t s = as_stream(stream);
+    if (nmix == 10 && (HW == 1024 || HW == 4096)) {
+        const int split = pick_split(N * HW);
+        return HW == 1024 ? dispatch_fwd<1024>(split, raw, x, N, (int)ns, err, partial, tickets, s)
+                          : dispatch_fwd<4096>(split, raw, x, N, (int)ns, err, partial, tickets, s);
     }
+    const int64_t chunks = ceil_div(HW, kThreads);
     dim3 grid((unsigned)N, (unsigned)chunks);
-    dmol_fwd_kernel<<<grid, kThreads, 0, as_stream(stream)>>>(raw, x, (int)ns, (int)nmix, (int)HW, (int)chunks, err, partial,
-                                                             tickets);
+    dmol_fwd_generic_kernel<<<grid, kThreads, 0, s>>>(raw, x, (int)ns, (int)nmix, (int)HW, (int)chunks, err, partial, tickets);
     return launch_status();
 }
 
@@ -157,7 +425,13 @@ extern "C" int mae_dmol_bwd(const float* raw, const float* x, const float* g, in
     int rc = check_dmol(B, ns, nmix, HW);
     if (rc != MAE_OK) return rc;
     const int64_t N = B * ns;
+    cudaStream_t s = as_stream(stream);
+    if (nmix == 10 && (HW == 1024 || HW == 4096)) {
+        const int split = pick_split(N * HW);
+        return HW == 1024 ? dispatch_bwd<1024>(split, raw, x, g, N, (int)ns, draw, s)
+                          : dispatch_bwd<4096>(split, raw, x, g, N, (int)ns, draw, s);
+    }
     dim3 grid((unsigned)N, (unsigned)ceil_div(HW, kThreads));
-    dmol_bwd_kernel<<<grid, kThreads, 0, as_stream(stream)>>>(raw, x, g, (int)ns, (int)nmix, (int)HW, draw);
+    dmol_bwd_generic_kernel<<<grid, kThreads, 0, s>>>(raw, x, g, (int)ns, (int)nmix, (int)HW, draw);
     return launch_status();
 }

@@ -270,6 +270,13 @@ __device__ __forceinline__ void stage_slab(const float* __restrict__ panel, int6
     dst[kq + 3][r] = a.w;
 }
 
+__device__ __forceinline__ void put_slab(float (*dst)[kLd], int r, int kq, const float4& a) {
+    dst[kq + 0][r] = a.x;
+    dst[kq + 1][r] = a.y;
+    dst[kq + 2][r] = a.z;
+    dst[kq + 3][r] = a.w;
+}
+
 __device__ __forceinline__ void fma_tile(const float (*A)[kLd], const float (*Bm)[kLd], int ty, int tx, float acc[4][4]) {
 #pragma unroll
     for (int k = 0; k < kKC; ++k) {
@@ -290,8 +297,8 @@ mpd_fwd_kernel(const float* __restrict__ Xp, const float* __restrict__ Yp, const
                const float* __restrict__ fvec, Hdr* hdr, double* part, int B, int D, int Kp, int row0, int row1, int tr0,
                int ntr, int ntc, float* __restrict__ KL, float* __restrict__ KLT, int Bp, double* __restrict__ sumsq_out,
                float* __restrict__ S_out) {
-    __shared__ __align__(16) float As[kKC][kLd];
-    __shared__ __align__(16) float Bs[kKC][kLd];
+    __shared__ __align__(16) float As[2][kKC][kLd];
+    __shared__ __align__(16) float Bs[2][kKC][kLd];
     __shared__ double scratch[32];
     __shared__ bool is_last;
     const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
@@ -305,12 +312,26 @@ mpd_fwd_kernel(const float* __restrict__ Xp, const float* __restrict__ Yp, const
         for (int i = 0; i < 4; ++i)
 #pragma unroll
             for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-        for (int k0 = 0; k0 < Kp; k0 += kKC) {
-            stage_slab(Xp, (int64_t)ti * kT, Kp, k0, As, tid);
-            stage_slab(Yp, (int64_t)tj * kT, Kp, k0, Bs, tid);
-            __syncthreads();
-            fma_tile(As, Bs, ty, tx, acc);
-            __syncthreads();
+        // K loop: the next slab is fetched into registers while the current one is multiplied
+        {
+            const int r = tid >> 2, kq = (tid & 3) * 4;
+            const float* xa = Xp + ((int64_t)ti * kT + r) * Kp + kq;
+            const float* yb = Yp + ((int64_t)tj * kT + r) * Kp + kq;
+            float4 ra = *reinterpret_cast<const float4*>(xa);
+            float4 rb = *reinterpret_cast<const float4*>(yb);
+            int buf = 0;
+            for (int k0 = 0; k0 < Kp; k0 += kKC) {
+                put_slab(As[buf], r, kq, ra);
+                put_slab(Bs[buf], r, kq, rb);
+                __syncthreads();
+                if (k0 + kKC < Kp) {
+                    ra = *reinterpret_cast<const float4*>(xa + k0 + kKC);
+                    rb = *reinterpret_cast<const float4*>(yb + k0 + kKC);
+                }
+                fma_tile(As[buf], Bs[buf], ty, tx, acc);
+                buf ^= 1;
+            }
+            __syncthreads();  // all reads of the last slab done before the next tile overwrites buffer 0/1
         }
         float psum = 0.f;
         const int jb = tj * kT + tx * 4;
@@ -345,7 +366,10 @@ mpd_fwd_kernel(const float* __restrict__ Xp, const float* __restrict__ Yp, const
         total += (double)psum;
     }
     total = block_sum(total, scratch);
-    if (tid == 0) {
+    if (gridDim.x == 1) {  // single CTA: nothing to combine
+        is_last = true;
+        if (tid == 0) part[0] = total;
+    } else if (tid == 0) {
         part[blockIdx.x] = total;
         __threadfence();
         const unsigned int t = atomicAdd(&hdr->ticket_fwd, 1u);
@@ -355,7 +379,9 @@ mpd_fwd_kernel(const float* __restrict__ Xp, const float* __restrict__ Yp, const
     if (is_last && tid == 0) {
         __threadfence();
         double s = 0.0;
-        for (int i = 0; i < (int)gridDim.x; ++i) s += __ldcg(part + i);
+        if (gridDim.x == 1) s = total;
+        else
+            for (int i = 0; i < (int)gridDim.x; ++i) s += __ldcg(part + i);
         hdr->sumsq = s;
         sumsq_out[0] = s;
         if (S_out != nullptr) {
@@ -425,14 +451,23 @@ mpd_bwd_small_kernel(const float* __restrict__ mu, int64_t mu_stride, const floa
         const float* kl_row = KL + (int64_t)i * Bp;    // KL_ij
         const float* klt_row = KLT + (int64_t)i * Bp;  // KL_ji
         const float opb_i = 1.0f + pi.z, opt_i = 1.0f + pi.w;
-        for (int j = 0; j < B; ++j) {
-            if (j == i) continue;
-            const float w1 = beta * (kl_row[j] - m);
-            const float w2 = beta * (klt_row[j] - m);
-            const float4 pj = active ? Vp[(int64_t)j * D + d] : zero4;
-            const float dl = pi.x - pj.x;
-            gmu = fmaf(dl, fmaf(w1, 1.0f + pj.z, w2 * opb_i), gmu);
-            glv += w1 * (fmaf(pi.y, pj.z, pi.y) + pj.z) - w2 * (fmaf(pj.y, pi.w, pj.y) + pi.w + dl * dl * opt_i * ivb);
+        const float4* vcol = Vp + d;
+        for (int jb = 0; jb < B; jb += 32) {
+            // the 32 lanes fetch the weights of 32 partners at once (one coalesced line each), then broadcast
+            const int jl = jb + lane;
+            const bool ok = jl < B && jl != i;
+            const float w1l = ok ? beta * (kl_row[jl] - m) : 0.f;
+            const float w2l = ok ? beta * (klt_row[jl] - m) : 0.f;
+            const int nj = min(32, B - jb);
+#pragma unroll 8
+            for (int jj = 0; jj < nj; ++jj) {
+                const float w1 = __shfl_sync(0xffffffffu, w1l, jj);
+                const float w2 = __shfl_sync(0xffffffffu, w2l, jj);
+                const float4 pj = active ? vcol[(int64_t)(jb + jj) * D] : zero4;
+                const float dl = pi.x - pj.x;
+                gmu = fmaf(dl, fmaf(w1, 1.0f + pj.z, w2 * opb_i), gmu);
+                glv += w1 * (fmaf(pi.y, pj.z, pi.y) + pj.z) - w2 * (fmaf(pj.y, pi.w, pj.y) + pi.w + dl * dl * opt_i * ivb);
+            }
         }
         gmu *= ivb;
         glv *= 0.5f;

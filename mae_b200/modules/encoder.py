@@ -167,12 +167,15 @@ class GaussianEncoder(Encoder):
         return z, (z_normal, logdet)
 
     # -- MPD --------------------------------------------------------------------------------------------
-    def _postKL(self, mu, logvar):
+    def _postKL(self, mu, logvar, side_stream=False):
         """(m_d [*z], S []).  Reference: gaussian_encoder.py:162-188; tiled CUDA kernels, never [B,B,D]."""
-        return ops.mpd(mu, logvar)
+        return ops.mpd(mu, logvar, side_stream=side_stream)
 
-    def encode(self, x, nsamples):
-        """-> z [B,ns,*z], KL [B], (m_d [*z], S []).  Reference: gaussian_encoder.py:190-229."""
+    def encode(self, x, nsamples, _side_stream=False):
+        """-> z [B,ns,*z], KL [B], (m_d [*z], S []).  Reference: gaussian_encoder.py:190-229.
+
+        ``_side_stream`` (internal, used by ``MAE.loss``): run the MPD kernels on a side stream so that they overlap
+        with the decoder; the caller must consume (m_d, S) through ``ops.assemble_loss`` / ``ops.join_side``."""
         no_flows = self.prior_flow is None and self.posterior_flow is None
         z, distr_params, kl = self._posterior(x, nsamples, want_kl=no_flows)
         mu, logvar = distr_params[0], distr_params[1]
@@ -181,7 +184,7 @@ class GaussianEncoder(Encoder):
             log_p = self.log_probability_prior(z.view(size[0] * size[1], *size[2:])).view(size[0], size[1])
             log_q = self.log_probability_posterior(x, z, distr_params=distr_params)
             kl = (log_q - log_p).mean(dim=1)
-        return z, kl, self._postKL(mu, logvar)
+        return z, kl, self._postKL(mu, logvar, side_stream=_side_stream)
 
     # -- log densities -----------------------------------------------------------------------------------
     def log_probability_prior(self, z, distr_params=None):

@@ -12,7 +12,7 @@ import torch.nn as nn
 
 from .. import ops
 from .decoder import Decoder
-from .encoder import Encoder
+from .encoder import Encoder, GaussianEncoder
 
 
 class MAE(nn.Module):
@@ -44,12 +44,15 @@ class MAE(nn.Module):
 
         Reference: mae/modules/mae.py:100-140.  ``loss`` carries the gradient; the other entries are logging
         values (the reference's training loops only ``.sum()``/print them)."""
-        z, KL, (m_d, S) = self.encode(x, nsamples)
+        if isinstance(self.encoder, GaussianEncoder):
+            z, KL, (m_d, S) = self.encoder.encode(x, nsamples, _side_stream=True)   # MPD overlaps with the decoder
+        else:
+            z, KL, (m_d, S) = self.encode(x, nsamples)
         err = self.decoder.reconstruct_error(x, z.view(z.size(0), z.size(1), *self.decoder.z_shape()))
         loss, stats, recon = ops.assemble_loss(err, KL, m_d, S, eta, gamma, free_bits)
         loss_mean = stats[1] if eta > 0. else 0.
         loss_std = stats[2] if gamma > 0. else 0.
-        return loss, recon, KL, stats[0], S.detach(), loss_mean, loss_std
+        return loss, recon, KL, stats[0], S, loss_mean, loss_std
 
     def reconstruct(self, x, k=50, random_sample=False):
         z, _ = self.sample_from_posterior(x, nsamples=k)

@@ -15,7 +15,7 @@ from . import _lib
 
 __all__ = [
     "reparam_kl", "mpd", "mpd_forward_only", "bernoulli_recon_error", "dmol_recon_error", "log_prob_prior",
-    "log_prob_posterior", "iw_nll", "assemble_loss", "launch_count", "reset_launch_count",
+    "log_prob_posterior", "iw_nll", "assemble_loss", "join_side", "launch_count", "reset_launch_count",
 ]
 
 _launches = 0  # number of kernels of ours enqueued since the last reset (bench.py reports it)
@@ -103,6 +103,32 @@ _pool = _Pool()
 
 
 # ------------------------------------------------------------------------------------------------
+# side stream: the MPD kernels only depend on (mu, logvar), so inside MAE.loss they run concurrently with
+# the decoder conv stack and the likelihood kernels (forward) and with the decoder's backward (backward).
+# ------------------------------------------------------------------------------------------------
+_side_streams: Dict[int, "torch.cuda.Stream"] = {}
+_pending_join: Dict[int, "torch.cuda.Event"] = {}     # forward: MPD results not yet joined into the main stream
+_grads_ready: Dict[int, "torch.cuda.Event"] = {}      # backward: recorded right after the assemble backward kernel
+
+
+def _side_stream(device: torch.device) -> "torch.cuda.Stream":
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    st = _side_streams.get(idx)
+    if st is None:
+        st = torch.cuda.Stream(device=device)
+        _side_streams[idx] = st
+    return st
+
+
+def join_side(device: torch.device) -> None:
+    """Make the current stream wait for MPD work that was launched on the side stream (no-op if none)."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    pending = _pending_join.pop(idx, None)
+    if pending is not None:
+        torch.cuda.current_stream(device).wait_event(pending[0])
+
+
+# ------------------------------------------------------------------------------------------------
 # A1 + A2
 # ------------------------------------------------------------------------------------------------
 class _ReparamKL(torch.autograd.Function):
@@ -153,12 +179,14 @@ def reparam_kl(mu: torch.Tensor, logvar: torch.Tensor, eps: torch.Tensor, want_k
 # ------------------------------------------------------------------------------------------------
 # A3
 # ------------------------------------------------------------------------------------------------
-def _mpd_launch_fwd(mu2, ms, lv2, ls, b, d, ws, store_kl, row0=0, nrows=None):
+def _mpd_alloc_outputs(d: int, dev: torch.device):
+    return (torch.empty(d, device=dev, dtype=torch.float32), torch.empty((), device=dev, dtype=torch.float32),
+            torch.empty(1, device=dev, dtype=torch.float64))
+
+
+def _mpd_launch_fwd(mu2, ms, lv2, ls, b, d, ws, store_kl, outs, row0=0, nrows=None):
     lib = _lib_()
-    dev = mu2.device
-    m_d = torch.empty(d, device=dev, dtype=torch.float32)
-    sumsq = torch.empty(1, device=dev, dtype=torch.float64)
-    s = torch.empty((), device=dev, dtype=torch.float32)
+    m_d, s, sumsq = outs
     nrows = b if nrows is None else nrows
     _lib.check(lib.mae_mpd_prepare(mu2.data_ptr(), ms, lv2.data_ptr(), ls, b, d, ws.data_ptr(), ws.numel(), m_d.data_ptr(),
                                    _stream()), "mae_mpd_prepare")
@@ -170,7 +198,7 @@ def _mpd_launch_fwd(mu2, ms, lv2, ls, b, d, ws, store_kl, row0=0, nrows=None):
 
 class _MPD(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, mu, logvar, bwd_path):
+    def forward(ctx, mu, logvar, bwd_path, side):
         ctx.set_materialize_grads(False)
         _req_cuda(mu, logvar)
         b = mu.size(0)
@@ -180,44 +208,96 @@ class _MPD(torch.autograd.Function):
         lv2, ls = _rows(logvar)
         d = mu2.size(1)
         lib = _lib_()
-        ws = _pool.take(lib.mae_mpd_workspace_bytes(b, d), mu.device)
+        dev = mu.device
         need_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
         small = b <= 2048 and bwd_path != 2
-        m_d, s, _ = _mpd_launch_fwd(mu2, ms, lv2, ls, b, d, ws, store_kl=need_grad and small)
+        nbytes = lib.mae_mpd_workspace_bytes(b, d)
+        outs = _mpd_alloc_outputs(d, dev)   # owned by the main stream; the side stream only writes them
+        if side:
+            cs = torch.cuda.current_stream(dev)
+            ss = _side_stream(dev)
+            ss.wait_stream(cs)
+            with torch.cuda.stream(ss):
+                ws = _pool.take(nbytes, dev)
+                m_d, s, _ = _mpd_launch_fwd(mu2, ms, lv2, ls, b, d, ws, need_grad and small, outs)
+                ev = torch.cuda.Event()
+                ev.record(ss)
+            # everything the side-stream kernels touch stays referenced until the join
+            _pending_join[dev.index if dev.index is not None else torch.cuda.current_device()] = (ev, (outs, mu2, lv2))
+        else:
+            ws = _pool.take(nbytes, dev)
+            m_d, s, _ = _mpd_launch_fwd(mu2, ms, lv2, ls, b, d, ws, need_grad and small, outs)
         if need_grad:
             ctx.ws = ws
+            ctx.side = bool(side)
             ctx.save_for_backward(mu2, lv2, s)
             ctx.meta = (ms, ls, b, d, mu.shape, logvar.shape, 1 if small else 2)
         else:
-            _pool.give(ws)
+            _MPD._release(ws, dev, side)
         return m_d.view(mu.shape[1:]), s
+
+    @staticmethod
+    def _release(ws, dev, side):
+        if side:
+            with torch.cuda.stream(_side_stream(dev)):
+                _pool.give(ws)
+        else:
+            _pool.give(ws)
 
     @staticmethod
     def backward(ctx, g_m, g_s):
         mu2, lv2, s = ctx.saved_tensors
         ms, ls, b, d, mu_shape, lv_shape, path = ctx.meta
-        ws = ctx.ws
+        ws, side = ctx.ws, ctx.side
+        dev = mu2.device
+        ctx.ws = None
         if g_m is None and g_s is None:
-            ctx.ws = None
-            _pool.give(ws)
-            return None, None, None
+            _MPD._release(ws, dev, side)
+            _grads_ready.pop(dev.index if dev.index is not None else torch.cuda.current_device(), None)
+            return None, None, None, None
         g_m = g_m.contiguous().view(-1) if g_m is not None else None
         g_s = g_s.contiguous() if g_s is not None else None
-        dmu = torch.empty(b, d, device=mu2.device, dtype=torch.float32)
+        dmu = torch.empty(b, d, device=dev, dtype=torch.float32)
         dlv = torch.empty_like(dmu)
-        _lib.check(_lib_().mae_mpd_bwd(mu2.data_ptr(), ms, lv2.data_ptr(), ls, ws.data_ptr(), ws.numel(), b, d, 0, b,
-                                       _ptr(g_m), _ptr(g_s), s.data_ptr(), dmu.data_ptr(), dlv.data_ptr(), 0, path, _stream()),
-                   "mae_mpd_bwd")
-        _count()
-        ctx.ws = None
-        _pool.give(ws)
-        return dmu.view(mu_shape), dlv.view(lv_shape), None
+
+        def launch():
+            _lib.check(_lib_().mae_mpd_bwd(mu2.data_ptr(), ms, lv2.data_ptr(), ls, ws.data_ptr(), ws.numel(), b, d, 0, b,
+                                           _ptr(g_m), _ptr(g_s), s.data_ptr(), dmu.data_ptr(), dlv.data_ptr(), 0, path, _stream()),
+                       "mae_mpd_bwd")
+            _count()
+
+        if side:
+            # run on the side stream as soon as the upstream scalars exist (event recorded by the assemble backward),
+            # concurrently with whatever the main stream already has queued (likelihood / decoder backward)
+            cs = torch.cuda.current_stream(dev)
+            ss = _side_stream(dev)
+            idx = dev.index if dev.index is not None else torch.cuda.current_device()
+            ready = _grads_ready.pop(idx, None)
+            ptrs = {t.data_ptr() for t in (g_m, g_s) if t is not None}
+            if ready is not None and ptrs <= ready[1]:
+                ss.wait_event(ready[0])     # produced by the assemble backward of this pass
+            else:
+                ss.wait_stream(cs)
+            with torch.cuda.stream(ss):
+                launch()
+                _pool.give(ws)
+                ev = torch.cuda.Event()
+                ev.record(ss)
+            cs.wait_event(ev)   # later main-stream work (and any reuse of g_m / g_s memory) is ordered after the kernel
+        else:
+            launch()
+            _pool.give(ws)
+        return dmu.view(mu_shape), dlv.view(lv_shape), None, None
 
 
-def mpd(mu: torch.Tensor, logvar: torch.Tensor, bwd_path: int = 0):
+def mpd(mu: torch.Tensor, logvar: torch.Tensor, bwd_path: int = 0, side_stream: bool = False):
     """Mutual posterior divergence: (m_d with the shape of one latent, S scalar).
-    Reference: GaussianEncoder._postKL, gaussian_encoder.py:162-188.  ``bwd_path``: 0 auto, 1 stored-KL, 2 tiles."""
-    return _MPD.apply(mu, logvar, bwd_path)
+    Reference: GaussianEncoder._postKL, gaussian_encoder.py:162-188.  ``bwd_path``: 0 auto, 1 stored-KL, 2 tiles.
+
+    ``side_stream=True`` launches the kernels on a side stream; the results may only be consumed after
+    :func:`join_side` (``assemble_loss`` does it).  Used by ``MAE.loss`` / ``heads`` to overlap the regulariser with
+    the decoder; the public ``encode()`` keeps the synchronous default."""
+    return _MPD.apply(mu, logvar, bwd_path, side_stream)
 
 
 def mpd_forward_only(mu: torch.Tensor, logvar: torch.Tensor, row0: int = 0, nrows: Optional[int] = None):
@@ -228,7 +308,7 @@ def mpd_forward_only(mu: torch.Tensor, logvar: torch.Tensor, row0: int = 0, nrow
     lv2, ls = _rows(logvar)
     b, d = mu2.shape
     ws = _pool.take(_lib_().mae_mpd_workspace_bytes(b, d), mu.device)
-    m_d, s, sumsq = _mpd_launch_fwd(mu2, ms, lv2, ls, b, d, ws, False, row0, nrows)
+    m_d, s, sumsq = _mpd_launch_fwd(mu2, ms, lv2, ls, b, d, ws, False, _mpd_alloc_outputs(d, mu.device), row0, nrows)
     _pool.give(ws)
     return m_d.view(mu.shape[1:]), s, sumsq
 
@@ -432,6 +512,7 @@ class _Assemble(torch.autograd.Function):
     def forward(ctx, err, kl, m_d, s, eta, gamma, free_bits, inv_batch, ext_sums):
         ctx.set_materialize_grads(False)
         _req_cuda(err, kl, m_d, s, ext_sums)
+        join_side(err.device)  # MPD results may still be in flight on the side stream
         b, ns = err.shape
         err_c, kl_c = err.contiguous(), kl.contiguous()
         m_c = m_d.contiguous().view(-1) if m_d is not None else None
@@ -465,6 +546,10 @@ class _Assemble(torch.autograd.Function):
                                                  b, ns, d, eta, gamma, free_bits, inv_batch, derr.data_ptr(), dkl.data_ptr(),
                                                  _ptr(dm), _ptr(ds), _stream()), "mae_loss_assemble_bwd")
         _count()
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(dev))
+        _grads_ready[dev.index if dev.index is not None else torch.cuda.current_device()] = (
+            ev, {t.data_ptr() for t in (dm, ds) if t is not None})
         return derr, dkl, (dm.view(m_shape) if dm is not None else None), ds, None, None, None, None, None
 
 
