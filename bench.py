@@ -293,7 +293,7 @@ def bench_ours(args):
 
     def k_bwd(i):
         j = i % ring
-        lib.mae_dmol_bwd(raws[j].data_ptr(), xs[j].data_ptr(), g.data_ptr(), batch, 1, 10, 1024, draw[i % 2].data_ptr(), sp)
+        lib.mae_dmol_bwd(raws[j].data_ptr(), xs[j].data_ptr(), g.data_ptr(), 1, 1.0, batch, 1, 10, 1024, draw[i % 2].data_ptr(), sp)
 
     def k_fwd(i):
         j = i % ring

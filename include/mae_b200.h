@@ -81,7 +81,9 @@ int mae_reparam_kl_bwd(const float* mu, int64_t mu_stride, const float* logvar, 
  * x~ = [v+mu^2, mu], y~ = [r, -2 mu r] (K = 2D) are produced in shared memory / registers.
  *
  * mae_mpd_prepare : O(B*D) pre-pass over ALL B posteriors (after an all-gather in multi-GPU runs):
- *                   packed panels, per-dimension column statistics, m_d (written to m_d[D]) and m.
+ *                   packed panels, per-dimension column statistics, m_d (written to m_d[D]) and m.  If kl is
+ *                   non-NULL it also writes the analytic KL(q_b || N(0,I)) [B] (gaussian_encoder.py:219), which
+ *                   shares every operand with the pre-pass (one launch less on the training path).
  * mae_mpd_fwd     : tiles for rows [row0,row0+nrows) x all B columns.  Writes sumsq[0] (double) =
  *                   sum over those rows and all j != i of (KL_ij - m)^2, and, if S is non-NULL,
  *                   S[0] = sqrt(sumsq/(B(B-1)-1)) (meaningful when the row range covers all rows).
@@ -92,13 +94,15 @@ int mae_reparam_kl_bwd(const float* mu, int64_t mu_stride, const float* logvar, 
  *                   [row0,row0+nrows): dmu/dlogvar are dense [nrows,D].  Each row's contribution both
  *                   as the "i" and as the "j" argument of KL_ij is included, so no cross-rank
  *                   reduce-scatter of column gradients is needed.  g_S and S are device scalars.
+ *                   gkl (nullable, [B] indexed by global row) is the upstream gradient of the analytic KL written
+ *                   by mae_mpd_prepare; its contribution gkl*mu / 0.5*gkl*(exp(logvar)-1) is added in the epilogue.
  *                   path: 0 = choose automatically, 1 = stored-KL path, 2 = recompute-tile path.
  * ---------------------------------------------------------------------------------------------- */
 #define MAE_MPD_SMALL_B 2048
 int64_t mae_mpd_workspace_bytes(int64_t B, int64_t D);
 int mae_mpd_prepare(const float* mu, int64_t mu_stride, const float* logvar, int64_t logvar_stride,
                     int64_t B, int64_t D, void* workspace, int64_t workspace_bytes,
-                    float* m_d, mae_stream_t stream);
+                    float* m_d, float* kl, mae_stream_t stream);
 int mae_mpd_fwd(void* workspace, int64_t workspace_bytes, int64_t B, int64_t D,
                 int64_t row0, int64_t nrows, int store_kl,
                 double* sumsq, float* S, mae_stream_t stream);
@@ -106,7 +110,7 @@ int mae_mpd_finalize(const double* sumsq, int64_t B, float* S, mae_stream_t stre
 int mae_mpd_bwd(const float* mu, int64_t mu_stride, const float* logvar, int64_t logvar_stride,
                 void* workspace, int64_t workspace_bytes, int64_t B, int64_t D,
                 int64_t row0, int64_t nrows,
-                const float* g_m, const float* g_S, const float* S,
+                const float* g_m, const float* g_S, const float* S, const float* gkl,
                 float* dmu, float* dlogvar, int accumulate, int path, mae_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
@@ -115,12 +119,14 @@ int mae_mpd_bwd(const float* mu, int64_t mu_stride, const float* logvar, int64_t
  *        and its duplicate in PixelCNNDecoderBinaryImage28x28 (.../image_decoders/pixelcnn.py:136-139)
  *   err[b,s] = - sum_p [ log(probs[b,s,p] + 1e-12) * x[b,p] + log(1 - probs[b,s,p] + 1e-12) * (1 - x[b,p]) ]
  *   probs are post-sigmoid probabilities [B,ns,P]; x is [B,P].
- * bwd: dprobs[b,s,p] = g[b,s] * ( (1-x)/(1-probs+1e-12) - x/(probs+1e-12) )
+ * bwd: dprobs[b,s,p] = G[b,s] * ( (1-x)/(1-probs+1e-12) - x/(probs+1e-12) ),  G[n] = g[n*g_stride]*g_mul
+ *      (g_stride = 1: per-sample upstream gradient; g_stride = 0: g is ONE device scalar, e.g. d loss, and
+ *       g_mul = 1/(B*ns) — lets the likelihood backward start without waiting for the objective's backward)
  * ---------------------------------------------------------------------------------------------- */
 int mae_bernoulli_fwd(const float* probs, const float* x, int64_t B, int64_t ns, int64_t P,
                       float* err, mae_stream_t stream);
-int mae_bernoulli_bwd(const float* probs, const float* x, const float* g, int64_t B, int64_t ns, int64_t P,
-                      float* dprobs, mae_stream_t stream);
+int mae_bernoulli_bwd(const float* probs, const float* x, const float* g, int64_t g_stride, float g_mul,
+                      int64_t B, int64_t ns, int64_t P, float* dprobs, mae_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * A4b + A4c  discretized mixture of logistics, from the RAW decoder output
@@ -132,13 +138,14 @@ int mae_bernoulli_bwd(const float* probs, const float* x, const float* g, int64_
  *   log-softmax of the logits, clamp(min=-7) of the log-scales and tanh of the coefficients happen
  *   inside the kernel.  bin 1/255, lower 1/255-1, upper 1-1/255 as in the reference.
  *   workspace: mae_dmol_workspace_bytes(B*ns, HW) bytes (per-CTA partial sums + tickets).
- * bwd: draw [B*ns,10*nmix,HW] = g[b,s] * d err[b,s] / d raw   (clamp gate passes at equality).
+ * bwd: draw [B*ns,10*nmix,HW] = G[b,s] * d err[b,s] / d raw   (clamp gate passes at equality),
+ *      G[n] = g[n*g_stride]*g_mul as for the Bernoulli backward.
  * ---------------------------------------------------------------------------------------------- */
 int64_t mae_dmol_workspace_bytes(int64_t N, int64_t HW);
 int mae_dmol_fwd(const float* raw, const float* x, int64_t B, int64_t ns, int64_t nmix, int64_t HW,
                  float* err, void* workspace, int64_t workspace_bytes, mae_stream_t stream);
-int mae_dmol_bwd(const float* raw, const float* x, const float* g, int64_t B, int64_t ns, int64_t nmix, int64_t HW,
-                 float* draw, mae_stream_t stream);
+int mae_dmol_bwd(const float* raw, const float* x, const float* g, int64_t g_stride, float g_mul,
+                 int64_t B, int64_t ns, int64_t nmix, int64_t HW, float* draw, mae_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * A5 / A6  Gaussian log densities
@@ -171,12 +178,15 @@ int mae_log_prob_posterior_bwd(const float* z_normal, const float* g,
  *   z_post_normal [B,K,D] + logdet_post [B,K] (nullable = 0), mu/logvar [B,D]  ->
  *   nll_elbo[b] = -mean_k log_iw ; recon[b] = -mean_k log_gen ; kl[b] = mean_k (log q - log p) ;
  *   nll_iw[b]   = -(max_k log_iw + log sum_k exp(log_iw - max)) + log K ,  log_iw = log_gen + log p - log q
- * ---------------------------------------------------------------------------------------------- */
+ *   workspace: mae_iw_nll_workspace_bytes(B, K) bytes (per-chunk partial states + tickets), zero-filled once.
+ */
+int64_t mae_iw_nll_workspace_bytes(int64_t B, int64_t K);
 int mae_iw_nll(const float* log_gen, const float* z_prior_normal, const float* logdet_prior,
                const float* z_post_normal, const float* logdet_post,
                const float* mu, int64_t mu_stride, const float* logvar, int64_t logvar_stride,
                int64_t B, int64_t K, int64_t D,
-               float* nll_elbo, float* recon, float* kl, float* nll_iw, mae_stream_t stream);
+               float* nll_elbo, float* recon, float* kl, float* nll_iw,
+               void* workspace, int64_t workspace_bytes, mae_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * A3' + A8  objective assembly

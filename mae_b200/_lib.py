@@ -20,19 +20,19 @@ _P, _I64, _I, _F = c_void_p, c_int64, c_int, c_float
 SIGNATURES = {
     "mae_reparam_kl_fwd": [_P, _I64, _P, _I64, _P, _I64, _I64, _I64, _P, _P, _P],
     "mae_reparam_kl_bwd": [_P, _I64, _P, _I64, _P, _P, _P, _I64, _I64, _I64, _P, _P, _I, _P],
-    "mae_mpd_prepare": [_P, _I64, _P, _I64, _I64, _I64, _P, _I64, _P, _P],
+    "mae_mpd_prepare": [_P, _I64, _P, _I64, _I64, _I64, _P, _I64, _P, _P, _P],
     "mae_mpd_fwd": [_P, _I64, _I64, _I64, _I64, _I64, _I, _P, _P, _P],
     "mae_mpd_finalize": [_P, _I64, _P, _P],
-    "mae_mpd_bwd": [_P, _I64, _P, _I64, _P, _I64, _I64, _I64, _I64, _I64, _P, _P, _P, _P, _P, _I, _I, _P],
+    "mae_mpd_bwd": [_P, _I64, _P, _I64, _P, _I64, _I64, _I64, _I64, _I64, _P, _P, _P, _P, _P, _P, _I, _I, _P],
     "mae_bernoulli_fwd": [_P, _P, _I64, _I64, _I64, _P, _P],
-    "mae_bernoulli_bwd": [_P, _P, _P, _I64, _I64, _I64, _P, _P],
+    "mae_bernoulli_bwd": [_P, _P, _P, _I64, _F, _I64, _I64, _I64, _P, _P],
     "mae_dmol_fwd": [_P, _P, _I64, _I64, _I64, _I64, _P, _P, _I64, _P],
-    "mae_dmol_bwd": [_P, _P, _P, _I64, _I64, _I64, _I64, _P, _P],
+    "mae_dmol_bwd": [_P, _P, _P, _I64, _F, _I64, _I64, _I64, _I64, _P, _P],
     "mae_log_prob_prior_fwd": [_P, _P, _I64, _I64, _P, _P],
     "mae_log_prob_prior_bwd": [_P, _P, _I64, _I64, _P, _P],
     "mae_log_prob_posterior_fwd": [_P, _P, _P, _I64, _P, _I64, _I64, _I64, _I64, _P, _P],
     "mae_log_prob_posterior_bwd": [_P, _P, _P, _I64, _P, _I64, _I64, _I64, _I64, _P, _P, _P, _P],
-    "mae_iw_nll": [_P, _P, _P, _P, _P, _P, _I64, _P, _I64, _I64, _I64, _I64, _P, _P, _P, _P, _P],
+    "mae_iw_nll": [_P, _P, _P, _P, _P, _P, _I64, _P, _I64, _I64, _I64, _I64, _P, _P, _P, _P, _P, _I64, _P],
     "mae_loss_assemble_fwd": [_P, _P, _P, _P, _P, _I64, _I64, _I64, _F, _F, _F, _F, _P, _P, _P],
     "mae_loss_assemble_bwd": [_P, _P, _P, _I64, _I64, _I64, _F, _F, _F, _F, _P, _P, _P, _P, _P],
 }
@@ -43,6 +43,7 @@ PLAIN = {
     "mae_device_info": (c_int, [_P, _P, _P]),
     "mae_mpd_workspace_bytes": (c_int64, [_I64, _I64]),
     "mae_dmol_workspace_bytes": (c_int64, [_I64, _I64]),
+    "mae_iw_nll_workspace_bytes": (c_int64, [_I64, _I64]),
 }
 ALL_SYMBOLS = sorted(list(SIGNATURES) + list(PLAIN))
 

@@ -23,13 +23,13 @@ bernoulli_fwd_kernel(const float* __restrict__ probs, const float* __restrict__ 
 
 __global__ void __launch_bounds__(kThreads)
 bernoulli_bwd_kernel(const float* __restrict__ probs, const float* __restrict__ x, const float* __restrict__ g,
-                     int ns, int P, int64_t total, float* __restrict__ dprobs) {
+                     int g_stride, float g_mul, int ns, int P, int64_t total, float* __restrict__ dprobs) {
     const int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     if (t >= total) return;
     const int64_t row = t / P;
     const int p = (int)(t % P);
     const int64_t b = row / ns;
-    stg_stream(dprobs + t, g[row] * hm::bernoulli_derr_dp(ldg_stream(probs + t), x[b * P + p]));
+    stg_stream(dprobs + t, g[row * g_stride] * g_mul * hm::bernoulli_derr_dp(ldg_stream(probs + t), x[b * P + p]));
 }
 
 }  // namespace
@@ -44,14 +44,15 @@ extern "C" int mae_bernoulli_fwd(const float* probs, const float* x, int64_t B, 
     return launch_status();
 }
 
-extern "C" int mae_bernoulli_bwd(const float* probs, const float* x, const float* g, int64_t B, int64_t ns, int64_t P,
-                                 float* dprobs, mae_stream_t stream) {
+extern "C" int mae_bernoulli_bwd(const float* probs, const float* x, const float* g, int64_t g_stride, float g_mul, int64_t B,
+                                 int64_t ns, int64_t P, float* dprobs, mae_stream_t stream) {
     using namespace mae;
     MAE_REQUIRE(probs && x && g && dprobs, MAE_ERR_NULL);
+    MAE_REQUIRE(g_stride == 0 || g_stride == 1, MAE_ERR_STRIDE);
     MAE_REQUIRE(B > 0 && ns > 0 && P > 0 && B * ns < (1ll << 31) && P < (1ll << 31), MAE_ERR_SHAPE);
     const int64_t total = B * ns * P;
     const int64_t blocks = ceil_div(total, kThreads);
     MAE_REQUIRE(blocks < (1ll << 31), MAE_ERR_SHAPE);
-    bernoulli_bwd_kernel<<<(unsigned)blocks, kThreads, 0, as_stream(stream)>>>(probs, x, g, (int)ns, (int)P, total, dprobs);
+    bernoulli_bwd_kernel<<<(unsigned)blocks, kThreads, 0, as_stream(stream)>>>(probs, x, g, (int)g_stride, g_mul, (int)ns, (int)P, total, dprobs);
     return launch_status();
 }

@@ -103,8 +103,8 @@ dmol_fwd_generic_kernel(const float* __restrict__ raw, const float* __restrict__
 }
 
 __global__ void __launch_bounds__(kThreads)
-dmol_bwd_generic_kernel(const float* __restrict__ raw, const float* __restrict__ x, const float* __restrict__ g, int ns,
-                        int nmix, int HW, float* __restrict__ draw) {
+dmol_bwd_generic_kernel(const float* __restrict__ raw, const float* __restrict__ x, const float* __restrict__ g,
+                        int g_stride, float g_mul, int ns, int nmix, int HW, float* __restrict__ draw) {
     const int64_t n = blockIdx.x;
     const int64_t b = n / ns;
     const int pix = blockIdx.y * kThreads + threadIdx.x;
@@ -113,7 +113,7 @@ dmol_bwd_generic_kernel(const float* __restrict__ raw, const float* __restrict__
 #pragma unroll
     for (int c = 0; c < 3; ++c) xs[c] = x[(b * 3 + c) * HW + pix];
     const int64_t off = n * (int64_t)(10 * nmix) * HW + pix;
-    hm::dmol_pixel_bwd<LdCached, StStream>(raw + off, draw + off, HW, nmix, xs, g[n]);
+    hm::dmol_pixel_bwd<LdCached, StStream>(raw + off, draw + off, HW, nmix, xs, g[n * g_stride] * g_mul);
 }
 
 // ---------------------------------------------------------------------------------- specialised kernels
@@ -254,8 +254,8 @@ dmol_fwd_kernel(const float* __restrict__ raw, const float* __restrict__ x, int 
 
 template <int NMIX, int HW, int SPLIT>
 __global__ void __launch_bounds__(Geo<NMIX, SPLIT>::kThreadsCta)
-dmol_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ x, const float* __restrict__ g, int ns,
-                float* __restrict__ draw) {
+dmol_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ x, const float* __restrict__ g, int g_stride,
+                float g_mul, int ns, float* __restrict__ draw) {
     using G = Geo<NMIX, SPLIT>;
     constexpr bool kCache = G::kK <= 5;  // keep local gradients in registers instead of recomputing
     __shared__ MergeSmem<NMIX, SPLIT> ms;
@@ -272,7 +272,7 @@ dmol_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ x, cons
     float xs[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) xs[c] = __ldg(x + (b * 3 + c) * HW + pix);
-    const float gn = __ldg(g + n);
+    const float gn = __ldg(g + n * g_stride) * g_mul;   // g_stride = 0: one broadcast scalar (d loss), times 1/(B*ns)
 
     float tl[G::kK], lg[G::kK];
     float gmu[kCache ? G::kK : 1][3], grho[kCache ? G::kK : 1][3], gkap[kCache ? G::kK : 1][3];
@@ -363,10 +363,11 @@ int launch_fwd(const float* raw, const float* x, int64_t N, int ns, float* err, 
 }
 
 template <int NMIX, int HW, int SPLIT>
-int launch_bwd(const float* raw, const float* x, const float* g, int64_t N, int ns, float* draw, cudaStream_t s) {
+int launch_bwd(const float* raw, const float* x, const float* g, int gs, float gm, int64_t N, int ns, float* draw,
+               cudaStream_t s) {
     using G = Geo<NMIX, SPLIT>;
     dim3 grid((unsigned)N, (unsigned)(HW / G::kPix));
-    dmol_bwd_kernel<NMIX, HW, SPLIT><<<grid, G::kThreadsCta, 0, s>>>(raw, x, g, ns, draw);
+    dmol_bwd_kernel<NMIX, HW, SPLIT><<<grid, G::kThreadsCta, 0, s>>>(raw, x, g, gs, gm, ns, draw);
     return launch_status();
 }
 
@@ -380,10 +381,11 @@ int dispatch_fwd(int split, const float* raw, const float* x, int64_t N, int ns,
     }
 }
 template <int HW>
-int dispatch_bwd(int split, const float* raw, const float* x, const float* g, int64_t N, int ns, float* draw, cudaStream_t s) {
+int dispatch_bwd(int split, const float* raw, const float* x, const float* g, int gs, float gm, int64_t N, int ns,
+                 float* draw, cudaStream_t s) {
     // the backward always splits a pixel over >= 2 warps so the local gradients stay in registers
-    if (split <= 2) return launch_bwd<10, HW, 2>(raw, x, g, N, ns, draw, s);
-    return launch_bwd<10, HW, 5>(raw, x, g, N, ns, draw, s);
+    if (split <= 2) return launch_bwd<10, HW, 2>(raw, x, g, gs, gm, N, ns, draw, s);
+    return launch_bwd<10, HW, 5>(raw, x, g, gs, gm, N, ns, draw, s);
 }
 
 }  // namespace
@@ -418,20 +420,21 @@ extern "C" int mae_dmol_fwd(const float* raw, const float* x, int64_t B, int64_t
     return launch_status();
 }
 
-extern "C" int mae_dmol_bwd(const float* raw, const float* x, const float* g, int64_t B, int64_t ns, int64_t nmix, int64_t HW,
-                            float* draw, mae_stream_t stream) {
+extern "C" int mae_dmol_bwd(const float* raw, const float* x, const float* g, int64_t g_stride, float g_mul, int64_t B,
+                            int64_t ns, int64_t nmix, int64_t HW, float* draw, mae_stream_t stream) {
     using namespace mae;
     MAE_REQUIRE(raw && x && g && draw, MAE_ERR_NULL);
+    MAE_REQUIRE(g_stride == 0 || g_stride == 1, MAE_ERR_STRIDE);
     int rc = check_dmol(B, ns, nmix, HW);
     if (rc != MAE_OK) return rc;
     const int64_t N = B * ns;
     cudaStream_t s = as_stream(stream);
     if (nmix == 10 && (HW == 1024 || HW == 4096)) {
         const int split = pick_split(N * HW);
-        return HW == 1024 ? dispatch_bwd<1024>(split, raw, x, g, N, (int)ns, draw, s)
-                          : dispatch_bwd<4096>(split, raw, x, g, N, (int)ns, draw, s);
+        return HW == 1024 ? dispatch_bwd<1024>(split, raw, x, g, (int)g_stride, g_mul, N, (int)ns, draw, s)
+                          : dispatch_bwd<4096>(split, raw, x, g, (int)g_stride, g_mul, N, (int)ns, draw, s);
     }
     dim3 grid((unsigned)N, (unsigned)ceil_div(HW, kThreads));
-    dmol_bwd_generic_kernel<<<grid, kThreads, 0, s>>>(raw, x, g, (int)ns, (int)nmix, (int)HW, draw);
+    dmol_bwd_generic_kernel<<<grid, kThreads, 0, s>>>(raw, x, g, (int)g_stride, g_mul, (int)ns, (int)nmix, (int)HW, draw);
     return launch_status();
 }

@@ -79,17 +79,24 @@ posterior_bwd_kernel(const float* __restrict__ z, const float* __restrict__ g, c
     dlv[t] = al;
 }
 
-// One CTA per datum b.  Each warp walks samples k = w, w+8, ...; per sample the two squared norms are
-// reduced across lanes; each warp keeps an online log-sum-exp and three running sums, merged across the
-// 8 warps at the end.
+// grid: (B, chunks).  A CTA handles kSamplesPerCta consecutive samples of one datum; each warp walks its samples
+// (two squared norms reduced across lanes per sample) keeping an online log-sum-exp and three running sums.  The
+// CTA's merged state goes to the workspace; the last CTA of a datum (ticket) merges the chunk states in order.
+constexpr int kSamplesPerCta = 64;
+
+struct IwState {
+    float m, s, iw, gen, kl;
+};
+
 __global__ void __launch_bounds__(kThreads)
 iw_nll_kernel(const float* __restrict__ log_gen, const float* __restrict__ zp, const float* __restrict__ ldp,
               const float* __restrict__ zq, const float* __restrict__ ldq, const float* __restrict__ mu, int64_t mu_stride,
-              const float* __restrict__ lv, int64_t lv_stride, int K, int D, float* __restrict__ nll_elbo,
-              float* __restrict__ recon, float* __restrict__ kl, float* __restrict__ nll_iw) {
-    __shared__ float sh_m[kWarps], sh_s[kWarps], sh_iw[kWarps], sh_gen[kWarps], sh_kl[kWarps];
+              const float* __restrict__ lv, int64_t lv_stride, int K, int D, int chunks, float* part, unsigned int* tickets,
+              float* __restrict__ nll_elbo, float* __restrict__ recon, float* __restrict__ kl, float* __restrict__ nll_iw) {
+    __shared__ IwState sh[kWarps];
     __shared__ float scratch[32];
-    const int b = blockIdx.x;
+    __shared__ bool is_last;
+    const int b = blockIdx.x, chunk = blockIdx.y;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const float* mr = mu + (int64_t)b * mu_stride;
     const float* lr = lv + (int64_t)b * lv_stride;
@@ -101,7 +108,8 @@ iw_nll_kernel(const float* __restrict__ log_gen, const float* __restrict__ zp, c
     hm::Lse lse;
     lse.init();
     float s_iw = 0.f, s_gen = 0.f, s_kl = 0.f;
-    for (int k = w; k < K; k += kWarps) {
+    const int k1 = min(K, (chunk + 1) * kSamplesPerCta);
+    for (int k = chunk * kSamplesPerCta + w; k < k1; k += kWarps) {
         const int64_t n = (int64_t)b * K + k;
         const float* zpr = zp + n * D;
         const float* zqr = zq + n * D;
@@ -123,25 +131,64 @@ iw_nll_kernel(const float* __restrict__ log_gen, const float* __restrict__ zp, c
         s_gen += lg;
         s_kl += lq - lp;
     }
-    if (lane == 0) {
-        sh_m[w] = lse.m; sh_s[w] = lse.s; sh_iw[w] = s_iw; sh_gen[w] = s_gen; sh_kl[w] = s_kl;
-    }
+    if (lane == 0) sh[w] = IwState{lse.m, lse.s, s_iw, s_gen, s_kl};
     __syncthreads();
     if (threadIdx.x == 0) {
         hm::Lse tot;
         tot.init();
         float a = 0.f, c = 0.f, e = 0.f;
         for (int i = 0; i < kWarps; ++i) {
-            hm::Lse o; o.m = sh_m[i]; o.s = sh_s[i];
+            hm::Lse o;
+            o.m = sh[i].m;
+            o.s = sh[i].s;
             tot.merge(o);
-            a += sh_iw[i]; c += sh_gen[i]; e += sh_kl[i];
+            a += sh[i].iw;
+            c += sh[i].gen;
+            e += sh[i].kl;
         }
-        const float invk = 1.0f / (float)K;
-        nll_elbo[b] = -a * invk;
-        recon[b] = -c * invk;
-        kl[b] = e * invk;
-        nll_iw[b] = -tot.value() + logf((float)K);
+        float* p = part + ((int64_t)b * chunks + chunk) * 5;
+        p[0] = tot.m; p[1] = tot.s; p[2] = a; p[3] = c; p[4] = e;
+        is_last = true;
+        if (chunks > 1) {
+            __threadfence();
+            const unsigned int t = atomicAdd(&tickets[b], 1u);
+            is_last = (t == (unsigned int)(chunks - 1));
+        }
+        if (is_last) {
+            __threadfence();
+            hm::Lse all;
+            all.init();
+            float sa = 0.f, sc = 0.f, se = 0.f;
+            for (int i = 0; i < chunks; ++i) {
+                const float* q = part + ((int64_t)b * chunks + i) * 5;
+                hm::Lse o;
+                o.m = __ldcg(q);
+                o.s = __ldcg(q + 1);
+                all.merge(o);
+                sa += __ldcg(q + 2);
+                sc += __ldcg(q + 3);
+                se += __ldcg(q + 4);
+            }
+            const float invk = 1.0f / (float)K;
+            nll_elbo[b] = -sa * invk;
+            recon[b] = -sc * invk;
+            kl[b] = se * invk;
+            nll_iw[b] = -all.value() + logf((float)K);
+            tickets[b] = 0u;
+        }
     }
+}
+
+struct IwWs {
+    int64_t part_off, ticket_off, total, chunks;
+};
+IwWs iw_ws(int64_t B, int64_t K) {
+    IwWs w;
+    w.chunks = ceil_div(K, kSamplesPerCta);
+    w.part_off = 0;
+    w.ticket_off = round_up(B * w.chunks * 5 * (int64_t)sizeof(float), 256);
+    w.total = w.ticket_off + round_up(B * (int64_t)sizeof(unsigned int), 256);
+    return w;
 }
 
 }  // namespace
@@ -196,16 +243,28 @@ extern "C" int mae_log_prob_posterior_bwd(const float* z, const float* g, const 
     return launch_status();
 }
 
+extern "C" int64_t mae_iw_nll_workspace_bytes(int64_t B, int64_t K) {
+    if (B <= 0 || K <= 0) return 0;
+    return mae::iw_ws(B, K).total;
+}
+
 extern "C" int mae_iw_nll(const float* log_gen, const float* z_prior_normal, const float* logdet_prior,
                           const float* z_post_normal, const float* logdet_post, const float* mu, int64_t mu_stride,
                           const float* logvar, int64_t logvar_stride, int64_t B, int64_t K, int64_t D, float* nll_elbo,
-                          float* recon, float* kl, float* nll_iw, mae_stream_t stream) {
+                          float* recon, float* kl, float* nll_iw, void* workspace, int64_t workspace_bytes,
+                          mae_stream_t stream) {
     using namespace mae;
-    MAE_REQUIRE(log_gen && z_prior_normal && z_post_normal && mu && logvar && nll_elbo && recon && kl && nll_iw, MAE_ERR_NULL);
-    MAE_REQUIRE(B > 0 && K > 0 && D > 0 && B < (1ll << 31) && D < (1ll << 30) && K < (1ll << 30), MAE_ERR_SHAPE);
+    MAE_REQUIRE(log_gen && z_prior_normal && z_post_normal && mu && logvar && nll_elbo && recon && kl && nll_iw && workspace,
+                MAE_ERR_NULL);
+    MAE_REQUIRE(B > 0 && K > 0 && D > 0 && B < (1ll << 31) && D < (1ll << 30) && K < (1ll << 22), MAE_ERR_SHAPE);
     MAE_REQUIRE(mu_stride >= D && logvar_stride >= D, MAE_ERR_STRIDE);
-    iw_nll_kernel<<<(unsigned)B, kThreads, 0, as_stream(stream)>>>(log_gen, z_prior_normal, logdet_prior, z_post_normal,
-                                                                  logdet_post, mu, mu_stride, logvar, logvar_stride, (int)K,
-                                                                  (int)D, nll_elbo, recon, kl, nll_iw);
+    const IwWs w = iw_ws(B, K);
+    MAE_REQUIRE(workspace_bytes >= w.total, MAE_ERR_WORKSPACE);
+    MAE_REQUIRE(w.chunks <= 65535, MAE_ERR_SHAPE);
+    dim3 grid((unsigned)B, (unsigned)w.chunks);
+    iw_nll_kernel<<<grid, kThreads, 0, as_stream(stream)>>>(
+        log_gen, z_prior_normal, logdet_prior, z_post_normal, logdet_post, mu, mu_stride, logvar, logvar_stride, (int)K, (int)D,
+        (int)w.chunks, reinterpret_cast<float*>(static_cast<char*>(workspace) + w.part_off),
+        reinterpret_cast<unsigned int*>(static_cast<char*>(workspace) + w.ticket_off), nll_elbo, recon, kl, nll_iw);
     return launch_status();
 }

@@ -23,6 +23,8 @@
 //                        column panels (two more FFMA GEMMs); the row owner receives its complete gradient
 //                        (as the i and as the j argument), so there are no atomics and no reduce-scatter.
 // All cross-CTA reductions are ticketed and summed in a fixed order -> bit-reproducible results.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace mae {
@@ -118,10 +120,11 @@ __global__ void __launch_bounds__(kNT)
 mpd_prepare_kernel(const float* __restrict__ mu, int64_t mu_stride, const float* __restrict__ lv, int64_t lv_stride, int B,
                    int D, int Kp, int R, int Bp, float* __restrict__ Xp, float* __restrict__ Yp, float4* __restrict__ Vp,
                    float* __restrict__ evec, float* __restrict__ fvec, double* part, double* __restrict__ colstats,
-                   double* pivots, Hdr* hdr, float* __restrict__ m_d_out) {
+                   double* pivots, Hdr* hdr, float* __restrict__ m_d_out, float* __restrict__ kl_out) {
     extern __shared__ __align__(16) unsigned char prep_smem[];
     double* row_e = reinterpret_cast<double*>(prep_smem);  // [R]
     double* row_f = row_e + R;                             // [R]
+    double* row_k = row_f + R;                             // [R] analytic KL(q_i || N(0,I)) accumulators
     __shared__ double col_part[kNT / 32][7][32];
     __shared__ double scratch[32];
     __shared__ bool is_last;
@@ -133,6 +136,7 @@ mpd_prepare_kernel(const float* __restrict__ mu, int64_t mu_stride, const float*
     for (int r = tid; r < R; r += kNT) {
         row_e[r] = 0.0;
         row_f[r] = 0.0;
+        row_k[r] = 0.0;
     }
     const int P = B < kPivotRows ? B : kPivotRows;
     const int nchunk = (D + 31) / 32;
@@ -142,9 +146,17 @@ mpd_prepare_kernel(const float* __restrict__ mu, int64_t mu_stride, const float*
         // pivots of this chunk: mean of the first P rows (every CTA computes the same values)
         double mu_bar = 0.0, l_bar = 0.0, v_bar = 1.0;
         if (dok) {
-            for (int i = 0; i < P; ++i) {
-                mu_bar += (double)mu[(int64_t)i * mu_stride + d];
-                l_bar += (double)lv[(int64_t)i * lv_stride + d];
+            // fixed trip count + predication so that all 2*kPivotRows loads are in flight together
+            float pm[kPivotRows], pl[kPivotRows];
+#pragma unroll
+            for (int i = 0; i < kPivotRows; ++i) {
+                pm[i] = i < P ? mu[(int64_t)i * mu_stride + d] : 0.f;
+                pl[i] = i < P ? lv[(int64_t)i * lv_stride + d] : 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < kPivotRows; ++i) {
+                mu_bar += (double)pm[i];
+                l_bar += (double)pl[i];
             }
             mu_bar /= (double)P;
             l_bar /= (double)P;
@@ -159,11 +171,13 @@ mpd_prepare_kernel(const float* __restrict__ mu, int64_t mu_stride, const float*
         for (int r = w; r < R; r += kWarps) {
             const int i = i0 + r;
             if (i >= Bp) break;
-            double es = 0.0, fs = 0.0;
+            double es = 0.0, fs = 0.0, ks = 0.0;
             if (dok) {
                 float2 xv = make_float2(0.f, 0.f), yv = xv;
                 if (i < B) {
-                    const Elem e = make_elem(mu[(int64_t)i * mu_stride + d], lv[(int64_t)i * lv_stride + d], mu_bar, l_bar, v_bar);
+                    const float mu_raw = mu[(int64_t)i * mu_stride + d], lv_raw = lv[(int64_t)i * lv_stride + d];
+                    const Elem e = make_elem(mu_raw, lv_raw, mu_bar, l_bar, v_bar);
+                    ks = (double)mu_raw * (double)mu_raw + e.v - (double)lv_raw - 1.0;  // gaussian_encoder.py:219
                     const double sq = e.mc * e.mc;
                     const double s = sq / v_bar;
                     const double t = e.a + (2.0 * e.b + e.b * e.b) * (1.0 + e.a);  // r^2 v v_bar - 1
@@ -185,9 +199,11 @@ mpd_prepare_kernel(const float* __restrict__ mu, int64_t mu_stride, const float*
             }
             es = warp_sum(es);
             fs = warp_sum(fs);
+            if (kl_out != nullptr) ks = warp_sum(ks);
             if (lane == 0) {
                 row_e[r] += es;
                 row_f[r] += fs;
+                row_k[r] += ks;
             }
         }
         col_part[w][0][lane] = a0;
@@ -220,6 +236,7 @@ mpd_prepare_kernel(const float* __restrict__ mu, int64_t mu_stride, const float*
         if (lane == 0) {
             evec[i] = (float)row_e[r];
             fvec[i] = (float)row_f[r];
+            if (kl_out != nullptr && i < B) kl_out[i] = (float)(0.5 * row_k[r]);
         }
     }
 
@@ -270,13 +287,6 @@ __device__ __forceinline__ void stage_slab(const float* __restrict__ panel, int6
     dst[kq + 3][r] = a.w;
 }
 
-__device__ __forceinline__ void put_slab(float (*dst)[kLd], int r, int kq, const float4& a) {
-    dst[kq + 0][r] = a.x;
-    dst[kq + 1][r] = a.y;
-    dst[kq + 2][r] = a.z;
-    dst[kq + 3][r] = a.w;
-}
-
 __device__ __forceinline__ void fma_tile(const float (*A)[kLd], const float (*Bm)[kLd], int ty, int tx, float acc[4][4]) {
 #pragma unroll
     for (int k = 0; k < kKC; ++k) {
@@ -292,59 +302,84 @@ __device__ __forceinline__ void fma_tile(const float (*A)[kLd], const float (*Bm
 }
 
 // ---------------------------------------------------------------------------------------------- forward
+// TM x TM micro-tile per thread, 16 x 16 threads -> (16*TM)^2 tile: TM = 4 (64 x 64) for throughput, TM = 2 (32 x 32)
+// for small batches where a handful of 64-tiles would leave the chip empty and serialise ~2k FFMA per thread.
+template <int TM>
 __global__ void __launch_bounds__(kNT)
 mpd_fwd_kernel(const float* __restrict__ Xp, const float* __restrict__ Yp, const float* __restrict__ evec,
-               const float* __restrict__ fvec, Hdr* hdr, double* part, int B, int D, int Kp, int row0, int row1, int tr0,
+               const float* __restrict__ fvec, Hdr* hdr, double* part, int B, int Kp, int row0, int row1, int tr0,
                int ntr, int ntc, float* __restrict__ KL, float* __restrict__ KLT, int Bp, double* __restrict__ sumsq_out,
                float* __restrict__ S_out) {
-    __shared__ __align__(16) float As[2][kKC][kLd];
-    __shared__ __align__(16) float Bs[2][kKC][kLd];
+    constexpr int T = 16 * TM;       // tile edge
+    constexpr int LD = T + 4;        // padded leading dimension
+    constexpr int NLOAD = T * 4;     // float4 loads per operand slab (T rows x 16 k)
+    __shared__ __align__(16) float As[2][kKC][LD];
+    __shared__ __align__(16) float Bs[2][kKC][LD];
     __shared__ double scratch[32];
     __shared__ bool is_last;
     const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
     const float m = (float)hdr->m;
     double total = 0.0;
     const int ntiles = ntr * ntc;
+    // slab staging role of this thread: TM = 4 -> every thread loads one float4 of X and one of Y;
+    // TM = 2 -> threads [0,128) load X, [128,256) load Y
+    const bool two = (NLOAD == kNT);
+    const int lid = two ? tid : (tid % NLOAD);
+    const bool ldx = two || tid < NLOAD, ldy = two || tid >= NLOAD;
+    const int r = lid >> 2, kq = (lid & 3) * 4;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int ti = tr0 + tile / ntc, tj = tile % ntc;
-        float acc[4][4];
+        float acc[TM][TM];
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < TM; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+            for (int j = 0; j < TM; ++j) acc[i][j] = 0.f;
         // K loop: the next slab is fetched into registers while the current one is multiplied
         {
-            const int r = tid >> 2, kq = (tid & 3) * 4;
-            const float* xa = Xp + ((int64_t)ti * kT + r) * Kp + kq;
-            const float* yb = Yp + ((int64_t)tj * kT + r) * Kp + kq;
-            float4 ra = *reinterpret_cast<const float4*>(xa);
-            float4 rb = *reinterpret_cast<const float4*>(yb);
+            const float* xa = Xp + ((int64_t)ti * T + r) * Kp + kq;
+            const float* yb = Yp + ((int64_t)tj * T + r) * Kp + kq;
+            float4 ra = make_float4(0.f, 0.f, 0.f, 0.f), rb = ra;
+            if (ldx) ra = *reinterpret_cast<const float4*>(xa);
+            if (ldy) rb = *reinterpret_cast<const float4*>(yb);
             int buf = 0;
             for (int k0 = 0; k0 < Kp; k0 += kKC) {
-                put_slab(As[buf], r, kq, ra);
-                put_slab(Bs[buf], r, kq, rb);
+                if (ldx) { As[buf][kq + 0][r] = ra.x; As[buf][kq + 1][r] = ra.y; As[buf][kq + 2][r] = ra.z; As[buf][kq + 3][r] = ra.w; }
+                if (ldy) { Bs[buf][kq + 0][r] = rb.x; Bs[buf][kq + 1][r] = rb.y; Bs[buf][kq + 2][r] = rb.z; Bs[buf][kq + 3][r] = rb.w; }
                 __syncthreads();
                 if (k0 + kKC < Kp) {
-                    ra = *reinterpret_cast<const float4*>(xa + k0 + kKC);
-                    rb = *reinterpret_cast<const float4*>(yb + k0 + kKC);
+                    if (ldx) ra = *reinterpret_cast<const float4*>(xa + k0 + kKC);
+                    if (ldy) rb = *reinterpret_cast<const float4*>(yb + k0 + kKC);
                 }
-                fma_tile(As[buf], Bs[buf], ty, tx, acc);
+#pragma unroll
+                for (int k = 0; k < kKC; ++k) {
+                    float av[TM], bv[TM];
+#pragma unroll
+                    for (int i = 0; i < TM; ++i) {
+                        av[i] = As[buf][k][ty * TM + i];
+                        bv[i] = Bs[buf][k][tx * TM + i];
+                    }
+#pragma unroll
+                    for (int i = 0; i < TM; ++i)
+#pragma unroll
+                        for (int j = 0; j < TM; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+                }
                 buf ^= 1;
             }
-            __syncthreads();  // all reads of the last slab done before the next tile overwrites buffer 0/1
+            __syncthreads();  // all reads of the last slab done before the next tile overwrites the buffers
         }
         float psum = 0.f;
-        const int jb = tj * kT + tx * 4;
-        const float4 f4 = *reinterpret_cast<const float4*>(fvec + jb);
-        const float fj[4] = {f4.x, f4.y, f4.z, f4.w};
-        float klv[4][4];
+        const int jb = tj * T + tx * TM;
+        float fj[TM];
 #pragma unroll
-        for (int ii = 0; ii < 4; ++ii) {
-            const int i = ti * kT + ty * 4 + ii;
+        for (int jj = 0; jj < TM; ++jj) fj[jj] = fvec[jb + jj];
+        float klv[TM][TM];
+#pragma unroll
+        for (int ii = 0; ii < TM; ++ii) {
+            const int i = ti * T + ty * TM + ii;
             const float ei = evec[i];
             const bool row_ok = (i >= row0) && (i < row1);
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
+            for (int jj = 0; jj < TM; ++jj) {
                 const int j = jb + jj;
                 const float kl = 0.5f * (acc[ii][jj] + ei + fj[jj]);
                 klv[ii][jj] = kl;
@@ -353,15 +388,17 @@ mpd_fwd_kernel(const float* __restrict__ Xp, const float* __restrict__ Yp, const
                     psum = fmaf(dev, dev, psum);
                 }
             }
-            if (KL != nullptr)
-                *reinterpret_cast<float4*>(KL + (int64_t)i * Bp + jb) = make_float4(klv[ii][0], klv[ii][1], klv[ii][2], klv[ii][3]);
+            if (KL != nullptr) {
+#pragma unroll
+                for (int jj = 0; jj < TM; ++jj) KL[(int64_t)i * Bp + jb + jj] = klv[ii][jj];
+            }
         }
         if (KLT != nullptr) {
-            const int ib = ti * kT + ty * 4;
+            const int ib = ti * T + ty * TM;
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj)
-                *reinterpret_cast<float4*>(KLT + (int64_t)(jb + jj) * Bp + ib) =
-                    make_float4(klv[0][jj], klv[1][jj], klv[2][jj], klv[3][jj]);
+            for (int jj = 0; jj < TM; ++jj)
+#pragma unroll
+                for (int ii = 0; ii < TM; ++ii) KLT[(int64_t)(jb + jj) * Bp + ib + ii] = klv[ii][jj];
         }
         total += (double)psum;
     }
@@ -407,9 +444,15 @@ __device__ __forceinline__ float weight_scale(const float* g_S, const float* S, 
 }
 
 // closed-form gradient of sum_d g_m[d]*m_d w.r.t. (mu_k,d ; lv_k,d), fp64, O(1) per element.
+// gkl (nullable scalar for this row): upstream gradient of the analytic KL, adds gkl*mu and 0.5*gkl*(v-1).
 __device__ __forceinline__ void mean_part(const double* __restrict__ cs, const double* __restrict__ pivots,
                                           const float* __restrict__ g_m, int B, int D, int d, float mu_f, float lv_f,
-                                          float& gmu, float& glv) {
+                                          float& gmu, float& glv, const float* __restrict__ gkl_row = nullptr) {
+    if (gkl_row != nullptr) {
+        const float gk = gkl_row[0];
+        gmu = fmaf(gk, mu_f, gmu);
+        glv = fmaf(0.5f * gk, expf(lv_f) - 1.0f, glv);
+    }
     if (g_m == nullptr) return;
     const double nb = (double)B;
     const double a = (double)g_m[d] / (nb * (nb - 1.0));
@@ -432,8 +475,9 @@ __global__ void __launch_bounds__(kNT)
 mpd_bwd_small_kernel(const float* __restrict__ mu, int64_t mu_stride, const float* __restrict__ lv, int64_t lv_stride,
                      const float4* __restrict__ Vp, const float* __restrict__ KL, const float* __restrict__ KLT, int Bp,
                      const double* __restrict__ colstats, const double* __restrict__ pivots, const Hdr* __restrict__ hdr,
-                     const float* __restrict__ g_m, const float* __restrict__ g_S, const float* __restrict__ S, int B, int D,
-                     int row0, int nrows, float* __restrict__ dmu, float* __restrict__ dlv, int accumulate) {
+                     const float* __restrict__ g_m, const float* __restrict__ g_S, const float* __restrict__ S,
+                     const float* __restrict__ gkl, int B, int D, int row0, int nrows, float* __restrict__ dmu,
+                     float* __restrict__ dlv, int accumulate) {
     const int lane = threadIdx.x & 31;
     const int nd32 = (D + 31) / 32;
     const int64_t wg = (int64_t)blockIdx.x * (kNT / 32) + (threadIdx.x >> 5);
@@ -458,12 +502,11 @@ mpd_bwd_small_kernel(const float* __restrict__ mu, int64_t mu_stride, const floa
             const bool ok = jl < B && jl != i;
             const float w1l = ok ? beta * (kl_row[jl] - m) : 0.f;
             const float w2l = ok ? beta * (klt_row[jl] - m) : 0.f;
-            const int nj = min(32, B - jb);
 #pragma unroll 8
-            for (int jj = 0; jj < nj; ++jj) {
+            for (int jj = 0; jj < 32; ++jj) {   // fixed trip count: the 8 unrolled panel loads overlap
                 const float w1 = __shfl_sync(0xffffffffu, w1l, jj);
                 const float w2 = __shfl_sync(0xffffffffu, w2l, jj);
-                const float4 pj = active ? vcol[(int64_t)(jb + jj) * D] : zero4;
+                const float4 pj = (active && jb + jj < B) ? vcol[(int64_t)(jb + jj) * D] : zero4;
                 const float dl = pi.x - pj.x;
                 gmu = fmaf(dl, fmaf(w1, 1.0f + pj.z, w2 * opb_i), gmu);
                 glv += w1 * (fmaf(pi.y, pj.z, pi.y) + pj.z) - w2 * (fmaf(pj.y, pi.w, pj.y) + pi.w + dl * dl * opt_i * ivb);
@@ -473,7 +516,8 @@ mpd_bwd_small_kernel(const float* __restrict__ mu, int64_t mu_stride, const floa
         glv *= 0.5f;
     }
     if (!active) return;
-    mean_part(colstats, pivots, g_m, B, D, d, mu[(int64_t)i * mu_stride + d], lv[(int64_t)i * lv_stride + d], gmu, glv);
+    mean_part(colstats, pivots, g_m, B, D, d, mu[(int64_t)i * mu_stride + d], lv[(int64_t)i * lv_stride + d], gmu, glv,
+              gkl ? gkl + i : nullptr);
     const int64_t o = (int64_t)(i - row0) * D + d;
     if (accumulate) {
         dmu[o] += gmu;
@@ -497,8 +541,8 @@ mpd_bwd_tile_kernel(const float* __restrict__ mu, int64_t mu_stride, const float
                     const float* __restrict__ Xp, const float* __restrict__ Yp, const float* __restrict__ evec,
                     const float* __restrict__ fvec, const float4* __restrict__ Vp, const double* __restrict__ colstats,
                     const double* __restrict__ pivots, const Hdr* __restrict__ hdr, const float* __restrict__ g_m, const float* __restrict__ g_S,
-                    const float* __restrict__ S, int B, int D, int Kp, int row0, int row1, int tr0, int ntc,
-                    float* __restrict__ dmu, float* __restrict__ dlv, int accumulate) {
+                    const float* __restrict__ S, const float* __restrict__ gkl, int B, int D, int Kp, int row0, int row1,
+                    int tr0, int ntc, float* __restrict__ dmu, float* __restrict__ dlv, int accumulate) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     BwdSmem& sm = *reinterpret_cast<BwdSmem*>(smem_raw);
     const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
@@ -633,7 +677,8 @@ mpd_bwd_tile_kernel(const float* __restrict__ mu, int64_t mu_stride, const float
             float gmu = mc * (g1r + rs1[ii]) * ivb + 0.5f * g1m - ri * (g2m - mc * rs2[ii]);
             float glv = 0.5f * ((1.0f + a) * g1r + a * rs1[ii]) +
                         0.5f * (-t * rs2[ii] - (1.0f + t) * (g2x - (2.0f * mc * g2m - mc * mc * rs2[ii]) * ivb));
-            mean_part(colstats, pivots, g_m, B, D, d, mu[(int64_t)i * mu_stride + d], lv[(int64_t)i * lv_stride + d], gmu, glv);
+            mean_part(colstats, pivots, g_m, B, D, d, mu[(int64_t)i * mu_stride + d], lv[(int64_t)i * lv_stride + d], gmu, glv,
+                      gkl ? gkl + i : nullptr);
             const int64_t o = (int64_t)(i - row0) * D + d;
             if (accumulate) {
                 dmu[o] += gmu;
@@ -664,18 +709,19 @@ extern "C" int64_t mae_mpd_workspace_bytes(int64_t B, int64_t D) {
 }
 
 extern "C" int mae_mpd_prepare(const float* mu, int64_t mu_stride, const float* logvar, int64_t logvar_stride, int64_t B,
-                               int64_t D, void* workspace, int64_t workspace_bytes, float* m_d, mae_stream_t stream) {
+                               int64_t D, void* workspace, int64_t workspace_bytes, float* m_d, float* kl,
+                               mae_stream_t stream) {
     using namespace mae;
     MAE_REQUIRE(mu && logvar && m_d, MAE_ERR_NULL);
     Layout L;
     int rc = check_common(B, D, workspace, workspace_bytes, L);
     if (rc != MAE_OK) return rc;
     MAE_REQUIRE(mu_stride >= D && logvar_stride >= D, MAE_ERR_STRIDE);
-    mpd_prepare_kernel<<<(unsigned)L.prep_grid, kNT, (size_t)(2 * L.prep_rows * sizeof(double)), as_stream(stream)>>>(
+    mpd_prepare_kernel<<<(unsigned)L.prep_grid, kNT, (size_t)(3 * L.prep_rows * sizeof(double)), as_stream(stream)>>>(
         mu, mu_stride, logvar, logvar_stride, (int)B, (int)D, (int)L.Kp, (int)L.prep_rows, (int)L.Bp,
         at<float>(workspace, L.xp), at<float>(workspace, L.yp),
         at<float4>(workspace, L.vp), at<float>(workspace, L.c), at<float>(workspace, L.l), at<double>(workspace, L.part_prep),
-        at<double>(workspace, L.colstats), at<double>(workspace, L.pivots), at<Hdr>(workspace, L.hdr), m_d);
+        at<double>(workspace, L.colstats), at<double>(workspace, L.pivots), at<Hdr>(workspace, L.hdr), m_d, kl);
     return launch_status();
 }
 
@@ -688,16 +734,23 @@ extern "C" int mae_mpd_fwd(void* workspace, int64_t workspace_bytes, int64_t B, 
     if (rc != MAE_OK) return rc;
     MAE_REQUIRE(row0 >= 0 && nrows >= 1 && row0 + nrows <= B, MAE_ERR_SHAPE);
     if (store_kl) MAE_REQUIRE(B <= MAE_MPD_SMALL_B && row0 == 0 && nrows == B, MAE_ERR_UNSUPPORTED);
-    const int tr0 = (int)(row0 / kT);
-    const int ntr = (int)(ceil_div(row0 + nrows, kT) - tr0);
-    const int ntc = (int)L.nblk;
-    const int64_t ntiles = (int64_t)ntr * ntc;
-    const int grid = (int)(ntiles < kMaxFwdCtas ? ntiles : kMaxFwdCtas);
-    mpd_fwd_kernel<<<grid, kNT, 0, as_stream(stream)>>>(
-        at<float>(workspace, L.xp), at<float>(workspace, L.yp), at<float>(workspace, L.c), at<float>(workspace, L.l),
-        at<Hdr>(workspace, L.hdr), at<double>(workspace, L.part_fwd), (int)B, (int)D, (int)L.Kp, (int)row0, (int)(row0 + nrows),
-        tr0, ntr, ntc, store_kl ? at<float>(workspace, L.kl) : nullptr, store_kl ? at<float>(workspace, L.klt) : nullptr,
-        (int)L.Bp, sumsq, S);
+    float* klp = store_kl ? at<float>(workspace, L.kl) : nullptr;
+    float* kltp = store_kl ? at<float>(workspace, L.klt) : nullptr;
+    auto launch = [&](auto tm_tag) {
+        constexpr int TM = decltype(tm_tag)::value;
+        constexpr int T = 16 * TM;
+        const int tr0 = (int)(row0 / T);
+        const int ntr = (int)(ceil_div(row0 + nrows, T) - tr0);
+        const int ntc = (int)(L.Bp / T);
+        const int64_t ntiles = (int64_t)ntr * ntc;
+        const int grid = (int)(ntiles < kMaxFwdCtas ? ntiles : kMaxFwdCtas);
+        mpd_fwd_kernel<TM><<<grid, kNT, 0, as_stream(stream)>>>(
+            at<float>(workspace, L.xp), at<float>(workspace, L.yp), at<float>(workspace, L.c), at<float>(workspace, L.l),
+            at<Hdr>(workspace, L.hdr), at<double>(workspace, L.part_fwd), (int)B, (int)L.Kp, (int)row0, (int)(row0 + nrows), tr0,
+            ntr, ntc, klp, kltp, (int)L.Bp, sumsq, S);
+    };
+    if (L.Bp <= 256) launch(std::integral_constant<int, 2>{});   // small batches: 32 x 32 tiles, more CTAs, less latency
+    else launch(std::integral_constant<int, 4>{});
     return launch_status();
 }
 
@@ -711,8 +764,8 @@ extern "C" int mae_mpd_finalize(const double* sumsq, int64_t B, float* S, mae_st
 
 extern "C" int mae_mpd_bwd(const float* mu, int64_t mu_stride, const float* logvar, int64_t logvar_stride, void* workspace,
                            int64_t workspace_bytes, int64_t B, int64_t D, int64_t row0, int64_t nrows, const float* g_m,
-                           const float* g_S, const float* S, float* dmu, float* dlogvar, int accumulate, int path,
-                           mae_stream_t stream) {
+                           const float* g_S, const float* S, const float* gkl, float* dmu, float* dlogvar, int accumulate,
+                           int path, mae_stream_t stream) {
     using namespace mae;
     MAE_REQUIRE(mu && logvar && dmu && dlogvar, MAE_ERR_NULL);
     MAE_REQUIRE(mu_stride >= D && logvar_stride >= D, MAE_ERR_STRIDE);
@@ -731,8 +784,7 @@ extern "C" int mae_mpd_bwd(const float* mu, int64_t mu_stride, const float* logv
         mpd_bwd_small_kernel<<<(unsigned)blocks, kNT, 0, as_stream(stream)>>>(
             mu, mu_stride, logvar, logvar_stride, at<float4>(workspace, L.vp), at<float>(workspace, L.kl),
             at<float>(workspace, L.klt), (int)L.Bp, at<double>(workspace, L.colstats), at<double>(workspace, L.pivots),
-            at<Hdr>(workspace, L.hdr), g_m, g_S, S, (int)B, (int)D, (int)row0, (int)nrows, dmu,
-            dlogvar, accumulate);
+            at<Hdr>(workspace, L.hdr), g_m, g_S, S, gkl, (int)B, (int)D, (int)row0, (int)nrows, dmu, dlogvar, accumulate);
         return launch_status();
     }
     {
@@ -747,7 +799,7 @@ extern "C" int mae_mpd_bwd(const float* mu, int64_t mu_stride, const float* logv
     mpd_bwd_tile_kernel<<<grid, kNT, sizeof(BwdSmem), as_stream(stream)>>>(
         mu, mu_stride, logvar, logvar_stride, at<float>(workspace, L.xp), at<float>(workspace, L.yp), at<float>(workspace, L.c),
         at<float>(workspace, L.l), at<float4>(workspace, L.vp), at<double>(workspace, L.colstats),
-        at<double>(workspace, L.pivots), at<Hdr>(workspace, L.hdr), g_m, g_S, S, (int)B, (int)D,
+        at<double>(workspace, L.pivots), at<Hdr>(workspace, L.hdr), g_m, g_S, S, gkl, (int)B, (int)D,
         (int)L.Kp, (int)row0, (int)(row0 + nrows), tr0, (int)L.nblk, dmu, dlogvar, accumulate);
     return launch_status();
 }

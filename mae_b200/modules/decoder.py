@@ -69,12 +69,19 @@ class BinaryImageDecoder(Decoder):
         b, ns = recon_x.size(0), recon_x.size(1)
         return ops.bernoulli_recon_error(recon_x.reshape(b, ns, -1), x.reshape(b, -1))
 
-    def reconstruct_error(self, x, z):
-        """x [B,*], z [B,ns,*z] -> [B,ns].  Reference: binary_image_decoder.py:71-93."""
+    likelihood_kind = "bernoulli"
+
+    def likelihood_input(self, x, z):
+        """The conv stack's output in the layout the likelihood kernel reads: probabilities [B,ns,P].
+        Sub-classes whose network also conditions on x (PixelCNN, pixelcnn.py:119-134) override this method instead of
+        ``reconstruct_error``, so that ``MAE.loss`` can keep likelihood + objective in one fused autograd node."""
         size = z.size()
         b, ns = size[:2]
-        recon_x = self(z.view(b * ns, *size[2:])).view(b, ns, -1)
-        return self.bernoulli_error(recon_x, x)
+        return self(z.view(b * ns, *size[2:])).view(b, ns, -1)
+
+    def reconstruct_error(self, x, z):
+        """x [B,*], z [B,ns,*z] -> [B,ns].  Reference: binary_image_decoder.py:71-93."""
+        return self.bernoulli_error(self.likelihood_input(x, z), x)
 
     def log_probability(self, x, z):
         return self.reconstruct_error(x, z) * -1.
@@ -118,13 +125,18 @@ class ColorImageDecoder(Decoder):
         x2 = (x[:, 2] + coeffs[:, 1] * x0 + coeffs[:, 2] * x1).clamp(min=-1., max=1.)
         return torch.stack([x0, x1, x2], dim=1), None
 
-    def reconstruct_error(self, x, z):
-        """x [B,3,H,W] in [-1,1], z [B,ns,*z] -> [B,ns].  Reference: color_image_decoder.py:91-125."""
+    likelihood_kind = "dmol"
+
+    def likelihood_input(self, x, z):
+        """The conv stack's raw output [B*ns, 10*nmix, H, W] (x repeated per sample, color_image_decoder.py:108-113)."""
         size = z.size()
         b, ns = size[:2]
         x_expand = x.repeat_interleave(ns, dim=0) if ns > 1 else x
-        raw = self(x_expand, z.view(b * ns, *size[2:]))
-        return ops.dmol_recon_error(raw, x, ns, self.nmix)
+        return self(x_expand, z.view(b * ns, *size[2:]))
+
+    def reconstruct_error(self, x, z):
+        """x [B,3,H,W] in [-1,1], z [B,ns,*z] -> [B,ns].  Reference: color_image_decoder.py:91-125."""
+        return ops.dmol_recon_error(self.likelihood_input(x, z), x, z.size(1), self.nmix)
 
     def log_probability(self, x, z):
         return self.reconstruct_error(x, z) * -1.

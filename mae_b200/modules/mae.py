@@ -11,7 +11,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
-from .decoder import Decoder
+from .decoder import BinaryImageDecoder, ColorImageDecoder, Decoder
 from .encoder import Encoder, GaussianEncoder
 
 
@@ -44,15 +44,41 @@ class MAE(nn.Module):
 
         Reference: mae/modules/mae.py:100-140.  ``loss`` carries the gradient; the other entries are logging
         values (the reference's training loops only ``.sum()``/print them)."""
-        if isinstance(self.encoder, GaussianEncoder):
-            z, KL, (m_d, S) = self.encoder.encode(x, nsamples, _side_stream=True)   # MPD overlaps with the decoder
+        enc, dec = self.encoder, self.decoder
+        z_shape_dec = dec.z_shape()
+        if self._fusable():
+            # no flows: analytic KL.  Three autograd nodes: reparam (z), KL+MPD (side stream, overlaps with the
+            # decoder), likelihood+objective.
+            mu, logvar = enc.core(x)
+            eps = enc._draw_eps(mu, nsamples)
+            z, _ = ops.reparam_kl(mu, logvar, eps, want_kl=False)
+            KL, m_d, S = ops.kl_mpd(mu, logvar, side_stream=True)
+            dec_out = dec.likelihood_input(x, z.view(z.size(0), z.size(1), *z_shape_dec))
+            loss, stats, recon = ops.loss_tail(dec_out, x, KL, m_d, S, dec.likelihood_kind, nsamples,
+                                               getattr(dec, "nmix", 0), eta, gamma, free_bits)
         else:
-            z, KL, (m_d, S) = self.encode(x, nsamples)
-        err = self.decoder.reconstruct_error(x, z.view(z.size(0), z.size(1), *self.decoder.z_shape()))
-        loss, stats, recon = ops.assemble_loss(err, KL, m_d, S, eta, gamma, free_bits)
+            if isinstance(enc, GaussianEncoder):
+                z, KL, (m_d, S) = enc.encode(x, nsamples, _side_stream=True)   # MPD overlaps with the decoder
+            else:
+                z, KL, (m_d, S) = self.encode(x, nsamples)
+            err = dec.reconstruct_error(x, z.view(z.size(0), z.size(1), *z_shape_dec))
+            loss, stats, recon = ops.assemble_loss(err, KL, m_d, S, eta, gamma, free_bits)
         loss_mean = stats[1] if eta > 0. else 0.
         loss_std = stats[2] if gamma > 0. else 0.
         return loss, recon, KL, stats[0], S, loss_mean, loss_std
+
+    def _fusable(self) -> bool:
+        """True when loss() can use the fused nodes: Gaussian encoder without flows (analytic KL) and a decoder that
+        keeps the stock ``reconstruct_error`` of one of the two likelihood heads."""
+        enc, dec = self.encoder, self.decoder
+        if not isinstance(enc, GaussianEncoder) or enc.prior_flow is not None or enc.posterior_flow is not None:
+            return False
+        if type(enc).encode is not GaussianEncoder.encode:
+            return False
+        for base in (BinaryImageDecoder, ColorImageDecoder):
+            if isinstance(dec, base):
+                return type(dec).reconstruct_error is base.reconstruct_error
+        return False
 
     def reconstruct(self, x, k=50, random_sample=False):
         z, _ = self.sample_from_posterior(x, nsamples=k)

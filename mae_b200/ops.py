@@ -15,7 +15,7 @@ from . import _lib
 
 __all__ = [
     "reparam_kl", "mpd", "mpd_forward_only", "bernoulli_recon_error", "dmol_recon_error", "log_prob_prior",
-    "log_prob_posterior", "iw_nll", "assemble_loss", "join_side", "launch_count", "reset_launch_count",
+    "log_prob_posterior", "iw_nll", "assemble_loss", "kl_mpd", "loss_tail", "join_side", "launch_count", "reset_launch_count",
 ]
 
 _launches = 0  # number of kernels of ours enqueued since the last reset (bench.py reports it)
@@ -184,12 +184,12 @@ def _mpd_alloc_outputs(d: int, dev: torch.device):
             torch.empty(1, device=dev, dtype=torch.float64))
 
 
-def _mpd_launch_fwd(mu2, ms, lv2, ls, b, d, ws, store_kl, outs, row0=0, nrows=None):
+def _mpd_launch_fwd(mu2, ms, lv2, ls, b, d, ws, store_kl, outs, row0=0, nrows=None, kl=None):
     lib = _lib_()
     m_d, s, sumsq = outs
     nrows = b if nrows is None else nrows
     _lib.check(lib.mae_mpd_prepare(mu2.data_ptr(), ms, lv2.data_ptr(), ls, b, d, ws.data_ptr(), ws.numel(), m_d.data_ptr(),
-                                   _stream()), "mae_mpd_prepare")
+                                   _ptr(kl), _stream()), "mae_mpd_prepare")
     _lib.check(lib.mae_mpd_fwd(ws.data_ptr(), ws.numel(), b, d, row0, nrows, int(store_kl), sumsq.data_ptr(), s.data_ptr(),
                                _stream()), "mae_mpd_fwd")
     _count(2)
@@ -197,8 +197,11 @@ def _mpd_launch_fwd(mu2, ms, lv2, ls, b, d, ws, store_kl, outs, row0=0, nrows=No
 
 
 class _MPD(torch.autograd.Function):
+    """(mu, logvar) -> (m_d, S, KL).  KL is the analytic KL(q || N(0,I)) when ``with_kl`` (else an empty tensor): it
+    shares the O(B*D) pre-pass with the MPD, and its gradient is folded into the MPD backward kernel."""
+
     @staticmethod
-    def forward(ctx, mu, logvar, bwd_path, side):
+    def forward(ctx, mu, logvar, bwd_path, side, with_kl):
         ctx.set_materialize_grads(False)
         _req_cuda(mu, logvar)
         b = mu.size(0)
@@ -213,20 +216,22 @@ class _MPD(torch.autograd.Function):
         small = b <= 2048 and bwd_path != 2
         nbytes = lib.mae_mpd_workspace_bytes(b, d)
         outs = _mpd_alloc_outputs(d, dev)   # owned by the main stream; the side stream only writes them
+        kl = torch.empty(b if with_kl else 0, device=dev, dtype=torch.float32)
+        klp = kl if with_kl else None
         if side:
             cs = torch.cuda.current_stream(dev)
             ss = _side_stream(dev)
             ss.wait_stream(cs)
             with torch.cuda.stream(ss):
                 ws = _pool.take(nbytes, dev)
-                m_d, s, _ = _mpd_launch_fwd(mu2, ms, lv2, ls, b, d, ws, need_grad and small, outs)
+                m_d, s, _ = _mpd_launch_fwd(mu2, ms, lv2, ls, b, d, ws, need_grad and small, outs, kl=klp)
                 ev = torch.cuda.Event()
                 ev.record(ss)
             # everything the side-stream kernels touch stays referenced until the join
-            _pending_join[dev.index if dev.index is not None else torch.cuda.current_device()] = (ev, (outs, mu2, lv2))
+            _pending_join[dev.index if dev.index is not None else torch.cuda.current_device()] = (ev, (outs, kl, mu2, lv2))
         else:
             ws = _pool.take(nbytes, dev)
-            m_d, s, _ = _mpd_launch_fwd(mu2, ms, lv2, ls, b, d, ws, need_grad and small, outs)
+            m_d, s, _ = _mpd_launch_fwd(mu2, ms, lv2, ls, b, d, ws, need_grad and small, outs, kl=klp)
         if need_grad:
             ctx.ws = ws
             ctx.side = bool(side)
@@ -234,7 +239,9 @@ class _MPD(torch.autograd.Function):
             ctx.meta = (ms, ls, b, d, mu.shape, logvar.shape, 1 if small else 2)
         else:
             _MPD._release(ws, dev, side)
-        return m_d.view(mu.shape[1:]), s
+        if not with_kl:
+            ctx.mark_non_differentiable(kl)
+        return m_d.view(mu.shape[1:]), s, kl
 
     @staticmethod
     def _release(ws, dev, side):
@@ -245,25 +252,28 @@ class _MPD(torch.autograd.Function):
             _pool.give(ws)
 
     @staticmethod
-    def backward(ctx, g_m, g_s):
+    def backward(ctx, g_m, g_s, g_kl):
         mu2, lv2, s = ctx.saved_tensors
         ms, ls, b, d, mu_shape, lv_shape, path = ctx.meta
         ws, side = ctx.ws, ctx.side
         dev = mu2.device
         ctx.ws = None
-        if g_m is None and g_s is None:
+        if g_kl is not None and g_kl.numel() != b:
+            g_kl = None
+        if g_m is None and g_s is None and g_kl is None:
             _MPD._release(ws, dev, side)
             _grads_ready.pop(dev.index if dev.index is not None else torch.cuda.current_device(), None)
-            return None, None, None, None
+            return None, None, None, None, None
         g_m = g_m.contiguous().view(-1) if g_m is not None else None
         g_s = g_s.contiguous() if g_s is not None else None
+        g_kl = g_kl.contiguous() if g_kl is not None else None
         dmu = torch.empty(b, d, device=dev, dtype=torch.float32)
         dlv = torch.empty_like(dmu)
 
         def launch():
             _lib.check(_lib_().mae_mpd_bwd(mu2.data_ptr(), ms, lv2.data_ptr(), ls, ws.data_ptr(), ws.numel(), b, d, 0, b,
-                                           _ptr(g_m), _ptr(g_s), s.data_ptr(), dmu.data_ptr(), dlv.data_ptr(), 0, path, _stream()),
-                       "mae_mpd_bwd")
+                                           _ptr(g_m), _ptr(g_s), s.data_ptr(), _ptr(g_kl), dmu.data_ptr(), dlv.data_ptr(), 0, path,
+                                           _stream()), "mae_mpd_bwd")
             _count()
 
         if side:
@@ -273,7 +283,7 @@ class _MPD(torch.autograd.Function):
             ss = _side_stream(dev)
             idx = dev.index if dev.index is not None else torch.cuda.current_device()
             ready = _grads_ready.pop(idx, None)
-            ptrs = {t.data_ptr() for t in (g_m, g_s) if t is not None}
+            ptrs = {t.data_ptr() for t in (g_m, g_s, g_kl) if t is not None}
             if ready is not None and ptrs <= ready[1]:
                 ss.wait_event(ready[0])     # produced by the assemble backward of this pass
             else:
@@ -287,7 +297,14 @@ class _MPD(torch.autograd.Function):
         else:
             launch()
             _pool.give(ws)
-        return dmu.view(mu_shape), dlv.view(lv_shape), None, None
+        return dmu.view(mu_shape), dlv.view(lv_shape), None, None, None
+
+
+def kl_mpd(mu: torch.Tensor, logvar: torch.Tensor, side_stream: bool = False, bwd_path: int = 0):
+    """Analytic KL [B] and MPD (m_d, S) from one pre-pass: returns (kl, m_d, S).  One autograd node whose backward is a
+    single kernel.  Reference: gaussian_encoder.py:219 and :162-188.  See :func:`mpd` for ``side_stream``."""
+    m_d, s, kl = _MPD.apply(mu, logvar, bwd_path, side_stream, True)
+    return kl, m_d, s
 
 
 def mpd(mu: torch.Tensor, logvar: torch.Tensor, bwd_path: int = 0, side_stream: bool = False):
@@ -297,7 +314,8 @@ def mpd(mu: torch.Tensor, logvar: torch.Tensor, bwd_path: int = 0, side_stream: 
     ``side_stream=True`` launches the kernels on a side stream; the results may only be consumed after
     :func:`join_side` (``assemble_loss`` does it).  Used by ``MAE.loss`` / ``heads`` to overlap the regulariser with
     the decoder; the public ``encode()`` keeps the synchronous default."""
-    return _MPD.apply(mu, logvar, bwd_path, side_stream)
+    m_d, s, _ = _MPD.apply(mu, logvar, bwd_path, side_stream, False)
+    return m_d, s
 
 
 def mpd_forward_only(mu: torch.Tensor, logvar: torch.Tensor, row0: int = 0, nrows: Optional[int] = None):
@@ -345,7 +363,7 @@ class _Bernoulli(torch.autograd.Function):
         b, ns, p = probs_c.shape
         g = g.contiguous()
         d = torch.empty_like(probs_c)
-        _lib.check(_lib_().mae_bernoulli_bwd(probs_c.data_ptr(), x_c.data_ptr(), g.data_ptr(), b, ns, p, d.data_ptr(), _stream()),
+        _lib.check(_lib_().mae_bernoulli_bwd(probs_c.data_ptr(), x_c.data_ptr(), g.data_ptr(), 1, 1.0, b, ns, p, d.data_ptr(), _stream()),
                    "mae_bernoulli_bwd")
         _count()
         return d, None
@@ -388,7 +406,7 @@ class _Dmol(torch.autograd.Function):
         b, ns, nmix, hw = ctx.meta
         g = g.contiguous()
         d = torch.empty_like(raw_c)
-        _lib.check(_lib_().mae_dmol_bwd(raw_c.data_ptr(), x_c.data_ptr(), g.data_ptr(), b, ns, nmix, hw, d.data_ptr(), _stream()),
+        _lib.check(_lib_().mae_dmol_bwd(raw_c.data_ptr(), x_c.data_ptr(), g.data_ptr(), 1, 1.0, b, ns, nmix, hw, d.data_ptr(), _stream()),
                    "mae_dmol_bwd")
         _count()
         return d, None, None, None
@@ -497,10 +515,13 @@ def iw_nll(log_gen: torch.Tensor, z_prior_normal: torch.Tensor, logdet_prior: Op
     ldp = logdet_prior.reshape(b, k).contiguous() if logdet_prior is not None else None
     ldq = logdet_post.reshape(b, k).contiguous() if logdet_post is not None else None
     out = torch.empty(4, b, device=lg.device, dtype=torch.float32)
-    _lib.check(_lib_().mae_iw_nll(lg.data_ptr(), zp.data_ptr(), _ptr(ldp), zq.data_ptr(), _ptr(ldq), mu2.data_ptr(), ms,
-                                  lv2.data_ptr(), ls, b, k, d, out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(),
-                                  out[3].data_ptr(), _stream()), "mae_iw_nll")
+    lib = _lib_()
+    ws = _pool.take(max(int(lib.mae_iw_nll_workspace_bytes(b, k)), 256), lg.device)
+    _lib.check(lib.mae_iw_nll(lg.data_ptr(), zp.data_ptr(), _ptr(ldp), zq.data_ptr(), _ptr(ldq), mu2.data_ptr(), ms,
+                              lv2.data_ptr(), ls, b, k, d, out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(),
+                              out[3].data_ptr(), ws.data_ptr(), ws.numel(), _stream()), "mae_iw_nll")
     _count()
+    _pool.give(ws)
     return (out[0], out[1], out[2]), out[3]
 
 
@@ -549,8 +570,112 @@ class _Assemble(torch.autograd.Function):
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(dev))
         _grads_ready[dev.index if dev.index is not None else torch.cuda.current_device()] = (
-            ev, {t.data_ptr() for t in (dm, ds) if t is not None})
+            ev, {t.data_ptr() for t in (dm, ds, dkl) if t is not None})
         return derr, dkl, (dm.view(m_shape) if dm is not None else None), ds, None, None, None, None, None
+
+
+class _LossTail(torch.autograd.Function):
+    """likelihood + objective assembly as ONE autograd node (the part of MAE.loss after the decoder):
+    forward = likelihood kernel, join of the MPD side stream, assembly kernel; backward = likelihood backward on the
+    main stream (taking d loss as a broadcast device scalar, so it does not wait for anything else) and, concurrently
+    on the side stream, the tiny assembly backward that feeds the KL / MPD backward."""
+
+    @staticmethod
+    def forward(ctx, dec_out, x, kl, m_d, s, kind, ns, nmix, eta, gamma, free_bits):
+        ctx.set_materialize_grads(False)
+        _req_cuda(dec_out, x, kl, m_d, s)
+        lib = _lib_()
+        dev = dec_out.device
+        b = x.size(0)
+        out_c = dec_out.contiguous()
+        if kind == "dmol":
+            hw = out_c[0, 0].numel()
+            if out_c.size(1) != 10 * nmix or out_c.size(0) != b * ns or x.size(1) != 3 or x[0, 0].numel() != hw:
+                raise RuntimeError("dmol: raw %s / x %s inconsistent with ns=%d nmix=%d" % (tuple(out_c.shape), tuple(x.shape), ns, nmix))
+            x_c = x.contiguous()
+            ws = _pool.take(max(int(lib.mae_dmol_workspace_bytes(b * ns, hw)), 256), dev)
+            err = torch.empty(b, ns, device=dev, dtype=torch.float32)
+            _lib.check(lib.mae_dmol_fwd(out_c.data_ptr(), x_c.data_ptr(), b, ns, nmix, hw, err.data_ptr(), ws.data_ptr(),
+                                        ws.numel(), _stream()), "mae_dmol_fwd")
+            _pool.give(ws)
+            geom = (hw,)
+        else:
+            out_c = out_c.reshape(b, ns, -1)
+            p = out_c.size(2)
+            x_c = x.reshape(b, -1).contiguous()
+            if x_c.size(1) != p:
+                raise RuntimeError("x has %d pixels per image, probabilities have %d" % (x_c.size(1), p))
+            err = torch.empty(b, ns, device=dev, dtype=torch.float32)
+            _lib.check(lib.mae_bernoulli_fwd(out_c.data_ptr(), x_c.data_ptr(), b, ns, p, err.data_ptr(), _stream()),
+                       "mae_bernoulli_fwd")
+            geom = (p,)
+        join_side(dev)
+        kl_c = kl.contiguous()
+        m_c = m_d.contiguous().view(-1) if m_d is not None else None
+        d = m_c.numel() if m_c is not None else 0
+        scalars = torch.empty(6, device=dev, dtype=torch.float32)
+        recon = torch.empty(b, device=dev, dtype=torch.float32)
+        _lib.check(lib.mae_loss_assemble_fwd(err.data_ptr(), kl_c.data_ptr(), _ptr(m_c), _ptr(s), None, b, ns, d, eta, gamma,
+                                             free_bits, 0.0, scalars.data_ptr(), recon.data_ptr(), _stream()),
+                   "mae_loss_assemble_fwd")
+        _count(2)
+        ctx.save_for_backward(out_c, x_c, scalars, m_c if m_c is not None else scalars)
+        ctx.meta = (kind, b, ns, nmix, geom, d, eta, gamma, free_bits, dec_out.shape,
+                    m_d.shape if m_d is not None else None, s is not None)
+        loss, stats = scalars[0], scalars[1:]
+        ctx.mark_non_differentiable(stats, recon)
+        return loss, stats, recon
+
+    @staticmethod
+    def backward(ctx, gloss, _gs, _gr):
+        if gloss is None:
+            return (None,) * 11
+        out_c, x_c, scalars, m_c = ctx.saved_tensors
+        kind, b, ns, nmix, geom, d, eta, gamma, free_bits, out_shape, m_shape, has_s = ctx.meta
+        lib = _lib_()
+        dev = out_c.device
+        gloss = gloss.contiguous()
+        cs = torch.cuda.current_stream(dev)
+        ss = _side_stream(dev)
+        ss.wait_stream(cs)                      # d loss is ready on the main stream
+        dout = None
+        if ctx.needs_input_grad[0]:
+            dout = torch.empty_like(out_c)
+            gmul = 1.0 / float(b * ns)
+            if kind == "dmol":
+                _lib.check(lib.mae_dmol_bwd(out_c.data_ptr(), x_c.data_ptr(), gloss.data_ptr(), 0, gmul, b, ns, nmix, geom[0],
+                                            dout.data_ptr(), _stream()), "mae_dmol_bwd")
+            else:
+                _lib.check(lib.mae_bernoulli_bwd(out_c.data_ptr(), x_c.data_ptr(), gloss.data_ptr(), 0, gmul, b, ns, geom[0],
+                                                 dout.data_ptr(), _stream()), "mae_bernoulli_bwd")
+            _count()
+            dout = dout.view(out_shape)
+        dkl = torch.empty(b, device=dev, dtype=torch.float32)
+        dm = torch.empty(d, device=dev, dtype=torch.float32) if m_shape is not None else None
+        ds = torch.empty((), device=dev, dtype=torch.float32) if has_s else None
+        with torch.cuda.stream(ss):
+            _lib.check(lib.mae_loss_assemble_bwd(gloss.data_ptr(), scalars.data_ptr(), _ptr(m_c) if m_shape is not None else None,
+                                                 b, ns, d, eta, gamma, free_bits, 0.0, None, dkl.data_ptr(), _ptr(dm), _ptr(ds),
+                                                 _stream()), "mae_loss_assemble_bwd")
+            _count()
+            ev = torch.cuda.Event()
+            ev.record(ss)
+        _grads_ready[dev.index if dev.index is not None else torch.cuda.current_device()] = (
+            ev, {t.data_ptr() for t in (dm, ds, dkl) if t is not None})
+        cs.wait_event(ev)                       # later main-stream consumers see dkl / dm / dS; the likelihood backward
+        #                                         enqueued above is not delayed
+        return dout, None, dkl, (dm.view(m_shape) if dm is not None else None), ds, None, None, None, None, None, None
+
+
+def loss_tail(dec_out: torch.Tensor, x: torch.Tensor, kl: torch.Tensor, m_d: Optional[torch.Tensor], s: Optional[torch.Tensor],
+              kind: str, ns: int, nmix: int = 10, eta: float = 0.0, gamma: float = 0.0, free_bits: float = 0.0):
+    """Decoder output -> objective of MAE.loss in one autograd node.  ``kind`` is "dmol" (dec_out = raw
+    [B*ns,10*nmix,H,W]) or "bernoulli" (dec_out = probabilities [B,ns,P]).  Returns (loss [], stats [5], recon [B])
+    like :func:`assemble_loss`.  Reference: color_image_decoder.py:91-125 / binary_image_decoder.py:84-93 +
+    mae.py:132-140."""
+    if kind not in ("dmol", "bernoulli"):
+        raise ValueError("kind must be 'dmol' or 'bernoulli'")
+    return _LossTail.apply(dec_out, x, kl, m_d, s, kind, int(ns), int(nmix), float(eta), float(gamma), float(free_bits))
 
 
 def assemble_loss(err: torch.Tensor, kl: torch.Tensor, m_d: Optional[torch.Tensor], s: Optional[torch.Tensor],

@@ -49,9 +49,9 @@ def test_argument_validation_without_gpu(lib):
     need = lib.mae_mpd_workspace_bytes(100, 64)
     assert need > 0 and need % 256 == 0
     aligned = (p + 255) & ~255
-    assert lib.mae_mpd_prepare(aligned, 64, aligned, 64, 100, 64, aligned, need - 1, aligned, None) == -4
-    assert lib.mae_mpd_prepare(aligned, 64, aligned, 64, 1, 64, aligned, need, aligned, None) == -2
-    assert lib.mae_mpd_prepare(aligned, 64, aligned, 64, 100, 64, aligned + 4, need, aligned, None) == -5
+    assert lib.mae_mpd_prepare(aligned, 64, aligned, 64, 100, 64, aligned, need - 1, aligned, None, None) == -4
+    assert lib.mae_mpd_prepare(aligned, 64, aligned, 64, 1, 64, aligned, need, aligned, None, None) == -2
+    assert lib.mae_mpd_prepare(aligned, 64, aligned, 64, 100, 64, aligned + 4, need, aligned, None, None) == -5
     assert lib.mae_mpd_fwd(aligned, need, 100, 64, 50, 60, 0, aligned, None, None) == -2   # rows past B
     assert lib.mae_dmol_workspace_bytes(64, 1024) >= 64 * 4 * 4
 

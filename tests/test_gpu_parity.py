@@ -332,6 +332,105 @@ def test_assemble_loss(ops, O, eta, gamma, free_bits):
     check_close(zero(s), zero(sr), what="dS", floor=1e-12)
 
 
+# ------------------------------------------------------------------------ fused nodes used by MAE.loss
+def test_kl_mpd_fused_node(ops, O):
+    torch.manual_seed(11)
+    for b, d, side in ((9, 5, False), (64, 64, True), (100, 32, True), (2100, 16, False)):
+        mu0, lv0 = torch.randn(b, d), torch.randn(b, d).clamp(-7, 7)
+        gk, gm = torch.randn(b), torch.randn(d)
+        mu, lv = cu(mu0).requires_grad_(), cu(lv0).requires_grad_()
+        kl, m_d, s = ops.kl_mpd(mu, lv, side_stream=side)
+        if side:
+            ops.join_side(mu.device)
+        ((kl * cu(gk)).sum() + (m_d * cu(gm)).sum() + 0.3 * s).backward()
+        torch.cuda.synchronize()
+        a, c = mu0.double().requires_grad_(), lv0.double().requires_grad_()
+        if b <= 512:
+            mr, sr = O.post_kl(a, c)
+            klr = O.analytic_kl(a, c)
+            ((klr * gk.double()).sum() + (mr * gm.double()).sum() + 0.3 * sr).backward()
+            check_close(mu.grad, a.grad, what="kl_mpd dmu b=%d" % b)
+            check_close(lv.grad, c.grad, what="kl_mpd dlv b=%d" % b)
+        else:
+            mr, sr = O.post_kl_chunked(mu0, lv0, 100)
+            klr = O.analytic_kl(a, c)
+        check_close(kl, klr, what="kl b=%d" % b)
+        check_close(m_d, mr, what="m_d b=%d" % b)
+        check_close(s, sr, what="S b=%d" % b)
+
+
+@pytest.mark.parametrize("kind", ["dmol", "bernoulli"])
+@pytest.mark.parametrize("eta,gamma,free_bits", [(1.0, 1.0, 0.0), (0.0, 0.0, 0.0), (0.5, 2.0, 1e5)])
+def test_fused_loss_heads_vs_oracle(ops, O, kind, eta, gamma, free_bits):
+    """heads.loss_head_* = reparam + KL/MPD node (side stream) + likelihood/objective node, against the oracle's
+    composition of the reference formulas, values and all gradients."""
+    from mae_b200 import heads, synth
+    b, ns, d = 12, 2, 10
+    mu0, lv0 = synth.posterior_params(b, (d,), seed=3, clamp=True)
+    eps = synth.noise(b, ns, (d,), seed=3)
+    mu, lv = cu(mu0).requires_grad_(), cu(lv0).requires_grad_()
+    mur, lvr = mu0.double().requires_grad_(), lv0.double().requires_grad_()
+    if kind == "dmol":
+        inp = synth.color_head(b, ns, 10, 8, 8, seed=4)
+        dec = cu(inp["raw"]).requires_grad_()
+        decr = inp["raw"].double().requires_grad_()
+        out = heads.loss_head_color(mu, lv, cu(eps), dec, cu(inp["x"]), 10, eta, gamma, free_bits)
+        ref, _ = O.loss_head_color(mur, lvr, eps.double(), lambda z: decr, inp["x"].double(), 10, eta, gamma, free_bits)
+    else:
+        inp = synth.binary_head(b, ns, 50, seed=4)
+        dec = cu(inp["probs"]).requires_grad_()
+        decr = inp["probs"].double().requires_grad_()
+        out = heads.loss_head_binary(mu, lv, cu(eps), dec, cu(inp["x"]), eta, gamma, free_bits)
+        ref, _ = O.loss_head_binary(mur, lvr, eps.double(), lambda z: decr, inp["x"].double(), eta, gamma, free_bits)
+    loss, recon, kl, stats, z = out
+    (loss * 0.9).backward()
+    (ref[0] * 0.9).backward()
+    torch.cuda.synchronize()
+    check_close(loss, ref[0], what="loss")
+    check_close(recon, ref[1], what="recon")
+    check_close(kl, ref[2], what="KL")
+    check_close(stats[0], ref[3], what="postKL_mean")
+    check_close(dec.grad, decr.grad, what="d decoder output")
+    zero = lambda t, like: torch.zeros_like(like) if t is None else t
+    check_close(zero(mu.grad, mu), zero(mur.grad, mur), what="dmu", floor=1e-12)
+    check_close(zero(lv.grad, lv), zero(lvr.grad, lvr), what="dlogvar", floor=1e-12)
+
+
+def test_fused_head_under_cuda_graph(ops, O):
+    """the training step captured in a CUDA graph (side-stream fork/join included) replays to the same numbers"""
+    from mae_b200 import heads, synth
+    b, d = 64, 64
+    mu0, lv0 = synth.posterior_params(b, (d,), seed=8, clamp=True)
+    eps = cu(synth.noise(b, 1, (d,), seed=8))
+    inp = synth.color_head(b, 1, 10, 32, 32, seed=9)
+    mu, lv = cu(mu0).requires_grad_(), cu(lv0).requires_grad_()
+    raw, x = cu(inp["raw"]).requires_grad_(), cu(inp["x"])
+    one = torch.ones((), device=DEV)
+
+    def step():
+        mu.grad = lv.grad = raw.grad = None
+        loss = heads.loss_head_color(mu, lv, eps, raw, x, 10, 1.0, 1.0, 0.0)[0]
+        loss.backward(gradient=one)
+        return loss
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            eager = step()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    ref_loss, ref_gmu, ref_graw = eager.detach().clone(), mu.grad.clone(), raw.grad.clone()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        cap = step()
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(cap.detach(), ref_loss)
+    assert torch.equal(mu.grad, ref_gmu) and torch.equal(raw.grad, ref_graw)
+
+
 # --------------------------------------------------------------------------------- drop-in: whole MAE
 def _build(case, name):
     import stubs
