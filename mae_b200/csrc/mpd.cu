@@ -37,8 +37,8 @@ constexpr int kLd = kT + 4;    // padded leading dimension (keeps float4 alignme
 constexpr int kOC = 128;       // K columns (= 64 latent dims) of gradient owned by one CTA of the tile backward
 constexpr int kLdP = kOC + 4;
 constexpr int kMaxFwdCtas = 592;  // 4 x 148; fixed so partial-sum order does not depend on the device
+constexpr int kStats = 8;         // per-dimension column statistics: SA SB SAB S1 S2 R1 R2 S(a+b)
 constexpr int kPivotRows = 32;    // pivots = mean of the first min(B,32) rows
-constexpr double kEpsD = 1e-12;
 
 struct Hdr {  // first 256 bytes of the workspace
     unsigned int ticket_prep;
@@ -80,7 +80,7 @@ Layout make_layout(int64_t B, int64_t D) {
     L.xp = take(L.Bp * L.Kp * 4);
     L.yp = take(L.Bp * L.Kp * 4);
     L.vp = take(L.Bp * D * 16);
-    L.part_prep = take(L.prep_grid * 7 * D * 8);
+    L.part_prep = take(L.prep_grid * kStats * D * 8);
     L.part_fwd = take(kMaxFwdCtas * 8);
     if (B <= MAE_MPD_SMALL_B) {
         L.kl = take(L.Bp * L.Bp * 4);
@@ -98,24 +98,45 @@ T* at(void* ws, int64_t off) {
 }
 
 // ---------------------------------------------------------------------------------------------- prepare
-// per-element quantities of the pivoted decomposition, fp64
+// e^x - 1 - x >= 0 without cancellation: Taylor series for |x| < 0.5 (truncation < 2e-9 relative), direct otherwise
+__device__ __forceinline__ float expm1_minus_x(float x, float em1) {
+    if (fabsf(x) < 0.5f) {
+        float p = 1.0f / 362880.0f;
+        p = fmaf(p, x, 1.0f / 40320.0f);
+        p = fmaf(p, x, 1.0f / 5040.0f);
+        p = fmaf(p, x, 1.0f / 720.0f);
+        p = fmaf(p, x, 1.0f / 120.0f);
+        p = fmaf(p, x, 1.0f / 24.0f);
+        p = fmaf(p, x, 1.0f / 6.0f);
+        p = fmaf(p, x, 0.5f);
+        return p * x * x;
+    }
+    return em1 - x;
+}
+
+// per-element quantities of the pivoted decomposition.  fp32 throughout: every quantity below is either a
+// product/quotient of well-conditioned terms or evaluated through a cancellation-free form, so fp32 keeps full
+// relative precision even when all posteriors coincide (fp64 transcendentals cost ~10 us of pure latency at B = 64).
 struct Elem {
-    double mc, alpha, a, v, r, b;
+    float mc, alpha, a, ema, v, r, b, bpa, apb;
 };
-__device__ __forceinline__ Elem make_elem(float mu, float lv, double mu_bar, double l_bar, double v_bar) {
+__device__ __forceinline__ Elem make_elem(float mu, float lv, float mu_bar, float l_bar, float v_bar) {
     Elem e;
-    e.mc = (double)mu - mu_bar;
-    e.alpha = (double)lv - l_bar;
-    e.a = expm1(e.alpha);
-    e.v = v_bar * (1.0 + e.a);
-    e.r = 1.0 / (e.v + kEpsD);
-    e.b = -(e.a * v_bar + kEpsD) * e.r;  // v_bar * r - 1 without cancellation
+    e.mc = mu - mu_bar;
+    e.alpha = lv - l_bar;
+    e.a = expm1f(e.alpha);                                   // v / v_bar - 1
+    e.ema = expm1_minus_x(e.alpha, e.a);                     // a - alpha
+    e.v = v_bar * (1.0f + e.a);
+    e.r = 1.0f / (e.v + kEps);
+    e.b = -(e.a * v_bar + kEps) * e.r;                       // v_bar * r - 1
+    e.bpa = (v_bar * (e.alpha * e.a - e.ema) + kEps * (e.alpha - 1.0f)) * e.r;   // b + alpha
+    e.apb = (v_bar * e.a * e.a + kEps * (e.a - 1.0f)) * e.r;                     // a + b
     return e;
 }
 
 // grid: G CTAs; CTA `blk` owns rows [blk*R, blk*R+R) (R a multiple of 8, so one warp owns whole rows).  Work is
 // organised in chunks of 32 latent dims: lane = dim inside the chunk, warp = row (stride 8).  Every element is
-// evaluated once in fp64 and feeds the panels, the row sums E_i/F_i and the per-dimension column partials.
+// evaluated once and feeds the panels, the row sums E_i/F_i/KL_i and the per-dimension column partials (fp64 adds).
 __global__ void __launch_bounds__(kNT)
 mpd_prepare_kernel(const float* __restrict__ mu, int64_t mu_stride, const float* __restrict__ lv, int64_t lv_stride, int B,
                    int D, int Kp, int R, int Bp, float* __restrict__ Xp, float* __restrict__ Yp, float4* __restrict__ Vp,
@@ -125,7 +146,7 @@ mpd_prepare_kernel(const float* __restrict__ mu, int64_t mu_stride, const float*
     double* row_e = reinterpret_cast<double*>(prep_smem);  // [R]
     double* row_f = row_e + R;                             // [R]
     double* row_k = row_f + R;                             // [R] analytic KL(q_i || N(0,I)) accumulators
-    __shared__ double col_part[kNT / 32][7][32];
+    __shared__ double col_part[kNT / 32][kStats][32];
     __shared__ double scratch[32];
     __shared__ bool is_last;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -143,8 +164,8 @@ mpd_prepare_kernel(const float* __restrict__ mu, int64_t mu_stride, const float*
     for (int ch = 0; ch < nchunk; ++ch) {
         const int d = ch * 32 + lane;
         const bool dok = d < D;
-        // pivots of this chunk: mean of the first P rows (every CTA computes the same values)
-        double mu_bar = 0.0, l_bar = 0.0, v_bar = 1.0;
+        // pivots of this chunk: mean of the first P rows (every CTA computes the same values, same order)
+        float mu_bar = 0.f, l_bar = 0.f, v_bar = 1.f;
         if (dok) {
             // fixed trip count + predication so that all 2*kPivotRows loads are in flight together
             float pm[kPivotRows], pl[kPivotRows];
@@ -155,44 +176,47 @@ mpd_prepare_kernel(const float* __restrict__ mu, int64_t mu_stride, const float*
             }
 #pragma unroll
             for (int i = 0; i < kPivotRows; ++i) {
-                mu_bar += (double)pm[i];
-                l_bar += (double)pl[i];
+                mu_bar += pm[i];
+                l_bar += pl[i];
             }
-            mu_bar /= (double)P;
-            l_bar /= (double)P;
-            v_bar = exp(l_bar);
+            mu_bar /= (float)P;
+            l_bar /= (float)P;
+            v_bar = expf(l_bar);
             if (blk == 0 && w == 0) {
                 pivots[d] = mu_bar;
                 pivots[(int64_t)D + d] = l_bar;
                 pivots[2 * (int64_t)D + d] = v_bar;
             }
         }
-        double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0, a6 = 0;
+        const float ivb = 1.0f / v_bar;
+        double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0, a6 = 0, a7 = 0;
         for (int r = w; r < R; r += kWarps) {
             const int i = i0 + r;
             if (i >= Bp) break;
-            double es = 0.0, fs = 0.0, ks = 0.0;
+            float es = 0.f, fs = 0.f, ks = 0.f;
             if (dok) {
                 float2 xv = make_float2(0.f, 0.f), yv = xv;
                 if (i < B) {
                     const float mu_raw = mu[(int64_t)i * mu_stride + d], lv_raw = lv[(int64_t)i * lv_stride + d];
                     const Elem e = make_elem(mu_raw, lv_raw, mu_bar, l_bar, v_bar);
-                    ks = (double)mu_raw * (double)mu_raw + e.v - (double)lv_raw - 1.0;  // gaussian_encoder.py:219
-                    const double sq = e.mc * e.mc;
-                    const double s = sq / v_bar;
-                    const double t = e.a + (2.0 * e.b + e.b * e.b) * (1.0 + e.a);  // r^2 v v_bar - 1
-                    xv = make_float2((float)(e.a + s), (float)e.mc);
-                    yv = make_float2((float)e.b, (float)(-2.0 * e.mc * e.r));
-                    Vp[(int64_t)i * D + d] = make_float4((float)e.mc, (float)e.a, (float)e.b, (float)t);
-                    es = (e.a - e.alpha) + s;
-                    fs = (e.b + e.alpha) + sq * e.r;
-                    a0 += e.v;
-                    a1 += e.r;
-                    a2 += e.v * e.r;
-                    a3 += e.mc;
-                    a4 += sq;
-                    a5 += e.r * e.mc;
-                    a6 += e.r * sq;
+                    const float sq = e.mc * e.mc;
+                    const float s = sq * ivb;
+                    const float t = e.a + (2.0f * e.b + e.b * e.b) * (1.0f + e.a);  // r^2 v v_bar - 1
+                    xv = make_float2(e.a + s, e.mc);
+                    yv = make_float2(e.b, -2.0f * e.mc * e.r);
+                    Vp[(int64_t)i * D + d] = make_float4(e.mc, e.a, e.b, t);
+                    es = e.ema + s;            // all terms >= 0: well-conditioned fp32 sums
+                    fs = e.bpa + sq * e.r;
+                    // analytic KL term mu^2 + (e^lv - lv - 1), gaussian_encoder.py:219, second part cancellation-free
+                    ks = fmaf(mu_raw, mu_raw, expm1_minus_x(lv_raw, expm1f(lv_raw)));
+                    a0 += (double)e.a;
+                    a1 += (double)e.b;
+                    a2 += (double)e.a * (double)e.b;
+                    a3 += (double)e.mc;
+                    a4 += (double)sq;
+                    a5 += (double)e.r * (double)e.mc;
+                    a6 += (double)e.r * (double)sq;
+                    a7 += (double)e.apb;
                 }
                 *reinterpret_cast<float2*>(Xp + (int64_t)i * Kp + 2 * d) = xv;
                 *reinterpret_cast<float2*>(Yp + (int64_t)i * Kp + 2 * d) = yv;
@@ -201,9 +225,9 @@ mpd_prepare_kernel(const float* __restrict__ mu, int64_t mu_stride, const float*
             fs = warp_sum(fs);
             if (kl_out != nullptr) ks = warp_sum(ks);
             if (lane == 0) {
-                row_e[r] += es;
-                row_f[r] += fs;
-                row_k[r] += ks;
+                row_e[r] += (double)es;
+                row_f[r] += (double)fs;
+                row_k[r] += (double)ks;
             }
         }
         col_part[w][0][lane] = a0;
@@ -213,14 +237,15 @@ mpd_prepare_kernel(const float* __restrict__ mu, int64_t mu_stride, const float*
         col_part[w][4][lane] = a4;
         col_part[w][5][lane] = a5;
         col_part[w][6][lane] = a6;
+        col_part[w][7][lane] = a7;
         __syncthreads();
-        if (tid < 7 * 32) {
-            const int q = tid >> 5, l = tid & 31;
+        {
+            const int q = tid >> 5, l = tid & 31;   // 8 warps x 32 lanes = 8 statistics x 32 dims
             if (ch * 32 + l < D) {
                 double t = 0.0;
 #pragma unroll
                 for (int ww = 0; ww < kWarps; ++ww) t += col_part[ww][q][l];
-                part[((int64_t)blk * 7 + q) * D + ch * 32 + l] = t;
+                part[((int64_t)blk * kStats + q) * D + ch * 32 + l] = t;
             }
         }
         __syncthreads();
@@ -250,21 +275,25 @@ mpd_prepare_kernel(const float* __restrict__ mu, int64_t mu_stride, const float*
     if (!is_last) return;
     __threadfence();
 
-    // last CTA: ordered sum of the partials, closed-form m_d
+    // last CTA: ordered sum of the partials, closed-form m_d (fp64, additions and products only)
     const double nb = (double)B;
     double msum = 0.0;
     for (int d = tid; d < D; d += kNT) {
-        double s[7] = {0, 0, 0, 0, 0, 0, 0};
-        for (int bk = 0; bk < (int)gridDim.x; ++bk) {
-            const double* p = part + (int64_t)bk * 7 * D + d;
+        double s[kStats];
 #pragma unroll
-            for (int q = 0; q < 7; ++q) s[q] += __ldcg(p + q * (int64_t)D);
+        for (int q = 0; q < kStats; ++q) s[q] = 0.0;
+        for (int bk = 0; bk < (int)gridDim.x; ++bk) {
+            const double* p = part + (int64_t)bk * kStats * D + d;
+#pragma unroll
+            for (int q = 0; q < kStats; ++q) s[q] += __ldcg(p + q * (int64_t)D);
         }
 #pragma unroll
-        for (int q = 0; q < 7; ++q) colstats[q * (int64_t)D + d] = s[q];
-        // sum_{i!=j} [v_i r_j + (mu_i-mu_j)^2 r_j] = Sv*R0 - Svr + S2*R0 - 2*S1*R1 + B*R2
-        const double tn = s[0] * s[1] - s[2] + s[4] * s[1] - 2.0 * s[3] * s[5] + nb * s[6];
-        const double md = 0.5 * tn / (nb * (nb - 1.0)) - 0.5;
+        for (int q = 0; q < kStats; ++q) colstats[q * (int64_t)D + d] = s[q];
+        // sum_{i!=j} (v_i r_j - 1)        = SA*SB - SAB + (B-1)*S(a+b)
+        // sum_{i!=j} (mu_i-mu_j)^2 r_j    = S2*R0 - 2*S1*R1 + B*R2,   R0 = (B + SB)/v_bar
+        const double r0 = (nb + s[1]) / pivots[2 * (int64_t)D + d];
+        const double tn = s[0] * s[1] - s[2] + (nb - 1.0) * s[7] + (s[4] * r0 - 2.0 * s[3] * s[5] + nb * s[6]);
+        const double md = 0.5 * tn / (nb * (nb - 1.0));
         m_d_out[d] = (float)md;
         msum += md;
     }
@@ -443,27 +472,32 @@ __device__ __forceinline__ float weight_scale(const float* g_S, const float* S, 
     return (float)((double)g_S[0] / ((nb * nb - nb - 1.0) * s));
 }
 
-// closed-form gradient of sum_d g_m[d]*m_d w.r.t. (mu_k,d ; lv_k,d), fp64, O(1) per element.
-// gkl (nullable scalar for this row): upstream gradient of the analytic KL, adds gkl*mu and 0.5*gkl*(v-1).
+// closed-form gradient of sum_d g_m[d]*m_d w.r.t. (mu_k,d ; lv_k,d): O(1) per element, fp64 products/sums of the
+// column statistics and the element's {mc, a, b, t} (no transcendental, no cancellation of large terms):
+//   dT/dmu = 2[(mc R0 - R1) + r_k (B mc - S1)],  r_k = (1+b_k)/v_bar, R0 = (B + SB)/v_bar
+//   dT/dlv = (B-1)(a_k - t_k) + (1+a_k)(SB - b_k) - (1+t_k)(SA - a_k) - (1+t_k)/v_bar (S2 - 2 S1 mc + B mc^2)
+// gkl (nullable scalar for this row): upstream gradient of the analytic KL, adds gkl*mu and 0.5*gkl*(e^lv - 1).
 __device__ __forceinline__ void mean_part(const double* __restrict__ cs, const double* __restrict__ pivots,
-                                          const float* __restrict__ g_m, int B, int D, int d, float mu_f, float lv_f,
-                                          float& gmu, float& glv, const float* __restrict__ gkl_row = nullptr) {
+                                          const float* __restrict__ g_m, int B, int D, int d, const float4& pk, float mu_f,
+                                          float lv_f, float& gmu, float& glv, const float* __restrict__ gkl_row = nullptr) {
     if (gkl_row != nullptr) {
         const float gk = gkl_row[0];
         gmu = fmaf(gk, mu_f, gmu);
-        glv = fmaf(0.5f * gk, expf(lv_f) - 1.0f, glv);
+        glv = fmaf(0.5f * gk, expm1f(lv_f), glv);
     }
     if (g_m == nullptr) return;
     const double nb = (double)B;
-    const double a = (double)g_m[d] / (nb * (nb - 1.0));
-    const double Sv = cs[0 * (int64_t)D + d], R0 = cs[1 * (int64_t)D + d], S1 = cs[3 * (int64_t)D + d],
+    const double w = 0.5 * (double)g_m[d] / (nb * (nb - 1.0));
+    const double SA = cs[0 * (int64_t)D + d], SB = cs[1 * (int64_t)D + d], S1 = cs[3 * (int64_t)D + d],
                  S2 = cs[4 * (int64_t)D + d], R1 = cs[5 * (int64_t)D + d];
-    const Elem e = make_elem(mu_f, lv_f, pivots[d], pivots[(int64_t)D + d], pivots[2 * (int64_t)D + d]);
-    const double mc = e.mc, v = e.v, r = e.r;
-    const double dT_dmu = 2.0 * ((mc * R0 - R1) + r * (nb * mc - S1));
-    const double dT_dlv = v * ((R0 - r) - r * r * (Sv - v + S2 - 2.0 * S1 * mc + nb * mc * mc));
-    gmu += (float)(0.5 * a * dT_dmu);
-    glv += (float)(0.5 * a * dT_dlv);
+    const double ivb = 1.0 / pivots[2 * (int64_t)D + d];
+    const double mc = pk.x, a = pk.y, b = pk.z, t = pk.w;
+    const double r0 = (nb + SB) * ivb, rk = (1.0 + b) * ivb;
+    const double dT_dmu = 2.0 * ((mc * r0 - R1) + rk * (nb * mc - S1));
+    const double dT_dlv = (nb - 1.0) * (a - t) + (1.0 + a) * (SB - b) - (1.0 + t) * (SA - a) -
+                          (1.0 + t) * ivb * (S2 - 2.0 * S1 * mc + nb * mc * mc);
+    gmu += (float)(w * dT_dmu);
+    glv += (float)(w * dT_dlv);
 }
 
 // ------------------------------------------------------------------------- backward, stored-KL (small B)
@@ -516,7 +550,7 @@ mpd_bwd_small_kernel(const float* __restrict__ mu, int64_t mu_stride, const floa
         glv *= 0.5f;
     }
     if (!active) return;
-    mean_part(colstats, pivots, g_m, B, D, d, mu[(int64_t)i * mu_stride + d], lv[(int64_t)i * lv_stride + d], gmu, glv,
+    mean_part(colstats, pivots, g_m, B, D, d, pi, mu[(int64_t)i * mu_stride + d], lv[(int64_t)i * lv_stride + d], gmu, glv,
               gkl ? gkl + i : nullptr);
     const int64_t o = (int64_t)(i - row0) * D + d;
     if (accumulate) {
@@ -677,8 +711,8 @@ mpd_bwd_tile_kernel(const float* __restrict__ mu, int64_t mu_stride, const float
             float gmu = mc * (g1r + rs1[ii]) * ivb + 0.5f * g1m - ri * (g2m - mc * rs2[ii]);
             float glv = 0.5f * ((1.0f + a) * g1r + a * rs1[ii]) +
                         0.5f * (-t * rs2[ii] - (1.0f + t) * (g2x - (2.0f * mc * g2m - mc * mc * rs2[ii]) * ivb));
-            mean_part(colstats, pivots, g_m, B, D, d, mu[(int64_t)i * mu_stride + d], lv[(int64_t)i * lv_stride + d], gmu, glv,
-                      gkl ? gkl + i : nullptr);
+            mean_part(colstats, pivots, g_m, B, D, d, pi, mu[(int64_t)i * mu_stride + d], lv[(int64_t)i * lv_stride + d], gmu,
+                      glv, gkl ? gkl + i : nullptr);
             const int64_t o = (int64_t)(i - row0) * D + d;
             if (accumulate) {
                 dmu[o] += gmu;

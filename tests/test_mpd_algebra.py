@@ -26,13 +26,20 @@ def kernel_algebra(mu, lv, g_m, g_S, npivot=32):
     t = a + (2 * b + b * b) * (1 + a)                # (1+b)^2 (1+a) - 1 = r^2 v v_bar - 1
     X = torch.stack([a + s, mc], dim=2).reshape(B, 2 * D)            # interleaved (2d, 2d+1)
     Y = torch.stack([b, -2.0 * mc * r], dim=2).reshape(B, 2 * D)
-    E = (a - alpha + s).sum(1)
-    F = (b + alpha + mc * mc * r).sum(1)
+    ema = a - alpha                                        # kernel: series for small alpha
+    bpa = (v_bar * (alpha * a - ema) + eps * (alpha - 1)) * r   # = b + alpha without cancellation
+    assert torch.allclose(bpa, b + alpha, rtol=1e-9, atol=1e-12)
+    E = (ema + s).sum(1)
+    F = (bpa + mc * mc * r).sum(1)
     KL = 0.5 * (X @ Y.t() + E[:, None] + F[None, :])
-    # column statistics and closed-form m_d
-    Sv, R0, Svr, S1, S2, R1, R2 = v.sum(0), r.sum(0), (v * r).sum(0), mc.sum(0), (mc * mc).sum(0), (r * mc).sum(0), (r * mc * mc).sum(0)
-    tn = Sv * R0 - Svr + S2 * R0 - 2 * S1 * R1 + B * R2
-    m_d = 0.5 * tn / (B * (B - 1)) - 0.5
+    # column statistics (all in the pivot-normalised quantities a, b: no "large minus large") and closed-form m_d
+    SA, SB, SAB, SApB = a.sum(0), b.sum(0), (a * b).sum(0), ((v_bar * a * a + eps * (a - 1)) * r).sum(0)   # last = sum(a+b)
+    assert torch.allclose(SApB, (a + b).sum(0), rtol=1e-9, atol=1e-12)
+    S1, S2, R1, R2 = mc.sum(0), (mc * mc).sum(0), (r * mc).sum(0), (r * mc * mc).sum(0)
+    R0 = (B + SB) * ivb.squeeze(0)
+    # sum_{i!=j} (v_i r_j - 1) = SA*SB - SAB + (B-1)*sum(a+b);  sum_{i!=j} (mu_i-mu_j)^2 r_j = S2*R0 - 2*S1*R1 + B*R2
+    tn2 = SA * SB - SAB + (B - 1) * SApB + (S2 * R0 - 2 * S1 * R1 + B * R2)
+    m_d = 0.5 * tn2 / (B * (B - 1))
     m = m_d.sum()
     off = ~torch.eye(B, dtype=torch.bool)
     sumsq = ((KL - m)[off] ** 2).sum()
@@ -50,8 +57,9 @@ def kernel_algebra(mu, lv, g_m, g_S, npivot=32):
     gmu = mc * (g1r + rs1) * ivb + 0.5 * g1m - ri * (g2m - mc * rs2)
     glv = 0.5 * ((1 + a) * g1r + a * rs1) + 0.5 * (-t * rs2 - (1 + t) * (g2x - (2 * mc * g2m - mc * mc * rs2) * ivb))
     aa = g_m / (B * (B - 1))
-    dT_dmu = 2 * ((mc * R0 - R1) + r * (B * mc - S1))
-    dT_dlv = v * ((R0 - r) - r * r * (Sv - v + S2 - 2 * S1 * mc + B * mc * mc))
+    dT_dmu = 2 * ((mc * R0 - R1) + ri * (B * mc - S1))
+    dT_dlv = ((B - 1) * (a - t) + (1 + a) * (SB - b) - (1 + t) * (SA - a)
+              - (1 + t) * ivb * (S2 - 2 * S1 * mc + B * mc * mc))
     gmu = gmu + 0.5 * aa * dT_dmu
     glv = glv + 0.5 * aa * dT_dlv
     # per-pair form used by the stored-KL kernel
