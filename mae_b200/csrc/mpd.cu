@@ -37,6 +37,7 @@ constexpr int kLd = kT + 4;    // padded leading dimension (keeps float4 alignme
 constexpr int kOC = 128;       // K columns (= 64 latent dims) of gradient owned by one CTA of the tile backward
 constexpr int kLdP = kOC + 4;
 constexpr int kMaxFwdCtas = 592;  // 4 x 148; fixed so partial-sum order does not depend on the device
+constexpr int kBwdBatch = 16;      // panel rows fetched per batch by the stored-KL backward
 constexpr int kStats = 8;         // per-dimension column statistics: SA SB SAB S1 S2 R1 R2 S(a+b)
 constexpr int kPivotRows = 32;    // pivots = mean of the first min(B,32) rows
 
@@ -46,7 +47,28 @@ struct Hdr {  // first 256 bytes of the workspace
     unsigned int pad[2];
     double m;      // sum_d m_d
     double sumsq;  // last forward result
+    unsigned long long dbg[24];  // phase timestamps (ns), written only when built with -DMAE_DEBUG_TIMING
 };
+
+#ifdef MAE_DEBUG_TIMING
+__device__ __forceinline__ unsigned long long now_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define MAE_STAMP(hdr, slot)                                  \
+    do {                                                      \
+        __syncthreads();                                      \
+        if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) (hdr)->dbg[slot] = now_ns(); \
+    } while (0)
+#define MAE_STAMP_ANY(hdr, slot)                              \
+    do {                                                      \
+        if (threadIdx.x == 0) (hdr)->dbg[slot] = now_ns();    \
+    } while (0)
+#else
+#define MAE_STAMP(hdr, slot) do {} while (0)
+#define MAE_STAMP_ANY(hdr, slot) do {} while (0)
+#endif
 
 struct Layout {
     int64_t Bp, Kp, nblk;
@@ -74,7 +96,7 @@ Layout make_layout(int64_t B, int64_t D) {
     };
     L.hdr = take(256);
     L.colstats = take(8 * D * 8);
-    L.pivots = take(3 * D * 8);  // double mu_bar[D], l_bar[D], v_bar[D]
+    L.pivots = take(4 * D * 8);  // double mu_bar[D], l_bar[D], v_bar[D], 1/v_bar[D]
     L.c = take(L.Bp * 4);
     L.l = take(L.Bp * 4);
     L.xp = take(L.Bp * L.Kp * 4);
@@ -141,12 +163,13 @@ __global__ void __launch_bounds__(kNT)
 mpd_prepare_kernel(const float* __restrict__ mu, int64_t mu_stride, const float* __restrict__ lv, int64_t lv_stride, int B,
                    int D, int Kp, int R, int Bp, float* __restrict__ Xp, float* __restrict__ Yp, float4* __restrict__ Vp,
                    float* __restrict__ evec, float* __restrict__ fvec, double* part, double* __restrict__ colstats,
-                   double* pivots, Hdr* hdr, float* __restrict__ m_d_out, float* __restrict__ kl_out) {
+                   double* pivots, Hdr* hdr, float* __restrict__ m_d_out, float* __restrict__ kl_out,
+                   double half_inv_pairs /* 0.5 / (B (B-1)) */) {
     extern __shared__ __align__(16) unsigned char prep_smem[];
     double* row_e = reinterpret_cast<double*>(prep_smem);  // [R]
     double* row_f = row_e + R;                             // [R]
     double* row_k = row_f + R;                             // [R] analytic KL(q_i || N(0,I)) accumulators
-    __shared__ double col_part[kNT / 32][kStats][32];
+    __shared__ double col_part[kNT / 32][kStats][64];
     __shared__ double scratch[32];
     __shared__ bool is_last;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -154,69 +177,102 @@ mpd_prepare_kernel(const float* __restrict__ mu, int64_t mu_stride, const float*
     const int i0 = blk * R;
     constexpr int kWarps = kNT / 32;
 
+    MAE_STAMP(hdr, 0);
     for (int r = tid; r < R; r += kNT) {
         row_e[r] = 0.0;
         row_f[r] = 0.0;
         row_k[r] = 0.0;
     }
     const int P = B < kPivotRows ? B : kPivotRows;
-    const int nchunk = (D + 31) / 32;
+    // chunks of 64 latent dims: every lane owns dims d0 = ch*64 + lane and d1 = d0 + 32 and carries both through
+    // the same instruction stream, so the two dependent chains (loads -> pivots -> transcendental math) overlap
+    const int nchunk = (D + 63) / 64;
     for (int ch = 0; ch < nchunk; ++ch) {
-        const int d = ch * 32 + lane;
-        const bool dok = d < D;
-        // pivots of this chunk: mean of the first P rows (every CTA computes the same values, same order)
-        float mu_bar = 0.f, l_bar = 0.f, v_bar = 1.f;
-        if (dok) {
-            // fixed trip count + predication so that all 2*kPivotRows loads are in flight together
-            float pm[kPivotRows], pl[kPivotRows];
+        int dd[2];
+        bool dok[2];
 #pragma unroll
-            for (int i = 0; i < kPivotRows; ++i) {
-                pm[i] = i < P ? mu[(int64_t)i * mu_stride + d] : 0.f;
-                pl[i] = i < P ? lv[(int64_t)i * lv_stride + d] : 0.f;
-            }
+        for (int h = 0; h < 2; ++h) {
+            dd[h] = ch * 64 + h * 32 + lane;
+            dok[h] = dd[h] < D;
+        }
+        // first row of this warp: issued together with the pivot loads (one L2 round trip instead of two)
+        float mu_first[2] = {0.f, 0.f}, lv_first[2] = {0.f, 0.f};
+        {
+            const int i = i0 + w;
 #pragma unroll
-            for (int i = 0; i < kPivotRows; ++i) {
-                mu_bar += pm[i];
-                l_bar += pl[i];
-            }
-            mu_bar /= (float)P;
-            l_bar /= (float)P;
-            v_bar = expf(l_bar);
-            if (blk == 0 && w == 0) {
-                pivots[d] = mu_bar;
-                pivots[(int64_t)D + d] = l_bar;
-                pivots[2 * (int64_t)D + d] = v_bar;
+            for (int h = 0; h < 2; ++h)
+                if (dok[h] && w < R && i < B) {
+                    mu_first[h] = mu[(int64_t)i * mu_stride + dd[h]];
+                    lv_first[h] = lv[(int64_t)i * lv_stride + dd[h]];
+                }
+        }
+        // pivots: mean of the first P rows (every CTA computes the same values in the same order)
+        float mu_bar[2], l_bar[2], v_bar[2], ivb[2];
+        {
+            float pm[2][kPivotRows], pl[2][kPivotRows];
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int i = 0; i < kPivotRows; ++i) {   // fixed trip count + predication: all loads in flight together
+                    pm[h][i] = (dok[h] && i < P) ? mu[(int64_t)i * mu_stride + dd[h]] : 0.f;
+                    pl[h][i] = (dok[h] && i < P) ? lv[(int64_t)i * lv_stride + dd[h]] : 0.f;
+                }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                float sm = 0.f, sl = 0.f;
+#pragma unroll
+                for (int i = 0; i < kPivotRows; ++i) {
+                    sm += pm[h][i];
+                    sl += pl[h][i];
+                }
+                mu_bar[h] = sm / (float)P;
+                l_bar[h] = sl / (float)P;
+                v_bar[h] = expf(l_bar[h]);
+                ivb[h] = 1.0f / v_bar[h];
+                if (dok[h] && blk == 0 && w == 0) {
+                    pivots[dd[h]] = mu_bar[h];
+                    pivots[(int64_t)D + dd[h]] = l_bar[h];
+                    pivots[2 * (int64_t)D + dd[h]] = v_bar[h];
+                    pivots[3 * (int64_t)D + dd[h]] = 1.0 / (double)v_bar[h];
+                }
             }
         }
-        const float ivb = 1.0f / v_bar;
-        double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0, a6 = 0, a7 = 0;
+        double acc[2][kStats];
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int q = 0; q < kStats; ++q) acc[h][q] = 0.0;
         for (int r = w; r < R; r += kWarps) {
             const int i = i0 + r;
             if (i >= Bp) break;
             float es = 0.f, fs = 0.f, ks = 0.f;
-            if (dok) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                if (!dok[h]) continue;
+                const int d = dd[h];
                 float2 xv = make_float2(0.f, 0.f), yv = xv;
                 if (i < B) {
-                    const float mu_raw = mu[(int64_t)i * mu_stride + d], lv_raw = lv[(int64_t)i * lv_stride + d];
-                    const Elem e = make_elem(mu_raw, lv_raw, mu_bar, l_bar, v_bar);
+                    const float mu_raw = (r == w) ? mu_first[h] : mu[(int64_t)i * mu_stride + d];
+                    const float lv_raw = (r == w) ? lv_first[h] : lv[(int64_t)i * lv_stride + d];
+                    const Elem e = make_elem(mu_raw, lv_raw, mu_bar[h], l_bar[h], v_bar[h]);
                     const float sq = e.mc * e.mc;
-                    const float s = sq * ivb;
+                    const float s = sq * ivb[h];
                     const float t = e.a + (2.0f * e.b + e.b * e.b) * (1.0f + e.a);  // r^2 v v_bar - 1
                     xv = make_float2(e.a + s, e.mc);
                     yv = make_float2(e.b, -2.0f * e.mc * e.r);
                     Vp[(int64_t)i * D + d] = make_float4(e.mc, e.a, e.b, t);
-                    es = e.ema + s;            // all terms >= 0: well-conditioned fp32 sums
-                    fs = e.bpa + sq * e.r;
+                    es += e.ema + s;            // all terms >= 0: well-conditioned fp32 sums
+                    fs += e.bpa + sq * e.r;
                     // analytic KL term mu^2 + (e^lv - lv - 1), gaussian_encoder.py:219, second part cancellation-free
-                    ks = fmaf(mu_raw, mu_raw, expm1_minus_x(lv_raw, expm1f(lv_raw)));
-                    a0 += (double)e.a;
-                    a1 += (double)e.b;
-                    a2 += (double)e.a * (double)e.b;
-                    a3 += (double)e.mc;
-                    a4 += (double)sq;
-                    a5 += (double)e.r * (double)e.mc;
-                    a6 += (double)e.r * (double)sq;
-                    a7 += (double)e.apb;
+                    ks += fmaf(mu_raw, mu_raw, expm1_minus_x(lv_raw, expm1f(lv_raw)));
+                    acc[h][0] += (double)e.a;
+                    acc[h][1] += (double)e.b;
+                    acc[h][2] += (double)e.a * (double)e.b;
+                    acc[h][3] += (double)e.mc;
+                    acc[h][4] += (double)sq;
+                    acc[h][5] += (double)e.r * (double)e.mc;
+                    acc[h][6] += (double)e.r * (double)sq;
+                    acc[h][7] += (double)e.apb;
                 }
                 *reinterpret_cast<float2*>(Xp + (int64_t)i * Kp + 2 * d) = xv;
                 *reinterpret_cast<float2*>(Yp + (int64_t)i * Kp + 2 * d) = yv;
@@ -230,26 +286,23 @@ mpd_prepare_kernel(const float* __restrict__ mu, int64_t mu_stride, const float*
                 row_k[r] += (double)ks;
             }
         }
-        col_part[w][0][lane] = a0;
-        col_part[w][1][lane] = a1;
-        col_part[w][2][lane] = a2;
-        col_part[w][3][lane] = a3;
-        col_part[w][4][lane] = a4;
-        col_part[w][5][lane] = a5;
-        col_part[w][6][lane] = a6;
-        col_part[w][7][lane] = a7;
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int q = 0; q < kStats; ++q) col_part[w][q][h * 32 + lane] = acc[h][q];
         __syncthreads();
-        {
-            const int q = tid >> 5, l = tid & 31;   // 8 warps x 32 lanes = 8 statistics x 32 dims
-            if (ch * 32 + l < D) {
+        for (int o = tid; o < kStats * 64; o += kNT) {   // 8 statistics x 64 dims of this chunk
+            const int q = o >> 6, l = o & 63;
+            if (ch * 64 + l < D) {
                 double t = 0.0;
 #pragma unroll
                 for (int ww = 0; ww < kWarps; ++ww) t += col_part[ww][q][l];
-                part[((int64_t)blk * kStats + q) * D + ch * 32 + l] = t;
+                part[((int64_t)blk * kStats + q) * D + ch * 64 + l] = t;
             }
         }
         __syncthreads();
     }
+    MAE_STAMP(hdr, 1);
     // zero the K padding of the panels and publish the row sums
     for (int r = w; r < R; r += kWarps) {
         const int i = i0 + r;
@@ -265,6 +318,7 @@ mpd_prepare_kernel(const float* __restrict__ mu, int64_t mu_stride, const float*
         }
     }
 
+    MAE_STAMP(hdr, 2);
     __threadfence();
     __syncthreads();
     if (tid == 0) {
@@ -274,6 +328,7 @@ mpd_prepare_kernel(const float* __restrict__ mu, int64_t mu_stride, const float*
     __syncthreads();
     if (!is_last) return;
     __threadfence();
+    MAE_STAMP_ANY(hdr, 3);
 
     // last CTA: ordered sum of the partials, closed-form m_d (fp64, additions and products only)
     const double nb = (double)B;
@@ -291,9 +346,9 @@ mpd_prepare_kernel(const float* __restrict__ mu, int64_t mu_stride, const float*
         for (int q = 0; q < kStats; ++q) colstats[q * (int64_t)D + d] = s[q];
         // sum_{i!=j} (v_i r_j - 1)        = SA*SB - SAB + (B-1)*S(a+b)
         // sum_{i!=j} (mu_i-mu_j)^2 r_j    = S2*R0 - 2*S1*R1 + B*R2,   R0 = (B + SB)/v_bar
-        const double r0 = (nb + s[1]) / pivots[2 * (int64_t)D + d];
+        const double r0 = (nb + s[1]) * pivots[3 * (int64_t)D + d];
         const double tn = s[0] * s[1] - s[2] + (nb - 1.0) * s[7] + (s[4] * r0 - 2.0 * s[3] * s[5] + nb * s[6]);
-        const double md = 0.5 * tn / (nb * (nb - 1.0));
+        const double md = half_inv_pairs * tn;
         m_d_out[d] = (float)md;
         msum += md;
     }
@@ -302,6 +357,7 @@ mpd_prepare_kernel(const float* __restrict__ mu, int64_t mu_stride, const float*
         hdr->m = msum;
         hdr->ticket_prep = 0u;
     }
+    MAE_STAMP_ANY(hdr, 4);
 }
 
 // ------------------------------------------------------------------------------------------ tile helpers
@@ -347,6 +403,7 @@ mpd_fwd_kernel(const float* __restrict__ Xp, const float* __restrict__ Yp, const
     __shared__ double scratch[32];
     __shared__ bool is_last;
     const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    MAE_STAMP(hdr, 8);
     const float m = (float)hdr->m;
     double total = 0.0;
     const int ntiles = ntr * ntc;
@@ -396,6 +453,7 @@ mpd_fwd_kernel(const float* __restrict__ Xp, const float* __restrict__ Yp, const
             }
             __syncthreads();  // all reads of the last slab done before the next tile overwrites the buffers
         }
+        MAE_STAMP(hdr, 9);
         float psum = 0.f;
         const int jb = tj * T + tx * TM;
         float fj[TM];
@@ -431,6 +489,7 @@ mpd_fwd_kernel(const float* __restrict__ Xp, const float* __restrict__ Yp, const
         }
         total += (double)psum;
     }
+    MAE_STAMP(hdr, 10);
     total = block_sum(total, scratch);
     if (gridDim.x == 1) {  // single CTA: nothing to combine
         is_last = true;
@@ -455,6 +514,7 @@ mpd_fwd_kernel(const float* __restrict__ Xp, const float* __restrict__ Yp, const
             S_out[0] = (float)sqrt(s / (nb * (nb - 1.0) - 1.0));
         }
         hdr->ticket_fwd = 0u;
+        MAE_STAMP_ANY(hdr, 11);
     }
 }
 
@@ -490,7 +550,7 @@ __device__ __forceinline__ void mean_part(const double* __restrict__ cs, const d
     const double w = 0.5 * (double)g_m[d] / (nb * (nb - 1.0));
     const double SA = cs[0 * (int64_t)D + d], SB = cs[1 * (int64_t)D + d], S1 = cs[3 * (int64_t)D + d],
                  S2 = cs[4 * (int64_t)D + d], R1 = cs[5 * (int64_t)D + d];
-    const double ivb = 1.0 / pivots[2 * (int64_t)D + d];
+    const double ivb = pivots[3 * (int64_t)D + d];
     const double mc = pk.x, a = pk.y, b = pk.z, t = pk.w;
     const double r0 = (nb + SB) * ivb, rk = (1.0 + b) * ivb;
     const double dT_dmu = 2.0 * ((mc * r0 - R1) + rk * (nb * mc - S1));
@@ -525,7 +585,7 @@ mpd_bwd_small_kernel(const float* __restrict__ mu, int64_t mu_stride, const floa
     const float4 pi = active ? Vp[(int64_t)i * D + d] : zero4;  // {mc, a, b, t} of row i
     float gmu = 0.f, glv = 0.f;
     if (beta != 0.f) {
-        const float ivb = active ? (float)(1.0 / pivots[2 * (int64_t)D + d]) : 0.f;
+        const float ivb = active ? (float)pivots[3 * (int64_t)D + d] : 0.f;
         const float* kl_row = KL + (int64_t)i * Bp;    // KL_ij
         const float* klt_row = KLT + (int64_t)i * Bp;  // KL_ji
         const float opb_i = 1.0f + pi.z, opt_i = 1.0f + pi.w;
@@ -536,14 +596,22 @@ mpd_bwd_small_kernel(const float* __restrict__ mu, int64_t mu_stride, const floa
             const bool ok = jl < B && jl != i;
             const float w1l = ok ? beta * (kl_row[jl] - m) : 0.f;
             const float w2l = ok ? beta * (klt_row[jl] - m) : 0.f;
-#pragma unroll 8
-            for (int jj = 0; jj < 32; ++jj) {   // fixed trip count: the 8 unrolled panel loads overlap
-                const float w1 = __shfl_sync(0xffffffffu, w1l, jj);
-                const float w2 = __shfl_sync(0xffffffffu, w2l, jj);
-                const float4 pj = (active && jb + jj < B) ? vcol[(int64_t)(jb + jj) * D] : zero4;
-                const float dl = pi.x - pj.x;
-                gmu = fmaf(dl, fmaf(w1, 1.0f + pj.z, w2 * opb_i), gmu);
-                glv += w1 * (fmaf(pi.y, pj.z, pi.y) + pj.z) - w2 * (fmaf(pj.y, pi.w, pj.y) + pi.w + dl * dl * opt_i * ivb);
+#pragma unroll
+            for (int j0 = 0; j0 < 32; j0 += kBwdBatch) {
+                // explicit batch: kBwdBatch independent 16-byte panel loads in flight before any of them is consumed
+                float4 pj[kBwdBatch];
+#pragma unroll
+                for (int u = 0; u < kBwdBatch; ++u)
+                    pj[u] = (active && jb + j0 + u < B) ? __ldg(vcol + (int64_t)(jb + j0 + u) * D) : zero4;
+#pragma unroll
+                for (int u = 0; u < kBwdBatch; ++u) {
+                    const float w1 = __shfl_sync(0xffffffffu, w1l, j0 + u);
+                    const float w2 = __shfl_sync(0xffffffffu, w2l, j0 + u);
+                    const float dl = pi.x - pj[u].x;
+                    gmu = fmaf(dl, fmaf(w1, 1.0f + pj[u].z, w2 * opb_i), gmu);
+                    glv += w1 * (fmaf(pi.y, pj[u].z, pi.y) + pj[u].z) -
+                           w2 * (fmaf(pj[u].y, pi.w, pj[u].y) + pi.w + dl * dl * opt_i * ivb);
+                }
             }
         }
         gmu *= ivb;
@@ -704,7 +772,7 @@ mpd_bwd_tile_kernel(const float* __restrict__ mu, int64_t mu_stride, const float
             const int d = kcol >> 1;
             if (d >= D) continue;
             const float4 pi = Vp[(int64_t)i * D + d];  // {mc, a, b, t}
-            const float ivb = (float)(1.0 / pivots[2 * (int64_t)D + d]);
+            const float ivb = (float)pivots[3 * (int64_t)D + d];
             const float g1r = G1[ii][cb], g1m = G1[ii][cb + 1], g2x = G2[ii][cb], g2m = G2[ii][cb + 1];
             const float mc = pi.x, a = pi.y, ri = (1.0f + pi.z) * ivb, t = pi.w;
             // row side: mu_i sum_j W r_j - sum_j W mu_j r_j ; column side: -r_i (sum_j W' mu_j - mu_i sum_j W')
@@ -755,7 +823,8 @@ extern "C" int mae_mpd_prepare(const float* mu, int64_t mu_stride, const float* 
         mu, mu_stride, logvar, logvar_stride, (int)B, (int)D, (int)L.Kp, (int)L.prep_rows, (int)L.Bp,
         at<float>(workspace, L.xp), at<float>(workspace, L.yp),
         at<float4>(workspace, L.vp), at<float>(workspace, L.c), at<float>(workspace, L.l), at<double>(workspace, L.part_prep),
-        at<double>(workspace, L.colstats), at<double>(workspace, L.pivots), at<Hdr>(workspace, L.hdr), m_d, kl);
+        at<double>(workspace, L.colstats), at<double>(workspace, L.pivots), at<Hdr>(workspace, L.hdr), m_d, kl,
+        0.5 / ((double)B * ((double)B - 1.0)));
     return launch_status();
 }
 

@@ -14,7 +14,12 @@ dev = torch.device("cuda")
 lib = _lib.load()
 
 
-def chain(fn, n=200):
+REP = int(os.environ.get("REP", 40))
+
+
+def chain(fn, n=20):
+    """REP dependent copies of the op inside ONE graph (same stream -> serial kernel nodes); per-op time = replay / REP,
+    i.e. kernel duration + the in-graph dependent-launch gap."""
     s = torch.cuda.Stream()
     s.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(s):
@@ -24,8 +29,9 @@ def chain(fn, n=200):
     torch.cuda.synchronize()
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g):
-        fn()
-    for _ in range(10):
+        for _ in range(REP):
+            fn()
+    for _ in range(3):
         g.replay()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
@@ -34,7 +40,7 @@ def chain(fn, n=200):
         g.replay()
     e1.record()
     torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / n * 1e3
+    return e0.elapsed_time(e1) / n / REP * 1e3
 
 
 def main():
@@ -69,6 +75,19 @@ def main():
     res["assemble_bwd"] = chain(lambda: lib.mae_loss_assemble_bwd(P(g_S), P(sc), P(m_d), B, 1, D, 1.0, 1.0, 0.0, 0.0, P(derr), P(dkl), P(dm), P(dS), st()))
     for k, v in res.items():
         print("%-32s %8.2f us" % (k, v))
+    if os.environ.get("MAE_DEBUG_TIMING"):
+        # phase timestamps written by the -DMAE_DEBUG_TIMING build (ns, %globaltimer), CTA 0 / last CTA
+        torch.cuda.synchronize()
+        lib.mae_mpd_prepare(P(mu), D, P(lv), D, B, D, P(ws), ws.numel(), P(m_d), P(kl), st())
+        lib.mae_mpd_fwd(P(ws), ws.numel(), B, D, 0, B, 1, P(sumsq), P(S), st())
+        torch.cuda.synchronize()
+        dbg = ws[32:32 + 24 * 8].view(torch.int64).cpu().tolist()
+        t0 = dbg[0]
+        print("prepare: start 0 | elems done %d | rows published %d | last-CTA start %d | end %d  (ns)" %
+              tuple(d - t0 for d in dbg[1:5]))
+        t8 = dbg[8]
+        print("fwd: start 0 | K loop done %d | epilogue done %d | finalize done %d  (ns)" % tuple(d - t8 for d in dbg[9:12]))
+        print("prepare start -> fwd start: %d ns" % (t8 - t0))
 
 
 if __name__ == "__main__":
