@@ -1,0 +1,147 @@
+"""Batch-sharded (one process per GPU) loss head and IW-NLL evaluation.
+
+Partitioning: every rank owns ``B_loc`` samples.  Per-sample work (reparameterisation, KL,
+likelihood, IW estimator) needs no communication.  The MPD regulariser is a function of the GLOBAL batch:
+
+  * forward: ONE collective, an all-gather of the packed rows [B_loc, 2D] = (mu | logvar).  Every rank then runs the
+    O(B*D) pre-pass on the gathered panel (identical m_d everywhere, plus the analytic KL of every row, so the
+    free-bits clamp sees the global KL mean without another collective).  For global batches <= 2048 every rank also
+    evaluates the full B x B tile pass redundantly (a few microseconds; cheaper than an all-reduce's latency); above
+    that each rank evaluates its own row block and one fp64 scalar is all-reduced.
+  * backward: each rank computes the COMPLETE gradient of its own rows (their role as the i and as the j argument
+    of KL_ij), so there is no reduce-scatter of column gradients.
+
+Semantics of the returned loss: gradients w.r.t. the rank's local tensors are the gradients of the GLOBAL objective
+(mean over the global batch), so parameter gradients of the conv stacks must be SUM-reduced across ranks (plain
+``all_reduce(SUM)``, or DDP with the loss multiplied by the world size).  The loss VALUE a rank returns contains its
+share of the reconstruction term plus the global KL / MPD terms; ``global_loss`` all-reduces the share for logging.
+
+The collective plumbing is independent of the compute engine: ``ShardedHead(engine=...)`` takes any object with the
+``mae_b200.ops`` functions used below, which is how the world_size-2 gloo tests drive this file on CPU with the
+oracle standing in for the CUDA kernels.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+SMALL_GLOBAL_BATCH = 2048   # <= : every rank evaluates the whole MPD forward redundantly (no all-reduce)
+
+
+def _all_gather_rows(t: torch.Tensor, group) -> torch.Tensor:
+    """[n, c] -> [world*n, c], rank-major (equal n on every rank)."""
+    world = dist.get_world_size(group)
+    out = t.new_empty(world * t.size(0), t.size(1))
+    dist.all_gather_into_tensor(out, t.contiguous(), group=group)
+    return out
+
+
+class _ShardedKLMPD(torch.autograd.Function):
+    """(mu_loc, logvar_loc) -> (kl_loc [B_loc], m_d [D], S [], kl_others_sum [])."""
+
+    @staticmethod
+    def forward(ctx, mu, logvar, head):
+        ctx.set_materialize_grads(False)
+        group, eng = head.group, head.engine
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        b_loc = mu.size(0)
+        d = mu[0].numel()
+        packed = torch.cat([mu.reshape(b_loc, d), logvar.reshape(b_loc, d)], dim=1)
+        sizes = torch.tensor([b_loc], device=mu.device, dtype=torch.int64)
+        if head.check_equal_batches:
+            lo, hi = sizes.clone(), sizes.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
+            if int(lo) != int(hi):
+                raise RuntimeError("ShardedHead needs the same local batch on every rank (got %d..%d): pad or drop the "
+                                   "ragged tail batch" % (int(lo), int(hi)))
+        gathered = _all_gather_rows(packed, group)              # the one collective of the forward
+        b = world * b_loc
+        mu_all, lv_all = gathered[:, :d], gathered[:, d:]       # strided views, no copy
+        row0 = rank * b_loc
+        full = b <= SMALL_GLOBAL_BATCH
+        m_d, s_or_sumsq, kl_all, state = eng.mpd_rows_forward(mu_all, lv_all, row0, b_loc, full)
+        if full:
+            s = s_or_sumsq
+        else:
+            dist.all_reduce(s_or_sumsq, op=dist.ReduceOp.SUM, group=group)
+            s = eng.mpd_finalize(s_or_sumsq, b)
+            state.s = s
+        kl_loc = kl_all[row0:row0 + b_loc]
+        kl_others = kl_all.sum() - kl_loc.sum()
+        ctx.state, ctx.eng, ctx.rows, ctx.shapes = state, eng, (row0, b_loc), (mu.shape, logvar.shape)
+        ctx.keep = gathered
+        ctx.mark_non_differentiable(kl_others)
+        return kl_loc.clone(), m_d.view(mu.shape[1:]), s, kl_others
+
+    @staticmethod
+    def backward(ctx, g_kl, g_m, g_s, _g_others):
+        row0, b_loc = ctx.rows
+        dmu, dlv = ctx.eng.mpd_rows_backward(ctx.state, row0, b_loc, g_m, g_s, g_kl)
+        ctx.keep = None
+        return dmu.view(ctx.shapes[0]), dlv.view(ctx.shapes[1]), None
+
+
+class ShardedHead:
+    """Batch-sharded MAE loss head / evaluator.  ``engine`` defaults to ``mae_b200.ops`` (the CUDA kernels)."""
+
+    def __init__(self, group=None, engine=None, check_equal_batches: bool = False):
+        if engine is None:
+            from . import ops as engine
+        self.engine = engine
+        self.group = group
+        self.check_equal_batches = check_equal_batches
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+
+    # ------------------------------------------------------------------------------------------ training
+    def kl_mpd(self, mu, logvar):
+        """Analytic KL of the local rows, global MPD (m_d, S) and the KL sum of the other ranks' rows."""
+        return _ShardedKLMPD.apply(mu, logvar, self)
+
+    def _tail(self, dec_out, x, kl, m_d, s, kl_others, kind, ns, nmix, eta, gamma, free_bits):
+        eng = self.engine
+        b_glob = self.world * x.size(0)
+        if kind == "dmol":
+            err = eng.dmol_recon_error(dec_out, x, ns, nmix)
+        else:
+            err = eng.bernoulli_recon_error(dec_out, x)
+        ext = torch.stack([kl_others.new_zeros(()), kl_others]).to(kl.dtype)
+        return eng.assemble_loss(err, kl, m_d, s, eta, gamma, free_bits, 1.0 / b_glob, ext)
+
+    def loss_head_color(self, mu, logvar, eps, raw, x, nmix=10, eta=0.0, gamma=0.0, free_bits=0.0):
+        """C3 on a batch shard.  Returns (loss, recon [B_loc], KL [B_loc], stats, z) like ``heads.loss_head_color``."""
+        z, _ = self.engine.reparam_kl(mu, logvar, eps, want_kl=False)
+        kl, m_d, s, kl_others = self.kl_mpd(mu, logvar)
+        loss, stats, recon = self._tail(raw, x, kl, m_d, s, kl_others, "dmol", eps.size(1), nmix, eta, gamma, free_bits)
+        return loss, recon, kl, stats, z
+
+    def loss_head_binary(self, mu, logvar, eps, probs, x, eta=0.0, gamma=0.0, free_bits=0.0):
+        """C1/C2 on a batch shard."""
+        z, _ = self.engine.reparam_kl(mu, logvar, eps, want_kl=False)
+        kl, m_d, s, kl_others = self.kl_mpd(mu, logvar)
+        loss, stats, recon = self._tail(probs, x, kl, m_d, s, kl_others, "bernoulli", eps.size(1), 0, eta, gamma, free_bits)
+        return loss, recon, kl, stats, z
+
+    def global_loss(self, loss: torch.Tensor, stats: torch.Tensor) -> torch.Tensor:
+        """The global objective from a rank's loss: all-reduce of the reconstruction share (stats[4] = mean recon share)."""
+        share = stats[4].detach().clone()
+        total = share.clone()
+        dist.all_reduce(total, op=dist.ReduceOp.SUM, group=self.group)
+        return loss.detach() - share + total
+
+    # ----------------------------------------------------------------------------------------- evaluation
+    def shard(self, n_items: int):
+        """Contiguous block of ``n_items`` test images owned by this rank: (start, stop)."""
+        per, rem = divmod(n_items, self.world)
+        start = self.rank * per + min(self.rank, rem)
+        return start, start + per + (1 if self.rank < rem else 0)
+
+    def reduce_eval(self, sums: torch.Tensor) -> torch.Tensor:
+        """Final reduction of an evaluation: element-wise SUM of per-rank accumulators
+        (e.g. [sum nll_elbo, sum recon, sum kl, sum nll_iw, n_images]); the only communication of IW-NLL evaluation."""
+        out = sums.clone()
+        dist.all_reduce(out, op=dist.ReduceOp.SUM, group=self.group)
+        return out

@@ -331,6 +331,60 @@ def mpd_forward_only(mu: torch.Tensor, logvar: torch.Tensor, row0: int = 0, nrow
     return m_d.view(mu.shape[1:]), s, sumsq
 
 
+class MpdRowsState:
+    """What the row-blocked MPD backward needs from the forward (workspace with panels / stored KL, S, geometry)."""
+
+    def __init__(self, ws, mu2, ms, lv2, ls, b, d, s, path):
+        self.ws, self.mu2, self.ms, self.lv2, self.ls, self.b, self.d, self.s, self.path = ws, mu2, ms, lv2, ls, b, d, s, path
+
+
+def mpd_rows_forward(mu_all: torch.Tensor, logvar_all: torch.Tensor, row0: int, nrows: int, full: bool):
+    """Row-blocked MPD forward for batch-sharded runs (mu_all / logvar_all are the ALL-GATHERED posteriors [B,D]).
+
+    ``full=True`` (small global batch): every rank evaluates the whole B x B forward redundantly and keeps the KL
+    tiles -> (m_d, S, kl_all, state), no collective needed.  ``full=False``: only the tiles of rows
+    [row0,row0+nrows) -> (m_d, sumsq_partial[1] fp64, kl_all, state); the caller all-reduces ``sumsq`` and calls
+    :func:`mpd_finalize`, then sets ``state.s``.  kl_all is the analytic KL of every gathered row [B]."""
+    _req_cuda(mu_all, logvar_all)
+    mu2, ms = _rows(mu_all)
+    lv2, ls = _rows(logvar_all)
+    b, d = mu2.shape
+    if b < 2:
+        raise RuntimeError("the MPD regulariser needs a global batch of at least 2 posteriors")
+    dev = mu2.device
+    ws = _pool.take(_lib_().mae_mpd_workspace_bytes(b, d), dev)
+    kl_all = torch.empty(b, device=dev, dtype=torch.float32)
+    outs = _mpd_alloc_outputs(d, dev)
+    small = full and b <= 2048
+    if full:
+        m_d, s, sumsq = _mpd_launch_fwd(mu2, ms, lv2, ls, b, d, ws, small, outs, kl=kl_all)
+    else:
+        m_d, s, sumsq = _mpd_launch_fwd(mu2, ms, lv2, ls, b, d, ws, False, outs, row0, nrows, kl=kl_all)
+    state = MpdRowsState(ws, mu2, ms, lv2, ls, b, d, s if full else None, 1 if small else 2)
+    return m_d, (s if full else sumsq), kl_all, state
+
+
+def mpd_rows_backward(state: "MpdRowsState", row0: int, nrows: int, g_m, g_s, g_kl_rows):
+    """Gradient w.r.t. mu / logvar of rows [row0,row0+nrows) only (complete: as the i and as the j argument), so a
+    batch-sharded run needs no reduce-scatter.  g_kl_rows [nrows] is the upstream gradient of those rows' KL."""
+    dev = state.mu2.device
+    dmu = torch.empty(nrows, state.d, device=dev, dtype=torch.float32)
+    dlv = torch.empty_like(dmu)
+    g_m = g_m.contiguous().view(-1) if g_m is not None else None
+    g_s = g_s.contiguous() if g_s is not None else None
+    gkl_ptr = None
+    if g_kl_rows is not None:
+        g_kl_rows = g_kl_rows.contiguous()
+        gkl_ptr = g_kl_rows.data_ptr() - 4 * row0      # the kernel indexes gkl by GLOBAL row and only touches own rows
+    _lib.check(_lib_().mae_mpd_bwd(state.mu2.data_ptr(), state.ms, state.lv2.data_ptr(), state.ls, state.ws.data_ptr(),
+                                   state.ws.numel(), state.b, state.d, row0, nrows, _ptr(g_m), _ptr(g_s), state.s.data_ptr(),
+                                   gkl_ptr, dmu.data_ptr(), dlv.data_ptr(), 0, state.path, _stream()), "mae_mpd_bwd")
+    _count()
+    _pool.give(state.ws)
+    state.ws = None
+    return dmu, dlv
+
+
 def mpd_finalize(sumsq: torch.Tensor, batch: int) -> torch.Tensor:
     s = torch.empty((), device=sumsq.device, dtype=torch.float32)
     _lib.check(_lib_().mae_mpd_finalize(sumsq.data_ptr(), batch, s.data_ptr(), _stream()), "mae_mpd_finalize")
