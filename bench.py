@@ -206,12 +206,13 @@ def bench_ours(args):
     ring = max(4, int(L2_BYTES * 3 / step_bytes) + 1)                     # > 3x L2 of distinct data in flight
     hosts = [c3_host_inputs(i + 17 * rank, batch, latent) for i in range(min(ring, 4))]
     steps_obj = []
+    use_graph = not args.no_graph
     for i in range(ring):
         st = C3Step(hosts[i % len(hosts)], dev, dist_ctx)
-        if not args.no_graph:
+        if use_graph:
             st.capture()
         steps_obj.append(st)
-    launches_per_step = steps_obj[0].launches if not args.no_graph else None
+    launches_per_step = steps_obj[0].launches if use_graph else None
     if launches_per_step is None:
         ops.reset_launch_count()
         steps_obj[0].run()
@@ -230,7 +231,9 @@ def bench_ours(args):
     # (100 ms period) sees the load
     n_warm = 0
     t_w = time.perf_counter()
-    while n_warm < max(args.warmup, 3) or time.perf_counter() - t_w < 0.4:
+    # multi-rank: a FIXED count (every rank must issue the same number of collectives)
+    fixed = max(args.warmup, 3000) if world > 1 else None
+    while (n_warm < fixed) if fixed is not None else (n_warm < max(args.warmup, 3) or time.perf_counter() - t_w < 0.4):
         for i in range(50):
             steps_obj[(n_warm + i) % ring].run()
         n_warm += 50
@@ -324,7 +327,7 @@ def bench_ours(args):
                                    "full MAE loss fwd+bwd on synthetic encoder/decoder outputs",
                        "global_batch": world * batch, "parallelism": "dp%d (batch-sharded; MPD over the all-gathered batch)" % world,
                        "l2": "ring of %d input slabs (%.0f MB) cycled > 126 MB L2" % (ring, ring * step_bytes / 1e6),
-                       "cuda_graph": not args.no_graph},
+                       "cuda_graph": use_graph},
             "e2e": {"value": world * batch * e2e_steps / dt_e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 4, "ms_per_step": dt_e2e / e2e_steps * 1e3},
             "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,

@@ -39,19 +39,22 @@ def _all_gather_rows(t: torch.Tensor, group) -> torch.Tensor:
 
 
 class _ShardedKLMPD(torch.autograd.Function):
-    """(mu_loc, logvar_loc) -> (kl_loc [B_loc], m_d [D], S [], kl_others_sum [])."""
+    """(mu_loc, logvar_loc) -> (kl_loc [B_loc], m_d [D], S [], kl_others_sum []).
+
+    With the CUDA engine the whole chain (pack, all-gather, pre-pass, tiles) runs on the engine's side stream, so the
+    collective's latency and the MPD kernels overlap with the likelihood kernel on the main stream; the results are
+    joined by ``assemble_loss``.  The backward runs on the side stream too (it needs no collective)."""
 
     @staticmethod
-    def forward(ctx, mu, logvar, head):
-        ctx.set_materialize_grads(False)
+    def _compute(mu, logvar, head):
         group, eng = head.group, head.engine
         world, rank = dist.get_world_size(group), dist.get_rank(group)
         b_loc = mu.size(0)
         d = mu[0].numel()
         packed = torch.cat([mu.reshape(b_loc, d), logvar.reshape(b_loc, d)], dim=1)
-        sizes = torch.tensor([b_loc], device=mu.device, dtype=torch.int64)
         if head.check_equal_batches:
-            lo, hi = sizes.clone(), sizes.clone()
+            lo = torch.tensor([b_loc], device=mu.device, dtype=torch.int64)
+            hi = lo.clone()
             dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)
             dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
             if int(lo) != int(hi):
@@ -69,17 +72,53 @@ class _ShardedKLMPD(torch.autograd.Function):
             dist.all_reduce(s_or_sumsq, op=dist.ReduceOp.SUM, group=group)
             s = eng.mpd_finalize(s_or_sumsq, b)
             state.s = s
-        kl_loc = kl_all[row0:row0 + b_loc]
+        kl_loc = kl_all[row0:row0 + b_loc].clone()
         kl_others = kl_all.sum() - kl_loc.sum()
-        ctx.state, ctx.eng, ctx.rows, ctx.shapes = state, eng, (row0, b_loc), (mu.shape, logvar.shape)
+        return kl_loc, m_d, s, kl_others, state, gathered, row0, b_loc
+
+    @staticmethod
+    def forward(ctx, mu, logvar, head):
+        ctx.set_materialize_grads(False)
+        eng = head.engine
+        side = mu.is_cuda and hasattr(eng, "_side_stream") and head.overlap
+        if side:
+            dev = mu.device
+            cs, ss = torch.cuda.current_stream(dev), eng._side_stream(dev)
+            ss.wait_stream(cs)
+            with torch.cuda.stream(ss):
+                kl_loc, m_d, s, kl_others, state, gathered, row0, b_loc = _ShardedKLMPD._compute(mu, logvar, head)
+                ev = torch.cuda.Event()
+                ev.record(ss)
+            eng._pending_join[dev.index if dev.index is not None else torch.cuda.current_device()] = (
+                ev, (kl_loc, m_d, s, kl_others, gathered, mu, logvar))
+        else:
+            kl_loc, m_d, s, kl_others, state, gathered, row0, b_loc = _ShardedKLMPD._compute(mu, logvar, head)
+        ctx.state, ctx.eng, ctx.rows, ctx.shapes, ctx.side = state, eng, (row0, b_loc), (mu.shape, logvar.shape), side
         ctx.keep = gathered
         ctx.mark_non_differentiable(kl_others)
-        return kl_loc.clone(), m_d.view(mu.shape[1:]), s, kl_others
+        return kl_loc, m_d.view(mu.shape[1:]), s, kl_others
 
     @staticmethod
     def backward(ctx, g_kl, g_m, g_s, _g_others):
         row0, b_loc = ctx.rows
-        dmu, dlv = ctx.eng.mpd_rows_backward(ctx.state, row0, b_loc, g_m, g_s, g_kl)
+        eng = ctx.eng
+        if ctx.side:
+            dev = ctx.keep.device
+            cs, ss = torch.cuda.current_stream(dev), eng._side_stream(dev)
+            idx = dev.index if dev.index is not None else torch.cuda.current_device()
+            ready = eng._grads_ready.pop(idx, None)
+            ptrs = {t.data_ptr() for t in (g_m, g_s, g_kl) if t is not None}
+            if ready is not None and ptrs <= ready[1]:
+                ss.wait_event(ready[0])
+            else:
+                ss.wait_stream(cs)
+            with torch.cuda.stream(ss):
+                dmu, dlv = eng.mpd_rows_backward(ctx.state, row0, b_loc, g_m, g_s, g_kl)
+                ev = torch.cuda.Event()
+                ev.record(ss)
+            cs.wait_event(ev)
+        else:
+            dmu, dlv = eng.mpd_rows_backward(ctx.state, row0, b_loc, g_m, g_s, g_kl)
         ctx.keep = None
         return dmu.view(ctx.shapes[0]), dlv.view(ctx.shapes[1]), None
 
@@ -87,12 +126,13 @@ class _ShardedKLMPD(torch.autograd.Function):
 class ShardedHead:
     """Batch-sharded MAE loss head / evaluator.  ``engine`` defaults to ``mae_b200.ops`` (the CUDA kernels)."""
 
-    def __init__(self, group=None, engine=None, check_equal_batches: bool = False):
+    def __init__(self, group=None, engine=None, check_equal_batches: bool = False, overlap: bool = True):
         if engine is None:
             from . import ops as engine
         self.engine = engine
         self.group = group
-        self.check_equal_batches = check_equal_batches
+        self.check_equal_batches = check_equal_batches   # costs two tiny all-reduces and a host sync per step
+        self.overlap = overlap                           # all-gather + MPD on the side stream (CUDA engine only)
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
 
