@@ -185,6 +185,11 @@ def time_kernel(fn, n_iter, stream):
     return e0.elapsed_time(e1) / n_iter * 1e-3
 
 
+def _dbg(msg):
+    if os.environ.get("MAE_BENCH_DEBUG"):
+        print("[bench rank %s %.2f] %s" % (os.environ.get("RANK", "0"), time.perf_counter(), msg), file=sys.stderr, flush=True)
+
+
 def bench_ours(args):
     import torch.distributed as dist
     from mae_b200 import _lib, ops
@@ -207,10 +212,12 @@ def bench_ours(args):
     hosts = [c3_host_inputs(i + 17 * rank, batch, latent) for i in range(min(ring, 4))]
     steps_obj = []
     use_graph = not args.no_graph
+    _dbg("init done, ring=%d" % ring)
     for i in range(ring):
         st = C3Step(hosts[i % len(hosts)], dev, dist_ctx)
         if use_graph:
             st.capture()
+            _dbg("captured %d" % i)
         steps_obj.append(st)
     launches_per_step = steps_obj[0].launches if use_graph else None
     if launches_per_step is None:
@@ -238,6 +245,7 @@ def bench_ours(args):
             steps_obj[(n_warm + i) % ring].run()
         n_warm += 50
         torch.cuda.synchronize()
+    _dbg("warm-up done (%d steps)" % n_warm)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -247,11 +255,13 @@ def bench_ours(args):
     e1.record(stream)
     barrier()
     dt = e0.elapsed_time(e1) * 1e-3
+    _dbg("timed region done")
     loss_val = float(steps_obj[(args.steps - 1) % ring].loss)
     if world > 1:
         t = torch.tensor([dt], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t)
+    _dbg("max over ranks done")
 
     # ---- end to end through the public API with HOST buffers: H2D of the step's inputs, step, D2H of the loss
     e2e_steps = max(3, min(args.steps, 50))
@@ -271,12 +281,14 @@ def bench_ours(args):
 
     for _ in range(3):
         e2e_once()
+    _dbg("e2e warm done")
     barrier()
     e0.record(stream)
     for _ in range(e2e_steps):
         e2e_once()
     e1.record(stream)
     barrier()
+    _dbg("e2e done")
     dt_e2e = e0.elapsed_time(e1) * 1e-3
     if world > 1:
         t = torch.tensor([dt_e2e], device=dev, dtype=torch.float64)
@@ -303,8 +315,10 @@ def bench_ours(args):
         lib.mae_dmol_fwd(raws[j].data_ptr(), xs[j].data_ptr(), batch, 1, 10, 1024, err.data_ptr(), ws.data_ptr(), ws.numel(), sp)
 
     n_k = max(20, min(200, args.steps))
+    _dbg("kernel timing start")
     t_bwd = time_kernel(k_bwd, n_k, stream)
     t_fwd = time_kernel(k_fwd, n_k, stream)
+    _dbg("kernel timing done")
     roof = {"bound": "hbm", "kernel": "dmol_bwd_kernel", "achieved": bwd_b / t_bwd / 1e9, "peak": hbm_gbs, "unit": "GB/s",
             "frac": bwd_b / t_bwd / 1e9 / hbm_gbs, "traffic": None, "peak_source": peak_src,
             "bytes_per_launch": bwd_b, "us_per_launch": t_bwd * 1e6,
@@ -335,7 +349,7 @@ def bench_ours(args):
         }
     if world > 1:
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
     return out
 
 
@@ -512,6 +526,12 @@ def main():
         out = bench_ours(args)
     if out is not None:
         print(json.dumps(out))
+    sys.stdout.flush()
+    sys.stderr.flush()
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 and args.impl == "ours":
+        # NCCL communicator teardown with live CUDA graphs that captured collectives hangs in this stack
+        # (torch 2.11 / NCCL 2.28.9); every rank has passed the final barrier, so leave without it.
+        os._exit(0)
 
 
 if __name__ == "__main__":

@@ -17,6 +17,8 @@
 // The backward keeps the per-component local gradients in registers when a thread owns <= 5 components
 // (SPLIT >= 2) and recomputes them otherwise; d raw is written exactly once with streaming stores.
 // Any other (nmix, HW) runs on the generic one-thread-per-pixel kernels.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "hot_math.cuh"
 
@@ -187,8 +189,8 @@ struct MergeSmem {
 };
 
 // grid: (N, HW / kPix).  HW is a multiple of kPix (static_assert in the launcher).
-template <int NMIX, int HW, int SPLIT>
-__global__ void __launch_bounds__(Geo<NMIX, SPLIT>::kThreadsCta, SPLIT == 1 ? 4 : 1)
+template <int NMIX, int HW, int SPLIT, int MINB>
+__global__ void __launch_bounds__(Geo<NMIX, SPLIT>::kThreadsCta, MINB)
 dmol_fwd_kernel(const float* __restrict__ raw, const float* __restrict__ x, int ns, int chunks, float* __restrict__ err,
                 float* partial, unsigned int* tickets) {
     using G = Geo<NMIX, SPLIT>;
@@ -325,6 +327,233 @@ dmol_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ x, cons
     }
 }
 
+// ------------------------------------------------------------------- vectorised forward for large launches
+// IW-NLL evaluation shape (>= 512 Ki pixels per launch): one thread owns 4 consecutive pixels and reads every
+// channel plane with 16-byte loads, so a warp request is 512 contiguous bytes and a CTA sweeps 4 KB of each plane
+// (DRAM-friendly: with 4-byte loads the same kernel plateaued at ~48 % of the copy bandwidth for every SPLIT).
+// The component loop is NOT unrolled (4 inlined evaluations per iteration already fill the instruction cache
+// budget); the next component's 10 loads are issued before the current one is evaluated.
+struct CompV {
+    float4 logit, mu[3], rho[3], kap[3];
+};
+template <int NMIX, int HW>
+__device__ __forceinline__ void load_comp_v(const float* __restrict__ pbase, int m, CompV& c) {
+    c.logit = ldg_stream4(pbase + m * HW);
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        const float* q = pbase + (3 * m + ch) * HW;
+        c.mu[ch] = ldg_stream4(q + NMIX * HW);
+        c.rho[ch] = ldg_stream4(q + 4 * NMIX * HW);
+        c.kap[ch] = ldg_stream4(q + 7 * NMIX * HW);
+    }
+}
+__device__ __forceinline__ float f4(const float4& v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w)); }
+
+constexpr int kVecThreads = 256;
+constexpr int kVecPix = 4 * kVecThreads;  // 1024 pixels per CTA
+
+template <int NMIX, int HW, int MINB>
+__global__ void __launch_bounds__(kVecThreads, MINB)
+dmol_fwd_vec4_kernel(const float* __restrict__ raw, const float* __restrict__ x, int ns, int chunks, float* __restrict__ err,
+                     float* partial, unsigned int* tickets) {
+    __shared__ float scratch[32];
+    __shared__ bool is_last;
+    const int64_t n = blockIdx.x;
+    const int64_t b = n / ns;
+    const int pix = blockIdx.y * kVecPix + threadIdx.x * 4;
+    const float* pbase = raw + n * (int64_t)(10 * NMIX * HW) + pix;
+    CompV cur, nxt;
+    load_comp_v<NMIX, HW>(pbase, 0, cur);
+    float xs[4][3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float4 xv = __ldg(reinterpret_cast<const float4*>(x + (b * 3 + c) * HW + pix));
+        xs[0][c] = xv.x; xs[1][c] = xv.y; xs[2][c] = xv.z; xs[3][c] = xv.w;
+    }
+    hm::Lse lt[4], ll[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        lt[p].init();
+        ll[p].init();
+    }
+#pragma unroll 1
+    for (int m = 0; m < NMIX; ++m) {
+        if (m + 1 < NMIX) load_comp_v<NMIX, HW>(pbase, m + 1, nxt);
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const float mu[3] = {f4(cur.mu[0], p), f4(cur.mu[1], p), f4(cur.mu[2], p)};
+            const float rho[3] = {f4(cur.rho[0], p), f4(cur.rho[1], p), f4(cur.rho[2], p)};
+            const float kap[3] = {f4(cur.kap[0], p), f4(cur.kap[1], p), f4(cur.kap[2], p)};
+            const float lg = f4(cur.logit, p);
+            const float T = hm::dmol_component<false>(mu, rho, kap, xs[p], nullptr, nullptr, nullptr);
+            lt[p].push(T + lg);
+            ll[p].push(lg);
+        }
+        cur = nxt;
+    }
+    float val = 0.f;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) val += ll[p].value() - lt[p].value();
+    val = block_sum(val, scratch);
+    publish_partial(val, n, blockIdx.y, chunks, err, partial, tickets, &is_last);
+}
+
+// ------------------------------------------------------- vectorised split kernels for training-size launches
+// Same 16-byte loads (4 pixels per thread), with the components of a pixel split over SPLIT warps like the scalar
+// kernels above: a CTA owns G groups of 128 pixels, group = SPLIT warps, warp `part` evaluates components
+// part, part+SPLIT, ...  Each thread has K*4 independent component evaluations in flight (ILP) instead of relying
+// on warp count, and all its K*10 loads are issued up front.
+template <int NMIX, int SPLIT>
+struct GeoV {
+    static constexpr int kK = NMIX / SPLIT;
+    static constexpr int kG = 1;
+    static constexpr int kThreadsCta = 32 * SPLIT * kG;
+    static constexpr int kPix = 128 * kG;
+    static_assert(NMIX % SPLIT == 0, "SPLIT must divide the number of components");
+};
+template <int NMIX, int SPLIT>
+struct MergeSmemV {
+    float4 mt[GeoV<NMIX, SPLIT>::kG][SPLIT][32], st[GeoV<NMIX, SPLIT>::kG][SPLIT][32];
+    float4 ml[GeoV<NMIX, SPLIT>::kG][SPLIT][32], sl[GeoV<NMIX, SPLIT>::kG][SPLIT][32];
+};
+__device__ __forceinline__ float& f4r(float4& v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w)); }
+
+// log-sum-exp over the SPLIT partial states of pixel p (component p of the float4s)
+template <int SPLIT>
+__device__ __forceinline__ float lse_merge_v(const float4 (*mxs)[32], const float4 (*sms)[32], int lane, int p) {
+    float mx = f4(mxs[0][lane], p);
+#pragma unroll
+    for (int q = 1; q < SPLIT; ++q) mx = fmaxf(mx, f4(mxs[q][lane], p));
+    float sm = 0.f;
+#pragma unroll
+    for (int q = 0; q < SPLIT; ++q) sm = fmaf(f4(sms[q][lane], p), hm::fast_ex2(hm::kLog2e * (f4(mxs[q][lane], p) - mx)), sm);
+    return fmaf(hm::fast_lg2(sm), hm::kLn2, mx);
+}
+
+template <int NMIX, int HW, int SPLIT, bool BWD>
+__global__ void __launch_bounds__(GeoV<NMIX, SPLIT>::kThreadsCta)
+dmol_split_vec4_kernel(const float* __restrict__ raw, const float* __restrict__ x, const float* __restrict__ g, int g_stride,
+                       float g_mul, int ns, int chunks, float* __restrict__ err, float* partial, unsigned int* tickets,
+                       float* __restrict__ draw) {
+    using G = GeoV<NMIX, SPLIT>;
+    constexpr int K = G::kK;
+    __shared__ MergeSmemV<NMIX, SPLIT> ms;
+    __shared__ float scratch[32];
+    __shared__ bool is_last;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int part = w % SPLIT, grp = w / SPLIT;
+    const int64_t n = blockIdx.x;
+    const int64_t b = n / ns;
+    const int pix = blockIdx.y * G::kPix + grp * 128 + lane * 4;
+    const int64_t off = n * (int64_t)(10 * NMIX * HW) + pix;
+    const float* pbase = raw + off;
+
+    CompV cp[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) load_comp_v<NMIX, HW>(pbase, part + k * SPLIT, cp[k]);
+    float xs[4][3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float4 xv = __ldg(reinterpret_cast<const float4*>(x + (b * 3 + c) * HW + pix));
+        xs[0][c] = xv.x; xs[1][c] = xv.y; xs[2][c] = xv.z; xs[3][c] = xv.w;
+    }
+    float tl[K][4], lg[K][4];
+    float gmu[BWD ? K : 1][4][3], grho[BWD ? K : 1][4][3], gkap[BWD ? K : 1][4][3];
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const float mu[3] = {f4(cp[k].mu[0], p), f4(cp[k].mu[1], p), f4(cp[k].mu[2], p)};
+            const float rho[3] = {f4(cp[k].rho[0], p), f4(cp[k].rho[1], p), f4(cp[k].rho[2], p)};
+            const float kap[3] = {f4(cp[k].kap[0], p), f4(cp[k].kap[1], p), f4(cp[k].kap[2], p)};
+            lg[k][p] = f4(cp[k].logit, p);
+            float T;
+            if (BWD) T = hm::dmol_component<true>(mu, rho, kap, xs[p], gmu[BWD ? k : 0][p], grho[BWD ? k : 0][p], gkap[BWD ? k : 0][p]);
+            else T = hm::dmol_component<false>(mu, rho, kap, xs[p], nullptr, nullptr, nullptr);
+            tl[k][p] = T + lg[k][p];
+        }
+    // per-thread partial log-sum-exp states of its K components, for each of the 4 pixels
+    float4 mt4, st4, ml4, sl4;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        float mt = tl[0][p], ml = lg[0][p];
+#pragma unroll
+        for (int k = 1; k < K; ++k) {
+            mt = fmaxf(mt, tl[k][p]);
+            ml = fmaxf(ml, lg[k][p]);
+        }
+        float st = 0.f, sl = 0.f;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            st += hm::fast_ex2(hm::kLog2e * (tl[k][p] - mt));
+            sl += hm::fast_ex2(hm::kLog2e * (lg[k][p] - ml));
+        }
+        f4r(mt4, p) = mt; f4r(st4, p) = st; f4r(ml4, p) = ml; f4r(sl4, p) = sl;
+    }
+    ms.mt[grp][part][lane] = mt4;
+    ms.st[grp][part][lane] = st4;
+    ms.ml[grp][part][lane] = ml4;
+    ms.sl[grp][part][lane] = sl4;
+    __syncthreads();
+    if (!BWD) {
+        float val = 0.f;
+        if (part == 0) {
+#pragma unroll
+            for (int p = 0; p < 4; ++p)
+                val += lse_merge_v<SPLIT>(ms.ml[grp], ms.sl[grp], lane, p) - lse_merge_v<SPLIT>(ms.mt[grp], ms.st[grp], lane, p);
+        }
+        val = block_sum(val, scratch);
+        publish_partial(val, n, blockIdx.y, chunks, err, partial, tickets, &is_last);
+    } else {
+        const float gn = __ldg(g + n * g_stride) * g_mul;
+        float zt[4], zl[4];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            zt[p] = lse_merge_v<SPLIT>(ms.mt[grp], ms.st[grp], lane, p);
+            zl[p] = lse_merge_v<SPLIT>(ms.ml[grp], ms.sl[grp], lane, p);
+        }
+        float* ob = draw + off;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int m = part + k * SPLIT;
+            float4 o_lg, o_mu[3], o_rho[3], o_kap[3];
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                const float wgt = hm::fast_ex2(hm::kLog2e * (tl[k][p] - zt[p]));  // responsibility of the component
+                const float pri = hm::fast_ex2(hm::kLog2e * (lg[k][p] - zl[p]));  // softmax(logits)
+                const float a = -gn * wgt;                                        // d err / d T_m
+                f4r(o_lg, p) = gn * (pri - wgt);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    f4r(o_mu[c], p) = a * gmu[BWD ? k : 0][p][c];
+                    f4r(o_rho[c], p) = a * grho[BWD ? k : 0][p][c];
+                    f4r(o_kap[c], p) = a * gkap[BWD ? k : 0][p][c];
+                }
+            }
+            __stcs(reinterpret_cast<float4*>(ob + m * HW), o_lg);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                float* q = ob + (3 * m + c) * HW;
+                __stcs(reinterpret_cast<float4*>(q + NMIX * HW), o_mu[c]);
+                __stcs(reinterpret_cast<float4*>(q + 4 * NMIX * HW), o_rho[c]);
+                __stcs(reinterpret_cast<float4*>(q + 7 * NMIX * HW), o_kap[c]);
+            }
+        }
+    }
+}
+
+template <int HW, int SPLIT, bool BWD>
+int launch_split_vec4(const float* raw, const float* x, const float* g, int gs, float gm, int64_t N, int ns, float* err,
+                      float* partial, unsigned int* tickets, float* draw, cudaStream_t s) {
+    using G = GeoV<10, SPLIT>;
+    static_assert(HW % G::kPix == 0, "HW must be a multiple of the CTA pixel count");
+    const int chunks = HW / G::kPix;
+    dim3 grid((unsigned)N, (unsigned)chunks);
+    dmol_split_vec4_kernel<10, HW, SPLIT, BWD><<<grid, G::kThreadsCta, 0, s>>>(raw, x, g, gs, gm, ns, chunks, err, partial, tickets,
+                                                                              draw);
+    return launch_status();
+}
+
 struct DmolWs {
     int64_t partial_off, ticket_off, total;
 };
@@ -346,20 +575,29 @@ int check_dmol(int64_t B, int64_t ns, int64_t nmix, int64_t HW) {
 
 // SPLIT from the number of pixel-threads a launch would have: fill ~2 waves of the 148 x 2048 thread slots
 int pick_split(int64_t pixels) {
+    static const int forced = getenv("MAE_DMOL_SPLIT") ? atoi(getenv("MAE_DMOL_SPLIT")) : 0;
+    if (forced == 1 || forced == 2 || forced == 5) return forced;
     if (pixels >= (1ll << 19)) return 1;
     if (pixels >= (1ll << 17)) return 2;
     return 5;
 }
 
-template <int NMIX, int HW, int SPLIT>
+template <int NMIX, int HW, int SPLIT, int MINB = 1>
 int launch_fwd(const float* raw, const float* x, int64_t N, int ns, float* err, float* partial, unsigned int* tickets,
                cudaStream_t s) {
     using G = Geo<NMIX, SPLIT>;
     static_assert(HW % G::kPix == 0, "HW must be a multiple of the CTA pixel count");
     const int chunks = HW / G::kPix;
     dim3 grid((unsigned)N, (unsigned)chunks);
-    dmol_fwd_kernel<NMIX, HW, SPLIT><<<grid, G::kThreadsCta, 0, s>>>(raw, x, ns, chunks, err, partial, tickets);
+    dmol_fwd_kernel<NMIX, HW, SPLIT, MINB><<<grid, G::kThreadsCta, 0, s>>>(raw, x, ns, chunks, err, partial, tickets);
     return launch_status();
+}
+
+// tuning knobs for profiling runs (read once): MAE_DMOL_SPLIT in {1,2,5} overrides pick_split,
+// MAE_DMOL_S1_OCC in {2,3,4} selects the register budget (min CTAs/SM) of the one-thread-per-pixel forward
+int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : dflt;
 }
 
 template <int NMIX, int HW, int SPLIT>
@@ -374,8 +612,25 @@ int launch_bwd(const float* raw, const float* x, const float* g, int gs, float g
 template <int HW>
 int dispatch_fwd(int split, const float* raw, const float* x, int64_t N, int ns, float* err, float* partial,
                  unsigned int* tickets, cudaStream_t s) {
+    static const int occ = env_int("MAE_DMOL_S1_OCC", 4);
+    static const int vec = env_int("MAE_DMOL_VEC4", 1);
+    if (split == 1 && vec && HW % kVecPix == 0) {
+        const int chunks = HW / kVecPix;
+        dim3 grid((unsigned)N, (unsigned)chunks);
+        static const int vocc = env_int("MAE_DMOL_VEC_OCC", 2);
+        if (vocc == 3) dmol_fwd_vec4_kernel<10, HW, 3><<<grid, kVecThreads, 0, s>>>(raw, x, ns, chunks, err, partial, tickets);
+        else if (vocc == 4) dmol_fwd_vec4_kernel<10, HW, 4><<<grid, kVecThreads, 0, s>>>(raw, x, ns, chunks, err, partial, tickets);
+        else dmol_fwd_vec4_kernel<10, HW, 2><<<grid, kVecThreads, 0, s>>>(raw, x, ns, chunks, err, partial, tickets);
+        return launch_status();
+    }
+    static const int vsplit = env_int("MAE_DMOL_VSPLIT", 0);
+    if (split != 1 && vsplit == 5) return launch_split_vec4<HW, 5, false>(raw, x, nullptr, 0, 0.f, N, ns, err, partial, tickets, nullptr, s);
+    if (split != 1 && vsplit == 10) return launch_split_vec4<HW, 10, false>(raw, x, nullptr, 0, 0.f, N, ns, err, partial, tickets, nullptr, s);
     switch (split) {
-        case 1: return launch_fwd<10, HW, 1>(raw, x, N, ns, err, partial, tickets, s);
+        case 1:
+            if (occ == 2) return launch_fwd<10, HW, 1, 2>(raw, x, N, ns, err, partial, tickets, s);
+            if (occ == 3) return launch_fwd<10, HW, 1, 3>(raw, x, N, ns, err, partial, tickets, s);
+            return launch_fwd<10, HW, 1, 4>(raw, x, N, ns, err, partial, tickets, s);
         case 2: return launch_fwd<10, HW, 2>(raw, x, N, ns, err, partial, tickets, s);
         default: return launch_fwd<10, HW, 5>(raw, x, N, ns, err, partial, tickets, s);
     }
@@ -384,6 +639,9 @@ template <int HW>
 int dispatch_bwd(int split, const float* raw, const float* x, const float* g, int gs, float gm, int64_t N, int ns,
                  float* draw, cudaStream_t s) {
     // the backward always splits a pixel over >= 2 warps so the local gradients stay in registers
+    static const int vsplit = env_int("MAE_DMOL_VSPLIT", 0);
+    if (vsplit == 5) return launch_split_vec4<HW, 5, true>(raw, x, g, gs, gm, N, ns, nullptr, nullptr, nullptr, draw, s);
+    if (vsplit == 10) return launch_split_vec4<HW, 10, true>(raw, x, g, gs, gm, N, ns, nullptr, nullptr, nullptr, draw, s);
     if (split <= 2) return launch_bwd<10, HW, 2>(raw, x, g, gs, gm, N, ns, draw, s);
     return launch_bwd<10, HW, 5>(raw, x, g, gs, gm, N, ns, draw, s);
 }

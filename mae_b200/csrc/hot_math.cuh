@@ -146,13 +146,10 @@ MAE_HD float bernoulli_derr_dp(float p, float x) {  // d(-logprob)/dp
 struct Lse {
     float m, s;
     MAE_HD void init() { m = -INFINITY; s = 0.f; }
-    MAE_HD void push(float v) {
-        if (v <= m) {
-            s += fast_ex2(kLog2e * (v - m));
-        } else {
-            s = s * fast_ex2(kLog2e * (m - v)) + 1.0f;
-            m = v;
-        }
+    MAE_HD void push(float v) {   // branch-free, one SFU op: e = exp(-|v-m|); s = v<=m ? s+e : s*e+1
+        const float e = fast_ex2(-kLog2e * fabsf(v - m));
+        s = (v <= m) ? (s + e) : fmaf(s, e, 1.0f);
+        m = fmaxf(m, v);
     }
     MAE_HD void merge(const Lse& o) {
         if (o.m == -INFINITY) return;
