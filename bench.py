@@ -142,7 +142,8 @@ class C3Step:
         self.raw.grad = None
         mu, lv = self.mu, self.lv
         if self.dist is None:
-            loss, recon, kl, stats, z = self.heads.loss_head_color(mu, lv, self.eps, self.raw, self.x, 10, ETA, GAMMA, FREE_BITS)
+            loss, recon, kl, stats, z = self.heads.loss_head_color(mu, lv, self.eps, self.raw, self.x, 10, ETA, GAMMA, FREE_BITS,
+                                                                   defer_join=True)
         else:
             loss, recon, kl, stats, z = self.dist.loss_head_color(mu, lv, self.eps, self.raw, self.x, 10, ETA, GAMMA, FREE_BITS)
         loss.backward(gradient=self.one)
@@ -397,7 +398,7 @@ def bench_extra(dev, hbm_gbs):
         mu_l.grad = None
         lv_l.grad = None
         probs.grad = None
-        loss = heads.loss_head_binary(mu_l, lv_l, eps, probs, xb, ETA, GAMMA, FREE_BITS)[0]
+        loss = heads.loss_head_binary(mu_l, lv_l, eps, probs, xb, ETA, GAMMA, FREE_BITS, defer_join=True)[0]
         loss.backward(gradient=one)
         return loss
 

@@ -133,6 +133,7 @@ class ShardedHead:
         self.group = group
         self.check_equal_batches = check_equal_batches   # costs two tiny all-reduces and a host sync per step
         self.overlap = overlap                           # all-gather + MPD on the side stream (CUDA engine only)
+        self.defer_join = True                           # loss value valid after backward() / ops.join_side()
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
 
@@ -144,6 +145,12 @@ class ShardedHead:
     def _tail(self, dec_out, x, kl, m_d, s, kl_others, kind, ns, nmix, eta, gamma, free_bits):
         eng = self.engine
         b_glob = self.world * x.size(0)
+        if hasattr(eng, "loss_tail") and dec_out.is_cuda:
+            # fused likelihood + objective node; with overlap the objective's tiny kernels stay on the side stream
+            # behind the all-gather / MPD chain, so the main stream runs likelihood fwd -> likelihood bwd back to back
+            ext = torch.stack([kl_others.new_zeros(()), kl_others]).to(kl.dtype)
+            return eng.loss_tail(dec_out, x, kl, m_d, s, kind, ns, nmix, eta, gamma, free_bits, 1.0 / b_glob, ext,
+                                 defer_join=self.overlap and self.defer_join)
         if kind == "dmol":
             err = eng.dmol_recon_error(dec_out, x, ns, nmix)
         else:

@@ -12,19 +12,23 @@ import torch
 from . import ops
 
 
-def loss_head_binary(mu, logvar, eps, probs, x, eta=0.0, gamma=0.0, free_bits=0.0):
-    """C1/C2: reparam + analytic KL, MPD, Bernoulli likelihood, assembly.  Returns (loss, recon, KL, stats, z)."""
+def loss_head_binary(mu, logvar, eps, probs, x, eta=0.0, gamma=0.0, free_bits=0.0, defer_join=False):
+    """C1/C2: reparam + analytic KL, MPD, Bernoulli likelihood, assembly.  Returns (loss, recon, KL, stats, z).
+    ``defer_join``: see ops.loss_tail (outputs valid after backward() / ops.join_side())."""
     z, _ = ops.reparam_kl(mu, logvar, eps, want_kl=False)
     kl, m_d, s = ops.kl_mpd(mu, logvar, side_stream=True)   # overlaps with the likelihood; joined inside loss_tail
-    loss, stats, recon = ops.loss_tail(probs, x, kl, m_d, s, "bernoulli", eps.size(1), 0, eta, gamma, free_bits)
+    loss, stats, recon = ops.loss_tail(probs, x, kl, m_d, s, "bernoulli", eps.size(1), 0, eta, gamma, free_bits,
+                                       defer_join=defer_join)
     return loss, recon, kl, stats, z
 
 
-def loss_head_color(mu, logvar, eps, raw, x, nmix=10, eta=0.0, gamma=0.0, free_bits=0.0):
-    """C3: reparam + analytic KL, MPD, discretized-logistic-mixture likelihood, assembly."""
+def loss_head_color(mu, logvar, eps, raw, x, nmix=10, eta=0.0, gamma=0.0, free_bits=0.0, defer_join=False):
+    """C3: reparam + analytic KL, MPD, discretized-logistic-mixture likelihood, assembly.
+    ``defer_join``: see ops.loss_tail (outputs valid after backward() / ops.join_side())."""
     z, _ = ops.reparam_kl(mu, logvar, eps, want_kl=False)
     kl, m_d, s = ops.kl_mpd(mu, logvar, side_stream=True)   # overlaps with the likelihood; joined inside loss_tail
-    loss, stats, recon = ops.loss_tail(raw, x, kl, m_d, s, "dmol", eps.size(1), nmix, eta, gamma, free_bits)
+    loss, stats, recon = ops.loss_tail(raw, x, kl, m_d, s, "dmol", eps.size(1), nmix, eta, gamma, free_bits,
+                                       defer_join=defer_join)
     return loss, recon, kl, stats, z
 
 

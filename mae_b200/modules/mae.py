@@ -55,7 +55,7 @@ class MAE(nn.Module):
             KL, m_d, S = ops.kl_mpd(mu, logvar, side_stream=True)
             dec_out = dec.likelihood_input(x, z.view(z.size(0), z.size(1), *z_shape_dec))
             loss, stats, recon = ops.loss_tail(dec_out, x, KL, m_d, S, dec.likelihood_kind, nsamples,
-                                               getattr(dec, "nmix", 0), eta, gamma, free_bits)
+                                               getattr(dec, "nmix", 0), eta, gamma, free_bits)   # joins the side stream
         else:
             if isinstance(enc, GaussianEncoder):
                 z, KL, (m_d, S) = enc.encode(x, nsamples, _side_stream=True)   # MPD overlaps with the decoder

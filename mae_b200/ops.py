@@ -632,14 +632,19 @@ class _LossTail(torch.autograd.Function):
     """likelihood + objective assembly as ONE autograd node (the part of MAE.loss after the decoder):
     forward = likelihood kernel, join of the MPD side stream, assembly kernel; backward = likelihood backward on the
     main stream (taking d loss as a broadcast device scalar, so it does not wait for anything else) and, concurrently
-    on the side stream, the tiny assembly backward that feeds the KL / MPD backward."""
+    on the side stream, the tiny assembly backward that feeds the KL / MPD backward.
+
+    ``defer``: the assembly kernels run on the side stream behind the MPD chain, so the main stream goes straight
+    from the likelihood forward to the likelihood backward; the returned values are valid on the main stream only
+    after ``backward()`` (which joins) or ``ops.join_side()``."""
 
     @staticmethod
-    def forward(ctx, dec_out, x, kl, m_d, s, kind, ns, nmix, eta, gamma, free_bits):
+    def forward(ctx, dec_out, x, kl, m_d, s, ext_sums, kind, ns, nmix, eta, gamma, free_bits, inv_batch, defer):
         ctx.set_materialize_grads(False)
-        _req_cuda(dec_out, x, kl, m_d, s)
+        _req_cuda(dec_out, x, kl, m_d, s, ext_sums)
         lib = _lib_()
         dev = dec_out.device
+        idx = dev.index if dev.index is not None else torch.cuda.current_device()
         b = x.size(0)
         out_c = dec_out.contiguous()
         if kind == "dmol":
@@ -663,19 +668,35 @@ class _LossTail(torch.autograd.Function):
             _lib.check(lib.mae_bernoulli_fwd(out_c.data_ptr(), x_c.data_ptr(), b, ns, p, err.data_ptr(), _stream()),
                        "mae_bernoulli_fwd")
             geom = (p,)
-        join_side(dev)
         kl_c = kl.contiguous()
         m_c = m_d.contiguous().view(-1) if m_d is not None else None
         d = m_c.numel() if m_c is not None else 0
         scalars = torch.empty(6, device=dev, dtype=torch.float32)
         recon = torch.empty(b, device=dev, dtype=torch.float32)
-        _lib.check(lib.mae_loss_assemble_fwd(err.data_ptr(), kl_c.data_ptr(), _ptr(m_c), _ptr(s), None, b, ns, d, eta, gamma,
-                                             free_bits, 0.0, scalars.data_ptr(), recon.data_ptr(), _stream()),
-                   "mae_loss_assemble_fwd")
+
+        def assemble():
+            _lib.check(lib.mae_loss_assemble_fwd(err.data_ptr(), kl_c.data_ptr(), _ptr(m_c), _ptr(s), _ptr(ext_sums), b, ns, d,
+                                                 eta, gamma, free_bits, inv_batch, scalars.data_ptr(), recon.data_ptr(),
+                                                 _stream()), "mae_loss_assemble_fwd")
+
+        if defer:
+            cs, ss = torch.cuda.current_stream(dev), _side_stream(dev)
+            ev_err = torch.cuda.Event()
+            ev_err.record(cs)
+            prev = _pending_join.pop(idx, None)      # the MPD chain already sits on the side stream: ordered by it
+            with torch.cuda.stream(ss):
+                ss.wait_event(ev_err)
+                assemble()
+                ev = torch.cuda.Event()
+                ev.record(ss)
+            _pending_join[idx] = (ev, (prev, err, kl_c, m_c, s, ext_sums, scalars, recon))
+        else:
+            join_side(dev)
+            assemble()
         _count(2)
         ctx.save_for_backward(out_c, x_c, scalars, m_c if m_c is not None else scalars)
-        ctx.meta = (kind, b, ns, nmix, geom, d, eta, gamma, free_bits, dec_out.shape,
-                    m_d.shape if m_d is not None else None, s is not None)
+        ctx.meta = (kind, b, ns, nmix, geom, d, eta, gamma, free_bits, inv_batch, dec_out.shape,
+                    m_d.shape if m_d is not None else None, s is not None, defer)
         loss, stats = scalars[0], scalars[1:]
         ctx.mark_non_differentiable(stats, recon)
         return loss, stats, recon
@@ -683,19 +704,26 @@ class _LossTail(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gloss, _gs, _gr):
         if gloss is None:
-            return (None,) * 11
+            return (None,) * 14
         out_c, x_c, scalars, m_c = ctx.saved_tensors
-        kind, b, ns, nmix, geom, d, eta, gamma, free_bits, out_shape, m_shape, has_s = ctx.meta
+        kind, b, ns, nmix, geom, d, eta, gamma, free_bits, inv_batch, out_shape, m_shape, has_s, defer = ctx.meta
         lib = _lib_()
         dev = out_c.device
+        idx = dev.index if dev.index is not None else torch.cuda.current_device()
         gloss = gloss.contiguous()
         cs = torch.cuda.current_stream(dev)
         ss = _side_stream(dev)
-        ss.wait_stream(cs)                      # d loss is ready on the main stream
+        if defer:
+            ev_g = torch.cuda.Event()
+            ev_g.record(cs)
+            ss.wait_event(ev_g)                 # d loss exists; the side stream still holds the deferred forward
+            _pending_join.pop(idx, None)        # joined below through the assembly backward's event
+        else:
+            ss.wait_stream(cs)                  # d loss is ready on the main stream
         dout = None
         if ctx.needs_input_grad[0]:
             dout = torch.empty_like(out_c)
-            gmul = 1.0 / float(b * ns)
+            gmul = (inv_batch if inv_batch > 0.0 else 1.0 / float(b)) / float(ns)
             if kind == "dmol":
                 _lib.check(lib.mae_dmol_bwd(out_c.data_ptr(), x_c.data_ptr(), gloss.data_ptr(), 0, gmul, b, ns, nmix, geom[0],
                                             dout.data_ptr(), _stream()), "mae_dmol_bwd")
@@ -709,27 +737,31 @@ class _LossTail(torch.autograd.Function):
         ds = torch.empty((), device=dev, dtype=torch.float32) if has_s else None
         with torch.cuda.stream(ss):
             _lib.check(lib.mae_loss_assemble_bwd(gloss.data_ptr(), scalars.data_ptr(), _ptr(m_c) if m_shape is not None else None,
-                                                 b, ns, d, eta, gamma, free_bits, 0.0, None, dkl.data_ptr(), _ptr(dm), _ptr(ds),
-                                                 _stream()), "mae_loss_assemble_bwd")
+                                                 b, ns, d, eta, gamma, free_bits, inv_batch, None, dkl.data_ptr(), _ptr(dm),
+                                                 _ptr(ds), _stream()), "mae_loss_assemble_bwd")
             _count()
             ev = torch.cuda.Event()
             ev.record(ss)
-        _grads_ready[dev.index if dev.index is not None else torch.cuda.current_device()] = (
-            ev, {t.data_ptr() for t in (dm, ds, dkl) if t is not None})
-        cs.wait_event(ev)                       # later main-stream consumers see dkl / dm / dS; the likelihood backward
-        #                                         enqueued above is not delayed
-        return dout, None, dkl, (dm.view(m_shape) if dm is not None else None), ds, None, None, None, None, None, None
+        _grads_ready[idx] = (ev, {t.data_ptr() for t in (dm, ds, dkl) if t is not None})
+        cs.wait_event(ev)                       # later main-stream consumers see dkl / dm / dS (and, when deferred, the
+        #                                         forward's loss); the likelihood backward enqueued above is not delayed
+        return (dout, None, dkl, (dm.view(m_shape) if dm is not None else None), ds, None, None, None, None, None, None, None,
+                None, None)
 
 
 def loss_tail(dec_out: torch.Tensor, x: torch.Tensor, kl: torch.Tensor, m_d: Optional[torch.Tensor], s: Optional[torch.Tensor],
-              kind: str, ns: int, nmix: int = 10, eta: float = 0.0, gamma: float = 0.0, free_bits: float = 0.0):
+              kind: str, ns: int, nmix: int = 10, eta: float = 0.0, gamma: float = 0.0, free_bits: float = 0.0,
+              inv_batch: float = 0.0, ext_sums: Optional[torch.Tensor] = None, defer_join: bool = False):
     """Decoder output -> objective of MAE.loss in one autograd node.  ``kind`` is "dmol" (dec_out = raw
     [B*ns,10*nmix,H,W]) or "bernoulli" (dec_out = probabilities [B,ns,P]).  Returns (loss [], stats [5], recon [B])
-    like :func:`assemble_loss`.  Reference: color_image_decoder.py:91-125 / binary_image_decoder.py:84-93 +
-    mae.py:132-140."""
+    like :func:`assemble_loss`.  ``inv_batch`` / ``ext_sums`` serve batch-sharded runs (see assemble_loss).
+    ``defer_join=True`` keeps the objective's tiny kernels on the side stream (see _LossTail); the outputs may then be
+    read only after ``backward()`` or :func:`join_side`.
+    Reference: color_image_decoder.py:91-125 / binary_image_decoder.py:84-93 + mae.py:132-140."""
     if kind not in ("dmol", "bernoulli"):
         raise ValueError("kind must be 'dmol' or 'bernoulli'")
-    return _LossTail.apply(dec_out, x, kl, m_d, s, kind, int(ns), int(nmix), float(eta), float(gamma), float(free_bits))
+    return _LossTail.apply(dec_out, x, kl, m_d, s, ext_sums, kind, int(ns), int(nmix), float(eta), float(gamma),
+                           float(free_bits), float(inv_batch), bool(defer_join))
 
 
 def assemble_loss(err: torch.Tensor, kl: torch.Tensor, m_d: Optional[torch.Tensor], s: Optional[torch.Tensor],

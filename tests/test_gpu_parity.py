@@ -359,9 +359,10 @@ def test_kl_mpd_fused_node(ops, O):
         check_close(s, sr, what="S b=%d" % b)
 
 
+@pytest.mark.parametrize("defer", [False, True])
 @pytest.mark.parametrize("kind", ["dmol", "bernoulli"])
 @pytest.mark.parametrize("eta,gamma,free_bits", [(1.0, 1.0, 0.0), (0.0, 0.0, 0.0), (0.5, 2.0, 1e5)])
-def test_fused_loss_heads_vs_oracle(ops, O, kind, eta, gamma, free_bits):
+def test_fused_loss_heads_vs_oracle(ops, O, kind, eta, gamma, free_bits, defer):
     """heads.loss_head_* = reparam + KL/MPD node (side stream) + likelihood/objective node, against the oracle's
     composition of the reference formulas, values and all gradients."""
     from mae_b200 import heads, synth
@@ -374,13 +375,13 @@ def test_fused_loss_heads_vs_oracle(ops, O, kind, eta, gamma, free_bits):
         inp = synth.color_head(b, ns, 10, 8, 8, seed=4)
         dec = cu(inp["raw"]).requires_grad_()
         decr = inp["raw"].double().requires_grad_()
-        out = heads.loss_head_color(mu, lv, cu(eps), dec, cu(inp["x"]), 10, eta, gamma, free_bits)
+        out = heads.loss_head_color(mu, lv, cu(eps), dec, cu(inp["x"]), 10, eta, gamma, free_bits, defer_join=defer)
         ref, _ = O.loss_head_color(mur, lvr, eps.double(), lambda z: decr, inp["x"].double(), 10, eta, gamma, free_bits)
     else:
         inp = synth.binary_head(b, ns, 50, seed=4)
         dec = cu(inp["probs"]).requires_grad_()
         decr = inp["probs"].double().requires_grad_()
-        out = heads.loss_head_binary(mu, lv, cu(eps), dec, cu(inp["x"]), eta, gamma, free_bits)
+        out = heads.loss_head_binary(mu, lv, cu(eps), dec, cu(inp["x"]), eta, gamma, free_bits, defer_join=defer)
         ref, _ = O.loss_head_binary(mur, lvr, eps.double(), lambda z: decr, inp["x"].double(), eta, gamma, free_bits)
     loss, recon, kl, stats, z = out
     (loss * 0.9).backward()
@@ -409,7 +410,7 @@ def test_fused_head_under_cuda_graph(ops, O):
 
     def step():
         mu.grad = lv.grad = raw.grad = None
-        loss = heads.loss_head_color(mu, lv, eps, raw, x, 10, 1.0, 1.0, 0.0)[0]
+        loss = heads.loss_head_color(mu, lv, eps, raw, x, 10, 1.0, 1.0, 0.0, defer_join=True)[0]
         loss.backward(gradient=one)
         return loss
 
