@@ -199,13 +199,16 @@ int mae_iw_nll(const float* log_gen, const float* z_prior_normal, const float* l
  *   inv_batch: 1/B_global (>0) lets multi-GPU callers pass local tensors; 0 -> 1/B.
  *   ext_sums (nullable, device float[2]): {sum of recon, sum of kl} contributed by the OTHER ranks of a
  *   batch-sharded run; they are added to the local sums before the means (and the free-bits clamp) are taken.
+ *   kl_count (0 -> B): number of entries of `kl` summed for the KL mean; a batch-sharded caller passes the
+ *   all-gathered KL vector [B_global] here (err stays local [B,ns]) instead of a separate reduction.
  * bwd, given gloss (device scalar, nullable = 1):
  *   derr[b,s] = gloss*inv_batch/ns ; dkl[b] = gloss*inv_batch*[mean kl >= free_bits] ;
  *   dm_d[d] = -gloss*eta*sigmoid(-m_d) ; dS = gloss*gamma
  *   kl_mean is read from scalars[4] written by the forward.
  * ---------------------------------------------------------------------------------------------- */
 int mae_loss_assemble_fwd(const float* err, const float* kl, const float* m_d, const float* S, const float* ext_sums,
-                          int64_t B, int64_t ns, int64_t D, float eta, float gamma, float free_bits, float inv_batch,
+                          int64_t B, int64_t ns, int64_t D, int64_t kl_count,
+                          float eta, float gamma, float free_bits, float inv_batch,
                           float* scalars, float* recon, mae_stream_t stream);
 int mae_loss_assemble_bwd(const float* gloss, const float* scalars, const float* m_d,
                           int64_t B, int64_t ns, int64_t D, float eta, float gamma, float free_bits, float inv_batch,

@@ -12,8 +12,9 @@ __device__ __forceinline__ float logsigmoid(float x) { return fminf(x, 0.f) - lo
 
 __global__ void __launch_bounds__(kThreads)
 assemble_fwd_kernel(const float* __restrict__ err, const float* __restrict__ kl, const float* __restrict__ m_d,
-                    const float* __restrict__ S, const float* __restrict__ ext_sums, int B, int ns, int D, float eta,
-                    float gamma, float free_bits, float inv_batch, float* __restrict__ scalars, float* __restrict__ recon) {
+                    const float* __restrict__ S, const float* __restrict__ ext_sums, int B, int ns, int D, int kl_count,
+                    float eta, float gamma, float free_bits, float inv_batch, float* __restrict__ scalars,
+                    float* __restrict__ recon) {
     __shared__ float scratch[32];
     float s_rec = 0.f, s_kl = 0.f, s_m = 0.f, s_ls = 0.f;
     const float inv_ns = 1.0f / (float)ns;
@@ -23,8 +24,8 @@ assemble_fwd_kernel(const float* __restrict__ err, const float* __restrict__ kl,
         a *= inv_ns;
         recon[b] = a;
         s_rec += a;
-        s_kl += kl[b];
     }
+    for (int b = threadIdx.x; b < kl_count; b += kThreads) s_kl += kl[b];   // kl_count > B: the all-gathered KL vector
     if (m_d != nullptr) {
         for (int d = threadIdx.x; d < D; d += kThreads) {
             const float v = m_d[d];
@@ -75,14 +76,16 @@ assemble_bwd_kernel(const float* __restrict__ gloss, const float* __restrict__ s
 }  // namespace mae
 
 extern "C" int mae_loss_assemble_fwd(const float* err, const float* kl, const float* m_d, const float* S,
-                                     const float* ext_sums, int64_t B, int64_t ns, int64_t D, float eta, float gamma, float free_bits, float inv_batch, float* scalars,
+                                     const float* ext_sums, int64_t B, int64_t ns, int64_t D, int64_t kl_count, float eta, float gamma, float free_bits, float inv_batch, float* scalars,
                                      float* recon, mae_stream_t stream) {
     using namespace mae;
     MAE_REQUIRE(err && kl && scalars && recon, MAE_ERR_NULL);
     MAE_REQUIRE(B > 0 && ns > 0 && D >= 0 && B < (1ll << 31) && ns < (1ll << 31) && D < (1ll << 31), MAE_ERR_SHAPE);
     if (inv_batch <= 0.f) inv_batch = 1.0f / (float)B;
-    assemble_fwd_kernel<<<1, kThreads, 0, as_stream(stream)>>>(err, kl, m_d, S, ext_sums, (int)B, (int)ns, (int)D, eta, gamma,
-                                                              free_bits, inv_batch, scalars, recon);
+    if (kl_count <= 0) kl_count = B;
+    MAE_REQUIRE(kl_count < (1ll << 31), MAE_ERR_SHAPE);
+    assemble_fwd_kernel<<<1, kThreads, 0, as_stream(stream)>>>(err, kl, m_d, S, ext_sums, (int)B, (int)ns, (int)D, (int)kl_count,
+                                                              eta, gamma, free_bits, inv_batch, scalars, recon);
     return launch_status();
 }
 

@@ -30,6 +30,22 @@ import torch.distributed as dist
 SMALL_GLOBAL_BATCH = 2048   # <= : every rank evaluates the whole MPD forward redundantly (no all-reduce)
 
 
+def _packed_parent(mu, logvar, b_loc, d):
+    """mu / logvar are usually the two chunk(2,1) halves of ONE contiguous [B, 2D] encoder output
+    (encoder_cores/resnet.py:43): return that parent as a tensor without copying, else None."""
+    try:
+        m2, l2 = mu.view(b_loc, d), logvar.view(b_loc, d)
+    except RuntimeError:
+        return None
+    if b_loc > 1 and (m2.stride() != (2 * d, 1) or l2.stride() != (2 * d, 1)):
+        return None
+    if l2.data_ptr() != m2.data_ptr() + 4 * d or m2.dtype != torch.float32:
+        return None
+    if b_loc == 1 and not (m2.is_contiguous() and l2.is_contiguous()):
+        return None
+    return torch.as_strided(m2.detach(), (b_loc, 2 * d), (2 * d, 1))
+
+
 def _all_gather_rows(t: torch.Tensor, group) -> torch.Tensor:
     """[n, c] -> [world*n, c], rank-major (equal n on every rank)."""
     world = dist.get_world_size(group)
@@ -39,7 +55,7 @@ def _all_gather_rows(t: torch.Tensor, group) -> torch.Tensor:
 
 
 class _ShardedKLMPD(torch.autograd.Function):
-    """(mu_loc, logvar_loc) -> (kl_loc [B_loc], m_d [D], S [], kl_others_sum []).
+    """(mu_loc, logvar_loc) -> (kl_loc [B_loc], m_d [D], S [], kl_all [B_global]).
 
     With the CUDA engine the whole chain (pack, all-gather, pre-pass, tiles) runs on the engine's side stream, so the
     collective's latency and the MPD kernels overlap with the likelihood kernel on the main stream; the results are
@@ -51,7 +67,9 @@ class _ShardedKLMPD(torch.autograd.Function):
         world, rank = dist.get_world_size(group), dist.get_rank(group)
         b_loc = mu.size(0)
         d = mu[0].numel()
-        packed = torch.cat([mu.reshape(b_loc, d), logvar.reshape(b_loc, d)], dim=1)
+        packed = _packed_parent(mu, logvar, b_loc, d)
+        if packed is None:
+            packed = torch.cat([mu.reshape(b_loc, d), logvar.reshape(b_loc, d)], dim=1)
         if head.check_equal_batches:
             lo = torch.tensor([b_loc], device=mu.device, dtype=torch.int64)
             hi = lo.clone()
@@ -72,9 +90,8 @@ class _ShardedKLMPD(torch.autograd.Function):
             dist.all_reduce(s_or_sumsq, op=dist.ReduceOp.SUM, group=group)
             s = eng.mpd_finalize(s_or_sumsq, b)
             state.s = s
-        kl_loc = kl_all[row0:row0 + b_loc].clone()
-        kl_others = kl_all.sum() - kl_loc.sum()
-        return kl_loc, m_d, s, kl_others, state, gathered, row0, b_loc
+        kl_loc = kl_all[row0:row0 + b_loc]
+        return kl_loc, m_d, s, kl_all, state, gathered, row0, b_loc
 
     @staticmethod
     def forward(ctx, mu, logvar, head):
@@ -86,17 +103,17 @@ class _ShardedKLMPD(torch.autograd.Function):
             cs, ss = torch.cuda.current_stream(dev), eng._side_stream(dev)
             ss.wait_stream(cs)
             with torch.cuda.stream(ss):
-                kl_loc, m_d, s, kl_others, state, gathered, row0, b_loc = _ShardedKLMPD._compute(mu, logvar, head)
+                kl_loc, m_d, s, kl_all, state, gathered, row0, b_loc = _ShardedKLMPD._compute(mu, logvar, head)
                 ev = torch.cuda.Event()
                 ev.record(ss)
             eng._pending_join[dev.index if dev.index is not None else torch.cuda.current_device()] = (
-                ev, (kl_loc, m_d, s, kl_others, gathered, mu, logvar))
+                ev, (kl_loc, m_d, s, kl_all, gathered, mu, logvar))
         else:
-            kl_loc, m_d, s, kl_others, state, gathered, row0, b_loc = _ShardedKLMPD._compute(mu, logvar, head)
+            kl_loc, m_d, s, kl_all, state, gathered, row0, b_loc = _ShardedKLMPD._compute(mu, logvar, head)
         ctx.state, ctx.eng, ctx.rows, ctx.shapes, ctx.side = state, eng, (row0, b_loc), (mu.shape, logvar.shape), side
         ctx.keep = gathered
-        ctx.mark_non_differentiable(kl_others)
-        return kl_loc, m_d.view(mu.shape[1:]), s, kl_others
+        ctx.mark_non_differentiable(kl_all)
+        return kl_loc, m_d.view(mu.shape[1:]), s, kl_all
 
     @staticmethod
     def backward(ctx, g_kl, g_m, g_s, _g_others):
@@ -139,18 +156,18 @@ class ShardedHead:
 
     # ------------------------------------------------------------------------------------------ training
     def kl_mpd(self, mu, logvar):
-        """Analytic KL of the local rows, global MPD (m_d, S) and the KL sum of the other ranks' rows."""
+        """Analytic KL of the local rows, global MPD (m_d, S) and the KL of every gathered row [B_global]."""
         return _ShardedKLMPD.apply(mu, logvar, self)
 
-    def _tail(self, dec_out, x, kl, m_d, s, kl_others, kind, ns, nmix, eta, gamma, free_bits):
+    def _tail(self, dec_out, x, kl, m_d, s, kl_all, kind, ns, nmix, eta, gamma, free_bits):
         eng = self.engine
         b_glob = self.world * x.size(0)
         if hasattr(eng, "loss_tail") and dec_out.is_cuda:
             # fused likelihood + objective node; with overlap the objective's tiny kernels stay on the side stream
             # behind the all-gather / MPD chain, so the main stream runs likelihood fwd -> likelihood bwd back to back
-            ext = torch.stack([kl_others.new_zeros(()), kl_others]).to(kl.dtype)
-            return eng.loss_tail(dec_out, x, kl, m_d, s, kind, ns, nmix, eta, gamma, free_bits, 1.0 / b_glob, ext,
-                                 defer_join=self.overlap and self.defer_join)
+            return eng.loss_tail(dec_out, x, kl, m_d, s, kind, ns, nmix, eta, gamma, free_bits, 1.0 / b_glob, None,
+                                 defer_join=self.overlap and self.defer_join, kl_all=kl_all)
+        kl_others = kl_all.sum() - kl.detach().sum()
         if kind == "dmol":
             err = eng.dmol_recon_error(dec_out, x, ns, nmix)
         else:
@@ -161,15 +178,15 @@ class ShardedHead:
     def loss_head_color(self, mu, logvar, eps, raw, x, nmix=10, eta=0.0, gamma=0.0, free_bits=0.0):
         """C3 on a batch shard.  Returns (loss, recon [B_loc], KL [B_loc], stats, z) like ``heads.loss_head_color``."""
         z, _ = self.engine.reparam_kl(mu, logvar, eps, want_kl=False)
-        kl, m_d, s, kl_others = self.kl_mpd(mu, logvar)
-        loss, stats, recon = self._tail(raw, x, kl, m_d, s, kl_others, "dmol", eps.size(1), nmix, eta, gamma, free_bits)
+        kl, m_d, s, kl_all = self.kl_mpd(mu, logvar)
+        loss, stats, recon = self._tail(raw, x, kl, m_d, s, kl_all, "dmol", eps.size(1), nmix, eta, gamma, free_bits)
         return loss, recon, kl, stats, z
 
     def loss_head_binary(self, mu, logvar, eps, probs, x, eta=0.0, gamma=0.0, free_bits=0.0):
         """C1/C2 on a batch shard."""
         z, _ = self.engine.reparam_kl(mu, logvar, eps, want_kl=False)
-        kl, m_d, s, kl_others = self.kl_mpd(mu, logvar)
-        loss, stats, recon = self._tail(probs, x, kl, m_d, s, kl_others, "bernoulli", eps.size(1), 0, eta, gamma, free_bits)
+        kl, m_d, s, kl_all = self.kl_mpd(mu, logvar)
+        loss, stats, recon = self._tail(probs, x, kl, m_d, s, kl_all, "bernoulli", eps.size(1), 0, eta, gamma, free_bits)
         return loss, recon, kl, stats, z
 
     def global_loss(self, loss: torch.Tensor, stats: torch.Tensor) -> torch.Tensor:

@@ -594,7 +594,7 @@ class _Assemble(torch.autograd.Function):
         d = m_c.numel() if m_c is not None else 0
         scalars = torch.empty(6, device=err.device, dtype=torch.float32)
         recon = torch.empty(b, device=err.device, dtype=torch.float32)
-        _lib.check(_lib_().mae_loss_assemble_fwd(err_c.data_ptr(), kl_c.data_ptr(), _ptr(m_c), _ptr(s), _ptr(ext_sums), b, ns, d, eta, gamma,
+        _lib.check(_lib_().mae_loss_assemble_fwd(err_c.data_ptr(), kl_c.data_ptr(), _ptr(m_c), _ptr(s), _ptr(ext_sums), b, ns, d, 0, eta, gamma,
                                                  free_bits, inv_batch, scalars.data_ptr(), recon.data_ptr(), _stream()),
                    "mae_loss_assemble_fwd")
         _count()
@@ -639,9 +639,9 @@ class _LossTail(torch.autograd.Function):
     after ``backward()`` (which joins) or ``ops.join_side()``."""
 
     @staticmethod
-    def forward(ctx, dec_out, x, kl, m_d, s, ext_sums, kind, ns, nmix, eta, gamma, free_bits, inv_batch, defer):
+    def forward(ctx, dec_out, x, kl, m_d, s, ext_sums, kl_all, kind, ns, nmix, eta, gamma, free_bits, inv_batch, defer):
         ctx.set_materialize_grads(False)
-        _req_cuda(dec_out, x, kl, m_d, s, ext_sums)
+        _req_cuda(dec_out, x, kl, m_d, s, ext_sums, kl_all)
         lib = _lib_()
         dev = dec_out.device
         idx = dev.index if dev.index is not None else torch.cuda.current_device()
@@ -668,7 +668,8 @@ class _LossTail(torch.autograd.Function):
             _lib.check(lib.mae_bernoulli_fwd(out_c.data_ptr(), x_c.data_ptr(), b, ns, p, err.data_ptr(), _stream()),
                        "mae_bernoulli_fwd")
             geom = (p,)
-        kl_c = kl.contiguous()
+        kl_c = (kl_all if kl_all is not None else kl).contiguous()   # sharded runs sum the all-gathered KL vector
+        kl_count = kl_c.numel() if kl_all is not None else 0
         m_c = m_d.contiguous().view(-1) if m_d is not None else None
         d = m_c.numel() if m_c is not None else 0
         scalars = torch.empty(6, device=dev, dtype=torch.float32)
@@ -676,8 +677,8 @@ class _LossTail(torch.autograd.Function):
 
         def assemble():
             _lib.check(lib.mae_loss_assemble_fwd(err.data_ptr(), kl_c.data_ptr(), _ptr(m_c), _ptr(s), _ptr(ext_sums), b, ns, d,
-                                                 eta, gamma, free_bits, inv_batch, scalars.data_ptr(), recon.data_ptr(),
-                                                 _stream()), "mae_loss_assemble_fwd")
+                                                 kl_count, eta, gamma, free_bits, inv_batch, scalars.data_ptr(),
+                                                 recon.data_ptr(), _stream()), "mae_loss_assemble_fwd")
 
         if defer:
             cs, ss = torch.cuda.current_stream(dev), _side_stream(dev)
@@ -704,7 +705,7 @@ class _LossTail(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gloss, _gs, _gr):
         if gloss is None:
-            return (None,) * 14
+            return (None,) * 15
         out_c, x_c, scalars, m_c = ctx.saved_tensors
         kind, b, ns, nmix, geom, d, eta, gamma, free_bits, inv_batch, out_shape, m_shape, has_s, defer = ctx.meta
         lib = _lib_()
@@ -746,21 +747,23 @@ class _LossTail(torch.autograd.Function):
         cs.wait_event(ev)                       # later main-stream consumers see dkl / dm / dS (and, when deferred, the
         #                                         forward's loss); the likelihood backward enqueued above is not delayed
         return (dout, None, dkl, (dm.view(m_shape) if dm is not None else None), ds, None, None, None, None, None, None, None,
-                None, None)
+                None, None, None)
 
 
 def loss_tail(dec_out: torch.Tensor, x: torch.Tensor, kl: torch.Tensor, m_d: Optional[torch.Tensor], s: Optional[torch.Tensor],
               kind: str, ns: int, nmix: int = 10, eta: float = 0.0, gamma: float = 0.0, free_bits: float = 0.0,
-              inv_batch: float = 0.0, ext_sums: Optional[torch.Tensor] = None, defer_join: bool = False):
+              inv_batch: float = 0.0, ext_sums: Optional[torch.Tensor] = None, defer_join: bool = False,
+              kl_all: Optional[torch.Tensor] = None):
     """Decoder output -> objective of MAE.loss in one autograd node.  ``kind`` is "dmol" (dec_out = raw
     [B*ns,10*nmix,H,W]) or "bernoulli" (dec_out = probabilities [B,ns,P]).  Returns (loss [], stats [5], recon [B])
     like :func:`assemble_loss`.  ``inv_batch`` / ``ext_sums`` serve batch-sharded runs (see assemble_loss).
-    ``defer_join=True`` keeps the objective's tiny kernels on the side stream (see _LossTail); the outputs may then be
+    ``kl_all`` (sharded runs): the all-gathered KL vector whose mean enters the free-bits clamp (``kl`` stays the local,
+    differentiable slice).  ``defer_join=True`` keeps the objective's tiny kernels on the side stream (see _LossTail); the outputs may then be
     read only after ``backward()`` or :func:`join_side`.
     Reference: color_image_decoder.py:91-125 / binary_image_decoder.py:84-93 + mae.py:132-140."""
     if kind not in ("dmol", "bernoulli"):
         raise ValueError("kind must be 'dmol' or 'bernoulli'")
-    return _LossTail.apply(dec_out, x, kl, m_d, s, ext_sums, kind, int(ns), int(nmix), float(eta), float(gamma),
+    return _LossTail.apply(dec_out, x, kl, m_d, s, ext_sums, kl_all, kind, int(ns), int(nmix), float(eta), float(gamma),
                            float(free_bits), float(inv_batch), bool(defer_join))
 
 
