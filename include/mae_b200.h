@@ -214,6 +214,25 @@ int mae_loss_assemble_bwd(const float* gloss, const float* scalars, const float*
                           int64_t B, int64_t ns, int64_t D, float eta, float gamma, float free_bits, float inv_batch,
                           float* derr, float* dkl, float* dm_d, float* dS, mae_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Multi-GPU: all-gather of the packed (mu | logvar) rows over NVLink peer memory (replaces the
+ * DataParallel gather of gaussian_encoder.py:41-42 for the loss head).  One kernel per rank pushes its rows into
+ * every peer's landing buffer, flags, waits for the peers' flags and copies the landed slots to `out`
+ * [world, n_floats].  Buffers come from mae_comm_alloc (cudaMalloc, zeroed) and are opened by the peers through
+ * CUDA IPC handles (64 bytes each, exchanged by the host layer over torch.distributed).
+ *   peer_buffers: DEVICE array of `world` pointers, entry r = rank r's buffer as mapped in this process.
+ *   Spins are bounded (2 s): on timeout the error flag (mae_comm_error) is set instead of hanging the GPU.
+ * ---------------------------------------------------------------------------------------------- */
+int64_t mae_comm_buffer_bytes(int64_t world, int64_t slot_floats);
+int mae_comm_alloc(int64_t bytes, void** ptr);
+int mae_comm_free(void* ptr);
+int mae_comm_get_handle(void* ptr, void* handle64);
+int mae_comm_open_handle(const void* handle64, void** ptr);
+int mae_comm_close_handle(void* ptr);
+int mae_comm_error(const void* own_buffer, int* error_out);
+int mae_allgather_rows(const float* local, int64_t n_floats, void* const* peer_buffers, int64_t rank, int64_t world,
+                       int64_t slot_floats, float* out, mae_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

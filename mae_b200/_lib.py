@@ -35,6 +35,13 @@ SIGNATURES = {
     "mae_iw_nll": [_P, _P, _P, _P, _P, _P, _I64, _P, _I64, _I64, _I64, _I64, _P, _P, _P, _P, _P, _I64, _P],
     "mae_loss_assemble_fwd": [_P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _F, _F, _F, _F, _P, _P, _P],
     "mae_loss_assemble_bwd": [_P, _P, _P, _I64, _I64, _I64, _F, _F, _F, _F, _P, _P, _P, _P, _P],
+    "mae_comm_alloc": [_I64, _P],
+    "mae_comm_free": [_P],
+    "mae_comm_get_handle": [_P, _P],
+    "mae_comm_open_handle": [_P, _P],
+    "mae_comm_close_handle": [_P],
+    "mae_comm_error": [_P, _P],
+    "mae_allgather_rows": [_P, _I64, _P, _I64, _I64, _I64, _P, _P],
 }
 # entry points that do not return a status code
 PLAIN = {
@@ -44,6 +51,7 @@ PLAIN = {
     "mae_mpd_workspace_bytes": (c_int64, [_I64, _I64]),
     "mae_dmol_workspace_bytes": (c_int64, [_I64, _I64]),
     "mae_iw_nll_workspace_bytes": (c_int64, [_I64, _I64]),
+    "mae_comm_buffer_bytes": (c_int64, [_I64, _I64]),
 }
 ALL_SYMBOLS = sorted(list(SIGNATURES) + list(PLAIN))
 

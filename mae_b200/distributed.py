@@ -78,7 +78,7 @@ class _ShardedKLMPD(torch.autograd.Function):
             if int(lo) != int(hi):
                 raise RuntimeError("ShardedHead needs the same local batch on every rank (got %d..%d): pad or drop the "
                                    "ragged tail batch" % (int(lo), int(hi)))
-        gathered = _all_gather_rows(packed, group)              # the one collective of the forward
+        gathered = head._gather(packed)                         # the one exchange of the forward
         b = world * b_loc
         mu_all, lv_all = gathered[:, :d], gathered[:, d:]       # strided views, no copy
         row0 = rank * b_loc
@@ -143,7 +143,8 @@ class _ShardedKLMPD(torch.autograd.Function):
 class ShardedHead:
     """Batch-sharded MAE loss head / evaluator.  ``engine`` defaults to ``mae_b200.ops`` (the CUDA kernels)."""
 
-    def __init__(self, group=None, engine=None, check_equal_batches: bool = False, overlap: bool = True):
+    def __init__(self, group=None, engine=None, check_equal_batches: bool = False, overlap: bool = True,
+                 use_p2p: bool = True):
         if engine is None:
             from . import ops as engine
         self.engine = engine
@@ -151,8 +152,26 @@ class ShardedHead:
         self.check_equal_batches = check_equal_batches   # costs two tiny all-reduces and a host sync per step
         self.overlap = overlap                           # all-gather + MPD on the side stream (CUDA engine only)
         self.defer_join = True                           # loss value valid after backward() / ops.join_side()
+        self.peer = None                                 # NVLink peer-memory gather (created lazily, CUDA only)
+        self.use_p2p = use_p2p
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
+
+    def _gather(self, packed: torch.Tensor) -> torch.Tensor:
+        """All-gather of the packed rows: one push-kernel over NVLink peer memory when available (tens of KB, pure
+        latency), else NCCL / gloo ``all_gather_into_tensor``."""
+        if self.use_p2p and packed.is_cuda and self.world > 1 and hasattr(self.engine, "_side_stream"):
+            if self.peer is None:
+                try:
+                    from .p2p import PeerGather
+                    self.peer = PeerGather(self.group, max(packed.numel(), 1 << 16), packed.device)
+                except Exception as exc:  # no IPC / no peer access: keep the library collective
+                    import warnings
+                    warnings.warn("peer-memory all-gather unavailable (%s); using the library all-gather" % (exc,))
+                    self.use_p2p = False
+            if self.peer is not None and self.peer.usable(packed):
+                return self.peer.gather(packed)
+        return _all_gather_rows(packed, self.group)
 
     # ------------------------------------------------------------------------------------------ training
     def kl_mpd(self, mu, logvar):

@@ -18,6 +18,7 @@ def _free_port():
 
 
 def _worker(rank, world, port, small_limit, out):
+    # (the NCCL fallback of the gather is exercised by the gloo tests' all_gather_into_tensor path)
     sys.path.insert(0, ROOT)
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
@@ -39,6 +40,8 @@ def _worker(rank, world, port, small_limit, out):
         loss, recon, kl, stats, z = head.loss_head_color(mu, lv, eps_g[sl].to(dev), raw, inp["x"][sl].to(dev), 10, 1.0, 1.0, 0.0)
         loss.backward()
         g_loss = head.global_loss(loss, stats)
+        assert head.peer is not None, "peer-memory gather was not used"
+        head.peer.check()
         res = {"loss": g_loss.cpu(), "dmu": mu.grad.cpu(), "dlv": lv.grad.cpu(), "draw": raw.grad.cpu()}
         if rank == 0:   # single-GPU head on the whole batch
             mu_a, lv_a = mu_g.to(dev).requires_grad_(), lv_g.to(dev).requires_grad_()
