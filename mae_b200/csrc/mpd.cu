@@ -565,6 +565,10 @@ __device__ __forceinline__ void mean_part(const double* __restrict__ cs, const d
 //   d KL_ij/d mu_i = dl*r_j,  d KL_ji/d mu_i = dl*r_i,                        r = (1+b)/v_bar
 //   2 d KL_ij/d lv_i = v_i r_j - 1 = a_i b_j + a_i + b_j
 //   2 d KL_ji/d lv_i = 1 - (v_j + dl^2) r_i^2 v_i = -(a_j + t_i + a_j t_i) - dl^2 (1+t_i)/v_bar
+// PS warps share one (row, 32-dim) item, each walking every PS-th block of 32 partners; their partial sums meet in
+// shared memory (fixed order).  PS = 1 for small batches, larger when a row has hundreds of partners (sharded runs
+// keep 64 own rows but the partner count grows with the world size).
+template <int PS>
 __global__ void __launch_bounds__(kNT)
 mpd_bwd_small_kernel(const float* __restrict__ mu, int64_t mu_stride, const float* __restrict__ lv, int64_t lv_stride,
                      const float4* __restrict__ Vp, const float* __restrict__ KL, const float* __restrict__ KLT, int Bp,
@@ -572,25 +576,28 @@ mpd_bwd_small_kernel(const float* __restrict__ mu, int64_t mu_stride, const floa
                      const float* __restrict__ g_m, const float* __restrict__ g_S, const float* __restrict__ S,
                      const float* __restrict__ gkl, int B, int D, int row0, int nrows, float* __restrict__ dmu,
                      float* __restrict__ dlv, int accumulate) {
-    const int lane = threadIdx.x & 31;
+    constexpr int kItems = (kNT / 32) / PS;   // (row, dim-chunk) items per CTA
+    __shared__ float red[2][kNT / 32][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int item_local = w / PS, ps = w % PS;
     const int nd32 = (D + 31) / 32;
-    const int64_t wg = (int64_t)blockIdx.x * (kNT / 32) + (threadIdx.x >> 5);
-    if (wg >= (int64_t)nrows * nd32) return;
-    const int i = row0 + (int)(wg / nd32);
-    const int d = (int)(wg % nd32) * 32 + lane;
-    const bool active = d < D;
+    const int64_t item = (int64_t)blockIdx.x * kItems + item_local;
+    const bool item_ok = item < (int64_t)nrows * nd32;
+    const int i = row0 + (int)((item_ok ? item : 0) / nd32);
+    const int d = (int)((item_ok ? item : 0) % nd32) * 32 + lane;
+    const bool active = item_ok && d < D;
     const float m = (float)hdr->m;
     const float beta = weight_scale(g_S, S, B);
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     const float4 pi = active ? Vp[(int64_t)i * D + d] : zero4;  // {mc, a, b, t} of row i
     float gmu = 0.f, glv = 0.f;
-    if (beta != 0.f) {
+    if (beta != 0.f && item_ok) {
         const float ivb = active ? (float)pivots[3 * (int64_t)D + d] : 0.f;
         const float* kl_row = KL + (int64_t)i * Bp;    // KL_ij
         const float* klt_row = KLT + (int64_t)i * Bp;  // KL_ji
         const float opb_i = 1.0f + pi.z, opt_i = 1.0f + pi.w;
         const float4* vcol = Vp + d;
-        for (int jb = 0; jb < B; jb += 32) {
+        for (int jb = ps * 32; jb < B; jb += 32 * PS) {
             // the 32 lanes fetch the weights of 32 partners at once (one coalesced line each), then broadcast
             const int jl = jb + lane;
             const bool ok = jl < B && jl != i;
@@ -616,6 +623,19 @@ mpd_bwd_small_kernel(const float* __restrict__ mu, int64_t mu_stride, const floa
         }
         gmu *= ivb;
         glv *= 0.5f;
+    }
+    if (PS > 1) {
+        red[0][w][lane] = gmu;
+        red[1][w][lane] = glv;
+        __syncthreads();
+        if (ps != 0) return;
+        gmu = 0.f;
+        glv = 0.f;
+#pragma unroll
+        for (int q = 0; q < PS; ++q) {
+            gmu += red[0][item_local * PS + q][lane];
+            glv += red[1][item_local * PS + q][lane];
+        }
     }
     if (!active) return;
     mean_part(colstats, pivots, g_m, B, D, d, pi, mu[(int64_t)i * mu_stride + d], lv[(int64_t)i * lv_stride + d], gmu, glv,
@@ -881,13 +901,20 @@ extern "C" int mae_mpd_bwd(const float* mu, int64_t mu_stride, const float* logv
     if (path == 0) path = (B <= MAE_MPD_SMALL_B) ? 1 : 2;
     if (path == 1) {
         MAE_REQUIRE(B <= MAE_MPD_SMALL_B, MAE_ERR_UNSUPPORTED);
-        const int64_t warps = nrows * ceil_div(D, 32);
-        const int64_t blocks = ceil_div(warps, kNT / 32);
-        MAE_REQUIRE(blocks < (1ll << 31), MAE_ERR_SHAPE);
-        mpd_bwd_small_kernel<<<(unsigned)blocks, kNT, 0, as_stream(stream)>>>(
-            mu, mu_stride, logvar, logvar_stride, at<float4>(workspace, L.vp), at<float>(workspace, L.kl),
-            at<float>(workspace, L.klt), (int)L.Bp, at<double>(workspace, L.colstats), at<double>(workspace, L.pivots),
-            at<Hdr>(workspace, L.hdr), g_m, g_S, S, gkl, (int)B, (int)D, (int)row0, (int)nrows, dmu, dlogvar, accumulate);
+        const int64_t items = nrows * ceil_div(D, 32);
+        auto launch = [&](auto ps_tag) {
+            constexpr int PS = decltype(ps_tag)::value;
+            const int64_t blocks = ceil_div(items, (kNT / 32) / PS);
+            mpd_bwd_small_kernel<PS><<<(unsigned)blocks, kNT, 0, as_stream(stream)>>>(
+                mu, mu_stride, logvar, logvar_stride, at<float4>(workspace, L.vp), at<float>(workspace, L.kl),
+                at<float>(workspace, L.klt), (int)L.Bp, at<double>(workspace, L.colstats), at<double>(workspace, L.pivots),
+                at<Hdr>(workspace, L.hdr), g_m, g_S, S, gkl, (int)B, (int)D, (int)row0, (int)nrows, dmu, dlogvar, accumulate);
+        };
+        MAE_REQUIRE(ceil_div(items, 1) < (1ll << 31), MAE_ERR_SHAPE);
+        // partners per row = B: keep every warp's walk at <= ~4 blocks of 32 partners while the grid is small
+        if (B > 256 && items <= 4096) launch(std::integral_constant<int, 8>{});
+        else if (B > 96 && items <= 8192) launch(std::integral_constant<int, 4>{});
+        else launch(std::integral_constant<int, 1>{});
         return launch_status();
     }
     {

@@ -7,7 +7,7 @@
 // copies the landed slots into a fixed output panel.
 //
 // Memory (per rank, allocated by mae_comm_alloc and opened by the peers through CUDA IPC):
-//   header  : epoch counter, ticket, error flag
+//   header  : error flag, one launch counter per CTA
 //   flags   : [2 parities][world]  uint32, value = epoch in which the slot was written
 //   landing : [2 parities][world][slot_floats]
 // Epochs live on the device (the kernel is CUDA-graph replayable); consecutive epochs alternate landing parities so a
@@ -22,15 +22,15 @@ namespace {
 constexpr int kThreads = 256;
 constexpr unsigned long long kTimeoutNs = 2000000000ull;  // 2 s
 
-struct CommHeader {        // 256 bytes
-    unsigned int epoch;
-    unsigned int ticket;
+constexpr int kMaxWorld = 64;
+struct CommHeader {        // 512 bytes
     unsigned int error;
-    unsigned int pad[61];
+    unsigned int pad[63];
+    unsigned int epoch[kMaxWorld];   // one counter per CTA (= per peer): no cross-CTA handshake inside the kernel
 };
 
-__host__ __device__ inline int64_t flags_off() { return 256; }
-__host__ __device__ inline int64_t landing_off(int world) { return 256 + ((2 * world * 4 + 255) / 256) * 256; }
+__host__ __device__ inline int64_t flags_off() { return 512; }
+__host__ __device__ inline int64_t landing_off(int world) { return 512 + ((2 * world * 4 + 255) / 256) * 256; }
 
 __device__ __forceinline__ unsigned long long now_ns() {
     unsigned long long t;
@@ -54,7 +54,7 @@ p2p_allgather_kernel(const float* __restrict__ local, int64_t n_floats, char* co
     const int p = blockIdx.x;
     char* own = peers[rank];
     CommHeader* hdr = reinterpret_cast<CommHeader*>(own);
-    const unsigned int e = hdr->epoch + 1;   // every CTA reads before the last one (ticket) publishes the new epoch
+    const unsigned int e = hdr->epoch[p] + 1;   // this CTA's own launch counter (all CTAs of a rank advance in lockstep)
     const int parity = e & 1;
     // ---- push my rows into peer p's landing slot [parity][rank]
     char* dst_base = peers[p];
@@ -64,9 +64,9 @@ p2p_allgather_kernel(const float* __restrict__ local, int64_t n_floats, char* co
     float4* dst4 = reinterpret_cast<float4*>(dst);
     for (int64_t i = threadIdx.x; i < n4; i += kThreads) dst4[i] = src4[i];
     for (int64_t i = n4 * 4 + threadIdx.x; i < n_floats; i += kThreads) dst[i] = local[i];
-    __threadfence_system();
-    __syncthreads();
+    __syncthreads();                 // the CTA's stores happen-before thread 0's system-scope fence + release
     if (threadIdx.x == 0) {
+        __threadfence_system();
         unsigned int* peer_flags = reinterpret_cast<unsigned int*>(dst_base + flags_off());
         st_release_sys(peer_flags + parity * world + rank, e);
         // ---- wait for peer p's rows in my own landing buffer
@@ -81,6 +81,7 @@ p2p_allgather_kernel(const float* __restrict__ local, int64_t n_floats, char* co
         }
         timed_out = bad;
         if (bad) hdr->error = 1u;
+        hdr->epoch[p] = e;
     }
     __syncthreads();
     if (!timed_out) {
@@ -92,15 +93,6 @@ p2p_allgather_kernel(const float* __restrict__ local, int64_t n_floats, char* co
         float4* o4 = reinterpret_cast<float4*>(o);
         for (int64_t i = threadIdx.x; i < n4; i += kThreads) o4[i] = __ldcg(l4 + i);
         for (int64_t i = n4 * 4 + threadIdx.x; i < n_floats; i += kThreads) o[i] = __ldcg(land + i);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        const unsigned int t = atomicAdd(&hdr->ticket, 1u);
-        if (t == gridDim.x - 1) {   // last CTA of this rank: publish the epoch, reset the ticket
-            hdr->epoch = e;
-            hdr->ticket = 0u;
-        }
     }
 }
 
@@ -164,9 +156,9 @@ extern "C" int mae_allgather_rows(const float* local, int64_t n_floats, void* co
 
 extern "C" int mae_comm_error(const void* own_buffer, int* error_out) {
     MAE_REQUIRE(own_buffer && error_out, MAE_ERR_NULL);
-    unsigned int host[3];
+    unsigned int host[1];
     cudaError_t e = cudaMemcpy(host, own_buffer, sizeof(host), cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) return (int)e;
-    *error_out = (int)host[2];
+    *error_out = (int)host[0];
     return MAE_OK;
 }
