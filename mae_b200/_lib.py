@@ -35,6 +35,8 @@ SIGNATURES = {
     "mae_iw_nll": [_P, _P, _P, _P, _P, _P, _I64, _P, _I64, _I64, _I64, _I64, _P, _P, _P, _P, _P, _I64, _P],
     "mae_loss_assemble_fwd": [_P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _F, _F, _F, _F, _P, _P, _P],
     "mae_loss_assemble_bwd": [_P, _P, _P, _I64, _I64, _I64, _F, _F, _F, _F, _P, _P, _P, _P, _P],
+    "mae_dmol_fwd_bwd": [_P, _P, _F, _I64, _I64, _I64, _I64, _P, _P, _P, _I64, _P],
+    "mae_scale_inplace": [_P, _I64, _P, _P],
     "mae_comm_alloc": [_I64, _P],
     "mae_comm_free": [_P],
     "mae_comm_get_handle": [_P, _P],

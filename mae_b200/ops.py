@@ -647,6 +647,7 @@ class _LossTail(torch.autograd.Function):
         idx = dev.index if dev.index is not None else torch.cuda.current_device()
         b = x.size(0)
         out_c = dec_out.contiguous()
+        fused_grad = None
         if kind == "dmol":
             hw = out_c[0, 0].numel()
             if out_c.size(1) != 10 * nmix or out_c.size(0) != b * ns or x.size(1) != 3 or x[0, 0].numel() != hw:
@@ -654,8 +655,15 @@ class _LossTail(torch.autograd.Function):
             x_c = x.contiguous()
             ws = _pool.take(max(int(lib.mae_dmol_workspace_bytes(b * ns, hw)), 256), dev)
             err = torch.empty(b, ns, device=dev, dtype=torch.float32)
-            _lib.check(lib.mae_dmol_fwd(out_c.data_ptr(), x_c.data_ptr(), b, ns, nmix, hw, err.data_ptr(), ws.data_ptr(),
-                                        ws.numel(), _stream()), "mae_dmol_fwd")
+            if ctx.needs_input_grad[0] and nmix == 10 and hw in (1024, 4096):
+                # training: one pass produces err AND (1/(B ns)) d err/d raw; the backward only applies d loss
+                fused_grad = torch.empty_like(out_c)
+                gmul = (inv_batch if inv_batch > 0.0 else 1.0 / float(b)) / float(ns)
+                _lib.check(lib.mae_dmol_fwd_bwd(out_c.data_ptr(), x_c.data_ptr(), gmul, b, ns, nmix, hw, err.data_ptr(),
+                                                fused_grad.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), "mae_dmol_fwd_bwd")
+            else:
+                _lib.check(lib.mae_dmol_fwd(out_c.data_ptr(), x_c.data_ptr(), b, ns, nmix, hw, err.data_ptr(), ws.data_ptr(),
+                                            ws.numel(), _stream()), "mae_dmol_fwd")
             _pool.give(ws)
             geom = (hw,)
         else:
@@ -696,6 +704,7 @@ class _LossTail(torch.autograd.Function):
             assemble()
         _count(2)
         ctx.save_for_backward(out_c, x_c, scalars, m_c if m_c is not None else scalars)
+        ctx.fused_grad = fused_grad
         ctx.meta = (kind, b, ns, nmix, geom, d, eta, gamma, free_bits, inv_batch, dec_out.shape,
                     m_d.shape if m_d is not None else None, s is not None, defer)
         loss, stats = scalars[0], scalars[1:]
@@ -722,7 +731,16 @@ class _LossTail(torch.autograd.Function):
         else:
             ss.wait_stream(cs)                  # d loss is ready on the main stream
         dout = None
-        if ctx.needs_input_grad[0]:
+        if ctx.needs_input_grad[0] and ctx.fused_grad is not None:
+            if ctx.fused_grad is False:
+                raise RuntimeError("loss_tail: the fused likelihood gradient was already consumed (retain_graph with a second "
+                                   "backward is not supported on this path)")
+            dout = ctx.fused_grad
+            ctx.fused_grad = False
+            _lib.check(lib.mae_scale_inplace(dout.data_ptr(), dout.numel(), gloss.data_ptr(), _stream()), "mae_scale_inplace")
+            _count()
+            dout = dout.view(out_shape)
+        elif ctx.needs_input_grad[0]:
             dout = torch.empty_like(out_c)
             gmul = (inv_batch if inv_batch > 0.0 else 1.0 / float(b)) / float(ns)
             if kind == "dmol":

@@ -397,6 +397,31 @@ def test_fused_loss_heads_vs_oracle(ops, O, kind, eta, gamma, free_bits, defer):
     check_close(zero(lv.grad, lv), zero(lvr.grad, lvr), what="dlogvar", floor=1e-12)
 
 
+def test_fused_dmol_forward_backward_full_size(ops, O):
+    """32x32, nmix=10: loss_tail takes the one-pass forward+backward kernel (err and the scaled gradient from a single
+    read of raw); d loss != 1 exercises the in-place rescale, d loss == 1 the no-op path."""
+    from mae_b200 import heads, synth
+    b, ns, d = 3, 2, 12
+    mu0, lv0 = synth.posterior_params(b, (d,), seed=5, clamp=True)
+    eps = synth.noise(b, ns, (d,), seed=5)
+    inp = synth.color_head(b, ns, 10, 32, 32, seed=6)
+    for scale in (1.0, -2.5):
+        mu, lv = cu(mu0).requires_grad_(), cu(lv0).requires_grad_()
+        raw = cu(inp["raw"]).requires_grad_()
+        loss, recon, kl, stats, z = heads.loss_head_color(mu, lv, cu(eps), raw, cu(inp["x"]), 10, 1.0, 1.0, 0.0)
+        (loss * scale).backward()
+        mur, lvr, rawr = mu0.double().requires_grad_(), lv0.double().requires_grad_(), inp["raw"].double().requires_grad_()
+        ref, _ = O.loss_head_color(mur, lvr, eps.double(), lambda z_: rawr, inp["x"].double(), 10, 1.0, 1.0, 0.0)
+        (ref[0] * scale).backward()
+        check_close(loss, ref[0], what="loss")
+        check_close(recon, ref[1], what="recon")
+        check_close(raw.grad, rawr.grad, what="draw scale=%g" % scale)
+        check_close(mu.grad, mur.grad, what="dmu")
+    # no gradient requested for the decoder output -> plain forward kernel, same value
+    loss2 = heads.loss_head_color(cu(mu0), cu(lv0), cu(eps), cu(inp["raw"]), cu(inp["x"]), 10, 1.0, 1.0, 0.0)[0]
+    check_close(loss2, ref[0], what="loss (no grad)")
+
+
 def test_fused_head_under_cuda_graph(ops, O):
     """the training step captured in a CUDA graph (side-stream fork/join included) replays to the same numbers"""
     from mae_b200 import heads, synth
