@@ -306,13 +306,14 @@ def bench_ours(args):
     g = torch.full((batch, 1), 1.0 / batch, device=dev)
     draw = [torch.empty_like(r) for r in raws[:2]]
     err = torch.empty(batch, 1, device=dev)
+    err_part = torch.empty(batch, max(int(lib.mae_dmol_err_chunks(batch, 1, 10, 1024)), 1), device=dev)
     ws = torch.zeros(max(int(lib.mae_dmol_workspace_bytes(batch, 1024)), 256), dtype=torch.uint8, device=dev)
     sp = stream.cuda_stream
 
     def k_fused(i):
         j = i % ring
-        lib.mae_dmol_fwd_bwd(raws[j].data_ptr(), xs[j].data_ptr(), 1.0 / batch, batch, 1, 10, 1024, err.data_ptr(),
-                             draw[i % 2].data_ptr(), ws.data_ptr(), ws.numel(), sp)
+        lib.mae_dmol_fwd_bwd(raws[j].data_ptr(), xs[j].data_ptr(), 1.0 / batch, batch, 1, 10, 1024, err_part.data_ptr(),
+                             draw[i % 2].data_ptr(), sp)
 
     def k_bwd(i):
         j = i % ring

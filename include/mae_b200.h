@@ -150,9 +150,12 @@ int mae_dmol_bwd(const float* raw, const float* x, const float* g, int64_t g_str
  * g_mul = 1/(B*ns) times d loss, known up to the scalar d loss): ONE pass reads raw, writes err[b,s] and
  * draw = g_mul * d err/d raw  (53 MB instead of 27 + 53 MB at the C3 shape).  The autograd backward then only calls
  * mae_scale_inplace(draw, d loss), which returns without touching memory when d loss == 1 (loss.backward()).
- * Only nmix = 10 and H*W in {1024, 4096} (MAE_ERR_UNSUPPORTED otherwise: use fwd + bwd). */
+ * Only nmix = 10 and H*W in {1024, 4096} (MAE_ERR_UNSUPPORTED otherwise: use fwd + bwd).
+ * err_partial is [B*ns, mae_dmol_err_chunks(...)]: per-CTA partial sums, reduced by mae_loss_assemble_fwd(err_chunks)
+ * (no tickets / cross-CTA dependency in the heavy kernel). */
+int64_t mae_dmol_err_chunks(int64_t B, int64_t ns, int64_t nmix, int64_t HW);
 int mae_dmol_fwd_bwd(const float* raw, const float* x, float g_mul, int64_t B, int64_t ns, int64_t nmix, int64_t HW,
-                     float* err, float* draw, void* workspace, int64_t workspace_bytes, mae_stream_t stream);
+                     float* err_partial, float* draw, mae_stream_t stream);
 /* data[i] *= scale[0] (device scalar); a no-op kernel when scale[0] == 1. */
 int mae_scale_inplace(float* data, int64_t n, const float* scale, mae_stream_t stream);
 
@@ -208,6 +211,7 @@ int mae_iw_nll(const float* log_gen, const float* z_prior_normal, const float* l
  *   inv_batch: 1/B_global (>0) lets multi-GPU callers pass local tensors; 0 -> 1/B.
  *   ext_sums (nullable, device float[2]): {sum of recon, sum of kl} contributed by the OTHER ranks of a
  *   batch-sharded run; they are added to the local sums before the means (and the free-bits clamp) are taken.
+ *   err_chunks (0 -> 1): err is [B, ns, err_chunks] per-CTA partial sums (mae_dmol_fwd_bwd) that are added here.
  *   kl_count (0 -> B): number of entries of `kl` summed for the KL mean; a batch-sharded caller passes the
  *   all-gathered KL vector [B_global] here (err stays local [B,ns]) instead of a separate reduction.
  * bwd, given gloss (device scalar, nullable = 1):
@@ -216,7 +220,7 @@ int mae_iw_nll(const float* log_gen, const float* z_prior_normal, const float* l
  *   kl_mean is read from scalars[4] written by the forward.
  * ---------------------------------------------------------------------------------------------- */
 int mae_loss_assemble_fwd(const float* err, const float* kl, const float* m_d, const float* S, const float* ext_sums,
-                          int64_t B, int64_t ns, int64_t D, int64_t kl_count,
+                          int64_t B, int64_t ns, int64_t D, int64_t kl_count, int64_t err_chunks,
                           float eta, float gamma, float free_bits, float inv_batch,
                           float* scalars, float* recon, mae_stream_t stream);
 int mae_loss_assemble_bwd(const float* gloss, const float* scalars, const float* m_d,

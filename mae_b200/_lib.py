@@ -33,9 +33,9 @@ SIGNATURES = {
     "mae_log_prob_posterior_fwd": [_P, _P, _P, _I64, _P, _I64, _I64, _I64, _I64, _P, _P],
     "mae_log_prob_posterior_bwd": [_P, _P, _P, _I64, _P, _I64, _I64, _I64, _I64, _P, _P, _P, _P],
     "mae_iw_nll": [_P, _P, _P, _P, _P, _P, _I64, _P, _I64, _I64, _I64, _I64, _P, _P, _P, _P, _P, _I64, _P],
-    "mae_loss_assemble_fwd": [_P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _F, _F, _F, _F, _P, _P, _P],
+    "mae_loss_assemble_fwd": [_P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _F, _F, _F, _F, _P, _P, _P],
     "mae_loss_assemble_bwd": [_P, _P, _P, _I64, _I64, _I64, _F, _F, _F, _F, _P, _P, _P, _P, _P],
-    "mae_dmol_fwd_bwd": [_P, _P, _F, _I64, _I64, _I64, _I64, _P, _P, _P, _I64, _P],
+    "mae_dmol_fwd_bwd": [_P, _P, _F, _I64, _I64, _I64, _I64, _P, _P, _P],
     "mae_scale_inplace": [_P, _I64, _P, _P],
     "mae_comm_alloc": [_I64, _P],
     "mae_comm_free": [_P],
@@ -54,6 +54,7 @@ PLAIN = {
     "mae_dmol_workspace_bytes": (c_int64, [_I64, _I64]),
     "mae_iw_nll_workspace_bytes": (c_int64, [_I64, _I64]),
     "mae_comm_buffer_bytes": (c_int64, [_I64, _I64]),
+    "mae_dmol_err_chunks": (c_int64, [_I64, _I64, _I64, _I64]),
 }
 ALL_SYMBOLS = sorted(list(SIGNATURES) + list(PLAIN))
 

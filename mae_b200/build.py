@@ -46,6 +46,8 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(objdir, exist_ok=True)
     nvcc = _nvcc()
     extra = ["-DMAE_DEBUG_TIMING"] if os.environ.get("MAE_DEBUG_TIMING") else []   # phase timestamps, profiling builds only
+    if os.environ.get("MAE_DMOL_G5"):                                              # tuning: pixel groups per CTA (SPLIT=5)
+        extra.append("-DMAE_DMOL_G5=%d" % int(os.environ["MAE_DMOL_G5"]))
     objs = []
     logs = []
     procs = []

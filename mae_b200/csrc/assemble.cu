@@ -13,14 +13,15 @@ __device__ __forceinline__ float logsigmoid(float x) { return fminf(x, 0.f) - lo
 __global__ void __launch_bounds__(kThreads)
 assemble_fwd_kernel(const float* __restrict__ err, const float* __restrict__ kl, const float* __restrict__ m_d,
                     const float* __restrict__ S, const float* __restrict__ ext_sums, int B, int ns, int D, int kl_count,
-                    float eta, float gamma, float free_bits, float inv_batch, float* __restrict__ scalars,
+                    int err_chunks, float eta, float gamma, float free_bits, float inv_batch, float* __restrict__ scalars,
                     float* __restrict__ recon) {
     __shared__ float scratch[32];
     float s_rec = 0.f, s_kl = 0.f, s_m = 0.f, s_ls = 0.f;
     const float inv_ns = 1.0f / (float)ns;
     for (int b = threadIdx.x; b < B; b += kThreads) {
         float a = 0.f;
-        for (int s = 0; s < ns; ++s) a += err[(int64_t)b * ns + s];
+        const int cnt = ns * err_chunks;   // err_chunks > 1: per-CTA partial sums of the fused likelihood pass
+        for (int s = 0; s < cnt; ++s) a += err[(int64_t)b * cnt + s];
         a *= inv_ns;
         recon[b] = a;
         s_rec += a;
@@ -76,16 +77,18 @@ assemble_bwd_kernel(const float* __restrict__ gloss, const float* __restrict__ s
 }  // namespace mae
 
 extern "C" int mae_loss_assemble_fwd(const float* err, const float* kl, const float* m_d, const float* S,
-                                     const float* ext_sums, int64_t B, int64_t ns, int64_t D, int64_t kl_count, float eta, float gamma, float free_bits, float inv_batch, float* scalars,
+                                     const float* ext_sums, int64_t B, int64_t ns, int64_t D, int64_t kl_count,
+                                     int64_t err_chunks, float eta, float gamma, float free_bits, float inv_batch, float* scalars,
                                      float* recon, mae_stream_t stream) {
     using namespace mae;
     MAE_REQUIRE(err && kl && scalars && recon, MAE_ERR_NULL);
     MAE_REQUIRE(B > 0 && ns > 0 && D >= 0 && B < (1ll << 31) && ns < (1ll << 31) && D < (1ll << 31), MAE_ERR_SHAPE);
     if (inv_batch <= 0.f) inv_batch = 1.0f / (float)B;
     if (kl_count <= 0) kl_count = B;
-    MAE_REQUIRE(kl_count < (1ll << 31), MAE_ERR_SHAPE);
+    if (err_chunks <= 0) err_chunks = 1;
+    MAE_REQUIRE(kl_count < (1ll << 31) && ns * err_chunks < (1ll << 31), MAE_ERR_SHAPE);
     assemble_fwd_kernel<<<1, kThreads, 0, as_stream(stream)>>>(err, kl, m_d, S, ext_sums, (int)B, (int)ns, (int)D, (int)kl_count,
-                                                              eta, gamma, free_bits, inv_batch, scalars, recon);
+                                                              (int)err_chunks, eta, gamma, free_bits, inv_batch, scalars, recon);
     return launch_status();
 }
 

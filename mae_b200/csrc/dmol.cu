@@ -26,7 +26,7 @@ namespace mae {
 namespace {
 
 constexpr int kThreads = 256;   // generic kernels
-constexpr int kMinPixPerCta = 64;
+constexpr int kMinPixPerCta = 32;
 
 // Load/store policies for hot_math.cuh's pixel routines (host branch only exists so the shared
 // __host__ __device__ templates instantiate cleanly; it is never executed).
@@ -122,7 +122,10 @@ dmol_bwd_generic_kernel(const float* __restrict__ raw, const float* __restrict__
 template <int NMIX, int SPLIT>
 struct Geo {
     static constexpr int kK = (NMIX + SPLIT - 1) / SPLIT;             // components per thread (upper bound)
-    static constexpr int kG = SPLIT == 1 ? 8 : (SPLIT == 2 ? 4 : 2);  // pixel groups per CTA
+#ifndef MAE_DMOL_G5
+#define MAE_DMOL_G5 2
+#endif
+    static constexpr int kG = SPLIT == 1 ? 8 : (SPLIT == 2 ? 4 : MAE_DMOL_G5);  // pixel groups per CTA
     static constexpr int kThreadsCta = 32 * SPLIT * kG;
     static constexpr int kPix = 32 * kG;                              // pixels per CTA
 };
@@ -310,11 +313,6 @@ dmol_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ x, cons
         zl = lse_merge<SPLIT>(ms.ml[grp], ms.sl[grp], lane);
     }
 
-    if (ERR) {
-        float val = (SPLIT == 1 || part == 0) ? (zl - zt) : 0.f;
-        val = block_sum(val, scratch);
-        publish_partial(val, n, blockIdx.y, chunks, err, partial, tickets, &is_last);
-    }
     float* ob = draw + off;
     float* olg = ob + part * HW;
     float* opr = ob + 3 * part * HW;
@@ -335,6 +333,12 @@ dmol_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ x, cons
                 stg_stream(q + 7 * NMIX * HW, a * (kCache ? gkap[kCache ? k : 0][c] : lkap[c]));
             }
         }
+    }
+    if (ERR) {   // after the gradient stores have been issued: the reduction's barriers do not delay them
+        float val = (SPLIT == 1 || part == 0) ? (zl - zt) : 0.f;
+        val = block_sum(val, scratch);
+        if (err != nullptr) publish_partial(val, n, blockIdx.y, chunks, err, partial, tickets, &is_last);
+        else if (threadIdx.x == 0) partial[n * chunks + blockIdx.y] = val;   // the objective kernel adds the chunks
     }
 }
 
@@ -613,11 +617,12 @@ int env_int(const char* name, int dflt) {
 
 template <int NMIX, int HW, int SPLIT>
 int launch_bwd(const float* raw, const float* x, const float* g, int gs, float gm, int64_t N, int ns, float* draw,
-               cudaStream_t s, float* err = nullptr, float* partial = nullptr, unsigned int* tickets = nullptr) {
+               cudaStream_t s, float* err = nullptr, float* partial = nullptr, unsigned int* tickets = nullptr,
+               bool with_err = false) {
     using G = Geo<NMIX, SPLIT>;
     const int chunks = HW / G::kPix;
     dim3 grid((unsigned)N, (unsigned)chunks);
-    if (err != nullptr)
+    if (err != nullptr || with_err)
         dmol_bwd_kernel<NMIX, HW, SPLIT, true><<<grid, G::kThreadsCta, 0, s>>>(raw, x, g, gs, gm, ns, draw, chunks, err, partial,
                                                                               tickets);
     else
@@ -654,13 +659,14 @@ int dispatch_fwd(int split, const float* raw, const float* x, int64_t N, int ns,
 }
 template <int HW>
 int dispatch_bwd(int split, const float* raw, const float* x, const float* g, int gs, float gm, int64_t N, int ns,
-                 float* draw, cudaStream_t s, float* err = nullptr, float* partial = nullptr, unsigned int* tickets = nullptr) {
+                 float* draw, cudaStream_t s, float* err = nullptr, float* partial = nullptr, unsigned int* tickets = nullptr,
+                 bool with_err = false) {
     // the backward always splits a pixel over >= 2 warps so the local gradients stay in registers
     static const int vsplit = env_int("MAE_DMOL_VSPLIT", 0);
-    if (err == nullptr && vsplit == 5) return launch_split_vec4<HW, 5, true>(raw, x, g, gs, gm, N, ns, nullptr, nullptr, nullptr, draw, s);
-    if (err == nullptr && vsplit == 10) return launch_split_vec4<HW, 10, true>(raw, x, g, gs, gm, N, ns, nullptr, nullptr, nullptr, draw, s);
-    if (split <= 2) return launch_bwd<10, HW, 2>(raw, x, g, gs, gm, N, ns, draw, s, err, partial, tickets);
-    return launch_bwd<10, HW, 5>(raw, x, g, gs, gm, N, ns, draw, s, err, partial, tickets);
+    if (err == nullptr && !with_err && vsplit == 5) return launch_split_vec4<HW, 5, true>(raw, x, g, gs, gm, N, ns, nullptr, nullptr, nullptr, draw, s);
+    if (err == nullptr && !with_err && vsplit == 10) return launch_split_vec4<HW, 10, true>(raw, x, g, gs, gm, N, ns, nullptr, nullptr, nullptr, draw, s);
+    if (split <= 2) return launch_bwd<10, HW, 2>(raw, x, g, gs, gm, N, ns, draw, s, err, partial, tickets, with_err);
+    return launch_bwd<10, HW, 5>(raw, x, g, gs, gm, N, ns, draw, s, err, partial, tickets, with_err);
 }
 
 }  // namespace
@@ -714,23 +720,28 @@ extern "C" int mae_dmol_bwd(const float* raw, const float* x, const float* g, in
     return launch_status();
 }
 
-// Fused forward + backward for training: err[b,s] and draw = g_mul * d err / d raw in ONE pass over raw.
-extern "C" int mae_dmol_fwd_bwd(const float* raw, const float* x, float g_mul, int64_t B, int64_t ns, int64_t nmix, int64_t HW,
-                                float* err, float* draw, void* workspace, int64_t workspace_bytes, mae_stream_t stream) {
+// Fused forward + backward for training: per-CTA partial sums of err and draw = g_mul * d err / d raw in ONE pass.
+extern "C" int64_t mae_dmol_err_chunks(int64_t B, int64_t ns, int64_t nmix, int64_t HW) {
     using namespace mae;
-    MAE_REQUIRE(raw && x && err && draw && workspace, MAE_ERR_NULL);
+    if (check_dmol(B, ns, nmix, HW) != MAE_OK || nmix != 10 || (HW != 1024 && HW != 4096)) return 0;
+    const int split = pick_split(B * ns * HW);
+    const int pix = split <= 2 ? Geo<10, 2>::kPix : Geo<10, 5>::kPix;
+    return HW / pix;
+}
+
+extern "C" int mae_dmol_fwd_bwd(const float* raw, const float* x, float g_mul, int64_t B, int64_t ns, int64_t nmix, int64_t HW,
+                                float* err_partial, float* draw, mae_stream_t stream) {
+    using namespace mae;
+    MAE_REQUIRE(raw && x && err_partial && draw, MAE_ERR_NULL);
     int rc = check_dmol(B, ns, nmix, HW);
     if (rc != MAE_OK) return rc;
     MAE_REQUIRE(nmix == 10 && (HW == 1024 || HW == 4096), MAE_ERR_UNSUPPORTED);
     const int64_t N = B * ns;
-    const DmolWs w = dmol_ws(N, HW);
-    MAE_REQUIRE(workspace_bytes >= w.total, MAE_ERR_WORKSPACE);
-    float* partial = reinterpret_cast<float*>(static_cast<char*>(workspace) + w.partial_off);
-    unsigned int* tickets = reinterpret_cast<unsigned int*>(static_cast<char*>(workspace) + w.ticket_off);
     cudaStream_t s = as_stream(stream);
     const int split = pick_split(N * HW);
-    return HW == 1024 ? dispatch_bwd<1024>(split, raw, x, nullptr, 0, g_mul, N, (int)ns, draw, s, err, partial, tickets)
-                      : dispatch_bwd<4096>(split, raw, x, nullptr, 0, g_mul, N, (int)ns, draw, s, err, partial, tickets);
+    // err == nullptr selects "partials only": err_partial[n][chunk], no tickets, no cross-CTA dependency
+    return HW == 1024 ? dispatch_bwd<1024>(split, raw, x, nullptr, 0, g_mul, N, (int)ns, draw, s, nullptr, err_partial, nullptr, true)
+                      : dispatch_bwd<4096>(split, raw, x, nullptr, 0, g_mul, N, (int)ns, draw, s, nullptr, err_partial, nullptr, true);
 }
 
 namespace mae {

@@ -594,7 +594,7 @@ class _Assemble(torch.autograd.Function):
         d = m_c.numel() if m_c is not None else 0
         scalars = torch.empty(6, device=err.device, dtype=torch.float32)
         recon = torch.empty(b, device=err.device, dtype=torch.float32)
-        _lib.check(_lib_().mae_loss_assemble_fwd(err_c.data_ptr(), kl_c.data_ptr(), _ptr(m_c), _ptr(s), _ptr(ext_sums), b, ns, d, 0, eta, gamma,
+        _lib.check(_lib_().mae_loss_assemble_fwd(err_c.data_ptr(), kl_c.data_ptr(), _ptr(m_c), _ptr(s), _ptr(ext_sums), b, ns, d, 0, 1, eta, gamma,
                                                  free_bits, inv_batch, scalars.data_ptr(), recon.data_ptr(), _stream()),
                    "mae_loss_assemble_fwd")
         _count()
@@ -653,18 +653,22 @@ class _LossTail(torch.autograd.Function):
             if out_c.size(1) != 10 * nmix or out_c.size(0) != b * ns or x.size(1) != 3 or x[0, 0].numel() != hw:
                 raise RuntimeError("dmol: raw %s / x %s inconsistent with ns=%d nmix=%d" % (tuple(out_c.shape), tuple(x.shape), ns, nmix))
             x_c = x.contiguous()
-            ws = _pool.take(max(int(lib.mae_dmol_workspace_bytes(b * ns, hw)), 256), dev)
-            err = torch.empty(b, ns, device=dev, dtype=torch.float32)
+            err_chunks = 1
             if ctx.needs_input_grad[0] and nmix == 10 and hw in (1024, 4096):
-                # training: one pass produces err AND (1/(B ns)) d err/d raw; the backward only applies d loss
+                # training: one pass produces the per-CTA partial sums of err AND (1/(B ns)) d err/d raw; the objective
+                # kernel adds the partials, the backward only applies d loss
+                err_chunks = int(lib.mae_dmol_err_chunks(b, ns, nmix, hw))
+                err = torch.empty(b, ns, err_chunks, device=dev, dtype=torch.float32)
                 fused_grad = torch.empty_like(out_c)
                 gmul = (inv_batch if inv_batch > 0.0 else 1.0 / float(b)) / float(ns)
                 _lib.check(lib.mae_dmol_fwd_bwd(out_c.data_ptr(), x_c.data_ptr(), gmul, b, ns, nmix, hw, err.data_ptr(),
-                                                fused_grad.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), "mae_dmol_fwd_bwd")
+                                                fused_grad.data_ptr(), _stream()), "mae_dmol_fwd_bwd")
             else:
+                ws = _pool.take(max(int(lib.mae_dmol_workspace_bytes(b * ns, hw)), 256), dev)
+                err = torch.empty(b, ns, device=dev, dtype=torch.float32)
                 _lib.check(lib.mae_dmol_fwd(out_c.data_ptr(), x_c.data_ptr(), b, ns, nmix, hw, err.data_ptr(), ws.data_ptr(),
                                             ws.numel(), _stream()), "mae_dmol_fwd")
-            _pool.give(ws)
+                _pool.give(ws)
             geom = (hw,)
         else:
             out_c = out_c.reshape(b, ns, -1)
@@ -673,6 +677,7 @@ class _LossTail(torch.autograd.Function):
             if x_c.size(1) != p:
                 raise RuntimeError("x has %d pixels per image, probabilities have %d" % (x_c.size(1), p))
             err = torch.empty(b, ns, device=dev, dtype=torch.float32)
+            err_chunks = 1
             _lib.check(lib.mae_bernoulli_fwd(out_c.data_ptr(), x_c.data_ptr(), b, ns, p, err.data_ptr(), _stream()),
                        "mae_bernoulli_fwd")
             geom = (p,)
@@ -685,7 +690,7 @@ class _LossTail(torch.autograd.Function):
 
         def assemble():
             _lib.check(lib.mae_loss_assemble_fwd(err.data_ptr(), kl_c.data_ptr(), _ptr(m_c), _ptr(s), _ptr(ext_sums), b, ns, d,
-                                                 kl_count, eta, gamma, free_bits, inv_batch, scalars.data_ptr(),
+                                                 kl_count, err_chunks, eta, gamma, free_bits, inv_batch, scalars.data_ptr(),
                                                  recon.data_ptr(), _stream()), "mae_loss_assemble_fwd")
 
         if defer:

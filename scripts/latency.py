@@ -71,7 +71,7 @@ def main():
     res["mpd_bwd path2"] = chain(lambda: lib.mae_mpd_bwd(P(mu), D, P(lv), D, P(ws), ws.numel(), B, D, 0, B, P(g_m), P(g_S), P(S), P(kl), P(dmu), P(dlv), 0, 2, st()))
     res["dmol_fwd"] = chain(lambda: lib.mae_dmol_fwd(P(raw), P(x), B, 1, 10, 1024, P(err), P(wsd), wsd.numel(), st()))
     res["dmol_bwd"] = chain(lambda: lib.mae_dmol_bwd(P(raw), P(x), P(g), 1, 1.0, B, 1, 10, 1024, P(draw), st()))
-    res["assemble_fwd"] = chain(lambda: lib.mae_loss_assemble_fwd(P(err), P(kl), P(m_d), P(S), None, B, 1, D, 0, 1.0, 1.0, 0.0, 0.0, P(sc), P(recon), st()))
+    res["assemble_fwd"] = chain(lambda: lib.mae_loss_assemble_fwd(P(err), P(kl), P(m_d), P(S), None, B, 1, D, 0, 1, 1.0, 1.0, 0.0, 0.0, P(sc), P(recon), st()))
     res["assemble_bwd"] = chain(lambda: lib.mae_loss_assemble_bwd(P(g_S), P(sc), P(m_d), B, 1, D, 1.0, 1.0, 0.0, 0.0, P(derr), P(dkl), P(dm), P(dS), st()))
     for k, v in res.items():
         print("%-32s %8.2f us" % (k, v))
