@@ -115,7 +115,9 @@ def _side_stream(device: torch.device) -> "torch.cuda.Stream":
     idx = device.index if device.index is not None else torch.cuda.current_device()
     st = _side_streams.get(idx)
     if st is None:
-        st = torch.cuda.Stream(device=device)
+        # high priority: the side-stream kernels are tiny (a handful of CTAs) but sit on a dependent chain; they must
+        # get SM slots as soon as CTAs of the big likelihood kernel retire instead of queueing behind its whole grid
+        st = torch.cuda.Stream(device=device, priority=-1)
         _side_streams[idx] = st
     return st
 
