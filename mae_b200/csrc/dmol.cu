@@ -413,6 +413,128 @@ dmol_fwd_vec4_kernel(const float* __restrict__ raw, const float* __restrict__ x,
     publish_partial(val, n, blockIdx.y, chunks, err, partial, tickets, &is_last);
 }
 
+// ------------------------------------------------ TMA-staged forward for large launches (IW-NLL evaluation)
+// Same 4-pixels-per-thread arithmetic as dmol_fwd_vec4_kernel, but the channel planes are brought into shared
+// memory by the bulk-copy engine (cp.async.bulk + mbarrier transaction counts; UBLKCP in SASS) instead of register
+// loads: a CTA owns 1024 consecutive pixels of one sample; the 10 planes of a component (10 x 4 KB) form one stage,
+// two stages are in flight (80 KB), refilled by thread 0 as soon as the CTA has consumed a stage.  Registers hold
+// only the component being evaluated, and the copy engine keeps ~80 KB per CTA outstanding independent of the
+// warps' progress.
+constexpr int kTmaStages = 2;
+constexpr int kTmaStageFloats = 10 * kVecPix;                 // one component: 10 planes x 1024 pixels
+constexpr int kTmaSmemBytes = kTmaStages * kTmaStageFloats * 4 + 64;
+
+__device__ __forceinline__ unsigned int smem_u32(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned int bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned int bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned int parity) {
+    unsigned int done;
+    unsigned int spins = 0;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done)
+                     : "r"(smem_u32(bar)), "r"(parity)
+                     : "memory");
+        if (!done && ++spins > (1u << 24)) asm volatile("trap;");   // a lost transaction must fault, never hang the GPU
+    } while (!done);
+}
+
+template <int NMIX, int HW>
+__device__ __forceinline__ void tma_issue_component(float* stage, const float* __restrict__ pbase, int m,
+                                                    unsigned long long* bar) {
+    // plane order inside a stage: logit, mu0..2, rho0..2, kap0..2 ; each plane chunk is kVecPix contiguous floats
+    mbar_expect_tx(bar, kTmaStageFloats * 4);
+    bulk_g2s(stage, pbase + m * HW, kVecPix * 4, bar);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float* q = pbase + (3 * m + c) * HW;
+        bulk_g2s(stage + (1 + c) * kVecPix, q + NMIX * HW, kVecPix * 4, bar);
+        bulk_g2s(stage + (4 + c) * kVecPix, q + 4 * NMIX * HW, kVecPix * 4, bar);
+        bulk_g2s(stage + (7 + c) * kVecPix, q + 7 * NMIX * HW, kVecPix * 4, bar);
+    }
+}
+
+template <int NMIX, int HW>
+__global__ void __launch_bounds__(kVecThreads, 2)
+dmol_fwd_tma_kernel(const float* __restrict__ raw, const float* __restrict__ x, int ns, int chunks, float* __restrict__ err,
+                    float* partial, unsigned int* tickets) {
+    extern __shared__ __align__(128) unsigned char tma_smem[];
+    float* stages = reinterpret_cast<float*>(tma_smem);
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(tma_smem + kTmaStages * kTmaStageFloats * 4);
+    __shared__ float scratch[32];
+    __shared__ bool is_last;
+    const int64_t n = blockIdx.x;
+    const int64_t b = n / ns;
+    const int pix0 = blockIdx.y * kVecPix;
+    const float* pbase = raw + n * (int64_t)(10 * NMIX * HW) + pix0;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < kTmaStages; ++s) mbar_init(&bars[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < kTmaStages; ++s)
+            if (s < NMIX) tma_issue_component<NMIX, HW>(stages + s * kTmaStageFloats, pbase, s, &bars[s]);
+    }
+    float xs[4][3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float4 xv = __ldg(reinterpret_cast<const float4*>(x + (b * 3 + c) * HW + pix0 + threadIdx.x * 4));
+        xs[0][c] = xv.x; xs[1][c] = xv.y; xs[2][c] = xv.z; xs[3][c] = xv.w;
+    }
+    hm::Lse lt[4], ll[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        lt[p].init();
+        ll[p].init();
+    }
+#pragma unroll 1
+    for (int m = 0; m < NMIX; ++m) {
+        const int s = m % kTmaStages;
+        mbar_wait(&bars[s], (m / kTmaStages) & 1);
+        const float4* st4 = reinterpret_cast<const float4*>(stages + s * kTmaStageFloats) + threadIdx.x;
+        const float4 lg4 = st4[0];
+        float4 mu4[3], rho4[3], kap4[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            mu4[c] = st4[(1 + c) * (kVecPix / 4)];
+            rho4[c] = st4[(4 + c) * (kVecPix / 4)];
+            kap4[c] = st4[(7 + c) * (kVecPix / 4)];
+        }
+        __syncthreads();   // every thread holds its values: the stage can be refilled
+        if (threadIdx.x == 0 && m + kTmaStages < NMIX) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy reads before async-proxy writes
+            tma_issue_component<NMIX, HW>(stages + s * kTmaStageFloats, pbase, m + kTmaStages, &bars[s]);
+        }
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const float mu[3] = {f4(mu4[0], p), f4(mu4[1], p), f4(mu4[2], p)};
+            const float rho[3] = {f4(rho4[0], p), f4(rho4[1], p), f4(rho4[2], p)};
+            const float kap[3] = {f4(kap4[0], p), f4(kap4[1], p), f4(kap4[2], p)};
+            const float lg = f4(lg4, p);
+            const float T = hm::dmol_component<false>(mu, rho, kap, xs[p], nullptr, nullptr, nullptr);
+            lt[p].push(T + lg);
+            ll[p].push(lg);
+        }
+    }
+    float val = 0.f;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) val += ll[p].value() - lt[p].value();
+    val = block_sum(val, scratch);
+    publish_partial(val, n, blockIdx.y, chunks, err, partial, tickets, &is_last);
+}
+
 // ------------------------------------------------------- vectorised split kernels for training-size launches
 // Same 16-byte loads (4 pixels per thread), with the components of a pixel split over SPLIT warps like the scalar
 // kernels above: a CTA owns G groups of 128 pixels, group = SPLIT warps, warp `part` evaluates components
@@ -639,6 +761,14 @@ int dispatch_fwd(int split, const float* raw, const float* x, int64_t N, int ns,
     if (split == 1 && vec && HW % kVecPix == 0) {
         const int chunks = HW / kVecPix;
         dim3 grid((unsigned)N, (unsigned)chunks);
+        static const int use_tma = env_int("MAE_DMOL_TMA", 0);
+        if (use_tma) {
+            cudaError_t e = cudaFuncSetAttribute(dmol_fwd_tma_kernel<10, HW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 kTmaSmemBytes);
+            if (e != cudaSuccess) return (int)e;
+            dmol_fwd_tma_kernel<10, HW><<<grid, kVecThreads, kTmaSmemBytes, s>>>(raw, x, ns, chunks, err, partial, tickets);
+            return launch_status();
+        }
         static const int vocc = env_int("MAE_DMOL_VEC_OCC", 2);
         if (vocc == 3) dmol_fwd_vec4_kernel<10, HW, 3><<<grid, kVecThreads, 0, s>>>(raw, x, ns, chunks, err, partial, tickets);
         else if (vocc == 4) dmol_fwd_vec4_kernel<10, HW, 4><<<grid, kVecThreads, 0, s>>>(raw, x, ns, chunks, err, partial, tickets);
