@@ -133,6 +133,121 @@ MAE_HD float dmol_component(const float mu[3], const float rho[3], const float k
     return T;
 }
 
+// ---- packed (two pixels at once) forward evaluation ------------------------------------------------------
+// Blackwell issues FADD2/FMUL2/FFMA2 (two fp32 operations per lane per instruction, __f{add,mul,fma}2_rn).  The
+// forward likelihood is issue-bound once its loads are wide, so the arithmetic of two neighbouring pixels is carried
+// in float2 registers; only the SFU ops, |x| and the few compares stay scalar.  Edge bins (x = 0 / 255) are folded
+// in with loop-invariant masks instead of selects:  Q = r * (fm*num + fu*(1+eh) + fl*(1+el)),
+// lin = fl*min(hi,0) - fu*max(lo,0)  with (fu, fl, fm) = (x is 255, x is 0, neither).
+#if !defined(__CUDACC__)
+struct float2 {
+    float x, y;
+};
+#endif
+MAE_HD float2 mk2(float a, float b) {
+    float2 r;
+    r.x = a;
+    r.y = b;
+    return r;
+}
+MAE_HD float2 splat2(float a) { return mk2(a, a); }
+#if defined(__CUDA_ARCH__)
+MAE_HD float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+MAE_HD float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+MAE_HD float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+#else
+MAE_HD float2 add2(float2 a, float2 b) { return mk2(a.x + b.x, a.y + b.y); }
+MAE_HD float2 mul2(float2 a, float2 b) { return mk2(a.x * b.x, a.y * b.y); }
+MAE_HD float2 fma2(float2 a, float2 b, float2 c) { return mk2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
+#endif
+MAE_HD float2 ex2_negabs2(float2 v, float scale) {  // exp2(-scale*|v|), scale > 0
+    return mk2(fast_ex2(-scale * fabsf(v.x)), fast_ex2(-scale * fabsf(v.y)));
+}
+
+struct EdgeMask2 {  // loop-invariant per (pixel pair, channel)
+    float2 fu, fl, fm;
+};
+MAE_HD EdgeMask2 edge_mask2(float2 x) {
+    EdgeMask2 e;
+    e.fu = mk2(x.x > kUpper ? 1.f : 0.f, x.y > kUpper ? 1.f : 0.f);
+    e.fl = mk2(x.x < kLower ? 1.f : 0.f, x.y < kLower ? 1.f : 0.f);
+    e.fm = fma2(add2(e.fu, e.fl), splat2(-1.0f), splat2(1.0f));
+    return e;
+}
+
+// rare fix-up: the "approx" branch of one pixel-channel (delta <= 1e-5 and not an edge bin)
+MAE_HD float logistic_approx_logprob(float u, float ls) {
+    const float eu = fast_ex2(-kLog2e * fabsf(u));
+    return u - ls - 2.0f * (fmaxf(u, 0.f) + kLn2 * fast_lg2(1.0f + eu)) + kLog2Bin;
+}
+
+// bin log-probability of one channel for two pixels (forward only); cx = x - mean, rho = RAW log-scale
+MAE_HD float2 logistic_bin_logprob2(float2 cx, float2 rho, float2 x) {
+    const EdgeMask2 em = edge_mask2(x);   // recomputed per call (2 FSET each): cheaper than 36 live mask registers
+    const float2 ls = mk2(fmaxf(rho.x, kLogScaleMin), fmaxf(rho.y, kLogScaleMin));
+    const float2 t = mul2(ls, splat2(-kLog2e));
+    const float2 s = mk2(fast_ex2(t.x), fast_ex2(t.y));
+    const float2 sh = mul2(s, splat2(kBin));
+    const float2 hi = fma2(s, cx, sh);
+    const float2 lo = fma2(sh, splat2(-2.0f), hi);
+    const float2 eh = ex2_negabs2(hi, kLog2e), el = ex2_negabs2(lo, kLog2e);
+    const float2 a = add2(eh, splat2(1.0f)), b = add2(el, splat2(1.0f));
+    const float2 ab = mul2(a, b);
+    const float2 r = mk2(fast_rcp(ab.x), fast_rcp(ab.y));
+    const float2 d = fma2(eh, splat2(-1.0f), el);                       // el - eh
+    const float2 mix = fma2(mul2(el, eh), splat2(-1.0f), splat2(1.0f));  // 1 - el*eh
+    const float2 hl = mul2(hi, lo);
+    const float2 num = mk2(hl.x > 0.f ? fabsf(d.x) : mix.x, hl.y > 0.f ? fabsf(d.y) : mix.y);
+    const float2 sel = fma2(em.fl, b, fma2(em.fu, a, mul2(em.fm, num)));
+    float2 q = mul2(sel, r);
+    q = mk2(fmaxf(q.x, kEpsF), fmaxf(q.y, kEpsF));
+    const float2 lin = fma2(em.fu, mk2(-fmaxf(lo.x, 0.f), -fmaxf(lo.y, 0.f)), mul2(em.fl, mk2(fminf(hi.x, 0.f), fminf(hi.y, 0.f))));
+    float2 L = fma2(mk2(fast_lg2(q.x), fast_lg2(q.y)), splat2(kLn2), lin);
+    if (em.fm.x > 0.f && !(q.x > kDeltaMin)) L.x = logistic_approx_logprob(hi.x - sh.x, ls.x);
+    if (em.fm.y > 0.f && !(q.y > kDeltaMin)) L.y = logistic_approx_logprob(hi.y - sh.y, ls.y);
+    return L;
+}
+
+// one mixture component for two pixels: T.x, T.y
+MAE_HD float2 dmol_component2(const float2 mu[3], const float2 rho[3], const float2 kap[3], const float2 x[3]) {
+    const float2 e0 = ex2_negabs2(kap[0], 2.0f * kLog2e), e1 = ex2_negabs2(kap[1], 2.0f * kLog2e),
+                 e2 = ex2_negabs2(kap[2], 2.0f * kLog2e);
+    const float2 one = splat2(1.0f);
+    const float2 p0 = add2(e0, one), p1 = add2(e1, one), p2 = add2(e2, one);
+    const float2 p01 = mul2(p0, p1), p12 = mul2(p1, p2);
+    const float2 p012 = mul2(p01, p2);
+    const float2 r3 = mk2(fast_rcp(p012.x), fast_rcp(p012.y));
+    const float2 i0 = mul2(r3, p12), i1 = mul2(mul2(r3, p0), p2), i2 = mul2(r3, p01);
+    const float2 m0 = mul2(fma2(e0, splat2(-1.0f), one), i0), m1 = mul2(fma2(e1, splat2(-1.0f), one), i1),
+                 m2 = mul2(fma2(e2, splat2(-1.0f), one), i2);
+    const float2 c0 = mk2(copysignf(m0.x, kap[0].x), copysignf(m0.y, kap[0].y));
+    const float2 c1 = mk2(copysignf(m1.x, kap[1].x), copysignf(m1.y, kap[1].y));
+    const float2 c2 = mk2(copysignf(m2.x, kap[2].x), copysignf(m2.y, kap[2].y));
+    const float2 mone = splat2(-1.0f);
+    // cx = x - mean, mean0 = mu0, mean1 = mu1 + c0 x0, mean2 = mu2 + c1 x0 + c2 x1
+    const float2 cx0 = fma2(mu[0], mone, x[0]);
+    const float2 cx1 = fma2(fma2(c0, x[0], mu[1]), mone, x[1]);
+    const float2 cx2 = fma2(fma2(c2, x[1], fma2(c1, x[0], mu[2])), mone, x[2]);
+    float2 T = logistic_bin_logprob2(cx0, rho[0], x[0]);
+    T = add2(T, logistic_bin_logprob2(cx1, rho[1], x[1]));
+    T = add2(T, logistic_bin_logprob2(cx2, rho[2], x[2]));
+    return T;
+}
+
+// online log-sum-exp for two pixels
+struct Lse2 {
+    float2 m, s;
+    MAE_HD void init() { m = splat2(-INFINITY); s = splat2(0.f); }
+    MAE_HD void push(float2 v) {
+        const float2 dv = mk2(v.x - m.x, v.y - m.y);   // (-inf) - (-inf) never occurs: v is finite
+        const float2 e = ex2_negabs2(dv, kLog2e);
+        const float2 grow = fma2(s, e, splat2(1.0f)), keep = add2(s, e);
+        s = mk2(v.x <= m.x ? keep.x : grow.x, v.y <= m.y ? keep.y : grow.y);
+        m = mk2(fmaxf(m.x, v.x), fmaxf(m.y, v.y));
+    }
+    MAE_HD float2 value() const { return fma2(mk2(fast_lg2(s.x), fast_lg2(s.y)), splat2(kLn2), m); }
+};
+
 // Bernoulli pixel term and its derivative w.r.t. the probability (binary_image_decoder.py:91).
 // "1.0 - p + eps" is evaluated left to right like the reference.
 MAE_HD float bernoulli_logprob(float p, float x) {

@@ -19,6 +19,40 @@ extern "C" void hc_dmol_fwd(const float* raw, const float* x, int64_t B, int64_t
     }
 }
 
+// forward through the packed two-pixel path (pixels p, p+1; an odd tail pixel is paired with itself)
+extern "C" void hc_dmol_fwd_pair(const float* raw, const float* x, int64_t B, int64_t ns, int64_t nmix, int64_t HW, float* err) {
+    for (int64_t n = 0; n < B * ns; ++n) {
+        const int64_t b = n / ns;
+        float tot = 0.f;
+        for (int64_t p = 0; p < HW; p += 2) {
+            const int64_t p1 = p + 1 < HW ? p + 1 : p;
+            float2 xs[3];
+            for (int c = 0; c < 3; ++c) xs[c] = mk2(x[(b * 3 + c) * HW + p], x[(b * 3 + c) * HW + p1]);
+            const float* base = raw + n * 10 * nmix * HW;
+            Lse2 lt, ll;
+            lt.init();
+            ll.init();
+            for (int m = 0; m < nmix; ++m) {
+                float2 mu[3], rho[3], kap[3];
+                for (int c = 0; c < 3; ++c) {
+                    const int64_t o = (3 * m + c) * HW;
+                    mu[c] = mk2(base[(nmix)*HW + o + p], base[(nmix)*HW + o + p1]);
+                    rho[c] = mk2(base[4 * nmix * HW + o + p], base[4 * nmix * HW + o + p1]);
+                    kap[c] = mk2(base[7 * nmix * HW + o + p], base[7 * nmix * HW + o + p1]);
+                }
+                const float2 lg = mk2(base[m * HW + p], base[m * HW + p1]);
+                const float2 T = dmol_component2(mu, rho, kap, xs);
+                lt.push(add2(T, lg));
+                ll.push(lg);
+            }
+            const float2 zt = lt.value(), zl = ll.value();
+            tot += zl.x - zt.x;
+            if (p1 != p) tot += zl.y - zt.y;
+        }
+        err[n] = tot;
+    }
+}
+
 extern "C" void hc_dmol_bwd(const float* raw, const float* x, const float* g, int64_t B, int64_t ns, int64_t nmix, int64_t HW,
                             float* draw) {
     for (int64_t n = 0; n < B * ns; ++n) {

@@ -39,6 +39,9 @@ def test_dmol_pixel_math(hc, golden):
         hc.hc_dmol_bwd(_p(raw), _p(x), _p(g), i64(b), i64(ns), i64(nmix), i64(hw), _p(draw))
         check_close(err, c["ref64"]["err"], c["ref32"]["err"], what=name + " err")
         check_close(draw, c["ref64"]["draw"], c["ref32"]["draw"], what=name + " draw")
+        err2 = torch.empty(b, ns)
+        hc.hc_dmol_fwd_pair(_p(raw), _p(x), i64(b), i64(ns), i64(nmix), i64(hw), _p(err2))   # packed two-pixel path
+        check_close(err2, c["ref64"]["err"], c["ref32"]["err"], what=name + " err (packed pair path)")
 
 
 def test_bernoulli_math(hc, golden):
