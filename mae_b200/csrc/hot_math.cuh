@@ -55,13 +55,13 @@ constexpr float kLn2 = 0.6931471805599453f;
 template <bool GRAD>
 MAE_HD float logistic_bin_logprob(float cx, float ls, float x, float& d_cx, float& d_ls) {
     const float s = fast_ex2(-kLog2e * ls);
-    const float u = s * cx;
     const float sh = s * kBin;
-    const float hi = u + sh, lo = u - sh;
+    const float hi = fmaf(s, cx, sh), lo = fmaf(s, cx, -sh);
     const float eh = fast_ex2(-kLog2e * fabsf(hi)), el = fast_ex2(-kLog2e * fabsf(lo));
     const float a = 1.0f + eh, b = 1.0f + el;
     const float r = fast_rcp(a * b);
-    const float num = lo > 0.f ? (el - eh) : (hi < 0.f ? (eh - el) : (1.0f - el * eh));
+    // same sign (hi*lo > 0): |el - eh| ; opposite signs: 1 - el*eh
+    const float num = (hi * lo > 0.f) ? fabsf(el - eh) : fmaf(-el, eh, 1.0f);
     const float delta = num * r;
     const bool is_up = x > kUpper, is_low = x < kLower;
     const float q = is_up ? a * r : (is_low ? b * r : fmaxf(delta, kEpsF));
@@ -78,6 +78,7 @@ MAE_HD float logistic_bin_logprob(float cx, float ls, float x, float& d_cx, floa
         d_ls = -(hi * dp + lo * dq);
     }
     if (!is_up && !is_low && !(delta > kDeltaMin)) {  // very wide / very far component: density * bin width
+        const float u = s * cx;
         const float eu = fast_ex2(-kLog2e * fabsf(u));
         const float sp = fmaxf(u, 0.f) + kLn2 * fast_lg2(1.0f + eu);  // softplus(u)
         L = u - ls - 2.0f * sp + kLog2Bin;
