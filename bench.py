@@ -43,6 +43,18 @@ def measured_peaks():
     return 6650.0, "fallback"
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu --set full capture
+    (profiles/r1_ncu_traffic.json); None if the file is absent."""
+    path = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
+    try:
+        with open(path) as f:
+            k = json.load(f)["dmol_bwd_kernel<10,1024,5>"]
+        return k["dram_bytes_read"] + k["dram_bytes_write"]
+    except Exception:
+        return None
+
+
 # ----------------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
     """Samples nvidia-smi SM clocks / throttle reasons while the timed region runs."""
@@ -331,7 +343,7 @@ def bench_ours(args):
     _dbg("kernel timing done")
     roof = {"bound": "hbm", "kernel": "dmol_bwd_kernel<10,1024,5,ERR=true> (fused forward+backward)",
             "achieved": step_bytes / t_fused / 1e9, "peak": hbm_gbs, "unit": "GB/s", "frac": step_bytes / t_fused / 1e9 / hbm_gbs,
-            "traffic": None, "peak_source": peak_src, "bytes_per_launch": step_bytes, "us_per_launch": t_fused * 1e6,
+            "traffic": ncu_traffic(), "peak_source": peak_src, "bytes_per_launch": step_bytes, "us_per_launch": t_fused * 1e6,
             "bytes_moved_by_design": bwd_b, "frac_of_bytes_moved": bwd_b / t_fused / 1e9 / hbm_gbs,
             "note": "algorithmic bytes = fwd 27.0 MB + bwd 53.2 MB (SURVEY 8d); the fused kernel reads raw once and writes d raw once",
             "dmol_bwd_alone": {"achieved": bwd_b / t_bwd / 1e9, "frac": bwd_b / t_bwd / 1e9 / hbm_gbs, "bytes_per_launch": bwd_b,
@@ -373,11 +385,13 @@ def bench_extra(dev, hbm_gbs):
     from mae_b200 import heads, ops, synth
     res = {}
     stream = torch.cuda.current_stream()
-    # ---- C4: K=512 samples per image, 2 images per launch, ring of 4 slabs (4 x 419 MB) > L2
-    k, nimg, d = 512, 2, 64
-    slabs = []
+    # ---- C4: K=512 samples per image, 4 images per launch, ring of 3 slabs (3 x 839 MB) > L2; each slab's evaluation
+    #      (DMOL forward + fused IW kernel) is captured in a CUDA graph so the figure is device throughput, not the
+    #      Python launch rate
+    k, nimg, d = 512, 4, 64
+    slabs, graphs, outs = [], [], []
     g = torch.Generator(device=dev).manual_seed(524287)
-    for i in range(4):
+    for i in range(3):
         raw = torch.randn(nimg * k, 100, 32, 32, device=dev, generator=g)
         x = (torch.randint(0, 256, (nimg, 3, 32, 32), device=dev, generator=g).float() / 127.5 - 1.0)
         mu = torch.randn(nimg, d, device=dev, generator=g)
@@ -385,16 +399,26 @@ def bench_extra(dev, hbm_gbs):
         z = mu[:, None] + torch.randn(nimg, k, d, device=dev, generator=g) * (0.5 * lv).exp()[:, None]
         slabs.append((raw, x, z, mu, lv))
     per_img = 4 * (k * 100 * 1024 + 3 * 1024 + k * (2 * d + 3) + 2 * d)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for sl in slabs:
+            heads.iw_eval_color(*sl, 10)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    for sl in slabs:
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            outs.append(heads.iw_eval_color(*sl, 10))
+        graphs.append(gr)
 
-    def c4(i):
-        raw, x, z, mu, lv = slabs[i % 4]
-        return heads.iw_eval_color(raw, x, z, mu, lv, 10)
-
-    t = time_kernel(c4, 24, stream)
+    t = time_kernel(lambda i: graphs[i % 3].replay(), 30, stream)
     res["c4_iw_nll_eval"] = {"metric": "iw_nll_eval_images_per_s", "value": nimg / t, "unit": "images/s",
-                             "config": "CIFAR shapes, K=512, %d images/launch, ring of 4 slabs (1.7 GB) > L2" % nimg,
+                             "config": "CIFAR shapes, K=512, %d images/launch, ring of 3 slabs (2.5 GB) > L2, CUDA graph" % nimg,
+                             "us_per_image": t / nimg * 1e6,
                              "roofline": {"bound": "hbm", "achieved": nimg * per_img / t / 1e9, "peak": hbm_gbs,
                                           "frac": nimg * per_img / t / 1e9 / hbm_gbs, "bytes_per_image": per_img}}
+    del graphs, outs
     del slabs
     torch.cuda.empty_cache()
     # ---- C1/C2: binary head fwd+bwd, B=100, D=64 (launch-latency-bound: 1.57 MB / 10 MFLOP per step)
