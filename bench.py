@@ -556,16 +556,22 @@ def main():
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads (C1, C4, C5)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
+    # stdout carries exactly one JSON line: library chatter written to fd 1 (NCCL prints its version banner there at
+    # N > 1) is sent to stderr while the benchmark runs
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         out = bench_reference(args)
     else:
         if not torch.cuda.is_available():
             raise SystemExit("bench.py needs a CUDA device (the hot path has no CPU fallback); use --impl reference for the CPU arm")
         out = bench_ours(args)
-    if out is not None:
-        print(json.dumps(out))
     sys.stdout.flush()
     sys.stderr.flush()
+    if out is not None:
+        os.write(real_stdout, (json.dumps(out) + "\n").encode())
+    os.close(real_stdout)
     if int(os.environ.get("WORLD_SIZE", "1")) > 1 and args.impl == "ours":
         # NCCL communicator teardown with live CUDA graphs that captured collectives hangs in this stack
         # (torch 2.11 / NCCL 2.28.9); every rank has passed the final barrier, so leave without it.

@@ -87,8 +87,8 @@ int mae_reparam_kl_bwd(const float* mu, int64_t mu_stride, const float* logvar, 
  * mae_mpd_fwd     : tiles for rows [row0,row0+nrows) x all B columns.  Writes sumsq[0] (double) =
  *                   sum over those rows and all j != i of (KL_ij - m)^2, and, if S is non-NULL,
  *                   S[0] = sqrt(sumsq/(B(B-1)-1)) (meaningful when the row range covers all rows).
- *                   store_kl != 0 additionally keeps the KL tiles in the workspace for the small-B
- *                   backward (requires B <= MAE_MPD_SMALL_B and the full row range).
+ *                   store_kl != 0 additionally keeps the KL tiles (and their transpose) in the workspace for the
+ *                   stored-KL backward paths (requires the full row range and a workspace sized with store_kl).
  * mae_mpd_finalize: S[0] = sqrt(sumsq[0]/(B(B-1)-1)) after sumsq has been all-reduced across ranks.
  * mae_mpd_bwd     : gradient of  sum_d g_m[d]*m_d + g_S*S  w.r.t. mu and logvar of rows
  *                   [row0,row0+nrows): dmu/dlogvar are dense [nrows,D].  Each row's contribution both
@@ -96,10 +96,15 @@ int mae_reparam_kl_bwd(const float* mu, int64_t mu_stride, const float* logvar, 
  *                   reduce-scatter of column gradients is needed.  g_S and S are device scalars.
  *                   gkl (nullable, [B] indexed by global row) is the upstream gradient of the analytic KL written
  *                   by mae_mpd_prepare; its contribution gkl*mu / 0.5*gkl*(exp(logvar)-1) is added in the epilogue.
- *                   path: 0 = choose automatically, 1 = stored-KL path, 2 = recompute-tile path.
+ *                   path: 0 = choose automatically, 1 = stored-KL per-row kernel (B <= 2048), 2 = recompute tiles
+ *                   (nothing stored), 3 = stored-KL tile GEMMs (any B whose KL tiles were kept by mae_mpd_fwd:
+ *                   8*B^2*D flop instead of 16*B^2*D, plus one streaming read of the two B x B matrices).
  * ---------------------------------------------------------------------------------------------- */
 #define MAE_MPD_SMALL_B 2048
-int64_t mae_mpd_workspace_bytes(int64_t B, int64_t D);
+/* store_kl != 0: room for KL[Bp][Bp] and its transpose (8*Bp^2 bytes, Bp = B rounded up to 64) at the end of the
+ * workspace, needed by the stored-KL backward paths 1 and 3; B200's 180 GB make this affordable far beyond the point
+ * where recomputing the tiles (path 2, 16*B^2*D flop) is the only option (B = 65536 -> 34 GB). */
+int64_t mae_mpd_workspace_bytes(int64_t B, int64_t D, int store_kl);
 int mae_mpd_prepare(const float* mu, int64_t mu_stride, const float* logvar, int64_t logvar_stride,
                     int64_t B, int64_t D, void* workspace, int64_t workspace_bytes,
                     float* m_d, float* kl, mae_stream_t stream);

@@ -50,7 +50,7 @@ PLAIN = {
     "mae_abi_version": (c_int, []),
     "mae_strerror": (c_char_p, [c_int]),
     "mae_device_info": (c_int, [_P, _P, _P]),
-    "mae_mpd_workspace_bytes": (c_int64, [_I64, _I64]),
+    "mae_mpd_workspace_bytes": (c_int64, [_I64, _I64, _I]),
     "mae_dmol_workspace_bytes": (c_int64, [_I64, _I64]),
     "mae_iw_nll_workspace_bytes": (c_int64, [_I64, _I64]),
     "mae_comm_buffer_bytes": (c_int64, [_I64, _I64]),

@@ -73,12 +73,15 @@ __device__ __forceinline__ unsigned long long now_ns() {
 struct Layout {
     int64_t Bp, Kp, nblk;
     int64_t prep_rows, prep_grid;  // rows per CTA / CTAs of mpd_prepare_kernel
-    int64_t hdr, colstats, pivots, c, l, xp, yp, vp, part_prep, part_fwd, kl, klt, total;
+    int64_t hdr, colstats, pivots, c, l, xp, yp, vp, part_prep, part_fwd, kl, klt, total, total_nokl;
 };
+
+constexpr int64_t kBigTileRows = 2048;  // padded batch from which the forward uses 128 x 128 tiles
 
 Layout make_layout(int64_t B, int64_t D) {
     Layout L;
     L.Bp = round_up(B, kT);
+    if (L.Bp >= kBigTileRows) L.Bp = round_up(B, 128);  // the 128 x 128 forward tiles need whole 128-row blocks
     L.Kp = round_up(2 * D, kKC);
     L.nblk = L.Bp / kT;
     // prepare: 8 rows per CTA for small batches (latency), at most ~1184 CTAs for large ones, <= 512 rows per CTA
@@ -104,12 +107,9 @@ Layout make_layout(int64_t B, int64_t D) {
     L.vp = take(L.Bp * D * 16);
     L.part_prep = take(L.prep_grid * kStats * D * 8);
     L.part_fwd = take(kMaxFwdCtas * 8);
-    if (B <= MAE_MPD_SMALL_B) {
-        L.kl = take(L.Bp * L.Bp * 4);
-        L.klt = take(L.Bp * L.Bp * 4);
-    } else {
-        L.kl = L.klt = -1;
-    }
+    L.total_nokl = off;           // everything the forward needs when the KL tiles are not kept
+    L.kl = take(L.Bp * L.Bp * 4);  // optional tail: KL[Bp][Bp] and its transpose (stored-KL backward paths)
+    L.klt = take(L.Bp * L.Bp * 4);
     L.total = off;
     return L;
 }
@@ -398,6 +398,7 @@ mpd_fwd_kernel(const float* __restrict__ Xp, const float* __restrict__ Yp, const
     constexpr int T = 16 * TM;       // tile edge
     constexpr int LD = T + 4;        // padded leading dimension
     constexpr int NLOAD = T * 4;     // float4 loads per operand slab (T rows x 16 k)
+    constexpr int LPT = (2 * NLOAD) / kNT;   // slab loads per thread per K step: 1 (TM=2), 2 (TM=4), 4 (TM=8)
     __shared__ __align__(16) float As[2][kKC][LD];
     __shared__ __align__(16) float Bs[2][kKC][LD];
     __shared__ double scratch[32];
@@ -407,12 +408,9 @@ mpd_fwd_kernel(const float* __restrict__ Xp, const float* __restrict__ Yp, const
     const float m = (float)hdr->m;
     double total = 0.0;
     const int ntiles = ntr * ntc;
-    // slab staging role of this thread: TM = 4 -> every thread loads one float4 of X and one of Y;
-    // TM = 2 -> threads [0,128) load X, [128,256) load Y
-    const bool two = (NLOAD == kNT);
-    const int lid = two ? tid : (tid % NLOAD);
-    const bool ldx = two || tid < NLOAD, ldy = two || tid >= NLOAD;
-    const int r = lid >> 2, kq = (lid & 3) * 4;
+    // micro-tile coordinates: contiguous TM x TM for TM <= 4; for TM = 8 two groups of 4, 64 apart, so that the
+    // 16-byte shared-memory reads of a quarter warp fall into distinct banks
+    auto rc = [](int t, int i) { return TM == 8 ? ((i < 4) ? t * 4 + i : 64 + t * 4 + (i - 4)) : t * TM + i; };
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int ti = tr0 + tile / ntc, tj = tile % ntc;
         float acc[TM][TM];
@@ -422,27 +420,43 @@ mpd_fwd_kernel(const float* __restrict__ Xp, const float* __restrict__ Yp, const
             for (int j = 0; j < TM; ++j) acc[i][j] = 0.f;
         // K loop: the next slab is fetched into registers while the current one is multiplied
         {
-            const float* xa = Xp + ((int64_t)ti * T + r) * Kp + kq;
-            const float* yb = Yp + ((int64_t)tj * T + r) * Kp + kq;
-            float4 ra = make_float4(0.f, 0.f, 0.f, 0.f), rb = ra;
-            if (ldx) ra = *reinterpret_cast<const float4*>(xa);
-            if (ldy) rb = *reinterpret_cast<const float4*>(yb);
+            const float* src[LPT];
+            float (*dstp[LPT])[kKC][LD];
+            int rr[LPT], kk[LPT];
+#pragma unroll
+            for (int q = 0; q < LPT; ++q) {
+                const int item = tid + q * kNT;          // [0, NLOAD): X slab, [NLOAD, 2 NLOAD): Y slab
+                const bool isx = item < NLOAD;
+                const int idx = isx ? item : item - NLOAD;
+                rr[q] = idx >> 2;
+                kk[q] = (idx & 3) * 4;
+                src[q] = (isx ? Xp + ((int64_t)ti * T + rr[q]) * Kp : Yp + ((int64_t)tj * T + rr[q]) * Kp) + kk[q];
+                dstp[q] = isx ? As : Bs;
+            }
+            float4 reg[LPT];
+#pragma unroll
+            for (int q = 0; q < LPT; ++q) reg[q] = *reinterpret_cast<const float4*>(src[q]);
             int buf = 0;
             for (int k0 = 0; k0 < Kp; k0 += kKC) {
-                if (ldx) { As[buf][kq + 0][r] = ra.x; As[buf][kq + 1][r] = ra.y; As[buf][kq + 2][r] = ra.z; As[buf][kq + 3][r] = ra.w; }
-                if (ldy) { Bs[buf][kq + 0][r] = rb.x; Bs[buf][kq + 1][r] = rb.y; Bs[buf][kq + 2][r] = rb.z; Bs[buf][kq + 3][r] = rb.w; }
+#pragma unroll
+                for (int q = 0; q < LPT; ++q) {
+                    dstp[q][buf][kk[q] + 0][rr[q]] = reg[q].x;
+                    dstp[q][buf][kk[q] + 1][rr[q]] = reg[q].y;
+                    dstp[q][buf][kk[q] + 2][rr[q]] = reg[q].z;
+                    dstp[q][buf][kk[q] + 3][rr[q]] = reg[q].w;
+                }
                 __syncthreads();
                 if (k0 + kKC < Kp) {
-                    if (ldx) ra = *reinterpret_cast<const float4*>(xa + k0 + kKC);
-                    if (ldy) rb = *reinterpret_cast<const float4*>(yb + k0 + kKC);
+#pragma unroll
+                    for (int q = 0; q < LPT; ++q) reg[q] = *reinterpret_cast<const float4*>(src[q] + k0 + kKC);
                 }
 #pragma unroll
                 for (int k = 0; k < kKC; ++k) {
                     float av[TM], bv[TM];
 #pragma unroll
                     for (int i = 0; i < TM; ++i) {
-                        av[i] = As[buf][k][ty * TM + i];
-                        bv[i] = Bs[buf][k][tx * TM + i];
+                        av[i] = As[buf][k][rc(ty, i)];
+                        bv[i] = Bs[buf][k][rc(tx, i)];
                     }
 #pragma unroll
                     for (int i = 0; i < TM; ++i)
@@ -455,19 +469,18 @@ mpd_fwd_kernel(const float* __restrict__ Xp, const float* __restrict__ Yp, const
         }
         MAE_STAMP(hdr, 9);
         float psum = 0.f;
-        const int jb = tj * T + tx * TM;
         float fj[TM];
 #pragma unroll
-        for (int jj = 0; jj < TM; ++jj) fj[jj] = fvec[jb + jj];
+        for (int jj = 0; jj < TM; ++jj) fj[jj] = fvec[tj * T + rc(tx, jj)];
         float klv[TM][TM];
 #pragma unroll
         for (int ii = 0; ii < TM; ++ii) {
-            const int i = ti * T + ty * TM + ii;
+            const int i = ti * T + rc(ty, ii);
             const float ei = evec[i];
             const bool row_ok = (i >= row0) && (i < row1);
 #pragma unroll
             for (int jj = 0; jj < TM; ++jj) {
-                const int j = jb + jj;
+                const int j = tj * T + rc(tx, jj);
                 const float kl = 0.5f * (acc[ii][jj] + ei + fj[jj]);
                 klv[ii][jj] = kl;
                 if (row_ok && j < B && j != i) {
@@ -477,15 +490,14 @@ mpd_fwd_kernel(const float* __restrict__ Xp, const float* __restrict__ Yp, const
             }
             if (KL != nullptr) {
 #pragma unroll
-                for (int jj = 0; jj < TM; ++jj) KL[(int64_t)i * Bp + jb + jj] = klv[ii][jj];
+                for (int jj = 0; jj < TM; ++jj) KL[(int64_t)i * Bp + tj * T + rc(tx, jj)] = klv[ii][jj];
             }
         }
         if (KLT != nullptr) {
-            const int ib = ti * T + ty * TM;
 #pragma unroll
             for (int jj = 0; jj < TM; ++jj)
 #pragma unroll
-                for (int ii = 0; ii < TM; ++ii) KLT[(int64_t)(jb + jj) * Bp + ib + ii] = klv[ii][jj];
+                for (int ii = 0; ii < TM; ++ii) KLT[(int64_t)(tj * T + rc(tx, jj)) * Bp + ti * T + rc(ty, ii)] = klv[ii][jj];
         }
         total += (double)psum;
     }
@@ -652,19 +664,24 @@ mpd_bwd_small_kernel(const float* __restrict__ mu, int64_t mu_stride, const floa
 
 // ----------------------------------------------------------------------- backward, recompute tiles (large B)
 struct BwdSmem {
-    float XI[kKC][kLd], YI[kKC][kLd], XJ[kKC][kLd], YJ[kKC][kLd];
     float W1T[kT][kLd], W2T[kT][kLd];  // [j][i]
     float PY[kT][kLdP], PX[kT][kLdP];  // column panels of block J, this CTA's K chunk
+    float XI[kKC][kLd], YI[kKC][kLd], XJ[kKC][kLd], YJ[kKC][kLd];  // recompute path only (last: the stored path omits them)
 };
+constexpr size_t kBwdStoredSmem = offsetof(BwdSmem, XI);
 
 // grid: (row tiles, K chunks of kOC columns).  CTA owns rows [i0,i0+64) and gradient dims of its chunk.
-__global__ void __launch_bounds__(kNT)
+// STORED: the KL_ij / KL_ji tiles are read from the matrices the forward kept (one streaming pass over 2 B^2 floats)
+// instead of being recomputed (two K = 2D contractions per tile pair), which halves the backward's FFMA work.
+template <bool STORED>
+__global__ void __launch_bounds__(kNT, STORED ? 2 : 1)
 mpd_bwd_tile_kernel(const float* __restrict__ mu, int64_t mu_stride, const float* __restrict__ lv, int64_t lv_stride,
                     const float* __restrict__ Xp, const float* __restrict__ Yp, const float* __restrict__ evec,
                     const float* __restrict__ fvec, const float4* __restrict__ Vp, const double* __restrict__ colstats,
                     const double* __restrict__ pivots, const Hdr* __restrict__ hdr, const float* __restrict__ g_m, const float* __restrict__ g_S,
                     const float* __restrict__ S, const float* __restrict__ gkl, int B, int D, int Kp, int row0, int row1,
-                    int tr0, int ntc, float* __restrict__ dmu, float* __restrict__ dlv, int accumulate) {
+                    int tr0, int ntc, float* __restrict__ dmu, float* __restrict__ dlv, int accumulate,
+                    const float* __restrict__ KL, const float* __restrict__ KLT, int Bp) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     BwdSmem& sm = *reinterpret_cast<BwdSmem*>(smem_raw);
     const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
@@ -692,19 +709,31 @@ mpd_bwd_tile_kernel(const float* __restrict__ mu, int64_t mu_stride, const float
         for (int tj = 0; tj < ntc; ++tj) {
             const int j0 = tj * kT;
             float a1[4][4], a2[4][4];
+            if (STORED) {
+                // KL_ij = KL[i][j], KL_ji = KLT[i][j]: both row-contiguous in j -> 16-byte loads
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+                for (int ii = 0; ii < 4; ++ii) {
+                    const int64_t o = (int64_t)(i0 + ty * 4 + ii) * Bp + j0 + tx * 4;
+                    const float4 k1 = __ldcs(reinterpret_cast<const float4*>(KL + o));
+                    const float4 k2 = __ldcs(reinterpret_cast<const float4*>(KLT + o));
+                    a1[ii][0] = k1.x; a1[ii][1] = k1.y; a1[ii][2] = k1.z; a1[ii][3] = k1.w;
+                    a2[ii][0] = k2.x; a2[ii][1] = k2.y; a2[ii][2] = k2.z; a2[ii][3] = k2.w;
+                }
+            } else {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) a1[i][j] = a2[i][j] = 0.f;
-            for (int k0 = 0; k0 < Kp; k0 += kKC) {
-                stage_slab(Xp, (int64_t)i0, Kp, k0, sm.XI, tid);
-                stage_slab(Yp, (int64_t)i0, Kp, k0, sm.YI, tid);
-                stage_slab(Xp, (int64_t)j0, Kp, k0, sm.XJ, tid);
-                stage_slab(Yp, (int64_t)j0, Kp, k0, sm.YJ, tid);
-                __syncthreads();
-                fma_tile(sm.XI, sm.YJ, ty, tx, a1);  // x~_i . y~_j  -> KL_ij
-                fma_tile(sm.YI, sm.XJ, ty, tx, a2);  // y~_i . x~_j  -> KL_ji
-                __syncthreads();
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) a1[i][j] = a2[i][j] = 0.f;
+                for (int k0 = 0; k0 < Kp; k0 += kKC) {
+                    stage_slab(Xp, (int64_t)i0, Kp, k0, sm.XI, tid);
+                    stage_slab(Yp, (int64_t)i0, Kp, k0, sm.YI, tid);
+                    stage_slab(Xp, (int64_t)j0, Kp, k0, sm.XJ, tid);
+                    stage_slab(Yp, (int64_t)j0, Kp, k0, sm.YJ, tid);
+                    __syncthreads();
+                    fma_tile(sm.XI, sm.YJ, ty, tx, a1);  // x~_i . y~_j  -> KL_ij
+                    fma_tile(sm.YI, sm.XJ, ty, tx, a2);  // y~_i . x~_j  -> KL_ji
+                    __syncthreads();
+                }
             }
             // weights; W1T/W2T stored [j][i]
             const int jb = j0 + tx * 4;
@@ -721,8 +750,8 @@ mpd_bwd_tile_kernel(const float* __restrict__ mu, int64_t mu_stride, const float
                 for (int jj = 0; jj < 4; ++jj) {
                     const int j = jb + jj;
                     const bool ok = row_ok && j < B && j != i;
-                    const float kij = 0.5f * (a1[ii][jj] + ei[ii] + fj[jj]);
-                    const float kji = 0.5f * (a2[ii][jj] + ej[jj] + fi[ii]);
+                    const float kij = STORED ? a1[ii][jj] : 0.5f * (a1[ii][jj] + ei[ii] + fj[jj]);
+                    const float kji = STORED ? a2[ii][jj] : 0.5f * (a2[ii][jj] + ej[jj] + fi[ii]);
                     w1[ii][jj] = ok ? beta * (kij - m) : 0.f;
                     w2[ii][jj] = ok ? beta * (kji - m) : 0.f;
                     rs1[ii] += w1[ii][jj];
@@ -818,16 +847,17 @@ int check_common(int64_t B, int64_t D, const void* ws, int64_t ws_bytes, Layout&
     MAE_REQUIRE(B >= 2 && D >= 1 && B <= (1ll << 22) && D <= (1ll << 20), MAE_ERR_SHAPE);
     MAE_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 255) == 0, MAE_ERR_ALIGN);
     L = make_layout(B, D);
-    MAE_REQUIRE(ws_bytes >= L.total, MAE_ERR_WORKSPACE);
+    MAE_REQUIRE(ws_bytes >= L.total_nokl, MAE_ERR_WORKSPACE);
     return MAE_OK;
 }
 
 }  // namespace
 }  // namespace mae
 
-extern "C" int64_t mae_mpd_workspace_bytes(int64_t B, int64_t D) {
+extern "C" int64_t mae_mpd_workspace_bytes(int64_t B, int64_t D, int store_kl) {
     if (B < 2 || D < 1) return 0;
-    return mae::make_layout(B, D).total;
+    const mae::Layout L = mae::make_layout(B, D);
+    return store_kl ? L.total : L.total_nokl;
 }
 
 extern "C" int mae_mpd_prepare(const float* mu, int64_t mu_stride, const float* logvar, int64_t logvar_stride, int64_t B,
@@ -856,7 +886,10 @@ extern "C" int mae_mpd_fwd(void* workspace, int64_t workspace_bytes, int64_t B, 
     int rc = check_common(B, D, workspace, workspace_bytes, L);
     if (rc != MAE_OK) return rc;
     MAE_REQUIRE(row0 >= 0 && nrows >= 1 && row0 + nrows <= B, MAE_ERR_SHAPE);
-    if (store_kl) MAE_REQUIRE(B <= MAE_MPD_SMALL_B && row0 == 0 && nrows == B, MAE_ERR_UNSUPPORTED);
+    if (store_kl) {
+        MAE_REQUIRE(row0 == 0 && nrows == B, MAE_ERR_UNSUPPORTED);
+        MAE_REQUIRE(workspace_bytes >= L.total, MAE_ERR_WORKSPACE);
+    }
     float* klp = store_kl ? at<float>(workspace, L.kl) : nullptr;
     float* kltp = store_kl ? at<float>(workspace, L.klt) : nullptr;
     auto launch = [&](auto tm_tag) {
@@ -872,8 +905,9 @@ extern "C" int mae_mpd_fwd(void* workspace, int64_t workspace_bytes, int64_t B, 
             at<Hdr>(workspace, L.hdr), at<double>(workspace, L.part_fwd), (int)B, (int)L.Kp, (int)row0, (int)(row0 + nrows), tr0,
             ntr, ntc, klp, kltp, (int)L.Bp, sumsq, S);
     };
-    if (L.Bp <= 256) launch(std::integral_constant<int, 2>{});   // small batches: 32 x 32 tiles, more CTAs, less latency
-    else launch(std::integral_constant<int, 4>{});
+    if (L.Bp <= 256) launch(std::integral_constant<int, 2>{});        // small batches: 32 x 32 tiles, more CTAs, less latency
+    else if (L.Bp < kBigTileRows) launch(std::integral_constant<int, 4>{});   // 64 x 64
+    else launch(std::integral_constant<int, 8>{});                    // 128 x 128, 8 x 8 micro-tiles: FFMA-bound regime
     return launch_status();
 }
 
@@ -897,8 +931,9 @@ extern "C" int mae_mpd_bwd(const float* mu, int64_t mu_stride, const float* logv
     int rc = check_common(B, D, workspace, workspace_bytes, L);
     if (rc != MAE_OK) return rc;
     MAE_REQUIRE(row0 >= 0 && nrows >= 1 && row0 + nrows <= B, MAE_ERR_SHAPE);
-    MAE_REQUIRE(path >= 0 && path <= 2, MAE_ERR_SHAPE);
+    MAE_REQUIRE(path >= 0 && path <= 3, MAE_ERR_SHAPE);
     if (path == 0) path = (B <= MAE_MPD_SMALL_B) ? 1 : 2;
+    if (path == 1 || path == 3) MAE_REQUIRE(workspace_bytes >= L.total, MAE_ERR_WORKSPACE);
     if (path == 1) {
         MAE_REQUIRE(B <= MAE_MPD_SMALL_B, MAE_ERR_UNSUPPORTED);
         const int64_t items = nrows * ceil_div(D, 32);
@@ -917,19 +952,25 @@ extern "C" int mae_mpd_bwd(const float* mu, int64_t mu_stride, const float* logv
         else launch(std::integral_constant<int, 1>{});
         return launch_status();
     }
-    {
-        cudaError_t e = cudaFuncSetAttribute(mpd_bwd_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdSmem));
-        if (e != cudaSuccess) return (int)e;
-    }
     const int tr0 = (int)(row0 / kT);
     const int ntr = (int)(ceil_div(row0 + nrows, kT) - tr0);
     const int nchunks = (int)ceil_div(L.Kp, kOC);
     MAE_REQUIRE(nchunks <= 65535, MAE_ERR_SHAPE);
     dim3 grid((unsigned)ntr, (unsigned)nchunks);
-    mpd_bwd_tile_kernel<<<grid, kNT, sizeof(BwdSmem), as_stream(stream)>>>(
-        mu, mu_stride, logvar, logvar_stride, at<float>(workspace, L.xp), at<float>(workspace, L.yp), at<float>(workspace, L.c),
-        at<float>(workspace, L.l), at<float4>(workspace, L.vp), at<double>(workspace, L.colstats),
-        at<double>(workspace, L.pivots), at<Hdr>(workspace, L.hdr), g_m, g_S, S, gkl, (int)B, (int)D,
-        (int)L.Kp, (int)row0, (int)(row0 + nrows), tr0, (int)L.nblk, dmu, dlogvar, accumulate);
+    auto launch = [&](auto stored_tag) -> int {
+        constexpr bool STORED = decltype(stored_tag)::value;
+        const size_t smem = STORED ? kBwdStoredSmem : sizeof(BwdSmem);
+        cudaError_t e = cudaFuncSetAttribute(mpd_bwd_tile_kernel<STORED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        mpd_bwd_tile_kernel<STORED><<<grid, kNT, smem, as_stream(stream)>>>(
+            mu, mu_stride, logvar, logvar_stride, at<float>(workspace, L.xp), at<float>(workspace, L.yp),
+            at<float>(workspace, L.c), at<float>(workspace, L.l), at<float4>(workspace, L.vp),
+            at<double>(workspace, L.colstats), at<double>(workspace, L.pivots), at<Hdr>(workspace, L.hdr), g_m, g_S, S, gkl,
+            (int)B, (int)D, (int)L.Kp, (int)row0, (int)(row0 + nrows), tr0, (int)L.nblk, dmu, dlogvar, accumulate,
+            STORED ? at<float>(workspace, L.kl) : nullptr, STORED ? at<float>(workspace, L.klt) : nullptr, (int)L.Bp);
+        return MAE_OK;
+    };
+    rc = (path == 3) ? launch(std::true_type{}) : launch(std::false_type{});
+    if (rc != MAE_OK) return rc;
     return launch_status();
 }

@@ -6,6 +6,7 @@ fallback.  Launches go to ``torch.cuda.current_stream()`` so the ops compose wit
 """
 from __future__ import annotations
 
+import os
 import threading
 from typing import Dict, List, Optional, Tuple
 
@@ -198,6 +199,24 @@ def _mpd_launch_fwd(mu2, ms, lv2, ls, b, d, ws, store_kl, outs, row0=0, nrows=No
     return m_d, s, sumsq
 
 
+# Largest pair of stored B x B KL matrices (KL and its transpose, 8*Bp^2 bytes) the backward may keep between forward
+# and backward; above it the tiles are recomputed (path 2).  B200: 180 GB of HBM, B = 32768 needs 8.6 GB.
+MPD_KL_BUDGET_BYTES = int(os.environ.get("MAE_MPD_KL_BUDGET_BYTES", 16 << 30))
+
+
+def _mpd_pick_path(b: int, d: int, requested: int) -> int:
+    """Backward path of mae_mpd_bwd: 1 stored-KL per-row kernel (B <= 2048), 3 stored-KL tile GEMMs, 2 recompute."""
+    if requested in (2, 3):
+        return requested
+    if requested == 1 or b <= 2048:
+        if b > 2048:
+            raise ValueError("bwd_path=1 (per-row stored-KL kernel) supports B <= 2048")
+        return 1
+    lib = _lib_()
+    extra = lib.mae_mpd_workspace_bytes(b, d, 1) - lib.mae_mpd_workspace_bytes(b, d, 0)
+    return 3 if extra <= MPD_KL_BUDGET_BYTES else 2
+
+
 class _MPD(torch.autograd.Function):
     """(mu, logvar) -> (m_d, S, KL).  KL is the analytic KL(q || N(0,I)) when ``with_kl`` (else an empty tensor): it
     shares the O(B*D) pre-pass with the MPD, and its gradient is folded into the MPD backward kernel."""
@@ -215,8 +234,9 @@ class _MPD(torch.autograd.Function):
         lib = _lib_()
         dev = mu.device
         need_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
-        small = b <= 2048 and bwd_path != 2
-        nbytes = lib.mae_mpd_workspace_bytes(b, d)
+        path = _mpd_pick_path(b, d, bwd_path) if need_grad else 2
+        store = path != 2
+        nbytes = lib.mae_mpd_workspace_bytes(b, d, int(store))
         outs = _mpd_alloc_outputs(d, dev)   # owned by the main stream; the side stream only writes them
         kl = torch.empty(b if with_kl else 0, device=dev, dtype=torch.float32)
         klp = kl if with_kl else None
@@ -226,19 +246,19 @@ class _MPD(torch.autograd.Function):
             ss.wait_stream(cs)
             with torch.cuda.stream(ss):
                 ws = _pool.take(nbytes, dev)
-                m_d, s, _ = _mpd_launch_fwd(mu2, ms, lv2, ls, b, d, ws, need_grad and small, outs, kl=klp)
+                m_d, s, _ = _mpd_launch_fwd(mu2, ms, lv2, ls, b, d, ws, store, outs, kl=klp)
                 ev = torch.cuda.Event()
                 ev.record(ss)
             # everything the side-stream kernels touch stays referenced until the join
             _pending_join[dev.index if dev.index is not None else torch.cuda.current_device()] = (ev, (outs, kl, mu2, lv2))
         else:
             ws = _pool.take(nbytes, dev)
-            m_d, s, _ = _mpd_launch_fwd(mu2, ms, lv2, ls, b, d, ws, need_grad and small, outs, kl=klp)
+            m_d, s, _ = _mpd_launch_fwd(mu2, ms, lv2, ls, b, d, ws, store, outs, kl=klp)
         if need_grad:
             ctx.ws = ws
             ctx.side = bool(side)
             ctx.save_for_backward(mu2, lv2, s)
-            ctx.meta = (ms, ls, b, d, mu.shape, logvar.shape, 1 if small else 2)
+            ctx.meta = (ms, ls, b, d, mu.shape, logvar.shape, path)
         else:
             _MPD._release(ws, dev, side)
         if not with_kl:
@@ -311,7 +331,7 @@ def kl_mpd(mu: torch.Tensor, logvar: torch.Tensor, side_stream: bool = False, bw
 
 def mpd(mu: torch.Tensor, logvar: torch.Tensor, bwd_path: int = 0, side_stream: bool = False):
     """Mutual posterior divergence: (m_d with the shape of one latent, S scalar).
-    Reference: GaussianEncoder._postKL, gaussian_encoder.py:162-188.  ``bwd_path``: 0 auto, 1 stored-KL, 2 tiles.
+    Reference: GaussianEncoder._postKL, gaussian_encoder.py:162-188.  ``bwd_path``: 0 auto, 1 stored-KL per-row kernel (B <= 2048), 2 recompute tiles, 3 stored-KL tile GEMMs.
 
     ``side_stream=True`` launches the kernels on a side stream; the results may only be consumed after
     :func:`join_side` (``assemble_loss`` does it).  Used by ``MAE.loss`` / ``heads`` to overlap the regulariser with
@@ -327,7 +347,7 @@ def mpd_forward_only(mu: torch.Tensor, logvar: torch.Tensor, row0: int = 0, nrow
     mu2, ms = _rows(mu)
     lv2, ls = _rows(logvar)
     b, d = mu2.shape
-    ws = _pool.take(_lib_().mae_mpd_workspace_bytes(b, d), mu.device)
+    ws = _pool.take(_lib_().mae_mpd_workspace_bytes(b, d, 0), mu.device)
     m_d, s, sumsq = _mpd_launch_fwd(mu2, ms, lv2, ls, b, d, ws, False, _mpd_alloc_outputs(d, mu.device), row0, nrows)
     _pool.give(ws)
     return m_d.view(mu.shape[1:]), s, sumsq
@@ -354,10 +374,10 @@ def mpd_rows_forward(mu_all: torch.Tensor, logvar_all: torch.Tensor, row0: int, 
     if b < 2:
         raise RuntimeError("the MPD regulariser needs a global batch of at least 2 posteriors")
     dev = mu2.device
-    ws = _pool.take(_lib_().mae_mpd_workspace_bytes(b, d), dev)
+    small = full and b <= 2048
+    ws = _pool.take(_lib_().mae_mpd_workspace_bytes(b, d, int(small)), dev)
     kl_all = torch.empty(b, device=dev, dtype=torch.float32)
     outs = _mpd_alloc_outputs(d, dev)
-    small = full and b <= 2048
     if full:
         m_d, s, sumsq = _mpd_launch_fwd(mu2, ms, lv2, ls, b, d, ws, small, outs, kl=kl_all)
     else:

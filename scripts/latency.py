@@ -52,7 +52,7 @@ def main():
     raw, x = inp["raw"].to(dev), inp["x"].to(dev)
     st = lambda: torch.cuda.current_stream().cuda_stream
     z = torch.empty_like(eps); kl = torch.empty(B, device=dev)
-    ws = torch.zeros(lib.mae_mpd_workspace_bytes(B, D), dtype=torch.uint8, device=dev)
+    ws = torch.zeros(lib.mae_mpd_workspace_bytes(B, D, 1), dtype=torch.uint8, device=dev)
     m_d = torch.empty(D, device=dev); sumsq = torch.empty(1, device=dev, dtype=torch.float64); S = torch.empty((), device=dev)
     dmu = torch.empty(B, D, device=dev); dlv = torch.empty(B, D, device=dev)
     g_m = torch.randn(D, device=dev); g_S = torch.ones((), device=dev)

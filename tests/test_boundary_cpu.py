@@ -45,8 +45,9 @@ def test_argument_validation_without_gpu(lib):
     assert lib.mae_reparam_kl_fwd(p, 4, p, 4, p, 0, 1, 4, p, None, None) == -2       # B = 0
     assert lib.mae_bernoulli_fwd(p, p, 1, 1, 0, p, None) == -2
     assert lib.mae_dmol_fwd(p, p, 1, 1, 0, 16, p, p, 1024, None) == -2
-    assert lib.mae_mpd_workspace_bytes(1, 8) == 0                                    # MPD needs B >= 2
-    need = lib.mae_mpd_workspace_bytes(100, 64)
+    assert lib.mae_mpd_workspace_bytes(1, 8, 0) == 0                                    # MPD needs B >= 2
+    need = lib.mae_mpd_workspace_bytes(100, 64, 0)
+    assert lib.mae_mpd_workspace_bytes(100, 64, 1) == need + 2 * 4 * 128 * 128              # KL and KL^T, Bp = 128
     assert need > 0 and need % 256 == 0
     aligned = (p + 255) & ~255
     assert lib.mae_mpd_prepare(aligned, 64, aligned, 64, 100, 64, aligned, need - 1, aligned, None, None) == -4

@@ -67,7 +67,7 @@ def test_reparam_strided_chunk_views(ops, O):
 
 
 # ---------------------------------------------------------------------------------------------------- A3
-@pytest.mark.parametrize("path", [1, 2])
+@pytest.mark.parametrize("path", [1, 2, 3])
 def test_mpd_golden(ops, golden, path):
     for name, c in golden("mpd").items():
         mu, lv = cu(c["mu"]).requires_grad_(), cu(c["logvar"]).requires_grad_()
@@ -88,7 +88,7 @@ def test_mpd_partial_upstream_grads(ops, O):
     mu0, lv0 = torch.randn(21, 13), torch.randn(21, 13)
     w = torch.randn(13)
     for mode in ("S", "m", "both"):
-        for path in (1, 2):
+        for path in (1, 2, 3):
             mu, lv = cu(mu0).requires_grad_(), cu(lv0).requires_grad_()
             m_d, s = ops.mpd(mu, lv, bwd_path=path)
             f = {"S": lambda m, s_: 2.0 * s_, "m": lambda m, s_: (m * w.to(m)).sum(),
@@ -101,14 +101,15 @@ def test_mpd_partial_upstream_grads(ops, O):
             check_close(lv.grad, b.grad, what="dlv %s path %d" % (mode, path))
 
 
-def test_mpd_tile_backward_multi_chunk(ops, O):
+@pytest.mark.parametrize("path", [2, 3])
+def test_mpd_tile_backward_multi_chunk(ops, O, path):
     """D > 64 -> several K chunks per row block; B not a multiple of the tile; strided inputs."""
     torch.manual_seed(4)
     out = torch.randn(150, 2 * 70)
     g = torch.randn(70)
     o_gpu = cu(out).requires_grad_()
     mu, lv = o_gpu.chunk(2, 1)
-    m_d, s = ops.mpd(mu, lv, bwd_path=2)
+    m_d, s = ops.mpd(mu, lv, bwd_path=path)
     ((m_d * cu(g)).sum() + 0.7 * s).backward()
     o = out.double().requires_grad_()
     a, b = o.chunk(2, 1)
@@ -120,12 +121,37 @@ def test_mpd_tile_backward_multi_chunk(ops, O):
 
 
 def test_mpd_large_vs_chunked_oracle(ops, O):
+    """B > 2048: 128 x 128 forward tiles (padded batch 3072 here, 2176 = 17 x 128 for B = 2100), with and without the
+    stored KL matrices."""
     from mae_b200 import synth
-    mu, lv = synth.posterior_params(3000, (32,), seed=11)
-    m_ref, s_ref = O.post_kl_chunked(mu, lv, rows_per_chunk=100)
-    m_d, s = ops.mpd(cu(mu), cu(lv))
-    check_close(m_d, m_ref, what="m_d B=3000")
-    check_close(s, s_ref, what="S B=3000")
+    for b, seed in ((3000, 11), (2100, 15)):
+        mu, lv = synth.posterior_params(b, (32,), seed=seed)
+        m_ref, s_ref = O.post_kl_chunked(mu, lv, rows_per_chunk=100)
+        m_d, s = ops.mpd(cu(mu), cu(lv))
+        check_close(m_d, m_ref, what="m_d B=%d" % b)
+        check_close(s, s_ref, what="S B=%d" % b)
+        m_g, s_g = ops.mpd(cu(mu).requires_grad_(), cu(lv).requires_grad_())     # keeps KL / KL^T (path 3)
+        assert torch.equal(m_g, m_d) and torch.equal(s_g, s)
+
+
+def test_mpd_large_backward_vs_chunked_oracle(ops, O):
+    """B = 2100 > 2048: the automatic choice is the stored-KL tile backward (path 3); checked against autograd through
+    the row-chunked fp64 oracle, and against the recompute path."""
+    from mae_b200 import synth
+    b, d = 2100, 12
+    mu0, lv0 = synth.posterior_params(b, (d,), seed=16)
+    a, c = mu0.double().requires_grad_(), lv0.double().requires_grad_()
+    m_ref, s_ref = O.post_kl_chunked(a, c, rows_per_chunk=100)
+    (-0.7 * torch.nn.functional.logsigmoid(m_ref).sum() + 1.3 * s_ref).backward()
+    g = {}
+    for path in (0, 2):
+        mu, lv = cu(mu0).requires_grad_(), cu(lv0).requires_grad_()
+        m_d, s = ops.mpd(mu, lv, bwd_path=path)
+        (-0.7 * torch.nn.functional.logsigmoid(m_d).sum() + 1.3 * s).backward()
+        check_close(mu.grad, a.grad, what="dmu B=2100 path %d" % path)
+        check_close(lv.grad, c.grad, what="dlv B=2100 path %d" % path)
+        g[path] = (mu.grad, lv.grad)
+    assert ops._mpd_pick_path(b, d, 0) == 3
 
 
 def test_mpd_row_blocks_add_up_and_deterministic(ops):
@@ -165,7 +191,7 @@ def test_mpd_full_size_properties(ops):
 
 def test_mpd_backward_translation_property_tile_path(ops):
     from mae_b200 import synth
-    mu, lv = synth.posterior_params(2500, (64,), seed=14)   # > 2048 -> recompute-tile path automatically
+    mu, lv = synth.posterior_params(2500, (64,), seed=14)   # > 2048 -> stored-KL tile path automatically
     mu, lv = cu(mu).requires_grad_(), cu(lv).requires_grad_()
     m_d, s = ops.mpd(mu, lv)
     (torch.nn.functional.logsigmoid(m_d).sum() * -1.0 + s).backward()
@@ -174,13 +200,15 @@ def test_mpd_backward_translation_property_tile_path(ops):
     # and the two backward paths agree on a sub-problem that both can run
     mu_s, lv_s = mu.detach()[:700].clone().requires_grad_(), lv.detach()[:700].clone().requires_grad_()
     g = {}
-    for path in (1, 2):
+    for path in (1, 2, 3):
         mu_s.grad = lv_s.grad = None
         m_d, s = ops.mpd(mu_s, lv_s, bwd_path=path)
         (torch.nn.functional.logsigmoid(m_d).sum() * -1.0 + s).backward()
         g[path] = (mu_s.grad.clone(), lv_s.grad.clone())
     check_close(g[2][0], g[1][0].double(), rel=2e-5, what="dmu path2 vs path1")
     check_close(g[2][1], g[1][1].double(), rel=2e-5, what="dlv path2 vs path1")
+    check_close(g[3][0], g[1][0].double(), rel=2e-5, what="dmu path3 vs path1")
+    check_close(g[3][1], g[1][1].double(), rel=2e-5, what="dlv path3 vs path1")
 
 
 def test_mpd_rejects_batch_of_one(ops):
