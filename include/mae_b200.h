@@ -77,8 +77,10 @@ int mae_reparam_kl_bwd(const float* mu, int64_t mu_stride, const float* logvar, 
  *   S     = sqrt( sum_{i!=j} (KL_ij - m)^2 / (B(B-1) - 1) ),   m = sum_d m_d
  *   (this is what the Eye*mean fill, unbiased .std() and the cc/dd factors at :181-187 reduce to.)
  *
- * The B x B matrix is never formed by the large path: tiles of 2*KL_ij = x~_i . y~_j + c_j - l_i - D with
- * x~ = [v+mu^2, mu], y~ = [r, -2 mu r] (K = 2D) are produced in shared memory / registers.
+ * The [B,B,D] tensor is never formed: tiles of 2*KL_ij = x~_i . y~_j + E_i + F_j (K = 2D contraction in FP32 FFMA) are
+ * produced in shared memory / registers from pivoted per-element quantities (pivots mu_bar, l_bar per latent dim;
+ * x~ = [a + mc^2/v_bar, mc], y~ = [b, -2 mc r], a = expm1(lv - l_bar), b = v_bar r - 1, mc = mu - mu_bar), which keep full
+ * relative precision when the posteriors coincide (posterior collapse), where the textbook form cancels.
  *
  * mae_mpd_prepare : O(B*D) pre-pass over ALL B posteriors (after an all-gather in multi-GPU runs):
  *                   packed panels, per-dimension column statistics, m_d (written to m_d[D]) and m.  If kl is
@@ -117,6 +119,19 @@ int mae_mpd_bwd(const float* mu, int64_t mu_stride, const float* logvar, int64_t
                 int64_t row0, int64_t nrows,
                 const float* g_m, const float* g_S, const float* S, const float* gkl,
                 float* dmu, float* dlogvar, int accumulate, int path, mae_stream_t stream);
+
+/* Training-sized batches (B <= 128, D <= 64: MNIST / OMNIGLOT / CIFAR heads): the whole encoder-side regulariser
+ *     reg = clamp(kl_weight * sum_b KL_b, min = free_bits) - eta * sum_d logsigmoid(m_d) + gamma * S
+ * (mae.py:132-139; KL_b gaussian_encoder.py:219; m_d, S gaussian_encoder.py:162-188) forward AND backward in ONE launch of
+ * one thread-block cluster, no workspace.  Writes m_d[D], S[1], kl[B] (nullable) and, when dmu / dlogvar are non-NULL,
+ * d reg / d mu and d reg / d logvar [B,D] (dense) - multiply by d loss afterwards (mae_scale_inplace) if it is not 1.
+ * kl_weight = 1/B for the reference's KL.mean(); 0 leaves the KL term out (flows: KL is a Monte-Carlo estimate).
+ * mae_kl_mpd_loss_fused_supported: 1 if this (B, D) can take the path on the current device, else 0 (use the
+ * prepare / fwd / bwd entry points above). */
+int mae_kl_mpd_loss_fused_supported(int64_t B, int64_t D);
+int mae_kl_mpd_loss_fused(const float* mu, int64_t mu_stride, const float* logvar, int64_t logvar_stride,
+                          int64_t B, int64_t D, float eta, float gamma, float free_bits, float kl_weight,
+                          float* m_d, float* S, float* kl, float* dmu, float* dlogvar, mae_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * A4a  Bernoulli reconstruction error

@@ -24,6 +24,7 @@ SIGNATURES = {
     "mae_mpd_fwd": [_P, _I64, _I64, _I64, _I64, _I64, _I, _P, _P, _P],
     "mae_mpd_finalize": [_P, _I64, _P, _P],
     "mae_mpd_bwd": [_P, _I64, _P, _I64, _P, _I64, _I64, _I64, _I64, _I64, _P, _P, _P, _P, _P, _P, _I, _I, _P],
+    "mae_kl_mpd_loss_fused": [_P, _I64, _P, _I64, _I64, _I64, _F, _F, _F, _F, _P, _P, _P, _P, _P, _P],
     "mae_bernoulli_fwd": [_P, _P, _I64, _I64, _I64, _P, _P],
     "mae_bernoulli_bwd": [_P, _P, _P, _I64, _F, _I64, _I64, _I64, _P, _P],
     "mae_dmol_fwd": [_P, _P, _I64, _I64, _I64, _I64, _P, _P, _I64, _P],
@@ -51,6 +52,7 @@ PLAIN = {
     "mae_strerror": (c_char_p, [c_int]),
     "mae_device_info": (c_int, [_P, _P, _P]),
     "mae_mpd_workspace_bytes": (c_int64, [_I64, _I64, _I]),
+    "mae_kl_mpd_loss_fused_supported": (c_int, [_I64, _I64]),
     "mae_dmol_workspace_bytes": (c_int64, [_I64, _I64]),
     "mae_iw_nll_workspace_bytes": (c_int64, [_I64, _I64]),
     "mae_comm_buffer_bytes": (c_int64, [_I64, _I64]),

@@ -51,11 +51,20 @@ class MAE(nn.Module):
             # decoder), likelihood+objective.
             mu, logvar = enc.core(x)
             eps = enc._draw_eps(mu, nsamples)
-            z, _ = ops.reparam_kl(mu, logvar, eps, want_kl=False)
-            KL, m_d, S = ops.kl_mpd(mu, logvar, side_stream=True)
-            dec_out = dec.likelihood_input(x, z.view(z.size(0), z.size(1), *z_shape_dec))
-            loss, stats, recon = ops.loss_tail(dec_out, x, KL, m_d, S, dec.likelihood_kind, nsamples,
-                                               getattr(dec, "nmix", 0), eta, gamma, free_bits)   # joins the side stream
+            if mu.size(0) >= 2 and ops.fused_reg_supported(mu.size(0), mu[0].numel(), mu.device):
+                # training-sized batch: KL + MPD forward AND backward in one launch on the side stream, beside the
+                # reparameterisation and the decoder; the whole head behind the decoder is one autograd node
+                reg = ops.kl_mpd_reg_launch(mu, logvar, eta, gamma, free_bits)
+                z, _ = ops.reparam_kl(mu, logvar, eps, want_kl=False)
+                dec_out = dec.likelihood_input(x, z.view(z.size(0), z.size(1), *z_shape_dec))
+                loss, stats, recon, KL, m_d, S = ops.loss_head(dec_out, x, mu, logvar, dec.likelihood_kind, nsamples,
+                                                               getattr(dec, "nmix", 0), eta, gamma, free_bits, reg=reg)
+            else:
+                z, _ = ops.reparam_kl(mu, logvar, eps, want_kl=False)
+                KL, m_d, S = ops.kl_mpd(mu, logvar, side_stream=True)
+                dec_out = dec.likelihood_input(x, z.view(z.size(0), z.size(1), *z_shape_dec))
+                loss, stats, recon = ops.loss_tail(dec_out, x, KL, m_d, S, dec.likelihood_kind, nsamples,
+                                                   getattr(dec, "nmix", 0), eta, gamma, free_bits)   # joins the side stream
         else:
             if isinstance(enc, GaussianEncoder):
                 z, KL, (m_d, S) = enc.encode(x, nsamples, _side_stream=True)   # MPD overlaps with the decoder

@@ -16,7 +16,7 @@ from . import _lib
 
 __all__ = [
     "reparam_kl", "mpd", "mpd_forward_only", "bernoulli_recon_error", "dmol_recon_error", "log_prob_prior",
-    "log_prob_posterior", "iw_nll", "assemble_loss", "kl_mpd", "loss_tail", "join_side", "launch_count", "reset_launch_count",
+    "log_prob_posterior", "iw_nll", "assemble_loss", "kl_mpd", "loss_tail", "loss_head", "kl_mpd_reg_fused", "kl_mpd_reg_launch", "fused_reg_supported", "join_side", "launch_count", "reset_launch_count",
 ]
 
 _launches = 0  # number of kernels of ours enqueued since the last reset (bench.py reports it)
@@ -650,6 +650,74 @@ class _Assemble(torch.autograd.Function):
         return derr, dkl, (dm.view(m_shape) if dm is not None else None), ds, None, None, None, None, None
 
 
+def _likelihood_fwd(dec_out, x, kind, ns, nmix, inv_batch, need_grad):
+    """Likelihood kernel of the fused loss nodes on the current stream.  Returns (out_c, x_c, err, err_chunks,
+    fused_grad, geom); ``fused_grad`` is (1/(B ns)) d err / d dec_out when the one-pass forward+backward DMOL kernel ran."""
+    lib = _lib_()
+    dev = dec_out.device
+    b = x.size(0)
+    out_c = dec_out.contiguous()
+    fused_grad = None
+    if kind == "dmol":
+        hw = out_c[0, 0].numel()
+        if out_c.size(1) != 10 * nmix or out_c.size(0) != b * ns or x.size(1) != 3 or x[0, 0].numel() != hw:
+            raise RuntimeError("dmol: raw %s / x %s inconsistent with ns=%d nmix=%d" % (tuple(out_c.shape), tuple(x.shape), ns, nmix))
+        x_c = x.contiguous()
+        err_chunks = 1
+        if need_grad and nmix == 10 and hw in (1024, 4096):
+            # training: one pass produces the per-CTA partial sums of err AND (1/(B ns)) d err/d raw; the objective
+            # kernel adds the partials, the backward only applies d loss
+            err_chunks = int(lib.mae_dmol_err_chunks(b, ns, nmix, hw))
+            err = torch.empty(b, ns, err_chunks, device=dev, dtype=torch.float32)
+            fused_grad = torch.empty_like(out_c)
+            gmul = (inv_batch if inv_batch > 0.0 else 1.0 / float(b)) / float(ns)
+            _lib.check(lib.mae_dmol_fwd_bwd(out_c.data_ptr(), x_c.data_ptr(), gmul, b, ns, nmix, hw, err.data_ptr(),
+                                            fused_grad.data_ptr(), _stream()), "mae_dmol_fwd_bwd")
+        else:
+            ws = _pool.take(max(int(lib.mae_dmol_workspace_bytes(b * ns, hw)), 256), dev)
+            err = torch.empty(b, ns, device=dev, dtype=torch.float32)
+            _lib.check(lib.mae_dmol_fwd(out_c.data_ptr(), x_c.data_ptr(), b, ns, nmix, hw, err.data_ptr(), ws.data_ptr(),
+                                        ws.numel(), _stream()), "mae_dmol_fwd")
+            _pool.give(ws)
+        geom = (hw,)
+    else:
+        out_c = out_c.reshape(b, ns, -1)
+        p = out_c.size(2)
+        x_c = x.reshape(b, -1).contiguous()
+        if x_c.size(1) != p:
+            raise RuntimeError("x has %d pixels per image, probabilities have %d" % (x_c.size(1), p))
+        err = torch.empty(b, ns, device=dev, dtype=torch.float32)
+        err_chunks = 1
+        _lib.check(lib.mae_bernoulli_fwd(out_c.data_ptr(), x_c.data_ptr(), b, ns, p, err.data_ptr(), _stream()),
+                   "mae_bernoulli_fwd")
+        geom = (p,)
+    _count()
+    return out_c, x_c, err, err_chunks, fused_grad, geom
+
+
+def _likelihood_bwd(ctx, out_c, x_c, gloss, kind, b, ns, nmix, geom, inv_batch, out_shape):
+    """d loss / d dec_out on the current stream (gloss: device scalar d loss)."""
+    lib = _lib_()
+    if ctx.fused_grad is not None:
+        if ctx.fused_grad is False:
+            raise RuntimeError("fused loss node: the likelihood gradient was already consumed (retain_graph with a second "
+                               "backward is not supported on this path)")
+        dout = ctx.fused_grad
+        ctx.fused_grad = False
+        _lib.check(lib.mae_scale_inplace(dout.data_ptr(), dout.numel(), gloss.data_ptr(), _stream()), "mae_scale_inplace")
+    else:
+        dout = torch.empty_like(out_c)
+        gmul = (inv_batch if inv_batch > 0.0 else 1.0 / float(b)) / float(ns)
+        if kind == "dmol":
+            _lib.check(lib.mae_dmol_bwd(out_c.data_ptr(), x_c.data_ptr(), gloss.data_ptr(), 0, gmul, b, ns, nmix, geom[0],
+                                        dout.data_ptr(), _stream()), "mae_dmol_bwd")
+        else:
+            _lib.check(lib.mae_bernoulli_bwd(out_c.data_ptr(), x_c.data_ptr(), gloss.data_ptr(), 0, gmul, b, ns, geom[0],
+                                             dout.data_ptr(), _stream()), "mae_bernoulli_bwd")
+    _count()
+    return dout.view(out_shape)
+
+
 class _LossTail(torch.autograd.Function):
     """likelihood + objective assembly as ONE autograd node (the part of MAE.loss after the decoder):
     forward = likelihood kernel, join of the MPD side stream, assembly kernel; backward = likelihood backward on the
@@ -668,41 +736,8 @@ class _LossTail(torch.autograd.Function):
         dev = dec_out.device
         idx = dev.index if dev.index is not None else torch.cuda.current_device()
         b = x.size(0)
-        out_c = dec_out.contiguous()
-        fused_grad = None
-        if kind == "dmol":
-            hw = out_c[0, 0].numel()
-            if out_c.size(1) != 10 * nmix or out_c.size(0) != b * ns or x.size(1) != 3 or x[0, 0].numel() != hw:
-                raise RuntimeError("dmol: raw %s / x %s inconsistent with ns=%d nmix=%d" % (tuple(out_c.shape), tuple(x.shape), ns, nmix))
-            x_c = x.contiguous()
-            err_chunks = 1
-            if ctx.needs_input_grad[0] and nmix == 10 and hw in (1024, 4096):
-                # training: one pass produces the per-CTA partial sums of err AND (1/(B ns)) d err/d raw; the objective
-                # kernel adds the partials, the backward only applies d loss
-                err_chunks = int(lib.mae_dmol_err_chunks(b, ns, nmix, hw))
-                err = torch.empty(b, ns, err_chunks, device=dev, dtype=torch.float32)
-                fused_grad = torch.empty_like(out_c)
-                gmul = (inv_batch if inv_batch > 0.0 else 1.0 / float(b)) / float(ns)
-                _lib.check(lib.mae_dmol_fwd_bwd(out_c.data_ptr(), x_c.data_ptr(), gmul, b, ns, nmix, hw, err.data_ptr(),
-                                                fused_grad.data_ptr(), _stream()), "mae_dmol_fwd_bwd")
-            else:
-                ws = _pool.take(max(int(lib.mae_dmol_workspace_bytes(b * ns, hw)), 256), dev)
-                err = torch.empty(b, ns, device=dev, dtype=torch.float32)
-                _lib.check(lib.mae_dmol_fwd(out_c.data_ptr(), x_c.data_ptr(), b, ns, nmix, hw, err.data_ptr(), ws.data_ptr(),
-                                            ws.numel(), _stream()), "mae_dmol_fwd")
-                _pool.give(ws)
-            geom = (hw,)
-        else:
-            out_c = out_c.reshape(b, ns, -1)
-            p = out_c.size(2)
-            x_c = x.reshape(b, -1).contiguous()
-            if x_c.size(1) != p:
-                raise RuntimeError("x has %d pixels per image, probabilities have %d" % (x_c.size(1), p))
-            err = torch.empty(b, ns, device=dev, dtype=torch.float32)
-            err_chunks = 1
-            _lib.check(lib.mae_bernoulli_fwd(out_c.data_ptr(), x_c.data_ptr(), b, ns, p, err.data_ptr(), _stream()),
-                       "mae_bernoulli_fwd")
-            geom = (p,)
+        out_c, x_c, err, err_chunks, fused_grad, geom = _likelihood_fwd(dec_out, x, kind, ns, nmix, inv_batch,
+                                                                         ctx.needs_input_grad[0])
         kl_c = (kl_all if kl_all is not None else kl).contiguous()   # sharded runs sum the all-gathered KL vector
         kl_count = kl_c.numel() if kl_all is not None else 0
         m_c = m_d.contiguous().view(-1) if m_d is not None else None
@@ -729,7 +764,7 @@ class _LossTail(torch.autograd.Function):
         else:
             join_side(dev)
             assemble()
-        _count(2)
+        _count()
         ctx.save_for_backward(out_c, x_c, scalars, m_c if m_c is not None else scalars)
         ctx.fused_grad = fused_grad
         ctx.meta = (kind, b, ns, nmix, geom, d, eta, gamma, free_bits, inv_batch, dec_out.shape,
@@ -758,26 +793,8 @@ class _LossTail(torch.autograd.Function):
         else:
             ss.wait_stream(cs)                  # d loss is ready on the main stream
         dout = None
-        if ctx.needs_input_grad[0] and ctx.fused_grad is not None:
-            if ctx.fused_grad is False:
-                raise RuntimeError("loss_tail: the fused likelihood gradient was already consumed (retain_graph with a second "
-                                   "backward is not supported on this path)")
-            dout = ctx.fused_grad
-            ctx.fused_grad = False
-            _lib.check(lib.mae_scale_inplace(dout.data_ptr(), dout.numel(), gloss.data_ptr(), _stream()), "mae_scale_inplace")
-            _count()
-            dout = dout.view(out_shape)
-        elif ctx.needs_input_grad[0]:
-            dout = torch.empty_like(out_c)
-            gmul = (inv_batch if inv_batch > 0.0 else 1.0 / float(b)) / float(ns)
-            if kind == "dmol":
-                _lib.check(lib.mae_dmol_bwd(out_c.data_ptr(), x_c.data_ptr(), gloss.data_ptr(), 0, gmul, b, ns, nmix, geom[0],
-                                            dout.data_ptr(), _stream()), "mae_dmol_bwd")
-            else:
-                _lib.check(lib.mae_bernoulli_bwd(out_c.data_ptr(), x_c.data_ptr(), gloss.data_ptr(), 0, gmul, b, ns, geom[0],
-                                                 dout.data_ptr(), _stream()), "mae_bernoulli_bwd")
-            _count()
-            dout = dout.view(out_shape)
+        if ctx.needs_input_grad[0]:
+            dout = _likelihood_bwd(ctx, out_c, x_c, gloss, kind, b, ns, nmix, geom, inv_batch, out_shape)
         dkl = torch.empty(b, device=dev, dtype=torch.float32)
         dm = torch.empty(d, device=dev, dtype=torch.float32) if m_shape is not None else None
         ds = torch.empty((), device=dev, dtype=torch.float32) if has_s else None
@@ -810,6 +827,167 @@ def loss_tail(dec_out: torch.Tensor, x: torch.Tensor, kl: torch.Tensor, m_d: Opt
         raise ValueError("kind must be 'dmol' or 'bernoulli'")
     return _LossTail.apply(dec_out, x, kl, m_d, s, ext_sums, kl_all, kind, int(ns), int(nmix), float(eta), float(gamma),
                            float(free_bits), float(inv_batch), bool(defer_join))
+
+
+_fused_reg_ok: Dict[Tuple[int, int, int], bool] = {}
+
+
+def fused_reg_supported(b: int, d: int, device: torch.device) -> bool:
+    """True when (B, D) can take the one-launch KL + MPD forward/backward (mae_kl_mpd_loss_fused) on this device."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    key = (idx, int(b), int(d))
+    ok = _fused_reg_ok.get(key)
+    if ok is None:
+        with torch.cuda.device(idx):
+            ok = bool(_lib_().mae_kl_mpd_loss_fused_supported(int(b), int(d)))
+        _fused_reg_ok[key] = ok
+    return ok
+
+
+def kl_mpd_reg_fused(mu: torch.Tensor, logvar: torch.Tensor, eta: float, gamma: float, free_bits: float,
+                     kl_weight: Optional[float] = None, want_grad: bool = True, launch_stream=None):
+    """Raw (non-autograd) call of the one-launch regulariser kernel on the current stream (or on ``launch_stream``, which
+    must already be ordered after the producers of mu / logvar; the outputs stay owned by the current stream).
+
+    Returns (kl [B], m_d [*z], S [], grads) with grads = [2,B,D] holding d reg / d mu and d reg / d logvar of
+    reg = clamp(kl_weight * sum KL, min=free_bits) - eta * sum logsigmoid(m_d) + gamma * S   (mae.py:132-139),
+    or None when ``want_grad`` is False.  ``kl_weight`` defaults to 1/B (KL.mean())."""
+    _req_cuda(mu, logvar)
+    mu2, ms = _rows(mu)
+    lv2, ls = _rows(logvar)
+    b, d = mu2.shape
+    dev = mu2.device
+    if not fused_reg_supported(b, d, dev):
+        raise RuntimeError("kl_mpd_reg_fused: B=%d, D=%d is outside the fused path (B <= 128, D <= 64)" % (b, d))
+    kw = 1.0 / float(b) if kl_weight is None else float(kl_weight)
+    m_d = torch.empty(d, device=dev, dtype=torch.float32)
+    s_ = torch.empty((), device=dev, dtype=torch.float32)
+    kl = torch.empty(b, device=dev, dtype=torch.float32)
+    grads = torch.empty(2, b, d, device=dev, dtype=torch.float32) if want_grad else None
+    with torch.cuda.stream(launch_stream if launch_stream is not None else torch.cuda.current_stream(dev)):
+        _lib.check(_lib_().mae_kl_mpd_loss_fused(mu2.data_ptr(), ms, lv2.data_ptr(), ls, b, d, float(eta), float(gamma),
+                                                 float(free_bits), kw, m_d.data_ptr(), s_.data_ptr(), kl.data_ptr(),
+                                                 grads[0].data_ptr() if want_grad else None,
+                                                 grads[1].data_ptr() if want_grad else None, _stream()),
+                   "mae_kl_mpd_loss_fused")
+    _count()
+    return kl, m_d.view(mu.shape[1:]), s_, grads, (mu2, lv2)
+
+
+class RegLaunch:
+    """Results of :func:`kl_mpd_reg_launch` still in flight on the side stream (consumed by :func:`loss_head`)."""
+
+    def __init__(self, kl, m_d, s, grads, keep, params):
+        self.kl, self.m_d, self.s, self.grads, self.keep, self.params = kl, m_d, s, grads, keep, params
+
+
+def kl_mpd_reg_launch(mu: torch.Tensor, logvar: torch.Tensor, eta: float, gamma: float, free_bits: float) -> RegLaunch:
+    """Start the one-launch regulariser kernel on the side stream as soon as mu / logvar exist, so that it overlaps with
+    everything the main stream does next (reparameterisation, decoder); pass the result to :func:`loss_head`."""
+    dev = mu.device
+    cs, ss = torch.cuda.current_stream(dev), _side_stream(dev)
+    ss.wait_stream(cs)
+    want_grad = torch.is_grad_enabled() and (mu.requires_grad or logvar.requires_grad)
+    kl, m_d, s, grads, keep = kl_mpd_reg_fused(mu.detach(), logvar.detach(), eta, gamma, free_bits, None, want_grad,
+                                               launch_stream=ss)
+    return RegLaunch(kl, m_d, s, grads, keep, (float(eta), float(gamma), float(free_bits)))
+
+
+class _LossHead(torch.autograd.Function):
+    """The whole loss head behind the decoder as ONE autograd node for training-sized batches:
+    (decoder output, x, mu, logvar) -> objective of MAE.loss (mae.py:100-140).
+
+    forward  main stream: likelihood kernel (for the DMOL head the one-pass forward+backward kernel);
+             side stream: mae_kl_mpd_loss_fused = KL, MPD and d regulariser / d(mu, logvar) in one launch, then the
+             assembly kernel once the likelihood's partial sums exist.
+    backward nothing but two conditional rescales by d loss (no-ops when it is 1, the usual ``loss.backward()``).
+    ``defer``: see _LossTail."""
+
+    @staticmethod
+    def forward(ctx, dec_out, x, mu, logvar, reg, kind, ns, nmix, eta, gamma, free_bits, defer):
+        ctx.set_materialize_grads(False)
+        _req_cuda(dec_out, x, mu, logvar)
+        lib = _lib_()
+        dev = dec_out.device
+        idx = dev.index if dev.index is not None else torch.cuda.current_device()
+        b = x.size(0)
+        want_grad = ctx.needs_input_grad[2] or ctx.needs_input_grad[3]
+        cs, ss = torch.cuda.current_stream(dev), _side_stream(dev)
+        prev = _pending_join.pop(idx, None)
+        if reg is not None:
+            if reg.params != (eta, gamma, free_bits) or (want_grad and reg.grads is None):
+                raise RuntimeError("loss_head: the RegLaunch was started with different eta / gamma / free_bits or without "
+                                   "gradients")
+            kl, m_d, s, grads, keep = reg.kl, reg.m_d, reg.s, (reg.grads if want_grad else None), reg.keep
+        else:
+            ss.wait_stream(cs)
+            kl, m_d, s, grads, keep = kl_mpd_reg_fused(mu, logvar, eta, gamma, free_bits, None, want_grad, launch_stream=ss)
+        out_c, x_c, err, err_chunks, fused_grad, geom = _likelihood_fwd(dec_out, x, kind, ns, nmix, 0.0,
+                                                                         ctx.needs_input_grad[0])
+        m_c = m_d.reshape(-1)
+        d = m_c.numel()
+        scalars = torch.empty(6, device=dev, dtype=torch.float32)
+        recon = torch.empty(b, device=dev, dtype=torch.float32)
+        ev_err = torch.cuda.Event()
+        ev_err.record(cs)
+        with torch.cuda.stream(ss):
+            ss.wait_event(ev_err)
+            _lib.check(lib.mae_loss_assemble_fwd(err.data_ptr(), kl.data_ptr(), m_c.data_ptr(), s.data_ptr(), None, b, ns, d,
+                                                 0, err_chunks, eta, gamma, free_bits, 0.0, scalars.data_ptr(),
+                                                 recon.data_ptr(), _stream()), "mae_loss_assemble_fwd")
+            _count()
+            ev = torch.cuda.Event()
+            ev.record(ss)
+        _pending_join[idx] = (ev, (prev, err, kl, m_c, s, scalars, recon, grads, keep))
+        if not defer:
+            join_side(dev)
+        ctx.save_for_backward(out_c, x_c)
+        ctx.fused_grad = fused_grad
+        ctx.reg_grads = grads
+        ctx.meta = (kind, b, ns, nmix, geom, dec_out.shape, mu.shape, logvar.shape, defer)
+        loss, stats = scalars[0], scalars[1:]
+        ctx.mark_non_differentiable(stats, recon, kl, m_d, s)
+        return loss, stats, recon, kl, m_d, s
+
+    @staticmethod
+    def backward(ctx, gloss, *_unused):
+        if gloss is None:
+            return (None,) * 12
+        out_c, x_c = ctx.saved_tensors
+        kind, b, ns, nmix, geom, out_shape, mu_shape, lv_shape, defer = ctx.meta
+        dev = out_c.device
+        gloss = gloss.contiguous()
+        dout = None
+        if ctx.needs_input_grad[0]:
+            dout = _likelihood_bwd(ctx, out_c, x_c, gloss, kind, b, ns, nmix, geom, 0.0, out_shape)
+        dmu = dlv = None
+        if ctx.reg_grads is not None:
+            if ctx.reg_grads is False:
+                raise RuntimeError("fused loss node: a second backward through the same graph is not supported")
+            grads = ctx.reg_grads
+            ctx.reg_grads = False
+            join_side(dev)                      # the regulariser kernel ran on the side stream
+            _lib.check(_lib_().mae_scale_inplace(grads.data_ptr(), grads.numel(), gloss.data_ptr(), _stream()),
+                       "mae_scale_inplace")
+            _count()
+            dmu, dlv = grads[0].view(mu_shape), grads[1].view(lv_shape)
+        elif defer:
+            join_side(dev)
+        return dout, None, dmu, dlv, None, None, None, None, None, None, None, None
+
+
+def loss_head(dec_out: torch.Tensor, x: torch.Tensor, mu: torch.Tensor, logvar: torch.Tensor, kind: str, ns: int,
+              nmix: int = 10, eta: float = 0.0, gamma: float = 0.0, free_bits: float = 0.0, defer_join: bool = False,
+              reg: Optional[RegLaunch] = None):
+    """Decoder output + posterior parameters -> objective of MAE.loss in one autograd node (analytic KL, single process,
+    training-sized batch: see :func:`fused_reg_supported`).  Returns (loss [], stats [5], recon [B], KL [B], m_d, S); only
+    ``loss`` carries a gradient.  ``reg``: a :func:`kl_mpd_reg_launch` started earlier for the same mu / logvar (so the
+    regulariser overlaps with the decoder); without it the kernel is launched here.  Everything else as :func:`loss_tail`.
+    Reference: mae.py:100-140 with gaussian_encoder.py:162-188, :219 and the two reconstruct_error heads."""
+    if kind not in ("dmol", "bernoulli"):
+        raise ValueError("kind must be 'dmol' or 'bernoulli'")
+    return _LossHead.apply(dec_out, x, mu, logvar, reg, kind, int(ns), int(nmix), float(eta), float(gamma), float(free_bits),
+                           bool(defer_join))
 
 
 def assemble_loss(err: torch.Tensor, kl: torch.Tensor, m_d: Optional[torch.Tensor], s: Optional[torch.Tensor],

@@ -387,13 +387,82 @@ def test_kl_mpd_fused_node(ops, O):
         check_close(s, sr, what="S b=%d" % b)
 
 
+def _reg_reference(O, mu0, lv0, eta, gamma, free_bits):
+    """fp64 oracle of the encoder-side regulariser of mae.py:132-139 and its gradient."""
+    a, c = mu0.double().requires_grad_(), lv0.double().requires_grad_()
+    kl = O.analytic_kl(a, c)
+    m_d, s = O.post_kl(a, c)
+    reg = kl.mean().clamp(min=free_bits)
+    if eta > 0:
+        reg = reg - eta * torch.nn.functional.logsigmoid(m_d).sum()
+    if gamma > 0:
+        reg = reg + gamma * s
+    reg.backward()
+    return kl.detach(), m_d.detach(), s.detach(), a.grad, c.grad
+
+
+@pytest.mark.parametrize("b,d", [(2, 1), (5, 3), (8, 64), (9, 7), (21, 13), (64, 64), (65, 33), (100, 32), (100, 64), (128, 64)])
+def test_fused_regulariser_kernel_vs_oracle(ops, O, b, d):
+    """mae_kl_mpd_loss_fused (one cluster launch: KL, m_d, S and d reg / d(mu, logvar)) against the fp64 oracle, for every
+    cluster size 1..16, ragged last CTA, D below / at the 64-dim limit, and the eta / gamma / free-bits switches."""
+    from mae_b200 import synth
+    mu0, lv0 = synth.posterior_params(b, (d,), seed=100 + b, clamp=True)
+    assert ops.fused_reg_supported(b, d, DEV)
+    klm = float(O.analytic_kl(mu0.double(), lv0.double()).mean())
+    for eta, gamma, fb in ((1.0, 1.0, 0.0), (0.0, 2.0, 0.0), (0.7, 0.0, 0.0), (1.0, 1.0, 2.0 * klm + 1.0)):
+        kl, m_d, s, grads, _ = ops.kl_mpd_reg_fused(cu(mu0), cu(lv0), eta, gamma, fb)
+        klr, mr, sr, gmu, glv = _reg_reference(O, mu0, lv0, eta, gamma, fb)
+        tag = "B=%d D=%d eta=%g gamma=%g fb=%g" % (b, d, eta, gamma, fb)
+        check_close(kl, klr, what="KL " + tag)
+        check_close(m_d, mr, what="m_d " + tag)
+        check_close(s, sr, what="S " + tag)
+        check_close(grads[0], gmu, what="dmu " + tag, floor=1e-12)
+        check_close(grads[1], glv, what="dlv " + tag, floor=1e-12)
+    # forward only (evaluation): same values, no gradient buffers
+    kl2, m2, s2, g2, _ = ops.kl_mpd_reg_fused(cu(mu0), cu(lv0), 1.0, 1.0, 0.0, want_grad=False)
+    assert g2 is None
+    kl1, m1, s1, _, _ = ops.kl_mpd_reg_fused(cu(mu0), cu(lv0), 1.0, 1.0, 0.0)
+    assert torch.equal(kl1, kl2) and torch.equal(m1, m2) and torch.equal(s1, s2)   # deterministic
+
+
+def test_fused_regulariser_goldens_and_strided_views(ops, O, golden):
+    """the reference's own _postKL goldens (incl. the posterior-collapse regime) through the fused kernel, fed with the
+    strided chunk views an encoder core returns"""
+    n = 0
+    for name, c in golden("mpd").items():
+        b, d = c["mu"].size(0), c["mu"][0].numel()
+        if b > 128 or d > 64:
+            continue
+        n += 1
+        packed = cu(torch.cat([c["mu"].reshape(b, d), c["logvar"].reshape(b, d)], dim=1))
+        mu, lv = packed.chunk(2, 1)
+        eta, gamma = float(c["eta"]), float(c["gamma"])
+        kl, m_d, s, grads, _ = ops.kl_mpd_reg_fused(mu, lv, eta, gamma, 0.0, kl_weight=0.0)
+        r64, r32 = c["ref64"], c["ref32"]
+        check_close(m_d, r64["m_d"].reshape(-1), r32["m_d"].reshape(-1), what="%s m_d" % name)
+        check_close(s, r64["S"], r32["S"], what="%s S" % name)
+        check_close(grads[0], r64["dmu"].reshape(b, d), r32["dmu"].reshape(b, d) if "dmu" in r32 else None, what="%s dmu" % name)
+        check_close(grads[1], r64["dlogvar"].reshape(b, d), r32["dlogvar"].reshape(b, d) if "dlogvar" in r32 else None,
+                    what="%s dlogvar" % name)
+    assert n >= 2
+
+
+def test_fused_regulariser_rejects_large_shapes(ops):
+    assert not ops.fused_reg_supported(129, 64, DEV) and not ops.fused_reg_supported(64, 65, DEV)
+    with pytest.raises(RuntimeError, match="outside the fused path"):
+        ops.kl_mpd_reg_fused(torch.zeros(200, 8, device=DEV), torch.zeros(200, 8, device=DEV), 1.0, 1.0, 0.0)
+
+
+@pytest.mark.parametrize("one_node", [True, False])
 @pytest.mark.parametrize("defer", [False, True])
 @pytest.mark.parametrize("kind", ["dmol", "bernoulli"])
 @pytest.mark.parametrize("eta,gamma,free_bits", [(1.0, 1.0, 0.0), (0.0, 0.0, 0.0), (0.5, 2.0, 1e5)])
-def test_fused_loss_heads_vs_oracle(ops, O, kind, eta, gamma, free_bits, defer):
-    """heads.loss_head_* = reparam + KL/MPD node (side stream) + likelihood/objective node, against the oracle's
-    composition of the reference formulas, values and all gradients."""
+def test_fused_loss_heads_vs_oracle(ops, O, kind, eta, gamma, free_bits, defer, one_node, monkeypatch):
+    """heads.loss_head_*: one_node = reparam + ONE node for everything else (regulariser kernel on the side stream);
+    otherwise reparam + KL/MPD node (side stream) + likelihood/objective node.  Against the oracle's composition of the
+    reference formulas, values and all gradients."""
     from mae_b200 import heads, synth
+    monkeypatch.setattr(heads, "ONE_NODE", one_node)
     b, ns, d = 12, 2, 10
     mu0, lv0 = synth.posterior_params(b, (d,), seed=3, clamp=True)
     eps = synth.noise(b, ns, (d,), seed=3)
