@@ -67,6 +67,14 @@ int mae_reparam_kl_bwd(const float* mu, int64_t mu_stride, const float* logvar, 
                        const float* eps, const float* gz, const float* gkl,
                        int64_t B, int64_t ns, int64_t D,
                        float* dmu, float* dlogvar, int accumulate, mae_stream_t stream);
+/* Same, plus the precomputed gradient of the encoder-side regulariser (extra_dmu / extra_dlogvar [B,D] dense, written by
+ * mae_kl_mpd_loss_fused) times its upstream device scalar extra_scale[0] (NULL = 1): the whole gradient of a training
+ * step w.r.t. the encoder outputs in one launch (no separate rescale, no accumulation kernels). */
+int mae_reparam_reg_bwd(const float* mu, int64_t mu_stride, const float* logvar, int64_t logvar_stride,
+                        const float* eps, const float* gz, const float* gkl,
+                        const float* extra_dmu, const float* extra_dlogvar, const float* extra_scale,
+                        int64_t B, int64_t ns, int64_t D,
+                        float* dmu, float* dlogvar, int accumulate, mae_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * A3  mutual posterior divergence (MPD) regulariser
@@ -123,15 +131,16 @@ int mae_mpd_bwd(const float* mu, int64_t mu_stride, const float* logvar, int64_t
 /* Training-sized batches (B <= 128, D <= 64: MNIST / OMNIGLOT / CIFAR heads): the whole encoder-side regulariser
  *     reg = clamp(kl_weight * sum_b KL_b, min = free_bits) - eta * sum_d logsigmoid(m_d) + gamma * S
  * (mae.py:132-139; KL_b gaussian_encoder.py:219; m_d, S gaussian_encoder.py:162-188) forward AND backward in ONE launch of
- * one thread-block cluster, no workspace.  Writes m_d[D], S[1], kl[B] (nullable) and, when dmu / dlogvar are non-NULL,
- * d reg / d mu and d reg / d logvar [B,D] (dense) - multiply by d loss afterwards (mae_scale_inplace) if it is not 1.
+ * one thread-block cluster, no workspace.  Writes m_d[D], S[1], kl[B] (nullable), reg[1] (nullable) and, when dmu /
+ * dlogvar are non-NULL, d reg / d mu and d reg / d logvar [B,D] (dense), which mae_reparam_reg_bwd folds into the
+ * encoder-output gradient together with their upstream scalar.
  * kl_weight = 1/B for the reference's KL.mean(); 0 leaves the KL term out (flows: KL is a Monte-Carlo estimate).
  * mae_kl_mpd_loss_fused_supported: 1 if this (B, D) can take the path on the current device, else 0 (use the
  * prepare / fwd / bwd entry points above). */
 int mae_kl_mpd_loss_fused_supported(int64_t B, int64_t D);
 int mae_kl_mpd_loss_fused(const float* mu, int64_t mu_stride, const float* logvar, int64_t logvar_stride,
                           int64_t B, int64_t D, float eta, float gamma, float free_bits, float kl_weight,
-                          float* m_d, float* S, float* kl, float* dmu, float* dlogvar, mae_stream_t stream);
+                          float* m_d, float* S, float* kl, float* reg, float* dmu, float* dlogvar, mae_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * A4a  Bernoulli reconstruction error

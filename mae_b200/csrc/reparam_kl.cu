@@ -41,7 +41,9 @@ reparam_kl_fwd_kernel(const float* __restrict__ mu, int64_t mu_stride, const flo
 __global__ void __launch_bounds__(kThreads)
 reparam_kl_bwd_kernel(const float* __restrict__ mu, int64_t mu_stride, const float* __restrict__ lv, int64_t lv_stride,
                       const float* __restrict__ eps, const float* __restrict__ gz, const float* __restrict__ gkl,
-                      int B, int ns, int D, float* __restrict__ dmu, float* __restrict__ dlv, int accumulate) {
+                      int B, int ns, int D, float* __restrict__ dmu, float* __restrict__ dlv, int accumulate,
+                      const float* __restrict__ extra_dmu, const float* __restrict__ extra_dlv,
+                      const float* __restrict__ extra_scale) {
     const int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     if (t >= (int64_t)B * D) return;
     const int b = (int)(t / D), d = (int)(t % D);
@@ -60,6 +62,11 @@ reparam_kl_bwd_kernel(const float* __restrict__ mu, int64_t mu_stride, const flo
         const float gk = gkl[b];
         gm += gk * m;
         gl += 0.5f * gk * (expf(l) - 1.0f);
+    }
+    if (extra_dmu != nullptr) {   // precomputed regulariser gradient (mae_kl_mpd_loss_fused), times its upstream scalar
+        const float sc = extra_scale != nullptr ? extra_scale[0] : 1.0f;
+        gm = fmaf(sc, extra_dmu[t], gm);
+        gl = fmaf(sc, extra_dlv[t], gl);
     }
     if (accumulate) {
         dmu[t] += gm;
@@ -88,17 +95,27 @@ extern "C" int mae_reparam_kl_fwd(const float* mu, int64_t mu_stride, const floa
     return launch_status();
 }
 
-extern "C" int mae_reparam_kl_bwd(const float* mu, int64_t mu_stride, const float* logvar, int64_t logvar_stride,
-                                  const float* eps, const float* gz, const float* gkl, int64_t B, int64_t ns, int64_t D,
-                                  float* dmu, float* dlogvar, int accumulate, mae_stream_t stream) {
+extern "C" int mae_reparam_reg_bwd(const float* mu, int64_t mu_stride, const float* logvar, int64_t logvar_stride,
+                                   const float* eps, const float* gz, const float* gkl, const float* extra_dmu,
+                                   const float* extra_dlogvar, const float* extra_scale, int64_t B, int64_t ns, int64_t D,
+                                   float* dmu, float* dlogvar, int accumulate, mae_stream_t stream) {
     using namespace mae;
     MAE_REQUIRE(mu && logvar && dmu && dlogvar, MAE_ERR_NULL);
     MAE_REQUIRE(gz == nullptr || eps != nullptr, MAE_ERR_NULL);
+    MAE_REQUIRE((extra_dmu == nullptr) == (extra_dlogvar == nullptr), MAE_ERR_NULL);
     MAE_REQUIRE(B > 0 && ns > 0 && D > 0 && B < (1ll << 31) && D < (1ll << 24) && ns < (1ll << 24), MAE_ERR_SHAPE);
     MAE_REQUIRE(mu_stride >= D && logvar_stride >= D, MAE_ERR_STRIDE);
     const int64_t blocks = ceil_div(B * D, kThreads);
     MAE_REQUIRE(blocks < (1ll << 31), MAE_ERR_SHAPE);
     reparam_kl_bwd_kernel<<<(unsigned)blocks, kThreads, 0, as_stream(stream)>>>(
-        mu, mu_stride, logvar, logvar_stride, eps, gz, gkl, (int)B, (int)ns, (int)D, dmu, dlogvar, accumulate);
+        mu, mu_stride, logvar, logvar_stride, eps, gz, gkl, (int)B, (int)ns, (int)D, dmu, dlogvar, accumulate, extra_dmu,
+        extra_dlogvar, extra_scale);
     return launch_status();
+}
+
+extern "C" int mae_reparam_kl_bwd(const float* mu, int64_t mu_stride, const float* logvar, int64_t logvar_stride,
+                                  const float* eps, const float* gz, const float* gkl, int64_t B, int64_t ns, int64_t D,
+                                  float* dmu, float* dlogvar, int accumulate, mae_stream_t stream) {
+    return mae_reparam_reg_bwd(mu, mu_stride, logvar, logvar_stride, eps, gz, gkl, nullptr, nullptr, nullptr, B, ns, D, dmu,
+                               dlogvar, accumulate, stream);
 }

@@ -16,7 +16,7 @@ ONE_NODE = True   # False forces the general three-node composition (kept for ba
 
 
 def _one_node(mu: torch.Tensor) -> bool:
-    """Training-sized batch: KL + MPD forward/backward in one launch, whole head in one autograd node (ops.loss_head)."""
+    """Training-sized batch: KL + MPD forward/backward in one launch (ops.encode_head), two autograd nodes in total."""
     b = mu.size(0)
     return ONE_NODE and b >= 2 and ops.fused_reg_supported(b, mu[0].numel(), mu.device)
 
@@ -25,11 +25,10 @@ def loss_head_binary(mu, logvar, eps, probs, x, eta=0.0, gamma=0.0, free_bits=0.
     """C1/C2: reparam + analytic KL, MPD, Bernoulli likelihood, assembly.  Returns (loss, recon, KL, stats, z).
     ``defer_join``: see ops.loss_tail (outputs valid after backward() / ops.join_side())."""
     if _one_node(mu):
-        reg = ops.kl_mpd_reg_launch(mu, logvar, eta, gamma, free_bits)   # side stream: overlaps with everything below
-        z, _ = ops.reparam_kl(mu, logvar, eps, want_kl=False)
-        loss, stats, recon, kl, _, _ = ops.loss_head(probs, x, mu, logvar, "bernoulli", eps.size(1), 0, eta, gamma, free_bits,
-                                                     defer_join=defer_join, reg=reg)
-        return loss, recon, kl, stats, z
+        z, enc = ops.encode_head(mu, logvar, eps, eta, gamma, free_bits)   # regulariser on the side stream
+        loss, stats, recon = ops.loss_head(probs, x, enc, "bernoulli", eps.size(1), 0, eta, gamma, free_bits,
+                                           defer_join=defer_join)
+        return loss, recon, enc.kl, stats, z
     z, _ = ops.reparam_kl(mu, logvar, eps, want_kl=False)
     kl, m_d, s = ops.kl_mpd(mu, logvar, side_stream=True)   # overlaps with the likelihood; joined inside loss_tail
     loss, stats, recon = ops.loss_tail(probs, x, kl, m_d, s, "bernoulli", eps.size(1), 0, eta, gamma, free_bits,
@@ -41,11 +40,10 @@ def loss_head_color(mu, logvar, eps, raw, x, nmix=10, eta=0.0, gamma=0.0, free_b
     """C3: reparam + analytic KL, MPD, discretized-logistic-mixture likelihood, assembly.
     ``defer_join``: see ops.loss_tail (outputs valid after backward() / ops.join_side())."""
     if _one_node(mu):
-        reg = ops.kl_mpd_reg_launch(mu, logvar, eta, gamma, free_bits)   # side stream: overlaps with everything below
-        z, _ = ops.reparam_kl(mu, logvar, eps, want_kl=False)
-        loss, stats, recon, kl, _, _ = ops.loss_head(raw, x, mu, logvar, "dmol", eps.size(1), nmix, eta, gamma, free_bits,
-                                                     defer_join=defer_join, reg=reg)
-        return loss, recon, kl, stats, z
+        z, enc = ops.encode_head(mu, logvar, eps, eta, gamma, free_bits)   # regulariser on the side stream
+        loss, stats, recon = ops.loss_head(raw, x, enc, "dmol", eps.size(1), nmix, eta, gamma, free_bits,
+                                           defer_join=defer_join)
+        return loss, recon, enc.kl, stats, z
     z, _ = ops.reparam_kl(mu, logvar, eps, want_kl=False)
     kl, m_d, s = ops.kl_mpd(mu, logvar, side_stream=True)   # overlaps with the likelihood; joined inside loss_tail
     loss, stats, recon = ops.loss_tail(raw, x, kl, m_d, s, "dmol", eps.size(1), nmix, eta, gamma, free_bits,

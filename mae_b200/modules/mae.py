@@ -52,13 +52,13 @@ class MAE(nn.Module):
             mu, logvar = enc.core(x)
             eps = enc._draw_eps(mu, nsamples)
             if mu.size(0) >= 2 and ops.fused_reg_supported(mu.size(0), mu[0].numel(), mu.device):
-                # training-sized batch: KL + MPD forward AND backward in one launch on the side stream, beside the
-                # reparameterisation and the decoder; the whole head behind the decoder is one autograd node
-                reg = ops.kl_mpd_reg_launch(mu, logvar, eta, gamma, free_bits)
-                z, _ = ops.reparam_kl(mu, logvar, eps, want_kl=False)
+                # training-sized batch, two autograd nodes: (1) z plus KL + MPD forward AND backward in one launch on the
+                # side stream, beside the decoder; (2) likelihood + objective
+                z, eb = ops.encode_head(mu, logvar, eps, eta, gamma, free_bits)
                 dec_out = dec.likelihood_input(x, z.view(z.size(0), z.size(1), *z_shape_dec))
-                loss, stats, recon, KL, m_d, S = ops.loss_head(dec_out, x, mu, logvar, dec.likelihood_kind, nsamples,
-                                                               getattr(dec, "nmix", 0), eta, gamma, free_bits, reg=reg)
+                loss, stats, recon = ops.loss_head(dec_out, x, eb, dec.likelihood_kind, nsamples,
+                                                   getattr(dec, "nmix", 0), eta, gamma, free_bits)
+                KL, m_d, S = eb.kl, eb.m_d, eb.s
             else:
                 z, _ = ops.reparam_kl(mu, logvar, eps, want_kl=False)
                 KL, m_d, S = ops.kl_mpd(mu, logvar, side_stream=True)

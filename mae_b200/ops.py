@@ -16,7 +16,7 @@ from . import _lib
 
 __all__ = [
     "reparam_kl", "mpd", "mpd_forward_only", "bernoulli_recon_error", "dmol_recon_error", "log_prob_prior",
-    "log_prob_posterior", "iw_nll", "assemble_loss", "kl_mpd", "loss_tail", "loss_head", "kl_mpd_reg_fused", "kl_mpd_reg_launch", "fused_reg_supported", "join_side", "launch_count", "reset_launch_count",
+    "log_prob_posterior", "iw_nll", "assemble_loss", "kl_mpd", "loss_tail", "loss_head", "encode_head", "kl_mpd_reg_fused", "fused_reg_supported", "join_side", "launch_count", "reset_launch_count",
 ]
 
 _launches = 0  # number of kernels of ours enqueued since the last reset (bench.py reports it)
@@ -849,9 +849,10 @@ def kl_mpd_reg_fused(mu: torch.Tensor, logvar: torch.Tensor, eta: float, gamma: 
     """Raw (non-autograd) call of the one-launch regulariser kernel on the current stream (or on ``launch_stream``, which
     must already be ordered after the producers of mu / logvar; the outputs stay owned by the current stream).
 
-    Returns (kl [B], m_d [*z], S [], grads) with grads = [2,B,D] holding d reg / d mu and d reg / d logvar of
-    reg = clamp(kl_weight * sum KL, min=free_bits) - eta * sum logsigmoid(m_d) + gamma * S   (mae.py:132-139),
-    or None when ``want_grad`` is False.  ``kl_weight`` defaults to 1/B (KL.mean())."""
+    Returns (kl [B], m_d [*z], S [], reg [], grads, keep) with
+    reg = clamp(kl_weight * sum KL, min=free_bits) - eta * sum logsigmoid(m_d) + gamma * S   (mae.py:132-139)
+    and grads = [2,B,D] holding d reg / d mu and d reg / d logvar (None when ``want_grad`` is False).
+    ``kl_weight`` defaults to 1/B (KL.mean())."""
     _req_cuda(mu, logvar)
     mu2, ms = _rows(mu)
     lv2, ls = _rows(logvar)
@@ -862,132 +863,171 @@ def kl_mpd_reg_fused(mu: torch.Tensor, logvar: torch.Tensor, eta: float, gamma: 
     kw = 1.0 / float(b) if kl_weight is None else float(kl_weight)
     m_d = torch.empty(d, device=dev, dtype=torch.float32)
     s_ = torch.empty((), device=dev, dtype=torch.float32)
+    reg = torch.empty((), device=dev, dtype=torch.float32)
     kl = torch.empty(b, device=dev, dtype=torch.float32)
     grads = torch.empty(2, b, d, device=dev, dtype=torch.float32) if want_grad else None
     with torch.cuda.stream(launch_stream if launch_stream is not None else torch.cuda.current_stream(dev)):
         _lib.check(_lib_().mae_kl_mpd_loss_fused(mu2.data_ptr(), ms, lv2.data_ptr(), ls, b, d, float(eta), float(gamma),
                                                  float(free_bits), kw, m_d.data_ptr(), s_.data_ptr(), kl.data_ptr(),
-                                                 grads[0].data_ptr() if want_grad else None,
+                                                 reg.data_ptr(), grads[0].data_ptr() if want_grad else None,
                                                  grads[1].data_ptr() if want_grad else None, _stream()),
                    "mae_kl_mpd_loss_fused")
     _count()
-    return kl, m_d.view(mu.shape[1:]), s_, grads, (mu2, lv2)
+    return kl, m_d.view(mu.shape[1:]), s_, reg, grads, (mu2, lv2)
 
 
-class RegLaunch:
-    """Results of :func:`kl_mpd_reg_launch` still in flight on the side stream (consumed by :func:`loss_head`)."""
+class _EncodeHead(torch.autograd.Function):
+    """Everything between the encoder core and the decoder as ONE autograd node for training-sized batches:
+    (mu, logvar, eps) -> (z, reg, KL, m_d, S), reg = clamp(KL.mean(), free_bits) - eta sum logsigmoid(m_d) + gamma S.
 
-    def __init__(self, kl, m_d, s, grads, keep, params):
-        self.kl, self.m_d, self.s, self.grads, self.keep, self.params = kl, m_d, s, grads, keep, params
-
-
-def kl_mpd_reg_launch(mu: torch.Tensor, logvar: torch.Tensor, eta: float, gamma: float, free_bits: float) -> RegLaunch:
-    """Start the one-launch regulariser kernel on the side stream as soon as mu / logvar exist, so that it overlaps with
-    everything the main stream does next (reparameterisation, decoder); pass the result to :func:`loss_head`."""
-    dev = mu.device
-    cs, ss = torch.cuda.current_stream(dev), _side_stream(dev)
-    ss.wait_stream(cs)
-    want_grad = torch.is_grad_enabled() and (mu.requires_grad or logvar.requires_grad)
-    kl, m_d, s, grads, keep = kl_mpd_reg_fused(mu.detach(), logvar.detach(), eta, gamma, free_bits, None, want_grad,
-                                               launch_stream=ss)
-    return RegLaunch(kl, m_d, s, grads, keep, (float(eta), float(gamma), float(free_bits)))
-
-
-class _LossHead(torch.autograd.Function):
-    """The whole loss head behind the decoder as ONE autograd node for training-sized batches:
-    (decoder output, x, mu, logvar) -> objective of MAE.loss (mae.py:100-140).
-
-    forward  main stream: likelihood kernel (for the DMOL head the one-pass forward+backward kernel);
-             side stream: mae_kl_mpd_loss_fused = KL, MPD and d regulariser / d(mu, logvar) in one launch, then the
-             assembly kernel once the likelihood's partial sums exist.
-    backward nothing but two conditional rescales by d loss (no-ops when it is 1, the usual ``loss.backward()``).
-    ``defer``: see _LossTail."""
+    forward  main stream: the reparameterisation (z is what the decoder waits for); side stream: mae_kl_mpd_loss_fused,
+             i.e. KL, MPD, reg AND d reg / d(mu, logvar) in one launch, overlapping with the decoder.
+    backward ONE launch: d(mu, logvar) = reparam backward of d z  +  d reg * (stored regulariser gradient)."""
 
     @staticmethod
-    def forward(ctx, dec_out, x, mu, logvar, reg, kind, ns, nmix, eta, gamma, free_bits, defer):
+    def forward(ctx, mu, logvar, eps, eta, gamma, free_bits):
         ctx.set_materialize_grads(False)
-        _req_cuda(dec_out, x, mu, logvar)
+        _req_cuda(mu, logvar, eps)
+        dev = mu.device
+        idx = dev.index if dev.index is not None else torch.cuda.current_device()
+        b, ns = eps.size(0), eps.size(1)
+        want_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        cs, ss = torch.cuda.current_stream(dev), _side_stream(dev)
+        ss.wait_stream(cs)
+        prev = _pending_join.pop(idx, None)
+        kl, m_d, s, reg, grads, (mu2, lv2) = kl_mpd_reg_fused(mu, logvar, eta, gamma, free_bits, None, want_grad,
+                                                              launch_stream=ss)
+        ev = torch.cuda.Event()
+        ev.record(ss)
+        _pending_join[idx] = (ev, (prev, kl, m_d, s, reg, grads, mu2, lv2))
+        ms, ls = mu2.stride(0), lv2.stride(0)
+        d = mu2.size(1)
+        eps_c = eps.contiguous()
+        z = torch.empty_like(eps_c)
+        _lib.check(_lib_().mae_reparam_kl_fwd(mu2.data_ptr(), ms, lv2.data_ptr(), ls, eps_c.data_ptr(), b, ns, d,
+                                              z.data_ptr(), None, _stream()), "mae_reparam_kl_fwd")
+        _count()
+        ctx.save_for_backward(mu2, lv2, eps_c)
+        ctx.reg_grads = grads
+        ctx.reg_event = ev
+        ctx.meta = (ms, ls, b, ns, d, mu.shape, logvar.shape)
+        ctx.mark_non_differentiable(kl, m_d, s)
+        return z, reg, kl, m_d, s
+
+    @staticmethod
+    def backward(ctx, gz, g_reg, *_unused):
+        if gz is None and g_reg is None:
+            return (None,) * 6
+        mu2, lv2, eps_c = ctx.saved_tensors
+        ms, ls, b, ns, d, mu_shape, lv_shape = ctx.meta
+        dev = mu2.device
+        grads = ctx.reg_grads if g_reg is not None else None
+        if g_reg is not None and grads is None:
+            raise RuntimeError("encode_head: reg has a gradient but mu / logvar did not require one in the forward")
+        gz = gz.contiguous() if gz is not None else None
+        g_reg = g_reg.contiguous() if g_reg is not None else None
+        torch.cuda.current_stream(dev).wait_event(ctx.reg_event)   # the regulariser kernel ran on the side stream
+        dmu = torch.empty(b, d, device=dev, dtype=torch.float32)
+        dlv = torch.empty_like(dmu)
+        _lib.check(_lib_().mae_reparam_reg_bwd(mu2.data_ptr(), ms, lv2.data_ptr(), ls, eps_c.data_ptr(), _ptr(gz), None,
+                                               grads[0].data_ptr() if grads is not None else None,
+                                               grads[1].data_ptr() if grads is not None else None, _ptr(g_reg), b, ns, d,
+                                               dmu.data_ptr(), dlv.data_ptr(), 0, _stream()), "mae_reparam_reg_bwd")
+        _count()
+        return dmu.view(mu_shape), dlv.view(lv_shape), None, None, None, None
+
+
+class EncodedBatch:
+    """What :func:`encode_head` hands to :func:`loss_head`: reg (the only differentiable entry), KL [B], m_d, S and the
+    hyper-parameters they were computed with.  Valid on the main stream after :func:`join_side` (loss_head does it)."""
+
+    def __init__(self, reg, kl, m_d, s, params):
+        self.reg, self.kl, self.m_d, self.s, self.params = reg, kl, m_d, s, params
+
+
+def encode_head(mu: torch.Tensor, logvar: torch.Tensor, eps: torch.Tensor, eta: float = 0.0, gamma: float = 0.0,
+                free_bits: float = 0.0):
+    """Training-sized batches (see :func:`fused_reg_supported`): z [B,ns,*z] and the encoder-side regulariser of
+    MAE.loss in one autograd node; -> (z, EncodedBatch).  Reference: gaussian_encoder.py:56-62, :162-188, :219 and
+    mae.py:132-139."""
+    z, reg, kl, m_d, s = _EncodeHead.apply(mu, logvar, eps, float(eta), float(gamma), float(free_bits))
+    return z, EncodedBatch(reg, kl, m_d, s, (float(eta), float(gamma), float(free_bits)))
+
+
+class _LossTailReg(torch.autograd.Function):
+    """(decoder output, x, reg) -> objective of MAE.loss (mae.py:100-140) when the encoder side came from
+    :func:`encode_head`: likelihood kernel on the main stream (for the DMOL head the one-pass forward+backward kernel),
+    assembly kernel once both the likelihood's partial sums and the side stream's KL / m_d / S exist.
+    backward: d dec_out (a conditional rescale by d loss) and d reg = d loss.  ``defer``: see _LossTail."""
+
+    @staticmethod
+    def forward(ctx, dec_out, x, reg, kl, m_d, s, kind, ns, nmix, eta, gamma, free_bits, defer):
+        ctx.set_materialize_grads(False)
+        _req_cuda(dec_out, x, reg, kl, m_d, s)
         lib = _lib_()
         dev = dec_out.device
         idx = dev.index if dev.index is not None else torch.cuda.current_device()
         b = x.size(0)
-        want_grad = ctx.needs_input_grad[2] or ctx.needs_input_grad[3]
-        cs, ss = torch.cuda.current_stream(dev), _side_stream(dev)
-        prev = _pending_join.pop(idx, None)
-        if reg is not None:
-            if reg.params != (eta, gamma, free_bits) or (want_grad and reg.grads is None):
-                raise RuntimeError("loss_head: the RegLaunch was started with different eta / gamma / free_bits or without "
-                                   "gradients")
-            kl, m_d, s, grads, keep = reg.kl, reg.m_d, reg.s, (reg.grads if want_grad else None), reg.keep
-        else:
-            ss.wait_stream(cs)
-            kl, m_d, s, grads, keep = kl_mpd_reg_fused(mu, logvar, eta, gamma, free_bits, None, want_grad, launch_stream=ss)
         out_c, x_c, err, err_chunks, fused_grad, geom = _likelihood_fwd(dec_out, x, kind, ns, nmix, 0.0,
                                                                          ctx.needs_input_grad[0])
         m_c = m_d.reshape(-1)
         d = m_c.numel()
         scalars = torch.empty(6, device=dev, dtype=torch.float32)
         recon = torch.empty(b, device=dev, dtype=torch.float32)
-        ev_err = torch.cuda.Event()
-        ev_err.record(cs)
-        with torch.cuda.stream(ss):
-            ss.wait_event(ev_err)
+
+        def assemble():
             _lib.check(lib.mae_loss_assemble_fwd(err.data_ptr(), kl.data_ptr(), m_c.data_ptr(), s.data_ptr(), None, b, ns, d,
                                                  0, err_chunks, eta, gamma, free_bits, 0.0, scalars.data_ptr(),
                                                  recon.data_ptr(), _stream()), "mae_loss_assemble_fwd")
             _count()
-            ev = torch.cuda.Event()
-            ev.record(ss)
-        _pending_join[idx] = (ev, (prev, err, kl, m_c, s, scalars, recon, grads, keep))
-        if not defer:
+
+        if defer:
+            cs, ss = torch.cuda.current_stream(dev), _side_stream(dev)
+            ev_err = torch.cuda.Event()
+            ev_err.record(cs)
+            prev = _pending_join.pop(idx, None)      # the regulariser kernel already sits on the side stream
+            with torch.cuda.stream(ss):
+                ss.wait_event(ev_err)
+                assemble()
+                ev = torch.cuda.Event()
+                ev.record(ss)
+            _pending_join[idx] = (ev, (prev, err, kl, m_c, s, scalars, recon))
+        else:
             join_side(dev)
+            assemble()
         ctx.save_for_backward(out_c, x_c)
         ctx.fused_grad = fused_grad
-        ctx.reg_grads = grads
-        ctx.meta = (kind, b, ns, nmix, geom, dec_out.shape, mu.shape, logvar.shape, defer)
+        ctx.meta = (kind, b, ns, nmix, geom, dec_out.shape, defer)
         loss, stats = scalars[0], scalars[1:]
-        ctx.mark_non_differentiable(stats, recon, kl, m_d, s)
-        return loss, stats, recon, kl, m_d, s
+        ctx.mark_non_differentiable(stats, recon)
+        return loss, stats, recon
 
     @staticmethod
     def backward(ctx, gloss, *_unused):
         if gloss is None:
-            return (None,) * 12
+            return (None,) * 13
         out_c, x_c = ctx.saved_tensors
-        kind, b, ns, nmix, geom, out_shape, mu_shape, lv_shape, defer = ctx.meta
-        dev = out_c.device
+        kind, b, ns, nmix, geom, out_shape, defer = ctx.meta
         gloss = gloss.contiguous()
         dout = None
         if ctx.needs_input_grad[0]:
             dout = _likelihood_bwd(ctx, out_c, x_c, gloss, kind, b, ns, nmix, geom, 0.0, out_shape)
-        dmu = dlv = None
-        if ctx.reg_grads is not None:
-            if ctx.reg_grads is False:
-                raise RuntimeError("fused loss node: a second backward through the same graph is not supported")
-            grads = ctx.reg_grads
-            ctx.reg_grads = False
-            join_side(dev)                      # the regulariser kernel ran on the side stream
-            _lib.check(_lib_().mae_scale_inplace(grads.data_ptr(), grads.numel(), gloss.data_ptr(), _stream()),
-                       "mae_scale_inplace")
-            _count()
-            dmu, dlv = grads[0].view(mu_shape), grads[1].view(lv_shape)
-        elif defer:
-            join_side(dev)
-        return dout, None, dmu, dlv, None, None, None, None, None, None, None, None
+        if defer:
+            join_side(out_c.device)
+        return (dout, None, gloss if ctx.needs_input_grad[2] else None) + (None,) * 10
 
 
-def loss_head(dec_out: torch.Tensor, x: torch.Tensor, mu: torch.Tensor, logvar: torch.Tensor, kind: str, ns: int,
-              nmix: int = 10, eta: float = 0.0, gamma: float = 0.0, free_bits: float = 0.0, defer_join: bool = False,
-              reg: Optional[RegLaunch] = None):
-    """Decoder output + posterior parameters -> objective of MAE.loss in one autograd node (analytic KL, single process,
-    training-sized batch: see :func:`fused_reg_supported`).  Returns (loss [], stats [5], recon [B], KL [B], m_d, S); only
-    ``loss`` carries a gradient.  ``reg``: a :func:`kl_mpd_reg_launch` started earlier for the same mu / logvar (so the
-    regulariser overlaps with the decoder); without it the kernel is launched here.  Everything else as :func:`loss_tail`.
-    Reference: mae.py:100-140 with gaussian_encoder.py:162-188, :219 and the two reconstruct_error heads."""
+def loss_head(dec_out: torch.Tensor, x: torch.Tensor, enc: EncodedBatch, kind: str, ns: int, nmix: int = 10,
+              eta: float = 0.0, gamma: float = 0.0, free_bits: float = 0.0, defer_join: bool = False):
+    """Decoder output + :func:`encode_head` result -> objective of MAE.loss.  Returns (loss [], stats [5], recon [B]) like
+    :func:`loss_tail`; KL / m_d / S are in ``enc``.  ``defer_join``: see :func:`loss_tail`.
+    Reference: mae.py:100-140 with the two reconstruct_error heads."""
     if kind not in ("dmol", "bernoulli"):
         raise ValueError("kind must be 'dmol' or 'bernoulli'")
-    return _LossHead.apply(dec_out, x, mu, logvar, reg, kind, int(ns), int(nmix), float(eta), float(gamma), float(free_bits),
-                           bool(defer_join))
+    if enc.params != (float(eta), float(gamma), float(free_bits)):
+        raise RuntimeError("loss_head: encode_head was called with different eta / gamma / free_bits")
+    return _LossTailReg.apply(dec_out, x, enc.reg, enc.kl, enc.m_d, enc.s, kind, int(ns), int(nmix), float(eta),
+                              float(gamma), float(free_bits), bool(defer_join))
 
 
 def assemble_loss(err: torch.Tensor, kl: torch.Tensor, m_d: Optional[torch.Tensor], s: Optional[torch.Tensor],

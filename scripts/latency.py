@@ -73,8 +73,26 @@ def main():
     res["dmol_bwd"] = chain(lambda: lib.mae_dmol_bwd(P(raw), P(x), P(g), 1, 1.0, B, 1, 10, 1024, P(draw), st()))
     res["assemble_fwd"] = chain(lambda: lib.mae_loss_assemble_fwd(P(err), P(kl), P(m_d), P(S), None, B, 1, D, 0, 1, 1.0, 1.0, 0.0, 0.0, P(sc), P(recon), st()))
     res["assemble_bwd"] = chain(lambda: lib.mae_loss_assemble_bwd(P(g_S), P(sc), P(m_d), B, 1, D, 1.0, 1.0, 0.0, 0.0, P(derr), P(dkl), P(dm), P(dS), st()))
+    if lib.mae_kl_mpd_loss_fused_supported(B, D):
+        gr = torch.empty(2, B, D, device=dev)
+        res["kl_mpd_loss_fused (fwd+bwd)"] = chain(lambda: lib.mae_kl_mpd_loss_fused(
+            P(mu), D, P(lv), D, B, D, 1.0, 1.0, 0.0, 1.0 / B, P(m_d), P(S), P(kl), None, P(gr[0]), P(gr[1]), st()))
+        res["kl_mpd_loss_fused (fwd only)"] = chain(lambda: lib.mae_kl_mpd_loss_fused(
+            P(mu), D, P(lv), D, B, D, 1.0, 1.0, 0.0, 1.0 / B, P(m_d), P(S), P(kl), None, None, None, st()))
     for k, v in res.items():
         print("%-32s %8.2f us" % (k, v))
+    if os.environ.get("MAE_DEBUG_TIMING") and lib.mae_kl_mpd_loss_fused_supported(B, D):
+        import ctypes
+        torch.cuda.synchronize()
+        for _ in range(3):
+            lib.mae_kl_mpd_loss_fused(P(mu), D, P(lv), D, B, D, 1.0, 1.0, 0.0, 1.0 / B, P(m_d), P(S), P(kl), None, P(gr[0]), P(gr[1]), st())
+        torch.cuda.synchronize()
+        buf = (ctypes.c_ulonglong * 16)()
+        lib.mae_debug_fused_stamps.argtypes = [ctypes.c_void_p]
+        lib.mae_debug_fused_stamps(ctypes.addressof(buf))
+        t0 = buf[0]
+        print("fused: loads+pivot partials %d | elements %d | stats, m_d, KL mean %d | KL rows + block sum %d | "
+              "cluster exchange %d | gradient %d   (ns since start, CTA 0)" % tuple(int(buf[i]) - int(t0) for i in range(1, 7)))
     if os.environ.get("MAE_DEBUG_TIMING"):
         # phase timestamps written by the -DMAE_DEBUG_TIMING build (ns, %globaltimer), CTA 0 / last CTA
         torch.cuda.synchronize()

@@ -398,10 +398,11 @@ def _reg_reference(O, mu0, lv0, eta, gamma, free_bits):
     if gamma > 0:
         reg = reg + gamma * s
     reg.backward()
-    return kl.detach(), m_d.detach(), s.detach(), a.grad, c.grad
+    return kl.detach(), m_d.detach(), s.detach(), a.grad, c.grad, reg.detach()
 
 
-@pytest.mark.parametrize("b,d", [(2, 1), (5, 3), (8, 64), (9, 7), (21, 13), (64, 64), (65, 33), (100, 32), (100, 64), (128, 64)])
+@pytest.mark.parametrize("b,d", [(2, 1), (5, 3), (8, 64), (9, 7), (16, 16), (17, 5), (21, 13), (64, 64), (65, 33), (100, 32),
+                                 (100, 64), (104, 64), (128, 48)])
 def test_fused_regulariser_kernel_vs_oracle(ops, O, b, d):
     """mae_kl_mpd_loss_fused (one cluster launch: KL, m_d, S and d reg / d(mu, logvar)) against the fp64 oracle, for every
     cluster size 1..16, ragged last CTA, D below / at the 64-dim limit, and the eta / gamma / free-bits switches."""
@@ -410,18 +411,19 @@ def test_fused_regulariser_kernel_vs_oracle(ops, O, b, d):
     assert ops.fused_reg_supported(b, d, DEV)
     klm = float(O.analytic_kl(mu0.double(), lv0.double()).mean())
     for eta, gamma, fb in ((1.0, 1.0, 0.0), (0.0, 2.0, 0.0), (0.7, 0.0, 0.0), (1.0, 1.0, 2.0 * klm + 1.0)):
-        kl, m_d, s, grads, _ = ops.kl_mpd_reg_fused(cu(mu0), cu(lv0), eta, gamma, fb)
-        klr, mr, sr, gmu, glv = _reg_reference(O, mu0, lv0, eta, gamma, fb)
+        kl, m_d, s, reg, grads, _ = ops.kl_mpd_reg_fused(cu(mu0), cu(lv0), eta, gamma, fb)
+        klr, mr, sr, gmu, glv, regr = _reg_reference(O, mu0, lv0, eta, gamma, fb)
         tag = "B=%d D=%d eta=%g gamma=%g fb=%g" % (b, d, eta, gamma, fb)
         check_close(kl, klr, what="KL " + tag)
         check_close(m_d, mr, what="m_d " + tag)
         check_close(s, sr, what="S " + tag)
+        check_close(reg, regr, what="reg " + tag)
         check_close(grads[0], gmu, what="dmu " + tag, floor=1e-12)
         check_close(grads[1], glv, what="dlv " + tag, floor=1e-12)
     # forward only (evaluation): same values, no gradient buffers
-    kl2, m2, s2, g2, _ = ops.kl_mpd_reg_fused(cu(mu0), cu(lv0), 1.0, 1.0, 0.0, want_grad=False)
+    kl2, m2, s2, _, g2, _ = ops.kl_mpd_reg_fused(cu(mu0), cu(lv0), 1.0, 1.0, 0.0, want_grad=False)
     assert g2 is None
-    kl1, m1, s1, _, _ = ops.kl_mpd_reg_fused(cu(mu0), cu(lv0), 1.0, 1.0, 0.0)
+    kl1, m1, s1, _, _, _ = ops.kl_mpd_reg_fused(cu(mu0), cu(lv0), 1.0, 1.0, 0.0)
     assert torch.equal(kl1, kl2) and torch.equal(m1, m2) and torch.equal(s1, s2)   # deterministic
 
 
@@ -437,7 +439,7 @@ def test_fused_regulariser_goldens_and_strided_views(ops, O, golden):
         packed = cu(torch.cat([c["mu"].reshape(b, d), c["logvar"].reshape(b, d)], dim=1))
         mu, lv = packed.chunk(2, 1)
         eta, gamma = float(c["eta"]), float(c["gamma"])
-        kl, m_d, s, grads, _ = ops.kl_mpd_reg_fused(mu, lv, eta, gamma, 0.0, kl_weight=0.0)
+        kl, m_d, s, _, grads, _ = ops.kl_mpd_reg_fused(mu, lv, eta, gamma, 0.0, kl_weight=0.0)
         r64, r32 = c["ref64"], c["ref32"]
         check_close(m_d, r64["m_d"].reshape(-1), r32["m_d"].reshape(-1), what="%s m_d" % name)
         check_close(s, r64["S"], r32["S"], what="%s S" % name)
@@ -449,6 +451,7 @@ def test_fused_regulariser_goldens_and_strided_views(ops, O, golden):
 
 def test_fused_regulariser_rejects_large_shapes(ops):
     assert not ops.fused_reg_supported(129, 64, DEV) and not ops.fused_reg_supported(64, 65, DEV)
+    assert not ops.fused_reg_supported(128, 64, DEV)    # shared memory: falls back to the general kernels
     with pytest.raises(RuntimeError, match="outside the fused path"):
         ops.kl_mpd_reg_fused(torch.zeros(200, 8, device=DEV), torch.zeros(200, 8, device=DEV), 1.0, 1.0, 0.0)
 
