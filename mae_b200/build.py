@@ -30,8 +30,25 @@ def _nvcc() -> str:
     return exe
 
 
+def _extra_flags():
+    extra = ["-DMAE_DEBUG_TIMING"] if os.environ.get("MAE_DEBUG_TIMING") else []   # phase timestamps, profiling builds only
+    if os.environ.get("MAE_DMOL_G5"):                                              # tuning: pixel groups per CTA (SPLIT=5)
+        extra.append("-DMAE_DMOL_G5=%d" % int(os.environ["MAE_DMOL_G5"]))
+    return extra
+
+
+def _flags_file() -> str:
+    return os.path.join(PKG, "build", "flags.txt")
+
+
 def _stale() -> bool:
     if not os.path.exists(LIB):
+        return True
+    try:
+        with open(_flags_file()) as f:
+            if f.read() != " ".join(_extra_flags()):
+                return True
+    except OSError:
         return True
     t = os.path.getmtime(LIB)
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(ROOT, "include", "mae_b200.h"), __file__]
@@ -45,9 +62,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     objdir = os.path.join(PKG, "build")
     os.makedirs(objdir, exist_ok=True)
     nvcc = _nvcc()
-    extra = ["-DMAE_DEBUG_TIMING"] if os.environ.get("MAE_DEBUG_TIMING") else []   # phase timestamps, profiling builds only
-    if os.environ.get("MAE_DMOL_G5"):                                              # tuning: pixel groups per CTA (SPLIT=5)
-        extra.append("-DMAE_DMOL_G5=%d" % int(os.environ["MAE_DMOL_G5"]))
+    extra = _extra_flags()
     objs = []
     logs = []
     procs = []
@@ -67,6 +82,8 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("link failed:\n%s" % r.stdout)
     with open(os.path.join(objdir, "ptxas.log"), "w") as f:
         f.write("\n".join(logs))
+    with open(_flags_file(), "w") as f:
+        f.write(" ".join(extra))
     if verbose:
         print("\n".join(logs))
     return LIB

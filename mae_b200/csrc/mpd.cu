@@ -229,7 +229,7 @@ mpd_prepare_kernel(const float* __restrict__ mu, int64_t mu_stride, const float*
                     es += e.ema + s;            // all terms >= 0: well-conditioned fp32 sums
                     fs += e.bpa + sq * e.r;
                     // analytic KL term mu^2 + (e^lv - lv - 1), gaussian_encoder.py:219, second part cancellation-free
-                    ks += fmaf(mu_raw, mu_raw, expm1_minus_x(lv_raw, expm1f(lv_raw)));
+                    ks += fmaf(mu_raw, mu_raw, expm1_minus_x(lv_raw));
                     acc[h][0] += (double)e.a;
                     acc[h][1] += (double)e.b;
                     acc[h][2] += (double)e.a * (double)e.b;

@@ -5,8 +5,9 @@
 // so the regulariser leaves the critical path of a training step: nothing of it remains in the backward pass except an
 // optional rescale by d loss.  The general three-kernel path (mpd.cu) spends ~21 us of dependent launches here.
 //
-// One thread-block CLUSTER of ceil(B/8) CTAs; CTA c owns rows [8c, 8c+8).  Every CTA evaluates the O(B*D) pre-pass for
-// ALL rows redundantly (4-8k elements: cheaper than exchanging them), keeps V = {mc, a, b, r} of every (row, dim) in its
+// One thread-block CLUSTER of up to 16 CTAs; CTA c owns R = ceil(B/16) rows.  Every CTA evaluates the O(B*D) pre-pass for
+// ALL rows redundantly (4-8k elements: cheaper than exchanging them - distributed shared memory moves only ~20 B/clk per
+// SM, measured: an all-to-all of the per-element results cost 9 us), keeps V = {mc, a, b, r} of every (row, dim) in its
 // shared memory, and then only works on its own rows:
 //   phase 1  pivots, per-element quantities, column statistics (fp64), row sums E_i, F_i, analytic KL_i, closed-form m_d
 //   phase 2  KL_ij and KL_ji for own i, all j:  2 KL_ij = sum_d [a_i b_j + (mc_i - mc_j)^2 r_j] + E_i + F_j
@@ -27,7 +28,6 @@ namespace {
 constexpr int kFT = 512;           // threads per CTA
 constexpr int kFD = 64;            // latent dims supported (one thread column per dim)
 constexpr int kFG = kFT / kFD;     // 8 row groups in the pre-pass
-constexpr int kFR = 8;             // own rows per CTA
 constexpr int kFStats = 8;         // SA SB SAB S1 S2 R1 R2 S(a+b), as in mpd.cu
 constexpr int kFPivotRows = 32;
 constexpr int kFMaxB = 128;
@@ -68,6 +68,27 @@ __device__ __forceinline__ void block_sum3(double& a, double& b, double& c, doub
     c = warp_sum(lane < NW ? scratch[2][lane] : 0.0);
 }
 
+// Lane sums of N per-lane values at once: butterfly that halves the number of values a lane carries at every step
+// (N-1 shuffles) followed by plain xor steps over the remaining lane bits, instead of 5 N shuffles.  Afterwards every lane
+// holds the complete sum of value number  (lane >> (5 - log2 N)) & (N - 1).
+template <int N>
+__device__ __forceinline__ float multi_warp_sum(float (&x)[N], int lane) {
+    int off = 16;
+#pragma unroll
+    for (int n = N; n > 1; n >>= 1, off >>= 1) {
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int k = 0; k < n / 2; ++k) {
+            const float send = upper ? x[k] : x[k + n / 2];
+            const float keep = upper ? x[k + n / 2] : x[k];
+            x[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    float v = x[0];
+    for (; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+
 __device__ __forceinline__ float logsigmoid_f(float x) { return fminf(x, 0.f) - log1pf(expf(-fabsf(x))); }
 
 template <int NJ>
@@ -77,7 +98,7 @@ struct FusedSmem {
     double scratch[3][kFT / 32];
     double xs[kFMaxCluster];   // every CTA's sum of squares, pushed by its owner
     float pivpart[2][kFG][kFD];
-    float rowsum[3][2][NJ];   // E, F, analytic KL: one partial per 32-dim half, pushed by the row's owner
+    float rowsum[3][2][NJ];   // E, F, analytic KL: one partial per 32-dim half
     float E[NJ], F[NJ], K[NJ];
     float w1[NJ / 16][NJ], w2[NJ / 16][NJ];   // (KL_ij - m), (KL_ji - m) of the own rows, 0 where excluded
     float gm[kFD];
@@ -85,16 +106,11 @@ struct FusedSmem {
 };
 
 // Shared-memory carve-up behind FusedSmem (all offsets multiples of 16 bytes):
-//   V    float4 [D][Bs]             {mc, a, b, r} of every (dim, row); rows pushed by their owners
-//   loc  double [RM][8][64]         this CTA's per-row column statistics before they are summed and pushed
-//   U    union: part double [C][8][64] (column statistics of every CTA) | red float2 [512/NJ][RM][NJ] | gpart float [8][RM][2][64]
+//   V    float4 [D][Bs]             {mc, a, b, r} of every (dim, row)
+//   U    union: part double [8][8][64] (column statistics per row group) | red float2 [512/NJ][RM][NJ] | gpart float [8][RM][2][64]
 template <int NJ>
 __host__ __device__ constexpr size_t fused_off_v() { return ((sizeof(FusedSmem<NJ>) + 15) / 16) * 16; }
-__host__ __device__ inline size_t fused_union_bytes(int nj, int cluster) {
-    const size_t part = (size_t)cluster * kFStats * kFD * sizeof(double);
-    const size_t other = (size_t)(nj / 16) * 8 * 2 * kFD * sizeof(float) * 2;   // red and gpart: 16 KB (NJ=64) / 32 KB
-    return part > other ? part : other;
-}
+constexpr size_t kFusedUnionBytes = (size_t)kFG * kFStats * kFD * sizeof(double);   // 32 KB >= red, gpart for both NJ
 
 template <int NJ>
 __global__ void __launch_bounds__(kFT, 1)
@@ -106,8 +122,7 @@ kl_mpd_loss_fused_kernel(const float* __restrict__ mu, int64_t mu_stride, const 
     extern __shared__ __align__(16) unsigned char fused_smem[];
     FusedSmem<NJ>& sm = *reinterpret_cast<FusedSmem<NJ>*>(fused_smem);
     float4* V = reinterpret_cast<float4*>(fused_smem + fused_off_v<NJ>());
-    double* loc = reinterpret_cast<double*>(V + (size_t)D * Bs);
-    unsigned char* U = reinterpret_cast<unsigned char*>(loc + RM * kFStats * kFD);
+    unsigned char* U = reinterpret_cast<unsigned char*>(V + (size_t)D * Bs);
     double* part = reinterpret_cast<double*>(U);
     cg::cluster_group cluster = cg::this_cluster();
     const int crank = (int)cluster.block_rank(), C = (int)cluster.num_blocks();
@@ -118,39 +133,28 @@ kl_mpd_loss_fused_kernel(const float* __restrict__ mu, int64_t mu_stride, const 
     const double nb = (double)B;
 
     FUSED_STAMP(0);
-    // ------------------------------------------------------------------ phase A: own rows only, results pushed to all
-    // what no peer writes: the padding rows of V and the row sums of rows >= B
-    for (int q = tid; q < 3 * 2 * NJ; q += kFT) (&sm.rowsum[0][0][0])[q] = 0.f;
-    for (int q = tid; q < D * (Bs - B); q += kFT) V[(q / (Bs - B)) * Bs + B + q % (Bs - B)] = make_float4(0.f, 0.f, 0.f, 0.f);
-    cluster.barrier_arrive();   // "I have started and initialised": peers may write into this CTA after the matching wait
-
-    const int i_own = i0 + g;
-    const bool own_row = g < R && i_own < B;   // warp-uniform
-    const bool own_ok = own_row && dok;
+    // ------------------------------------------------------------------ phase 1: every row, every dim, redundantly
+    // (exchanging the per-element results instead costs more: distributed shared memory moves ~20 B/clk per SM)
+    constexpr int RPT = NJ / kFG;   // rows per thread
+    float mur[RPT], lvr[RPT];
+#pragma unroll
+    for (int q = 0; q < RPT; ++q) {
+        const int i = g + q * kFG;
+        const bool ok = dok && i < B;
+        mur[q] = ok ? mu[(int64_t)i * mu_stride + d] : 0.f;
+        lvr[q] = ok ? lv[(int64_t)i * lv_stride + d] : 0.f;
+    }
     const int P = B < kFPivotRows ? B : kFPivotRows;
-    float mu_own = 0.f, lv_own = 0.f;
     {
-        constexpr int PQ = kFPivotRows / kFG;   // pivot rows per thread
-        float pm[PQ], pl[PQ];
+        float pm = 0.f, pl = 0.f;
 #pragma unroll
-        for (int q = 0; q < PQ; ++q) {
-            const int i = g + q * kFG;
-            const bool ok = dok && i < P;
-            pm[q] = ok ? mu[(int64_t)i * mu_stride + d] : 0.f;
-            pl[q] = ok ? lv[(int64_t)i * lv_stride + d] : 0.f;
-        }
-        if (own_ok) {
-            mu_own = mu[(int64_t)i_own * mu_stride + d];
-            lv_own = lv[(int64_t)i_own * lv_stride + d];
-        }
-        float sm_ = 0.f, sl_ = 0.f;
-#pragma unroll
-        for (int q = 0; q < PQ; ++q) {
-            sm_ += pm[q];
-            sl_ += pl[q];
-        }
-        sm.pivpart[0][g][d] = sm_;
-        sm.pivpart[1][g][d] = sl_;
+        for (int q = 0; q < RPT; ++q)
+            if (g + q * kFG < P) {
+                pm += mur[q];
+                pl += lvr[q];
+            }
+        sm.pivpart[0][g][d] = pm;
+        sm.pivpart[1][g][d] = pl;
     }
     __syncthreads();
     FUSED_STAMP(1);
@@ -171,60 +175,57 @@ kl_mpd_loss_fused_kernel(const float* __restrict__ mu, int64_t mu_stride, const 
         sm.piv[3][d] = 1.0 / (double)v_bar;
     }
     {
-        double acc[kFStats];
+        // per-thread partial column statistics over <= 16 rows in fp32 (every term is small and well-conditioned in the
+        // pivoted variables), widened to fp64 for the sums across threads and CTAs
+        float acc[kFStats];
 #pragma unroll
-        for (int q = 0; q < kFStats; ++q) acc[q] = 0.0;
-        float es = 0.f, fs = 0.f, ks = 0.f;
-        float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (own_ok) {
-            const Elem e = make_elem(mu_own, lv_own, mu_bar, l_bar, v_bar);
-            const float sq = e.mc * e.mc;
-            v4 = make_float4(e.mc, e.a, e.b, e.r);
-            es = e.ema;   // a - alpha >= 0
-            fs = e.bpa;   // b + alpha
-            ks = fmaf(mu_own, mu_own, expm1_minus_x(lv_own, expm1f(lv_own)));   // gaussian_encoder.py:219
-            acc[0] = (double)e.a;
-            acc[1] = (double)e.b;
-            acc[2] = (double)e.a * (double)e.b;
-            acc[3] = (double)e.mc;
-            acc[4] = (double)sq;
-            acc[5] = (double)e.r * (double)e.mc;
-            acc[6] = (double)e.r * (double)sq;
-            acc[7] = (double)e.apb;
-        }
-        if (g < RM) {
+        for (int q = 0; q < kFStats; ++q) acc[q] = 0.f;
+        float es[RPT], fs[RPT], ks[RPT];
 #pragma unroll
-            for (int q = 0; q < kFStats; ++q) loc[(g * kFStats + q) * kFD + d] = acc[q];
+        for (int q = 0; q < RPT; ++q) {
+            const int i = g + q * kFG;
+            es[q] = fs[q] = ks[q] = 0.f;
+            float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (dok && i < B) {
+                const Elem e = make_elem(mur[q], lvr[q], mu_bar, l_bar, v_bar);
+                const float sq = e.mc * e.mc;
+                v4 = make_float4(e.mc, e.a, e.b, e.r);
+                es[q] = e.ema;   // a - alpha >= 0
+                fs[q] = e.bpa;   // b + alpha
+                ks[q] = fmaf(mur[q], mur[q], expm1_minus_x(lvr[q]));   // gaussian_encoder.py:219, cancellation-free
+                acc[0] += e.a;
+                acc[1] += e.b;
+                acc[2] = fmaf(e.a, e.b, acc[2]);
+                acc[3] += e.mc;
+                acc[4] += sq;
+                acc[5] = fmaf(e.r, e.mc, acc[5]);
+                acc[6] = fmaf(e.r, sq, acc[6]);
+                acc[7] += e.apb;
+            }
+            if (dok && i < Bs) V[d * Bs + i] = v4;   // rows in [B, Bs) are zero padding
         }
-        es = warp_sum(es);
-        fs = warp_sum(fs);
-        ks = warp_sum(ks);
-        cluster.barrier_wait();   // every CTA of the cluster runs and has initialised its shared memory
-        if (own_ok) {
-            for (int c = 0; c < C; ++c) cluster.map_shared_rank(V, c)[d * Bs + i_own] = v4;
-        }
-        if (own_row && lane < C) {   // lane c tells CTA c
-            float* rs = cluster.map_shared_rank(&sm.rowsum[0][0][0], lane);
-            rs[(0 * 2 + half) * NJ + i_own] = es;
-            rs[(1 * 2 + half) * NJ + i_own] = fs;
-            rs[(2 * 2 + half) * NJ + i_own] = ks;
-        }
-        __syncthreads();
         {
-            const int q = g;   // statistic (kFT / kFD == kFStats)
-            double t = 0.0;
-#pragma unroll
-            for (int gg = 0; gg < RM; ++gg) t += loc[(gg * kFStats + q) * kFD + d];
-            for (int c = 0; c < C; ++c) cluster.map_shared_rank(part, c)[(crank * kFStats + q) * kFD + d] = t;
+            constexpr int SH = RPT == 8 ? 2 : 1;   // lanes sharing one row's total after the butterfly: 4 or 2
+            const float e_ = multi_warp_sum<RPT>(es, lane);
+            const float f_ = multi_warp_sum<RPT>(fs, lane);
+            const float k_ = multi_warp_sum<RPT>(ks, lane);
+            if ((lane & ((1 << SH) - 1)) == 0) {
+                const int i = g + ((lane >> SH) & (RPT - 1)) * kFG;
+                sm.rowsum[0][half][i] = e_;
+                sm.rowsum[1][half][i] = f_;
+                sm.rowsum[2][half][i] = k_;
+            }
         }
+#pragma unroll
+        for (int q = 0; q < kFStats; ++q) part[(g * kFStats + q) * kFD + d] = (double)acc[q];
     }
-    cluster.sync();
+    __syncthreads();
     FUSED_STAMP(2);
-    // ------------------------------------------------------------------ phase B: column statistics, m_d, scalars
     {
-        const int q = g;
+        const int q = g;   // statistic (kFT / kFD == kFStats)
         double t = 0.0;
-        for (int c = 0; c < C; ++c) t += part[(c * kFStats + q) * kFD + d];
+#pragma unroll
+        for (int gg = 0; gg < kFG; ++gg) t += part[(gg * kFStats + q) * kFD + d];
         sm.cs[q][d] = t;
         for (int i = tid; i < NJ; i += kFT) {
             sm.E[i] = sm.rowsum[0][0][i] + sm.rowsum[0][1][i];
@@ -421,8 +422,7 @@ bool fused_geom(int64_t B, int64_t D, FusedGeom& g) {
     if (bs < (int64_t)g.cluster * g.rows) bs = (int64_t)g.cluster * g.rows;
     g.bs = (int)(bs | 1);   // odd row pitch (in float4): conflict-free for lane = row and for lane = dim
     const size_t off_v = g.nj == 64 ? fused_off_v<64>() : fused_off_v<128>();
-    g.smem = off_v + (size_t)D * g.bs * sizeof(float4) + (size_t)(g.nj / 16) * kFStats * kFD * sizeof(double) +
-             fused_union_bytes(g.nj, g.cluster);
+    g.smem = off_v + (size_t)D * g.bs * sizeof(float4) + kFusedUnionBytes;
     return g.smem <= 227 * 1024;
 }
 

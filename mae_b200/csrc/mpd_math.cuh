@@ -6,8 +6,9 @@
 
 namespace mae {
 
-// e^x - 1 - x >= 0 without cancellation: Taylor series for |x| < 0.5 (truncation < 2e-9 relative), direct otherwise
-__device__ __forceinline__ float expm1_minus_x(float x, float em1) {
+// em1 = e^x - 1 and ema = e^x - 1 - x >= 0, both without cancellation and with ONE exponential at most: Taylor series of
+// ema for |x| < 0.5 (truncation < 2e-9 relative; em1 = x + ema), expf(x) - 1 otherwise (no cancellation there).
+__device__ __forceinline__ void expm1_pair(float x, float& em1, float& ema) {
     if (fabsf(x) < 0.5f) {
         float p = 1.0f / 362880.0f;
         p = fmaf(p, x, 1.0f / 40320.0f);
@@ -17,9 +18,17 @@ __device__ __forceinline__ float expm1_minus_x(float x, float em1) {
         p = fmaf(p, x, 1.0f / 24.0f);
         p = fmaf(p, x, 1.0f / 6.0f);
         p = fmaf(p, x, 0.5f);
-        return p * x * x;
+        ema = p * x * x;
+        em1 = x + ema;
+    } else {
+        em1 = expf(x) - 1.0f;
+        ema = em1 - x;
     }
-    return em1 - x;
+}
+__device__ __forceinline__ float expm1_minus_x(float x) {
+    float em1, ema;
+    expm1_pair(x, em1, ema);
+    return ema;
 }
 
 // per-element quantities of the pivoted decomposition.  fp32 throughout: every quantity below is either a
@@ -32,8 +41,7 @@ __device__ __forceinline__ Elem make_elem(float mu, float lv, float mu_bar, floa
     Elem e;
     e.mc = mu - mu_bar;
     e.alpha = lv - l_bar;
-    e.a = expm1f(e.alpha);                                   // v / v_bar - 1
-    e.ema = expm1_minus_x(e.alpha, e.a);                     // a - alpha
+    expm1_pair(e.alpha, e.a, e.ema);                         // a = v / v_bar - 1,  ema = a - alpha
     e.v = v_bar * (1.0f + e.a);
     e.r = 1.0f / (e.v + kEps);
     e.b = -(e.a * v_bar + kEps) * e.r;                       // v_bar * r - 1
