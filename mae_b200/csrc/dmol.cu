@@ -876,19 +876,33 @@ extern "C" int mae_dmol_fwd_bwd(const float* raw, const float* x, float g_mul, i
 
 namespace mae {
 namespace {
-// data *= scale[0] unless the scale is exactly 1 (then every CTA returns after one load: no traffic)
+// data *= scale[0] unless the scale is exactly 1 (then every CTA returns after one load: no traffic).  The grid is kept
+// small (2 CTAs per SM) because the no-op case - d loss == 1, i.e. the usual loss.backward() - sits on the critical path of
+// every training step; four 16-byte loads in flight per thread keep the real case at bandwidth.
 __global__ void __launch_bounds__(256) scale_inplace_kernel(float* __restrict__ data, int64_t n4, int64_t n,
                                                             const float* __restrict__ scale) {
     const float sc = scale[0];
     if (sc == 1.0f) return;
     float4* d4 = reinterpret_cast<float4*>(data);
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n4; i += 4 * stride) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = d4[i + u * stride];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            v[u].x *= sc; v[u].y *= sc; v[u].z *= sc; v[u].w *= sc;
+            d4[i + u * stride] = v[u];
+        }
+    }
+    for (; i < n4; i += stride) {
         float4 v = d4[i];
         v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc;
         d4[i] = v;
     }
     if (blockIdx.x == 0)
-        for (int64_t i = n4 * 4 + threadIdx.x; i < n; i += blockDim.x) data[i] *= sc;
+        for (int64_t k = n4 * 4 + threadIdx.x; k < n; k += blockDim.x) data[k] *= sc;
 }
 }  // namespace
 }  // namespace mae
@@ -899,7 +913,7 @@ extern "C" int mae_scale_inplace(float* data, int64_t n, const float* scale, mae
     MAE_REQUIRE(n > 0, MAE_ERR_SHAPE);
     MAE_REQUIRE((reinterpret_cast<uintptr_t>(data) & 15) == 0, MAE_ERR_ALIGN);
     int64_t blocks = ceil_div(n / 4 + 1, 256);
-    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks > 148 * 2) blocks = 148 * 2;
     scale_inplace_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(data, n / 4, n, scale);
     return launch_status();
 }

@@ -1013,7 +1013,10 @@ class _LossTailReg(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dout = _likelihood_bwd(ctx, out_c, x_c, gloss, kind, b, ns, nmix, geom, 0.0, out_shape)
         if defer:
-            join_side(out_c.device)
+            # nothing in the backward pass consumes the deferred objective kernel: join once the whole pass has been
+            # enqueued, so that the encoder-side backward is not ordered behind it
+            dev = out_c.device
+            torch.autograd.Variable._execution_engine.queue_callback(lambda: join_side(dev))
         return (dout, None, gloss if ctx.needs_input_grad[2] else None) + (None,) * 10
 
 

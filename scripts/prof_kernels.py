@@ -54,3 +54,12 @@ if what in ("mpd_large", "all"):
         (m_d.sum() + s).backward()
     torch.cuda.synchronize()
     print("mpd_large", float(s))
+
+if what in ("reg_fused", "all"):
+    for b in (64, 100):
+        mu, lv = synth.posterior_params(b, (64,), clamp=True)
+        mu, lv = mu.to(dev), lv.to(dev)
+        for _ in range(reps):
+            kl, m_d, s, reg, grads, _ = ops.kl_mpd_reg_fused(mu, lv, 1.0, 1.0, 0.0)
+        torch.cuda.synchronize()
+        print("reg_fused B=%d" % b, float(reg))
