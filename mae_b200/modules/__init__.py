@@ -1,9 +1,15 @@
-"""Drop-in for the hot-path part of ``mae.modules`` (same names, signatures and registries)."""
+"""Drop-in for ``mae.modules``: the loss / evaluation hot path on the CUDA kernels (same names, signatures and registries)
+plus the PyTorch conv stacks and flows of the reference's binary-image and ResNet colour configurations."""
 from .flow import Flow
 from .encoder import Encoder, EncoderCore, GaussianEncoder
 from .decoder import Decoder, BinaryImageDecoder, ColorImageDecoder
+from . import networks
+from .zoo import (AFMADE, PixelCNNDecoderBinaryImage28x28, ResnetDecoderBinaryImage28x28, ResnetDecoderColorImage32x32,
+                  ResnetEncoderCoreBinaryImage28x28, ResnetEncoderCoreColorImage32x32)
 from .mae import MAE
 from .utils import exponentialMovingAverage, logsumexp
 
 __all__ = ["MAE", "Encoder", "EncoderCore", "GaussianEncoder", "Flow", "Decoder", "BinaryImageDecoder",
-           "ColorImageDecoder", "exponentialMovingAverage", "logsumexp"]
+           "ColorImageDecoder", "exponentialMovingAverage", "logsumexp", "networks", "AFMADE",
+           "PixelCNNDecoderBinaryImage28x28", "ResnetDecoderBinaryImage28x28", "ResnetDecoderColorImage32x32",
+           "ResnetEncoderCoreBinaryImage28x28", "ResnetEncoderCoreColorImage32x32"]

@@ -1,0 +1,474 @@
+"""PyTorch building blocks of the conv stacks around the hot path: weight-normalised layers with
+data-dependent initialisation, residual stacks, masked layers, PixelCNN and MADE.
+
+These are the callers' side of the boundary: plain ``torch.nn`` (cuDNN / cuBLAS), no kernels of ours.  They are written
+from the published layer definitions with the SAME module / parameter names as the reference so that its ``model.pt``
+files load with ``strict=True``:
+
+  reference                                               state_dict keys kept
+  networks/weight_norm.py:8-128                           ``<name>.linear|conv|deconv.{weight_g, weight_v, bias}``
+  networks/resnet.py:23-154                               ``main.<i>.{conv1, conv2, downsample}`` / ``{deconv1, deconv2, downsample}``
+  networks/masked.py:15-212                               ``{weight_v, weight_g (log scale), bias, mask}``
+  networks/auto_regressives/pixelcnn.py:8-105             ``main.<i>.main.<j>``, ``direct_connects.<i>.main.<j>``
+  networks/auto_regressives/made.py:8-60                  ``input_layer, direct_connect, hidden_layers.<i>, output_layer``
+
+Differences in mechanism (not in function): weight normalisation is evaluated explicitly in ``forward`` instead of through
+``torch.nn.utils.weight_norm`` hooks, and masks are applied functionally (``weight_v * mask``) instead of overwriting
+``weight_v.data`` on every call (masked entries are zero from construction on and receive a zero gradient, so they stay
+zero; outputs and state dicts are identical).  A per-step cache of the masked, normalised weights for the K-fold repeated
+flow evaluation is SURVEY §8f N4.
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+__all__ = ["LinearWeightNorm", "Conv2dWeightNorm", "ConvTranspose2dWeightNorm", "ResNet", "DeResNet", "MaskedLinear",
+           "MaskedConv2d", "PixelCNN", "MADE", "ReShape"]
+
+_INIT_STD = 0.05
+_STD_FLOOR = 1e-6
+
+
+def _rownorm(v: torch.Tensor, dim: int) -> torch.Tensor:
+    """L2 norm over every dimension except ``dim`` (kept, so it broadcasts against ``v``)."""
+    dims = [i for i in range(v.dim()) if i != dim]
+    return torch.linalg.vector_norm(v, dim=dims, keepdim=True)     # zero sub-gradient at 0 (fully masked rows)
+
+
+def _channel_stats(out: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """mean and unbiased std of every output channel (dim 1) over batch and positions."""
+    flat = out.transpose(0, 1).reshape(out.size(1), -1)
+    return flat.mean(dim=1), flat.std(dim=1)
+
+
+class _NormedWeight(nn.Module):
+    """Holds (weight_g, weight_v, bias) under the names ``torch.nn.utils.weight_norm`` would create and rebuilds
+    ``w = g * v / ||v||`` (norm over everything but ``norm_dim``) on demand."""
+
+    def __init__(self, shape: Sequence[int], norm_dim: int, n_out: int, bias: bool):
+        super().__init__()
+        self.norm_dim = norm_dim
+        v = torch.empty(*shape).normal_(mean=0.0, std=_INIT_STD)
+        self.bias = nn.Parameter(torch.zeros(n_out)) if bias else None
+        self.weight_g = nn.Parameter(_rownorm(v, norm_dim).clone())
+        self.weight_v = nn.Parameter(v)
+
+    def weight(self) -> torch.Tensor:
+        return self.weight_v * (self.weight_g / _rownorm(self.weight_v, self.norm_dim))
+
+    def rescale(self, mean: torch.Tensor, std: torch.Tensor, init_scale: float) -> None:
+        """Data-dependent init (Salimans & Kingma 2016): make the layer's output zero-mean with std ``init_scale``."""
+        gain = init_scale / (std + _STD_FLOOR)
+        g_shape = [1] * self.weight_g.dim()
+        g_shape[self.norm_dim] = -1
+        self.weight_g.mul_(gain.view(g_shape))
+        if self.bias is not None:
+            self.bias.sub_(mean).mul_(gain)
+
+
+class LinearWeightNorm(nn.Module):
+    """Weight-normalised affine map; parameters live in ``self.linear`` (weight_norm.py:8-43)."""
+
+    def __init__(self, in_features: int, out_features: int, bias: bool = True):
+        super().__init__()
+        self.in_features, self.out_features = in_features, out_features
+        self.linear = _NormedWeight((out_features, in_features), 0, out_features, bias)
+
+    def forward(self, input):
+        return F.linear(input, self.linear.weight(), self.linear.bias)
+
+    def initialize(self, x, init_scale=1.0):
+        with torch.no_grad():
+            out = self(x)
+            self.linear.rescale(out.mean(dim=0), out.std(dim=0), init_scale)
+            return self(x)
+
+    def extra_repr(self):
+        return 'in_features={}, out_features={}, bias={}'.format(self.in_features, self.out_features, self.linear.bias is not None)
+
+
+class Conv2dWeightNorm(nn.Module):
+    """Weight-normalised convolution; parameters live in ``self.conv`` (weight_norm.py:46-86)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1, bias=True):
+        super().__init__()
+        k = nn.modules.utils._pair(kernel_size)
+        self.conv = _NormedWeight((out_channels, in_channels // groups, *k), 0, out_channels, bias)
+        self.geometry = dict(stride=stride, padding=padding, dilation=dilation, groups=groups)
+
+    def _conv(self, input):
+        return F.conv2d(input, self.conv.weight(), self.conv.bias, **self.geometry)
+
+    def forward(self, input):
+        return self._conv(input)
+
+    def initialize(self, x, init_scale=1.0):
+        with torch.no_grad():
+            mean, std = _channel_stats(self(x))
+            self.conv.rescale(mean, std, init_scale)
+            return self(x)
+
+
+class ConvTranspose2dWeightNorm(nn.Module):
+    """Weight-normalised transposed convolution, normalised per OUTPUT channel (dim 1 of the weight); parameters live in
+    ``self.deconv`` (weight_norm.py:89-128)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, output_padding=0, groups=1, bias=True,
+                 dilation=1):
+        super().__init__()
+        k = nn.modules.utils._pair(kernel_size)
+        self.deconv = _NormedWeight((in_channels, out_channels // groups, *k), 1, out_channels, bias)
+        self.geometry = dict(stride=stride, padding=padding, output_padding=output_padding, groups=groups, dilation=dilation)
+
+    def _deconv(self, input):
+        return F.conv_transpose2d(input, self.deconv.weight(), self.deconv.bias, **self.geometry)
+
+    def forward(self, input):
+        return self._deconv(input)
+
+    def initialize(self, x, init_scale=1.0):
+        with torch.no_grad():
+            mean, std = _channel_stats(self(x))
+            self.deconv.rescale(mean, std, init_scale)
+            return self(x)
+
+
+def _run(layers, x, init: bool, init_scale: float):
+    """Feed x through ``layers``; with ``init`` every layer that has a data-dependent ``initialize`` runs it."""
+    for layer in layers:
+        x = layer.initialize(x, init_scale=init_scale) if init and hasattr(layer, 'initialize') else layer(x)
+    return x
+
+
+# ------------------------------------------------------------------------------------------- residual stacks
+class ResNetBlock(nn.Module):
+    """ELU(conv2(ELU(conv1(x))) + shortcut(x)), 3x3 weight-normalised convolutions (resnet.py:23-61)."""
+
+    def __init__(self, inplanes, planes, stride=1):
+        super().__init__()
+        self.conv1 = Conv2dWeightNorm(inplanes, planes, 3, stride=stride, padding=1)
+        self.activation = nn.ELU()
+        self.conv2 = Conv2dWeightNorm(planes, planes, 3, padding=1)
+        self.downsample = (Conv2dWeightNorm(inplanes, planes, 1, stride=stride)
+                           if (stride != 1 or inplanes != planes) else None)
+        self.stride = stride
+
+    def _pass(self, x, init, init_scale):
+        shortcut = x if self.downsample is None else _run([self.downsample], x, init, init_scale)
+        h = self.activation(_run([self.conv1], x, init, init_scale))
+        h = _run([self.conv2], h, init, init_scale)
+        return self.activation(h + shortcut)
+
+    def forward(self, x):
+        return self._pass(x, False, 1.0)
+
+    def initialize(self, x, init_scale=1.0):
+        return self._pass(x, True, init_scale)
+
+
+class DeResNetBlock(nn.Module):
+    """Pre-activated transposed block: a = ELU(x); deconv2(ELU(deconv1(a))) + shortcut(a)  (resnet.py:64-107)."""
+
+    def __init__(self, inplanes, planes, stride=1, output_padding=0):
+        super().__init__()
+        self.deconv1 = ConvTranspose2dWeightNorm(inplanes, planes, 3, stride=stride, padding=1, output_padding=output_padding)
+        self.activation = nn.ELU()
+        self.deconv2 = ConvTranspose2dWeightNorm(planes, planes, 3, padding=1)
+        self.downsample = (ConvTranspose2dWeightNorm(inplanes, planes, 1, stride=stride, output_padding=output_padding)
+                           if (stride != 1 or inplanes != planes) else None)
+        self.stride = stride
+
+    def _pass(self, x, init, init_scale):
+        a = self.activation(x)
+        shortcut = a if self.downsample is None else _run([self.downsample], a, init, init_scale)
+        h = self.activation(_run([self.deconv1], a, init, init_scale))
+        return _run([self.deconv2], h, init, init_scale) + shortcut
+
+    def forward(self, x):
+        return self._pass(x, False, 1.0)
+
+    def initialize(self, x, init_scale=1.0):
+        return self._pass(x, True, init_scale)
+
+
+class ResNet(nn.Module):
+    def __init__(self, inplanes, planes: List[int], strides: List[int]):
+        super().__init__()
+        if len(planes) != len(strides):
+            raise ValueError('planes and strides must have the same length')
+        blocks, cin = [], inplanes
+        for cout, stride in zip(planes, strides):
+            blocks.append(ResNetBlock(cin, cout, stride=stride))
+            cin = cout
+        self.main = nn.Sequential(*blocks)
+
+    def forward(self, x):
+        return self.main(x)
+
+    def initialize(self, x, init_scale=1.0):
+        return _run(self.main, x, True, init_scale)
+
+
+class DeResNet(nn.Module):
+    def __init__(self, inplanes, planes: List[int], strides: List[int], output_paddings: List[int]):
+        super().__init__()
+        if not (len(planes) == len(strides) == len(output_paddings)):
+            raise ValueError('planes, strides and output_paddings must have the same length')
+        blocks, cin = [], inplanes
+        for cout, stride, op in zip(planes, strides, output_paddings):
+            blocks.append(DeResNetBlock(cin, cout, stride=stride, output_padding=op))
+            cin = cout
+        self.main = nn.Sequential(*blocks)
+
+    def forward(self, x):
+        return self.main(x)
+
+    def initialize(self, x, init_scale=1.0):
+        return _run(self.main, x, True, init_scale)
+
+
+# ----------------------------------------------------------------------------------------------- masked layers
+class _MaskedWeight(nn.Module):
+    """Common part of the masked layers (masked.py:15-212): ``w = (v*mask) * exp(g) / (||v*mask|| + 1e-8)`` with a
+    LOG-scale gain ``weight_g`` and a constant 0/1 ``mask`` buffer."""
+
+    def _setup(self, shape, mask: torch.Tensor, n_out: int, bias: bool):
+        self.register_buffer('mask', mask.to(torch.float32))
+        v = torch.empty(*shape).normal_(mean=0.0, std=_INIT_STD) * self.mask
+        g_shape = (n_out,) + (1,) * (len(shape) - 1)
+        self.weight_v = nn.Parameter(v)
+        self.weight_g = nn.Parameter((_rownorm(v, 0) + 1e-8).log().view(g_shape))
+        if bias:
+            self.bias = nn.Parameter(torch.zeros(n_out))
+        else:
+            self.register_parameter('bias', None)
+
+    def masked_weight(self) -> torch.Tensor:
+        v = self.weight_v * self.mask
+        return v * (self.weight_g.exp() / (_rownorm(v, 0) + 1e-8))
+
+    def _rescale(self, mean, std, init_scale):
+        gain = init_scale / (std + _STD_FLOOR)
+        self.weight_g.add_(gain.log().view(self.weight_g.shape))
+        if self.bias is not None:
+            self.bias.sub_(mean).mul_(gain)
+
+
+def made_degrees(n_units: int, total_units: int, kind: str) -> torch.Tensor:
+    """Degree ("max unit") of each unit of a MADE layer (masked.py:44-60): inputs 1..n; hidden units spread evenly over
+    1..total_units (ceil((i+1) * total/n)); outputs 0..n-1 capped at total_units."""
+    idx = torch.arange(n_units, dtype=torch.float64)
+    if kind == 'input':
+        return (idx + 1).to(torch.int64)
+    if kind == 'output':
+        return torch.clamp(idx, max=float(total_units)).to(torch.int64)
+    # float32 product as numpy's np.ceil((i + 1) * (float(total)/n)) evaluates it in double: do the same in double
+    return torch.ceil((idx + 1) * (float(total_units) / n_units)).to(torch.int64)
+
+
+class MaskedLinear(_MaskedWeight):
+    """MADE layer: output unit i sees input unit j iff degree_out[i] >= degree_in[j]; order 'B' reverses both axes."""
+
+    def __init__(self, in_features, out_features, mask_type, total_units, max_units=None, bias=True):
+        super().__init__()
+        layer_type, order = mask_type
+        if layer_type not in ('input-hidden', 'hidden-hidden', 'hidden-output', 'input-output') or order not in ('A', 'B'):
+            raise ValueError('unknown mask type %s' % (mask_type,))
+        self.in_features, self.out_features = in_features, out_features
+        self.layer_type, self.order = layer_type, order
+        if layer_type.startswith('input'):
+            deg_in = made_degrees(in_features, total_units, 'input')
+        else:
+            if max_units is None or len(max_units) != in_features:
+                raise ValueError('hidden layers need the degrees of their %d inputs' % in_features)
+            deg_in = torch.as_tensor(max_units, dtype=torch.int64)
+        if layer_type.endswith('output'):
+            if out_features <= total_units:
+                raise ValueError('an output layer needs more than total_units units')
+            deg_out = made_degrees(out_features, total_units, 'output')
+        else:
+            deg_out = made_degrees(out_features, total_units, 'hidden')
+        self.max_units = deg_out.numpy()
+        mask = (deg_out.view(-1, 1) >= deg_in.view(1, -1)).to(torch.float32)
+        if order == 'B':
+            mask = mask.flip(0, 1)
+        self._setup((out_features, in_features), mask.contiguous(), out_features, bias)
+
+    def forward(self, input):
+        return F.linear(input, self.masked_weight(), self.bias)
+
+    def initialize(self, x, init_scale=1.0):
+        with torch.no_grad():
+            out = self(x)
+            std = out.std(dim=0)
+            std = std + (std <= 0).to(std.dtype)      # constant units (fully masked rows) keep their scale
+            self._rescale(out.mean(dim=0), std, init_scale)
+            return self(x)
+
+    def extra_repr(self):
+        return 'in_features={}, out_features={}, bias={}, type={}, order={}'.format(
+            self.in_features, self.out_features, self.bias is not None, self.layer_type, self.order)
+
+
+class MaskedConv2d(_MaskedWeight):
+    """PixelCNN convolution: of the first ``masked_channels`` input channels only the taps strictly before the centre in
+    raster order are visible (type 'B': the centre too); the remaining input channels (conditioning) are unmasked;
+    order 'B' flips the raster order (masked.py:113-212)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, mask_type='A', order='A', masked_channels=None, stride=1,
+                 padding=0, dilation=1, groups=1, bias=True):
+        super().__init__()
+        if mask_type not in ('A', 'B') or order not in ('A', 'B'):
+            raise ValueError('mask_type and order must be "A" or "B"')
+        if in_channels % groups or out_channels % groups:
+            raise ValueError('in_channels and out_channels must be divisible by groups')
+        pair = nn.modules.utils._pair
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.mask_type, self.order = mask_type, order
+        self.masked_channels = in_channels if masked_channels is None else masked_channels
+        self.kernel_size, self.stride, self.padding, self.dilation = pair(kernel_size), pair(stride), pair(padding), pair(dilation)
+        self.groups = groups
+        kh, kw = self.kernel_size
+        shape = (out_channels, in_channels // groups, kh, kw)
+        mask = torch.ones(shape)
+        first_hidden_col = kw // 2 + (1 if mask_type == 'B' else 0)
+        mask[:, :self.masked_channels, kh // 2, first_hidden_col:] = 0
+        mask[:, :self.masked_channels, kh // 2 + 1:, :] = 0
+        if order == 'B':
+            mask = mask.flip(2, 3)
+        self._setup(shape, mask.contiguous(), out_channels, bias)
+
+    def forward(self, input):
+        return F.conv2d(input, self.masked_weight(), self.bias, self.stride, self.padding, self.dilation, self.groups)
+
+    def initialize(self, x, init_scale=1.0):
+        with torch.no_grad():
+            mean, std = _channel_stats(self(x))
+            self._rescale(mean, std, init_scale)
+            return self(x)
+
+
+# ---------------------------------------------------------------------------------------------------- PixelCNN
+class PixelCNNBlock(nn.Module):
+    """Bottleneck residual block: 1x1 -> masked kxk (type B) -> 1x1 at half width (pixelcnn.py:8-33)."""
+
+    def __init__(self, in_channels, kernel_size):
+        super().__init__()
+        self.mask_type = 'B'
+        mid = in_channels // 2
+        self.main = nn.Sequential(
+            Conv2dWeightNorm(in_channels, mid, 1),
+            nn.ELU(),
+            MaskedConv2d(mid, mid, kernel_size, mask_type='B', padding=kernel_size // 2),
+            nn.ELU(),
+            Conv2dWeightNorm(mid, in_channels, 1),
+        )
+        self.activation = nn.ELU()
+
+    def forward(self, input):
+        return self.activation(self.main(input) + input)
+
+    def initialize(self, x, init_scale=1.0):
+        return self.activation(_run(self.main, x, True, init_scale) + x)
+
+
+class MaskABlock(nn.Module):
+    """First layer: type-A masked convolution over [image | conditioning] channels (pixelcnn.py:36-53)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, masked_channels):
+        super().__init__()
+        self.mask_type = 'A'
+        self.main = nn.Sequential(
+            MaskedConv2d(in_channels, out_channels, kernel_size, mask_type='A', masked_channels=masked_channels,
+                         padding=kernel_size // 2),
+            nn.ELU(),
+        )
+
+    def forward(self, input):
+        return self.main(input)
+
+    def initialize(self, x, init_scale=1.0):
+        return _run(self.main, x, True, init_scale)
+
+
+class PixelCNN(nn.Module):
+    """Stack of masked blocks with long skip connections: the output of block i re-enters, through its own bottleneck
+    block ``direct_connects[i]``, in front of block i+3 (and the third-last output after the last block)
+    (pixelcnn.py:56-105)."""
+
+    def __init__(self, in_channels, out_channels, num_blocks, kernel_sizes, masked_channels):
+        super().__init__()
+        if num_blocks != len(kernel_sizes):
+            raise ValueError('one kernel size per block')
+        blocks = [MaskABlock(in_channels, out_channels, kernel_sizes[0], masked_channels)]
+        blocks += [PixelCNNBlock(out_channels, k) for k in kernel_sizes[1:]]
+        self.main = nn.ModuleList(blocks)
+        self.direct_connects = nn.ModuleList([PixelCNNBlock(out_channels, kernel_sizes[i]) for i in range(1, num_blocks - 1)])
+
+    def _pass(self, x, init, init_scale):
+        pending = []                                   # outputs waiting for their skip connection (lag 3)
+        for i, block in enumerate(self.main):
+            if i >= 3:
+                x = x + _run([self.direct_connects[i - 3]], pending.pop(0), init, init_scale)
+            x = _run([block], x, init, init_scale)
+            pending.append(x)
+        if len(pending) != 3:
+            raise RuntimeError('PixelCNN needs at least 3 blocks')
+        return x + _run([self.direct_connects[-1]], pending.pop(0), init, init_scale)
+
+    def forward(self, input):
+        return self._pass(input, False, 1.0)
+
+    def initialize(self, x, init_scale=1.0):
+        return self._pass(x, True, init_scale)
+
+
+# -------------------------------------------------------------------------------------------------------- MADE
+class MADE(nn.Module):
+    """Masked autoencoder for distribution estimation (Germain et al. 2015) with a masked direct input->output
+    connection; ReLU hidden units (auto_regressives/made.py:8-60).  Output i depends on inputs < i (order 'A')."""
+
+    def __init__(self, input_size, num_hiddens, hidden_size, order, bias=True):
+        super().__init__()
+        if num_hiddens < 1:
+            raise ValueError('MADE needs at least one hidden layer')
+        self.input_size, self.num_hiddens, self.hidden_size = input_size, num_hiddens, hidden_size
+        self.activation = nn.ReLU()
+        total = input_size - 1
+        self.input_layer = MaskedLinear(input_size, hidden_size, ('input-hidden', order), total, bias=bias)
+        self.direct_connect = MaskedLinear(input_size, input_size, ('input-output', order), total, bias=bias)
+        degrees = self.input_layer.max_units
+        hidden = []
+        for _ in range(1, num_hiddens):
+            layer = MaskedLinear(hidden_size, hidden_size, ('hidden-hidden', order), total, max_units=degrees, bias=bias)
+            degrees = layer.max_units
+            hidden.append(layer)
+        self.hidden_layers = nn.ModuleList(hidden)
+        self.output_layer = MaskedLinear(hidden_size, input_size, ('hidden-output', order), total, max_units=degrees, bias=bias)
+
+    def _pass(self, x, init, init_scale):
+        h = self.activation(_run([self.input_layer], x, init, init_scale))
+        for layer in self.hidden_layers:
+            h = self.activation(_run([layer], h, init, init_scale))
+        out = _run([self.output_layer], h, init, init_scale)
+        return out + _run([self.direct_connect], x, init, init_scale)
+
+    def forward(self, x):
+        return self._pass(x, False, 1.0)
+
+    def initialize(self, x, init_scale=1.0):
+        return self._pass(x, True, init_scale)
+
+
+class ReShape(nn.Module):
+    def __init__(self, out_shape):
+        super().__init__()
+        self.out_shape = tuple(out_shape)
+
+    def forward(self, input):
+        return input.view(input.size(0), *self.out_shape)

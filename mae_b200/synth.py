@@ -82,3 +82,32 @@ def color_head_hard(nimages: int = 3, nsamples: int = 2, nmix: int = 10, height:
     pix[edge > 0.8] = 255
     x = pix.float() / 127.5 - 1.0
     return {"raw": raw, "x": x}
+
+
+def fill_state(module, seed: int = SEED, gain: float = 0.7):
+    """Deterministic parameter values keyed by parameter NAME (crc32), for model-level parity tests without stored
+    weights: the same call on the reference's model and on ours (identical state_dict keys) yields identical weights.
+    weight_v ~ N(0, 0.05); weight_g ~ |gain (1 + 0.1 N)| for weight-normalised layers (row norm of the weight), 0.1 N +
+    log(gain / 3) for the masked layers (log-scale gain, recognised by their ``mask`` buffer; kept small so that stacked
+    autoregressive flows stay in range); bias ~ 0.1 N.  Mask buffers are left as constructed."""
+    import math
+    import zlib
+    sd = module.state_dict()
+    masked = {n[:-len("mask")] for n in sd if n.endswith("mask")}
+    with torch.no_grad():
+        for name, t in sd.items():
+            if name.endswith("mask"):
+                continue
+            g = torch.Generator().manual_seed((seed ^ zlib.crc32(name.encode())) & 0x7FFFFFFF)
+            r = torch.randn(tuple(t.shape), generator=g, dtype=torch.float32)
+            prefix = name[:name.rfind(".") + 1]
+            if name.endswith("weight_v"):
+                v = 0.05 * r
+            elif name.endswith("weight_g"):
+                v = 0.1 * r + math.log(gain / 3.0) if prefix in masked else (gain * (1.0 + 0.1 * r)).abs()
+            elif name.endswith("bias"):
+                v = 0.1 * r
+            else:
+                v = 0.05 * r
+            t.copy_(v.to(t.dtype))
+    return module

@@ -1,0 +1,101 @@
+"""the PyTorch model shell (conv stacks, masked layers, flows) against the LIVE reference's models.
+
+Fixtures: tests/golden/models.pt (tests/golden/make_golden_models.py) = ``MAE.from_params`` of the reference on its
+shipped binary_image.json and on a ResNet colour config, parameters filled from their names (synth.fill_state).  These
+tests run on the CPU: they cover construction from the reference's JSON, state_dict key/shape/mask identity (so that
+reference checkpoints load strictly), the networks' forward passes, the AF-MADE flow in both directions and the
+data-dependent initialisation.  The loss / NLL through the CUDA hot path is tests/test_gpu_models.py."""
+import copy
+
+import pytest
+import torch
+
+from tolerance import check_close
+
+from mae_b200 import synth
+from mae_b200.modules import MAE
+
+
+@pytest.fixture(scope="module")
+def fixtures(golden):
+    return golden("models")
+
+
+def _ours(c):
+    return synth.fill_state(MAE.from_params(copy.deepcopy(c["params"])))
+
+
+@pytest.mark.parametrize("name", ["binary_image_json", "color_resnet"])
+def test_state_dict_identity_with_reference(fixtures, name):
+    c = fixtures[name]
+    model = MAE.from_params(copy.deepcopy(c["params"]))
+    sd = model.state_dict()
+    assert {n: tuple(t.shape) for n, t in sd.items()} == c["keys"]          # strict loading of reference checkpoints
+    for n, checksum in c["masks"].items():
+        t = sd[n]
+        got = float((t * torch.arange(1, t.numel() + 1, dtype=torch.float64).view(t.shape) % 977).sum())
+        assert got == checksum, "mask %s differs from the reference's" % n
+    # the reference's own state dict round-trips
+    model.load_state_dict({n: torch.zeros(s) for n, s in c["keys"].items()}, strict=True)
+
+
+@pytest.mark.parametrize("name", ["binary_image_json", "color_resnet"])
+def test_encoder_core_and_flow_forward(fixtures, name):
+    c = fixtures[name]
+    r64, r32 = c["ref64"], c["ref32"]
+    model = _ours(c).eval()
+    with torch.no_grad():
+        mu, logvar = model.encoder.core(c["x"])
+        check_close(mu, r64["mu"], r32["mu"], what="%s mu" % name)
+        check_close(logvar, r64["logvar"], r32["logvar"], what="%s logvar" % name)
+        flow = model.encoder.prior_flow
+        if "flow_bwd" in r64:
+            zn, ld = flow.backward(mu.view(mu.size(0), *flow.input_size()))
+            check_close(zn, r64["flow_bwd"], r32["flow_bwd"], what="flow backward")
+            check_close(ld, r64["flow_bwd_logdet"], r32["flow_bwd_logdet"], what="flow backward logdet")
+            zf, ldf = flow.forward(zn[:2])
+            check_close(zf, r64["flow_fwd"], r32["flow_fwd"], what="flow forward (sequential inverse)")
+            check_close(ldf, r64["flow_fwd_logdet"], r32["flow_fwd_logdet"], what="flow forward logdet")
+            check_close(zf, mu[:2], rel=1e-4, what="forward(backward(z)) == z")
+        else:
+            assert flow is None
+
+
+@pytest.mark.parametrize("name", ["binary_image_json", "color_resnet"])
+def test_data_dependent_initialize(fixtures, name):
+    """MAE.initialize (weight_norm.py:25-37, masked.py:84-98 through every stack) from identical filled weights ends in
+    the same gains and biases."""
+    c = fixtures[name]
+    model = _ours(c)
+    with torch.no_grad():
+        model.initialize(c["x_init"], init_scale=1.0)
+    sd = model.state_dict()
+    for n, ref in c["init"].items():
+        check_close(sd[n].reshape(-1)[:32], ref, rel=2e-4, what="%s after initialize" % n)
+    for n, ref in c["init_bias"].items():
+        check_close(sd[n].reshape(-1)[:32], ref, rel=2e-4, floor=2e-5, what="%s after initialize" % n)
+
+
+def test_masked_layers_keep_masked_entries_zero():
+    """functional masking: masked entries are zero from construction on and get a zero gradient (the reference re-zeroes
+    ``weight_v.data`` on every call, masked.py:102)."""
+    from mae_b200.modules.networks import MADE, MaskedConv2d
+    torch.manual_seed(0)
+    made = MADE(6, 2, 18, 'B')
+    conv = MaskedConv2d(3, 4, 5, mask_type='A', masked_channels=1, padding=2)
+    made(torch.randn(4, 6)).sum().backward()
+    conv(torch.randn(2, 3, 7, 7)).sum().backward()
+    for layer in [made.input_layer, made.output_layer, made.direct_connect, made.hidden_layers[0], conv]:
+        assert float((layer.weight_v * (1 - layer.mask)).abs().max()) == 0.0
+        assert float((layer.weight_v.grad * (1 - layer.mask)).abs().max()) == 0.0
+    # autoregressive property of MADE order B: output i depends only on inputs > i
+    x = torch.randn(1, 6, requires_grad=True)
+    jac = torch.autograd.functional.jacobian(lambda t: made(t), x)[0, :, 0, :]
+    assert float(jac.tril().abs().max()) == 0.0
+
+
+def test_registries_hold_the_reference_keys():
+    from mae_b200.modules import Decoder, EncoderCore, Flow
+    for key in ("resnet_binary_28x28", "resnet_color_32x32"):
+        assert EncoderCore.by_name(key) is not None and Decoder.by_name(key) is not None
+    assert Decoder.by_name("pixelcnn_binary_28x28") is not None and Flow.by_name("af_made") is not None
