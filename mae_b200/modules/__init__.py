@@ -4,12 +4,16 @@ from .flow import Flow
 from .encoder import Encoder, EncoderCore, GaussianEncoder
 from .decoder import Decoder, BinaryImageDecoder, ColorImageDecoder
 from . import networks
-from .zoo import (AFMADE, PixelCNNDecoderBinaryImage28x28, ResnetDecoderBinaryImage28x28, ResnetDecoderColorImage32x32,
-                  ResnetEncoderCoreBinaryImage28x28, ResnetEncoderCoreColorImage32x32)
+from .zoo import (AF2dMADE, AFMADE, DenseNetEncoderCoreColorImage32x32, DenseNetEncoderCoreColorImage64x64,
+                  PixelCNNDecoderBinaryImage28x28, PixelCNNPPDecoderColorImage32x32, PixelCNNPPDecoderColorImage64x64,
+                  ResnetDecoderBinaryImage28x28, ResnetDecoderColorImage32x32, ResnetEncoderCoreBinaryImage28x28,
+                  ResnetEncoderCoreColorImage32x32)
 from .mae import MAE
 from .utils import exponentialMovingAverage, logsumexp
 
 __all__ = ["MAE", "Encoder", "EncoderCore", "GaussianEncoder", "Flow", "Decoder", "BinaryImageDecoder",
            "ColorImageDecoder", "exponentialMovingAverage", "logsumexp", "networks", "AFMADE",
            "PixelCNNDecoderBinaryImage28x28", "ResnetDecoderBinaryImage28x28", "ResnetDecoderColorImage32x32",
-           "ResnetEncoderCoreBinaryImage28x28", "ResnetEncoderCoreColorImage32x32"]
+           "ResnetEncoderCoreBinaryImage28x28", "ResnetEncoderCoreColorImage32x32", "AF2dMADE",
+           "DenseNetEncoderCoreColorImage32x32", "DenseNetEncoderCoreColorImage64x64", "PixelCNNPPDecoderColorImage32x32",
+           "PixelCNNPPDecoderColorImage64x64"]

@@ -109,9 +109,10 @@ class ColorImageDecoder(Decoder):
         coeffs = output[:, (nc * 2 + 1) * nmix:(nc * 2 + 4) * nmix].view(batch, nmix, nc, H, W)
         return mu, log_scale.clamp(min=-7.), F.log_softmax(logit_probs, dim=1), coeffs.tanh()
 
-    def decode(self, z, random_sample):
-        """Reference: color_image_decoder.py:71-88 + utils.py:127-160 (sampling; not on the hot path)."""
-        mu, log_scale, logit_probs, coeffs = self.execute(z, None)
+    @staticmethod
+    def sample_pixels(mu, log_scale, logit_probs, coeffs, random_sample):
+        """Most probable component per pixel, logistic noise if ``random_sample``, colour coupling, clamp to [-1, 1]
+        -> [B, 3, H, W].  Reference: utils.py:127-160 (sampling; not on the hot path)."""
         index = logit_probs.argmax(dim=1, keepdim=True).unsqueeze(2).expand(-1, 1, mu.size(2), -1, -1)
         mu = mu.gather(1, index).squeeze(1)
         log_scale = log_scale.gather(1, index).squeeze(1)
@@ -123,7 +124,11 @@ class ColorImageDecoder(Decoder):
         x0 = x[:, 0].clamp(min=-1., max=1.)
         x1 = (x[:, 1] + coeffs[:, 0] * x0).clamp(min=-1., max=1.)
         x2 = (x[:, 2] + coeffs[:, 1] * x0 + coeffs[:, 2] * x1).clamp(min=-1., max=1.)
-        return torch.stack([x0, x1, x2], dim=1), None
+        return torch.stack([x0, x1, x2], dim=1)
+
+    def decode(self, z, random_sample):
+        """Reference: color_image_decoder.py:71-88 (decoders that do not condition on x)."""
+        return self.sample_pixels(*self.execute(z, None), random_sample), None
 
     likelihood_kind = "dmol"
 

@@ -10,7 +10,9 @@ files load with ``strict=True``:
   networks/resnet.py:23-154                               ``main.<i>.{conv1, conv2, downsample}`` / ``{deconv1, deconv2, downsample}``
   networks/masked.py:15-212                               ``{weight_v, weight_g (log scale), bias, mask}``
   networks/auto_regressives/pixelcnn.py:8-105             ``main.<i>.main.<j>``, ``direct_connects.<i>.main.<j>``
-  networks/auto_regressives/made.py:8-60                  ``input_layer, direct_connect, hidden_layers.<i>, output_layer``
+  networks/auto_regressives/made.py:8-121                 ``input_layer|top_layer, direct_connect, hidden_layers.<i>, output_layer``
+  networks/dense.py:13-54                                 ``main.block<i>.main.<j>``
+  networks/auto_regressives/pixelcnnpp.py:21-338          ``up_layers, down_layers, nins1, nins2, up_hs, down_hs``
 
 Differences in mechanism (not in function): weight normalisation is evaluated explicitly in ``forward`` instead of through
 ``torch.nn.utils.weight_norm`` hooks, and masks are applied functionally (``weight_v * mask``) instead of overwriting
@@ -28,7 +30,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 __all__ = ["LinearWeightNorm", "Conv2dWeightNorm", "ConvTranspose2dWeightNorm", "ResNet", "DeResNet", "MaskedLinear",
-           "MaskedConv2d", "PixelCNN", "MADE", "ReShape"]
+           "MaskedConv2d", "PixelCNN", "MADE", "ReShape", "DenseNet", "PixelCNNPP", "MADE2d"]
 
 _INIT_STD = 0.05
 _STD_FLOOR = 1e-6
@@ -472,3 +474,370 @@ class ReShape(nn.Module):
 
     def forward(self, input):
         return input.view(input.size(0), *self.out_shape)
+
+
+# ---------------------------------------------------------------------------------------------------- DenseNet
+class DenseNetBlock(nn.Module):
+    """x -> cat[x, conv3x3(ELU(conv1x1(x)))] with a 4*growth bottleneck (dense.py:13-32)."""
+
+    def __init__(self, inplanes, growth_rate):
+        super().__init__()
+        self.main = nn.Sequential(
+            Conv2dWeightNorm(inplanes, 4 * growth_rate, 1),
+            nn.ELU(),
+            Conv2dWeightNorm(4 * growth_rate, growth_rate, 3, padding=1),
+        )
+
+    def forward(self, x):
+        return torch.cat([x, self.main(x)], dim=1)
+
+    def initialize(self, x, init_scale=1.0):
+        return torch.cat([x, _run(self.main, x, True, init_scale)], dim=1)
+
+
+class DenseNet(nn.Module):
+    """``steps`` dense blocks, each followed by an ELU; channels grow by ``growth_rate`` per step (dense.py:35-54)."""
+
+    def __init__(self, inplanes, growth_rate, steps):
+        super().__init__()
+        from collections import OrderedDict
+        layers = OrderedDict()
+        for step in range(steps):
+            layers['block%d' % step] = DenseNetBlock(inplanes + step * growth_rate, growth_rate)
+            layers['activation%d' % step] = nn.ELU()
+        self.main = nn.Sequential(layers)
+
+    def forward(self, x):
+        return self.main(x)
+
+    def initialize(self, x, init_scale=1.0):
+        return _run(self.main, x, True, init_scale)
+
+
+# ------------------------------------------------------------------------------------------ PixelCNN++ layers
+class DownShiftConv2d(Conv2dWeightNorm):
+    """Convolution that only sees rows at or above the output row: pad kh-1 rows on top, (kw-1)/2 columns on both sides
+    (masked.py:215-227; Salimans et al. 2017)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=(1, 1), bias=True):
+        kh, kw = kernel_size
+        super().__init__(in_channels, out_channels, (kh, kw), stride=tuple(stride), bias=bias)
+        self.shift_padding = ((kw - 1) // 2, (kw - 1) // 2, kh - 1, 0)     # left, right, top, bottom
+
+    def forward(self, input):
+        return self._conv(F.pad(input, self.shift_padding))
+
+
+class DownRightShiftConv2d(DownShiftConv2d):
+    """... and only columns at or left of the output column: pad kw-1 columns on the left (masked.py:230-237)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=(1, 1), bias=True):
+        super().__init__(in_channels, out_channels, kernel_size, stride=stride, bias=bias)
+        kh, kw = kernel_size
+        self.shift_padding = (kw - 1, 0, kh - 1, 0)
+
+
+class DownShiftConvTranspose2d(ConvTranspose2dWeightNorm):
+    """Transposed counterpart: full transposed convolution, then drop the last kh-1 rows and (kw-1)/2 columns on both
+    sides (masked.py:240-255)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=(1, 1), bias=True):
+        kh, kw = kernel_size
+        super().__init__(in_channels, out_channels, (kh, kw), stride=tuple(stride),
+                         output_padding=(stride[0] - 1, stride[1] - 1), bias=bias)
+        self.crop = (kh - 1, (kw - 1) // 2, (kw - 1) // 2)       # rows at the bottom, columns left, columns right
+
+    def forward(self, input):
+        out = self._deconv(input)
+        bottom, left, right = self.crop
+        return out[:, :, :out.size(2) - bottom, left:out.size(3) - right]
+
+
+class DownRightShiftConvTranspose2d(DownShiftConvTranspose2d):
+    def __init__(self, in_channels, out_channels, kernel_size, stride=(1, 1), bias=True):
+        super().__init__(in_channels, out_channels, kernel_size, stride=stride, bias=bias)
+        kh, kw = kernel_size
+        self.crop = (kh - 1, 0, kw - 1)
+
+
+def concat_elu(x, dim=1):
+    """ELU of [x, -x] (Shang et al. 2016 with ELU): doubles the channels."""
+    return F.elu(torch.cat([x, -x], dim=dim))
+
+
+def _call(layer, init, init_scale, *args, **kwargs):
+    return layer.initialize(*args, init_scale=init_scale, **kwargs) if init else layer(*args, **kwargs)
+
+
+class GatedResnetBlock(nn.Module):
+    """One residual step of both PixelCNN++ streams (pixelcnnpp.py:21-103): the vertical stream x1 (down-shifted
+    convolutions) and the horizontal stream x2 (down-right-shifted, fed by x1 through a 1x1 ``nin``); gated output
+    ``a * sigmoid(b)``; optional conditioning h enters both gates through two 3x3 convolutions."""
+
+    def __init__(self, in_channels, h_channels=0, dropout=0.0, activation=concat_elu):
+        super().__init__()
+        gain = 2 if activation is concat_elu else 1
+        c = in_channels
+        self.activation = activation
+        self.down_conv1 = DownShiftConv2d(gain * c, c, (2, 3))
+        self.down_conv2 = DownShiftConv2d(gain * c, c, (2, 3))
+        self.down_conv3 = DownShiftConv2d(gain * c, 2 * c, (2, 3))
+        self.down_right_conv1 = DownRightShiftConv2d(gain * c, c, (2, 2))
+        self.down_right_conv2 = DownRightShiftConv2d(gain * c, c, (2, 2))
+        self.nin = Conv2dWeightNorm(gain * c, c, (1, 1))
+        self.down_right_conv3 = DownRightShiftConv2d(gain * c, 2 * c, (2, 2))
+        self.h_conv1 = Conv2dWeightNorm(gain * h_channels, c, (3, 3), padding=1) if h_channels else None
+        self.h_conv2 = Conv2dWeightNorm(gain * c, 2 * c, (3, 3), padding=1) if h_channels else None
+        self.dropout = nn.Dropout(p=dropout)
+
+    def _pass(self, x1, x2, h, init, s):
+        act = self.activation
+        hc = 0
+        if h is not None:
+            hc = _call(self.h_conv1, init, s, act(h))
+            hc = _call(self.h_conv2, init, 0.1 * s, act(hc))
+
+        def gate(t, skip):
+            a, b = (t + hc).chunk(2, 1)
+            return a * torch.sigmoid(b) + skip
+
+        c1 = _call(self.down_conv1, init, s, act(x1))
+        c1 = _call(self.down_conv2, init, s, act(c1))
+        c1 = gate(_call(self.down_conv3, init, 0.1 * s, self.dropout(act(c1))), x1)
+        aux = _call(self.nin, init, s, act(c1))
+        c2 = _call(self.down_right_conv1, init, s, act(x2))
+        c2 = _call(self.down_right_conv2, init, s, act(c2))
+        c2 = gate(_call(self.down_right_conv3, init, 0.1 * s, self.dropout(act(c2 + aux))), x2)
+        return c1, c2
+
+    def forward(self, x1, x2, h=None):
+        return self._pass(x1, x2, h, False, 1.0)
+
+    def initialize(self, x1, x2, h=None, init_scale=1.0):
+        return self._pass(x1, x2, h, True, init_scale)
+
+
+def _shift_down(t):
+    return F.pad(t, (0, 0, 1, 0))[:, :, :-1, :]
+
+
+def _shift_right(t):
+    return F.pad(t, (1, 0, 0, 0))[:, :, :, :-1]
+
+
+class TopShiftBlock(nn.Module):
+    """Entry of the two streams: shifted convolutions of the image so that neither stream sees the current pixel
+    (pixelcnnpp.py:106-135)."""
+
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.down_conv1 = DownShiftConv2d(in_channels, out_channels, (2, 3))
+        self.down_conv2 = DownShiftConv2d(in_channels, out_channels, (1, 3))
+        self.down_right_conv = DownRightShiftConv2d(in_channels, out_channels, (2, 1))
+
+    def _pass(self, x, init, s):
+        x1 = _shift_down(_call(self.down_conv1, init, s, x))
+        x2 = _shift_down(_call(self.down_conv2, init, s, x)) + _shift_right(_call(self.down_right_conv, init, s, x))
+        return x1, x2
+
+    def forward(self, input):
+        return self._pass(input, False, 1.0)
+
+    def initialize(self, x, init_scale=1.0):
+        return self._pass(x, True, init_scale)
+
+
+class _StreamPair(nn.Module):
+    """Applies one layer per stream (strided down-sampling or transposed up-sampling of both streams)."""
+    first: str
+    second: str
+
+    def _pass(self, x1, x2, init, s):
+        return _call(getattr(self, self.first), init, s, x1), _call(getattr(self, self.second), init, s, x2)
+
+    def forward(self, x1, x2, h=None):
+        return self._pass(x1, x2, False, 1.0)
+
+    def initialize(self, x1, x2, h=None, init_scale=1.0):
+        return self._pass(x1, x2, True, init_scale)
+
+
+class DownSamplingBlock(_StreamPair):
+    first, second = 'down_conv', 'down_right_conv'
+
+    def __init__(self, num_filters):
+        super().__init__()
+        self.down_conv = DownShiftConv2d(num_filters, num_filters, (2, 3), stride=(2, 2))
+        self.down_right_conv = DownRightShiftConv2d(num_filters, num_filters, (2, 2), stride=(2, 2))
+
+
+class UpSamplingBlock(_StreamPair):
+    first, second = 'down_deconv', 'down_right_deconv'
+
+    def __init__(self, num_filters):
+        super().__init__()
+        self.down_deconv = DownShiftConvTranspose2d(num_filters, num_filters, (2, 3), stride=(2, 2))
+        self.down_right_deconv = DownRightShiftConvTranspose2d(num_filters, num_filters, (2, 2), stride=(2, 2))
+
+
+class NINBlock(nn.Module):
+    """x + conv1x1(act(residual)): merges a stored up-pass activation into the down pass."""
+
+    def __init__(self, num_filters, activation=concat_elu):
+        super().__init__()
+        self.activation = activation
+        self.nin = Conv2dWeightNorm((2 if activation is concat_elu else 1) * num_filters, num_filters, (1, 1))
+
+    def forward(self, x, residual):
+        return x + self.nin(self.activation(residual))
+
+    def initialize(self, x, residual, init_scale=1.0):
+        return x + self.nin.initialize(self.activation(residual), init_scale=init_scale)
+
+
+class Identity(nn.Module):
+    def forward(self, input):
+        return input
+
+    def initialize(self, x, init_scale=1.0):
+        return x
+
+
+class DownSampling(nn.Module):
+    """conditioning h: stride-2 convolution doubling the channels"""
+
+    def __init__(self, num_filters):
+        super().__init__()
+        self.conv = Conv2dWeightNorm(num_filters, num_filters * 2, (3, 3), stride=(2, 2), padding=1)
+
+    def forward(self, x):
+        return self.conv(x)
+
+    def initialize(self, x, init_scale=1.0):
+        return self.conv.initialize(x, init_scale=init_scale)
+
+
+class UpSampling(nn.Module):
+    """conditioning h: stride-2 transposed convolution halving the channels"""
+
+    def __init__(self, num_filters):
+        super().__init__()
+        self.deconv = ConvTranspose2dWeightNorm(num_filters, num_filters // 2, (3, 3), stride=(2, 2), padding=1, output_padding=1)
+
+    def forward(self, x):
+        return self.deconv(x)
+
+    def initialize(self, x, init_scale=1.0):
+        return self.deconv.initialize(x, init_scale=init_scale)
+
+
+class PixelCNNPP(nn.Module):
+    """PixelCNN++ trunk (Salimans et al. 2017; pixelcnnpp.py:205-338): an "up" pass of ``levels`` resolutions with
+    ``num_resnets`` gated blocks each (down-sampling in between), then a mirrored "down" pass that pops the stored
+    up-pass activations through 1x1 ``nins``; the conditioning map h is down/up-sampled alongside.  Returns the
+    horizontal stream [B, out_channels, H, W]."""
+
+    def __init__(self, levels, in_channels, out_channels, num_resnets, h_channels=0, dropout=0.0, activation='concat_elu'):
+        super().__init__()
+        if activation not in ('elu', 'concat_elu'):
+            raise ValueError('unknown activation %s' % activation)
+        act = F.elu if activation == 'elu' else concat_elu
+        hc = h_channels
+        up_layers, up_hs, nins1, nins2 = [], [], [], []
+        for level in range(levels):
+            if level == 0:
+                up_layers.append(TopShiftBlock(in_channels, out_channels))
+                up_hs.append(Identity())
+            else:
+                up_layers.append(DownSamplingBlock(out_channels))
+                nins1.append(NINBlock(out_channels, act))
+                nins2.append(NINBlock(out_channels, act))
+                up_hs.append(DownSampling(hc) if hc else Identity())
+                hc *= 2
+            for _ in range(num_resnets):
+                up_layers.append(GatedResnetBlock(out_channels, hc, dropout, act))
+                nins1.append(NINBlock(out_channels, act))
+                nins2.append(NINBlock(out_channels, act))
+                up_hs.append(Identity())
+        down_layers, down_hs = [], []
+        for level in range(levels):
+            for _ in range(num_resnets):
+                down_layers.append(GatedResnetBlock(out_channels, hc, dropout, act))
+                down_hs.append(Identity())
+            if level < levels - 1:
+                down_layers.append(UpSamplingBlock(out_channels))
+                down_hs.append(UpSampling(hc) if hc else Identity())
+                hc //= 2
+        if not (len(nins1) == len(down_layers) and len(up_hs) == len(up_layers) and hc == h_channels):
+            raise RuntimeError('PixelCNN++ layer bookkeeping is inconsistent')
+        self.up_layers = nn.ModuleList(up_layers)
+        self.down_layers = nn.ModuleList(down_layers)
+        self.nins1 = nn.ModuleList(nins1)
+        self.nins2 = nn.ModuleList(nins2)
+        self.up_hs = nn.ModuleList(up_hs)
+        self.down_hs = nn.ModuleList(down_hs)
+
+    def _pass(self, x, h, init, s):
+        stack = []
+        x1 = x2 = None
+        for i, (layer, h_layer) in enumerate(zip(self.up_layers, self.up_hs)):
+            if i == 0:
+                x1, x2 = _call(layer, init, s, x)
+            else:
+                x1, x2 = _call(layer, init, s, x1, x2, h=h)
+                stack.append((x1, x2))
+            h = _call(h_layer, init, s, h)
+        for i, (layer, h_layer, nin1, nin2) in enumerate(zip(self.down_layers, self.down_hs, self.nins1, self.nins2)):
+            u1, u2 = stack.pop()
+            if i == 0:
+                x1, x2 = u1, u2
+            else:
+                x1 = _call(nin1, init, s, x1, u1)
+                x2 = _call(nin2, init, s, x2, u2)
+            x1, x2 = _call(layer, init, s, x1, x2, h)
+            h = _call(h_layer, init, s, h)
+        if stack:
+            raise RuntimeError('unbalanced up / down pass')
+        return x2
+
+    def forward(self, input, h=None):
+        return self._pass(input, h, False, 1.0)
+
+    def initialize(self, x, h=None, init_scale=1.0):
+        return self._pass(x, h, True, init_scale)
+
+
+# ------------------------------------------------------------------------------------------------------ MADE2d
+class MADE2d(nn.Module):
+    """Convolutional MADE over [C, H, W] in raster order (made.py:63-121): type-A masked convolution in, residual type-B
+    masked hidden layers, type-B output layer, plus a type-A masked direct connection; ReLU units."""
+
+    def __init__(self, in_channels, kernel_size, num_hiddens, hidden_channels, hidden_kernels, order, bias=True):
+        super().__init__()
+        if num_hiddens < 1 or num_hiddens != len(hidden_kernels):
+            raise ValueError('one kernel per hidden layer')
+        pair = nn.modules.utils._pair
+        pad = lambda k: (pair(k)[0] // 2, pair(k)[1] // 2)    # noqa: E731
+        self.activation = nn.ReLU()
+        self.top_layer = MaskedConv2d(in_channels, hidden_channels, kernel_size, mask_type='A', order=order,
+                                      padding=pad(kernel_size), bias=bias)
+        self.direct_connect = MaskedConv2d(in_channels, in_channels, kernel_size, mask_type='A', order=order,
+                                           padding=pad(kernel_size), bias=bias)
+        self.hidden_layers = nn.ModuleList([
+            MaskedConv2d(hidden_channels, hidden_channels, pair(k), mask_type='B', order=order, padding=pad(k), bias=bias)
+            for k in hidden_kernels[:num_hiddens - 1]])
+        k_out = hidden_kernels[-1]
+        self.output_layer = MaskedConv2d(hidden_channels, in_channels, pair(k_out), mask_type='B', order=order,
+                                         padding=pad(k_out), bias=bias)
+
+    def _pass(self, x, init, s):
+        h = self.activation(_call(self.top_layer, init, s, x))
+        for layer in self.hidden_layers:
+            h = self.activation(_call(layer, init, s, h) + h)
+        return _call(self.output_layer, init, s, h) + _call(self.direct_connect, init, s, x)
+
+    def forward(self, x):
+        return self._pass(x, False, 1.0)
+
+    def initialize(self, x, init_scale=1.0):
+        return self._pass(x, True, init_scale)

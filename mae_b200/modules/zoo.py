@@ -5,7 +5,9 @@ and its checkpoints load with ``strict=True``.  Registry keys as in the referenc
   EncoderCore  'resnet_binary_28x28'   encoder_cores/resnet.py:13-51     'resnet_color_32x32'  encoder_cores/resnet.py:54-111
   Decoder      'resnet_binary_28x28'   image_decoders/resnet.py:12-55    'resnet_color_32x32'  image_decoders/resnet.py:58-121
                'pixelcnn_binary_28x28' image_decoders/pixelcnn.py:22-163
-  Flow         'af_made'               flows/af/made.py:12-123
+               'pixelcnn++_color_32x32' / '_64x64'  image_decoders/pixelcnnpp.py:54-170
+  EncoderCore  'densenet_color_32x32' / '_64x64'    encoder_cores/densenet.py:13-112
+  Flow         'af_made'               flows/af/made.py:12-123           'af2d_made'  flows/af/made2d.py:12-131
 
 Everything here is ordinary PyTorch; the loss / evaluation arithmetic behind these stacks is the CUDA path
 (``BinaryImageDecoder`` / ``ColorImageDecoder`` / ``GaussianEncoder`` in this package)."""
@@ -20,11 +22,13 @@ import torch.nn.functional as F
 from .decoder import BinaryImageDecoder, ColorImageDecoder
 from .encoder import EncoderCore
 from .flow import Flow
-from .networks import (MADE, Conv2dWeightNorm, ConvTranspose2dWeightNorm, DeResNet, LinearWeightNorm, PixelCNN, ReShape,
-                       ResNet, _run)
+from .networks import (MADE, MADE2d, Conv2dWeightNorm, ConvTranspose2dWeightNorm, DenseNet, DeResNet, LinearWeightNorm,
+                       PixelCNN, PixelCNNPP, ReShape, ResNet, _call, _run)
 
 __all__ = ["ResnetEncoderCoreBinaryImage28x28", "ResnetEncoderCoreColorImage32x32", "ResnetDecoderBinaryImage28x28",
-           "ResnetDecoderColorImage32x32", "PixelCNNDecoderBinaryImage28x28", "AFMADE"]
+           "ResnetDecoderColorImage32x32", "PixelCNNDecoderBinaryImage28x28", "AFMADE", "DenseNetEncoderCoreColorImage32x32",
+           "DenseNetEncoderCoreColorImage64x64", "PixelCNNPPDecoderColorImage32x32", "PixelCNNPPDecoderColorImage64x64",
+           "AF2dMADE"]
 
 
 def _unwrap(m):
@@ -330,9 +334,204 @@ class AFMADE(Flow):
         return cls(**params)
 
 
+# ------------------------------------------------------------------- colour configuration (color_image32x32.json)
+class DenseNetEncoderCoreColorImage32x32(EncoderCore):
+    """32x32x3 -> (mu, hardtanh(logvar, -7, 7)) [B, z_channels, 8, 8] through three dense stages."""
+
+    def __init__(self, z_channels):
+        super().__init__()
+        self.z_channels, self.H, self.W, self.nc = z_channels, 8, 8, 3
+        self.main = nn.Sequential(*self._stages(z_channels))
+
+    def _stages(self, z_channels):
+        return [
+            DenseNet(self.nc, 15, 3),                    # 48 x 32 x 32
+            Conv2dWeightNorm(48, 48, 3, 2, 1), nn.ELU(),  # 48 x 16 x 16
+            DenseNet(48, 16, 3),                         # 96 x 16 x 16
+            Conv2dWeightNorm(96, 96, 3, 2, 1), nn.ELU(),  # 96 x 8 x 8
+            DenseNet(96, 16, 6),                         # 192 x 8 x 8
+            Conv2dWeightNorm(192, 96, 1, 1), nn.ELU(),
+            Conv2dWeightNorm(96, 2 * z_channels, 1, 1),
+        ]
+
+    def _split(self, out):
+        mu, logvar = out.chunk(2, 1)
+        return mu, F.hardtanh(logvar, min_val=-7., max_val=7.)
+
+    def forward(self, input):
+        return self._split(self.main(input))
+
+    def initialize(self, x, init_scale=1.0):
+        return self._split(_run(self.main, x, True, init_scale))
+
+    def output_size(self) -> Tuple:
+        return self.z_channels, self.H, self.W
+
+    @classmethod
+    def from_params(cls, params: Dict):
+        return cls(**params)
+
+
+class DenseNetEncoderCoreColorImage64x64(DenseNetEncoderCoreColorImage32x32):
+    """64x64x3 variant: one more stride-2 stage."""
+
+    def _stages(self, z_channels):
+        return [
+            DenseNet(self.nc, 15, 3),                      # 48 x 64 x 64
+            Conv2dWeightNorm(48, 48, 3, 2, 1), nn.ELU(),    # 48 x 32 x 32
+            DenseNet(48, 16, 3),                           # 96 x 32 x 32
+            Conv2dWeightNorm(96, 96, 3, 2, 1), nn.ELU(),    # 96 x 16 x 16
+            DenseNet(96, 16, 3),                           # 144 x 16 x 16
+            Conv2dWeightNorm(144, 144, 3, 2, 1), nn.ELU(),  # 144 x 8 x 8
+            DenseNet(144, 16, 3),                          # 192 x 8 x 8
+            Conv2dWeightNorm(192, 96, 1, 1), nn.ELU(),
+            Conv2dWeightNorm(96, 2 * z_channels, 1, 1),
+        ]
+
+
+class _PixelCNNPPCore(nn.Module):
+    """z [B, zc, 8, 8] -> conditioning map h at image resolution (transposed convolutions), PixelCNN++ trunk over
+    (x, h), two 1x1 convolutions to the 10*nmix raw mixture parameters the likelihood kernel reads."""
+
+    def __init__(self, nc, z_channels, h_channels, hidden_channels, levels, num_resnets, nmix, dropout=0., activation='concat_elu'):
+        super().__init__()
+        from collections import OrderedDict
+        layers, c = OrderedDict(), z_channels
+        for i in range(levels - 1):
+            layers['level%d' % i] = ConvTranspose2dWeightNorm(c, c // 2, 3, 2, 1, 1)
+            layers['elu%d' % i] = nn.ELU()
+            c //= 2
+        layers['h_level'] = Conv2dWeightNorm(c, h_channels, 1)
+        self.z_transform = nn.Sequential(layers)
+        self.core = PixelCNNPP(levels, nc, hidden_channels, num_resnets, h_channels, dropout=dropout, activation=activation)
+        self.output = nn.Sequential(
+            nn.ELU(),
+            Conv2dWeightNorm(hidden_channels, hidden_channels, 1),
+            nn.ELU(),
+            Conv2dWeightNorm(hidden_channels, (nc * 3 + 1) * nmix, 1),
+        )
+
+    def _pass(self, x, z, init, s):
+        h = _run(self.z_transform, z, init, s)
+        return _run(self.output, _call(self.core, init, s, x, h=h), init, s)
+
+    def forward(self, x, z):
+        return self._pass(x, z, False, 1.0)
+
+    def initialize(self, x, z, init_scale=1.0):
+        return self._pass(x, z, True, init_scale)
+
+
+class PixelCNNPPDecoderColorImage32x32(ColorImageDecoder):
+    """PixelCNN++ decoder of the CIFAR configuration: raw [B, 10*nmix, 32, 32] from (x, z)."""
+
+    _GEOMETRY = dict(image_size=32, levels=3, hidden_channels=96, num_resnets=6)
+
+    def __init__(self, z_channels, h_channels, nmix, dropout=0., activation='elu', ngpu=1):
+        super().__init__(nmix, ngpu=ngpu)
+        g = self._GEOMETRY
+        self.z_channels, self.H, self.W, self.image_size = z_channels, 8, 8, g['image_size']
+        self.core = _replicate(_PixelCNNPPCore(self.nc, z_channels, h_channels, g['hidden_channels'], g['levels'],
+                                               g['num_resnets'], nmix, dropout=dropout, activation=activation), ngpu)
+
+    def z_shape(self) -> Tuple:
+        return self.z_channels, self.H, self.W
+
+    def output_size(self) -> Tuple:
+        return self.nc, self.image_size, self.image_size
+
+    def forward(self, x, z):
+        return self.core(x, z)
+
+    def decode(self, z, random_sample):
+        """Ancestral sampling, one pixel per network evaluation (image_decoders/pixelcnnpp.py:101-123)."""
+        side = self.image_size
+        x = z.new_zeros(z.size(0), self.nc, side, side)
+        for i in range(side):
+            for j in range(side):
+                x[:, :, i, j] = self.sample_pixels(*self.execute(z, x), random_sample)[:, :, i, j]
+        return x, None
+
+    def initialize(self, x, z, init_scale=1.0):
+        return _unwrap(self.core).initialize(x, z, init_scale=init_scale)
+
+    @classmethod
+    def from_params(cls, params: Dict):
+        return cls(**params)
+
+
+class PixelCNNPPDecoderColorImage64x64(PixelCNNPPDecoderColorImage32x32):
+    _GEOMETRY = dict(image_size=64, levels=4, hidden_channels=64, num_resnets=4)
+
+
+class AF2dMADEBlock(nn.Module):
+    """Autoregressive affine layer over [C, H, W] in raster order (flows/af/made2d.py:12-62); see AFMADEBlock."""
+
+    def __init__(self, in_channels, kernel_size, num_hiddens, hidden_channels, hidden_kernels, order, bias=True, var=True):
+        super().__init__()
+        self.order = order
+        args = (in_channels, kernel_size, num_hiddens, hidden_channels, hidden_kernels, order)
+        self.mu = MADE2d(*args, bias=bias)
+        self.logvar = MADE2d(*args, bias=bias) if var else None
+
+    def _affine(self, y, init, init_scale):
+        mu = _run([self.mu], y, init, init_scale)
+        logstd = _run([self.logvar], y, init, init_scale) * 0.5 if self.logvar is not None else torch.zeros_like(mu)
+        return mu, logstd
+
+    def backward(self, y):
+        mu, logstd = self._affine(y, False, 1.0)
+        return mu + y * logstd.exp(), logstd.flatten(1).sum(dim=1)
+
+    def initialize(self, y, init_scale=1.0):
+        mu, logstd = self._affine(y, True, init_scale)
+        return mu + y * logstd.exp(), logstd.flatten(1).sum(dim=1)
+
+    def forward(self, x):
+        eps = 1e-12
+        y, logstd = torch.zeros_like(x), torch.zeros_like(x)
+        rows, cols = list(range(x.size(2))), list(range(x.size(3)))
+        if self.order == 'B':
+            rows, cols = rows[::-1], cols[::-1]
+        for i in rows:
+            for j in cols:      # position (i, j) of (mu, logstd) only depends on the positions already solved
+                mu, logstd = self._affine(y, False, 1.0)
+                y[:, :, i, j] = ((x - mu) / (logstd.exp() + eps))[:, :, i, j]
+        return y, logstd.flatten(1).sum(dim=1)
+
+
+class AF2dMADEDualBlock(AFMADEDualBlock):
+    def __init__(self, in_channels, kernel_size, num_hiddens, hidden_channels, hidden_kernels, bias=True, var=True):
+        nn.Module.__init__(self)
+        args = (in_channels, kernel_size, num_hiddens, hidden_channels, hidden_kernels)
+        self.fwd = AF2dMADEBlock(*args, 'A', bias=bias, var=var)
+        self.bwd = AF2dMADEBlock(*args, 'B', bias=bias, var=var)
+
+
+class AF2dMADE(AFMADE):
+    """Prior flow of the colour configurations over z [C, 8, 8] (flows/af/made2d.py:88-131)."""
+
+    def __init__(self, in_channels, height, width, num_blocks, kernel_size, num_hiddens=1, hidden_channels=None,
+                 hidden_kernels=None, bias=True, var=True):
+        Flow.__init__(self)
+        self._input_shape = (in_channels, height, width)
+        hidden_channels = in_channels * 8 if hidden_channels is None else hidden_channels
+        hidden_kernels = [kernel_size] * num_hiddens if hidden_kernels is None else hidden_kernels
+        self.blocks = nn.ModuleList([AF2dMADEDualBlock(in_channels, kernel_size, num_hiddens, hidden_channels, hidden_kernels,
+                                                       bias=bias, var=var) for _ in range(num_blocks)])
+
+    def input_size(self) -> Tuple:
+        return self._input_shape
+
+
 ResnetEncoderCoreBinaryImage28x28.register('resnet_binary_28x28')
 ResnetEncoderCoreColorImage32x32.register('resnet_color_32x32')
 ResnetDecoderBinaryImage28x28.register('resnet_binary_28x28')
 ResnetDecoderColorImage32x32.register('resnet_color_32x32')
 PixelCNNDecoderBinaryImage28x28.register('pixelcnn_binary_28x28')
 AFMADE.register('af_made')
+DenseNetEncoderCoreColorImage32x32.register('densenet_color_32x32')
+DenseNetEncoderCoreColorImage64x64.register('densenet_color_64x64')
+PixelCNNPPDecoderColorImage32x32.register('pixelcnn++_color_32x32')
+PixelCNNPPDecoderColorImage64x64.register('pixelcnn++_color_64x64')
+AF2dMADE.register('af2d_made')

@@ -129,9 +129,16 @@ def main():
     xb_init = (torch.rand(16, 1, 28, 28) < 0.3).float()
     xc = torch.randint(0, 256, (4, 3, 32, 32)).float() / 127.5 - 1.0
     xc_init = torch.randint(0, 256, (8, 3, 32, 32)).float() / 127.5 - 1.0
+    # the shipped CIFAR configuration (DenseNet core, AF2d-MADE prior flow, PixelCNN++ decoder); only the replica count
+    # (2 GPUs -> 1: DataParallel adds a "module." key level and needs 2 devices) and the dropout rate (0.5 -> 0: the
+    # training-mode loss must be deterministic) are changed
+    color = json.load(open("/root/reference/experiments/configs/color_image32x32.json"))
+    color["encoder"]["ngpu"] = color["decoder"]["ngpu"] = 1
+    color["decoder"]["dropout"] = 0.0
     fixtures = {
         "binary_image_json": run_model(binary, xb, xb_init, ns=2, k=4, eta=1.0, gamma=0.5, free_bits=0.0),
         "color_resnet": run_model(COLOR_RESNET, xc, xc_init, ns=2, k=3, eta=0.5, gamma=1.0, free_bits=0.0),
+        "color_image32x32_json": run_model(color, xc[:3], xc_init[:4], ns=1, k=2, eta=1.0, gamma=1.0, free_bits=0.0),
     }
     path = os.path.join(HERE, "models.pt")
     torch.save(fixtures, path)

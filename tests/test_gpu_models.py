@@ -3,7 +3,8 @@ against the LIVE reference's loss 7-tuple, parameter gradients and importance-we
 tests/golden/make_golden_models.py with name-keyed weights and injected noise).  binary_image_json = the shipped
 binary_image.json (ResNet core, AF-MADE prior flow -> Monte-Carlo KL branch, PixelCNN decoder -> Bernoulli kernel);
 color_resnet = ResNet core/decoder without flows (analytic-KL branch: encode_head/loss_head nodes at D = 128 fall back to
-the general MPD kernels, DMOL kernel on the raw conv output)."""
+the general MPD kernels, DMOL kernel on the raw conv output); color_image32x32_json = the shipped color_image32x32.json
+(DenseNet core, AF2d-MADE prior flow, PixelCNN++ decoder, D = 1024) with one replica and dropout 0."""
 import copy
 
 import pytest
@@ -33,7 +34,7 @@ def _no_tf32():
     torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
 
 
-@pytest.mark.parametrize("name", ["binary_image_json", "color_resnet"])
+@pytest.mark.parametrize("name", ["binary_image_json", "color_resnet", "color_image32x32_json"])
 def test_full_model_loss_grads_and_nll_match_reference(fixtures, name, monkeypatch):
     from mae_b200 import synth
     from mae_b200.modules import MAE, GaussianEncoder

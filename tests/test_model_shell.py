@@ -25,7 +25,10 @@ def _ours(c):
     return synth.fill_state(MAE.from_params(copy.deepcopy(c["params"])))
 
 
-@pytest.mark.parametrize("name", ["binary_image_json", "color_resnet"])
+ALL = ["binary_image_json", "color_resnet", "color_image32x32_json"]
+
+
+@pytest.mark.parametrize("name", ALL)
 def test_state_dict_identity_with_reference(fixtures, name):
     c = fixtures[name]
     model = MAE.from_params(copy.deepcopy(c["params"]))
@@ -39,7 +42,7 @@ def test_state_dict_identity_with_reference(fixtures, name):
     model.load_state_dict({n: torch.zeros(s) for n, s in c["keys"].items()}, strict=True)
 
 
-@pytest.mark.parametrize("name", ["binary_image_json", "color_resnet"])
+@pytest.mark.parametrize("name", ALL)
 def test_encoder_core_and_flow_forward(fixtures, name):
     c = fixtures[name]
     r64, r32 = c["ref64"], c["ref32"]
@@ -61,7 +64,7 @@ def test_encoder_core_and_flow_forward(fixtures, name):
             assert flow is None
 
 
-@pytest.mark.parametrize("name", ["binary_image_json", "color_resnet"])
+@pytest.mark.parametrize("name", ALL)
 def test_data_dependent_initialize(fixtures, name):
     """MAE.initialize (weight_norm.py:25-37, masked.py:84-98 through every stack) from identical filled weights ends in
     the same gains and biases."""
@@ -95,7 +98,30 @@ def test_masked_layers_keep_masked_entries_zero():
 
 
 def test_registries_hold_the_reference_keys():
-    from mae_b200.modules import Decoder, EncoderCore, Flow
-    for key in ("resnet_binary_28x28", "resnet_color_32x32"):
-        assert EncoderCore.by_name(key) is not None and Decoder.by_name(key) is not None
-    assert Decoder.by_name("pixelcnn_binary_28x28") is not None and Flow.by_name("af_made") is not None
+    """every registry key the reference's three shipped JSON configurations (and its ResNet variants) use"""
+    from mae_b200.modules import Decoder, Encoder, EncoderCore, Flow
+    assert Encoder.by_name("gaussian") is not None
+    for key in ("resnet_binary_28x28", "resnet_color_32x32", "densenet_color_32x32", "densenet_color_64x64"):
+        assert EncoderCore.by_name(key) is not None
+    for key in ("resnet_binary_28x28", "resnet_color_32x32", "pixelcnn_binary_28x28", "pixelcnn++_color_32x32",
+                "pixelcnn++_color_64x64"):
+        assert Decoder.by_name(key) is not None
+    assert Flow.by_name("af_made") is not None and Flow.by_name("af2d_made") is not None
+
+
+def test_pixelcnnpp_is_causal():
+    """raw mixture parameters at pixel (i, j) must not depend on x at (i, j) or later in raster order"""
+    from mae_b200.modules import PixelCNNPPDecoderColorImage32x32
+    torch.manual_seed(0)
+    dec = PixelCNNPPDecoderColorImage32x32(4, 4, 2, dropout=0.0, activation='concat_elu').eval()
+    z = torch.randn(1, 4, 8, 8)
+    x = torch.rand(1, 3, 32, 32) * 2 - 1
+    with torch.no_grad():
+        base = dec(x, z)
+        x2 = x.clone()
+        x2[:, :, 13, 17:] += 0.5
+        x2[:, :, 14:, :] -= 0.5
+        moved = dec(x2, z)
+    diff = (moved - base).abs().amax(dim=(0, 1))
+    assert float(diff[:13].max()) == 0.0 and float(diff[13, :18].max()) == 0.0     # rows above, and up to (13, 17) itself
+    assert float(diff[13, 18:].max()) > 0.0 and float(diff[14:].max()) > 0.0
