@@ -140,6 +140,14 @@ def main():
         "color_resnet": run_model(COLOR_RESNET, xc, xc_init, ns=2, k=3, eta=0.5, gamma=1.0, free_bits=0.0),
         "color_image32x32_json": run_model(color, xc[:3], xc_init[:4], ns=1, k=2, eta=1.0, gamma=1.0, free_bits=0.0),
     }
+    # state_dict keys / shapes of the three shipped configurations exactly as written (ngpu = 2 for the colour ones ->
+    # DataParallel "module." level; pass-through on a CPU-only host)
+    literal = {}
+    for cfg in ("binary_image.json", "color_image32x32.json", "color_image64x64.json"):
+        params = json.load(open("/root/reference/experiments/configs/" + cfg))
+        model = RefMAE.from_params(copy.deepcopy(params))
+        literal[cfg] = {"params": params, "keys": {n: tuple(t.shape) for n, t in model.state_dict().items()}}
+    fixtures["literal_configs"] = literal
     path = os.path.join(HERE, "models.pt")
     torch.save(fixtures, path)
     print("wrote models.pt %.1f KB" % (os.path.getsize(path) / 1024.0))

@@ -42,6 +42,16 @@ def test_state_dict_identity_with_reference(fixtures, name):
     model.load_state_dict({n: torch.zeros(s) for n, s in c["keys"].items()}, strict=True)
 
 
+@pytest.mark.parametrize("cfg", ["binary_image.json", "color_image32x32.json", "color_image64x64.json"])
+def test_shipped_json_configs_build_with_reference_keys(fixtures, cfg):
+    """experiments/configs/*.json as written (the colour ones ask for 2 replicas -> DataParallel 'module.' key level)"""
+    c = fixtures["literal_configs"][cfg]
+    if torch.cuda.is_available() and torch.cuda.device_count() < 2 and "color" in cfg:
+        pytest.skip("ngpu=2 configuration needs two devices when CUDA is present")
+    model = MAE.from_params(copy.deepcopy(c["params"]))
+    assert {n: tuple(t.shape) for n, t in model.state_dict().items()} == c["keys"]
+
+
 @pytest.mark.parametrize("name", ALL)
 def test_encoder_core_and_flow_forward(fixtures, name):
     c = fixtures[name]
