@@ -128,6 +128,20 @@ int mae_mpd_bwd(const float* mu, int64_t mu_stride, const float* logvar, int64_t
                 const float* g_m, const float* g_S, const float* S, const float* gkl,
                 float* dmu, float* dlogvar, int accumulate, int path, mae_stream_t stream);
 
+/* The regulariser's consumers are closed forms (mae.py:132-139), so its gradient does not have to wait for the objective:
+ *     reg = clamp(kl_weight * sum_b kl_all[b], min = free_bits) - eta * sum_d logsigmoid(m_d[d]) + gamma * S
+ * mae_mpd_loss_bwd = d reg / d(mu, logvar) of rows [row0,row0+nrows) (dense [nrows,D]) and reg[0] (nullable), enqueued in
+ * the FORWARD pass right behind mae_mpd_prepare / mae_mpd_fwd (two launches: the upstream gradients g_m, g_S, gkl are
+ * derived on the device into the workspace, then the mae_mpd_bwd kernel of the chosen path runs).  m_d / S / kl_all are the
+ * outputs of prepare / fwd (after mae_mpd_finalize in row-sharded runs); kl_all NULL or kl_weight = 0 leaves the KL term
+ * out; dmu / dlogvar NULL: only reg is written.  Works for any B, D (the general-shape companion of
+ * mae_kl_mpd_loss_fused below). */
+int mae_mpd_loss_bwd(const float* mu, int64_t mu_stride, const float* logvar, int64_t logvar_stride,
+                     void* workspace, int64_t workspace_bytes, int64_t B, int64_t D,
+                     int64_t row0, int64_t nrows, float eta, float gamma, float free_bits, float kl_weight,
+                     const float* m_d, const float* S, const float* kl_all, float* reg,
+                     float* dmu, float* dlogvar, int path, mae_stream_t stream);
+
 /* Training-sized batches (B <= 128, D <= 64: MNIST / OMNIGLOT / CIFAR heads): the whole encoder-side regulariser
  *     reg = clamp(kl_weight * sum_b KL_b, min = free_bits) - eta * sum_d logsigmoid(m_d) + gamma * S
  * (mae.py:132-139; KL_b gaussian_encoder.py:219; m_d, S gaussian_encoder.py:162-188) forward AND backward in ONE launch of

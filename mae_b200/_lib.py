@@ -25,6 +25,7 @@ SIGNATURES = {
     "mae_mpd_fwd": [_P, _I64, _I64, _I64, _I64, _I64, _I, _P, _P, _P],
     "mae_mpd_finalize": [_P, _I64, _P, _P],
     "mae_mpd_bwd": [_P, _I64, _P, _I64, _P, _I64, _I64, _I64, _I64, _I64, _P, _P, _P, _P, _P, _P, _I, _I, _P],
+    "mae_mpd_loss_bwd": [_P, _I64, _P, _I64, _P, _I64, _I64, _I64, _I64, _I64, _F, _F, _F, _F, _P, _P, _P, _P, _P, _P, _I, _P],
     "mae_kl_mpd_loss_fused": [_P, _I64, _P, _I64, _I64, _I64, _F, _F, _F, _F, _P, _P, _P, _P, _P, _P, _P],
     "mae_bernoulli_fwd": [_P, _P, _I64, _I64, _I64, _P, _P],
     "mae_bernoulli_bwd": [_P, _P, _P, _I64, _F, _I64, _I64, _I64, _P, _P],

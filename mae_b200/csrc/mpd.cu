@@ -74,7 +74,7 @@ __device__ __forceinline__ unsigned long long now_ns() {
 struct Layout {
     int64_t Bp, Kp, nblk;
     int64_t prep_rows, prep_grid;  // rows per CTA / CTAs of mpd_prepare_kernel
-    int64_t hdr, colstats, pivots, c, l, xp, yp, vp, part_prep, part_fwd, kl, klt, total, total_nokl;
+    int64_t hdr, colstats, pivots, c, l, xp, yp, vp, part_prep, part_fwd, lossg, kl, klt, total, total_nokl;
 };
 
 constexpr int64_t kBigTileRows = 2048;  // padded batch from which the forward uses 128 x 128 tiles
@@ -108,6 +108,7 @@ Layout make_layout(int64_t B, int64_t D) {
     L.vp = take(L.Bp * D * 16);
     L.part_prep = take(L.prep_grid * kStats * D * 8);
     L.part_fwd = take(kMaxFwdCtas * 8);
+    L.lossg = take((D + B + 8) * 4);   // mae_mpd_loss_bwd: g_m[D] | g_S | pad[7] | gkl[B]
     L.total_nokl = off;           // everything the forward needs when the KL tiles are not kept
     L.kl = take(L.Bp * L.Bp * 4);  // optional tail: KL[Bp][Bp] and its transpose (stored-KL backward paths)
     L.klt = take(L.Bp * L.Bp * 4);
@@ -497,6 +498,43 @@ mpd_fwd_kernel(const float* __restrict__ Xp, const float* __restrict__ Yp, const
 
 __global__ void mpd_finalize_kernel(const double* __restrict__ sumsq, double nb, float* __restrict__ S) {
     S[0] = (float)sqrt(sumsq[0] / (nb * (nb - 1.0) - 1.0));
+}
+
+// upstream gradients of the regulariser's closed-form consumers (mae.py:132-139), evaluated on the device so that the
+// MPD backward can be enqueued in the FORWARD pass behind the tile kernel (no round trip through the objective):
+//   reg = clamp(kl_weight * sum_b KL_b, min = free_bits) - eta * sum_d logsigmoid(m_d) + gamma * S
+__global__ void __launch_bounds__(kNT)
+mpd_loss_grads_kernel(const float* __restrict__ m_d, const float* __restrict__ S, const float* __restrict__ kl_all, int B, int D,
+                      float eta, float gamma, float free_bits, float kl_weight, float* __restrict__ g_m, float* __restrict__ g_S,
+                      float* __restrict__ gkl, float* __restrict__ reg) {
+    __shared__ double scratch[32];
+    const int tid = threadIdx.x;
+    double ks = 0.0, ls = 0.0;
+    if (kl_all != nullptr)
+        for (int i = tid; i < B; i += kNT) ks += (double)kl_all[i];
+    for (int d = tid; d < D; d += kNT) {
+        const float v = m_d[d];
+        const float e = expf(-fabsf(v));
+        const float sig_neg = v >= 0.f ? e / (1.0f + e) : 1.0f / (1.0f + e);
+        g_m[d] = -eta * sig_neg;
+        ls += (double)(fminf(v, 0.f) - log1pf(e));
+    }
+    ks = block_sum(ks, scratch);
+    ls = block_sum(ls, scratch);
+    const float mean_kl = (float)(ks * (double)kl_weight);
+    const bool kl_on = kl_all != nullptr && kl_weight > 0.f;
+    const float gk = (kl_on && mean_kl >= free_bits) ? kl_weight : 0.f;   // clamp(min) passes at equality
+    if (gkl != nullptr)
+        for (int i = tid; i < B; i += kNT) gkl[i] = gk;
+    if (tid == 0) {
+        g_S[0] = gamma > 0.f ? gamma : 0.f;
+        if (reg != nullptr) {
+            float r = kl_on ? fmaxf(mean_kl, free_bits) : 0.f;
+            if (eta > 0.f) r -= eta * (float)ls;
+            if (gamma > 0.f) r += gamma * S[0];
+            reg[0] = r;
+        }
+    }
 }
 
 // --------------------------------------------------------------------------------- backward: common parts
@@ -910,4 +948,24 @@ extern "C" int mae_mpd_bwd(const float* mu, int64_t mu_stride, const float* logv
     rc = (path == 3) ? launch(std::true_type{}) : launch(std::false_type{});
     if (rc != MAE_OK) return rc;
     return launch_status();
+}
+
+extern "C" int mae_mpd_loss_bwd(const float* mu, int64_t mu_stride, const float* logvar, int64_t logvar_stride, void* workspace,
+                                int64_t workspace_bytes, int64_t B, int64_t D, int64_t row0, int64_t nrows, float eta, float gamma,
+                                float free_bits, float kl_weight, const float* m_d, const float* S, const float* kl_all,
+                                float* reg, float* dmu, float* dlogvar, int path, mae_stream_t stream) {
+    using namespace mae;
+    MAE_REQUIRE(m_d && S, MAE_ERR_NULL);
+    Layout L;
+    int rc = check_common(B, D, workspace, workspace_bytes, L);
+    if (rc != MAE_OK) return rc;
+    float* g_m = at<float>(workspace, L.lossg);
+    float* g_S = g_m + D;
+    float* gkl = (kl_all != nullptr && kl_weight > 0.f) ? g_m + D + 8 : nullptr;
+    mpd_loss_grads_kernel<<<1, kNT, 0, as_stream(stream)>>>(m_d, S, kl_all, (int)B, (int)D, eta, gamma, free_bits, kl_weight, g_m,
+                                                           g_S, gkl, reg);
+    rc = launch_status();
+    if (rc != MAE_OK || dmu == nullptr) return rc;   // dmu NULL: only reg is wanted (evaluation)
+    return mae_mpd_bwd(mu, mu_stride, logvar, logvar_stride, workspace, workspace_bytes, B, D, row0, nrows,
+                       eta > 0.f ? g_m : nullptr, gamma > 0.f ? g_S : nullptr, S, gkl, dmu, dlogvar, 0, path, stream);
 }

@@ -140,6 +140,59 @@ class _ShardedKLMPD(torch.autograd.Function):
         return dmu.view(ctx.shapes[0]), dlv.view(ctx.shapes[1]), None
 
 
+class _ShardedEncodeHead(torch.autograd.Function):
+    """(mu_loc, logvar_loc, eps_loc) -> (z_loc, reg, kl_all [B_global], m_d, S): the sharded counterpart of
+    ``ops.encode_head``.  Side stream: pack, all-gather, pre-pass, tiles, (all-reduce of the fp64 scalar for large global
+    batches) AND the regulariser's backward for the own rows, all enqueued back to back in the forward pass.  Main stream:
+    the reparameterisation.  The backward pass is ONE launch (reparam backward + d reg * stored gradient): nothing of
+    the regulariser, and no collective, is left on it."""
+
+    @staticmethod
+    def forward(ctx, mu, logvar, eps, head, eta, gamma, free_bits):
+        ctx.set_materialize_grads(False)
+        eng = head.engine
+        want_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        world = head.world
+
+        def chain():
+            kl_loc, m_d, s, kl_all, state, gathered, row0, b_loc = _ShardedKLMPD._compute(mu, logvar, head)
+            grads, reg = eng.mpd_rows_loss_backward(state, row0, b_loc, eta, gamma, free_bits, 1.0 / (world * b_loc), m_d,
+                                                    kl_all, want_grad)
+            return m_d, s, kl_all, gathered, grads, reg
+
+        side = mu.is_cuda and hasattr(eng, "_side_stream") and head.overlap
+        ev = None
+        if side:
+            dev = mu.device
+            idx = dev.index if dev.index is not None else torch.cuda.current_device()
+            cs, ss = torch.cuda.current_stream(dev), eng._side_stream(dev)
+            ss.wait_stream(cs)
+            prev = eng._pending_join.pop(idx, None)
+            with torch.cuda.stream(ss):
+                m_d, s, kl_all, gathered, grads, reg = chain()
+                ev = torch.cuda.Event()
+                ev.record(ss)
+            eng._pending_join[idx] = (ev, (prev, m_d, s, kl_all, gathered, grads, reg, mu, logvar))
+        else:
+            m_d, s, kl_all, gathered, grads, reg = chain()
+        z, saved = eng.reparam_fwd(mu, logvar, eps)
+        ctx.saved, ctx.grads, ctx.event, ctx.eng = saved, grads, ev, eng
+        ctx.shapes = (mu.shape, logvar.shape)
+        ctx.mark_non_differentiable(kl_all, m_d, s)
+        return z, reg, kl_all, m_d.view(mu.shape[1:]), s
+
+    @staticmethod
+    def backward(ctx, gz, g_reg, *_unused):
+        if gz is None and g_reg is None:
+            return (None,) * 7
+        if g_reg is not None and ctx.grads is None:
+            raise RuntimeError("sharded encode head: reg has a gradient but mu / logvar did not require one in the forward")
+        if ctx.event is not None:
+            torch.cuda.current_stream().wait_event(ctx.event)
+        dmu, dlv = ctx.eng.reparam_reg_bwd(ctx.saved, gz, ctx.grads, g_reg)
+        return dmu.view(ctx.shapes[0]), dlv.view(ctx.shapes[1]), None, None, None, None, None
+
+
 class ShardedHead:
     """Batch-sharded MAE loss head / evaluator.  ``engine`` defaults to ``mae_b200.ops`` (the CUDA kernels)."""
 
@@ -152,6 +205,7 @@ class ShardedHead:
         self.check_equal_batches = check_equal_batches   # costs two tiny all-reduces and a host sync per step
         self.overlap = overlap                           # all-gather + MPD on the side stream (CUDA engine only)
         self.defer_join = True                           # loss value valid after backward() / ops.join_side()
+        self.two_node = True                             # regulariser backward in the forward pass (engine permitting)
         self.peer = None                                 # NVLink peer-memory gather (created lazily, CUDA only)
         self.use_p2p = use_p2p
         self.world = dist.get_world_size(group)
@@ -194,8 +248,25 @@ class ShardedHead:
         ext = torch.stack([kl_others.new_zeros(()), kl_others]).to(kl.dtype)
         return eng.assemble_loss(err, kl, m_d, s, eta, gamma, free_bits, 1.0 / b_glob, ext)
 
+    def _two_node(self, mu, logvar, eps, dec_out, x, kind, nmix, eta, gamma, free_bits):
+        """encode head (regulariser forward + backward behind the all-gather, side stream) + loss head."""
+        eng = self.engine
+        z, reg, kl_all, m_d, s = _ShardedEncodeHead.apply(mu, logvar, eps, self, float(eta), float(gamma), float(free_bits))
+        enc = eng.EncodedBatch(reg, kl_all, m_d, s, (float(eta), float(gamma), float(free_bits)))
+        b_loc = x.size(0)
+        loss, stats, recon = eng.loss_head(dec_out, x, enc, kind, eps.size(1), nmix, eta, gamma, free_bits,
+                                           defer_join=self.overlap and self.defer_join, inv_batch=1.0 / (self.world * b_loc))
+        row0 = self.rank * b_loc
+        return loss, recon, kl_all[row0:row0 + b_loc], stats, z
+
+    def _has_two_node(self) -> bool:
+        return self.two_node and all(hasattr(self.engine, n) for n in ("mpd_rows_loss_backward", "reparam_fwd",
+                                                                       "reparam_reg_bwd", "loss_head", "EncodedBatch"))
+
     def loss_head_color(self, mu, logvar, eps, raw, x, nmix=10, eta=0.0, gamma=0.0, free_bits=0.0):
         """C3 on a batch shard.  Returns (loss, recon [B_loc], KL [B_loc], stats, z) like ``heads.loss_head_color``."""
+        if self._has_two_node():
+            return self._two_node(mu, logvar, eps, raw, x, "dmol", nmix, eta, gamma, free_bits)
         z, _ = self.engine.reparam_kl(mu, logvar, eps, want_kl=False)
         kl, m_d, s, kl_all = self.kl_mpd(mu, logvar)
         loss, stats, recon = self._tail(raw, x, kl, m_d, s, kl_all, "dmol", eps.size(1), nmix, eta, gamma, free_bits)
@@ -203,6 +274,8 @@ class ShardedHead:
 
     def loss_head_binary(self, mu, logvar, eps, probs, x, eta=0.0, gamma=0.0, free_bits=0.0):
         """C1/C2 on a batch shard."""
+        if self._has_two_node():
+            return self._two_node(mu, logvar, eps, probs, x, "bernoulli", 0, eta, gamma, free_bits)
         z, _ = self.engine.reparam_kl(mu, logvar, eps, want_kl=False)
         kl, m_d, s, kl_all = self.kl_mpd(mu, logvar)
         loss, stats, recon = self._tail(probs, x, kl, m_d, s, kl_all, "bernoulli", eps.size(1), 0, eta, gamma, free_bits)

@@ -12,13 +12,13 @@ import torch
 from . import ops
 
 
-ONE_NODE = True   # False forces the general three-node composition (kept for batches / latents outside the fused kernel)
+ONE_NODE = True   # False forces the three-node composition (reparam, kl_mpd, loss_tail) that flows / sharded runs use
 
 
 def _one_node(mu: torch.Tensor) -> bool:
-    """Training-sized batch: KL + MPD forward/backward in one launch (ops.encode_head), two autograd nodes in total."""
-    b = mu.size(0)
-    return ONE_NODE and b >= 2 and ops.fused_reg_supported(b, mu[0].numel(), mu.device)
+    """Two autograd nodes in total: ops.encode_head (z + the whole regulariser forward AND backward on the side stream: one
+    cluster launch for training-sized batches, the general kernel chain otherwise) and ops.loss_head."""
+    return ONE_NODE and mu.size(0) >= 2
 
 
 def loss_head_binary(mu, logvar, eps, probs, x, eta=0.0, gamma=0.0, free_bits=0.0, defer_join=False):

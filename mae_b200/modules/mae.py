@@ -51,9 +51,10 @@ class MAE(nn.Module):
             # decoder), likelihood+objective.
             mu, logvar = enc.core(x)
             eps = enc._draw_eps(mu, nsamples)
-            if mu.size(0) >= 2 and ops.fused_reg_supported(mu.size(0), mu[0].numel(), mu.device):
-                # training-sized batch, two autograd nodes: (1) z plus KL + MPD forward AND backward in one launch on the
-                # side stream, beside the decoder; (2) likelihood + objective
+            if mu.size(0) >= 2:
+                # two autograd nodes: (1) z plus KL + MPD forward AND backward on the side stream, beside the decoder
+                # (one cluster launch for B <= 128, D <= 64, else prepare -> tiles -> backward kernels back to back);
+                # (2) likelihood + objective
                 z, eb = ops.encode_head(mu, logvar, eps, eta, gamma, free_bits)
                 dec_out = dec.likelihood_input(x, z.view(z.size(0), z.size(1), *z_shape_dec))
                 loss, stats, recon = ops.loss_head(dec_out, x, eb, dec.likelihood_kind, nsamples,

@@ -16,7 +16,8 @@ from . import _lib
 
 __all__ = [
     "reparam_kl", "mpd", "mpd_forward_only", "bernoulli_recon_error", "dmol_recon_error", "log_prob_prior",
-    "log_prob_posterior", "iw_nll", "assemble_loss", "kl_mpd", "loss_tail", "loss_head", "encode_head", "kl_mpd_reg_fused", "fused_reg_supported", "join_side", "launch_count", "reset_launch_count",
+    "log_prob_posterior", "iw_nll", "assemble_loss", "kl_mpd", "loss_tail", "loss_head", "encode_head", "kl_mpd_reg_fused", "kl_mpd_reg", "mpd_rows_loss_backward", "reparam_fwd",
+    "reparam_reg_bwd", "fused_reg_supported", "join_side", "launch_count", "reset_launch_count",
 ]
 
 _launches = 0  # number of kernels of ours enqueued since the last reset (bench.py reports it)
@@ -404,6 +405,59 @@ def mpd_rows_backward(state: "MpdRowsState", row0: int, nrows: int, g_m, g_s, g_
     _count()
     _pool.give(state.ws)
     state.ws = None
+    return dmu, dlv
+
+
+def mpd_rows_loss_backward(state: "MpdRowsState", row0: int, nrows: int, eta: float, gamma: float, free_bits: float,
+                           kl_weight: float, m_d: torch.Tensor, kl_all: Optional[torch.Tensor], want_grad: bool = True):
+    """Regulariser value and its gradient w.r.t. rows [row0,row0+nrows), enqueued right behind the forward kernels
+    (mae_mpd_loss_bwd): -> (grads [2,nrows,D] or None, reg []).  ``state.s`` must hold S (finalized in row-sharded runs).
+    Consumes the state (the workspace goes back to the pool)."""
+    dev = state.mu2.device
+    grads = torch.empty(2, nrows, state.d, device=dev, dtype=torch.float32) if want_grad else None
+    reg = torch.empty((), device=dev, dtype=torch.float32)
+    m_c = m_d.contiguous().view(-1)
+    _lib.check(_lib_().mae_mpd_loss_bwd(state.mu2.data_ptr(), state.ms, state.lv2.data_ptr(), state.ls, state.ws.data_ptr(),
+                                        state.ws.numel(), state.b, state.d, row0, nrows, float(eta), float(gamma),
+                                        float(free_bits), float(kl_weight), m_c.data_ptr(), state.s.data_ptr(), _ptr(kl_all),
+                                        reg.data_ptr(), grads[0].data_ptr() if want_grad else None,
+                                        grads[1].data_ptr() if want_grad else None, state.path, _stream()), "mae_mpd_loss_bwd")
+    _count(2 if want_grad else 1)
+    _pool.give(state.ws)
+    state.ws = None
+    return grads, reg
+
+
+def reparam_fwd(mu: torch.Tensor, logvar: torch.Tensor, eps: torch.Tensor):
+    """z = eps * exp(0.5 logvar) + mu without an autograd node (building block of the fused encoder nodes):
+    -> (z, saved) with ``saved`` = what :func:`reparam_reg_bwd` needs."""
+    _req_cuda(mu, logvar, eps)
+    mu2, ms = _rows(mu)
+    lv2, ls = _rows(logvar)
+    b, ns, d = eps.size(0), eps.size(1), mu2.size(1)
+    eps_c = eps.contiguous()
+    z = torch.empty_like(eps_c)
+    _lib.check(_lib_().mae_reparam_kl_fwd(mu2.data_ptr(), ms, lv2.data_ptr(), ls, eps_c.data_ptr(), b, ns, d, z.data_ptr(), None,
+                                          _stream()), "mae_reparam_kl_fwd")
+    _count()
+    return z, (mu2, ms, lv2, ls, eps_c, b, ns, d)
+
+
+def reparam_reg_bwd(saved, gz: Optional[torch.Tensor], grads: Optional[torch.Tensor], g_reg: Optional[torch.Tensor]):
+    """d(mu, logvar) = reparameterisation backward of d z  +  g_reg * grads  in one launch (mae_reparam_reg_bwd);
+    grads = [2,B,D] from the regulariser kernels, g_reg a device scalar.  -> (dmu, dlv) dense [B,D]."""
+    mu2, ms, lv2, ls, eps_c, b, ns, d = saved
+    dev = mu2.device
+    gz = gz.contiguous() if gz is not None else None
+    use = grads is not None and g_reg is not None
+    g_reg = g_reg.contiguous() if use else None
+    dmu = torch.empty(b, d, device=dev, dtype=torch.float32)
+    dlv = torch.empty_like(dmu)
+    _lib.check(_lib_().mae_reparam_reg_bwd(mu2.data_ptr(), ms, lv2.data_ptr(), ls, eps_c.data_ptr(), _ptr(gz), None,
+                                           grads[0].data_ptr() if use else None, grads[1].data_ptr() if use else None,
+                                           _ptr(g_reg), b, ns, d, dmu.data_ptr(), dlv.data_ptr(), 0, _stream()),
+               "mae_reparam_reg_bwd")
+    _count()
     return dmu, dlv
 
 
@@ -876,6 +930,43 @@ def kl_mpd_reg_fused(mu: torch.Tensor, logvar: torch.Tensor, eta: float, gamma: 
     return kl, m_d.view(mu.shape[1:]), s_, reg, grads, (mu2, lv2)
 
 
+def kl_mpd_reg(mu: torch.Tensor, logvar: torch.Tensor, eta: float, gamma: float, free_bits: float,
+               kl_weight: Optional[float] = None, want_grad: bool = True, launch_stream=None):
+    """Same contract as :func:`kl_mpd_reg_fused` for ANY batch / latent size: the one-launch cluster kernel where it
+    applies, else the general chain prepare -> tiles -> (device-side upstream gradients -> backward kernel), all enqueued
+    back to back (on ``launch_stream``), so that nothing of the regulariser is left for the backward pass."""
+    _req_cuda(mu, logvar)
+    mu2, ms = _rows(mu)
+    lv2, ls = _rows(logvar)
+    b, d = mu2.shape
+    dev = mu2.device
+    if b < 2:
+        raise RuntimeError("the MPD regulariser needs a batch of at least 2 posteriors (gaussian_encoder.py:181)")
+    if fused_reg_supported(b, d, dev):
+        return kl_mpd_reg_fused(mu, logvar, eta, gamma, free_bits, kl_weight, want_grad, launch_stream)
+    kw = 1.0 / float(b) if kl_weight is None else float(kl_weight)
+    lib = _lib_()
+    path = _mpd_pick_path(b, d, 0) if want_grad else 2
+    store = want_grad and path != 2
+    outs = _mpd_alloc_outputs(d, dev)
+    kl = torch.empty(b, device=dev, dtype=torch.float32)
+    with torch.cuda.stream(launch_stream if launch_stream is not None else torch.cuda.current_stream(dev)):
+        ws = _pool.take(lib.mae_mpd_workspace_bytes(b, d, int(store)), dev)
+        m_d, s_, _ = _mpd_launch_fwd(mu2, ms, lv2, ls, b, d, ws, store, outs, kl=kl)
+    state = MpdRowsState(ws, mu2, ms, lv2, ls, b, d, s_, path)
+    # outputs are allocated on the current stream, the kernels go to the launch stream
+    grads = torch.empty(2, b, d, device=dev, dtype=torch.float32) if want_grad else None
+    reg = torch.empty((), device=dev, dtype=torch.float32)
+    with torch.cuda.stream(launch_stream if launch_stream is not None else torch.cuda.current_stream(dev)):
+        _lib.check(lib.mae_mpd_loss_bwd(mu2.data_ptr(), ms, lv2.data_ptr(), ls, ws.data_ptr(), ws.numel(), b, d, 0, b,
+                                        float(eta), float(gamma), float(free_bits), kw, m_d.data_ptr(), s_.data_ptr(),
+                                        kl.data_ptr(), reg.data_ptr(), grads[0].data_ptr() if want_grad else None,
+                                        grads[1].data_ptr() if want_grad else None, state.path, _stream()), "mae_mpd_loss_bwd")
+        _count(2 if want_grad else 1)
+        _pool.give(ws)
+    return kl, m_d.view(mu.shape[1:]), s_, reg, grads, (mu2, lv2)
+
+
 class _EncodeHead(torch.autograd.Function):
     """Everything between the encoder core and the decoder as ONE autograd node for training-sized batches:
     (mu, logvar, eps) -> (z, reg, KL, m_d, S), reg = clamp(KL.mean(), free_bits) - eta sum logsigmoid(m_d) + gamma S.
@@ -895,8 +986,7 @@ class _EncodeHead(torch.autograd.Function):
         cs, ss = torch.cuda.current_stream(dev), _side_stream(dev)
         ss.wait_stream(cs)
         prev = _pending_join.pop(idx, None)
-        kl, m_d, s, reg, grads, (mu2, lv2) = kl_mpd_reg_fused(mu, logvar, eta, gamma, free_bits, None, want_grad,
-                                                              launch_stream=ss)
+        kl, m_d, s, reg, grads, (mu2, lv2) = kl_mpd_reg(mu, logvar, eta, gamma, free_bits, None, want_grad, launch_stream=ss)
         ev = torch.cuda.Event()
         ev.record(ss)
         _pending_join[idx] = (ev, (prev, kl, m_d, s, reg, grads, mu2, lv2))
@@ -961,15 +1051,16 @@ class _LossTailReg(torch.autograd.Function):
     backward: d dec_out (a conditional rescale by d loss) and d reg = d loss.  ``defer``: see _LossTail."""
 
     @staticmethod
-    def forward(ctx, dec_out, x, reg, kl, m_d, s, kind, ns, nmix, eta, gamma, free_bits, defer):
+    def forward(ctx, dec_out, x, reg, kl, m_d, s, kind, ns, nmix, eta, gamma, free_bits, defer, inv_batch):
         ctx.set_materialize_grads(False)
         _req_cuda(dec_out, x, reg, kl, m_d, s)
         lib = _lib_()
         dev = dec_out.device
         idx = dev.index if dev.index is not None else torch.cuda.current_device()
         b = x.size(0)
-        out_c, x_c, err, err_chunks, fused_grad, geom = _likelihood_fwd(dec_out, x, kind, ns, nmix, 0.0,
+        out_c, x_c, err, err_chunks, fused_grad, geom = _likelihood_fwd(dec_out, x, kind, ns, nmix, inv_batch,
                                                                          ctx.needs_input_grad[0])
+        kl_count = kl.numel() if inv_batch > 0.0 else 0     # sharded runs: kl is the all-gathered vector of the global batch
         m_c = m_d.reshape(-1)
         d = m_c.numel()
         scalars = torch.empty(6, device=dev, dtype=torch.float32)
@@ -977,7 +1068,7 @@ class _LossTailReg(torch.autograd.Function):
 
         def assemble():
             _lib.check(lib.mae_loss_assemble_fwd(err.data_ptr(), kl.data_ptr(), m_c.data_ptr(), s.data_ptr(), None, b, ns, d,
-                                                 0, err_chunks, eta, gamma, free_bits, 0.0, scalars.data_ptr(),
+                                                 kl_count, err_chunks, eta, gamma, free_bits, inv_batch, scalars.data_ptr(),
                                                  recon.data_ptr(), _stream()), "mae_loss_assemble_fwd")
             _count()
 
@@ -997,7 +1088,7 @@ class _LossTailReg(torch.autograd.Function):
             assemble()
         ctx.save_for_backward(out_c, x_c)
         ctx.fused_grad = fused_grad
-        ctx.meta = (kind, b, ns, nmix, geom, dec_out.shape, defer)
+        ctx.meta = (kind, b, ns, nmix, geom, dec_out.shape, defer, inv_batch)
         loss, stats = scalars[0], scalars[1:]
         ctx.mark_non_differentiable(stats, recon)
         return loss, stats, recon
@@ -1005,32 +1096,35 @@ class _LossTailReg(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gloss, *_unused):
         if gloss is None:
-            return (None,) * 13
+            return (None,) * 14
         out_c, x_c = ctx.saved_tensors
-        kind, b, ns, nmix, geom, out_shape, defer = ctx.meta
+        kind, b, ns, nmix, geom, out_shape, defer, inv_batch = ctx.meta
         gloss = gloss.contiguous()
         dout = None
         if ctx.needs_input_grad[0]:
-            dout = _likelihood_bwd(ctx, out_c, x_c, gloss, kind, b, ns, nmix, geom, 0.0, out_shape)
+            dout = _likelihood_bwd(ctx, out_c, x_c, gloss, kind, b, ns, nmix, geom, inv_batch, out_shape)
         if defer:
             # nothing in the backward pass consumes the deferred objective kernel: join once the whole pass has been
             # enqueued, so that the encoder-side backward is not ordered behind it
             dev = out_c.device
             torch.autograd.Variable._execution_engine.queue_callback(lambda: join_side(dev))
-        return (dout, None, gloss if ctx.needs_input_grad[2] else None) + (None,) * 10
+        return (dout, None, gloss if ctx.needs_input_grad[2] else None) + (None,) * 11
 
 
 def loss_head(dec_out: torch.Tensor, x: torch.Tensor, enc: EncodedBatch, kind: str, ns: int, nmix: int = 10,
-              eta: float = 0.0, gamma: float = 0.0, free_bits: float = 0.0, defer_join: bool = False):
+              eta: float = 0.0, gamma: float = 0.0, free_bits: float = 0.0, defer_join: bool = False,
+              inv_batch: float = 0.0):
     """Decoder output + :func:`encode_head` result -> objective of MAE.loss.  Returns (loss [], stats [5], recon [B]) like
-    :func:`loss_tail`; KL / m_d / S are in ``enc``.  ``defer_join``: see :func:`loss_tail`.
+    :func:`loss_tail`; KL / m_d / S are in ``enc``.  ``defer_join``: see :func:`loss_tail`.  ``inv_batch`` (batch-sharded
+    runs): 1 / global batch; ``enc.kl`` is then the all-gathered KL vector and the returned loss holds this rank's share of
+    the reconstruction term plus the global regulariser.
     Reference: mae.py:100-140 with the two reconstruct_error heads."""
     if kind not in ("dmol", "bernoulli"):
         raise ValueError("kind must be 'dmol' or 'bernoulli'")
     if enc.params != (float(eta), float(gamma), float(free_bits)):
         raise RuntimeError("loss_head: encode_head was called with different eta / gamma / free_bits")
     return _LossTailReg.apply(dec_out, x, enc.reg, enc.kl, enc.m_d, enc.s, kind, int(ns), int(nmix), float(eta),
-                              float(gamma), float(free_bits), bool(defer_join))
+                              float(gamma), float(free_bits), bool(defer_join), float(inv_batch))
 
 
 def assemble_loss(err: torch.Tensor, kl: torch.Tensor, m_d: Optional[torch.Tensor], s: Optional[torch.Tensor],

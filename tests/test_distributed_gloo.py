@@ -86,20 +86,67 @@ class _State:
         self.s = d["s"]
 
 
+class _Enc:
+    def __init__(self, reg, kl, m_d, s, params):
+        self.reg, self.kl, self.m_d, self.s, self.params = reg, kl, m_d, s, params
+
+
+class OracleEngine2(OracleEngine):
+    """adds the call surface of the two-node path (regulariser backward in the forward pass, loss head on reg)"""
+    EncodedBatch = _Enc
+
+    def mpd_rows_loss_backward(self, state, row0, nrows, eta, gamma, free_bits, kl_weight, m_d, kl_all, want_grad=True):
+        O = self.O
+        with torch.enable_grad():
+            mu = state.d["mu"].clone().requires_grad_()
+            lv = state.d["lv"].clone().requires_grad_()
+            md, s = O.post_kl(mu, lv)
+            reg = (O.analytic_kl(mu, lv).sum() * kl_weight).clamp(min=free_bits)
+            _, _, l_mean, l_std = O.mpd_loss_terms(md, s, eta, gamma)
+            reg = reg + l_mean + l_std
+            reg.backward()
+        grads = torch.stack([mu.grad[row0:row0 + nrows], lv.grad[row0:row0 + nrows]])
+        return (grads if want_grad else None), reg.detach()
+
+    def reparam_fwd(self, mu, logvar, eps):
+        return self.O.reparameterize(mu.detach(), logvar.detach(), eps), (mu.detach(), logvar.detach(), eps)
+
+    def reparam_reg_bwd(self, saved, gz, grads, g_reg):
+        mu, lv, eps = saved
+        dmu, dlv = torch.zeros_like(mu), torch.zeros_like(lv)
+        if gz is not None:
+            dmu = dmu + gz.sum(dim=1)
+            dlv = dlv + 0.5 * (0.5 * lv).exp() * (gz * eps).sum(dim=1)
+        if grads is not None and g_reg is not None:
+            dmu, dlv = dmu + g_reg * grads[0], dlv + g_reg * grads[1]
+        return dmu, dlv
+
+    def loss_head(self, dec_out, x, enc, kind, ns, nmix, eta, gamma, free_bits, defer_join=False, inv_batch=0.0):
+        err = self.dmol_recon_error(dec_out, x, ns, nmix) if kind == "dmol" else self.bernoulli_recon_error(dec_out, x)
+        recon = err.mean(dim=1)
+        mean_rec = recon.sum() * inv_batch
+        loss = mean_rec + enc.reg
+        _, _, l_mean, l_std = self.O.mpd_loss_terms(enc.m_d, enc.s, eta, gamma)
+        stats = torch.stack([enc.m_d.sum().detach(), torch.as_tensor(l_mean).detach().double(),
+                             torch.as_tensor(l_std).detach().double(), (enc.kl.sum() * inv_batch).detach(), mean_rec.detach()])
+        return loss, stats, recon.detach()
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, small_limit, kind, free_bits, out):
+def _worker(rank, world, port, small_limit, kind, free_bits, out, two_node=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     torch.set_num_threads(1)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         from mae_b200 import distributed as D, synth
         D.SMALL_GLOBAL_BATCH = small_limit
-        head = D.ShardedHead(engine=OracleEngine(), check_equal_batches=True)
+        head = D.ShardedHead(engine=OracleEngine2() if two_node else OracleEngine(), check_equal_batches=True)
+        assert head._has_two_node() == two_node
         b_loc, ns, d = 5, 2, 6
         b = world * b_loc
         mu_g, lv_g = synth.posterior_params(b, (d,), seed=1, clamp=True)
@@ -127,14 +174,15 @@ def _worker(rank, world, port, small_limit, kind, free_bits, out):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("small_limit,kind,free_bits", [(2048, "bernoulli", 0.0), (4, "bernoulli", 0.0), (2048, "dmol", 1e4),
-                                                         (4, "dmol", 0.0)])
-def test_sharded_head_matches_single_process(tmp_path, small_limit, kind, free_bits):
+@pytest.mark.parametrize("small_limit,kind,free_bits,two_node", [
+    (2048, "bernoulli", 0.0, False), (4, "bernoulli", 0.0, False), (2048, "dmol", 1e4, False), (4, "dmol", 0.0, False),
+    (2048, "dmol", 0.0, True), (4, "bernoulli", 1e4, True)])
+def test_sharded_head_matches_single_process(tmp_path, small_limit, kind, free_bits, two_node):
     from mae_b200 import synth
     from oracle import mae_oracle as O
     world = 2
     out = str(tmp_path / "r%d.pt")
-    mp.spawn(_worker, args=(world, _free_port(), small_limit, kind, free_bits, out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), small_limit, kind, free_bits, out, two_node), nprocs=world, join=True)
     res = [torch.load(out % r) for r in range(world)]
     b_loc, ns, d = 5, 2, 6
     b = world * b_loc

@@ -427,6 +427,38 @@ def test_fused_regulariser_kernel_vs_oracle(ops, O, b, d):
     assert torch.equal(kl1, kl2) and torch.equal(m1, m2) and torch.equal(s1, s2)   # deterministic
 
 
+@pytest.mark.parametrize("b,d", [(150, 70), (64, 1024), (300, 16), (2100, 8)])
+def test_general_regulariser_chain_vs_oracle(ops, O, b, d):
+    """ops.kl_mpd_reg outside the cluster kernel's shapes: prepare -> tiles -> device-side upstream gradients -> backward
+    kernel (paths 1 and 3), same contract as the one-launch kernel (reg value and d reg / d(mu, logvar))."""
+    from mae_b200 import synth
+    mu0, lv0 = synth.posterior_params(b, (d,), seed=200 + b, clamp=True)
+    assert not ops.fused_reg_supported(b, d, DEV)
+    klm = float(O.analytic_kl(mu0.double(), lv0.double()).mean())
+    for eta, gamma, fb in ((1.0, 1.0, 0.0), (0.0, 2.0, 0.0), (0.7, 0.0, 2.0 * klm + 1.0)):
+        kl, m_d, s, reg, grads, _ = ops.kl_mpd_reg(cu(mu0), cu(lv0), eta, gamma, fb)
+        a, c = mu0.double().requires_grad_(), lv0.double().requires_grad_()
+        klr = O.analytic_kl(a, c)
+        mr, sr = O.post_kl(a, c) if b <= 512 else O.post_kl_chunked(a, c, rows_per_chunk=100)
+        regr = klr.mean().clamp(min=fb)
+        if eta > 0:
+            regr = regr - eta * torch.nn.functional.logsigmoid(mr).sum()
+        if gamma > 0:
+            regr = regr + gamma * sr
+        regr.backward()
+        tag = "B=%d D=%d eta=%g gamma=%g fb=%g" % (b, d, eta, gamma, fb)
+        check_close(kl, klr, what="KL " + tag)
+        check_close(m_d, mr, what="m_d " + tag)
+        check_close(s, sr, what="S " + tag)
+        check_close(reg, regr, what="reg " + tag)
+        check_close(grads[0], a.grad, what="dmu " + tag, floor=1e-12)
+        check_close(grads[1], c.grad, what="dlv " + tag, floor=1e-12)
+    kl2, m2, s2, reg2, g2, _ = ops.kl_mpd_reg(cu(mu0), cu(lv0), 1.0, 1.0, 0.0, want_grad=False)
+    assert g2 is None
+    kl1, m1, s1, reg1, _, _ = ops.kl_mpd_reg(cu(mu0), cu(lv0), 1.0, 1.0, 0.0)
+    assert torch.equal(m1, m2) and torch.equal(s1, s2) and torch.equal(reg1, reg2)
+
+
 def test_fused_regulariser_goldens_and_strided_views(ops, O, golden):
     """the reference's own _postKL goldens (incl. the posterior-collapse regime) through the fused kernel, fed with the
     strided chunk views an encoder core returns"""
@@ -465,7 +497,7 @@ def test_fused_loss_heads_vs_oracle(ops, O, kind, eta, gamma, free_bits, defer, 
     reference formulas, values and all gradients."""
     from mae_b200 import heads, synth
     monkeypatch.setattr(heads, "ONE_NODE", one_node)
-    b, ns, d = 12, 2, 10
+    b, ns, d = (12, 2, 10) if kind == "dmol" else (12, 2, 70)     # D = 70: encode_head takes the general kernel chain
     mu0, lv0 = synth.posterior_params(b, (d,), seed=3, clamp=True)
     eps = synth.noise(b, ns, (d,), seed=3)
     mu, lv = cu(mu0).requires_grad_(), cu(lv0).requires_grad_()
