@@ -10,7 +10,7 @@ import os
 from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libmae_b200.so")
+LIB_PATH = os.environ.get("MAE_B200_LIB") or os.path.join(_PKG, "libmae_b200.so")   # env: tuning builds only
 
 ABI_VERSION = 1
 

@@ -34,6 +34,8 @@ def _extra_flags():
     extra = ["-DMAE_DEBUG_TIMING"] if os.environ.get("MAE_DEBUG_TIMING") else []   # phase timestamps, profiling builds only
     if os.environ.get("MAE_DMOL_G5"):                                              # tuning: pixel groups per CTA (SPLIT=5)
         extra.append("-DMAE_DMOL_G5=%d" % int(os.environ["MAE_DMOL_G5"]))
+    if os.environ.get("MAE_DMOL_BWD_MINB"):                                        # tuning: min CTAs/SM of the DMOL backward
+        extra.append("-DMAE_DMOL_BWD_MINB=%d" % int(os.environ["MAE_DMOL_BWD_MINB"]))
     return extra
 
 

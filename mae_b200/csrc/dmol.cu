@@ -123,7 +123,7 @@ template <int NMIX, int SPLIT>
 struct Geo {
     static constexpr int kK = (NMIX + SPLIT - 1) / SPLIT;             // components per thread (upper bound)
 #ifndef MAE_DMOL_G5
-#define MAE_DMOL_G5 2
+#define MAE_DMOL_G5 1   // measured at C3 (64 Ki pixels): 160-thread CTAs 14.6 us vs 15.4 us (320) vs 21.5 us (640)
 #endif
     static constexpr int kG = SPLIT == 1 ? 8 : (SPLIT == 2 ? 4 : MAE_DMOL_G5);  // pixel groups per CTA
     static constexpr int kThreadsCta = 32 * SPLIT * kG;
@@ -259,8 +259,11 @@ dmol_fwd_kernel(const float* __restrict__ raw, const float* __restrict__ x, int 
 
 // ERR: the same pass also produces err[n] (fused forward+backward for training: raw is read once, d raw written once,
 // 53 MB instead of 27 + 53 MB at C3); g is then nullptr and the gradient is scaled by g_mul = 1/(B*ns) only.
+#ifndef MAE_DMOL_BWD_MINB
+#define MAE_DMOL_BWD_MINB 6   // 160-thread CTAs x 6 = 30 warps/SM at <= 64 registers
+#endif
 template <int NMIX, int HW, int SPLIT, bool ERR>
-__global__ void __launch_bounds__(Geo<NMIX, SPLIT>::kThreadsCta)
+__global__ void __launch_bounds__(Geo<NMIX, SPLIT>::kThreadsCta, MAE_DMOL_BWD_MINB)
 dmol_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ x, const float* __restrict__ g, int g_stride,
                 float g_mul, int ns, float* __restrict__ draw, int chunks, float* __restrict__ err, float* partial,
                 unsigned int* tickets) {
