@@ -269,6 +269,8 @@ dmol_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ x, cons
                 unsigned int* tickets) {
     using G = Geo<NMIX, SPLIT>;
     constexpr bool kCache = G::kK <= 5;  // keep local gradients in registers instead of recomputing
+    pdl_launch_dependents();             // the (tiny) successor may be placed while this grid drains
+    pdl_wait();                          // raw / x / g come from the predecessor in the stream
     __shared__ MergeSmem<NMIX, SPLIT> ms;
     __shared__ float scratch[32];
     __shared__ bool is_last;
@@ -748,7 +750,7 @@ int launch_bwd(const float* raw, const float* x, const float* g, int gs, float g
     const int chunks = HW / G::kPix;
     dim3 grid((unsigned)N, (unsigned)chunks);
     if (err != nullptr || with_err)
-        dmol_bwd_kernel<NMIX, HW, SPLIT, true><<<grid, G::kThreadsCta, 0, s>>>(raw, x, g, gs, gm, ns, draw, chunks, err, partial,
+        launch_pdl(dmol_bwd_kernel<NMIX, HW, SPLIT, true>, grid, dim3(G::kThreadsCta), 0, s, raw, x, g, gs, gm, ns, draw, chunks, err, partial,
                                                                               tickets);
     else
         dmol_bwd_kernel<NMIX, HW, SPLIT, false><<<grid, G::kThreadsCta, 0, s>>>(raw, x, g, gs, gm, ns, draw, chunks, nullptr,
@@ -884,6 +886,8 @@ namespace {
 // every training step; four 16-byte loads in flight per thread keep the real case at bandwidth.
 __global__ void __launch_bounds__(256) scale_inplace_kernel(float* __restrict__ data, int64_t n4, int64_t n,
                                                             const float* __restrict__ scale) {
+    pdl_launch_dependents();
+    pdl_wait();
     const float sc = scale[0];
     if (sc == 1.0f) return;
     float4* d4 = reinterpret_cast<float4*>(data);
@@ -917,6 +921,6 @@ extern "C" int mae_scale_inplace(float* data, int64_t n, const float* scale, mae
     MAE_REQUIRE((reinterpret_cast<uintptr_t>(data) & 15) == 0, MAE_ERR_ALIGN);
     int64_t blocks = ceil_div(n / 4 + 1, 256);
     if (blocks > 148 * 2) blocks = 148 * 2;
-    scale_inplace_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(data, n / 4, n, scale);
+    launch_pdl(scale_inplace_kernel, dim3((unsigned)blocks), dim3(256), 0, as_stream(stream), data, n / 4, n, scale);
     return launch_status();
 }

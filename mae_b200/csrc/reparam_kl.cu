@@ -14,6 +14,7 @@ __global__ void __launch_bounds__(kThreads)
 reparam_kl_fwd_kernel(const float* __restrict__ mu, int64_t mu_stride, const float* __restrict__ lv, int64_t lv_stride,
                       const float* __restrict__ eps, int ns, int D, float* __restrict__ z, float* __restrict__ kl) {
     __shared__ float scratch[32];
+    pdl_launch_dependents();   // the likelihood kernel behind it may be placed while this (tiny) grid drains
     const int b = blockIdx.x;
     const float* mu_b = mu + (int64_t)b * mu_stride;
     const float* lv_b = lv + (int64_t)b * lv_stride;
@@ -44,6 +45,7 @@ reparam_kl_bwd_kernel(const float* __restrict__ mu, int64_t mu_stride, const flo
                       int B, int ns, int D, float* __restrict__ dmu, float* __restrict__ dlv, int accumulate,
                       const float* __restrict__ extra_dmu, const float* __restrict__ extra_dlv,
                       const float* __restrict__ extra_scale) {
+    pdl_wait();                // gz / extra_* come from the predecessor in the stream
     const int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     if (t >= (int64_t)B * D) return;
     const int b = (int)(t / D), d = (int)(t % D);
@@ -107,9 +109,9 @@ extern "C" int mae_reparam_reg_bwd(const float* mu, int64_t mu_stride, const flo
     MAE_REQUIRE(mu_stride >= D && logvar_stride >= D, MAE_ERR_STRIDE);
     const int64_t blocks = ceil_div(B * D, kThreads);
     MAE_REQUIRE(blocks < (1ll << 31), MAE_ERR_SHAPE);
-    reparam_kl_bwd_kernel<<<(unsigned)blocks, kThreads, 0, as_stream(stream)>>>(
-        mu, mu_stride, logvar, logvar_stride, eps, gz, gkl, (int)B, (int)ns, (int)D, dmu, dlogvar, accumulate, extra_dmu,
-        extra_dlogvar, extra_scale);
+    launch_pdl(reparam_kl_bwd_kernel, dim3((unsigned)blocks), dim3(kThreads), 0, as_stream(stream), mu, mu_stride, logvar,
+               logvar_stride, eps, gz, gkl, (int)B, (int)ns, (int)D, dmu, dlogvar, accumulate, extra_dmu, extra_dlogvar,
+               extra_scale);
     return launch_status();
 }
 
