@@ -17,11 +17,12 @@ files load with ``strict=True``:
 Differences in mechanism (not in function): weight normalisation is evaluated explicitly in ``forward`` instead of through
 ``torch.nn.utils.weight_norm`` hooks, and masks are applied functionally (``weight_v * mask``) instead of overwriting
 ``weight_v.data`` on every call (masked entries are zero from construction on and receive a zero gradient, so they stay
-zero; outputs and state dicts are identical).  A per-step cache of the masked, normalised weights for the K-fold repeated
-flow evaluation is SURVEY §8f N4.
+zero; outputs and state dicts are identical).  ``cached_weights()`` memoises the effective weights across
+the sequential evaluations of the autoregressive directions.
 """
 from __future__ import annotations
 
+import contextlib
 import math
 from typing import List, Optional, Sequence, Tuple
 
@@ -30,10 +31,37 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 __all__ = ["LinearWeightNorm", "Conv2dWeightNorm", "ConvTranspose2dWeightNorm", "ResNet", "DeResNet", "MaskedLinear",
-           "MaskedConv2d", "PixelCNN", "MADE", "ReShape", "DenseNet", "PixelCNNPP", "MADE2d"]
+           "MaskedConv2d", "PixelCNN", "MADE", "ReShape", "DenseNet", "PixelCNNPP", "MADE2d", "cached_weights"]
 
 _INIT_STD = 0.05
 _STD_FLOOR = 1e-6
+
+_weight_cache = None     # id(layer) -> effective weight, only inside cached_weights() with autograd off
+
+
+@contextlib.contextmanager
+def cached_weights():
+    """Inside this context (and only while autograd is off) every weight-normalised / masked layer evaluates its effective
+    weight once and reuses it: the sequential directions of the autoregressive models (``Flow.forward``: D evaluations of
+    the same MADE, pixel-by-pixel ``decode``: H*W evaluations of the same PixelCNN) otherwise re-normalise and re-mask
+    every layer's weight on every call (masked.py:102-106).  SURVEY.md §8f N4."""
+    global _weight_cache
+    outer = _weight_cache
+    if outer is None:
+        _weight_cache = {}
+    try:
+        yield
+    finally:
+        _weight_cache = outer
+
+
+def _memo(layer, compute):
+    if _weight_cache is None or torch.is_grad_enabled():
+        return compute()
+    w = _weight_cache.get(id(layer))
+    if w is None:
+        w = _weight_cache[id(layer)] = compute()
+    return w
 
 
 def _rownorm(v: torch.Tensor, dim: int) -> torch.Tensor:
@@ -61,7 +89,7 @@ class _NormedWeight(nn.Module):
         self.weight_v = nn.Parameter(v)
 
     def weight(self) -> torch.Tensor:
-        return self.weight_v * (self.weight_g / _rownorm(self.weight_v, self.norm_dim))
+        return _memo(self, lambda: self.weight_v * (self.weight_g / _rownorm(self.weight_v, self.norm_dim)))
 
     def rescale(self, mean: torch.Tensor, std: torch.Tensor, init_scale: float) -> None:
         """Data-dependent init (Salimans & Kingma 2016): make the layer's output zero-mean with std ``init_scale``."""
@@ -251,8 +279,10 @@ class _MaskedWeight(nn.Module):
             self.register_parameter('bias', None)
 
     def masked_weight(self) -> torch.Tensor:
-        v = self.weight_v * self.mask
-        return v * (self.weight_g.exp() / (_rownorm(v, 0) + 1e-8))
+        def compute():
+            v = self.weight_v * self.mask
+            return v * (self.weight_g.exp() / (_rownorm(v, 0) + 1e-8))
+        return _memo(self, compute)
 
     def _rescale(self, mean, std, init_scale):
         gain = init_scale / (std + _STD_FLOOR)

@@ -23,7 +23,7 @@ from .decoder import BinaryImageDecoder, ColorImageDecoder
 from .encoder import EncoderCore
 from .flow import Flow
 from .networks import (MADE, MADE2d, Conv2dWeightNorm, ConvTranspose2dWeightNorm, DenseNet, DeResNet, LinearWeightNorm,
-                       PixelCNN, PixelCNNPP, ReShape, ResNet, _call, _run)
+                       PixelCNN, PixelCNNPP, ReShape, ResNet, _call, _run, cached_weights)
 
 __all__ = ["ResnetEncoderCoreBinaryImage28x28", "ResnetEncoderCoreColorImage32x32", "ResnetDecoderBinaryImage28x28",
            "ResnetDecoderColorImage32x32", "PixelCNNDecoderBinaryImage28x28", "AFMADE", "DenseNetEncoderCoreColorImage32x32",
@@ -213,11 +213,12 @@ class PixelCNNDecoderBinaryImage28x28(BinaryImageDecoder):
         side = 28
         cond = self.z_transform(z)
         canvas = torch.cat([cond.new_zeros(z.size(0), self.nc, side, side), cond], dim=1)
-        for i in range(side):
-            for j in range(side):
-                probs = self.core(canvas)[:, :, i, j]
-                canvas[:, :self.nc, i, j] = torch.bernoulli(probs) if random_sample else probs.ge(0.5).float()
-        return canvas[:, :self.nc], self.core(canvas)
+        with cached_weights():
+            for i in range(side):
+                for j in range(side):
+                    probs = self.core(canvas)[:, :, i, j]
+                    canvas[:, :self.nc, i, j] = torch.bernoulli(probs) if random_sample else probs.ge(0.5).float()
+            return canvas[:, :self.nc], self.core(canvas)
 
     def likelihood_input(self, x, z):
         """Bernoulli probabilities [B, ns, 784] of every pixel given the TRUE previous pixels and z [B, ns, nz]: what the
@@ -268,9 +269,10 @@ class AFMADEBlock(nn.Module):
         y = torch.zeros_like(x)
         logstd = torch.zeros_like(x)
         coords = range(self._input_size) if self.order == 'A' else reversed(range(self._input_size))
-        for i in coords:           # coordinate i of (mu, logstd) only depends on the coordinates already solved
-            mu, logstd = self._affine(y, False, 1.0)
-            y[:, i] = ((x - mu) / (logstd.exp() + eps))[:, i]
+        with cached_weights():
+            for i in coords:       # coordinate i of (mu, logstd) only depends on the coordinates already solved
+                mu, logstd = self._affine(y, False, 1.0)
+                y[:, i] = ((x - mu) / (logstd.exp() + eps))[:, i]
         return y, logstd.sum(dim=1)
 
 
@@ -447,9 +449,10 @@ class PixelCNNPPDecoderColorImage32x32(ColorImageDecoder):
         """Ancestral sampling, one pixel per network evaluation (image_decoders/pixelcnnpp.py:101-123)."""
         side = self.image_size
         x = z.new_zeros(z.size(0), self.nc, side, side)
-        for i in range(side):
-            for j in range(side):
-                x[:, :, i, j] = self.sample_pixels(*self.execute(z, x), random_sample)[:, :, i, j]
+        with cached_weights():
+            for i in range(side):
+                for j in range(side):
+                    x[:, :, i, j] = self.sample_pixels(*self.execute(z, x), random_sample)[:, :, i, j]
         return x, None
 
     def initialize(self, x, z, init_scale=1.0):
@@ -493,10 +496,11 @@ class AF2dMADEBlock(nn.Module):
         rows, cols = list(range(x.size(2))), list(range(x.size(3)))
         if self.order == 'B':
             rows, cols = rows[::-1], cols[::-1]
-        for i in rows:
-            for j in cols:      # position (i, j) of (mu, logstd) only depends on the positions already solved
-                mu, logstd = self._affine(y, False, 1.0)
-                y[:, :, i, j] = ((x - mu) / (logstd.exp() + eps))[:, :, i, j]
+        with cached_weights():
+            for i in rows:
+                for j in cols:  # position (i, j) of (mu, logstd) only depends on the positions already solved
+                    mu, logstd = self._affine(y, False, 1.0)
+                    y[:, :, i, j] = ((x - mu) / (logstd.exp() + eps))[:, :, i, j]
         return y, logstd.flatten(1).sum(dim=1)
 
 

@@ -80,3 +80,31 @@ def test_pixelcnn_decoder_sampling_runs(fixtures):
         img, probs = dec.decode(torch.randn(2, 4, device=DEV), random_sample=True)
     assert img.shape == (2, 1, 28, 28) and probs.shape == (2, 1, 28, 28)
     assert set(img.unique().tolist()) <= {0.0, 1.0} and 0.0 <= float(probs.min()) and float(probs.max()) <= 1.0
+
+
+def test_batched_calc_nll_equals_per_image_loop(monkeypatch):
+    """evaluate.calc_nll (several images x K per call, ragged last batch) == the reference's loop of one image per call
+    (experiments/color_image.py:260) when both consume the same noise"""
+    import stubs
+    from mae_b200 import evaluate
+    from mae_b200.modules import MAE, GaussianEncoder
+    torch.manual_seed(0)
+    model = MAE(GaussianEncoder(stubs.LinearCore(48, 6, True)), stubs.ColorLinearDecoder(6, 3, 4, 4)).to(DEV)
+    data = torch.rand(7, 3, 4, 4) * 2 - 1
+    k = 16
+    noise = torch.randn(7, k, 6, generator=torch.Generator().manual_seed(1))
+    cursor = {"i": 0}
+
+    def draw(mu, ns):
+        b = mu.size(0)
+        e = noise[cursor["i"]:cursor["i"] + b]
+        cursor["i"] += b
+        return e.to(mu.device)
+
+    monkeypatch.setattr(GaussianEncoder, "_draw_eps", staticmethod(draw))
+    (e1, r1, k1), iw1, bpd1 = evaluate.calc_nll(model, data, k, images_per_step=1)
+    cursor["i"] = 0
+    (e3, r3, k3), iw3, bpd3 = evaluate.calc_nll(model, data, k, images_per_step=3)
+    for a, b in ((e1, e3), (r1, r3), (k1, k3), (iw1, iw3), (bpd1, bpd3)):
+        assert abs(a - b) <= 1e-5 * max(1.0, abs(a)), (a, b)
+    assert model.training

@@ -135,3 +135,34 @@ def test_pixelcnnpp_is_causal():
     diff = (moved - base).abs().amax(dim=(0, 1))
     assert float(diff[:13].max()) == 0.0 and float(diff[13, :18].max()) == 0.0     # rows above, and up to (13, 17) itself
     assert float(diff[13, 18:].max()) > 0.0 and float(diff[14:].max()) > 0.0
+
+
+def test_cached_weights_give_identical_flow_samples():
+    """N4: memoised effective weights inside the sequential direction (no-grad) == recomputing them on every call; with
+    autograd on the cache is bypassed"""
+    from mae_b200.modules import AFMADE, networks
+    torch.manual_seed(0)
+    flow = AFMADE(6, 2)
+    z = torch.randn(3, 6)
+    with torch.no_grad():
+        y1, ld1 = flow.forward(z)                      # uses cached_weights() internally
+        calls = {"n": 0}
+        orig = networks._memo
+
+        def no_cache(layer, compute):
+            calls["n"] += 1
+            return compute()
+
+        networks._memo = no_cache
+        try:
+            y2, ld2 = flow.forward(z)
+        finally:
+            networks._memo = orig
+    assert calls["n"] > 0 and torch.equal(y1, y2) and torch.equal(ld1, ld2)
+    with networks.cached_weights():
+        w = flow.blocks[0].fwd.mu.input_layer
+        a = w.masked_weight()
+        assert w.masked_weight() is not a               # autograd on: never cached
+        with torch.no_grad():
+            b = w.masked_weight()
+            assert w.masked_weight() is b
