@@ -364,7 +364,9 @@ def bench_ours(args):
             "achieved": step_bytes / t_fused / 1e9, "peak": hbm_gbs, "unit": "GB/s", "frac": step_bytes / t_fused / 1e9 / hbm_gbs,
             "traffic": ncu_traffic(), "peak_source": peak_src, "bytes_per_launch": step_bytes, "us_per_launch": t_fused * 1e6,
             "bytes_moved_by_design": bwd_b, "frac_of_bytes_moved": bwd_b / t_fused / 1e9 / hbm_gbs,
-            "note": "algorithmic bytes = fwd 27.0 MB + bwd 53.2 MB (SURVEY 8d); the fused kernel reads raw once and writes d raw once",
+            "note": "algorithmic bytes = fwd 27.0 MB + bwd 53.2 MB (SURVEY 8d); the fused kernel reads raw once and writes d raw once; "
+                    "timed alone as back-to-back launches over the slab ring (> L2): consecutive launches overlap head/tail "
+                    "through programmatic dependent launch, an isolated launch (ncu) takes ~15-16 us",
             "dmol_bwd_alone": {"achieved": bwd_b / t_bwd / 1e9, "frac": bwd_b / t_bwd / 1e9 / hbm_gbs, "bytes_per_launch": bwd_b,
                                "us_per_launch": t_bwd * 1e6},
             "dmol_fwd_alone": {"achieved": fwd_b / t_fwd / 1e9, "frac": fwd_b / t_fwd / 1e9 / hbm_gbs, "bytes_per_launch": fwd_b,
