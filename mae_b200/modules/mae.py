@@ -47,25 +47,34 @@ class MAE(nn.Module):
         enc, dec = self.encoder, self.decoder
         z_shape_dec = dec.z_shape()
         if self._fusable():
-            # no flows: analytic KL.  Three autograd nodes: reparam (z), KL+MPD (side stream, overlaps with the
-            # decoder), likelihood+objective.
+            # two autograd nodes of ours around the decoder: (1) ops.encode_head = z plus the regulariser (KL + MPD, or MPD
+            # only when flows make the KL a Monte-Carlo estimate) forward AND backward on the side stream, beside the
+            # decoder (one cluster launch for B <= 128, D <= 64, else prepare -> tiles -> backward kernels back to back);
+            # (2) ops.loss_head = likelihood (DMOL: forward+backward in one pass over the raw output) + objective
             mu, logvar = enc.core(x)
             eps = enc._draw_eps(mu, nsamples)
-            if mu.size(0) >= 2:
-                # two autograd nodes: (1) z plus KL + MPD forward AND backward on the side stream, beside the decoder
-                # (one cluster launch for B <= 128, D <= 64, else prepare -> tiles -> backward kernels back to back);
-                # (2) likelihood + objective
-                z, eb = ops.encode_head(mu, logvar, eps, eta, gamma, free_bits)
-                dec_out = dec.likelihood_input(x, z.view(z.size(0), z.size(1), *z_shape_dec))
-                loss, stats, recon = ops.loss_head(dec_out, x, eb, dec.likelihood_kind, nsamples,
-                                                   getattr(dec, "nmix", 0), eta, gamma, free_bits)
-                KL, m_d, S = eb.kl, eb.m_d, eb.s
-            else:
-                z, _ = ops.reparam_kl(mu, logvar, eps, want_kl=False)
-                KL, m_d, S = ops.kl_mpd(mu, logvar, side_stream=True)
-                dec_out = dec.likelihood_input(x, z.view(z.size(0), z.size(1), *z_shape_dec))
-                loss, stats, recon = ops.loss_tail(dec_out, x, KL, m_d, S, dec.likelihood_kind, nsamples,
-                                                   getattr(dec, "nmix", 0), eta, gamma, free_bits)   # joins the side stream
+            flows = enc.prior_flow is not None or enc.posterior_flow is not None
+            z, eb = ops.encode_head(mu, logvar, eps, eta, gamma, free_bits, with_kl=not flows)
+            KL = None
+            if flows:
+                # gaussian_encoder.py:220-225: KL = mean_s(log q(z|x) - log p(z)) through the flows (PyTorch) and the
+                # log-density kernels
+                size = z.size()
+                z_normal = z
+                if enc.posterior_flow is not None:
+                    z, logdet = enc.posterior_flow.forward(z_normal.view(size[0] * size[1], *enc.posterior_flow.input_size()))
+                    z, logdet = z.view(size), logdet.view(size[0], size[1])
+                else:
+                    logdet = None
+                log_p = enc.log_probability_prior(z.reshape(size[0] * size[1], *size[2:])).view(size[0], size[1])
+                log_q = ops.log_prob_posterior(z_normal, mu, logvar, logdet)
+                KL = (log_q - log_p).mean(dim=1)
+            dec_out = dec.likelihood_input(x, z.view(z.size(0), z.size(1), *z_shape_dec))
+            loss, stats, recon = ops.loss_head(dec_out, x, eb, dec.likelihood_kind, nsamples, getattr(dec, "nmix", 0), eta, gamma,
+                                               free_bits, kl=KL)
+            if KL is None:
+                KL = eb.kl
+            m_d, S = eb.m_d, eb.s
         else:
             if isinstance(enc, GaussianEncoder):
                 z, KL, (m_d, S) = enc.encode(x, nsamples, _side_stream=True)   # MPD overlaps with the decoder
@@ -78,10 +87,10 @@ class MAE(nn.Module):
         return loss, recon, KL, stats[0], S, loss_mean, loss_std
 
     def _fusable(self) -> bool:
-        """True when loss() can use the fused nodes: Gaussian encoder without flows (analytic KL) and a decoder that
+        """True when loss() can use the fused nodes: a stock Gaussian encoder (with or without flows) and a decoder that
         keeps the stock ``reconstruct_error`` of one of the two likelihood heads."""
         enc, dec = self.encoder, self.decoder
-        if not isinstance(enc, GaussianEncoder) or enc.prior_flow is not None or enc.posterior_flow is not None:
+        if not isinstance(enc, GaussianEncoder):
             return False
         if type(enc).encode is not GaussianEncoder.encode:
             return False

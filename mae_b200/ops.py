@@ -976,7 +976,7 @@ class _EncodeHead(torch.autograd.Function):
     backward ONE launch: d(mu, logvar) = reparam backward of d z  +  d reg * (stored regulariser gradient)."""
 
     @staticmethod
-    def forward(ctx, mu, logvar, eps, eta, gamma, free_bits):
+    def forward(ctx, mu, logvar, eps, eta, gamma, free_bits, with_kl):
         ctx.set_materialize_grads(False)
         _req_cuda(mu, logvar, eps)
         dev = mu.device
@@ -986,7 +986,8 @@ class _EncodeHead(torch.autograd.Function):
         cs, ss = torch.cuda.current_stream(dev), _side_stream(dev)
         ss.wait_stream(cs)
         prev = _pending_join.pop(idx, None)
-        kl, m_d, s, reg, grads, (mu2, lv2) = kl_mpd_reg(mu, logvar, eta, gamma, free_bits, None, want_grad, launch_stream=ss)
+        kl, m_d, s, reg, grads, (mu2, lv2) = kl_mpd_reg(mu, logvar, eta, gamma, free_bits, None if with_kl else 0.0, want_grad,
+                                                        launch_stream=ss)
         ev = torch.cuda.Event()
         ev.record(ss)
         _pending_join[idx] = (ev, (prev, kl, m_d, s, reg, grads, mu2, lv2))
@@ -1007,7 +1008,7 @@ class _EncodeHead(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gz, g_reg, *_unused):
         if gz is None and g_reg is None:
-            return (None,) * 6
+            return (None,) * 7
         mu2, lv2, eps_c = ctx.saved_tensors
         ms, ls, b, ns, d, mu_shape, lv_shape = ctx.meta
         dev = mu2.device
@@ -1024,7 +1025,7 @@ class _EncodeHead(torch.autograd.Function):
                                                grads[1].data_ptr() if grads is not None else None, _ptr(g_reg), b, ns, d,
                                                dmu.data_ptr(), dlv.data_ptr(), 0, _stream()), "mae_reparam_reg_bwd")
         _count()
-        return dmu.view(mu_shape), dlv.view(lv_shape), None, None, None, None
+        return dmu.view(mu_shape), dlv.view(lv_shape), None, None, None, None, None
 
 
 class EncodedBatch:
@@ -1036,12 +1037,13 @@ class EncodedBatch:
 
 
 def encode_head(mu: torch.Tensor, logvar: torch.Tensor, eps: torch.Tensor, eta: float = 0.0, gamma: float = 0.0,
-                free_bits: float = 0.0):
-    """Training-sized batches (see :func:`fused_reg_supported`): z [B,ns,*z] and the encoder-side regulariser of
-    MAE.loss in one autograd node; -> (z, EncodedBatch).  Reference: gaussian_encoder.py:56-62, :162-188, :219 and
-    mae.py:132-139."""
-    z, reg, kl, m_d, s = _EncodeHead.apply(mu, logvar, eps, float(eta), float(gamma), float(free_bits))
-    return z, EncodedBatch(reg, kl, m_d, s, (float(eta), float(gamma), float(free_bits)))
+                free_bits: float = 0.0, with_kl: bool = True):
+    """z [B,ns,*z] and the encoder-side regulariser of MAE.loss in one autograd node; -> (z, EncodedBatch).
+    ``with_kl=False`` (encoders with flows: KL is a Monte-Carlo estimate computed by the caller, gaussian_encoder.py:220-225):
+    reg holds the MPD terms only and :func:`loss_head` takes the KL through its ``kl`` argument.
+    Reference: gaussian_encoder.py:56-62, :162-188, :219 and mae.py:132-139."""
+    z, reg, kl, m_d, s = _EncodeHead.apply(mu, logvar, eps, float(eta), float(gamma), float(free_bits), bool(with_kl))
+    return z, EncodedBatch(reg, kl if with_kl else None, m_d, s, (float(eta), float(gamma), float(free_bits)))
 
 
 class _LossTailReg(torch.autograd.Function):
@@ -1054,6 +1056,8 @@ class _LossTailReg(torch.autograd.Function):
     def forward(ctx, dec_out, x, reg, kl, m_d, s, kind, ns, nmix, eta, gamma, free_bits, defer, inv_batch):
         ctx.set_materialize_grads(False)
         _req_cuda(dec_out, x, reg, kl, m_d, s)
+        kl_ext = ctx.needs_input_grad[3]      # a differentiable KL from the caller (Monte-Carlo estimate with flows)
+        kl = kl.contiguous()
         lib = _lib_()
         dev = dec_out.device
         idx = dev.index if dev.index is not None else torch.cuda.current_device()
@@ -1086,9 +1090,9 @@ class _LossTailReg(torch.autograd.Function):
         else:
             join_side(dev)
             assemble()
-        ctx.save_for_backward(out_c, x_c)
+        ctx.save_for_backward(out_c, x_c, scalars)
         ctx.fused_grad = fused_grad
-        ctx.meta = (kind, b, ns, nmix, geom, dec_out.shape, defer, inv_batch)
+        ctx.meta = (kind, b, ns, nmix, geom, dec_out.shape, defer, inv_batch, kl_ext, (eta, gamma, free_bits))
         loss, stats = scalars[0], scalars[1:]
         ctx.mark_non_differentiable(stats, recon)
         return loss, stats, recon
@@ -1097,34 +1101,48 @@ class _LossTailReg(torch.autograd.Function):
     def backward(ctx, gloss, *_unused):
         if gloss is None:
             return (None,) * 14
-        out_c, x_c = ctx.saved_tensors
-        kind, b, ns, nmix, geom, out_shape, defer, inv_batch = ctx.meta
+        out_c, x_c, scalars = ctx.saved_tensors
+        kind, b, ns, nmix, geom, out_shape, defer, inv_batch, kl_ext, (eta, gamma, free_bits) = ctx.meta
         gloss = gloss.contiguous()
         dout = None
         if ctx.needs_input_grad[0]:
             dout = _likelihood_bwd(ctx, out_c, x_c, gloss, kind, b, ns, nmix, geom, inv_batch, out_shape)
+        dkl = None
+        if kl_ext:
+            # d loss / d KL_b = d loss * [mean KL >= free_bits] / B: needs the forward's scalars (side stream when deferred)
+            dev = out_c.device
+            if defer:
+                join_side(dev)
+            dkl = torch.empty(b, device=dev, dtype=torch.float32)
+            _lib.check(_lib_().mae_loss_assemble_bwd(gloss.data_ptr(), scalars.data_ptr(), None, b, ns, 0, eta, gamma, free_bits,
+                                                     inv_batch, None, dkl.data_ptr(), None, None, _stream()),
+                       "mae_loss_assemble_bwd")
+            _count()
         if defer:
             # nothing in the backward pass consumes the deferred objective kernel: join once the whole pass has been
             # enqueued, so that the encoder-side backward is not ordered behind it
             dev = out_c.device
             torch.autograd.Variable._execution_engine.queue_callback(lambda: join_side(dev))
-        return (dout, None, gloss if ctx.needs_input_grad[2] else None) + (None,) * 11
+        return (dout, None, gloss if ctx.needs_input_grad[2] else None, dkl) + (None,) * 10
 
 
 def loss_head(dec_out: torch.Tensor, x: torch.Tensor, enc: EncodedBatch, kind: str, ns: int, nmix: int = 10,
               eta: float = 0.0, gamma: float = 0.0, free_bits: float = 0.0, defer_join: bool = False,
-              inv_batch: float = 0.0):
+              inv_batch: float = 0.0, kl: Optional[torch.Tensor] = None):
     """Decoder output + :func:`encode_head` result -> objective of MAE.loss.  Returns (loss [], stats [5], recon [B]) like
     :func:`loss_tail`; KL / m_d / S are in ``enc``.  ``defer_join``: see :func:`loss_tail`.  ``inv_batch`` (batch-sharded
     runs): 1 / global batch; ``enc.kl`` is then the all-gathered KL vector and the returned loss holds this rank's share of
-    the reconstruction term plus the global regulariser.
+    the reconstruction term plus the global regulariser.  ``kl`` [B] (differentiable): the caller's KL estimate, required
+    when ``enc`` was made with ``with_kl=False``; it enters the free-bits clamp and receives its gradient from this node.
     Reference: mae.py:100-140 with the two reconstruct_error heads."""
     if kind not in ("dmol", "bernoulli"):
         raise ValueError("kind must be 'dmol' or 'bernoulli'")
     if enc.params != (float(eta), float(gamma), float(free_bits)):
         raise RuntimeError("loss_head: encode_head was called with different eta / gamma / free_bits")
-    return _LossTailReg.apply(dec_out, x, enc.reg, enc.kl, enc.m_d, enc.s, kind, int(ns), int(nmix), float(eta),
-                              float(gamma), float(free_bits), bool(defer_join), float(inv_batch))
+    if (kl is None) == (enc.kl is None):
+        raise RuntimeError("loss_head: pass kl exactly when encode_head was called with with_kl=False")
+    return _LossTailReg.apply(dec_out, x, enc.reg, enc.kl if kl is None else kl, enc.m_d, enc.s, kind, int(ns), int(nmix),
+                              float(eta), float(gamma), float(free_bits), bool(defer_join), float(inv_batch))
 
 
 def assemble_loss(err: torch.Tensor, kl: torch.Tensor, m_d: Optional[torch.Tensor], s: Optional[torch.Tensor],
