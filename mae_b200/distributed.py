@@ -62,14 +62,16 @@ class _ShardedKLMPD(torch.autograd.Function):
     joined by ``assemble_loss``.  The backward runs on the side stream too (it needs no collective)."""
 
     @staticmethod
-    def _compute(mu, logvar, head):
+    def _compute(mu, logvar, head, gathered=None):
         group, eng = head.group, head.engine
         world, rank = dist.get_world_size(group), dist.get_rank(group)
         b_loc = mu.size(0)
         d = mu[0].numel()
-        packed = _packed_parent(mu, logvar, b_loc, d)
-        if packed is None:
-            packed = torch.cat([mu.reshape(b_loc, d), logvar.reshape(b_loc, d)], dim=1)
+        packed = None
+        if gathered is None:
+            packed = _packed_parent(mu, logvar, b_loc, d)
+            if packed is None:
+                packed = torch.cat([mu.reshape(b_loc, d), logvar.reshape(b_loc, d)], dim=1)
         if head.check_equal_batches:
             lo = torch.tensor([b_loc], device=mu.device, dtype=torch.int64)
             hi = lo.clone()
@@ -78,7 +80,8 @@ class _ShardedKLMPD(torch.autograd.Function):
             if int(lo) != int(hi):
                 raise RuntimeError("ShardedHead needs the same local batch on every rank (got %d..%d): pad or drop the "
                                    "ragged tail batch" % (int(lo), int(hi)))
-        gathered = head._gather(packed)                         # the one exchange of the forward
+        if gathered is None:
+            gathered = head._gather(packed)                     # the one exchange of the forward
         b = world * b_loc
         mu_all, lv_all = gathered[:, :d], gathered[:, d:]       # strided views, no copy
         row0 = rank * b_loc
@@ -155,7 +158,22 @@ class _ShardedEncodeHead(torch.autograd.Function):
         world = head.world
 
         def chain():
-            kl_loc, m_d, s, kl_all, state, gathered, row0, b_loc = _ShardedKLMPD._compute(mu, logvar, head)
+            if hasattr(eng, "reg_rows_fused"):
+                # small global batch: gather, then ONE cluster launch for the whole regulariser of the gathered rows
+                b_loc, d = mu.size(0), mu[0].numel()
+                packed = _packed_parent(mu, logvar, b_loc, d)
+                if packed is None:
+                    packed = torch.cat([mu.reshape(b_loc, d), logvar.reshape(b_loc, d)], dim=1)
+                gathered = head._gather(packed)
+                row0 = head.rank * b_loc
+                out = eng.reg_rows_fused(gathered[:, :d], gathered[:, d:], row0, b_loc, eta, gamma, free_bits, want_grad)
+                if out is not None:
+                    m_d, s, kl_all, grads, reg = out
+                    return m_d, s, kl_all, gathered, grads, reg
+                state_in = gathered
+            else:
+                state_in = None
+            kl_loc, m_d, s, kl_all, state, gathered, row0, b_loc = _ShardedKLMPD._compute(mu, logvar, head, state_in)
             grads, reg = eng.mpd_rows_loss_backward(state, row0, b_loc, eta, gamma, free_bits, 1.0 / (world * b_loc), m_d,
                                                     kl_all, want_grad)
             return m_d, s, kl_all, gathered, grads, reg

@@ -16,7 +16,7 @@ from . import _lib
 
 __all__ = [
     "reparam_kl", "mpd", "mpd_forward_only", "bernoulli_recon_error", "dmol_recon_error", "log_prob_prior",
-    "log_prob_posterior", "iw_nll", "assemble_loss", "kl_mpd", "loss_tail", "loss_head", "encode_head", "kl_mpd_reg_fused", "kl_mpd_reg", "mpd_rows_loss_backward", "reparam_fwd",
+    "log_prob_posterior", "iw_nll", "assemble_loss", "kl_mpd", "loss_tail", "loss_head", "encode_head", "kl_mpd_reg_fused", "kl_mpd_reg", "mpd_rows_loss_backward", "reg_rows_fused", "reparam_fwd",
     "reparam_reg_bwd", "fused_reg_supported", "join_side", "launch_count", "reset_launch_count",
 ]
 
@@ -426,6 +426,21 @@ def mpd_rows_loss_backward(state: "MpdRowsState", row0: int, nrows: int, eta: fl
     _pool.give(state.ws)
     state.ws = None
     return grads, reg
+
+
+def reg_rows_fused(mu_all: torch.Tensor, logvar_all: torch.Tensor, row0: int, nrows: int, eta: float, gamma: float,
+                   free_bits: float, want_grad: bool = True):
+    """Batch-sharded runs whose GLOBAL batch fits the cluster kernel (B_global <= 128, D <= 64): the whole regulariser of
+    the gathered rows in one launch instead of prepare -> tiles -> gradients -> backward.  Every rank evaluates all rows
+    (a few microseconds) and keeps the gradient of its own.  -> (m_d, S, kl_all, grads [2,nrows,D] or None, reg), or None
+    when the shape is outside the kernel."""
+    mu2, _ = _rows(mu_all)
+    b, d = mu2.shape
+    if not fused_reg_supported(b, d, mu2.device):
+        return None
+    kl_all, m_d, s_, reg, grads, _ = kl_mpd_reg_fused(mu_all, logvar_all, eta, gamma, free_bits, None, want_grad)
+    own = grads[:, row0:row0 + nrows] if grads is not None else None      # [2, nrows, D]: rows are contiguous
+    return m_d, s_, kl_all, own, reg
 
 
 def reparam_fwd(mu: torch.Tensor, logvar: torch.Tensor, eps: torch.Tensor):

@@ -56,6 +56,8 @@ class PeerGather:
         _lib.check(self.lib.mae_allgather_rows(packed.data_ptr(), n, self.peer_table.data_ptr(), self.rank, self.world,
                                                self.slot_floats, out.data_ptr(),
                                                torch.cuda.current_stream(packed.device).cuda_stream), "mae_allgather_rows")
+        from . import ops
+        ops._count()
         return out
 
     def check(self) -> None:
