@@ -189,6 +189,30 @@ def test_mpd_full_size_properties(ops):
     check_close(s3, s1, rel=1e-5, what="S translation")
 
 
+def test_mpd_maximum_size_c5(ops):
+    """BASELINE C5 maximum (B = 65536, D = 256: the reference's [B,B,D] tensor would be 4.4 TB): the forward's permutation
+    invariance and, through the recompute backward (the two B x B matrices would be 34 GB, above the storage budget), the
+    translation property sum_i d/dmu_i = 0 and finiteness."""
+    from mae_b200 import synth
+    b, d = 65536, 256
+    mu, lv = synth.posterior_params(b, (d,), seed=21)
+    mu, lv = cu(mu), cu(lv)
+    m1, s1, _ = ops.mpd_forward_only(mu, lv)
+    perm = torch.randperm(b, device=DEV, generator=torch.Generator(DEV).manual_seed(6))
+    m2, s2, _ = ops.mpd_forward_only(mu[perm], lv[perm])
+    check_close(m2, m1, rel=2e-6, what="m_d permutation (B=65536)")
+    check_close(s2, s1, rel=2e-6, what="S permutation (B=65536)")
+    assert ops._mpd_pick_path(b, d, 0) == 2
+    mu.requires_grad_()
+    lv.requires_grad_()
+    m_d, s = ops.mpd(mu, lv)
+    assert torch.equal(m_d, m1) and torch.equal(s, s1)
+    (-torch.nn.functional.logsigmoid(m_d).sum() + s).backward()
+    assert torch.isfinite(mu.grad).all() and torch.isfinite(lv.grad).all()
+    col = mu.grad.double().sum(dim=0)
+    assert float(col.abs().max()) <= 1e-4 * float(mu.grad.double().abs().sum(dim=0).max())
+
+
 def test_mpd_backward_translation_property_tile_path(ops):
     from mae_b200 import synth
     mu, lv = synth.posterior_params(2500, (64,), seed=14)   # > 2048 -> stored-KL tile path automatically
