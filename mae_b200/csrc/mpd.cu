@@ -23,6 +23,7 @@
 //                        column panels (two more FFMA GEMMs); the row owner receives its complete gradient
 //                        (as the i and as the j argument), so there are no atomics and no reduce-scatter.
 // All cross-CTA reductions are ticketed and summed in a fixed order -> bit-reproducible results.
+#include <cstdlib>
 #include <type_traits>
 
 #include "common.cuh"
@@ -35,8 +36,8 @@ constexpr int kT = 64;         // tile edge (rows and columns per CTA tile)
 constexpr int kKC = 16;        // K chunk staged in shared memory per step
 constexpr int kNT = 256;       // threads per CTA: 16 x 16 threads, 4 x 4 micro-tile each
 constexpr int kLd = kT + 4;    // padded leading dimension (keeps float4 alignment)
-constexpr int kOC = 128;       // K columns (= 64 latent dims) of gradient owned by one CTA of the tile backward
-constexpr int kLdP = kOC + 4;
+// K columns of gradient owned by one CTA of the tile backward: template parameter OC = 128 (64 latent dims), or 64 when the
+// grid would otherwise leave SMs idle (B = 8192, D = 64: 128 row tiles x 1 chunk on 148 SMs -> 256 CTAs, 2 per SM)
 constexpr int kMaxFwdCtas = 592;  // 4 x 148; fixed so partial-sum order does not depend on the device
 constexpr int kBwdBatch = 16;      // panel rows fetched per batch by the stored-KL backward
 constexpr int kStats = 8;         // per-dimension column statistics: SA SB SAB S1 S2 R1 R2 S(a+b)
@@ -455,15 +456,33 @@ mpd_fwd_kernel(const float* __restrict__ Xp, const float* __restrict__ Yp, const
                 }
             }
             if (KL != nullptr) {
+                // a thread's columns come in groups of 4 consecutive ones (rc): 16-byte stores, a quarter warp covers 256
+                // contiguous bytes of the row (scalar stores wrote every 32-byte sector four times over)
+                if constexpr (TM >= 4) {
 #pragma unroll
-                for (int jj = 0; jj < TM; ++jj) KL[(int64_t)i * Bp + tj * T + rc(tx, jj)] = klv[ii][jj];
+                    for (int gq = 0; gq < TM / 4; ++gq)
+                        *reinterpret_cast<float4*>(KL + (int64_t)i * Bp + tj * T + rc(tx, gq * 4)) =
+                            make_float4(klv[ii][gq * 4], klv[ii][gq * 4 + 1], klv[ii][gq * 4 + 2], klv[ii][gq * 4 + 3]);
+                } else {
+#pragma unroll
+                    for (int jj = 0; jj < TM; ++jj) KL[(int64_t)i * Bp + tj * T + rc(tx, jj)] = klv[ii][jj];
+                }
             }
         }
         if (KLT != nullptr) {
 #pragma unroll
-            for (int jj = 0; jj < TM; ++jj)
+            for (int jj = 0; jj < TM; ++jj) {
+                float* dst = KLT + (int64_t)(tj * T + rc(tx, jj)) * Bp + ti * T;
+                if constexpr (TM >= 4) {
 #pragma unroll
-                for (int ii = 0; ii < TM; ++ii) KLT[(int64_t)(tj * T + rc(tx, jj)) * Bp + ti * T + rc(ty, ii)] = klv[ii][jj];
+                    for (int gq = 0; gq < TM / 4; ++gq)
+                        *reinterpret_cast<float4*>(dst + rc(ty, gq * 4)) =
+                            make_float4(klv[gq * 4][jj], klv[gq * 4 + 1][jj], klv[gq * 4 + 2][jj], klv[gq * 4 + 3][jj]);
+                } else {
+#pragma unroll
+                    for (int ii = 0; ii < TM; ++ii) dst[rc(ty, ii)] = klv[ii][jj];
+                }
+            }
         }
         total += (double)psum;
     }
@@ -638,18 +657,20 @@ mpd_bwd_small_kernel(const float* __restrict__ mu, int64_t mu_stride, const floa
 }
 
 // ----------------------------------------------------------------------- backward, recompute tiles (large B)
+template <int OC>
 struct BwdSmem {
     float W1T[kT][kLd], W2T[kT][kLd];  // [j][i]
-    float PY[kT][kLdP], PX[kT][kLdP];  // column panels of block J, this CTA's K chunk
+    float PY[kT][OC + 4], PX[kT][OC + 4];  // column panels of block J, this CTA's K chunk
     float XI[kKC][kLd], YI[kKC][kLd], XJ[kKC][kLd], YJ[kKC][kLd];  // recompute path only (last: the stored path omits them)
 };
-constexpr size_t kBwdStoredSmem = offsetof(BwdSmem, XI);
+template <int OC>
+constexpr size_t bwd_stored_smem() { return offsetof(BwdSmem<OC>, XI); }
 
 // grid: (row tiles, K chunks of kOC columns).  CTA owns rows [i0,i0+64) and gradient dims of its chunk.
 // STORED: the KL_ij / KL_ji tiles are read from the matrices the forward kept (one streaming pass over 2 B^2 floats)
 // instead of being recomputed (two K = 2D contractions per tile pair), which halves the backward's FFMA work.
-template <bool STORED>
-__global__ void __launch_bounds__(kNT, STORED ? 2 : 1)
+template <bool STORED, int OC, int MINB>
+__global__ void __launch_bounds__(kNT, MINB)
 mpd_bwd_tile_kernel(const float* __restrict__ mu, int64_t mu_stride, const float* __restrict__ lv, int64_t lv_stride,
                     const float* __restrict__ Xp, const float* __restrict__ Yp, const float* __restrict__ evec,
                     const float* __restrict__ fvec, const float4* __restrict__ Vp, const double* __restrict__ colstats,
@@ -658,20 +679,21 @@ mpd_bwd_tile_kernel(const float* __restrict__ mu, int64_t mu_stride, const float
                     int tr0, int ntc, float* __restrict__ dmu, float* __restrict__ dlv, int accumulate,
                     const float* __restrict__ KL, const float* __restrict__ KLT, int Bp) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    BwdSmem& sm = *reinterpret_cast<BwdSmem*>(smem_raw);
+    constexpr int NG = OC / 16;   // gradient columns per thread: groups of 4 at tx*4 (+64 for OC = 128)
+    BwdSmem<OC>& sm = *reinterpret_cast<BwdSmem<OC>*>(smem_raw);
     const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
     const int ti = tr0 + blockIdx.x;
     const int i0 = ti * kT;
-    const int kbase = blockIdx.y * kOC;
+    const int kbase = blockIdx.y * OC;
     const float m = (float)hdr->m;
     const float beta = weight_scale(g_S, S, B);
 
-    float G1[4][8], G2[4][8], rs1[4], rs2[4];
+    float G1[4][NG], G2[4][NG], rs1[4], rs2[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         rs1[i] = rs2[i] = 0.f;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) G1[i][j] = G2[i][j] = 0.f;
+        for (int j = 0; j < NG; ++j) G1[i][j] = G2[i][j] = 0.f;
     }
     float ei[4], fi[4];
 #pragma unroll
@@ -739,8 +761,8 @@ mpd_bwd_tile_kernel(const float* __restrict__ mu, int64_t mu_stride, const float
                 *reinterpret_cast<float4*>(&sm.W2T[tx * 4 + jj][ty * 4]) = make_float4(w2[0][jj], w2[1][jj], w2[2][jj], w2[3][jj]);
             }
             // column panels of block J restricted to this CTA's K chunk: 64 rows x 128 columns each
-            for (int q = tid; q < kT * (kOC / 4); q += kNT) {
-                const int r = q / (kOC / 4), c = (q % (kOC / 4)) * 4;
+            for (int q = tid; q < kT * (OC / 4); q += kNT) {
+                const int r = q / (OC / 4), c = (q % (OC / 4)) * 4;
                 float4 y = make_float4(0.f, 0.f, 0.f, 0.f), x = y;
                 if (kbase + c < Kp) {
                     y = *reinterpret_cast<const float4*>(Yp + (int64_t)(j0 + r) * Kp + kbase + c);
@@ -755,18 +777,20 @@ mpd_bwd_tile_kernel(const float* __restrict__ mu, int64_t mu_stride, const float
             for (int j = 0; j < kT; ++j) {
                 const float4 wa = *reinterpret_cast<const float4*>(&sm.W1T[j][ty * 4]);
                 const float4 wb = *reinterpret_cast<const float4*>(&sm.W2T[j][ty * 4]);
-                const float4 y0 = *reinterpret_cast<const float4*>(&sm.PY[j][tx * 4]);
-                const float4 y1 = *reinterpret_cast<const float4*>(&sm.PY[j][64 + tx * 4]);
-                const float4 x0 = *reinterpret_cast<const float4*>(&sm.PX[j][tx * 4]);
-                const float4 x1 = *reinterpret_cast<const float4*>(&sm.PX[j][64 + tx * 4]);
+                float yv[NG], xv[NG];
+#pragma unroll
+                for (int gq = 0; gq < NG / 4; ++gq) {
+                    const float4 yq = *reinterpret_cast<const float4*>(&sm.PY[j][gq * 64 + tx * 4]);
+                    const float4 xq = *reinterpret_cast<const float4*>(&sm.PX[j][gq * 64 + tx * 4]);
+                    yv[gq * 4 + 0] = yq.x; yv[gq * 4 + 1] = yq.y; yv[gq * 4 + 2] = yq.z; yv[gq * 4 + 3] = yq.w;
+                    xv[gq * 4 + 0] = xq.x; xv[gq * 4 + 1] = xq.y; xv[gq * 4 + 2] = xq.z; xv[gq * 4 + 3] = xq.w;
+                }
                 const float wav[4] = {wa.x, wa.y, wa.z, wa.w};
                 const float wbv[4] = {wb.x, wb.y, wb.z, wb.w};
-                const float yv[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
-                const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
 #pragma unroll
                 for (int ii = 0; ii < 4; ++ii)
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) {
+                    for (int c = 0; c < NG; ++c) {
                         G1[ii][c] = fmaf(wav[ii], yv[c], G1[ii][c]);
                         G2[ii][c] = fmaf(wbv[ii], xv[c], G2[ii][c]);
                     }
@@ -790,7 +814,7 @@ mpd_bwd_tile_kernel(const float* __restrict__ mu, int64_t mu_stride, const float
         const int i = i0 + ty * 4 + ii;
         if (i < row0 || i >= row1) continue;
 #pragma unroll
-        for (int h = 0; h < 4; ++h) {
+        for (int h = 0; h < NG / 2; ++h) {
             const int cb = (h >> 1) * 4 + (h & 1) * 2;           // register column of the pair (2d, 2d+1)
             const int kcol = kbase + (h >> 1) * 64 + tx * 4 + (h & 1) * 2;
             const int d = kcol >> 1;
@@ -929,15 +953,17 @@ extern "C" int mae_mpd_bwd(const float* mu, int64_t mu_stride, const float* logv
     }
     const int tr0 = (int)(row0 / kT);
     const int ntr = (int)(ceil_div(row0 + nrows, kT) - tr0);
-    const int nchunks = (int)ceil_div(L.Kp, kOC);
-    MAE_REQUIRE(nchunks <= 65535, MAE_ERR_SHAPE);
-    dim3 grid((unsigned)ntr, (unsigned)nchunks);
-    auto launch = [&](auto stored_tag) -> int {
+    auto launch = [&](auto stored_tag, auto oc_tag, auto minb_tag) -> int {
         constexpr bool STORED = decltype(stored_tag)::value;
-        const size_t smem = STORED ? kBwdStoredSmem : sizeof(BwdSmem);
-        cudaError_t e = cudaFuncSetAttribute(mpd_bwd_tile_kernel<STORED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        constexpr int OC = decltype(oc_tag)::value;
+        constexpr int MINB = decltype(minb_tag)::value;
+        const int nchunks = (int)ceil_div(L.Kp, OC);
+        if (nchunks > 65535) return MAE_ERR_SHAPE;
+        dim3 grid((unsigned)ntr, (unsigned)nchunks);
+        const size_t smem = STORED ? bwd_stored_smem<OC>() : sizeof(BwdSmem<OC>);
+        cudaError_t e = cudaFuncSetAttribute(mpd_bwd_tile_kernel<STORED, OC, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        mpd_bwd_tile_kernel<STORED><<<grid, kNT, smem, as_stream(stream)>>>(
+        mpd_bwd_tile_kernel<STORED, OC, MINB><<<grid, kNT, smem, as_stream(stream)>>>(
             mu, mu_stride, logvar, logvar_stride, at<float>(workspace, L.xp), at<float>(workspace, L.yp),
             at<float>(workspace, L.c), at<float>(workspace, L.l), at<float4>(workspace, L.vp),
             at<double>(workspace, L.colstats), at<double>(workspace, L.pivots), at<Hdr>(workspace, L.hdr), g_m, g_S, S, gkl,
@@ -945,7 +971,23 @@ extern "C" int mae_mpd_bwd(const float* mu, int64_t mu_stride, const float* logv
             STORED ? at<float>(workspace, L.kl) : nullptr, STORED ? at<float>(workspace, L.klt) : nullptr, (int)L.Bp);
         return MAE_OK;
     };
-    rc = (path == 3) ? launch(std::true_type{}) : launch(std::false_type{});
+    // 64-column chunks double the CTA count when 128-column chunks would not even fill the SMs once (stored path: the
+    // KL tiles are then streamed twice, which costs far less than idle SMs); the recompute path keeps 128
+    const bool narrow = path == 3 && (int64_t)ntr * ceil_div(L.Kp, 128) < 148 && L.Kp > 64;
+    using I1 = std::integral_constant<int, 1>;
+    using I2 = std::integral_constant<int, 2>;
+    using OC128 = std::integral_constant<int, 128>;
+    const int variant = []() { const char* e = getenv("MAE_MPD_BWD_VARIANT"); return e ? atoi(e) : 0; }();   // tuning only
+    if (path == 3) {
+        // grids that do not fill the SMs once (B = 8192, D = 64: 128 CTAs): one CTA per SM with the full register budget
+        // (160 registers, deeper load/FFMA overlap) measured 1.12 ms vs 1.21 ms for 64-column chunks x 2 CTAs/SM and
+        // 1.40 ms for 128 registers; larger grids keep 2 CTAs per SM
+        if (narrow && variant == 2) rc = launch(std::true_type{}, std::integral_constant<int, 64>{}, I2{});
+        else if (narrow) rc = launch(std::true_type{}, OC128{}, I1{});
+        else rc = launch(std::true_type{}, OC128{}, I2{});
+    } else {
+        rc = launch(std::false_type{}, OC128{}, I1{});
+    }
     if (rc != MAE_OK) return rc;
     return launch_status();
 }
