@@ -116,6 +116,40 @@ MAE_HD float dmol_component(const float mu[3], const float rho[3], const float k
     mean[2] = fmaf(c2, x[1], fmaf(c1, x[0], mu[2]));
     float T = 0.f;
     float d_cx[3], d_ls[3];
+    if (!GRAD) {
+        // forward only: the three channels share ONE reciprocal and ONE logarithm,
+        //   sum_c [log(sel_c / den_c) + lin_c] = log(prod sel_c / prod den_c) + sum lin_c,
+        // sel_c in (1e-5, 4], den_c = (1+e_hi)(1+e_lo) in [1, 4]: the products stay far inside the fp32 range.  Channels
+        // on the rare "approx" branch drop out of the products (sel = den = 1) and contribute through lin.
+        float sel_p = 1.0f, den_p = 1.0f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float ls = fmaxf(rho[c], kLogScaleMin);
+            const float cx = x[c] - mean[c];
+            const float s = fast_ex2(-kLog2e * ls);
+            const float sh = s * kBin;
+            const float hi = fmaf(s, cx, sh), lo = fmaf(s, cx, -sh);
+            const float eh = fast_ex2(-kLog2e * fabsf(hi)), el = fast_ex2(-kLog2e * fabsf(lo));
+            const float a = 1.0f + eh, b = 1.0f + el;
+            const float den = a * b;
+            const float num = (hi * lo > 0.f) ? fabsf(el - eh) : fmaf(-el, eh, 1.0f);
+            const bool is_up = x[c] > kUpper, is_low = x[c] < kLower;
+            float sel = is_up ? a : (is_low ? b : num);
+            float dn = den;
+            float lin = is_up ? -fmaxf(lo, 0.f) : (is_low ? fminf(hi, 0.f) : 0.f);
+            if (!is_up && !is_low && !(num > kDeltaMin * den)) {   // delta = num / den <= 1e-5
+                const float u = s * cx;
+                const float eu = fast_ex2(-kLog2e * fabsf(u));
+                lin = u - ls - 2.0f * (fmaxf(u, 0.f) + kLn2 * fast_lg2(1.0f + eu)) + kLog2Bin;
+                sel = 1.0f;
+                dn = 1.0f;
+            }
+            sel_p *= sel;
+            den_p *= dn;
+            T += lin;
+        }
+        return fmaf(fast_lg2(sel_p * fast_rcp(den_p)), kLn2, T);
+    }
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         const float ls = fmaxf(rho[c], kLogScaleMin);
