@@ -601,7 +601,7 @@ mpd_bwd_small_kernel(const float* __restrict__ mu, int64_t mu_stride, const floa
         const float ivb = active ? (float)pivots[3 * (int64_t)D + d] : 0.f;
         const float* kl_row = KL + (int64_t)i * Bp;    // KL_ij
         const float* klt_row = KLT + (int64_t)i * Bp;  // KL_ji
-        const float opb_i = 1.0f + pi.z, opt_i = 1.0f + pi.w;
+        const float opb_i = 1.0f + pi.z, opt_i = 1.0f + pi.w, opa_i = 1.0f + pi.y, oi = opt_i * ivb;
         const float4* vcol = Vp + d;
         for (int jb = ps * 32; jb < B; jb += 32 * PS) {
             // the 32 lanes fetch the weights of 32 partners at once (one coalesced line each), then broadcast
@@ -622,8 +622,8 @@ mpd_bwd_small_kernel(const float* __restrict__ mu, int64_t mu_stride, const floa
                     const float w2 = __shfl_sync(0xffffffffu, w2l, j0 + u);
                     const float dl = pi.x - pj[u].x;
                     gmu = fmaf(dl, fmaf(w1, 1.0f + pj[u].z, w2 * opb_i), gmu);
-                    glv += w1 * (fmaf(pi.y, pj[u].z, pi.y) + pj[u].z) -
-                           w2 * (fmaf(pj[u].y, pi.w, pj[u].y) + pi.w + dl * dl * opt_i * ivb);
+                    glv = fmaf(w1, fmaf(opa_i, pj[u].z, pi.y), glv);                                  // (a_i+1) b_j + a_i
+                    glv = fmaf(-w2, fmaf(opt_i, pj[u].y, fmaf(dl * dl, oi, pi.w)), glv);               // (t_i+1) a_j + t_i + dl^2 o_i
                 }
             }
         }

@@ -365,10 +365,11 @@ kl_mpd_loss_fused_kernel(const float* __restrict__ mu, int64_t mu_stride, const 
                         const float w2v[4] = {wb.x, wb.y, wb.z, wb.w};
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
+                            // a_i b_j + a_i + b_j = (a_i + 1) b_j + a_i ;  a_j t_i + a_j + t_i + dl^2 o_i = (t_i + 1) a_j + (t_i + dl^2 o_i)
                             const float dl = pi[r].x - pj[u].x;
                             gmu[r] = fmaf(dl, fmaf(w1v[u], pj[u].w, w2v[u] * pi[r].w), gmu[r]);
-                            glv[r] += w1v[u] * (fmaf(pi[r].y, pj[u].z, pi[r].y) + pj[u].z) -
-                                      w2v[u] * (fmaf(pj[u].y, ti[r], pj[u].y) + ti[r] + dl * dl * oi[r]);
+                            glv[r] = fmaf(w1v[u], fmaf(pi[r].y + 1.0f, pj[u].z, pi[r].y), glv[r]);
+                            glv[r] = fmaf(-w2v[u], fmaf(ti[r] + 1.0f, pj[u].y, fmaf(dl * dl, oi[r], ti[r])), glv[r]);
                         }
                     }
                 }
