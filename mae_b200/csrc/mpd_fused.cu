@@ -107,10 +107,11 @@ struct FusedSmem {
 
 // Shared-memory carve-up behind FusedSmem (all offsets multiples of 16 bytes):
 //   V    float4 [D][Bs]             {mc, a, b, r} of every (dim, row)
-//   U    union: part double [8][8][64] (column statistics per row group) | red float2 [512/NJ][RM][NJ] | gpart float [8][RM][2][64]
+//   U    union: part double [8][8][64] (column statistics per row group) | red float2 [8][RM][NJ] | gpart float [8][RM][2][64]
 template <int NJ>
 __host__ __device__ constexpr size_t fused_off_v() { return ((sizeof(FusedSmem<NJ>) + 15) / 16) * 16; }
-constexpr size_t kFusedUnionBytes = (size_t)kFG * kFStats * kFD * sizeof(double);   // 32 KB >= red, gpart for both NJ
+// union area: part 32 KB, red 8 * RM * NJ * 8 B = 16 KB (NJ = 64) / 64 KB (NJ = 128), gpart 16 / 32 KB
+static inline size_t fused_union_bytes(int nj) { return nj == 64 ? 32 * 1024 : 64 * 1024; }
 
 template <int NJ>
 __global__ void __launch_bounds__(kFT, 1)
@@ -259,34 +260,47 @@ kl_mpd_loss_fused_kernel(const float* __restrict__ mu, int64_t mu_stride, const 
     FUSED_STAMP(3);
     // ------------------------------------------------------------------ phase 2: KL_ij, KL_ji of the own rows
     {
-        constexpr int NDG = kFT / NJ;     // dim groups
-        constexpr int DPG = kFD / NDG;    // dims per group
+        // thread = (partner column j0 [+64], group of 8 latent dims): with two partner columns per thread (B > 64) every
+        // broadcast load of an own row's V serves two pairs and the two accumulation chains interleave
+        constexpr int NDG = kFT / 64;     // 8 dim groups
+        constexpr int DPG = kFD / NDG;    // 8 dims per group
+        constexpr int JPT = NJ / 64;      // partner columns per thread
         float2* red = reinterpret_cast<float2*>(U);   // [NDG][RM][NJ]
-        const int j = tid % NJ, dg = tid / NJ;
-        float a1[RM], a2[RM];
+        const int j0 = tid & 63, dg = tid >> 6;
+        float a1[JPT][RM], a2[JPT][RM];
 #pragma unroll
-        for (int r = 0; r < RM; ++r) a1[r] = a2[r] = 0.f;
-        if (j < B) {
+        for (int u = 0; u < JPT; ++u)
+#pragma unroll
+            for (int r = 0; r < RM; ++r) a1[u][r] = a2[u][r] = 0.f;
 #pragma unroll 2
-            for (int dd = 0; dd < DPG; ++dd) {
-                const int dc = dg * DPG + dd;
-                if (dc >= D) break;
-                const float4* vrow = V + dc * Bs;
-                const float4 vj = vrow[j];
+        for (int dd = 0; dd < DPG; ++dd) {
+            const int dc = dg * DPG + dd;
+            if (dc >= D) break;
+            const float4* vrow = V + dc * Bs;
+            float4 vj[JPT];
 #pragma unroll
-                for (int r = 0; r < RM; ++r) {
-                    if (r < R) {
-                        const float4 vi = vrow[i0 + r];   // warp-wide broadcast
-                        const float dl = vi.x - vj.x;
+            for (int u = 0; u < JPT; ++u) {
+                const int j = j0 + 64 * u;
+                vj[u] = j < B ? vrow[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int r = 0; r < RM; ++r) {
+                if (r < R) {
+                    const float4 vi = vrow[i0 + r];   // warp-wide broadcast
+#pragma unroll
+                    for (int u = 0; u < JPT; ++u) {
+                        const float dl = vi.x - vj[u].x;
                         const float q2 = dl * dl;
-                        a1[r] = fmaf(vi.y, vj.z, fmaf(q2, vj.w, a1[r]));
-                        a2[r] = fmaf(vj.y, vi.z, fmaf(q2, vi.w, a2[r]));
+                        a1[u][r] = fmaf(vi.y, vj[u].z, fmaf(q2, vj[u].w, a1[u][r]));
+                        a2[u][r] = fmaf(vj[u].y, vi.z, fmaf(q2, vi.w, a2[u][r]));
                     }
                 }
             }
         }
 #pragma unroll
-        for (int r = 0; r < RM; ++r) red[(dg * RM + r) * NJ + j] = make_float2(a1[r], a2[r]);
+        for (int u = 0; u < JPT; ++u)
+#pragma unroll
+            for (int r = 0; r < RM; ++r) red[(dg * RM + r) * NJ + j0 + 64 * u] = make_float2(a1[u][r], a2[u][r]);
         __syncthreads();
         float psum = 0.f;
         for (int item = tid; item < RM * NJ; item += kFT) {
@@ -423,7 +437,7 @@ bool fused_geom(int64_t B, int64_t D, FusedGeom& g) {
     if (bs < (int64_t)g.cluster * g.rows) bs = (int64_t)g.cluster * g.rows;
     g.bs = (int)(bs | 1);   // odd row pitch (in float4): conflict-free for lane = row and for lane = dim
     const size_t off_v = g.nj == 64 ? fused_off_v<64>() : fused_off_v<128>();
-    g.smem = off_v + (size_t)D * g.bs * sizeof(float4) + kFusedUnionBytes;
+    g.smem = off_v + (size_t)D * g.bs * sizeof(float4) + fused_union_bytes(g.nj);
     return g.smem <= 227 * 1024;
 }
 
