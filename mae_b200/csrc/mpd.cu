@@ -79,6 +79,7 @@ struct Layout {
 };
 
 constexpr int64_t kBigTileRows = 2048;  // padded batch from which the forward uses 128 x 128 tiles
+constexpr int64_t kSmallTileRows = 512;  // padded batch up to which it uses 32 x 32 tiles (latency regime)
 
 Layout make_layout(int64_t B, int64_t D) {
     Layout L;
@@ -297,27 +298,47 @@ mpd_prepare_kernel(const float* __restrict__ mu, int64_t mu_stride, const float*
     __threadfence();
     MAE_STAMP_ANY(hdr, 3);
 
-    // last CTA: ordered sum of the partials, closed-form m_d (fp64, additions and products only)
+    // last CTA: fixed-order sum of the per-CTA partials, one (statistic, dim) item per thread (the CTA count grows with
+    // B: a loop over the CTAs by only D threads made this step 8-10 us at B = 512), then the closed-form m_d (fp64)
     const double nb = (double)B;
+    const int G = (int)gridDim.x;
+    double (*sh)[64] = col_part[0];       // [kStats][64]: the sums of one chunk of 64 dims (the column partials are done)
     double msum = 0.0;
-    for (int d = tid; d < D; d += kNT) {
-        double s[kStats];
-#pragma unroll
-        for (int q = 0; q < kStats; ++q) s[q] = 0.0;
-        for (int bk = 0; bk < (int)gridDim.x; ++bk) {
-            const double* p = part + (int64_t)bk * kStats * D + d;
-#pragma unroll
-            for (int q = 0; q < kStats; ++q) s[q] += __ldcg(p + q * (int64_t)D);
+    for (int ch = 0; ch < nchunk; ++ch) {
+        for (int o = tid; o < kStats * 64; o += kNT) {
+            const int q = o >> 6, l = o & 63, d = ch * 64 + l;
+            if (d < D) {
+                const double* p = part + (int64_t)q * D + d;      // partials are [bk][q][d]
+                const int64_t step = (int64_t)kStats * D;
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+                int bk = 0;
+                for (; bk + 3 < G; bk += 4) {
+                    s0 += __ldcg(p + (bk + 0) * step);
+                    s1 += __ldcg(p + (bk + 1) * step);
+                    s2 += __ldcg(p + (bk + 2) * step);
+                    s3 += __ldcg(p + (bk + 3) * step);
+                }
+                for (; bk < G; ++bk) s0 += __ldcg(p + bk * step);
+                const double t = (s0 + s1) + (s2 + s3);
+                sh[q][l] = t;
+                colstats[q * (int64_t)D + d] = t;
+            }
         }
+        __syncthreads();
+        const int d = ch * 64 + tid;
+        if (tid < 64 && d < D) {
+            double s[kStats];
 #pragma unroll
-        for (int q = 0; q < kStats; ++q) colstats[q * (int64_t)D + d] = s[q];
-        // sum_{i!=j} (v_i r_j - 1)        = SA*SB - SAB + (B-1)*S(a+b)
-        // sum_{i!=j} (mu_i-mu_j)^2 r_j    = S2*R0 - 2*S1*R1 + B*R2,   R0 = (B + SB)/v_bar
-        const double r0 = (nb + s[1]) * pivots[3 * (int64_t)D + d];
-        const double tn = s[0] * s[1] - s[2] + (nb - 1.0) * s[7] + (s[4] * r0 - 2.0 * s[3] * s[5] + nb * s[6]);
-        const double md = half_inv_pairs * tn;
-        m_d_out[d] = (float)md;
-        msum += md;
+            for (int q = 0; q < kStats; ++q) s[q] = sh[q][tid];
+            // sum_{i!=j} (v_i r_j - 1)        = SA*SB - SAB + (B-1)*S(a+b)
+            // sum_{i!=j} (mu_i-mu_j)^2 r_j    = S2*R0 - 2*S1*R1 + B*R2,   R0 = (B + SB)/v_bar
+            const double r0 = (nb + s[1]) * pivots[3 * (int64_t)D + d];
+            const double tn = s[0] * s[1] - s[2] + (nb - 1.0) * s[7] + (s[4] * r0 - 2.0 * s[3] * s[5] + nb * s[6]);
+            const double md = half_inv_pairs * tn;
+            m_d_out[d] = (float)md;
+            msum += md;
+        }
+        __syncthreads();
     }
     msum = block_sum(msum, scratch);
     if (tid == 0) {
@@ -498,20 +519,25 @@ mpd_fwd_kernel(const float* __restrict__ Xp, const float* __restrict__ Yp, const
         is_last = (t == gridDim.x - 1);
     }
     __syncthreads();
-    if (is_last && tid == 0) {
+    if (is_last && tid < 32) {
         __threadfence();
+        // warp 0: lane-strided fixed-order sums of the per-CTA partials, then a fixed xor tree
         double s = 0.0;
         if (gridDim.x == 1) s = total;
-        else
-            for (int i = 0; i < (int)gridDim.x; ++i) s += __ldcg(part + i);
-        hdr->sumsq = s;
-        sumsq_out[0] = s;
-        if (S_out != nullptr) {
-            const double nb = (double)B;
-            S_out[0] = (float)sqrt(s / (nb * (nb - 1.0) - 1.0));
+        else {
+            for (int i = tid; i < (int)gridDim.x; i += 32) s += __ldcg(part + i);
+            s = warp_sum(s);
         }
-        hdr->ticket_fwd = 0u;
-        MAE_STAMP_ANY(hdr, 11);
+        if (tid == 0) {
+            hdr->sumsq = s;
+            sumsq_out[0] = s;
+            if (S_out != nullptr) {
+                const double nb = (double)B;
+                S_out[0] = (float)sqrt(s / (nb * (nb - 1.0) - 1.0));
+            }
+            hdr->ticket_fwd = 0u;
+            MAE_STAMP_ANY(hdr, 11);
+        }
     }
 }
 
@@ -904,7 +930,9 @@ extern "C" int mae_mpd_fwd(void* workspace, int64_t workspace_bytes, int64_t B, 
             at<Hdr>(workspace, L.hdr), at<double>(workspace, L.part_fwd), (int)B, (int)L.Kp, (int)row0, (int)(row0 + nrows), tr0,
             ntr, ntc, klp, kltp, (int)L.Bp, sumsq, S);
     };
-    if (L.Bp <= 256) launch(std::integral_constant<int, 2>{});        // small batches: 32 x 32 tiles, more CTAs, less latency
+    const int tm_env = []() { const char* e = getenv("MAE_MPD_FWD_TM"); return e ? atoi(e) : 0; }();   // tuning only
+    const int64_t small_limit = tm_env == 2 ? 1024 : (tm_env == 4 ? 256 : kSmallTileRows);
+    if (L.Bp <= small_limit) launch(std::integral_constant<int, 2>{});   // small batches: 32 x 32 tiles, more CTAs, less latency
     else if (L.Bp < kBigTileRows) launch(std::integral_constant<int, 4>{});   // 64 x 64
     else launch(std::integral_constant<int, 8>{});                    // 128 x 128, 8 x 8 micro-tiles: FFMA-bound regime
     return launch_status();
