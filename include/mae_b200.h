@@ -233,13 +233,15 @@ int mae_log_prob_posterior_bwd(const float* z_normal, const float* g,
  *   z_post_normal [B,K,D] + logdet_post [B,K] (nullable = 0), mu/logvar [B,D]  ->
  *   nll_elbo[b] = -mean_k log_iw ; recon[b] = -mean_k log_gen ; kl[b] = mean_k (log q - log p) ;
  *   nll_iw[b]   = -(max_k log_iw + log sum_k exp(log_iw - max)) + log K ,  log_iw = log_gen + log p - log q
+ *   gen_scale multiplies log_gen on the fly: -1 feeds the reconstruction ERROR written by mae_dmol_fwd / mae_bernoulli_fwd
+ *   directly (log p(x|z) = -error, decoder.py log_probability), saving a negation pass.
  *   workspace: mae_iw_nll_workspace_bytes(B, K) bytes (per-chunk partial states + tickets), zero-filled once.
  */
 int64_t mae_iw_nll_workspace_bytes(int64_t B, int64_t K);
 int mae_iw_nll(const float* log_gen, const float* z_prior_normal, const float* logdet_prior,
                const float* z_post_normal, const float* logdet_post,
                const float* mu, int64_t mu_stride, const float* logvar, int64_t logvar_stride,
-               int64_t B, int64_t K, int64_t D,
+               int64_t B, int64_t K, int64_t D, float gen_scale,
                float* nll_elbo, float* recon, float* kl, float* nll_iw,
                void* workspace, int64_t workspace_bytes, mae_stream_t stream);
 

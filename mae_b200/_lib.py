@@ -35,7 +35,7 @@ SIGNATURES = {
     "mae_log_prob_prior_bwd": [_P, _P, _I64, _I64, _P, _P],
     "mae_log_prob_posterior_fwd": [_P, _P, _P, _I64, _P, _I64, _I64, _I64, _I64, _P, _P],
     "mae_log_prob_posterior_bwd": [_P, _P, _P, _I64, _P, _I64, _I64, _I64, _I64, _P, _P, _P, _P],
-    "mae_iw_nll": [_P, _P, _P, _P, _P, _P, _I64, _P, _I64, _I64, _I64, _I64, _P, _P, _P, _P, _P, _I64, _P],
+    "mae_iw_nll": [_P, _P, _P, _P, _P, _P, _I64, _P, _I64, _I64, _I64, _I64, _F, _P, _P, _P, _P, _P, _I64, _P],
     "mae_loss_assemble_fwd": [_P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _F, _F, _F, _F, _P, _P, _P],
     "mae_loss_assemble_bwd": [_P, _P, _P, _I64, _I64, _I64, _F, _F, _F, _F, _P, _P, _P, _P, _P],
     "mae_dmol_fwd_bwd": [_P, _P, _F, _I64, _I64, _I64, _I64, _P, _P, _P],

@@ -376,6 +376,7 @@ template <int NMIX, int HW, int MINB>
 __global__ void __launch_bounds__(kVecThreads, MINB)
 dmol_fwd_vec4_kernel(const float* __restrict__ raw, const float* __restrict__ x, int ns, int chunks, float* __restrict__ err,
                      float* partial, unsigned int* tickets) {
+    pdl_launch_dependents();   // the tiny IW / objective kernel behind it may be placed while this grid drains
     __shared__ float scratch[32];
     __shared__ bool is_last;
     const int64_t n = blockIdx.x;

@@ -92,10 +92,12 @@ __global__ void __launch_bounds__(kThreads)
 iw_nll_kernel(const float* __restrict__ log_gen, const float* __restrict__ zp, const float* __restrict__ ldp,
               const float* __restrict__ zq, const float* __restrict__ ldq, const float* __restrict__ mu, int64_t mu_stride,
               const float* __restrict__ lv, int64_t lv_stride, int K, int D, int chunks, float* part, unsigned int* tickets,
-              float* __restrict__ nll_elbo, float* __restrict__ recon, float* __restrict__ kl, float* __restrict__ nll_iw) {
+              float* __restrict__ nll_elbo, float* __restrict__ recon, float* __restrict__ kl, float* __restrict__ nll_iw,
+              float gen_scale) {
     __shared__ IwState sh[kWarps];
     __shared__ float scratch[32];
     __shared__ bool is_last;
+    pdl_wait();   // log_gen comes from the likelihood kernel right before it in the stream
     const int b = blockIdx.x, chunk = blockIdx.y;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const float* mr = mu + (int64_t)b * mu_stride;
@@ -124,7 +126,7 @@ iw_nll_kernel(const float* __restrict__ log_gen, const float* __restrict__ zp, c
         aq = warp_sum(aq);
         const float lp = -0.5f * (ap + cst) + (ldp ? ldp[n] : 0.f);
         const float lq = -0.5f * (lsum + aq + cst) + (ldq ? ldq[n] : 0.f);
-        const float lg = log_gen[n];
+        const float lg = gen_scale * log_gen[n];
         const float liw = lg + lp - lq;
         lse.push(liw);
         s_iw += liw;
@@ -250,8 +252,8 @@ extern "C" int64_t mae_iw_nll_workspace_bytes(int64_t B, int64_t K) {
 
 extern "C" int mae_iw_nll(const float* log_gen, const float* z_prior_normal, const float* logdet_prior,
                           const float* z_post_normal, const float* logdet_post, const float* mu, int64_t mu_stride,
-                          const float* logvar, int64_t logvar_stride, int64_t B, int64_t K, int64_t D, float* nll_elbo,
-                          float* recon, float* kl, float* nll_iw, void* workspace, int64_t workspace_bytes,
+                          const float* logvar, int64_t logvar_stride, int64_t B, int64_t K, int64_t D, float gen_scale,
+                          float* nll_elbo, float* recon, float* kl, float* nll_iw, void* workspace, int64_t workspace_bytes,
                           mae_stream_t stream) {
     using namespace mae;
     MAE_REQUIRE(log_gen && z_prior_normal && z_post_normal && mu && logvar && nll_elbo && recon && kl && nll_iw && workspace,
@@ -262,9 +264,10 @@ extern "C" int mae_iw_nll(const float* log_gen, const float* z_prior_normal, con
     MAE_REQUIRE(workspace_bytes >= w.total, MAE_ERR_WORKSPACE);
     MAE_REQUIRE(w.chunks <= 65535, MAE_ERR_SHAPE);
     dim3 grid((unsigned)B, (unsigned)w.chunks);
-    iw_nll_kernel<<<grid, kThreads, 0, as_stream(stream)>>>(
-        log_gen, z_prior_normal, logdet_prior, z_post_normal, logdet_post, mu, mu_stride, logvar, logvar_stride, (int)K, (int)D,
-        (int)w.chunks, reinterpret_cast<float*>(static_cast<char*>(workspace) + w.part_off),
-        reinterpret_cast<unsigned int*>(static_cast<char*>(workspace) + w.ticket_off), nll_elbo, recon, kl, nll_iw);
+    launch_pdl(iw_nll_kernel, grid, dim3(kThreads), 0, as_stream(stream), log_gen, z_prior_normal, logdet_prior, z_post_normal,
+               logdet_post, mu, mu_stride, logvar, logvar_stride, (int)K, (int)D, (int)w.chunks,
+               reinterpret_cast<float*>(static_cast<char*>(workspace) + w.part_off),
+               reinterpret_cast<unsigned int*>(static_cast<char*>(workspace) + w.ticket_off), nll_elbo, recon, kl, nll_iw,
+               gen_scale);
     return launch_status();
 }

@@ -14,7 +14,7 @@ from typing import Optional
 import torch
 
 
-def calc_nll(model, data: torch.Tensor, k: int, images_per_step: int = 4, sharded=None, device: Optional[torch.device] = None):
+def calc_nll(model, data: torch.Tensor, k: int, images_per_step: int = 8, sharded=None, device: Optional[torch.device] = None):
     """model: ``mae_b200.modules.MAE``; data: [N, *x] tensor (host or device) of test images; k: importance samples.
     -> ((nll_elbo, recon, kl), nll_iw, bits_per_dim) as Python floats, averaged over the N images (all ranks return the
     global averages when ``sharded`` is given)."""

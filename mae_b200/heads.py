@@ -57,6 +57,6 @@ def iw_eval_color(raw, x, z, mu, logvar, nmix=10, z_prior_normal: Optional[torch
     raw [B*K,10*nmix,H,W], x [B,3,H,W], z [B,K,D] -> ((nll_elbo, recon, kl), nll_iw), each [B]."""
     with torch.no_grad():
         k = z.size(1)
-        log_gen = ops.dmol_recon_error(raw, x, k, nmix).neg_()
+        err = ops.dmol_recon_error(raw, x, k, nmix)          # log p(x|z) = -err: the IW kernel applies the sign
         zp = z if z_prior_normal is None else z_prior_normal
-        return ops.iw_nll(log_gen, zp, logdet_prior, z, logdet_post, mu, logvar)
+        return ops.iw_nll(err, zp, logdet_prior, z, logdet_post, mu, logvar, gen_scale=-1.0)

@@ -121,9 +121,16 @@ class MAE(nn.Module):
             else:
                 z_prior_normal, logdet_prior = prior_flow.backward(z.view(batch * k, *prior_flow.input_size()))
             post_flow = getattr(enc, 'posterior_flow', None)
-            log_gen = self.decoder.log_probability(x, z.view(batch, k, *self.decoder.z_shape()))
+            dec = self.decoder
+            zd = z.view(batch, k, *dec.z_shape())
+            stock = any(isinstance(dec, base) and type(dec).log_probability is base.log_probability
+                        for base in (BinaryImageDecoder, ColorImageDecoder))
+            if stock:   # log p(x|z) = -reconstruct_error: the IW kernel applies the sign, no negation pass
+                log_gen, scale = dec.reconstruct_error(x, zd), -1.0
+            else:
+                log_gen, scale = dec.log_probability(x, zd), 1.0
             return ops.iw_nll(log_gen, z_prior_normal, logdet_prior, z_post_normal,
-                              logdet_post if post_flow is not None else None, mu, logvar)
+                              logdet_post if post_flow is not None else None, mu, logvar, gen_scale=scale)
 
     @classmethod
     def from_params(cls, params: Dict) -> "MAE":

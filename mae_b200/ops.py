@@ -647,8 +647,10 @@ def log_prob_posterior(z_normal: torch.Tensor, mu: torch.Tensor, logvar: torch.T
 # ------------------------------------------------------------------------------------------------
 @torch.no_grad()
 def iw_nll(log_gen: torch.Tensor, z_prior_normal: torch.Tensor, logdet_prior: Optional[torch.Tensor],
-           z_post_normal: torch.Tensor, logdet_post: Optional[torch.Tensor], mu: torch.Tensor, logvar: torch.Tensor):
-    """Returns ((nll_elbo, recon, kl), nll_iw), each [B].  Reference: mae.py:203-215 + utils.py:23-38."""
+           z_post_normal: torch.Tensor, logdet_post: Optional[torch.Tensor], mu: torch.Tensor, logvar: torch.Tensor,
+           gen_scale: float = 1.0):
+    """Returns ((nll_elbo, recon, kl), nll_iw), each [B].  ``gen_scale=-1`` takes the reconstruction ERROR [B,K] in place of
+    log p(x|z) (no negation pass).  Reference: mae.py:203-215 + utils.py:23-38."""
     _req_cuda(log_gen, z_prior_normal, logdet_prior, z_post_normal, logdet_post, mu, logvar)
     b, k = log_gen.shape
     zq = z_post_normal.reshape(b, k, -1).contiguous()
@@ -663,7 +665,7 @@ def iw_nll(log_gen: torch.Tensor, z_prior_normal: torch.Tensor, logdet_prior: Op
     lib = _lib_()
     ws = _pool.take(max(int(lib.mae_iw_nll_workspace_bytes(b, k)), 256), lg.device)
     _lib.check(lib.mae_iw_nll(lg.data_ptr(), zp.data_ptr(), _ptr(ldp), zq.data_ptr(), _ptr(ldq), mu2.data_ptr(), ms,
-                              lv2.data_ptr(), ls, b, k, d, out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(),
+                              lv2.data_ptr(), ls, b, k, d, float(gen_scale), out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(),
                               out[3].data_ptr(), ws.data_ptr(), ws.numel(), _stream()), "mae_iw_nll")
     _count()
     _pool.give(ws)
