@@ -373,11 +373,12 @@ def bench_ours(args):
                                "us_per_launch": t_fwd * 1e6},
             "step": {"bytes": step_bytes, "us": dt / args.steps * 1e6, "frac": step_bytes / (dt / args.steps) / 1e9 / hbm_gbs}}
 
+    c4 = bench_c4(dev, hbm_gbs, world) if not args.no_extra else {}      # every rank: its shard of the evaluation
     out = None
     if rank == 0:
-        extra = {}
+        extra = dict(c4)
         if world == 1 and not args.no_extra:
-            extra = bench_extra(dev, hbm_gbs)
+            extra = bench_extra(dev, hbm_gbs, c4)
         cpu = cpu_baseline_c3(budget_s=12.0) if not args.no_cpu else None
         value = world * batch * args.steps / dt
         out = {
@@ -401,9 +402,11 @@ def bench_ours(args):
 
 
 # ------------------------------------------------------------------------------- secondary workloads (N=1)
-def bench_extra(dev, hbm_gbs):
-    """C4 (IW-NLL eval), C1/C2 (binary head) and C5 (MPD microbench) as secondary numbers with their own rooflines."""
-    from mae_b200 import heads, ops, synth
+def bench_c4(dev, hbm_gbs, world=1):
+    """C4 (IW-NLL eval) on every rank's own shard of synthetic images (no communication but the final reduction, §8e);
+    throughput = images of all ranks / max time over ranks."""
+    import torch.distributed as dist
+    from mae_b200 import heads
     res = {}
     stream = torch.cuda.current_stream()
     # ---- C4: K=512 samples per image, 8 images per launch, ring of 3 slabs (3 x 1.68 GB) > L2; each slab's evaluation
@@ -433,15 +436,32 @@ def bench_extra(dev, hbm_gbs):
             outs.append(heads.iw_eval_color(*sl, 10))
         graphs.append(gr)
 
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
     t = time_kernel(lambda i: graphs[i % 3].replay(), 30, stream)
-    res["c4_iw_nll_eval"] = {"metric": "iw_nll_eval_images_per_s", "value": nimg / t, "unit": "images/s",
+    if world > 1:
+        tt = torch.tensor([t], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t = float(tt)
+    res["c4_iw_nll_eval"] = {"metric": "iw_nll_eval_images_per_s", "value": world * nimg / t, "unit": "images/s", "n_gpus": world,
+                             "scaling": "weak (8 images x K=512 per launch per GPU; test images are sharded, one final all-reduce)",
                              "config": "CIFAR shapes, K=512, %d images/launch, ring of 3 slabs (%.1f GB) > L2, CUDA graph" % (nimg, 3 * nimg * k * 100 * 1024 * 4 / 1e9),
                              "us_per_image": t / nimg * 1e6,
-                             "roofline": {"bound": "hbm", "achieved": nimg * per_img / t / 1e9, "peak": hbm_gbs,
+                             "roofline": {"bound": "hbm", "achieved_per_gpu": nimg * per_img / t / 1e9, "peak": hbm_gbs,
                                           "frac": nimg * per_img / t / 1e9 / hbm_gbs, "bytes_per_image": per_img}}
     del graphs, outs
     del slabs
     torch.cuda.empty_cache()
+    return res
+
+
+def bench_extra(dev, hbm_gbs, c4):
+    """C4 (IW-NLL eval), C1/C2 (binary head) and C5 (MPD microbench) as secondary numbers with their own rooflines."""
+    from mae_b200 import heads, ops, synth
+    res = {}
+    stream = torch.cuda.current_stream()
+    res.update(c4)
     # ---- C1/C2: binary head fwd+bwd, B=100, D=64 (launch-latency-bound: 1.57 MB / 10 MFLOP per step)
     h = synth.binary_head(100, 1, 784)
     mu0, lv0 = synth.posterior_params(100, (64,))
