@@ -144,6 +144,8 @@ mpd_prepare_kernel(const float* __restrict__ mu, int64_t mu_stride, const float*
     const int blk = blockIdx.x;
     const int i0 = blk * R;
     constexpr int kWarps = kNT / 32;
+    pdl_wait();                // mu / logvar may come from the gather kernel right before it in the stream
+    pdl_launch_dependents();   // the tile kernel may be placed while this grid (and its last-CTA reduction) drains
 
     MAE_STAMP(hdr, 0);
     for (int r = tid; r < R; r += kNT) {
@@ -392,6 +394,8 @@ mpd_fwd_kernel(const float* __restrict__ Xp, const float* __restrict__ Yp, const
     __shared__ double scratch[32];
     __shared__ bool is_last;
     const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    pdl_wait();                // panels, E / F and m come from mpd_prepare_kernel
+    pdl_launch_dependents();   // (after the wait: successors are placed one kernel ahead, not a whole chain)
     MAE_STAMP(hdr, 8);
     const float m = (float)hdr->m;
     double total = 0.0;
@@ -554,6 +558,8 @@ mpd_loss_grads_kernel(const float* __restrict__ m_d, const float* __restrict__ S
                       float* __restrict__ gkl, float* __restrict__ reg) {
     __shared__ double scratch[32];
     const int tid = threadIdx.x;
+    pdl_wait();                // S comes from the tile kernel right before it
+    pdl_launch_dependents();
     double ks = 0.0, ls = 0.0;
     if (kl_all != nullptr)
         for (int i = tid; i < B; i += kNT) ks += (double)kl_all[i];
@@ -611,6 +617,7 @@ mpd_bwd_small_kernel(const float* __restrict__ mu, int64_t mu_stride, const floa
     constexpr int kItems = (kNT / 32) / PS;   // (row, dim-chunk) items per CTA
     __shared__ float red[2][kNT / 32][32];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    pdl_wait();                // g_m / g_S / gkl may come from mpd_loss_grads_kernel right before it
     const int item_local = w / PS, ps = w % PS;
     const int nd32 = (D + 31) / 32;
     const int64_t item = (int64_t)blockIdx.x * kItems + item_local;
@@ -894,7 +901,7 @@ extern "C" int mae_mpd_prepare(const float* mu, int64_t mu_stride, const float* 
     int rc = check_common(B, D, workspace, workspace_bytes, L);
     if (rc != MAE_OK) return rc;
     MAE_REQUIRE(mu_stride >= D && logvar_stride >= D, MAE_ERR_STRIDE);
-    mpd_prepare_kernel<<<(unsigned)L.prep_grid, kNT, (size_t)(3 * L.prep_rows * sizeof(double)), as_stream(stream)>>>(
+    launch_pdl(mpd_prepare_kernel, dim3((unsigned)L.prep_grid), dim3(kNT), (size_t)(3 * L.prep_rows * sizeof(double)), as_stream(stream),
         mu, mu_stride, logvar, logvar_stride, (int)B, (int)D, (int)L.Kp, (int)L.prep_rows, (int)L.Bp,
         at<float>(workspace, L.xp), at<float>(workspace, L.yp),
         at<float4>(workspace, L.vp), at<float>(workspace, L.c), at<float>(workspace, L.l), at<double>(workspace, L.part_prep),
@@ -925,7 +932,7 @@ extern "C" int mae_mpd_fwd(void* workspace, int64_t workspace_bytes, int64_t B, 
         const int ntc = (int)(L.Bp / T);
         const int64_t ntiles = (int64_t)ntr * ntc;
         const int grid = (int)(ntiles < kMaxFwdCtas ? ntiles : kMaxFwdCtas);
-        mpd_fwd_kernel<TM><<<grid, kNT, 0, as_stream(stream)>>>(
+        launch_pdl(mpd_fwd_kernel<TM>, dim3((unsigned)grid), dim3(kNT), 0, as_stream(stream),
             at<float>(workspace, L.xp), at<float>(workspace, L.yp), at<float>(workspace, L.c), at<float>(workspace, L.l),
             at<Hdr>(workspace, L.hdr), at<double>(workspace, L.part_fwd), (int)B, (int)L.Kp, (int)row0, (int)(row0 + nrows), tr0,
             ntr, ntc, klp, kltp, (int)L.Bp, sumsq, S);
@@ -967,7 +974,7 @@ extern "C" int mae_mpd_bwd(const float* mu, int64_t mu_stride, const float* logv
         auto launch = [&](auto ps_tag) {
             constexpr int PS = decltype(ps_tag)::value;
             const int64_t blocks = ceil_div(items, (kNT / 32) / PS);
-            mpd_bwd_small_kernel<PS><<<(unsigned)blocks, kNT, 0, as_stream(stream)>>>(
+            launch_pdl(mpd_bwd_small_kernel<PS>, dim3((unsigned)blocks), dim3(kNT), 0, as_stream(stream),
                 mu, mu_stride, logvar, logvar_stride, at<float4>(workspace, L.vp), at<float>(workspace, L.kl),
                 at<float>(workspace, L.klt), (int)L.Bp, at<double>(workspace, L.colstats), at<double>(workspace, L.pivots),
                 at<Hdr>(workspace, L.hdr), g_m, g_S, S, gkl, (int)B, (int)D, (int)row0, (int)nrows, dmu, dlogvar, accumulate);
@@ -1032,8 +1039,8 @@ extern "C" int mae_mpd_loss_bwd(const float* mu, int64_t mu_stride, const float*
     float* g_m = at<float>(workspace, L.lossg);
     float* g_S = g_m + D;
     float* gkl = (kl_all != nullptr && kl_weight > 0.f) ? g_m + D + 8 : nullptr;
-    mpd_loss_grads_kernel<<<1, kNT, 0, as_stream(stream)>>>(m_d, S, kl_all, (int)B, (int)D, eta, gamma, free_bits, kl_weight, g_m,
-                                                           g_S, gkl, reg);
+    launch_pdl(mpd_loss_grads_kernel, dim3(1), dim3(kNT), 0, as_stream(stream), m_d, S, kl_all, (int)B, (int)D, eta, gamma, free_bits,
+               kl_weight, g_m, g_S, gkl, reg);
     rc = launch_status();
     if (rc != MAE_OK || dmu == nullptr) return rc;   // dmu NULL: only reg is wanted (evaluation)
     return mae_mpd_bwd(mu, mu_stride, logvar, logvar_stride, workspace, workspace_bytes, B, D, row0, nrows,

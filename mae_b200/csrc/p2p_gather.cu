@@ -51,6 +51,7 @@ __global__ void __launch_bounds__(kThreads)
 p2p_allgather_kernel(const float* __restrict__ local, int64_t n_floats, char* const* __restrict__ peers, int rank, int world,
                      int64_t slot_floats, float* __restrict__ out) {
     __shared__ bool timed_out;
+    pdl_launch_dependents();   // the MPD pre-pass behind it may be placed while the flags are awaited
     const int p = blockIdx.x;
     char* own = peers[rank];
     CommHeader* hdr = reinterpret_cast<CommHeader*>(own);
