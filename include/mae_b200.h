@@ -45,6 +45,11 @@ enum {
 };
 
 int mae_abi_version(void);
+/* Programmatic dependent launch between the kernels of a dependent chain (each kernel still waits for its predecessor's
+ * completion before reading its output, so results are unaffected).  On by default; mae_set_pdl(0) switches it off for the
+ * process (the batch-sharded head does: at 8 GPUs early-placed successors cost 8 us per step while ranks wait for each
+ * other's rows); MAE_NO_PDL=1 in the environment has the same effect.  Returns the previous setting. */
+int mae_set_pdl(int enabled);
 const char* mae_strerror(int code);
 /* SM count / compute capability of the current device; used by the host layer to refuse non-sm_100 parts. */
 int mae_device_info(int* sm_count, int* cc_major, int* cc_minor);

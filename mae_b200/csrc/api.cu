@@ -1,4 +1,6 @@
 // Library-level entry points: ABI version, error strings, device query.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace mae {
@@ -13,7 +15,24 @@ int sm_count() {
     }
     return cached[dev];
 }
+
+namespace {
+int g_pdl = -1;   // -1: not decided yet (MAE_NO_PDL is consulted on first use), 0 off, 1 on
+}
+bool pdl_enabled() {
+    if (g_pdl < 0) {
+        const char* e = getenv("MAE_NO_PDL");
+        g_pdl = (e != nullptr && e[0] == '1') ? 0 : 1;
+    }
+    return g_pdl != 0;
+}
 }  // namespace mae
+
+extern "C" int mae_set_pdl(int enabled) {
+    const int before = mae::pdl_enabled() ? 1 : 0;
+    mae::g_pdl = enabled ? 1 : 0;
+    return before;
+}
 
 extern "C" int mae_abi_version(void) { return MAE_ABI_VERSION; }
 

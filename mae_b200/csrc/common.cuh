@@ -2,6 +2,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <cstdlib>
 #include <stdint.h>
 
 #include "../../include/mae_b200.h"
@@ -32,6 +33,11 @@ static inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b
 // when the predecessor grid has completed and its memory is visible; it is a no-op for ordinary launches).  A predecessor
 // opts in by calling pdl_launch_dependents() - typically first thing - which lets the successor's CTAs be placed as soon
 // as resources free up.  Cuts the dependent-launch gaps of the latency-bound training step (4 dependent edges).
+// Process-wide PDL switch: on by default (single-GPU steps gain ~0.7 us), switched off by the batch-sharded head (measured
+// at 8 GPUs on one box: 60.5 us/step without vs 68.3 us with early-placed successors while ranks wait for each other's
+// rows) or by MAE_NO_PDL=1.  Defined in api.cu.
+bool pdl_enabled();
+
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
@@ -39,6 +45,7 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 template <typename... KArgs, typename... Args>
 static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
                                      Args... args) {
+    const bool enabled = pdl_enabled();   // process-wide switch (mae_set_pdl / MAE_NO_PDL), see api.cu
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = block;
@@ -46,7 +53,7 @@ static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 b
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    attr[0].val.programmaticStreamSerializationAllowed = enabled ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);

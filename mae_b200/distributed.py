@@ -228,6 +228,9 @@ class ShardedHead:
         self.use_p2p = use_p2p
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
+        if self.world > 1 and hasattr(self.engine, "set_pdl"):
+            # measured at 8 GPUs (same box, A/B): 60.5 us/step without programmatic dependent launch vs 68.3 us with it
+            self.engine.set_pdl(False)
 
     def _gather(self, packed: torch.Tensor) -> torch.Tensor:
         """All-gather of the packed rows: one push-kernel over NVLink peer memory when available (tens of KB, pure

@@ -17,7 +17,7 @@ from . import _lib
 __all__ = [
     "reparam_kl", "mpd", "mpd_forward_only", "bernoulli_recon_error", "dmol_recon_error", "log_prob_prior",
     "log_prob_posterior", "iw_nll", "assemble_loss", "kl_mpd", "loss_tail", "loss_head", "encode_head", "kl_mpd_reg_fused", "kl_mpd_reg", "mpd_rows_loss_backward", "reg_rows_fused", "reparam_fwd",
-    "reparam_reg_bwd", "fused_reg_supported", "join_side", "launch_count", "reset_launch_count",
+    "reparam_reg_bwd", "fused_reg_supported", "set_pdl", "join_side", "launch_count", "reset_launch_count",
 ]
 
 _launches = 0  # number of kernels of ours enqueued since the last reset (bench.py reports it)
@@ -39,6 +39,12 @@ def _count(n: int = 1) -> None:
 
 def _lib_():
     return _lib.load()
+
+
+def set_pdl(enabled: bool) -> bool:
+    """Process-wide switch of programmatic dependent launch between the kernels of a chain (mae_set_pdl); returns the
+    previous setting.  On by default; the batch-sharded head turns it off."""
+    return bool(_lib_().mae_set_pdl(1 if enabled else 0))
 
 
 def _stream() -> int:
