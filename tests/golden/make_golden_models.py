@@ -96,6 +96,19 @@ def run_model(params, x, x_init, ns, k, eta, gamma, free_bits):
                 res["flow_bwd"], res["flow_bwd_logdet"] = zn, ld
                 zf, ldf = m.encoder.prior_flow.forward(zn[:2])
                 res["flow_fwd"], res["flow_fwd_logdet"] = zf, ldf
+        with torch.no_grad():
+            # decoder network output for z = mu (what the likelihood kernel reads): raw mixture parameters [B,10*nmix,H,W]
+            # (colour) or Bernoulli probabilities (binary); a strided slice keeps the fixture small
+            dec = m.decoder
+            zdec = mu.view(b, *dec.z_shape())
+            if hasattr(dec, "nmix"):
+                net = dec(xx, zdec)
+            elif hasattr(dec, "z_transform"):      # PixelCNN binary decoder: conditioning maps + image through the core
+                net = dec.core(torch.cat([xx, dec.z_transform(zdec)], dim=1))
+            else:
+                net = dec(zdec)
+            res["dec_out_shape"] = tuple(net.shape)
+            res["dec_out_slice"] = net[:2, ::7, ::3, ::3].clone()
         m.train()
         with _InjectNoise(eps_loss):
             loss7 = m.loss(xx, ns, eta=eta, gamma=gamma, free_bits=free_bits)
@@ -140,6 +153,23 @@ def main():
         "color_resnet": run_model(COLOR_RESNET, xc, xc_init, ns=2, k=3, eta=0.5, gamma=1.0, free_bits=0.0),
         "color_image32x32_json": run_model(color, xc[:3], xc_init[:4], ns=1, k=2, eta=1.0, gamma=1.0, free_bits=0.0),
     }
+    # the shipped 64x64 configuration: networks only (one replica, dropout 0), forward of core / flow / decoder in fp32+fp64
+    c64 = json.load(open("/root/reference/experiments/configs/color_image64x64.json"))
+    c64["encoder"]["ngpu"] = c64["decoder"]["ngpu"] = 1
+    c64["decoder"]["dropout"] = 0.0
+    x64 = torch.randint(0, 256, (2, 3, 64, 64)).float() / 127.5 - 1.0
+    f64 = {"params": copy.deepcopy(c64), "x": x64}
+    for tag in ("ref32", "ref64"):
+        m = synth.fill_state(RefMAE.from_params(copy.deepcopy(c64)))
+        m = (m.double() if tag == "ref64" else m).eval()
+        xx = x64.double() if tag == "ref64" else x64
+        with torch.no_grad():
+            mu, logvar = m.encoder.core(xx)
+            zn, ld = m.encoder.prior_flow.backward(mu)
+            net = m.decoder(xx, mu)
+        f64[tag] = {"mu": mu, "logvar": logvar, "flow_bwd": zn, "flow_bwd_logdet": ld, "dec_out_shape": tuple(net.shape),
+                    "dec_out_slice": net[:2, ::7, ::3, ::3].clone()}
+    fixtures["color_image64x64_networks"] = f64
     # state_dict keys / shapes of the three shipped configurations exactly as written (ngpu = 2 for the colour ones ->
     # DataParallel "module." level; pass-through on a CPU-only host)
     literal = {}

@@ -74,6 +74,45 @@ def test_encoder_core_and_flow_forward(fixtures, name):
             assert flow is None
 
 
+def _decoder_net(dec, x, z):
+    """the decoder network's output for a given z: raw mixture parameters (colour) or Bernoulli probabilities (binary)"""
+    zdec = z.view(z.size(0), *dec.z_shape())
+    if hasattr(dec, "nmix"):
+        return dec(x, zdec)
+    if hasattr(dec, "z_transform"):
+        return dec.core(torch.cat([x, dec.z_transform(zdec)], dim=1))
+    return dec(zdec)
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_decoder_network_output(fixtures, name):
+    """ResNet / PixelCNN / PixelCNN++ decoders: the tensor the likelihood kernel reads, against the live reference"""
+    c = fixtures[name]
+    r64, r32 = c["ref64"], c["ref32"]
+    model = _ours(c).eval()
+    with torch.no_grad():
+        net = _decoder_net(model.decoder, c["x"], r32["mu"])
+    assert tuple(net.shape) == tuple(r32["dec_out_shape"])
+    check_close(net[:2, ::7, ::3, ::3], r64["dec_out_slice"], r32["dec_out_slice"], rel=2e-5, what="%s decoder output" % name)
+
+
+def test_color64_networks_forward(fixtures):
+    """color_image64x64.json (DenseNet 64x64 core, AF2d-MADE, PixelCNN++ with 4 levels): cores, flow and decoder forward"""
+    c = fixtures["color_image64x64_networks"]
+    r64, r32 = c["ref64"], c["ref32"]
+    model = _ours(c).eval()
+    with torch.no_grad():
+        mu, logvar = model.encoder.core(c["x"])
+        check_close(mu, r64["mu"], r32["mu"], what="mu 64x64")
+        check_close(logvar, r64["logvar"], r32["logvar"], what="logvar 64x64")
+        zn, ld = model.encoder.prior_flow.backward(r32["mu"])
+        check_close(zn, r64["flow_bwd"], r32["flow_bwd"], what="flow backward 64x64")
+        check_close(ld, r64["flow_bwd_logdet"], r32["flow_bwd_logdet"], what="flow logdet 64x64")
+        net = model.decoder(c["x"], r32["mu"])
+    assert tuple(net.shape) == tuple(r32["dec_out_shape"])
+    check_close(net[:2, ::7, ::3, ::3], r64["dec_out_slice"], r32["dec_out_slice"], rel=2e-5, what="decoder output 64x64")
+
+
 @pytest.mark.parametrize("name", ALL)
 def test_data_dependent_initialize(fixtures, name):
     """MAE.initialize (weight_norm.py:25-37, masked.py:84-98 through every stack) from identical filled weights ends in
