@@ -11,9 +11,11 @@
  *   - every pointer is a DEVICE pointer to fp32 data unless stated otherwise; sizes are int64_t;
  *     "stride" arguments are ROW strides in elements (the reference's mu is a chunk(2,1) view with
  *     row stride 2*D, encoder_cores/resnet.py:43); the innermost dimension is always contiguous.
- *   - no allocation, no synchronisation and no global state inside: the caller owns every buffer,
- *     including workspaces and outputs; all work is enqueued on `stream` (a cudaStream_t), so every
- *     call can be captured into a CUDA graph.
+ *   - no allocation and no synchronisation inside: the caller owns every buffer, including
+ *     workspaces and outputs; all work is enqueued on `stream` (a cudaStream_t), so every call can be
+ *     captured into a CUDA graph.  The only process-wide state is the launch-attribute switch
+ *     mae_set_pdl() and the peer-memory communication buffers (mae_comm_*), which the library allocates
+ *     because they must be cudaMalloc'ed to be shareable through CUDA IPC.
  *   - workspaces must be zero-filled once when allocated (they carry self-resetting tickets) and
  *     must not be shared by calls that may run concurrently.
  *   - return value: 0 on success, a negative MAE_ERR_* code for an argument error, or a positive
