@@ -9,10 +9,11 @@ from .zoo import (AF2dMADE, AFMADE, DenseNetEncoderCoreColorImage32x32, DenseNet
                   ResnetDecoderBinaryImage28x28, ResnetDecoderColorImage32x32, ResnetEncoderCoreBinaryImage28x28,
                   ResnetEncoderCoreColorImage32x32)
 from .mae import MAE
-from .utils import exponentialMovingAverage, logsumexp
+from .utils import exponentialMovingAverage, logavgexp, logsumexp, norm, sample_from_discretized_mix_logistic
 
 __all__ = ["MAE", "Encoder", "EncoderCore", "GaussianEncoder", "Flow", "Decoder", "BinaryImageDecoder",
-           "ColorImageDecoder", "exponentialMovingAverage", "logsumexp", "networks", "AFMADE",
+           "ColorImageDecoder", "exponentialMovingAverage", "logsumexp", "logavgexp", "norm",
+           "sample_from_discretized_mix_logistic", "networks", "AFMADE",
            "PixelCNNDecoderBinaryImage28x28", "ResnetDecoderBinaryImage28x28", "ResnetDecoderColorImage32x32",
            "ResnetEncoderCoreBinaryImage28x28", "ResnetEncoderCoreColorImage32x32", "AF2dMADE",
            "DenseNetEncoderCoreColorImage32x32", "DenseNetEncoderCoreColorImage64x64", "PixelCNNPPDecoderColorImage32x32",

@@ -24,3 +24,29 @@ def exponentialMovingAverage(original, shadow, decay_rate, init=False):
                 sp.copy_(p)
             else:
                 sp.add_((1.0 - decay_rate) * (p - sp))
+
+
+def norm(p: torch.Tensor, dim):
+    """L2 norm over all dimensions except ``dim`` (kept for broadcasting); ``dim=None``: the full norm.
+    Reference: mae/modules/utils.py:9-20."""
+    if dim is None:
+        return p.norm()
+    if dim < 0:
+        dim += p.dim()
+    dims = [i for i in range(p.dim()) if i != dim]
+    return torch.linalg.vector_norm(p, dim=dims, keepdim=True) if dims else p.abs()
+
+
+def logavgexp(x, dim=None):
+    """log(mean(exp(x))) over ``dim`` (all axes when None).  Reference: mae/modules/utils.py:41-58."""
+    import math
+    n = x.numel() if dim is None else x.size(dim)
+    return logsumexp(x, dim) - math.log(n)
+
+
+def sample_from_discretized_mix_logistic(means, logscales, coeffs, logit_probs, random_sample):
+    """Most probable mixture component per pixel, optional logistic noise, colour coupling, clamp to [-1, 1]:
+    [B,nmix,3,H,W] x3, [B,nmix,H,W] -> [B,3,H,W].  Reference: mae/modules/utils.py:124-160 (sampling is not on the hot path;
+    the likelihood itself is ``ColorImageDecoder.reconstruct_error`` on the CUDA kernels)."""
+    from .decoder import ColorImageDecoder
+    return ColorImageDecoder.sample_pixels(means, logscales, logit_probs, coeffs, random_sample)

@@ -205,3 +205,40 @@ def test_cached_weights_give_identical_flow_samples():
         with torch.no_grad():
             b = w.masked_weight()
             assert w.masked_weight() is b
+
+
+def test_utils_helpers_match_reference_semantics():
+    """norm / logsumexp / logavgexp / deterministic mixture sampling (mae/modules/utils.py) on small inputs"""
+    import math
+    from mae_b200.modules import logavgexp, logsumexp, norm, sample_from_discretized_mix_logistic
+    torch.manual_seed(0)
+    p = torch.randn(5, 3, 2, 2)
+    assert torch.allclose(norm(p, 0), p.reshape(5, -1).norm(dim=1).view(5, 1, 1, 1))
+    assert torch.allclose(norm(p, 3), p.reshape(-1, 2).norm(dim=0).view(1, 1, 1, 2))
+    assert torch.allclose(norm(p, None), p.norm())
+    x = torch.randn(4, 7)
+    assert torch.allclose(logsumexp(x, 1), torch.log(torch.exp(x).sum(1)))
+    assert torch.allclose(logavgexp(x, 1), torch.log(torch.exp(x).mean(1)))
+    assert torch.allclose(logavgexp(x), torch.log(torch.exp(x).mean()))
+    means, ls, co = torch.randn(2, 3, 3, 4, 4), torch.randn(2, 3, 3, 4, 4), torch.tanh(torch.randn(2, 3, 3, 4, 4))
+    logits = torch.log_softmax(torch.randn(2, 3, 4, 4), dim=1)
+    out = sample_from_discretized_mix_logistic(means, ls, co, logits, False)
+    k = logits.argmax(dim=1)
+    sel = lambda t: t.gather(1, k[:, None, None].expand(-1, 1, 3, -1, -1)).squeeze(1)
+    m, c = sel(means), sel(co)
+    x0 = m[:, 0].clamp(-1, 1)
+    x1 = (m[:, 1] + c[:, 0] * x0).clamp(-1, 1)
+    x2 = (m[:, 2] + c[:, 1] * x0 + c[:, 2] * x1).clamp(-1, 1)
+    assert torch.equal(out, torch.stack([x0, x1, x2], 1)) and out.shape == (2, 3, 4, 4)
+
+
+def test_mae_load_round_trip(tmp_path, fixtures):
+    """MAE.load(model_path, device): config.json + model.pt as the reference's training scripts write them"""
+    import json
+    c = fixtures["binary_image_json"]
+    model = _ours(c)
+    json.dump(c["params"], open(tmp_path / "config.json", "w"))
+    torch.save(model.state_dict(), tmp_path / "model.pt")
+    loaded = MAE.load(str(tmp_path), torch.device("cpu"))
+    for (n1, t1), (n2, t2) in zip(model.state_dict().items(), loaded.state_dict().items()):
+        assert n1 == n2 and torch.equal(t1, t2)
