@@ -44,6 +44,29 @@ def test_dmol_pixel_math(hc, golden):
         check_close(err2, c["ref64"]["err"], c["ref32"]["err"], what=name + " err (packed pair path)")
 
 
+def test_dmol_forward_extremes_vs_oracle(hc):
+    """the forward path (one reciprocal and one logarithm per component, product over the three channels) on adversarial
+    inputs: log-scales far below the -7 clamp and up to +6, means far outside [-1, 1], every pixel value incl. both edge
+    bins, saturated coefficients -> must stay finite and match the fp64 oracle like the goldens do"""
+    from oracle import mae_oracle as O
+    g = torch.Generator().manual_seed(11)
+    b, ns, nmix, h, w = 3, 2, 10, 8, 8
+    raw = torch.randn(b * ns, 10 * nmix, h, w, generator=g)
+    raw[:, nmix:4 * nmix] *= 3.0                                            # means up to +-9
+    raw[:, 4 * nmix:7 * nmix] = torch.empty(b * ns, 3 * nmix, h, w).uniform_(-12.0, 6.0, generator=g)   # raw log-scales
+    raw[:, 7 * nmix:] *= 6.0                                                # tanh saturates
+    x = (torch.randint(0, 256, (b, 3, h, w), generator=g).float() / 127.5 - 1.0)
+    x[0, :, 0, :4] = 1.0                                                    # 255
+    x[0, :, 0, 4:] = -1.0                                                   # 0
+    err = torch.empty(b, ns)
+    i64 = ctypes.c_int64
+    hc.hc_dmol_fwd(_p(raw), _p(x), i64(b), i64(ns), i64(nmix), i64(h * w), _p(err))
+    assert torch.isfinite(err).all()
+    ref64 = O.dmol_recon_error(raw.double(), x.double(), ns, nmix)
+    ref32 = O.dmol_recon_error(raw, x, ns, nmix)
+    check_close(err, ref64, ref32, what="err on extreme inputs")
+
+
 def test_bernoulli_math(hc, golden):
     for name, c in golden("bernoulli").items():
         probs, x, g = c["probs"].contiguous(), c["x"].contiguous(), c["g"].contiguous()
