@@ -88,3 +88,75 @@ def test_mpd_kernel_algebra_matches_oracle_autograd():
                                (gmu2, mu.grad, "dmu direct"), (glv2, lv.grad, "dlv direct")]:
             err = (got - ref.detach()).abs().max() / ref.detach().abs().max().clamp_min(1e-300)
             assert err < 1e-9, (B, D, name, float(err))
+
+
+def cluster_kernel_algebra(mu, lv, eta, gamma, free_bits, npivot=32):
+    """fp64 restatement of mpd_fused.cu: direct pair form without the K = 2D panels (both orientations share the squared
+    difference), factored gradient terms, upstream gradients derived from the closed-form consumers (mae.py:132-139), the
+    analytic-KL part with the free-bits gate, (a, b) -> (r, a+b) reconstruction used when V is rebuilt from (a, b)."""
+    B, D = mu.shape
+    eps = 1e-12
+    P = min(B, npivot)
+    mu_bar, l_bar = mu[:P].mean(0, keepdim=True), lv[:P].mean(0, keepdim=True)
+    v_bar = l_bar.exp()
+    ivb = 1.0 / v_bar
+    mc, alpha = mu - mu_bar, lv - l_bar
+    a = torch.expm1(alpha)
+    v = v_bar * (1 + a)
+    r = 1.0 / (v + eps)
+    b = -(a * v_bar + eps) * r
+    assert torch.allclose((1 + b) * ivb, r, rtol=1e-12)                        # r rebuilt from b
+    apb = (v_bar * a * a + eps * (a - 1)) * r
+    t = a + (2 * b + b * b) * (1 + a)
+    ema = a - alpha
+    bpa = (v_bar * (alpha * a - ema) + eps * (alpha - 1)) * r
+    E, F = ema.sum(1), bpa.sum(1)                                              # no mc^2 terms: the pair loop carries them
+    dl = mc[:, None, :] - mc[None, :, :]
+    q2 = dl * dl
+    KL = 0.5 * ((a[:, None] * b[None] + q2 * r[None]).sum(2) + E[:, None] + F[None, :])         # KL_ij
+    KLT = 0.5 * ((a[None] * b[:, None] + q2 * r[:, None]).sum(2) + E[None, :] + F[:, None])      # KL_ji seen from row i
+    assert torch.allclose(KLT, KL.t(), rtol=1e-10, atol=1e-12)
+    SA, SB, SAB, SApB = a.sum(0), b.sum(0), (a * b).sum(0), apb.sum(0)
+    S1, S2, R1, R2 = mc.sum(0), (mc * mc).sum(0), (r * mc).sum(0), (r * mc * mc).sum(0)
+    R0 = (B + SB) * ivb.squeeze(0)
+    m_d = 0.5 * (SA * SB - SAB + (B - 1) * SApB + (S2 * R0 - 2 * S1 * R1 + B * R2)) / (B * (B - 1))
+    m = m_d.sum()
+    off = ~torch.eye(B, dtype=torch.bool)
+    S = torch.sqrt(((KL - m)[off] ** 2).sum() / (B * (B - 1) - 1))
+    kl = 0.5 * (mu * mu + torch.expm1(lv) - lv).sum(1)
+    mean_kl = kl.sum() / B
+    reg = torch.clamp(mean_kl, min=free_bits) - eta * torch.nn.functional.logsigmoid(m_d).sum() + gamma * S
+    # upstream gradients of the closed-form consumers
+    g_m = -eta * torch.sigmoid(-m_d)
+    gk = (1.0 / B) if float(mean_kl) >= free_bits else 0.0
+    beta = gamma / ((B * B - B - 1) * S)
+    w1 = (beta * (KL - m) * off)[:, :, None]
+    w2 = (beta * (KLT - m) * off)[:, :, None]
+    ai, aj, bj, ri, rj, ti = a[:, None], a[None], b[None], r[:, None], r[None], t[:, None]
+    oi = (1 + ti) * ivb
+    gmu = (dl * (w1 * rj + w2 * ri)).sum(1)                                                       # r carries 1/v_bar
+    glv = 0.5 * (w1 * ((ai + 1) * bj + ai) - w2 * ((ti + 1) * aj + (q2 * oi + ti))).sum(1)        # factored forms
+    aa = g_m / (B * (B - 1))
+    dT_dmu = 2 * ((mc * R0 - R1) + r * (B * mc - S1))
+    dT_dlv = ((B - 1) * (a - t) + (1 + a) * (SB - b) - (1 + t) * (SA - a) - (1 + t) * ivb * (S2 - 2 * S1 * mc + B * mc * mc))
+    gmu = gmu + 0.5 * aa * dT_dmu + gk * mu
+    glv = glv + 0.5 * aa * dT_dlv + 0.5 * gk * torch.expm1(lv)
+    return kl, m_d, S, reg, gmu, glv
+
+
+def test_cluster_kernel_algebra_matches_oracle_autograd():
+    torch.manual_seed(1)
+    for B, D, off, eta, gamma, fb in [(2, 3, 0.0, 1.0, 1.0, 0.0), (9, 4, 20.0, 0.5, 2.0, 0.0), (33, 17, -3.0, 1.0, 0.0, 0.0),
+                                      (40, 6, 0.5, 0.0, 1.0, 1e6), (100, 8, 0.0, 1.0, 1.0, 0.0)]:
+        mu = (torch.randn(B, D, dtype=torch.float64) + off).requires_grad_()
+        lv = torch.randn(B, D, dtype=torch.float64).clamp(-7, 7).requires_grad_()
+        m_ref, s_ref = O.post_kl(mu, lv)
+        kl_ref = O.analytic_kl(mu, lv)
+        reg_ref = kl_ref.mean().clamp(min=fb) - eta * torch.nn.functional.logsigmoid(m_ref).sum() + gamma * s_ref
+        reg_ref.backward()
+        with torch.no_grad():
+            kl, m_d, S, reg, gmu, glv = cluster_kernel_algebra(mu.detach(), lv.detach(), eta, gamma, fb)
+        for got, ref, name in [(kl, kl_ref, "KL"), (m_d, m_ref, "m_d"), (S, s_ref, "S"), (reg, reg_ref, "reg"),
+                               (gmu, mu.grad, "dmu"), (glv, lv.grad, "dlv")]:
+            err = (got - ref.detach()).abs().max() / ref.detach().abs().max().clamp_min(1e-300)
+            assert err < 1e-9, (B, D, name, float(err))
