@@ -1,17 +1,19 @@
 #!/usr/bin/env python
 """Benchmark of the MAE loss-and-evaluation hot path on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c1|c4|c5]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-Default workload (N=1):  C3 = BASELINE.json configs[2], "CIFAR-10 32x32x3, discretized logistic mixture (10 comps)
-decoder, latent 64, batch 64, full MAE loss fwd+bwd" — the loss-head configuration with a real HBM roofline
-(configs[1], OMNIGLOT, is 1.6 MB / 10 MFLOP per step and purely launch-latency-bound; it is reported under
-"workloads" together with C4 = IW-NLL eval and C5 = MPD microbench).  One step = reparam+KL, MPD, DMOL likelihood,
-objective assembly, forward AND backward, on synthetic encoder/decoder outputs (the conv stacks stay in PyTorch
-and are not part of the measured path).  Prints ONE JSON line on rank 0.
+Default workload:  C3 = BASELINE.json configs[2], "CIFAR-10 32x32x3, discretized logistic mixture (10 comps) decoder,
+latent 64, batch 64, full MAE loss fwd+bwd" - the loss-head configuration with a real HBM roofline (configs[1],
+OMNIGLOT, is 1.6 MB / 10 MFLOP per step and purely launch-latency-bound; it is reported under "workloads" together with
+C4 = IW-NLL eval and C5 = MPD microbench at every N).  One step = reparam+KL, MPD, DMOL likelihood, objective assembly,
+forward AND backward, on synthetic encoder/decoder outputs (the conv stacks stay in PyTorch and are not part of the
+measured path).  Prints ONE JSON line on rank 0.
 
-Timing rules followed: >= 3 warm-up steps; a ring of input slabs larger than L2 is cycled so every step reads
-from HBM; CUDA events on the launching stream; max over ranks; nvidia-smi clocks sampled during the timed region.
+Timing rules followed: at least --warmup (and >= 3) warm-up steps, extended to ~0.4 s so that clocks have ramped; a ring
+of input slabs larger than 3x L2 is cycled so every step reads from HBM; CUDA events on the launching stream; max over
+ranks; the timed block of K steps is repeated (5x when K < 200) and the MEDIAN block is reported; nvidia-smi clocks are
+sampled during the timed region.
 """
 from __future__ import annotations
 
@@ -32,6 +34,11 @@ import torch  # noqa: E402
 
 ETA, GAMMA, FREE_BITS = 1.0, 1.0, 0.0
 L2_BYTES = 126e6
+BATCH, LATENT = 64, 64
+# identical in both arms (the driver compares the strings)
+WORKLOAD = ("C3: CIFAR-10 32x32x3 head, DMOL nmix=10, latent 64, batch 64 per GPU, MPD on (eta=gamma=1), "
+            "full MAE loss fwd+bwd on synthetic encoder/decoder outputs")
+METRIC = "mae_loss_head_fwd_bwd_samples_per_s"
 
 
 def measured_peaks():
@@ -39,17 +46,17 @@ def measured_peaks():
     if os.path.exists(path):
         with open(path) as f:
             d = json.load(f)
-        return float(d["hbm_gbs"]), "measured"
-    return 6650.0, "fallback"
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
 
 
 def ncu_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu --set full capture
-    (profiles/r1_ncu_traffic.json); None if the file is absent."""
-    path = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the benched kernel (dmol_bwd_kernel<10,1024,5,true>, 160
+    threads) from the committed ncu --set full capture; None if no capture of THAT kernel is committed."""
+    path = os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")
     try:
         with open(path) as f:
-            k = json.load(f)["dmol_bwd_kernel<10,1024,5>"]
+            k = json.load(f)["dmol_fwd_bwd"]
         return k["dram_bytes_read"] + k["dram_bytes_write"]
     except Exception:
         return None
@@ -108,7 +115,7 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------- synthetic inputs
-def c3_host_inputs(slab: int, batch=64, latent=64):
+def c3_host_inputs(slab: int, batch=BATCH, latent=LATENT):
     """One slab of C3 inputs on the host (pinned): encoder outputs, noise, decoder output, images."""
     from mae_b200 import synth
     seed = synth.SEED + 1000 * slab
@@ -121,7 +128,7 @@ def c3_host_inputs(slab: int, batch=64, latent=64):
             for k, v in dict(enc=enc, eps=eps, gz=gz, raw=head["raw"], x=head["x"]).items()}
 
 
-def c3_bytes(batch=64, ns=1, nmix=10, hw=1024):
+def c3_bytes(batch=BATCH, ns=1, nmix=10, hw=1024):
     fwd = 4 * (10 * nmix * hw * batch * ns + 3 * hw * batch + batch * ns)
     bwd = 4 * (2 * 10 * nmix * hw * batch * ns + 3 * hw * batch + batch * ns)
     return fwd, bwd
@@ -147,10 +154,10 @@ class C3Step:
         self.x = host["x"].to(dev)
         self.graph = None
         self.loss = None
+        self.stats = None
         self.launches = 0
 
     def eager(self):
-        from mae_b200 import ops
         self.mu.grad = None
         self.lv.grad = None
         self.raw.grad = None
@@ -162,6 +169,7 @@ class C3Step:
             loss, recon, kl, stats, z = self.dist.loss_head_color(mu, lv, self.eps, self.raw, self.x, 10, ETA, GAMMA, FREE_BITS)
         # the decoder is not part of the measured path: its backward is represented by the gradient it would hand to z
         torch.autograd.backward([loss, z], [self.one, self.gz])
+        self.stats = stats
         return loss
 
     def capture(self):
@@ -187,23 +195,73 @@ class C3Step:
         return self.loss
 
 
-def time_kernel(fn, n_iter, stream):
-    """average device time of fn() over n_iter back-to-back launches, CUDA events on the launching stream"""
+def time_kernel(fn, n_iter, stream, reps=1):
+    """median over ``reps`` of the average device time of fn() over n_iter back-to-back launches (CUDA events on the
+    launching stream)"""
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for i in range(3):
         fn(i)
     torch.cuda.synchronize()
-    e0.record(stream)
-    for i in range(n_iter):
-        fn(i)
-    e1.record(stream)
-    torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / n_iter * 1e-3
+    ts = []
+    for _ in range(reps):
+        e0.record(stream)
+        for i in range(n_iter):
+            fn(i)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) / n_iter * 1e-3)
+    return statistics.median(ts)
 
 
 def _dbg(msg):
     if os.environ.get("MAE_BENCH_DEBUG"):
         print("[bench rank %s %.2f] %s" % (os.environ.get("RANK", "0"), time.perf_counter(), msg), file=sys.stderr, flush=True)
+
+
+def parity_across_ranks(dist_ctx, hosts, dev, rank, world):
+    """N > 1: the sharded step of slab 0 must reproduce the single-GPU head on the concatenated global batch: global loss
+    to 2e-6 relative, this rank's own-row gradients to 1e-5 of the tensor scale.  Every rank evaluates the reference."""
+    import torch.distributed as dist
+    from mae_b200 import heads, ops
+    h = hosts[0]
+    loc = {k: v.to(dev) for k, v in h.items()}
+    glob = {}
+    for k, v in loc.items():
+        out = torch.empty((world * v.size(0),) + tuple(v.shape[1:]), device=dev, dtype=v.dtype)
+        dist.all_gather_into_tensor(out, v.contiguous())
+        glob[k] = out
+    half = loc["enc"].size(1) // 2
+
+    def leaves(t):
+        return t[:, :half].detach().requires_grad_(), t[:, half:].detach().requires_grad_()
+
+    mu, lv = leaves(loc["enc"])
+    raw = loc["raw"].detach().requires_grad_()
+    loss, recon, kl, stats, z = dist_ctx.loss_head_color(mu, lv, loc["eps"], raw, loc["x"], 10, ETA, GAMMA, FREE_BITS)
+    torch.autograd.backward([loss, z], [torch.ones((), device=dev), loc["gz"]])
+    g_loss = dist_ctx.global_loss(loss, stats)
+    mu_a, lv_a = leaves(glob["enc"])
+    raw_a = glob["raw"].detach().requires_grad_()
+    ref = heads.loss_head_color(mu_a, lv_a, glob["eps"], raw_a, glob["x"], 10, ETA, GAMMA, FREE_BITS)
+    torch.autograd.backward([ref[0], ref[4]], [torch.ones((), device=dev), glob["gz"]])
+    ops.join_side(dev)
+    torch.cuda.synchronize()
+    b = loc["enc"].size(0)
+    sl = slice(rank * b, (rank + 1) * b)
+
+    def rel(a, r):
+        return float((a.double() - r.double()).abs().max()) / max(float(r.double().abs().max()), 1e-30)
+
+    errs = {"loss": rel(g_loss, ref[0].detach()), "dmu": rel(mu.grad, mu_a.grad[sl]), "dlogvar": rel(lv.grad, lv_a.grad[sl]),
+            "draw": rel(raw.grad, raw_a.grad[sl])}
+    ok = errs["loss"] <= 2e-6 and errs["dmu"] <= 1e-5 and errs["dlogvar"] <= 1e-5 and errs["draw"] <= 1e-5
+    t = torch.tensor([1.0 if ok else 0.0] + [errs[k] for k in ("loss", "dmu", "dlogvar", "draw")], device=dev, dtype=torch.float64)
+    lo = t.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dist_ctx.check()
+    return bool(lo[0] > 0.5), {"loss": float(t[1]), "dmu": float(t[2]), "dlogvar": float(t[3]), "draw": float(t[4]),
+                               "global_loss": float(g_loss), "single_gpu_loss": float(ref[0].detach())}
 
 
 def bench_ours(args):
@@ -219,13 +277,20 @@ def bench_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
         from mae_b200.distributed import ShardedHead
-        dist_ctx = ShardedHead()
+        dist_ctx = ShardedHead(defer_join=True, check_every=0)
     hbm_gbs, peak_src = measured_peaks()
-    batch, latent = 64, 64
+    batch, latent = BATCH, LATENT
     fwd_b, bwd_b = c3_bytes(batch)
     step_bytes = fwd_b + bwd_b
-    ring = max(4, int(L2_BYTES * 3 / step_bytes) + 1)                     # > 3x L2 of distinct data in flight
+    ring = max(4, int(L2_BYTES * 3 / bwd_b) + 1)                     # > 3x L2 of distinct data actually moved per step
     hosts = [c3_host_inputs(i + 17 * rank, batch, latent) for i in range(min(ring, 4))]
+    parity_n = None
+    if world > 1:
+        parity_n = parity_across_ranks(dist_ctx, hosts, dev, rank, world)
+        _dbg("parity across ranks: %s" % (parity_n,))
+    # d loss == 1 is created by this script (torch.autograd.backward([loss, z], [one, gz])): the conditional rescale launch
+    # of the fused DMOL node is skipped (ops.set_unit_loss_grad)
+    ops.set_unit_loss_grad(True)
     steps_obj = []
     use_graph = not args.no_graph
     _dbg("init done, ring=%d" % ring)
@@ -250,11 +315,10 @@ def bench_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    # warm-up: at least W (>= 3) steps and at least ~0.4 s of replay so that clocks have ramped and nvidia-smi
-    # (100 ms period) sees the load
+    # warm-up: at least W (>= 3) steps, extended to ~0.4 s of replay so that clocks have ramped and nvidia-smi (100 ms
+    # period) sees the load.  Multi-rank: a FIXED count (every rank must issue the same number of collectives).
     n_warm = 0
     t_w = time.perf_counter()
-    # multi-rank: a FIXED count (every rank must issue the same number of collectives)
     fixed = max(args.warmup, 3000) if world > 1 else None
     while (n_warm < fixed) if fixed is not None else (n_warm < max(args.warmup, 3) or time.perf_counter() - t_w < 0.4):
         for i in range(50):
@@ -264,20 +328,25 @@ def bench_ours(args):
     _dbg("warm-up done (%d steps)" % n_warm)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record(stream)
-    for i in range(args.steps):
-        steps_obj[i % ring].run()
-    e1.record(stream)
-    barrier()
-    dt = e0.elapsed_time(e1) * 1e-3
+    repeats = 5 if args.steps < 200 else 3
+    block_ms = []
+    for _ in range(repeats):
+        barrier()
+        e0.record(stream)
+        for i in range(args.steps):
+            steps_obj[i % ring].run()
+        e1.record(stream)
+        barrier()
+        t_blk = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([t_blk], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            t_blk = float(t)
+        block_ms.append(t_blk)
+    dt = statistics.median(block_ms) * 1e-3
     _dbg("timed region done")
-    loss_val = float(steps_obj[(args.steps - 1) % ring].loss)
-    if world > 1:
-        t = torch.tensor([dt], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt = float(t)
-    _dbg("max over ranks done")
+    ops.join_side(dev)
+    loss_val = float(steps_obj[(args.steps - 1) % ring].loss.detach())
 
     # ---- end to end through the public API with HOST buffers: H2D of the step's inputs, step, D2H of the loss
     e2e_steps = max(3, min(args.steps, 50))
@@ -314,28 +383,32 @@ def bench_ours(args):
     for _ in range(3):
         e2e_once()
     _dbg("e2e warm done")
-    barrier()
-    e0.record(stream)
-    for _ in range(e2e_steps):
-        e2e_once()
-    e1.record(stream)
-    barrier()
+    e2e_ms = []
+    for _ in range(3):
+        barrier()
+        e0.record(stream)
+        for _ in range(e2e_steps):
+            e2e_once()
+        e1.record(stream)
+        barrier()
+        t_blk = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([t_blk], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            t_blk = float(t)
+        e2e_ms.append(t_blk)
+    dt_e2e = statistics.median(e2e_ms) * 1e-3
     _dbg("e2e done")
-    dt_e2e = e0.elapsed_time(e1) * 1e-3
-    if world > 1:
-        t = torch.tensor([dt_e2e], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt_e2e = float(t)
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- roofline of the dominant kernel, timed alone on the launching stream: the fused DMOL forward+backward
-    #      (one pass: reads raw + x, writes err + d raw).  Algorithmic bytes of the work it does:
-    #      fwd 27.0 MB + bwd 53.2 MB = 80.2 MB per 64 samples; bytes it actually has to move: 53.2 MB.
+    # ---- roofline of the dominant kernel, timed alone on the launching stream: the fused DMOL forward+backward (one pass:
+    #      reads raw + x, writes err + d raw = 53.2 MB moved; the work it replaces is SURVEY.md §8d's fwd 27.0 MB + bwd 53.2 MB).
+    #      Inputs AND outputs cycle through rings of > 3x L2 each, so reads come from and writes go to HBM.
     lib = _lib.load()
     raws = [s_.raw.detach() for s_ in steps_obj]
     xs = [s_.x for s_ in steps_obj]
     g = torch.full((batch, 1), 1.0 / batch, device=dev)
-    draw = [torch.empty_like(r) for r in raws[:2]]
+    draw = [torch.empty_like(raws[0]) for _ in range(ring)]
     err = torch.empty(batch, 1, device=dev)
     err_part = torch.empty(batch, max(int(lib.mae_dmol_err_chunks(batch, 1, 10, 1024)), 1), device=dev)
     ws = torch.zeros(max(int(lib.mae_dmol_workspace_bytes(batch, 1024)), 256), dtype=torch.uint8, device=dev)
@@ -344,11 +417,11 @@ def bench_ours(args):
     def k_fused(i):
         j = i % ring
         lib.mae_dmol_fwd_bwd(raws[j].data_ptr(), xs[j].data_ptr(), 1.0 / batch, batch, 1, 10, 1024, err_part.data_ptr(),
-                             draw[i % 2].data_ptr(), sp)
+                             draw[j].data_ptr(), sp)
 
     def k_bwd(i):
         j = i % ring
-        lib.mae_dmol_bwd(raws[j].data_ptr(), xs[j].data_ptr(), g.data_ptr(), 1, 1.0, batch, 1, 10, 1024, draw[i % 2].data_ptr(), sp)
+        lib.mae_dmol_bwd(raws[j].data_ptr(), xs[j].data_ptr(), g.data_ptr(), 1, 1.0, batch, 1, 10, 1024, draw[j].data_ptr(), sp)
 
     def k_fwd(i):
         j = i % ring
@@ -356,52 +429,102 @@ def bench_ours(args):
 
     n_k = max(20, min(200, args.steps))
     _dbg("kernel timing start")
-    t_fused = time_kernel(k_fused, n_k, stream)
-    t_bwd = time_kernel(k_bwd, n_k, stream)
-    t_fwd = time_kernel(k_fwd, n_k, stream)
+    t_fused = time_kernel(k_fused, n_k, stream, 5)
+    # the same kernel launched one at a time (a synchronize between launches): no head/tail overlap with its neighbour
+    ei0, ei1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    iso = []
+    for i in range(20):
+        torch.cuda.synchronize()
+        ei0.record(stream)
+        k_fused(i)
+        ei1.record(stream)
+        torch.cuda.synchronize()
+        iso.append(ei0.elapsed_time(ei1) * 1e-3)
+    t_iso = statistics.median(iso)
+    t_bwd = time_kernel(k_bwd, n_k, stream, 3)
+    t_fwd = time_kernel(k_fwd, n_k, stream, 3)
+    del draw
     _dbg("kernel timing done")
-    roof = {"bound": "hbm", "kernel": "dmol_bwd_kernel<10,1024,5,ERR=true> (fused forward+backward)",
-            "achieved": step_bytes / t_fused / 1e9, "peak": hbm_gbs, "unit": "GB/s", "frac": step_bytes / t_fused / 1e9 / hbm_gbs,
-            "traffic": ncu_traffic(), "peak_source": peak_src, "bytes_per_launch": step_bytes, "us_per_launch": t_fused * 1e6,
-            "bytes_moved_by_design": bwd_b, "frac_of_bytes_moved": bwd_b / t_fused / 1e9 / hbm_gbs,
-            "note": "algorithmic bytes = fwd 27.0 MB + bwd 53.2 MB (SURVEY 8d); the fused kernel reads raw once and writes d raw once; "
-                    "timed alone as back-to-back launches over the slab ring (> L2): consecutive launches overlap head/tail "
-                    "through programmatic dependent launch, an isolated launch (ncu) takes ~15-16 us",
+    step_s = dt / args.steps
+    roof = {"bound": "hbm", "kernel": "dmol_bwd_kernel<10,1024,5,ERR=true> (fused DMOL forward+backward, mae_dmol_fwd_bwd)",
+            "achieved": bwd_b / t_fused / 1e9, "peak": hbm_gbs, "unit": "GB/s", "frac": bwd_b / t_fused / 1e9 / hbm_gbs,
+            "traffic": ncu_traffic(), "peak_source": peak_src, "bytes_per_launch": bwd_b, "us_per_launch": t_fused * 1e6,
+            "us_per_launch_isolated": t_iso * 1e6, "frac_isolated": bwd_b / t_iso / 1e9 / hbm_gbs,
+            "algorithmic_bytes_replaced": step_bytes, "frac_of_algorithmic_bytes": step_bytes / t_fused / 1e9 / hbm_gbs,
+            "note": "achieved/frac count the 53.2 MB the kernel MOVES per launch (reads raw + x, writes d raw + err partials); "
+                    "the separate forward + backward it replaces are 27.0 + 53.2 = 80.2 MB (SURVEY 8d, frac_of_algorithmic_bytes); "
+                    "back-to-back launches over input and output rings of %d slabs each (> 3x L2), median of 5 blocks; "
+                    "us_per_launch_isolated = one launch between synchronizes" % ring,
             "dmol_bwd_alone": {"achieved": bwd_b / t_bwd / 1e9, "frac": bwd_b / t_bwd / 1e9 / hbm_gbs, "bytes_per_launch": bwd_b,
                                "us_per_launch": t_bwd * 1e6},
             "dmol_fwd_alone": {"achieved": fwd_b / t_fwd / 1e9, "frac": fwd_b / t_fwd / 1e9 / hbm_gbs, "bytes_per_launch": fwd_b,
                                "us_per_launch": t_fwd * 1e6},
-            "step": {"bytes": step_bytes, "us": dt / args.steps * 1e6, "frac": step_bytes / (dt / args.steps) / 1e9 / hbm_gbs}}
+            "step": {"bytes_algorithmic": step_bytes, "bytes_moved": bwd_b, "us": step_s * 1e6,
+                     "frac_algorithmic": step_bytes / step_s / 1e9 / hbm_gbs, "frac_moved": bwd_b / step_s / 1e9 / hbm_gbs}}
 
-    c4 = bench_c4(dev, hbm_gbs, world) if not args.no_extra else {}      # every rank: its shard of the evaluation
+    extra = {}
+    peaks = None
+    if not args.no_extra:
+        if rank == 0:
+            from mae_b200 import peaks as P
+            peaks = P.measure(dev)
+        barrier()
+        extra.update(bench_c4(dev, hbm_gbs, world))                       # every rank: its shard of the evaluation
+        if peaks is not None and "c4_iw_nll_eval" in extra:
+            extra["c4_iw_nll_eval"]["roofline"]["sfu_coroof"] = c4_sfu_coroof(peaks)
+        ffma_peak = [peaks["ffma_tflops"] if peaks else 0.0]
+        if world > 1:
+            t = torch.tensor(ffma_peak, device=dev, dtype=torch.float64)
+            dist.broadcast(t, 0)
+            ffma_peak = [float(t)]
+        extra.update(bench_c5(dev, world, rank, dist_ctx, ffma_peak[0], quick=args.quick))
+        if world == 1:
+            extra.update(bench_c1(dev, hbm_gbs))
+            extra["gpu_eager_baseline"] = gpu_eager_baseline(dev, value_ours=batch * args.steps / dt)
     out = None
     if rank == 0:
-        extra = dict(c4)
-        if world == 1 and not args.no_extra:
-            extra = bench_extra(dev, hbm_gbs, c4)
-        cpu = cpu_baseline_c3(budget_s=12.0) if not args.no_cpu else None
+        cpu = cpu_baseline_c3(budget_s=12.0) if (not args.no_cpu and world == 1) else None
         value = world * batch * args.steps / dt
         out = {
-            "metric": "mae_loss_head_fwd_bwd_samples_per_s", "value": value, "unit": "samples/s", "n_gpus": world,
+            "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world,
             "steps": args.steps, "warmup": n_warm, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "C3: CIFAR-10 32x32x3 head, DMOL nmix=10, latent 64, batch 64/GPU, MPD on (eta=gamma=1), "
-                                   "full MAE loss fwd+bwd on synthetic encoder/decoder outputs",
+            "config": {"workload": WORKLOAD,
                        "global_batch": world * batch, "parallelism": "dp%d (batch-sharded; MPD over the all-gathered batch)" % world,
-                       "l2": "ring of %d input slabs (%.0f MB) cycled > 126 MB L2" % (ring, ring * step_bytes / 1e6),
-                       "cuda_graph": use_graph},
+                       "l2": "ring of %d input slabs (%.0f MB read, %.0f MB written per cycle) > 3x 126 MB L2" % (
+                           ring, ring * (fwd_b) / 1e6, ring * (bwd_b - fwd_b) / 1e6),
+                       "cuda_graph": use_graph,
+                       "timing": "median of %d blocks of %d steps; warmup = max(--warmup=%d, 3, ~0.4 s of replay%s)" % (
+                           repeats, args.steps, args.warmup, ", 3000 at N>1" if world > 1 else "")},
+            "block_ms": block_ms,
             "e2e": {"value": world * batch * e2e_steps / dt_e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": 4, "ms_per_step": dt_e2e / e2e_steps * 1e3},
+                    "d2h_bytes_per_step": 4, "ms_per_step": dt_e2e / e2e_steps * 1e3, "steps": e2e_steps,
+                    "note": "median of 3 blocks; pinned host inputs -> H2D (copy stream, double-buffered) -> graph replay -> D2H of the loss"},
             "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
-            "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "loss": loss_val, "workloads": extra,
+            "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "loss": loss_val, "measured_peaks": peaks,
+            "workloads": extra,
         }
+        if parity_n is not None:
+            out["parity_n"] = parity_n[0]
+            out["parity_n_rel_err"] = parity_n[1]
     if world > 1:
+        dist_ctx.check()
         dist.barrier()
         torch.cuda.synchronize()
-    return out
+    return out, steps_obj
 
 
-# ------------------------------------------------------------------------------- secondary workloads (N=1)
+# ------------------------------------------------------------------------------------- secondary workloads
+def c4_sfu_coroof(peaks):
+    """SFU co-roof of the DMOL forward: 17 SFU instructions per (pixel, component) on the common path (hot_math.cuh: 3 ex2
+    of the scales, 6 ex2 of |hi| / |lo|, 3 ex2 + 1 rcp of the tanh coefficients, 1 rcp + 1 lg2 shared by the three channels,
+    2 ex2 of the two log-sum-exp accumulations) -> 170 per pixel-sample + ~4 to finish the two log-sum-exps."""
+    per_pix = 17 * 10 + 4
+    per_img = per_pix * 512 * 1024
+    rate = min(peaks["mufu_ex2_gops"], peaks["mufu_lg2_gops"], peaks["mufu_rcp_gops"]) * 1e9
+    return {"sfu_ops_per_image": per_img, "sfu_peak_gops_measured": rate / 1e9, "images_per_s_at_sfu_peak": rate / per_img}
+
+
 def bench_c4(dev, hbm_gbs, world=1):
     """C4 (IW-NLL eval) on every rank's own shard of synthetic images (no communication but the final reduction, §8e);
     throughput = images of all ranks / max time over ranks."""
@@ -439,7 +562,7 @@ def bench_c4(dev, hbm_gbs, world=1):
     if world > 1:
         dist.barrier()
         torch.cuda.synchronize()
-    t = time_kernel(lambda i: graphs[i % 3].replay(), 30, stream)
+    t = time_kernel(lambda i: graphs[i % 3].replay(), 30, stream, 3)
     if world > 1:
         tt = torch.tensor([t], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -456,13 +579,11 @@ def bench_c4(dev, hbm_gbs, world=1):
     return res
 
 
-def bench_extra(dev, hbm_gbs, c4):
-    """C4 (IW-NLL eval), C1/C2 (binary head) and C5 (MPD microbench) as secondary numbers with their own rooflines."""
+def bench_c1(dev, hbm_gbs):
+    """C1/C2 (binary head, B = 100, D = 64): launch-latency-bound (1.57 MB / 10 MFLOP per step)."""
     from mae_b200 import heads, ops, synth
     res = {}
     stream = torch.cuda.current_stream()
-    res.update(c4)
-    # ---- C1/C2: binary head fwd+bwd, B=100, D=64 (launch-latency-bound: 1.57 MB / 10 MFLOP per step)
     h = synth.binary_head(100, 1, 784)
     mu0, lv0 = synth.posterior_params(100, (64,))
     enc = torch.cat([mu0, lv0], 1).to(dev)
@@ -492,57 +613,125 @@ def bench_extra(dev, hbm_gbs, c4):
     with torch.cuda.graph(graph):
         c1_step()
     n_launch = ops.launch_count()
-    t = time_kernel(lambda i: graph.replay(), 200, stream)
+    t = time_kernel(lambda i: graph.replay(), 200, stream, 5)
     c1_bytes = 4 * (100 * 784 + 100 * 784 + 100) + 4 * (2 * 100 * 784 + 100 * 784 + 100)
-    res["c1_binary_head"] = {"metric": "mae_loss_head_fwd_bwd_samples_per_s", "value": 100 / t, "unit": "samples/s",
+    res["c1_binary_head"] = {"metric": METRIC, "value": 100 / t, "unit": "samples/s",
                              "config": "MNIST/OMNIGLOT 28x28 head, B=100, latent 64, Bernoulli + MPD fwd+bwd, CUDA graph",
                              "us_per_step": t * 1e6, "launches_per_step": n_launch,
                              "roofline": {"bound": "launch-latency", "hbm_floor_us": c1_bytes / (hbm_gbs * 1e9) * 1e6,
                                           "frac": c1_bytes / t / 1e9 / hbm_gbs}}
-    # ---- C5: MPD microbench fwd+bwd, B=8192, D=64 (16*B^2*D flop algorithmic)
-    for b5, d5 in ((8192, 64),):
-        mu5, lv5 = synth.posterior_params(b5, (d5,), seed=5)
-        mu5, lv5 = mu5.to(dev).requires_grad_(), lv5.to(dev).requires_grad_()
+    return res
+
+
+C5_SHAPES = ((4096, 64), (16384, 64), (65536, 64), (4096, 256), (16384, 256), (65536, 256))
+
+
+def bench_c5(dev, world, rank, dist_ctx, ffma_peak_tflops, quick=False):
+    """C5: MPD regulariser microbench, forward + backward, 16*B^2*D algorithmic flop.  At N > 1 the batch is
+    STRONG-scaled: every rank owns B/N rows, the packed (mu | logvar) rows are all-gathered, each rank evaluates its row
+    block of the B x B tile pass (one fp64 all-reduce of sum (KL - m)^2) and the complete gradient of its own rows."""
+    import torch.distributed as dist
+    from mae_b200 import ops, synth
+    res = {}
+    stream = torch.cuda.current_stream()
+    head = None
+    if world > 1:
+        from mae_b200.distributed import ShardedHead
+        head = ShardedHead(check_every=0, overlap=False)     # results are consumed by torch ops on the main stream
+    shapes = C5_SHAPES[:2] + C5_SHAPES[3:4] if quick else C5_SHAPES
+    for b5, d5 in shapes:
+        if b5 % world:
+            continue
+        b_loc = b5 // world
+        mu_g, lv_g = synth.posterior_params(b5, (d5,), seed=5)
+        sl = slice(rank * b_loc, (rank + 1) * b_loc)
+        enc = torch.cat([mu_g[sl], lv_g[sl]], 1).to(dev)
+        del mu_g, lv_g
+        mu5 = enc[:, :d5].detach().requires_grad_()
+        lv5 = enc[:, d5:].detach().requires_grad_()
 
         def c5(i):
             mu5.grad = None
             lv5.grad = None
-            m_d, s_ = ops.mpd(mu5, lv5)
+            if head is None:
+                m_d, s_ = ops.mpd(mu5, lv5)
+            else:
+                _, m_d, s_, _ = head.kl_mpd(mu5, lv5)
             (-torch.nn.functional.logsigmoid(m_d).sum() + s_).backward()
 
-        t = time_kernel(c5, 5, stream)
         flop = 16.0 * b5 * b5 * d5
-        res["c5_mpd_b%d_d%d" % (b5, d5)] = {"metric": "mpd_fwd_bwd_pairs_per_s", "value": b5 * b5 / t, "unit": "pairs/s",
-                                            "ms": t * 1e3, "tflops_algorithmic": flop / t / 1e12,
-                                            "roofline": {"bound": "fp32 ffma", "peak_tflops_nominal": 148 * 128 * 2 * 1.965e-3,
-                                                         "frac": flop / t / 1e12 / (148 * 128 * 2 * 1.965e-3)}}
+        n_it = 2 if flop > 2e12 else (5 if flop > 1e11 else 20)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+        t = time_kernel(c5, n_it, stream, 3)
+        if world > 1:
+            tt = torch.tensor([t], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            t = float(tt)
+        path = "sharded row block, recompute backward" if world > 1 else ("stored-KL backward" if b5 <= 32768 else "recompute backward")
+        res["c5_mpd_b%d_d%d" % (b5, d5)] = {
+            "metric": "mpd_fwd_bwd_pairs_per_s", "value": b5 * b5 / t, "unit": "pairs/s", "n_gpus": world, "scaling": "strong",
+            "ms": t * 1e3, "tflops_algorithmic": flop / t / 1e12, "path": path,
+            "roofline": {"bound": "fp32 ffma", "peak_tflops_measured": ffma_peak_tflops * world,
+                         "frac": (flop / t / 1e12 / (ffma_peak_tflops * world)) if ffma_peak_tflops > 0 else None}}
+        del enc, mu5, lv5
+        torch.cuda.empty_cache()
+    if head is not None:
+        head.check()
     return res
 
 
 # ------------------------------------------------------------------------------------------- CPU / reference
-def cpu_c3_step_fn(batch=64, latent=64):
-    """The oracle port of the reference's CPU path for one C3 step (fwd+bwd) on host cores."""
-    from mae_b200 import synth
+def c3_oracle_step_fn(device, batch=BATCH, latent=LATENT):
+    """The oracle port of the reference's ATen path for one C3 step (fwd+bwd) on ``device`` (host cores or, for the
+    same-box eager bar, the B200)."""
     from oracle import mae_oracle as O
-    h = c3_host_inputs(0, batch, latent)
+    h = {k: v.to(device) for k, v in c3_host_inputs(0, batch, latent).items()}
     enc = h["enc"].clone().requires_grad_()
     raw = h["raw"].clone().requires_grad_()
+    one = torch.ones((), device=device)
 
     def step():
         enc.grad = None
         raw.grad = None
         mu, lv = enc.chunk(2, 1)
         out, z = O.loss_head_color(mu, lv, h["eps"], lambda z_: raw, h["x"], 10, ETA, GAMMA, FREE_BITS)
-        torch.autograd.backward([out[0], z], [torch.ones(()), h["gz"]])
-        return float(out[0])
+        torch.autograd.backward([out[0], z], [one, h["gz"]])
+        return out[0].detach()
 
     return step
+
+
+def gpu_eager_baseline(dev, value_ours):
+    """SURVEY 8d / 2a 'same-box bar': the reference's own eager-PyTorch formulation of the path (oracle port = the same
+    ATen ops in the same order) executed on the B200 with CUDA tensors, timed with CUDA events.  C3 fwd+bwd and one C4
+    image (K = 512).  Not the product path: reported beside it."""
+    from oracle import mae_oracle as O
+    stream = torch.cuda.current_stream()
+    step = c3_oracle_step_fn(dev)
+    t_c3 = time_kernel(lambda i: step(), 10, stream, 3)
+    g = torch.Generator(device=dev).manual_seed(3)
+    k, d = 512, 64
+    raw = torch.randn(k, 100, 32, 32, device=dev, generator=g)
+    x = (torch.randint(0, 256, (1, 3, 32, 32), device=dev, generator=g).float() / 127.5 - 1.0)
+    mu = torch.randn(1, d, device=dev, generator=g)
+    lv = torch.randn(1, d, device=dev, generator=g).clamp(-7, 7)
+    z = mu[:, None] + torch.randn(1, k, d, device=dev, generator=g) * (0.5 * lv).exp()[:, None]
+    with torch.no_grad():
+        t_c4 = time_kernel(lambda i: O.iw_eval_color(raw, x, z, mu, lv, 10), 5, stream, 3)
+    out = {"what": "oracle port (the reference's ATen op sequence) on CUDA tensors, eager, CUDA events; median of 3 blocks",
+           "c3_samples_per_s": BATCH / t_c3, "c3_ms_per_step": t_c3 * 1e3, "c3_speedup_ours_device": value_ours * t_c3 / BATCH,
+           "c4_images_per_s": 1.0 / t_c4, "c4_ms_per_image": t_c4 * 1e3}
+    del raw
+    torch.cuda.empty_cache()
+    return out
 
 
 def cpu_baseline_c3(budget_s=12.0):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    step = cpu_c3_step_fn()
+    step = c3_oracle_step_fn("cpu")
     step()
     t0 = time.perf_counter()
     n = 0
@@ -550,7 +739,7 @@ def cpu_baseline_c3(budget_s=12.0):
         step()
         n += 1
     dt = (time.perf_counter() - t0) / n
-    return {"value": 64 / dt, "unit": "samples/s", "cores": cores, "kind": "port",
+    return {"value": BATCH / dt, "unit": "samples/s", "cores": cores, "kind": "port",
             "sample": "%d full C3 steps (B=64) of oracle/mae_oracle.py (torch CPU restatement of the reference's ATen path), "
                       "%.1f ms/step" % (n, dt * 1e3)}
 
@@ -563,28 +752,50 @@ def bench_reference(args):
         return None
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    step = cpu_c3_step_fn()
+    step = c3_oracle_step_fn("cpu")
     warm = max(1, min(args.warmup, 3))
     for _ in range(warm):
         step()
     steps = max(1, min(args.steps, 40))
     t0 = time.perf_counter()
     for _ in range(steps):
-        loss = step()
+        loss = float(step())
     dt = time.perf_counter() - t0
-    value = 64 * steps / dt
+    value = BATCH * steps / dt
     world = int(os.environ.get("WORLD_SIZE", "1"))
     return {
-        "impl": "reference", "metric": "mae_loss_head_fwd_bwd_samples_per_s", "value": value, "unit": "samples/s",
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "samples/s",
         "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C3: CIFAR-10 32x32x3 head, DMOL nmix=10, latent 64, batch 64, MPD on (eta=gamma=1), full MAE "
-                               "loss fwd+bwd on synthetic encoder/decoder outputs", "global_batch": 64, "parallelism": "host cpu"},
+        "config": {"workload": WORKLOAD, "global_batch": BATCH, "parallelism": "host cpu (one process, all cores; one batch of 64)"},
         "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port",
                          "sample": "%d C3 steps (B=64) of the oracle port on %d host threads" % (steps, cores)},
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "loss": loss,
     }
+
+
+def _teardown(steps_obj, timeout_s=20.0):
+    """Destroy the captured graphs, then the NCCL communicator.  A watchdog leaves the process if the communicator
+    teardown does not return (seen with torch 2.11 / NCCL 2.28.9 when graphs that captured peer / collective work are
+    still alive at destroy time)."""
+    import gc
+    import torch.distributed as dist
+    done = threading.Event()
+
+    def watchdog():
+        if not done.wait(timeout_s):
+            print("[bench] NCCL teardown did not return within %.0f s; leaving without it" % timeout_s, file=sys.stderr, flush=True)
+            os._exit(0)
+
+    threading.Thread(target=watchdog, daemon=True).start()
+    for st in steps_obj:
+        st.graph = None
+    steps_obj.clear()
+    gc.collect()
+    torch.cuda.synchronize()
+    dist.destroy_process_group()
+    done.set()
 
 
 def main():
@@ -594,29 +805,29 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying CUDA graphs")
-    ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads (C1, C4, C5)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads (C1, C4, C5, GPU-eager bar)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--quick", action="store_true", help="C5: three small shapes only")
     args = ap.parse_args()
     # stdout carries exactly one JSON line: library chatter written to fd 1 (NCCL prints its version banner there at
     # N > 1) is sent to stderr while the benchmark runs
     sys.stdout.flush()
     real_stdout = os.dup(1)
     os.dup2(2, 1)
+    steps_obj = None
     if args.impl == "reference":
         out = bench_reference(args)
     else:
         if not torch.cuda.is_available():
             raise SystemExit("bench.py needs a CUDA device (the hot path has no CPU fallback); use --impl reference for the CPU arm")
-        out = bench_ours(args)
+        out, steps_obj = bench_ours(args)
     sys.stdout.flush()
     sys.stderr.flush()
     if out is not None:
         os.write(real_stdout, (json.dumps(out) + "\n").encode())
     os.close(real_stdout)
     if int(os.environ.get("WORLD_SIZE", "1")) > 1 and args.impl == "ours":
-        # NCCL communicator teardown with live CUDA graphs that captured collectives hangs in this stack
-        # (torch 2.11 / NCCL 2.28.9); every rank has passed the final barrier, so leave without it.
-        os._exit(0)
+        _teardown(steps_obj)
 
 
 if __name__ == "__main__":

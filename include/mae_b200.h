@@ -298,6 +298,15 @@ int mae_comm_error(const void* own_buffer, int* error_out);
 int mae_allgather_rows(const float* local, int64_t n_floats, void* const* peer_buffers, int64_t rank, int64_t world,
                        int64_t slot_floats, float* out, mae_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Pipe-peak micro-benchmarks (measurement support, SURVEY.md §7 / §8d: the FP32-FFMA and SFU peaks that the MPD and
+ * DMOL rooflines are quoted against are measured on the box, not assumed).  Register-only loops; the caller times
+ * the launch with CUDA events.  *ops_out (host pointer, nullable) receives the lane-level instruction count of the
+ * launch (FFMA: flop = 2 * ops).  mufu op: 0 ex2.approx, 1 lg2.approx, 2 rcp.approx.
+ * ---------------------------------------------------------------------------------------------- */
+int mae_microbench_ffma(int64_t blocks, int64_t iters, float* sink, double* ops_out, mae_stream_t stream);
+int mae_microbench_mufu(int op, int64_t blocks, int64_t iters, float* sink, double* ops_out, mae_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -47,6 +47,8 @@ SIGNATURES = {
     "mae_comm_close_handle": [_P],
     "mae_comm_error": [_P, _P],
     "mae_allgather_rows": [_P, _I64, _P, _I64, _I64, _I64, _P, _P],
+    "mae_microbench_ffma": [_I64, _I64, _P, _P, _P],
+    "mae_microbench_mufu": [_I, _I64, _I64, _P, _P, _P],
 }
 # entry points that do not return a status code
 PLAIN = {

@@ -13,7 +13,7 @@
 // Epochs live on the device (the kernel is CUDA-graph replayable); consecutive epochs alternate landing parities so a
 // fast rank never overwrites data a slow peer is still copying out (a rank can start epoch e+1 only after every peer
 // has started epoch e, i.e. finished epoch e-1 entirely).  Spins are bounded: on timeout the kernel sets the error
-// flag and returns instead of hanging the GPU.
+// flag, NaN-fills its output slot and returns instead of hanging the GPU.
 #include "common.cuh"
 
 namespace mae {
@@ -85,7 +85,13 @@ p2p_allgather_kernel(const float* __restrict__ local, int64_t n_floats, char* co
         hdr->epoch[p] = e;
     }
     __syncthreads();
-    if (!timed_out) {
+    if (timed_out) {
+        // never hand uninitialised rows to the MPD kernels: NaN-fill the slot so the loss of this and every later step is
+        // visibly NaN (the error flag is sticky); ShardedHead.check() turns the flag into an exception
+        float* o = out + (int64_t)p * n_floats;
+        const float nan = __int_as_float(0x7fc00000);
+        for (int64_t i = threadIdx.x; i < n_floats; i += kThreads) o[i] = nan;
+    } else {
         // ---- copy slot p out of the landing buffer into the fixed output panel (L2 is the coherence point for
         //      the peer's NVLink writes; .cg loads skip this SM's L1)
         const float* land = reinterpret_cast<const float*>(own + landing_off(world)) + ((int64_t)parity * world + p) * slot_floats;

@@ -28,6 +28,9 @@ import torch
 import torch.distributed as dist
 
 SMALL_GLOBAL_BATCH = 2048   # <= : every rank evaluates the whole MPD forward redundantly (no all-reduce)
+# Rows per rank up to this many floats (1 MB) take the one-kernel NVLink push gather (pure latency regime); larger panels
+# (C5: up to 16 MB per rank) are bandwidth-bound and go through the library all-gather.
+PEER_SLOT_FLOATS = 1 << 18
 
 
 def _packed_parent(mu, logvar, b_loc, d):
@@ -137,6 +140,8 @@ class _ShardedKLMPD(torch.autograd.Function):
                 ev = torch.cuda.Event()
                 ev.record(ss)
             cs.wait_event(ev)
+            dmu.record_stream(cs)      # allocated on the side stream, consumed (and freed) on the main stream
+            dlv.record_stream(cs)
         else:
             dmu, dlv = eng.mpd_rows_backward(ctx.state, row0, b_loc, g_m, g_s, g_kl)
         ctx.keep = None
@@ -151,7 +156,7 @@ class _ShardedEncodeHead(torch.autograd.Function):
     the regulariser, and no collective, is left on it."""
 
     @staticmethod
-    def forward(ctx, mu, logvar, eps, head, eta, gamma, free_bits):
+    def forward(ctx, mu, logvar, eps, head, eta, gamma, free_bits, with_kl=True):
         ctx.set_materialize_grads(False)
         eng = head.engine
         want_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
@@ -166,7 +171,8 @@ class _ShardedEncodeHead(torch.autograd.Function):
                     packed = torch.cat([mu.reshape(b_loc, d), logvar.reshape(b_loc, d)], dim=1)
                 gathered = head._gather(packed)
                 row0 = head.rank * b_loc
-                out = eng.reg_rows_fused(gathered[:, :d], gathered[:, d:], row0, b_loc, eta, gamma, free_bits, want_grad)
+                out = eng.reg_rows_fused(gathered[:, :d], gathered[:, d:], row0, b_loc, eta, gamma, free_bits, want_grad,
+                                         kl_weight=None if with_kl else 0.0)
                 if out is not None:
                     m_d, s, kl_all, grads, reg = out
                     return m_d, s, kl_all, gathered, grads, reg
@@ -174,8 +180,8 @@ class _ShardedEncodeHead(torch.autograd.Function):
             else:
                 state_in = None
             kl_loc, m_d, s, kl_all, state, gathered, row0, b_loc = _ShardedKLMPD._compute(mu, logvar, head, state_in)
-            grads, reg = eng.mpd_rows_loss_backward(state, row0, b_loc, eta, gamma, free_bits, 1.0 / (world * b_loc), m_d,
-                                                    kl_all, want_grad)
+            grads, reg = eng.mpd_rows_loss_backward(state, row0, b_loc, eta, gamma, free_bits,
+                                                    1.0 / (world * b_loc) if with_kl else 0.0, m_d, kl_all, want_grad)
             return m_d, s, kl_all, gathered, grads, reg
 
         side = mu.is_cuda and hasattr(eng, "_side_stream") and head.overlap
@@ -202,49 +208,71 @@ class _ShardedEncodeHead(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gz, g_reg, *_unused):
         if gz is None and g_reg is None:
-            return (None,) * 7
+            return (None,) * 8
         if g_reg is not None and ctx.grads is None:
             raise RuntimeError("sharded encode head: reg has a gradient but mu / logvar did not require one in the forward")
         if ctx.event is not None:
-            torch.cuda.current_stream().wait_event(ctx.event)
+            torch.cuda.current_stream(ctx.saved[0].device).wait_event(ctx.event)
         dmu, dlv = ctx.eng.reparam_reg_bwd(ctx.saved, gz, ctx.grads, g_reg)
-        return dmu.view(ctx.shapes[0]), dlv.view(ctx.shapes[1]), None, None, None, None, None
+        return dmu.view(ctx.shapes[0]), dlv.view(ctx.shapes[1]), None, None, None, None, None, None
 
 
 class ShardedHead:
     """Batch-sharded MAE loss head / evaluator.  ``engine`` defaults to ``mae_b200.ops`` (the CUDA kernels)."""
 
     def __init__(self, group=None, engine=None, check_equal_batches: bool = False, overlap: bool = True,
-                 use_p2p: bool = True):
+                 use_p2p: bool = True, defer_join: bool = False, check_every: int = 256):
         if engine is None:
             from . import ops as engine
         self.engine = engine
         self.group = group
         self.check_equal_batches = check_equal_batches   # costs two tiny all-reduces and a host sync per step
         self.overlap = overlap                           # all-gather + MPD on the side stream (CUDA engine only)
-        self.defer_join = True                           # loss value valid after backward() / ops.join_side()
+        # defer_join=True keeps the objective's scalar on the side stream: loss / stats are then valid only after
+        # backward() or ops.join_side() (what a CUDA-graph-captured training step wants; bench.py sets it)
+        self.defer_join = defer_join
         self.two_node = True                             # regulariser backward in the forward pass (engine permitting)
-        self.peer = None                                 # NVLink peer-memory gather (created lazily, CUDA only)
+        self.peer = None                                 # NVLink peer-memory gather (created collectively, CUDA only)
         self.use_p2p = use_p2p
+        self.check_every = check_every                   # poll the gather's error flag every N eager steps (0: never)
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
+        self._pdl_before = None
         if self.world > 1 and hasattr(self.engine, "set_pdl"):
-            # measured at 8 GPUs (same box, A/B): 60.5 us/step without programmatic dependent launch vs 68.3 us with it
-            self.engine.set_pdl(False)
+            # measured at 8 GPUs (same box, A/B): 60.5 us/step without programmatic dependent launch vs 68.3 us with it.
+            # The switch is process-wide in the library; close() restores the previous setting.
+            self._pdl_before = self.engine.set_pdl(False)
+
+    def close(self) -> None:
+        """Release the peer buffers and restore the process-wide PDL setting this head changed."""
+        if self.peer is not None:
+            self.peer.close()
+            self.peer = None
+        if self._pdl_before is not None:
+            self.engine.set_pdl(self._pdl_before)
+            self._pdl_before = None
+
+    def check(self) -> None:
+        """Raise if the peer-memory gather ever timed out (its rows were NaN-filled).  Synchronises with the device."""
+        if self.peer is not None:
+            self.peer.check()
 
     def _gather(self, packed: torch.Tensor) -> torch.Tensor:
         """All-gather of the packed rows: one push-kernel over NVLink peer memory when available (tens of KB, pure
-        latency), else NCCL / gloo ``all_gather_into_tensor``."""
+        latency), else NCCL / gloo ``all_gather_into_tensor``.  Whether the peer path is used is decided collectively."""
         if self.use_p2p and packed.is_cuda and self.world > 1 and hasattr(self.engine, "_side_stream"):
             if self.peer is None:
-                try:
-                    from .p2p import PeerGather
-                    self.peer = PeerGather(self.group, max(packed.numel(), 1 << 16), packed.device)
-                except Exception as exc:  # no IPC / no peer access: keep the library collective
+                from .p2p import PeerGather
+                self.peer = PeerGather.create(self.group, PEER_SLOT_FLOATS, packed.device)
+                if self.peer is None:     # same outcome on every rank
                     import warnings
-                    warnings.warn("peer-memory all-gather unavailable (%s); using the library all-gather" % (exc,))
+                    warnings.warn("peer-memory all-gather unavailable (%s); using the library all-gather"
+                                  % (PeerGather.last_failure,))
                     self.use_p2p = False
             if self.peer is not None and self.peer.usable(packed):
+                if (self.check_every and self.peer.calls and self.peer.calls % self.check_every == 0
+                        and not torch.cuda.is_current_stream_capturing()):
+                    self.peer.check()
                 return self.peer.gather(packed)
         return _all_gather_rows(packed, self.group)
 
@@ -269,16 +297,37 @@ class ShardedHead:
         ext = torch.stack([kl_others.new_zeros(()), kl_others]).to(kl.dtype)
         return eng.assemble_loss(err, kl, m_d, s, eta, gamma, free_bits, 1.0 / b_glob, ext)
 
+    def encode_head(self, mu, logvar, eps, eta=0.0, gamma=0.0, free_bits=0.0, with_kl: bool = True):
+        """Sharded counterpart of ``ops.encode_head``: -> (z_loc, EncodedBatch).  ``enc.kl`` is the all-gathered analytic KL
+        vector [B_global] (None when ``with_kl`` is False: encoders with flows pass their own KL to ``loss_head``)."""
+        eng = self.engine
+        z, reg, kl_all, m_d, s = _ShardedEncodeHead.apply(mu, logvar, eps, self, float(eta), float(gamma), float(free_bits),
+                                                          bool(with_kl))
+        enc = eng.EncodedBatch(reg, kl_all if with_kl else None, m_d, s, (float(eta), float(gamma), float(free_bits)))
+        return z, enc
+
+    def loss_head(self, dec_out, x, enc, kind, ns, nmix=10, eta=0.0, gamma=0.0, free_bits=0.0, kl=None):
+        """Sharded counterpart of ``ops.loss_head``: -> (loss, stats, recon [B_loc]).  ``kl`` [B_loc] (differentiable): the
+        caller's Monte-Carlo KL when ``enc`` was made with ``with_kl=False``; its global mean enters the free-bits clamp
+        through one scalar all-reduce."""
+        b_loc = x.size(0)
+        ext = None
+        if kl is not None:
+            own = kl.detach().sum()
+            tot = own.clone()
+            dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=self.group)
+            ext = torch.stack([torch.zeros_like(own), tot - own]).float()
+        return self.engine.loss_head(dec_out, x, enc, kind, ns, nmix, eta, gamma, free_bits,
+                                     defer_join=self.overlap and self.defer_join, inv_batch=1.0 / (self.world * b_loc),
+                                     kl=kl, ext_sums=ext)
+
     def _two_node(self, mu, logvar, eps, dec_out, x, kind, nmix, eta, gamma, free_bits):
         """encode head (regulariser forward + backward behind the all-gather, side stream) + loss head."""
-        eng = self.engine
-        z, reg, kl_all, m_d, s = _ShardedEncodeHead.apply(mu, logvar, eps, self, float(eta), float(gamma), float(free_bits))
-        enc = eng.EncodedBatch(reg, kl_all, m_d, s, (float(eta), float(gamma), float(free_bits)))
+        z, enc = self.encode_head(mu, logvar, eps, eta, gamma, free_bits)
         b_loc = x.size(0)
-        loss, stats, recon = eng.loss_head(dec_out, x, enc, kind, eps.size(1), nmix, eta, gamma, free_bits,
-                                           defer_join=self.overlap and self.defer_join, inv_batch=1.0 / (self.world * b_loc))
+        loss, stats, recon = self.loss_head(dec_out, x, enc, kind, eps.size(1), nmix, eta, gamma, free_bits)
         row0 = self.rank * b_loc
-        return loss, recon, kl_all[row0:row0 + b_loc], stats, z
+        return loss, recon, enc.kl[row0:row0 + b_loc], stats, z
 
     def _has_two_node(self) -> bool:
         return self.two_node and all(hasattr(self.engine, n) for n in ("mpd_rows_loss_backward", "reparam_fwd",
@@ -304,10 +353,29 @@ class ShardedHead:
 
     def global_loss(self, loss: torch.Tensor, stats: torch.Tensor) -> torch.Tensor:
         """The global objective from a rank's loss: all-reduce of the reconstruction share (stats[4] = mean recon share)."""
+        if hasattr(self.engine, "join_side") and loss.is_cuda:
+            self.engine.join_side(loss.device)      # deferred objective kernels may still sit on the side stream
         share = stats[4].detach().clone()
         total = share.clone()
         dist.all_reduce(total, op=dist.ReduceOp.SUM, group=self.group)
         return loss.detach() - share + total
+
+    def global_loss_value(self, loss: torch.Tensor) -> torch.Tensor:
+        """Global objective from the per-rank losses returned by a sharded ``MAE.loss``: every rank's loss holds its share
+        of the reconstruction term plus the (identical) global KL / MPD terms, so
+        global = sum_r loss_r - (world - 1) * common, with common = loss_r - share_r; computed as
+        all_reduce(share) + (loss - share) using the share recorded by the last sharded loss call."""
+        share = self._last_share
+        if share is None:
+            raise RuntimeError("global_loss_value: no sharded MAE.loss call recorded on this head")
+        if hasattr(self.engine, "join_side") and loss.is_cuda:
+            self.engine.join_side(loss.device)
+        share = share.detach().clone()
+        total = share.clone()
+        dist.all_reduce(total, op=dist.ReduceOp.SUM, group=self.group)
+        return loss.detach() - share + total
+
+    _last_share = None
 
     # ----------------------------------------------------------------------------------------- evaluation
     def shard(self, n_items: int):
@@ -322,3 +390,45 @@ class ShardedHead:
         out = sums.clone()
         dist.all_reduce(out, op=dist.ReduceOp.SUM, group=self.group)
         return out
+
+
+# ------------------------------------------------------------------------------------------------ whole models
+def shard_model(model, head: Optional[ShardedHead]):
+    """Make ``model.loss`` (mae_b200.modules.MAE) treat its batch as this rank's shard of the global batch: the MPD
+    regulariser and the KL mean are taken over the all-gathered posteriors, and the returned gradients are those of the
+    GLOBAL objective, so ``all_reduce_gradients`` (SUM) afterwards reproduces the single-process parameter gradients.
+    Replaces the reference's ``nn.DataParallel`` replicas of the conv cores (gaussian_encoder.py:41-42).  ``None`` undoes it."""
+    model._sharded_head = head
+    return model
+
+
+def all_reduce_gradients(model, group=None, bucket_bytes: int = 64 << 20) -> None:
+    """SUM-all-reduce of every parameter gradient in flat buckets (north_star: 'gradients are all-reduced').  SUM, not
+    MEAN: the sharded loss already divides by the global batch.  Parameters without a gradient on some rank are treated as
+    zero there (every rank must own the same parameter set)."""
+    params = [p for p in model.parameters() if p.requires_grad]
+    bucket, size = [], 0
+
+    def flush():
+        nonlocal bucket, size
+        if not bucket:
+            return
+        flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in bucket])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        off = 0
+        for p in bucket:
+            n = p.numel()
+            g = flat[off:off + n].view_as(p)
+            if p.grad is None:
+                p.grad = g.clone()
+            else:
+                p.grad.copy_(g)
+            off += n
+        bucket, size = [], 0
+
+    for p in params:
+        if bucket and (bucket[0].dtype != p.dtype or size + p.numel() * p.element_size() > bucket_bytes):
+            flush()
+        bucket.append(p)
+        size += p.numel() * p.element_size()
+    flush()

@@ -23,6 +23,7 @@ class MAE(nn.Module):
                              % (encoder.z_shape(), decoder.z_shape()))
         self.encoder = encoder
         self.decoder = decoder
+        self._sharded_head = None     # mae_b200.distributed.shard_model
 
     def z_shape(self) -> Tuple:
         return self.encoder.z_shape()
@@ -54,7 +55,11 @@ class MAE(nn.Module):
             mu, logvar = enc.core(x)
             eps = enc._draw_eps(mu, nsamples)
             flows = enc.prior_flow is not None or enc.posterior_flow is not None
-            z, eb = ops.encode_head(mu, logvar, eps, eta, gamma, free_bits, with_kl=not flows)
+            head = getattr(self, "_sharded_head", None)     # set by mae_b200.distributed.shard_model: x is this rank's shard
+            if head is None:
+                z, eb = ops.encode_head(mu, logvar, eps, eta, gamma, free_bits, with_kl=not flows)
+            else:
+                z, eb = head.encode_head(mu, logvar, eps, eta, gamma, free_bits, with_kl=not flows)
             KL = None
             if flows:
                 # gaussian_encoder.py:220-225: KL = mean_s(log q(z|x) - log p(z)) through the flows (PyTorch) and the
@@ -70,16 +75,27 @@ class MAE(nn.Module):
                 log_q = ops.log_prob_posterior(z_normal, mu, logvar, logdet)
                 KL = (log_q - log_p).mean(dim=1)
             dec_out = dec.likelihood_input(x, z.view(z.size(0), z.size(1), *z_shape_dec))
-            loss, stats, recon = ops.loss_head(dec_out, x, eb, dec.likelihood_kind, nsamples, getattr(dec, "nmix", 0), eta, gamma,
-                                               free_bits, kl=KL)
-            if KL is None:
-                KL = eb.kl
+            if head is None:
+                loss, stats, recon = ops.loss_head(dec_out, x, eb, dec.likelihood_kind, nsamples, getattr(dec, "nmix", 0), eta,
+                                                   gamma, free_bits, kl=KL)
+                if KL is None:
+                    KL = eb.kl
+            else:
+                loss, stats, recon = head.loss_head(dec_out, x, eb, dec.likelihood_kind, nsamples, getattr(dec, "nmix", 0), eta,
+                                                    gamma, free_bits, kl=KL)
+                if KL is None:
+                    row0 = head.rank * x.size(0)
+                    KL = eb.kl[row0:row0 + x.size(0)]          # eb.kl is the all-gathered vector of the global batch
+                head._last_share = stats[4]                    # this rank's share of the reconstruction mean (global_loss_value)
             m_d, S = eb.m_d, eb.s
         else:
-            if isinstance(enc, GaussianEncoder):
+            if getattr(self, "_sharded_head", None) is not None:
+                raise RuntimeError("shard_model: batch-sharded MAE.loss needs the stock GaussianEncoder.encode and a stock "
+                                   "Bernoulli / DMOL reconstruct_error (custom encoders / decoders are single-process only)")
+            if isinstance(enc, GaussianEncoder) and type(enc).encode is GaussianEncoder.encode:
                 z, KL, (m_d, S) = enc.encode(x, nsamples, _side_stream=True)   # MPD overlaps with the decoder
             else:
-                z, KL, (m_d, S) = self.encode(x, nsamples)
+                z, KL, (m_d, S) = self.encode(x, nsamples)                     # subclass with the reference's signature
             err = dec.reconstruct_error(x, z.view(z.size(0), z.size(1), *z_shape_dec))
             loss, stats, recon = ops.assemble_loss(err, KL, m_d, S, eta, gamma, free_bits)
         loss_mean = stats[1] if eta > 0. else 0.
@@ -113,8 +129,19 @@ class MAE(nn.Module):
         Reference: mae/modules/mae.py:179-216.  Evaluation-only (the reference calls it under no_grad)."""
         batch = x.size(0)
         with torch.no_grad():
-            z, (mu, logvar, z_post_normal, logdet_post) = self.sample_from_posterior(x, nsamples=k)
+            z, distr_params = self.sample_from_posterior(x, nsamples=k)
             enc = self.encoder
+            if not (isinstance(distr_params, (tuple, list)) and len(distr_params) == 4):
+                # an encoder whose posterior is not (mu, logvar, z_normal, logdet)-shaped: the reference's own composition
+                # (mae.py:203-215) through its log_probability_* methods
+                zd = z.view(batch, k, *self.decoder.z_shape())
+                log_gen = self.decoder.log_probability(x, zd)
+                log_prior = enc.log_probability_prior(z.view(batch * k, *z.size()[2:])).view(batch, k)
+                log_post = enc.log_probability_posterior(x, z, distr_params=distr_params)
+                log_iw = log_gen + log_prior - log_post
+                nll_iw = -(torch.logsumexp(log_iw, dim=1) - float(np.log(k)))
+                return (log_iw.mean(dim=1) * -1., log_gen.mean(dim=1) * -1., (log_post - log_prior).mean(dim=1)), nll_iw
+            mu, logvar, z_post_normal, logdet_post = distr_params
             prior_flow = getattr(enc, 'prior_flow', None)
             if prior_flow is None:
                 z_prior_normal, logdet_prior = z, None

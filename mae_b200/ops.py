@@ -17,7 +17,7 @@ from . import _lib
 __all__ = [
     "reparam_kl", "mpd", "mpd_forward_only", "bernoulli_recon_error", "dmol_recon_error", "log_prob_prior",
     "log_prob_posterior", "iw_nll", "assemble_loss", "kl_mpd", "loss_tail", "loss_head", "encode_head", "kl_mpd_reg_fused", "kl_mpd_reg", "mpd_rows_loss_backward", "reg_rows_fused", "reparam_fwd",
-    "reparam_reg_bwd", "fused_reg_supported", "set_pdl", "join_side", "launch_count", "reset_launch_count",
+    "reparam_reg_bwd", "fused_reg_supported", "set_pdl", "set_unit_loss_grad", "join_side", "launch_count", "reset_launch_count",
 ]
 
 _launches = 0  # number of kernels of ours enqueued since the last reset (bench.py reports it)
@@ -51,7 +51,56 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+class _on:
+    """Device guard: the library launches on the CURRENT device and ``_stream()`` is that device's current stream, so every
+    op body runs with the device of its tensors current (a model on cuda:1 while cuda:0 is current, MAE.load(path,
+    'cuda:1'), DataParallel replicas).  A no-op when the device already is current."""
+    __slots__ = ("idx", "prev")
+
+    def __init__(self, dev):
+        idx = dev.index if isinstance(dev, torch.device) else dev
+        self.idx = idx if (idx is not None and idx != torch.cuda.current_device()) else None
+
+    def __enter__(self):
+        if self.idx is not None:
+            self.prev = torch.cuda.current_device()
+            torch.cuda.set_device(self.idx)
+        return self
+
+    def __exit__(self, *exc):
+        if self.idx is not None:
+            torch.cuda.set_device(self.prev)
+        return False
+
+
+def _guarded(fn):
+    """Decorator for autograd.Function.forward / backward and plain ops: runs the body under the device of the first CUDA
+    tensor among the arguments (backward: of the tensors the forward saw, remembered on ctx)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        dev = None
+        for a in args:
+            if isinstance(a, torch.Tensor) and a.is_cuda:
+                dev = a.device
+                break
+        ctx = args[0] if args and hasattr(args[0], "save_for_backward") else None
+        if ctx is not None:
+            if dev is None:
+                dev = getattr(ctx, "_mae_dev", None)
+            else:
+                ctx._mae_dev = dev
+        if dev is None:
+            return fn(*args, **kwargs)
+        with _on(dev):
+            return fn(*args, **kwargs)
+
+    return wrapper
+
+
 def _req_cuda(*tensors: Optional[torch.Tensor]) -> None:
+    dev = None
     for t in tensors:
         if t is None:
             continue
@@ -59,6 +108,10 @@ def _req_cuda(*tensors: Optional[torch.Tensor]) -> None:
             raise RuntimeError("mae_b200 ops run on CUDA tensors only (got %s): there is no CPU fallback" % t.device)
         if t.dtype != torch.float32:
             raise RuntimeError("mae_b200 ops compute in float32 (got %s)" % t.dtype)
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError("mae_b200 ops need all tensors on one device (got %s and %s)" % (dev, t.device))
 
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -143,6 +196,7 @@ def join_side(device: torch.device) -> None:
 # ------------------------------------------------------------------------------------------------
 class _ReparamKL(torch.autograd.Function):
     @staticmethod
+    @_guarded
     def forward(ctx, mu, logvar, eps, want_kl):
         ctx.set_materialize_grads(False)
         _req_cuda(mu, logvar, eps)
@@ -164,6 +218,7 @@ class _ReparamKL(torch.autograd.Function):
         return z, kl
 
     @staticmethod
+    @_guarded
     def backward(ctx, gz, gkl):
         mu2, lv2, eps_c = ctx.saved_tensors
         ms, ls, b, ns, d, mu_shape, lv_shape = ctx.meta
@@ -229,6 +284,7 @@ class _MPD(torch.autograd.Function):
     shares the O(B*D) pre-pass with the MPD, and its gradient is folded into the MPD backward kernel."""
 
     @staticmethod
+    @_guarded
     def forward(ctx, mu, logvar, bwd_path, side, with_kl):
         ctx.set_materialize_grads(False)
         _req_cuda(mu, logvar)
@@ -281,6 +337,7 @@ class _MPD(torch.autograd.Function):
             _pool.give(ws)
 
     @staticmethod
+    @_guarded
     def backward(ctx, g_m, g_s, g_kl):
         mu2, lv2, s = ctx.saved_tensors
         ms, ls, b, d, mu_shape, lv_shape, path = ctx.meta
@@ -296,10 +353,14 @@ class _MPD(torch.autograd.Function):
         g_m = g_m.contiguous().view(-1) if g_m is not None else None
         g_s = g_s.contiguous() if g_s is not None else None
         g_kl = g_kl.contiguous() if g_kl is not None else None
-        dmu = torch.empty(b, d, device=dev, dtype=torch.float32)
-        dlv = torch.empty_like(dmu)
+        dmu = dlv = None
 
         def launch():
+            # allocated on the stream that writes them (on the side-stream path autograd has already queued the decoder's
+            # backward on the main stream: a block freshly freed there may still be in use by a pending main-stream kernel)
+            nonlocal dmu, dlv
+            dmu = torch.empty(b, d, device=dev, dtype=torch.float32)
+            dlv = torch.empty_like(dmu)
             _lib.check(_lib_().mae_mpd_bwd(mu2.data_ptr(), ms, lv2.data_ptr(), ls, ws.data_ptr(), ws.numel(), b, d, 0, b,
                                            _ptr(g_m), _ptr(g_s), s.data_ptr(), _ptr(g_kl), dmu.data_ptr(), dlv.data_ptr(), 0, path,
                                            _stream()), "mae_mpd_bwd")
@@ -323,6 +384,8 @@ class _MPD(torch.autograd.Function):
                 ev = torch.cuda.Event()
                 ev.record(ss)
             cs.wait_event(ev)   # later main-stream work (and any reuse of g_m / g_s memory) is ordered after the kernel
+            dmu.record_stream(cs)   # consumed and freed on the main stream
+            dlv.record_stream(cs)
         else:
             launch()
             _pool.give(ws)
@@ -347,6 +410,7 @@ def mpd(mu: torch.Tensor, logvar: torch.Tensor, bwd_path: int = 0, side_stream: 
     return m_d, s
 
 
+@_guarded
 def mpd_forward_only(mu: torch.Tensor, logvar: torch.Tensor, row0: int = 0, nrows: Optional[int] = None):
     """Forward on a row block: returns (m_d, S_of_block_as_if_complete, sumsq[1] fp64).  For multi-GPU
     row-blocked evaluation: all-reduce ``sumsq`` and call :func:`mpd_finalize`."""
@@ -367,6 +431,7 @@ class MpdRowsState:
         self.ws, self.mu2, self.ms, self.lv2, self.ls, self.b, self.d, self.s, self.path = ws, mu2, ms, lv2, ls, b, d, s, path
 
 
+@_guarded
 def mpd_rows_forward(mu_all: torch.Tensor, logvar_all: torch.Tensor, row0: int, nrows: int, full: bool):
     """Row-blocked MPD forward for batch-sharded runs (mu_all / logvar_all are the ALL-GATHERED posteriors [B,D]).
 
@@ -393,6 +458,7 @@ def mpd_rows_forward(mu_all: torch.Tensor, logvar_all: torch.Tensor, row0: int, 
     return m_d, (s if full else sumsq), kl_all, state
 
 
+@_guarded
 def mpd_rows_backward(state: "MpdRowsState", row0: int, nrows: int, g_m, g_s, g_kl_rows):
     """Gradient w.r.t. mu / logvar of rows [row0,row0+nrows) only (complete: as the i and as the j argument), so a
     batch-sharded run needs no reduce-scatter.  g_kl_rows [nrows] is the upstream gradient of those rows' KL."""
@@ -414,6 +480,7 @@ def mpd_rows_backward(state: "MpdRowsState", row0: int, nrows: int, g_m, g_s, g_
     return dmu, dlv
 
 
+@_guarded
 def mpd_rows_loss_backward(state: "MpdRowsState", row0: int, nrows: int, eta: float, gamma: float, free_bits: float,
                            kl_weight: float, m_d: torch.Tensor, kl_all: Optional[torch.Tensor], want_grad: bool = True):
     """Regulariser value and its gradient w.r.t. rows [row0,row0+nrows), enqueued right behind the forward kernels
@@ -435,7 +502,7 @@ def mpd_rows_loss_backward(state: "MpdRowsState", row0: int, nrows: int, eta: fl
 
 
 def reg_rows_fused(mu_all: torch.Tensor, logvar_all: torch.Tensor, row0: int, nrows: int, eta: float, gamma: float,
-                   free_bits: float, want_grad: bool = True):
+                   free_bits: float, want_grad: bool = True, kl_weight: Optional[float] = None):
     """Batch-sharded runs whose GLOBAL batch fits the cluster kernel (B_global <= 128, D <= 64): the whole regulariser of
     the gathered rows in one launch instead of prepare -> tiles -> gradients -> backward.  Every rank evaluates all rows
     (a few microseconds) and keeps the gradient of its own.  -> (m_d, S, kl_all, grads [2,nrows,D] or None, reg), or None
@@ -444,11 +511,12 @@ def reg_rows_fused(mu_all: torch.Tensor, logvar_all: torch.Tensor, row0: int, nr
     b, d = mu2.shape
     if not fused_reg_supported(b, d, mu2.device):
         return None
-    kl_all, m_d, s_, reg, grads, _ = kl_mpd_reg_fused(mu_all, logvar_all, eta, gamma, free_bits, None, want_grad)
+    kl_all, m_d, s_, reg, grads, _ = kl_mpd_reg_fused(mu_all, logvar_all, eta, gamma, free_bits, kl_weight, want_grad)
     own = grads[:, row0:row0 + nrows] if grads is not None else None      # [2, nrows, D]: rows are contiguous
     return m_d, s_, kl_all, own, reg
 
 
+@_guarded
 def reparam_fwd(mu: torch.Tensor, logvar: torch.Tensor, eps: torch.Tensor):
     """z = eps * exp(0.5 logvar) + mu without an autograd node (building block of the fused encoder nodes):
     -> (z, saved) with ``saved`` = what :func:`reparam_reg_bwd` needs."""
@@ -464,6 +532,7 @@ def reparam_fwd(mu: torch.Tensor, logvar: torch.Tensor, eps: torch.Tensor):
     return z, (mu2, ms, lv2, ls, eps_c, b, ns, d)
 
 
+@_guarded
 def reparam_reg_bwd(saved, gz: Optional[torch.Tensor], grads: Optional[torch.Tensor], g_reg: Optional[torch.Tensor]):
     """d(mu, logvar) = reparameterisation backward of d z  +  g_reg * grads  in one launch (mae_reparam_reg_bwd);
     grads = [2,B,D] from the regulariser kernels, g_reg a device scalar.  -> (dmu, dlv) dense [B,D]."""
@@ -482,6 +551,7 @@ def reparam_reg_bwd(saved, gz: Optional[torch.Tensor], grads: Optional[torch.Ten
     return dmu, dlv
 
 
+@_guarded
 def mpd_finalize(sumsq: torch.Tensor, batch: int) -> torch.Tensor:
     s = torch.empty((), device=sumsq.device, dtype=torch.float32)
     _lib.check(_lib_().mae_mpd_finalize(sumsq.data_ptr(), batch, s.data_ptr(), _stream()), "mae_mpd_finalize")
@@ -494,6 +564,7 @@ def mpd_finalize(sumsq: torch.Tensor, batch: int) -> torch.Tensor:
 # ------------------------------------------------------------------------------------------------
 class _Bernoulli(torch.autograd.Function):
     @staticmethod
+    @_guarded
     def forward(ctx, probs, x):
         _req_cuda(probs, x)
         b, ns, p = probs.shape
@@ -509,6 +580,7 @@ class _Bernoulli(torch.autograd.Function):
         return err
 
     @staticmethod
+    @_guarded
     def backward(ctx, g):
         probs_c, x_c = ctx.saved_tensors
         b, ns, p = probs_c.shape
@@ -531,6 +603,7 @@ def bernoulli_recon_error(probs: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
 # ------------------------------------------------------------------------------------------------
 class _Dmol(torch.autograd.Function):
     @staticmethod
+    @_guarded
     def forward(ctx, raw, x, ns, nmix):
         _req_cuda(raw, x)
         n, ch = raw.size(0), raw.size(1)
@@ -552,6 +625,7 @@ class _Dmol(torch.autograd.Function):
         return err
 
     @staticmethod
+    @_guarded
     def backward(ctx, g):
         raw_c, x_c = ctx.saved_tensors
         b, ns, nmix, hw = ctx.meta
@@ -574,6 +648,7 @@ def dmol_recon_error(raw: torch.Tensor, x: torch.Tensor, ns: int, nmix: int) -> 
 # ------------------------------------------------------------------------------------------------
 class _LogPrior(torch.autograd.Function):
     @staticmethod
+    @_guarded
     def forward(ctx, z, logdet):
         _req_cuda(z, logdet)
         n = z.size(0)
@@ -589,6 +664,7 @@ class _LogPrior(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_guarded
     def backward(ctx, g):
         (z_c,) = ctx.saved_tensors
         shape, has_ld = ctx.meta
@@ -610,6 +686,7 @@ def log_prob_prior(z_normal: torch.Tensor, logdet: Optional[torch.Tensor] = None
 
 class _LogPosterior(torch.autograd.Function):
     @staticmethod
+    @_guarded
     def forward(ctx, z, mu, logvar, logdet):
         _req_cuda(z, mu, logvar, logdet)
         b, k = z.size(0), z.size(1)
@@ -627,6 +704,7 @@ class _LogPosterior(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_guarded
     def backward(ctx, g):
         z_c, mu2, lv2 = ctx.saved_tensors
         ms, ls, z_shape, mu_shape, lv_shape, has_ld = ctx.meta
@@ -651,6 +729,7 @@ def log_prob_posterior(z_normal: torch.Tensor, mu: torch.Tensor, logvar: torch.T
 # ------------------------------------------------------------------------------------------------
 # A5 + A6 + A7 fused (evaluation only: outputs carry no autograd graph, like calc_nll's no_grad use)
 # ------------------------------------------------------------------------------------------------
+@_guarded
 @torch.no_grad()
 def iw_nll(log_gen: torch.Tensor, z_prior_normal: torch.Tensor, logdet_prior: Optional[torch.Tensor],
            z_post_normal: torch.Tensor, logdet_post: Optional[torch.Tensor], mu: torch.Tensor, logvar: torch.Tensor,
@@ -683,6 +762,7 @@ def iw_nll(log_gen: torch.Tensor, z_prior_normal: torch.Tensor, logdet_prior: Op
 # ------------------------------------------------------------------------------------------------
 class _Assemble(torch.autograd.Function):
     @staticmethod
+    @_guarded
     def forward(ctx, err, kl, m_d, s, eta, gamma, free_bits, inv_batch, ext_sums):
         ctx.set_materialize_grads(False)
         _req_cuda(err, kl, m_d, s, ext_sums)
@@ -705,6 +785,7 @@ class _Assemble(torch.autograd.Function):
         return loss, stats, recon
 
     @staticmethod
+    @_guarded
     def backward(ctx, gloss, _gstats, _grecon):
         scalars, m_c = ctx.saved_tensors
         b, ns, d, eta, gamma, free_bits, inv_batch, m_shape, has_s = ctx.meta
@@ -772,6 +853,22 @@ def _likelihood_fwd(dec_out, x, kind, ns, nmix, inv_batch, need_grad):
     return out_c, x_c, err, err_chunks, fused_grad, geom
 
 
+_unit_loss_grad = False
+
+
+def set_unit_loss_grad(enabled: bool) -> bool:
+    """Promise that every ``backward()`` through the fused loss nodes starts from d loss = 1 (``loss.backward()`` without an
+    explicit gradient and without scaling the loss first, as in experiments/color_image.py:158).  The fused DMOL node
+    produced (1/B) d err / d raw in the forward pass already; with the promise its backward is a no-op instead of a
+    conditional rescale launch that would find the scale to be 1.  Used by ``mae_b200.graph.capture_step`` and bench.py,
+    which create that gradient themselves.  Returns the previous setting.  NOT safe with loss scaling (AMP) or when the
+    loss enters a larger expression before ``backward()``."""
+    global _unit_loss_grad
+    prev = _unit_loss_grad
+    _unit_loss_grad = bool(enabled)
+    return prev
+
+
 def _likelihood_bwd(ctx, out_c, x_c, gloss, kind, b, ns, nmix, geom, inv_batch, out_shape):
     """d loss / d dec_out on the current stream (gloss: device scalar d loss)."""
     lib = _lib_()
@@ -781,6 +878,8 @@ def _likelihood_bwd(ctx, out_c, x_c, gloss, kind, b, ns, nmix, geom, inv_batch, 
                                "backward is not supported on this path)")
         dout = ctx.fused_grad
         ctx.fused_grad = False
+        if _unit_loss_grad:
+            return dout.view(out_shape)       # d loss == 1 by the caller's promise: nothing to launch
         _lib.check(lib.mae_scale_inplace(dout.data_ptr(), dout.numel(), gloss.data_ptr(), _stream()), "mae_scale_inplace")
     else:
         dout = torch.empty_like(out_c)
@@ -806,6 +905,7 @@ class _LossTail(torch.autograd.Function):
     after ``backward()`` (which joins) or ``ops.join_side()``."""
 
     @staticmethod
+    @_guarded
     def forward(ctx, dec_out, x, kl, m_d, s, ext_sums, kl_all, kind, ns, nmix, eta, gamma, free_bits, inv_batch, defer):
         ctx.set_materialize_grads(False)
         _req_cuda(dec_out, x, kl, m_d, s, ext_sums, kl_all)
@@ -851,6 +951,7 @@ class _LossTail(torch.autograd.Function):
         return loss, stats, recon
 
     @staticmethod
+    @_guarded
     def backward(ctx, gloss, _gs, _gr):
         if gloss is None:
             return (None,) * 15
@@ -921,6 +1022,7 @@ def fused_reg_supported(b: int, d: int, device: torch.device) -> bool:
     return ok
 
 
+@_guarded
 def kl_mpd_reg_fused(mu: torch.Tensor, logvar: torch.Tensor, eta: float, gamma: float, free_bits: float,
                      kl_weight: Optional[float] = None, want_grad: bool = True, launch_stream=None):
     """Raw (non-autograd) call of the one-launch regulariser kernel on the current stream (or on ``launch_stream``, which
@@ -953,6 +1055,7 @@ def kl_mpd_reg_fused(mu: torch.Tensor, logvar: torch.Tensor, eta: float, gamma: 
     return kl, m_d.view(mu.shape[1:]), s_, reg, grads, (mu2, lv2)
 
 
+@_guarded
 def kl_mpd_reg(mu: torch.Tensor, logvar: torch.Tensor, eta: float, gamma: float, free_bits: float,
                kl_weight: Optional[float] = None, want_grad: bool = True, launch_stream=None):
     """Same contract as :func:`kl_mpd_reg_fused` for ANY batch / latent size: the one-launch cluster kernel where it
@@ -999,6 +1102,7 @@ class _EncodeHead(torch.autograd.Function):
     backward ONE launch: d(mu, logvar) = reparam backward of d z  +  d reg * (stored regulariser gradient)."""
 
     @staticmethod
+    @_guarded
     def forward(ctx, mu, logvar, eps, eta, gamma, free_bits, with_kl):
         ctx.set_materialize_grads(False)
         _req_cuda(mu, logvar, eps)
@@ -1029,6 +1133,7 @@ class _EncodeHead(torch.autograd.Function):
         return z, reg, kl, m_d, s
 
     @staticmethod
+    @_guarded
     def backward(ctx, gz, g_reg, *_unused):
         if gz is None and g_reg is None:
             return (None,) * 7
@@ -1076,9 +1181,10 @@ class _LossTailReg(torch.autograd.Function):
     backward: d dec_out (a conditional rescale by d loss) and d reg = d loss.  ``defer``: see _LossTail."""
 
     @staticmethod
-    def forward(ctx, dec_out, x, reg, kl, m_d, s, kind, ns, nmix, eta, gamma, free_bits, defer, inv_batch):
+    @_guarded
+    def forward(ctx, dec_out, x, reg, kl, m_d, s, kind, ns, nmix, eta, gamma, free_bits, defer, inv_batch, ext_sums=None):
         ctx.set_materialize_grads(False)
-        _req_cuda(dec_out, x, reg, kl, m_d, s)
+        _req_cuda(dec_out, x, reg, kl, m_d, s, ext_sums)
         kl_ext = ctx.needs_input_grad[3]      # a differentiable KL from the caller (Monte-Carlo estimate with flows)
         kl = kl.contiguous()
         lib = _lib_()
@@ -1094,7 +1200,7 @@ class _LossTailReg(torch.autograd.Function):
         recon = torch.empty(b, device=dev, dtype=torch.float32)
 
         def assemble():
-            _lib.check(lib.mae_loss_assemble_fwd(err.data_ptr(), kl.data_ptr(), m_c.data_ptr(), s.data_ptr(), None, b, ns, d,
+            _lib.check(lib.mae_loss_assemble_fwd(err.data_ptr(), kl.data_ptr(), m_c.data_ptr(), s.data_ptr(), _ptr(ext_sums), b, ns, d,
                                                  kl_count, err_chunks, eta, gamma, free_bits, inv_batch, scalars.data_ptr(),
                                                  recon.data_ptr(), _stream()), "mae_loss_assemble_fwd")
             _count()
@@ -1109,7 +1215,7 @@ class _LossTailReg(torch.autograd.Function):
                 assemble()
                 ev = torch.cuda.Event()
                 ev.record(ss)
-            _pending_join[idx] = (ev, (prev, err, kl, m_c, s, scalars, recon))
+            _pending_join[idx] = (ev, (prev, err, kl, m_c, s, scalars, recon, ext_sums))
         else:
             join_side(dev)
             assemble()
@@ -1121,9 +1227,10 @@ class _LossTailReg(torch.autograd.Function):
         return loss, stats, recon
 
     @staticmethod
+    @_guarded
     def backward(ctx, gloss, *_unused):
         if gloss is None:
-            return (None,) * 14
+            return (None,) * 15
         out_c, x_c, scalars = ctx.saved_tensors
         kind, b, ns, nmix, geom, out_shape, defer, inv_batch, kl_ext, (eta, gamma, free_bits) = ctx.meta
         gloss = gloss.contiguous()
@@ -1146,17 +1253,18 @@ class _LossTailReg(torch.autograd.Function):
             # enqueued, so that the encoder-side backward is not ordered behind it
             dev = out_c.device
             torch.autograd.Variable._execution_engine.queue_callback(lambda: join_side(dev))
-        return (dout, None, gloss if ctx.needs_input_grad[2] else None, dkl) + (None,) * 10
+        return (dout, None, gloss if ctx.needs_input_grad[2] else None, dkl) + (None,) * 11
 
 
 def loss_head(dec_out: torch.Tensor, x: torch.Tensor, enc: EncodedBatch, kind: str, ns: int, nmix: int = 10,
               eta: float = 0.0, gamma: float = 0.0, free_bits: float = 0.0, defer_join: bool = False,
-              inv_batch: float = 0.0, kl: Optional[torch.Tensor] = None):
+              inv_batch: float = 0.0, kl: Optional[torch.Tensor] = None, ext_sums: Optional[torch.Tensor] = None):
     """Decoder output + :func:`encode_head` result -> objective of MAE.loss.  Returns (loss [], stats [5], recon [B]) like
     :func:`loss_tail`; KL / m_d / S are in ``enc``.  ``defer_join``: see :func:`loss_tail`.  ``inv_batch`` (batch-sharded
     runs): 1 / global batch; ``enc.kl`` is then the all-gathered KL vector and the returned loss holds this rank's share of
     the reconstruction term plus the global regulariser.  ``kl`` [B] (differentiable): the caller's KL estimate, required
     when ``enc`` was made with ``with_kl=False``; it enters the free-bits clamp and receives its gradient from this node.
+    ``ext_sums`` (sharded runs with such a KL): device float[2] = (recon, KL) sums of the OTHER ranks, added before the means.
     Reference: mae.py:100-140 with the two reconstruct_error heads."""
     if kind not in ("dmol", "bernoulli"):
         raise ValueError("kind must be 'dmol' or 'bernoulli'")
@@ -1165,7 +1273,7 @@ def loss_head(dec_out: torch.Tensor, x: torch.Tensor, enc: EncodedBatch, kind: s
     if (kl is None) == (enc.kl is None):
         raise RuntimeError("loss_head: pass kl exactly when encode_head was called with with_kl=False")
     return _LossTailReg.apply(dec_out, x, enc.reg, enc.kl if kl is None else kl, enc.m_d, enc.s, kind, int(ns), int(nmix),
-                              float(eta), float(gamma), float(free_bits), bool(defer_join), float(inv_batch))
+                              float(eta), float(gamma), float(free_bits), bool(defer_join), float(inv_batch), ext_sums)
 
 
 def assemble_loss(err: torch.Tensor, kl: torch.Tensor, m_d: Optional[torch.Tensor], s: Optional[torch.Tensor],

@@ -121,7 +121,8 @@ class OracleEngine2(OracleEngine):
             dmu, dlv = dmu + g_reg * grads[0], dlv + g_reg * grads[1]
         return dmu, dlv
 
-    def loss_head(self, dec_out, x, enc, kind, ns, nmix, eta, gamma, free_bits, defer_join=False, inv_batch=0.0):
+    def loss_head(self, dec_out, x, enc, kind, ns, nmix, eta, gamma, free_bits, defer_join=False, inv_batch=0.0, kl=None,
+                  ext_sums=None):
         err = self.dmol_recon_error(dec_out, x, ns, nmix) if kind == "dmol" else self.bernoulli_recon_error(dec_out, x)
         recon = err.mean(dim=1)
         mean_rec = recon.sum() * inv_batch
