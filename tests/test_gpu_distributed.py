@@ -138,6 +138,9 @@ def _model_worker(rank, world, port, flows, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
+    # fp32 conv stacks: TF32 convolutions differ at 1e-3 between batch splits, which would hide what is being tested
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     try:
         from mae_b200 import distributed as D, synth
@@ -205,6 +208,6 @@ def test_sharded_model_gradients_all_reduced(tmp_path, world, flows):
         check_close(res[r]["recon"], ref["recon"][sl].double(), rel=1e-5, what="rank %d recon" % r)
         assert set(res[r]["grads"]) == set(ref["grads"])
         for n, gref in ref["grads"].items():
-            # fp32 conv stacks with different batch splits: cuDNN picks different algorithms / summation orders
-            worst = max(worst, check_close(res[r]["grads"][n], gref.double(), rel=2e-4, what="rank %d grad %s" % (r, n)))
+            # fp32 conv stacks with different batch splits: cuDNN may pick different algorithms / summation orders
+            worst = max(worst, check_close(res[r]["grads"][n], gref.double(), rel=5e-5, what="rank %d grad %s" % (r, n)))
     print("sharded MAE.loss world=%d flows=%s: worst parameter-gradient rel err %.1e" % (world, flows, worst))
