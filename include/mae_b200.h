@@ -299,6 +299,26 @@ int mae_allgather_rows(const float* local, int64_t n_floats, void* const* peer_b
                        int64_t slot_floats, float* out, mae_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Multi-GPU, training batches: the exchange of the packed rows AND the regulariser over the global batch (forward, and
+ * backward for this rank's rows) in ONE cluster launch per rank (csrc/mpd_rows_fused.cu).  Supported shapes:
+ * 2 <= world <= 8, b_loc <= 64, D <= 64, world * b_loc <= 512 (mae_kl_mpd_rows_fused_supported).
+ *   local_rows   this rank's packed rows [b_loc][2 D] = (mu | logvar), 16-byte aligned
+ *   peer_buffers DEVICE array of `world` pointers to communication buffers of mae_rows_comm_bytes(world, slot_floats)
+ *                bytes (mae_comm_alloc, opened through IPC like the gather's); slot_floats >= b_loc * 2 D, multiple of 4
+ *   outputs      m_d [D], S [1], kl_all [world * b_loc] (analytic KL of every global row, nullable), reg [1] (nullable),
+ *                dmu / dlogvar [b_loc][D] = d reg / d(mu, logvar) of the own rows (both NULL: forward only)
+ *   scratch      mae_rows_scratch_bytes() bytes of device memory owned by the caller (no initialisation needed)
+ * Same timeout behaviour as mae_allgather_rows: the sticky error flag (mae_comm_error) and NaN outputs.
+ * ---------------------------------------------------------------------------------------------- */
+int64_t mae_rows_comm_bytes(int64_t world, int64_t slot_floats);
+int64_t mae_rows_scratch_bytes(void);
+int mae_kl_mpd_rows_fused_supported(int64_t world, int64_t b_loc, int64_t D);
+int mae_kl_mpd_rows_fused(const float* local_rows, void* const* peer_buffers, int64_t rank, int64_t world,
+                          int64_t slot_floats, int64_t b_loc, int64_t D, float eta, float gamma, float free_bits,
+                          float kl_weight, float* m_d, float* S, float* kl_all, float* reg, float* dmu, float* dlogvar,
+                          void* scratch, int64_t scratch_bytes, mae_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Pipe-peak micro-benchmarks (measurement support, SURVEY.md §7 / §8d: the FP32-FFMA and SFU peaks that the MPD and
  * DMOL rooflines are quoted against are measured on the box, not assumed).  Register-only loops; the caller times
  * the launch with CUDA events.  *ops_out (host pointer, nullable) receives the lane-level instruction count of the

@@ -47,6 +47,7 @@ SIGNATURES = {
     "mae_comm_close_handle": [_P],
     "mae_comm_error": [_P, _P],
     "mae_allgather_rows": [_P, _I64, _P, _I64, _I64, _I64, _P, _P],
+    "mae_kl_mpd_rows_fused": [_P, _P, _I64, _I64, _I64, _I64, _I64, _F, _F, _F, _F, _P, _P, _P, _P, _P, _P, _P, _I64, _P],
     "mae_microbench_ffma": [_I64, _I64, _P, _P, _P],
     "mae_microbench_mufu": [_I, _I64, _I64, _P, _P, _P],
 }
@@ -61,6 +62,9 @@ PLAIN = {
     "mae_dmol_workspace_bytes": (c_int64, [_I64, _I64]),
     "mae_iw_nll_workspace_bytes": (c_int64, [_I64, _I64]),
     "mae_comm_buffer_bytes": (c_int64, [_I64, _I64]),
+    "mae_rows_comm_bytes": (c_int64, [_I64, _I64]),
+    "mae_rows_scratch_bytes": (c_int64, []),
+    "mae_kl_mpd_rows_fused_supported": (c_int, [_I64, _I64, _I64]),
     "mae_dmol_err_chunks": (c_int64, [_I64, _I64, _I64, _I64]),
 }
 ALL_SYMBOLS = sorted(list(SIGNATURES) + list(PLAIN))

@@ -347,170 +347,6 @@ dmol_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ x, cons
     }
 }
 
-// --------------------------------------------------------- persistent fused forward+backward (training batches)
-// Same arithmetic and work split as dmol_bwd_kernel<NMIX, HW, 5, true> (a task = 32 consecutive pixels of one sample, served
-// by SPLIT warps with kK components each), but the CTAs are PERSISTENT: gridDim.x = MINB x #SM CTAs walk the task list with
-// stride gridDim.x, and the 10*kK parameters (+ 3 sub-pixels) a thread needs for its NEXT task are fetched with cp.async
-// (LDGSTS) into a private shared-memory slot while the current task is evaluated.  The one-shot kernel runs its resident
-// CTAs through load -> evaluate -> merge -> store nearly in lockstep (ncu: 64 % issue-active, load latency exposed at
-// the head of every CTA); here the load phase of task t+1 hides behind the ~900 instructions of task t, and the grid is
-// sized so that every CTA gets the same number of tasks (C3: 2048 tasks / 1036 CTAs at 7 per SM = 2 rounds, instead of
-// 2.3 waves of one-shot CTAs).  Shared memory per CTA: 2 stages x (10*kK [+3]) x threads floats + two merge buffers.
-__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned int)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
-                 : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-
-template <int NMIX, int SPLIT, bool XSTAGE>
-struct PersistGeo {
-    using G = Geo<NMIX, SPLIT>;
-    static constexpr int kK = G::kK;
-    static constexpr int kThreadsCta = 32 * SPLIT;              // one pixel group per CTA
-    static constexpr int kVals = 10 * kK + (XSTAGE ? 3 : 0);    // staged floats per thread per task
-    static constexpr size_t kStageFloats = (size_t)kVals * kThreadsCta;
-    static constexpr size_t kSmemBytes = 2 * kStageFloats * sizeof(float);
-};
-
-template <int NMIX, int HW, int SPLIT, int MINB, bool XSTAGE>
-__global__ void __launch_bounds__(32 * SPLIT, MINB)
-dmol_fb_persist_kernel(const float* __restrict__ raw, const float* __restrict__ x, float g_mul, int ns, float* __restrict__ draw,
-                       int chunks, float* __restrict__ partial, int ntasks) {
-    using P = PersistGeo<NMIX, SPLIT, XSTAGE>;
-    constexpr int K = P::kK;
-    constexpr int NT = P::kThreadsCta;
-    static_assert(NMIX % SPLIT == 0, "persistent kernel: SPLIT must divide the number of components");
-    extern __shared__ __align__(16) float stage[];               // [2][kVals][NT]
-    __shared__ float ms_mt[2][SPLIT][32], ms_st[2][SPLIT][32], ms_ml[2][SPLIT][32], ms_sl[2][SPLIT][32];
-    pdl_launch_dependents();
-    pdl_wait();
-    const int tid = threadIdx.x, lane = tid & 31, part = tid >> 5;
-
-    auto prefetch = [&](int task, int buf) {
-        const int n = task / chunks, chunk = task - n * chunks;
-        const int pix = chunk * 32 + lane;
-        const float* pbase = raw + (int64_t)n * (10 * NMIX * HW) + pix;
-        const float* lg = pbase + part * HW;
-        const float* pr = pbase + 3 * part * HW;
-        float* dst = stage + (size_t)buf * P::kStageFloats + tid;
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            cp_async4(dst + (10 * k) * NT, lg + k * SPLIT * HW);
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const float* q = pr + (3 * k * SPLIT + c) * HW;
-                cp_async4(dst + (10 * k + 1 + c) * NT, q + NMIX * HW);
-                cp_async4(dst + (10 * k + 4 + c) * NT, q + 4 * NMIX * HW);
-                cp_async4(dst + (10 * k + 7 + c) * NT, q + 7 * NMIX * HW);
-            }
-        }
-        if (XSTAGE) {
-            const int b = n / ns;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) cp_async4(dst + (10 * K + c) * NT, x + ((int64_t)b * 3 + c) * HW + pix);
-        }
-        cp_async_commit();
-    };
-
-    int task = blockIdx.x;
-    if (task < ntasks) prefetch(task, 0);
-    int buf = 0;
-    for (; task < ntasks; task += gridDim.x, buf ^= 1) {
-        const int next = task + gridDim.x;
-        const int n = task / chunks, chunk = task - n * chunks;
-        const int pix = chunk * 32 + lane;
-        float xs[3];
-        if (!XSTAGE) {
-            const int b = n / ns;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) xs[c] = __ldg(x + ((int64_t)b * 3 + c) * HW + pix);
-        }
-        if (next < ntasks) {
-            prefetch(next, buf ^ 1);
-            cp_async_wait<1>();      // everything but the newest group (the next task's) has landed
-        } else {
-            cp_async_wait<0>();
-        }
-        // a thread reads back only the slots it copied itself: no barrier needed after the wait
-        const float* src = stage + (size_t)buf * P::kStageFloats + tid;
-        Comp cp[K];
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            cp[k].logit = src[(10 * k) * NT];
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                cp[k].mu[c] = src[(10 * k + 1 + c) * NT];
-                cp[k].rho[c] = src[(10 * k + 4 + c) * NT];
-                cp[k].kap[c] = src[(10 * k + 7 + c) * NT];
-            }
-        }
-        if (XSTAGE) {
-#pragma unroll
-            for (int c = 0; c < 3; ++c) xs[c] = src[(10 * K + c) * NT];
-        }
-        float tl[K], lg[K], gmu[K][3], grho[K][3], gkap[K][3];
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            lg[k] = cp[k].logit;
-            tl[k] = hm::dmol_component<true>(cp[k].mu, cp[k].rho, cp[k].kap, xs, gmu[k], grho[k], gkap[k]) + cp[k].logit;
-        }
-        float mt, st, ml, sl;
-        lse_local<K>(tl, K, mt, st);
-        lse_local<K>(lg, K, ml, sl);
-        ms_mt[buf][part][lane] = mt;
-        ms_st[buf][part][lane] = st;
-        ms_ml[buf][part][lane] = ml;
-        ms_sl[buf][part][lane] = sl;
-        __syncthreads();             // the only barrier of a task (the merge buffers alternate with the stage parity)
-        const float zt = lse_merge<SPLIT>(ms_mt[buf], ms_st[buf], lane);
-        const float zl = lse_merge<SPLIT>(ms_ml[buf], ms_sl[buf], lane);
-        float* ob = draw + (int64_t)n * (10 * NMIX * HW) + pix;
-        float* olg = ob + part * HW;
-        float* opr = ob + 3 * part * HW;
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const float wgt = hm::fast_ex2(hm::kLog2e * (tl[k] - zt));  // responsibility of the component
-            const float pri = hm::fast_ex2(hm::kLog2e * (lg[k] - zl));  // softmax(logits)
-            const float a = -g_mul * wgt;                               // d err / d T_m
-            stg_stream(olg + k * SPLIT * HW, g_mul * (pri - wgt));
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                float* q = opr + (3 * k * SPLIT + c) * HW;
-                stg_stream(q + NMIX * HW, a * gmu[k][c]);
-                stg_stream(q + 4 * NMIX * HW, a * grho[k][c]);
-                stg_stream(q + 7 * NMIX * HW, a * gkap[k][c]);
-            }
-        }
-        if (part == 0) {             // per-task partial sum of err (32 pixels): one warp, no block barrier
-            const float v = warp_sum(zl - zt);
-            if (lane == 0) partial[(int64_t)n * chunks + chunk] = v;
-        }
-    }
-}
-
-template <int HW, int MINB, bool XSTAGE>
-int launch_fb_persist(const float* raw, const float* x, float gm, int64_t N, int ns, float* draw, float* partial, cudaStream_t s) {
-    using P = PersistGeo<10, 5, XSTAGE>;
-    const int chunks = HW / 32;
-    const int64_t ntasks = N * chunks;
-    if (ntasks >= (1ll << 31)) return MAE_ERR_SHAPE;
-    static bool attr_set = false;
-    auto kern = dmol_fb_persist_kernel<10, HW, 5, MINB, XSTAGE>;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P::kSmemBytes);
-        if (e != cudaSuccess) return (int)e;
-        attr_set = true;
-    }
-    int64_t grid = (int64_t)sm_count() * MINB;
-    if (grid > ntasks) grid = ntasks;
-    launch_pdl(kern, dim3((unsigned)grid), dim3(P::kThreadsCta), P::kSmemBytes, s, raw, x, gm, ns, draw, chunks, partial, (int)ntasks);
-    return launch_status();
-}
-
 // ------------------------------------------------------------------- vectorised forward for large launches
 // IW-NLL evaluation shape (>= 512 Ki pixels per launch): one thread owns 4 consecutive pixels and reads every
 // channel plane with 16-byte loads, so a warp request is 512 contiguous bytes and a CTA sweeps 4 KB of each plane
@@ -902,9 +738,6 @@ int launch_fwd(const float* raw, const float* x, int64_t N, int ns, float* err, 
 
 // tuning knobs for profiling runs (read once): MAE_DMOL_SPLIT in {1,2,5} overrides pick_split,
 // MAE_DMOL_S1_OCC in {2,3,4} selects the register budget (min CTAs/SM) of the one-thread-per-pixel forward
-#ifndef MAE_DMOL_PERSIST_DEFAULT
-#define MAE_DMOL_PERSIST_DEFAULT 0
-#endif
 int env_int(const char* name, int dflt) {
     const char* v = getenv(name);
     return v ? atoi(v) : dflt;
@@ -1042,19 +875,6 @@ extern "C" int mae_dmol_fwd_bwd(const float* raw, const float* x, float g_mul, i
     const int64_t N = B * ns;
     cudaStream_t s = as_stream(stream);
     const int split = pick_split(N * HW);
-    // persistent, prefetching variant (split == 5 shapes): MAE_DMOL_PERSIST = CTAs per SM (6, 7; 0 = one-shot kernel),
-    // MAE_DMOL_XSTAGE = 1 stages the sub-pixels through shared memory as well (6 per SM only: shared-memory budget)
-    static const int persist = env_int("MAE_DMOL_PERSIST", MAE_DMOL_PERSIST_DEFAULT);
-    static const int xstage = env_int("MAE_DMOL_XSTAGE", 0);
-    if (split == 5 && persist > 0) {
-        if (HW == 1024) {
-            if (persist >= 7) return launch_fb_persist<1024, 7, false>(raw, x, g_mul, N, (int)ns, draw, err_partial, s);
-            if (persist == 5) return launch_fb_persist<1024, 5, false>(raw, x, g_mul, N, (int)ns, draw, err_partial, s);
-            return xstage ? launch_fb_persist<1024, 6, true>(raw, x, g_mul, N, (int)ns, draw, err_partial, s)
-                          : launch_fb_persist<1024, 6, false>(raw, x, g_mul, N, (int)ns, draw, err_partial, s);
-        }
-        return launch_fb_persist<4096, 6, false>(raw, x, g_mul, N, (int)ns, draw, err_partial, s);
-    }
     // err == nullptr selects "partials only": err_partial[n][chunk], no tickets, no cross-CTA dependency
     return HW == 1024 ? dispatch_bwd<1024>(split, raw, x, nullptr, 0, g_mul, N, (int)ns, draw, s, nullptr, err_partial, nullptr, true)
                       : dispatch_bwd<4096>(split, raw, x, nullptr, 0, g_mul, N, (int)ns, draw, s, nullptr, err_partial, nullptr, true);

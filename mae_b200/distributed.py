@@ -31,6 +31,7 @@ SMALL_GLOBAL_BATCH = 2048   # <= : every rank evaluates the whole MPD forward re
 # Rows per rank up to this many floats (1 MB) take the one-kernel NVLink push gather (pure latency regime); larger panels
 # (C5: up to 16 MB per rank) are bandwidth-bound and go through the library all-gather.
 PEER_SLOT_FLOATS = 1 << 18
+ROWS_SLOT_FLOATS = 64 * 128      # one-launch sharded regulariser: b_loc <= 64 rows of 2 D <= 128 floats
 
 
 def _packed_parent(mu, logvar, b_loc, d):
@@ -156,13 +157,25 @@ class _ShardedEncodeHead(torch.autograd.Function):
     the regulariser, and no collective, is left on it."""
 
     @staticmethod
-    def forward(ctx, mu, logvar, eps, head, eta, gamma, free_bits, with_kl=True):
+    def forward(ctx, mu, logvar, eps, head, eta, gamma, free_bits, with_kl=True, holder=None):
         ctx.set_materialize_grads(False)
         eng = head.engine
         want_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
         world = head.world
+        z_side = holder is not None and holder.get("z_on_side", False)
 
         def chain():
+            b_loc0, d0 = mu.size(0), mu[0].numel()
+            if head._rows_cluster_ok(b_loc0, d0, mu):
+                # training batches: exchange + regulariser of the global batch (forward, and backward of the own rows) in
+                # ONE cluster launch; the landed rows are consumed in place, nothing of the B x B work is replicated
+                packed = _packed_parent(mu, logvar, b_loc0, d0)
+                if packed is None:
+                    packed = torch.cat([mu.reshape(b_loc0, d0), logvar.reshape(b_loc0, d0)], dim=1)
+                packed = packed.detach()
+                m_d, s, kl_all, grads, reg = eng.reg_rows_cluster(packed, head.peer_rows, eta, gamma, free_bits,
+                                                                  None if with_kl else 0.0, want_grad, head._rows_scratch)
+                return m_d, s, kl_all, packed, grads, reg
             if hasattr(eng, "reg_rows_fused"):
                 # small global batch: gather, then ONE cluster launch for the whole regulariser of the gathered rows
                 b_loc, d = mu.size(0), mu[0].numel()
@@ -192,14 +205,22 @@ class _ShardedEncodeHead(torch.autograd.Function):
             cs, ss = torch.cuda.current_stream(dev), eng._side_stream(dev)
             ss.wait_stream(cs)
             prev = eng._pending_join.pop(idx, None)
+            z = None
             with torch.cuda.stream(ss):
                 m_d, s, kl_all, gathered, grads, reg = chain()
+                if z_side:      # see ops.encode_head(z_on_side=True): joined by loss_head behind the likelihood kernel
+                    z, saved = eng.reparam_fwd(mu, logvar, eps)
+                    z.record_stream(cs)
                 ev = torch.cuda.Event()
                 ev.record(ss)
-            eng._pending_join[idx] = (ev, (prev, m_d, s, kl_all, gathered, grads, reg, mu, logvar))
+                if z_side:
+                    holder["z_event"] = ev
+            eng._pending_join[idx] = (ev, (prev, m_d, s, kl_all, gathered, grads, reg, mu, logvar, z))
+            if z is None:
+                z, saved = eng.reparam_fwd(mu, logvar, eps)
         else:
             m_d, s, kl_all, gathered, grads, reg = chain()
-        z, saved = eng.reparam_fwd(mu, logvar, eps)
+            z, saved = eng.reparam_fwd(mu, logvar, eps)
         ctx.saved, ctx.grads, ctx.event, ctx.eng = saved, grads, ev, eng
         ctx.shapes = (mu.shape, logvar.shape)
         ctx.mark_non_differentiable(kl_all, m_d, s)
@@ -208,13 +229,13 @@ class _ShardedEncodeHead(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gz, g_reg, *_unused):
         if gz is None and g_reg is None:
-            return (None,) * 8
+            return (None,) * 9
         if g_reg is not None and ctx.grads is None:
             raise RuntimeError("sharded encode head: reg has a gradient but mu / logvar did not require one in the forward")
         if ctx.event is not None:
             torch.cuda.current_stream(ctx.saved[0].device).wait_event(ctx.event)
         dmu, dlv = ctx.eng.reparam_reg_bwd(ctx.saved, gz, ctx.grads, g_reg)
-        return dmu.view(ctx.shapes[0]), dlv.view(ctx.shapes[1]), None, None, None, None, None, None
+        return dmu.view(ctx.shapes[0]), dlv.view(ctx.shapes[1]), None, None, None, None, None, None, None
 
 
 class ShardedHead:
@@ -233,6 +254,10 @@ class ShardedHead:
         self.defer_join = defer_join
         self.two_node = True                             # regulariser backward in the forward pass (engine permitting)
         self.peer = None                                 # NVLink peer-memory gather (created collectively, CUDA only)
+        self.peer_rows = None                            # buffers of the one-launch exchange + regulariser kernel
+        self._rows_failed = False
+        self._rows_scratch = None
+        self.rows_cluster = True                         # use mae_kl_mpd_rows_fused where the shape fits
         self.use_p2p = use_p2p
         self.check_every = check_every                   # poll the gather's error flag every N eager steps (0: never)
         self.world = dist.get_world_size(group)
@@ -243,11 +268,33 @@ class ShardedHead:
             # The switch is process-wide in the library; close() restores the previous setting.
             self._pdl_before = self.engine.set_pdl(False)
 
+    def _rows_cluster_ok(self, b_loc: int, d: int, like: torch.Tensor) -> bool:
+        """Whether this step can take the one-launch exchange + regulariser kernel (decided identically on every rank: it
+        depends on shapes, on the collectively created buffers and on the ``rows_cluster`` switch only)."""
+        eng = self.engine
+        if not (self.rows_cluster and self.use_p2p and like.is_cuda and self.world > 1 and hasattr(eng, "reg_rows_cluster")):
+            return False
+        if (b_loc * 2 * d) % 4 != 0 or b_loc * 2 * d > ROWS_SLOT_FLOATS or not eng.rows_cluster_supported(self.world, b_loc, d, like.device):
+            return False
+        if self.peer_rows is None and not self._rows_failed:
+            from .p2p import PeerGather
+            self.peer_rows = PeerGather.create(self.group, ROWS_SLOT_FLOATS, like.device, layout="rows")
+            if self.peer_rows is None:
+                self._rows_failed = True
+            else:
+                import ctypes
+                from . import _lib
+                self._rows_scratch = torch.empty(int(_lib.load().mae_rows_scratch_bytes()), dtype=torch.uint8, device=like.device)
+        return self.peer_rows is not None
+
     def close(self) -> None:
         """Release the peer buffers and restore the process-wide PDL setting this head changed."""
         if self.peer is not None:
             self.peer.close()
             self.peer = None
+        if self.peer_rows is not None:
+            self.peer_rows.close()
+            self.peer_rows = None
         if self._pdl_before is not None:
             self.engine.set_pdl(self._pdl_before)
             self._pdl_before = None
@@ -256,6 +303,8 @@ class ShardedHead:
         """Raise if the peer-memory gather ever timed out (its rows were NaN-filled).  Synchronises with the device."""
         if self.peer is not None:
             self.peer.check()
+        if self.peer_rows is not None:
+            self.peer_rows.check()
 
     def _gather(self, packed: torch.Tensor) -> torch.Tensor:
         """All-gather of the packed rows: one push-kernel over NVLink peer memory when available (tens of KB, pure
@@ -297,13 +346,15 @@ class ShardedHead:
         ext = torch.stack([kl_others.new_zeros(()), kl_others]).to(kl.dtype)
         return eng.assemble_loss(err, kl, m_d, s, eta, gamma, free_bits, 1.0 / b_glob, ext)
 
-    def encode_head(self, mu, logvar, eps, eta=0.0, gamma=0.0, free_bits=0.0, with_kl: bool = True):
+    def encode_head(self, mu, logvar, eps, eta=0.0, gamma=0.0, free_bits=0.0, with_kl: bool = True, z_on_side: bool = False):
         """Sharded counterpart of ``ops.encode_head``: -> (z_loc, EncodedBatch).  ``enc.kl`` is the all-gathered analytic KL
         vector [B_global] (None when ``with_kl`` is False: encoders with flows pass their own KL to ``loss_head``)."""
         eng = self.engine
+        holder = {"z_on_side": bool(z_on_side) and self.overlap}
         z, reg, kl_all, m_d, s = _ShardedEncodeHead.apply(mu, logvar, eps, self, float(eta), float(gamma), float(free_bits),
-                                                          bool(with_kl))
+                                                          bool(with_kl), holder)
         enc = eng.EncodedBatch(reg, kl_all if with_kl else None, m_d, s, (float(eta), float(gamma), float(free_bits)))
+        enc.z_event = holder.get("z_event")
         return z, enc
 
     def loss_head(self, dec_out, x, enc, kind, ns, nmix=10, eta=0.0, gamma=0.0, free_bits=0.0, kl=None):
@@ -323,7 +374,7 @@ class ShardedHead:
 
     def _two_node(self, mu, logvar, eps, dec_out, x, kind, nmix, eta, gamma, free_bits):
         """encode head (regulariser forward + backward behind the all-gather, side stream) + loss head."""
-        z, enc = self.encode_head(mu, logvar, eps, eta, gamma, free_bits)
+        z, enc = self.encode_head(mu, logvar, eps, eta, gamma, free_bits, z_on_side=True)   # dec_out is an input here
         b_loc = x.size(0)
         loss, stats, recon = self.loss_head(dec_out, x, enc, kind, eps.size(1), nmix, eta, gamma, free_bits)
         row0 = self.rank * b_loc

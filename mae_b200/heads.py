@@ -25,7 +25,8 @@ def loss_head_binary(mu, logvar, eps, probs, x, eta=0.0, gamma=0.0, free_bits=0.
     """C1/C2: reparam + analytic KL, MPD, Bernoulli likelihood, assembly.  Returns (loss, recon, KL, stats, z).
     ``defer_join``: see ops.loss_tail (outputs valid after backward() / ops.join_side())."""
     if _one_node(mu):
-        z, enc = ops.encode_head(mu, logvar, eps, eta, gamma, free_bits)   # regulariser on the side stream
+        # regulariser AND z on the side stream: the likelihood kernel below reads the given decoder output, not z
+        z, enc = ops.encode_head(mu, logvar, eps, eta, gamma, free_bits, z_on_side=True)
         loss, stats, recon = ops.loss_head(probs, x, enc, "bernoulli", eps.size(1), 0, eta, gamma, free_bits,
                                            defer_join=defer_join)
         return loss, recon, enc.kl, stats, z
@@ -40,7 +41,8 @@ def loss_head_color(mu, logvar, eps, raw, x, nmix=10, eta=0.0, gamma=0.0, free_b
     """C3: reparam + analytic KL, MPD, discretized-logistic-mixture likelihood, assembly.
     ``defer_join``: see ops.loss_tail (outputs valid after backward() / ops.join_side())."""
     if _one_node(mu):
-        z, enc = ops.encode_head(mu, logvar, eps, eta, gamma, free_bits)   # regulariser on the side stream
+        # regulariser AND z on the side stream: the likelihood kernel below reads the given decoder output, not z
+        z, enc = ops.encode_head(mu, logvar, eps, eta, gamma, free_bits, z_on_side=True)
         loss, stats, recon = ops.loss_head(raw, x, enc, "dmol", eps.size(1), nmix, eta, gamma, free_bits,
                                            defer_join=defer_join)
         return loss, recon, enc.kl, stats, z

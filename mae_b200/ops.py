@@ -16,7 +16,7 @@ from . import _lib
 
 __all__ = [
     "reparam_kl", "mpd", "mpd_forward_only", "bernoulli_recon_error", "dmol_recon_error", "log_prob_prior",
-    "log_prob_posterior", "iw_nll", "assemble_loss", "kl_mpd", "loss_tail", "loss_head", "encode_head", "kl_mpd_reg_fused", "kl_mpd_reg", "mpd_rows_loss_backward", "reg_rows_fused", "reparam_fwd",
+    "log_prob_posterior", "iw_nll", "assemble_loss", "kl_mpd", "loss_tail", "loss_head", "encode_head", "kl_mpd_reg_fused", "kl_mpd_reg", "mpd_rows_loss_backward", "reg_rows_fused", "reg_rows_cluster", "rows_cluster_supported", "reparam_fwd",
     "reparam_reg_bwd", "fused_reg_supported", "set_pdl", "set_unit_loss_grad", "join_side", "launch_count", "reset_launch_count",
 ]
 
@@ -514,6 +514,52 @@ def reg_rows_fused(mu_all: torch.Tensor, logvar_all: torch.Tensor, row0: int, nr
     kl_all, m_d, s_, reg, grads, _ = kl_mpd_reg_fused(mu_all, logvar_all, eta, gamma, free_bits, kl_weight, want_grad)
     own = grads[:, row0:row0 + nrows] if grads is not None else None      # [2, nrows, D]: rows are contiguous
     return m_d, s_, kl_all, own, reg
+
+
+_rows_ok: Dict[Tuple[int, int, int, int], bool] = {}
+
+
+def rows_cluster_supported(world: int, b_loc: int, d: int, device: torch.device) -> bool:
+    """True when (world, local batch, D) fits the one-launch sharded regulariser (mae_kl_mpd_rows_fused)."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    key = (idx, int(world), int(b_loc), int(d))
+    ok = _rows_ok.get(key)
+    if ok is None:
+        with torch.cuda.device(idx):
+            ok = bool(_lib_().mae_kl_mpd_rows_fused_supported(int(world), int(b_loc), int(d)))
+        _rows_ok[key] = ok
+    return ok
+
+
+@_guarded
+def reg_rows_cluster(packed: torch.Tensor, peer, eta: float, gamma: float, free_bits: float,
+                     kl_weight: Optional[float] = None, want_grad: bool = True, scratch: Optional[torch.Tensor] = None):
+    """Batch-sharded runs: exchange of the packed rows over NVLink peer memory AND the regulariser of the global batch,
+    forward and backward for the own rows, in ONE cluster launch (csrc/mpd_rows_fused.cu).  ``packed`` [b_loc, 2D] =
+    (mu | logvar) of this rank, contiguous; ``peer`` a ``p2p.PeerGather`` created with ``layout="rows"``.
+    -> (m_d [D], S [], kl_all [world*b_loc], grads [2,b_loc,D] or None, reg [])."""
+    _req_cuda(packed)
+    b_loc, w2 = packed.shape
+    d = w2 // 2
+    dev = packed.device
+    world, rank = peer.world, peer.rank
+    kw = 1.0 / float(world * b_loc) if kl_weight is None else float(kl_weight)
+    lib = _lib_()
+    if scratch is None:
+        scratch = torch.empty(int(lib.mae_rows_scratch_bytes()), dtype=torch.uint8, device=dev)
+    m_d = torch.empty(d, device=dev, dtype=torch.float32)
+    s_ = torch.empty((), device=dev, dtype=torch.float32)
+    reg = torch.empty((), device=dev, dtype=torch.float32)
+    kl_all = torch.empty(world * b_loc, device=dev, dtype=torch.float32)
+    grads = torch.empty(2, b_loc, d, device=dev, dtype=torch.float32) if want_grad else None
+    _lib.check(lib.mae_kl_mpd_rows_fused(packed.data_ptr(), peer.peer_table.data_ptr(), rank, world, peer.slot_floats, b_loc, d,
+                                         float(eta), float(gamma), float(free_bits), kw, m_d.data_ptr(), s_.data_ptr(),
+                                         kl_all.data_ptr(), reg.data_ptr(), grads[0].data_ptr() if want_grad else None,
+                                         grads[1].data_ptr() if want_grad else None, scratch.data_ptr(), scratch.numel(),
+                                         _stream()), "mae_kl_mpd_rows_fused")
+    _count()
+    peer.calls += 1
+    return m_d, s_, kl_all, grads, reg
 
 
 @_guarded
@@ -1103,7 +1149,7 @@ class _EncodeHead(torch.autograd.Function):
 
     @staticmethod
     @_guarded
-    def forward(ctx, mu, logvar, eps, eta, gamma, free_bits, with_kl):
+    def forward(ctx, mu, logvar, eps, eta, gamma, free_bits, with_kl, holder=None):
         ctx.set_materialize_grads(False)
         _req_cuda(mu, logvar, eps)
         dev = mu.device
@@ -1113,18 +1159,36 @@ class _EncodeHead(torch.autograd.Function):
         cs, ss = torch.cuda.current_stream(dev), _side_stream(dev)
         ss.wait_stream(cs)
         prev = _pending_join.pop(idx, None)
-        kl, m_d, s, reg, grads, (mu2, lv2) = kl_mpd_reg(mu, logvar, eta, gamma, free_bits, None if with_kl else 0.0, want_grad,
-                                                        launch_stream=ss)
-        ev = torch.cuda.Event()
-        ev.record(ss)
-        _pending_join[idx] = (ev, (prev, kl, m_d, s, reg, grads, mu2, lv2))
-        ms, ls = mu2.stride(0), lv2.stride(0)
+        mu2, ms = _rows(mu)
+        lv2, ls = _rows(logvar)
         d = mu2.size(1)
         eps_c = eps.contiguous()
         z = torch.empty_like(eps_c)
-        _lib.check(_lib_().mae_reparam_kl_fwd(mu2.data_ptr(), ms, lv2.data_ptr(), ls, eps_c.data_ptr(), b, ns, d,
-                                              z.data_ptr(), None, _stream()), "mae_reparam_kl_fwd")
-        _count()
+        z_side = holder is not None and holder.get("z_on_side", False)
+
+        def reparam():
+            _lib.check(_lib_().mae_reparam_kl_fwd(mu2.data_ptr(), ms, lv2.data_ptr(), ls, eps_c.data_ptr(), b, ns, d,
+                                                  z.data_ptr(), None, _stream()), "mae_reparam_kl_fwd")
+            _count()
+
+        kl, m_d, s, reg, grads, _ = kl_mpd_reg(mu2, lv2, eta, gamma, free_bits, None if with_kl else 0.0, want_grad,
+                                               launch_stream=ss)
+        m_d = m_d.view(mu.shape[1:])
+        if z_side:
+            # the caller's next main-stream kernel does not consume z (heads.*: the decoder output is an input): z is
+            # produced on the side stream BEHIND the regulariser (whose cluster must be placed before the likelihood kernel
+            # fills the SMs: with the reparameterisation first the step measured 30.8 us instead of 28.6) and joined by
+            # loss_head after it has enqueued the likelihood kernel
+            with torch.cuda.stream(ss):
+                reparam()
+            holder["z_event"] = True
+        ev = torch.cuda.Event()
+        ev.record(ss)
+        if z_side:
+            holder["z_event"] = ev
+        _pending_join[idx] = (ev, (prev, kl, m_d, s, reg, grads, mu2, lv2, z, eps_c))
+        if not z_side:
+            reparam()
         ctx.save_for_backward(mu2, lv2, eps_c)
         ctx.reg_grads = grads
         ctx.reg_event = ev
@@ -1136,7 +1200,7 @@ class _EncodeHead(torch.autograd.Function):
     @_guarded
     def backward(ctx, gz, g_reg, *_unused):
         if gz is None and g_reg is None:
-            return (None,) * 7
+            return (None,) * 8
         mu2, lv2, eps_c = ctx.saved_tensors
         ms, ls, b, ns, d, mu_shape, lv_shape = ctx.meta
         dev = mu2.device
@@ -1153,25 +1217,31 @@ class _EncodeHead(torch.autograd.Function):
                                                grads[1].data_ptr() if grads is not None else None, _ptr(g_reg), b, ns, d,
                                                dmu.data_ptr(), dlv.data_ptr(), 0, _stream()), "mae_reparam_reg_bwd")
         _count()
-        return dmu.view(mu_shape), dlv.view(lv_shape), None, None, None, None, None
+        return dmu.view(mu_shape), dlv.view(lv_shape), None, None, None, None, None, None
 
 
 class EncodedBatch:
     """What :func:`encode_head` hands to :func:`loss_head`: reg (the only differentiable entry), KL [B], m_d, S and the
     hyper-parameters they were computed with.  Valid on the main stream after :func:`join_side` (loss_head does it)."""
 
-    def __init__(self, reg, kl, m_d, s, params):
+    def __init__(self, reg, kl, m_d, s, params, z_event=None):
         self.reg, self.kl, self.m_d, self.s, self.params = reg, kl, m_d, s, params
+        self.z_event = z_event      # z was produced on the side stream: loss_head joins it behind the likelihood kernel
 
 
 def encode_head(mu: torch.Tensor, logvar: torch.Tensor, eps: torch.Tensor, eta: float = 0.0, gamma: float = 0.0,
-                free_bits: float = 0.0, with_kl: bool = True):
+                free_bits: float = 0.0, with_kl: bool = True, z_on_side: bool = False):
     """z [B,ns,*z] and the encoder-side regulariser of MAE.loss in one autograd node; -> (z, EncodedBatch).
     ``with_kl=False`` (encoders with flows: KL is a Monte-Carlo estimate computed by the caller, gaussian_encoder.py:220-225):
     reg holds the MPD terms only and :func:`loss_head` takes the KL through its ``kl`` argument.
+    ``z_on_side=True`` (only for callers whose next main-stream work does NOT consume z, i.e. ``heads.*`` where the decoder
+    output is an input): z is produced on the side stream too and becomes valid on the main stream when :func:`loss_head`
+    returns (or after :func:`join_side`).
     Reference: gaussian_encoder.py:56-62, :162-188, :219 and mae.py:132-139."""
-    z, reg, kl, m_d, s = _EncodeHead.apply(mu, logvar, eps, float(eta), float(gamma), float(free_bits), bool(with_kl))
-    return z, EncodedBatch(reg, kl if with_kl else None, m_d, s, (float(eta), float(gamma), float(free_bits)))
+    holder = {"z_on_side": bool(z_on_side)}
+    z, reg, kl, m_d, s = _EncodeHead.apply(mu, logvar, eps, float(eta), float(gamma), float(free_bits), bool(with_kl), holder)
+    return z, EncodedBatch(reg, kl if with_kl else None, m_d, s, (float(eta), float(gamma), float(free_bits)),
+                           holder.get("z_event"))
 
 
 class _LossTailReg(torch.autograd.Function):
@@ -1272,8 +1342,12 @@ def loss_head(dec_out: torch.Tensor, x: torch.Tensor, enc: EncodedBatch, kind: s
         raise RuntimeError("loss_head: encode_head was called with different eta / gamma / free_bits")
     if (kl is None) == (enc.kl is None):
         raise RuntimeError("loss_head: pass kl exactly when encode_head was called with with_kl=False")
-    return _LossTailReg.apply(dec_out, x, enc.reg, enc.kl if kl is None else kl, enc.m_d, enc.s, kind, int(ns), int(nmix),
-                              float(eta), float(gamma), float(free_bits), bool(defer_join), float(inv_batch), ext_sums)
+    out = _LossTailReg.apply(dec_out, x, enc.reg, enc.kl if kl is None else kl, enc.m_d, enc.s, kind, int(ns), int(nmix),
+                             float(eta), float(gamma), float(free_bits), bool(defer_join), float(inv_batch), ext_sums)
+    if enc.z_event is not None:      # z came from the side stream: valid on the main stream from here on
+        torch.cuda.current_stream(dec_out.device).wait_event(enc.z_event)
+        enc.z_event = None
+    return out
 
 
 def assemble_loss(err: torch.Tensor, kl: torch.Tensor, m_d: Optional[torch.Tensor], s: Optional[torch.Tensor],

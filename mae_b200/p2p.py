@@ -25,7 +25,7 @@ class PeerGather:
         raise RuntimeError("use PeerGather.create(group, slot_floats, device)")
 
     @classmethod
-    def create(cls, group, slot_floats: int, device: torch.device) -> Optional["PeerGather"]:
+    def create(cls, group, slot_floats: int, device: torch.device, layout: str = "gather") -> Optional["PeerGather"]:
         """Collective over ``group``.  Returns a ready object on EVERY rank, or None on every rank (with the reason in
         ``PeerGather.last_failure``) when any rank could not allocate / export / map the buffers."""
         self = object.__new__(cls)
@@ -43,7 +43,12 @@ class PeerGather:
         handle_raw = None
         with torch.cuda.device(device):
             try:
-                nbytes = int(lib.mae_comm_buffer_bytes(self.world, self.slot_floats))
+                # "gather": landing buffers of mae_allgather_rows; "rows": those of mae_kl_mpd_rows_fused (the exchange
+                # fused into the regulariser's cluster kernel: its own header, flags and partial-sum slots)
+                self.layout = layout
+                nbytes = int((lib.mae_rows_comm_bytes if layout == "rows" else lib.mae_comm_buffer_bytes)(self.world, self.slot_floats))
+                if nbytes <= 0:
+                    raise RuntimeError("unsupported world size / slot size for the %s buffers" % layout)
                 own = ctypes.c_void_p()
                 _lib.check(lib.mae_comm_alloc(nbytes, ctypes.byref(own)), "mae_comm_alloc")
                 self.own = own.value

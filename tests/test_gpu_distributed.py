@@ -4,8 +4,10 @@ loss / gradients must equal the single-GPU head evaluated on the concatenated ba
 Cases (world 2, 4 and 8; a case is skipped when the box has fewer GPUs):
   small      24 rows x D=32 per rank, 32x32 colour head; with SMALL_GLOBAL_BATCH patched to 16 it takes the row-block +
              fp64 all-reduce branch at a tiny size as well
-  c3         the benchmarked shape: 64 rows x D=64 per rank, DMOL 32x32 -> global batch 128 (one-launch cluster kernel) at
-             world 2, 256 / 512 (prepare -> tiles -> mae_mpd_loss_bwd with row0 != 0) at world 4 / 8
+  c3         the benchmarked shape: 64 rows x D=64 per rank, DMOL 32x32, global batch 128 / 256 / 512 at world 2 / 4 / 8:
+             rows_cluster=True  the one-launch exchange + regulariser kernel (mae_kl_mpd_rows_fused)
+             rows_cluster=False peer gather, then the cluster kernel (world 2) or prepare -> tiles -> mae_mpd_loss_bwd
+                                with row0 != 0 (world 4 / 8)
   rowblock   global batch > 2048 (binary head, D=64): the row-blocked tile pass + fp64 all-reduce path for real, no patching
   model      sharded ``MAE.loss`` of a full model (conv stacks in PyTorch) + ``all_reduce_gradients``: parameter
              gradients must equal the single-process gradients on the whole batch
@@ -50,7 +52,7 @@ def _case_inputs(case, world):
     return kind, b_loc, d, (mu, lv, eps, dec, x)
 
 
-def _worker(rank, world, port, case, small_limit, out):
+def _worker(rank, world, port, case, small_limit, rows_cluster, out):
     sys.path.insert(0, ROOT)
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
@@ -62,6 +64,7 @@ def _worker(rank, world, port, case, small_limit, out):
         if small_limit is not None:
             D.SMALL_GLOBAL_BATCH = small_limit
         head = D.ShardedHead(check_equal_batches=True)
+        head.rows_cluster = rows_cluster      # False: peer gather + cluster / general kernel chain (row0 != 0)
         kind, b_loc, d, (mu_g, lv_g, eps_g, dec_g, x_g) = _case_inputs(case, world)
         sl = slice(rank * b_loc, (rank + 1) * b_loc)
         mu, lv = mu_g[sl].to(dev).requires_grad_(), lv_g[sl].to(dev).requires_grad_()
@@ -74,7 +77,9 @@ def _worker(rank, world, port, case, small_limit, out):
             loss, recon, kl, stats, z = fn(mu, lv, eps_g[sl].to(dev), dec, x_g[sl].to(dev), *args)
             loss.backward()
             g_loss = head.global_loss(loss, stats)
-            assert head.peer is not None, "peer-memory gather was not used"
+            assert (head.peer is not None) or (head.peer_rows is not None), "peer-memory exchange was not used"
+            if rows_cluster and case != "rowblock":
+                assert head.peer_rows is not None and head.peer is None, "the one-launch exchange + regulariser kernel was not used"
             head.check()
             res["rep%d" % rep] = {"loss": g_loss.cpu(), "dmu": mu.grad.cpu(), "dlv": lv.grad.cpu(), "ddec": dec.grad.cpu(),
                                   "kl": kl.detach().cpu(), "recon": recon.cpu()}
@@ -92,14 +97,14 @@ def _worker(rank, world, port, case, small_limit, out):
         dist.destroy_process_group()
 
 
-def _run(tmp_path, world, case, small_limit=None):
+def _run(tmp_path, world, case, small_limit=None, rows_cluster=True):
     if torch.cuda.device_count() < world:
         pytest.skip("needs %d GPUs" % world)
     import torch.multiprocessing as mp
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from tolerance import check_close
     out = str(tmp_path / "r%d.pt")
-    mp.spawn(_worker, args=(world, _free_port(), case, small_limit, out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), case, small_limit, rows_cluster, out), nprocs=world, join=True)
     res = [torch.load(out % r) for r in range(world)]
     ref = res[0]["ref"]
     b_loc = res[0]["rep0"]["dmu"].size(0)
@@ -112,17 +117,24 @@ def _run(tmp_path, world, case, small_limit=None):
                 want = ref[key] if key == "loss" else ref[key][sl]
                 e = check_close(got[key], want.double(), rel=rel, what="world %d %s rank %d %s %s" % (world, case, r, rep, key))
                 worst[key] = max(worst.get(key, 0.0), e)
-    print("sharded head world=%d case=%s: worst rel err %s" % (world, case, {k: "%.1e" % v for k, v in worst.items()}))
+    print("sharded head world=%d case=%s rows_cluster=%s: worst rel err %s" % (world, case, rows_cluster,
+                                                                                {k: "%.1e" % v for k, v in worst.items()}))
 
 
 @pytest.mark.parametrize("small_limit", [2048, 16])
 def test_sharded_head_two_gpus(tmp_path, small_limit):
-    _run(tmp_path, 2, "small", small_limit)
+    _run(tmp_path, 2, "small", small_limit, rows_cluster=False)
 
 
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_head_small_one_launch(tmp_path, world):
+    _run(tmp_path, world, "small")
+
+
+@pytest.mark.parametrize("rows_cluster", [True, False])
 @pytest.mark.parametrize("world", [2, 4, 8])
-def test_sharded_head_c3_shape(tmp_path, world):
-    _run(tmp_path, world, "c3")
+def test_sharded_head_c3_shape(tmp_path, world, rows_cluster):
+    _run(tmp_path, world, "c3", rows_cluster=rows_cluster)
 
 
 @pytest.mark.parametrize("world", [2, 4, 8])
