@@ -122,6 +122,9 @@ int mae_reparam_reg_bwd(const float* mu, int64_t mu_stride, const float* logvar,
  * workspace, needed by the stored-KL backward paths 1 and 3; B200's 180 GB make this affordable far beyond the point
  * where recomputing the tiles (path 2, 16*B^2*D flop) is the only option (B = 65536 -> 34 GB). */
 int64_t mae_mpd_workspace_bytes(int64_t B, int64_t D, int store_kl);
+/* workspace for a ROW BLOCK [row0, row0 + nrows) that keeps KL_ij and KL_ji of its rows (store_kl of mae_mpd_fwd with a
+ * row block; sharded runs): everything of mae_mpd_workspace_bytes(B, D, 0) plus 2 * rows_pad * Bp floats. */
+int64_t mae_mpd_workspace_bytes_rows(int64_t B, int64_t D, int64_t row0, int64_t nrows);
 int mae_mpd_prepare(const float* mu, int64_t mu_stride, const float* logvar, int64_t logvar_stride,
                     int64_t B, int64_t D, void* workspace, int64_t workspace_bytes,
                     float* m_d, float* kl, mae_stream_t stream);

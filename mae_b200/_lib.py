@@ -58,6 +58,7 @@ PLAIN = {
     "mae_strerror": (c_char_p, [c_int]),
     "mae_device_info": (c_int, [_P, _P, _P]),
     "mae_mpd_workspace_bytes": (c_int64, [_I64, _I64, _I]),
+    "mae_mpd_workspace_bytes_rows": (c_int64, [_I64, _I64, _I64, _I64]),
     "mae_kl_mpd_loss_fused_supported": (c_int, [_I64, _I64]),
     "mae_dmol_workspace_bytes": (c_int64, [_I64, _I64]),
     "mae_iw_nll_workspace_bytes": (c_int64, [_I64, _I64]),

@@ -384,7 +384,9 @@ __global__ void __launch_bounds__(kNT)
 mpd_fwd_kernel(const float* __restrict__ Xp, const float* __restrict__ Yp, const float* __restrict__ evec,
                const float* __restrict__ fvec, Hdr* hdr, double* part, int B, int Kp, int row0, int row1, int tr0,
                int ntr, int ntc, float* __restrict__ KL, float* __restrict__ KLT, int Bp, double* __restrict__ sumsq_out,
-               float* __restrict__ S_out) {
+               float* __restrict__ S_out, int tc0, int kl_base) {
+    // tc0: first column tile (0 except for the transposed pass of a row block); kl_base: global row stored in row 0 of the
+    // KL / KLT buffers (row blocks keep only their rows); sumsq_out == nullptr: store pass only, no reduction
     constexpr int T = 16 * TM;       // tile edge
     constexpr int LD = T + 4;        // padded leading dimension
     constexpr int NLOAD = T * 4;     // float4 loads per operand slab (T rows x 16 k)
@@ -404,7 +406,7 @@ mpd_fwd_kernel(const float* __restrict__ Xp, const float* __restrict__ Yp, const
     // 16-byte shared-memory reads of a quarter warp fall into distinct banks
     auto rc = [](int t, int i) { return TM == 8 ? ((i < 4) ? t * 4 + i : 64 + t * 4 + (i - 4)) : t * TM + i; };
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int ti = tr0 + tile / ntc, tj = tile % ntc;
+        const int ti = tr0 + tile / ntc, tj = tc0 + tile % ntc;
         float acc[TM][TM];
 #pragma unroll
         for (int i = 0; i < TM; ++i)
@@ -486,18 +488,18 @@ mpd_fwd_kernel(const float* __restrict__ Xp, const float* __restrict__ Yp, const
                 if constexpr (TM >= 4) {
 #pragma unroll
                     for (int gq = 0; gq < TM / 4; ++gq)
-                        *reinterpret_cast<float4*>(KL + (int64_t)i * Bp + tj * T + rc(tx, gq * 4)) =
+                        *reinterpret_cast<float4*>(KL + (int64_t)(i - kl_base) * Bp + tj * T + rc(tx, gq * 4)) =
                             make_float4(klv[ii][gq * 4], klv[ii][gq * 4 + 1], klv[ii][gq * 4 + 2], klv[ii][gq * 4 + 3]);
                 } else {
 #pragma unroll
-                    for (int jj = 0; jj < TM; ++jj) KL[(int64_t)i * Bp + tj * T + rc(tx, jj)] = klv[ii][jj];
+                    for (int jj = 0; jj < TM; ++jj) KL[(int64_t)(i - kl_base) * Bp + tj * T + rc(tx, jj)] = klv[ii][jj];
                 }
             }
         }
         if (KLT != nullptr) {
 #pragma unroll
             for (int jj = 0; jj < TM; ++jj) {
-                float* dst = KLT + (int64_t)(tj * T + rc(tx, jj)) * Bp + ti * T;
+                float* dst = KLT + (int64_t)(tj * T + rc(tx, jj) - kl_base) * Bp + ti * T;
                 if constexpr (TM >= 4) {
 #pragma unroll
                     for (int gq = 0; gq < TM / 4; ++gq)
@@ -512,6 +514,7 @@ mpd_fwd_kernel(const float* __restrict__ Xp, const float* __restrict__ Yp, const
         total += (double)psum;
     }
     MAE_STAMP(hdr, 10);
+    if (sumsq_out == nullptr) return;   // store-only pass (KL_ji of a row block)
     total = block_sum(total, scratch);
     if (gridDim.x == 1) {  // single CTA: nothing to combine
         is_last = true;
@@ -874,6 +877,28 @@ mpd_bwd_tile_kernel(const float* __restrict__ mu, int64_t mu_stride, const float
     }
 }
 
+// Stored-KL buffers of a row block [row0, row0 + nrows): only the rows [base, base + rows_pad) of KL (= KL_ij, own i) and
+// of KL^T (= KL_ji, own i) are kept, base a multiple of the largest tile edge.  The full batch keeps Bp rows (base 0).
+struct KlGeom {
+    int64_t base, rows_pad, kl_off, klt_off, total;
+};
+KlGeom kl_geom(const Layout& L, int64_t B, int64_t row0, int64_t nrows) {
+    KlGeom g;
+    if (row0 == 0 && nrows == B) {
+        g.base = 0;
+        g.rows_pad = L.Bp;
+    } else {
+        g.base = (row0 / 128) * 128;
+        int64_t end = round_up(row0 + nrows, 128);
+        if (end > L.Bp) end = L.Bp;
+        g.rows_pad = end - g.base;
+    }
+    g.kl_off = L.kl;
+    g.klt_off = L.kl + round_up(g.rows_pad * L.Bp * 4, 256);
+    g.total = g.klt_off + round_up(g.rows_pad * L.Bp * 4, 256);
+    return g;
+}
+
 int check_common(int64_t B, int64_t D, const void* ws, int64_t ws_bytes, Layout& L) {
     MAE_REQUIRE(ws != nullptr, MAE_ERR_NULL);
     MAE_REQUIRE(B >= 2 && D >= 1 && B <= (1ll << 22) && D <= (1ll << 20), MAE_ERR_SHAPE);
@@ -890,6 +915,12 @@ extern "C" int64_t mae_mpd_workspace_bytes(int64_t B, int64_t D, int store_kl) {
     if (B < 2 || D < 1) return 0;
     const mae::Layout L = mae::make_layout(B, D);
     return store_kl ? L.total : L.total_nokl;
+}
+
+extern "C" int64_t mae_mpd_workspace_bytes_rows(int64_t B, int64_t D, int64_t row0, int64_t nrows) {
+    if (B < 2 || D < 1 || row0 < 0 || nrows < 1 || row0 + nrows > B) return 0;
+    const mae::Layout L = mae::make_layout(B, D);
+    return mae::kl_geom(L, B, row0, nrows).total;
 }
 
 extern "C" int mae_mpd_prepare(const float* mu, int64_t mu_stride, const float* logvar, int64_t logvar_stride, int64_t B,
@@ -918,12 +949,11 @@ extern "C" int mae_mpd_fwd(void* workspace, int64_t workspace_bytes, int64_t B, 
     int rc = check_common(B, D, workspace, workspace_bytes, L);
     if (rc != MAE_OK) return rc;
     MAE_REQUIRE(row0 >= 0 && nrows >= 1 && row0 + nrows <= B, MAE_ERR_SHAPE);
-    if (store_kl) {
-        MAE_REQUIRE(row0 == 0 && nrows == B, MAE_ERR_UNSUPPORTED);
-        MAE_REQUIRE(workspace_bytes >= L.total, MAE_ERR_WORKSPACE);
-    }
-    float* klp = store_kl ? at<float>(workspace, L.kl) : nullptr;
-    float* kltp = store_kl ? at<float>(workspace, L.klt) : nullptr;
+    const bool full = row0 == 0 && nrows == B;
+    const KlGeom kg = kl_geom(L, B, row0, nrows);
+    if (store_kl) MAE_REQUIRE(workspace_bytes >= kg.total, MAE_ERR_WORKSPACE);
+    float* klp = store_kl ? at<float>(workspace, kg.kl_off) : nullptr;
+    float* kltp = store_kl ? at<float>(workspace, kg.klt_off) : nullptr;
     auto launch = [&](auto tm_tag) {
         constexpr int TM = decltype(tm_tag)::value;
         constexpr int T = 16 * TM;
@@ -932,10 +962,21 @@ extern "C" int mae_mpd_fwd(void* workspace, int64_t workspace_bytes, int64_t B, 
         const int ntc = (int)(L.Bp / T);
         const int64_t ntiles = (int64_t)ntr * ntc;
         const int grid = (int)(ntiles < kMaxFwdCtas ? ntiles : kMaxFwdCtas);
+        // pass 1: tiles (own rows) x (all columns): sum of squares, KL_ij rows; the full batch also gets KL^T from the same tiles
         launch_pdl(mpd_fwd_kernel<TM>, dim3((unsigned)grid), dim3(kNT), 0, as_stream(stream),
             at<float>(workspace, L.xp), at<float>(workspace, L.yp), at<float>(workspace, L.c), at<float>(workspace, L.l),
             at<Hdr>(workspace, L.hdr), at<double>(workspace, L.part_fwd), (int)B, (int)L.Kp, (int)row0, (int)(row0 + nrows), tr0,
-            ntr, ntc, klp, kltp, (int)L.Bp, sumsq, S);
+            ntr, ntc, klp, full ? kltp : nullptr, (int)L.Bp, sumsq, S, 0, (int)kg.base);
+        if (store_kl && !full) {
+            // pass 2 (row blocks): tiles (all rows) x (own columns), stored transposed = KL_ji for the own i
+            const int tcb = (int)(kg.base / T), ntcb = (int)(kg.rows_pad / T), ntra = (int)(L.Bp / T);
+            const int64_t nt2 = (int64_t)ntra * ntcb;
+            const int grid2 = (int)(nt2 < kMaxFwdCtas ? nt2 : kMaxFwdCtas);
+            mpd_fwd_kernel<TM><<<grid2, kNT, 0, as_stream(stream)>>>(
+                at<float>(workspace, L.xp), at<float>(workspace, L.yp), at<float>(workspace, L.c), at<float>(workspace, L.l),
+                at<Hdr>(workspace, L.hdr), at<double>(workspace, L.part_fwd), (int)B, (int)L.Kp, 0, 0, 0, ntra, ntcb, nullptr, kltp,
+                (int)L.Bp, nullptr, nullptr, tcb, (int)kg.base);
+        }
     };
     const int tm_env = []() { const char* e = getenv("MAE_MPD_FWD_TM"); return e ? atoi(e) : 0; }();   // tuning only
     const int64_t small_limit = tm_env == 2 ? 1024 : (tm_env == 4 ? 256 : kSmallTileRows);
@@ -967,7 +1008,8 @@ extern "C" int mae_mpd_bwd(const float* mu, int64_t mu_stride, const float* logv
     MAE_REQUIRE(row0 >= 0 && nrows >= 1 && row0 + nrows <= B, MAE_ERR_SHAPE);
     MAE_REQUIRE(path >= 0 && path <= 3, MAE_ERR_SHAPE);
     if (path == 0) path = (B <= MAE_MPD_SMALL_B) ? 1 : 2;
-    if (path == 1 || path == 3) MAE_REQUIRE(workspace_bytes >= L.total, MAE_ERR_WORKSPACE);
+    const KlGeom kg = kl_geom(L, B, path == 1 ? 0 : row0, path == 1 ? B : nrows);   // path 1 always holds the full matrices
+    if (path == 1 || path == 3) MAE_REQUIRE(workspace_bytes >= kg.total, MAE_ERR_WORKSPACE);
     if (path == 1) {
         MAE_REQUIRE(B <= MAE_MPD_SMALL_B, MAE_ERR_UNSUPPORTED);
         const int64_t items = nrows * ceil_div(D, 32);
@@ -1003,7 +1045,8 @@ extern "C" int mae_mpd_bwd(const float* mu, int64_t mu_stride, const float* logv
             at<float>(workspace, L.c), at<float>(workspace, L.l), at<float4>(workspace, L.vp),
             at<double>(workspace, L.colstats), at<double>(workspace, L.pivots), at<Hdr>(workspace, L.hdr), g_m, g_S, S, gkl,
             (int)B, (int)D, (int)L.Kp, (int)row0, (int)(row0 + nrows), tr0, (int)L.nblk, dmu, dlogvar, accumulate,
-            STORED ? at<float>(workspace, L.kl) : nullptr, STORED ? at<float>(workspace, L.klt) : nullptr, (int)L.Bp);
+            STORED ? at<float>(workspace, kg.kl_off) - kg.base * L.Bp : nullptr,
+            STORED ? at<float>(workspace, kg.klt_off) - kg.base * L.Bp : nullptr, (int)L.Bp);
         return MAE_OK;
     };
     // 64-column chunks double the CTA count when 128-column chunks would not even fill the SMs once (stored path: the

@@ -262,8 +262,8 @@ def _mpd_launch_fwd(mu2, ms, lv2, ls, b, d, ws, store_kl, outs, row0=0, nrows=No
 
 
 # Largest pair of stored B x B KL matrices (KL and its transpose, 8*Bp^2 bytes) the backward may keep between forward
-# and backward; above it the tiles are recomputed (path 2).  B200: 180 GB of HBM, B = 32768 needs 8.6 GB.
-MPD_KL_BUDGET_BYTES = int(os.environ.get("MAE_MPD_KL_BUDGET_BYTES", 16 << 30))
+# and backward; above it the tiles are recomputed (path 2).  B200: 180 GB of HBM; B = 32768 needs 8.6 GB, B = 65536 34.4 GB.
+MPD_KL_BUDGET_BYTES = int(os.environ.get("MAE_MPD_KL_BUDGET_BYTES", 48 << 30))
 
 
 def _mpd_pick_path(b: int, d: int, requested: int) -> int:
@@ -446,15 +446,29 @@ def mpd_rows_forward(mu_all: torch.Tensor, logvar_all: torch.Tensor, row0: int, 
     if b < 2:
         raise RuntimeError("the MPD regulariser needs a global batch of at least 2 posteriors")
     dev = mu2.device
+    lib = _lib_()
     small = full and b <= 2048
-    ws = _pool.take(_lib_().mae_mpd_workspace_bytes(b, d, int(small)), dev)
+    if full:
+        store, path = small, (1 if small else 2)
+        nbytes = lib.mae_mpd_workspace_bytes(b, d, int(small))
+    else:
+        # row block: keep KL_ij and KL_ji of the own rows (two tile passes) when they fit the budget, so that the backward
+        # is the stored-KL tile kernel (8 B_loc B D executed flop) instead of the recompute path (16, times the K chunks)
+        base = lib.mae_mpd_workspace_bytes(b, d, 0)
+        with_rows = lib.mae_mpd_workspace_bytes_rows(b, d, row0, nrows)
+        store = with_rows - base <= MPD_KL_BUDGET_BYTES
+        path = 3 if store else 2
+        nbytes = with_rows if store else base
+    ws = _pool.take(nbytes, dev)
     kl_all = torch.empty(b, device=dev, dtype=torch.float32)
     outs = _mpd_alloc_outputs(d, dev)
     if full:
-        m_d, s, sumsq = _mpd_launch_fwd(mu2, ms, lv2, ls, b, d, ws, small, outs, kl=kl_all)
+        m_d, s, sumsq = _mpd_launch_fwd(mu2, ms, lv2, ls, b, d, ws, store, outs, kl=kl_all)
     else:
-        m_d, s, sumsq = _mpd_launch_fwd(mu2, ms, lv2, ls, b, d, ws, False, outs, row0, nrows, kl=kl_all)
-    state = MpdRowsState(ws, mu2, ms, lv2, ls, b, d, s if full else None, 1 if small else 2)
+        m_d, s, sumsq = _mpd_launch_fwd(mu2, ms, lv2, ls, b, d, ws, store, outs, row0, nrows, kl=kl_all)
+        if store:
+            _count()      # the transposed tile pass
+    state = MpdRowsState(ws, mu2, ms, lv2, ls, b, d, s if full else None, path)
     return m_d, (s if full else sumsq), kl_all, state
 
 

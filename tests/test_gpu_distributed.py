@@ -153,6 +153,9 @@ def _model_worker(rank, world, port, flows, out):
     # fp32 conv stacks: TF32 convolutions differ at 1e-3 between batch splits, which would hide what is being tested
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
+    # cuDNN picks its (Winograd / FFT) weight-gradient algorithms by batch size: 1e-3 relative differences between a batch
+    # of 16 and one of 32 on cancelling sums.  The native convolution path is batch-size independent to fp32 rounding.
+    torch.backends.cudnn.enabled = False
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     try:
         from mae_b200 import distributed as D, synth
@@ -219,7 +222,9 @@ def test_sharded_model_gradients_all_reduced(tmp_path, world, flows):
         check_close(res[r]["kl"], ref["kl"][sl].double(), rel=1e-5, what="rank %d KL" % r)
         check_close(res[r]["recon"], ref["recon"][sl].double(), rel=1e-5, what="rank %d recon" % r)
         assert set(res[r]["grads"]) == set(ref["grads"])
+        gscale = max(float(g_.abs().max()) for g_ in ref["grads"].values())   # parameters with a vanishing gradient: noise
         for n, gref in ref["grads"].items():
             # fp32 conv stacks with different batch splits: cuDNN may pick different algorithms / summation orders
-            worst = max(worst, check_close(res[r]["grads"][n], gref.double(), rel=5e-5, what="rank %d grad %s" % (r, n)))
+            worst = max(worst, check_close(res[r]["grads"][n], gref.double(), rel=5e-5, floor=1e-6 * gscale,
+                                           what="rank %d grad %s" % (r, n)))
     print("sharded MAE.loss world=%d flows=%s: worst parameter-gradient rel err %.1e" % (world, flows, worst))
