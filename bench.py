@@ -669,7 +669,13 @@ def bench_c5(dev, world, rank, dist_ctx, ffma_peak_tflops, quick=False):
             tt = torch.tensor([t], device=dev, dtype=torch.float64)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             t = float(tt)
-        path = "sharded row block, recompute backward" if world > 1 else ("stored-KL backward" if b5 <= 32768 else "recompute backward")
+        if world > 1:
+            lib_ = ops._lib_()
+            extra = lib_.mae_mpd_workspace_bytes_rows(b5, d5, rank * b_loc, b_loc) - lib_.mae_mpd_workspace_bytes(b5, d5, 0)
+            path = "sharded row block, " + ("stored-KL backward (KL_ij and KL_ji of the own rows: two tile passes)"
+                                            if extra <= ops.MPD_KL_BUDGET_BYTES else "recompute backward")
+        else:
+            path = "stored-KL backward" if ops._mpd_pick_path(b5, d5, 0) != 2 else "recompute backward"
         res["c5_mpd_b%d_d%d" % (b5, d5)] = {
             "metric": "mpd_fwd_bwd_pairs_per_s", "value": b5 * b5 / t, "unit": "pairs/s", "n_gpus": world, "scaling": "strong",
             "ms": t * 1e3, "tflops_algorithmic": flop / t / 1e12, "path": path,

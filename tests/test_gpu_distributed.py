@@ -215,7 +215,7 @@ def test_sharded_model_gradients_all_reduced(tmp_path, world, flows):
     mp.spawn(_model_worker, args=(world, _free_port(), flows, out), nprocs=world, join=True)
     res = [torch.load(out % r) for r in range(world)]
     ref = res[0]["ref"]
-    worst = 0.0
+    worst = worst_global = 0.0
     for r in range(world):
         check_close(res[r]["loss"], ref["loss"].double(), rel=5e-6, what="rank %d loss" % r)
         sl = slice(r * 16, (r + 1) * 16)
@@ -225,6 +225,11 @@ def test_sharded_model_gradients_all_reduced(tmp_path, world, flows):
         gscale = max(float(g_.abs().max()) for g_ in ref["grads"].values())   # parameters with a vanishing gradient: noise
         for n, gref in ref["grads"].items():
             # fp32 conv stacks with different batch splits: cuDNN may pick different algorithms / summation orders
-            worst = max(worst, check_close(res[r]["grads"][n], gref.double(), rel=5e-5, floor=1e-6 * gscale,
-                                           what="rank %d grad %s" % (r, n)))
-    print("sharded MAE.loss world=%d flows=%s: worst parameter-gradient rel err %.1e" % (world, flows, worst))
+            e = check_close(res[r]["grads"][n], gref.double(), rel=5e-5, floor=1e-6 * gscale, what="rank %d grad %s" % (r, n))
+            sc = float(gref.abs().max())
+            worst_global = max(worst_global, e * sc / gscale)
+            if sc > 1e-3 * gscale:       # a parameter whose whole gradient is rounding noise has no relative error to speak of
+                worst = max(worst, e)
+    print("sharded MAE.loss world=%d flows=%s: worst parameter-gradient error %.1e of the parameter's own scale "
+          "(parameters above 1e-3 of the largest gradient), %.1e of the largest gradient (all parameters)"
+          % (world, flows, worst, worst_global))
