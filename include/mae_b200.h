@@ -213,6 +213,25 @@ int mae_dmol_fwd_bwd(const float* raw, const float* x, float g_mul, int64_t B, i
 int mae_scale_inplace(float* data, int64_t n, const float* scale, mae_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * N2  the decoder's final 1x1 convolution fused with the DMOL likelihood (tcgen05 3xTF32, accumulators in TMEM)
+ *   replaces the LAST layer of the colour decoders' conv stacks together with A4b + A4c:
+ *     nn.Sequential(..., nn.ELU(), Conv2dWeightNorm(hidden, 10*nmix, 1))   image_decoders/pixelcnnpp.py:32-34  (act = 1)
+ *     Conv2dWeightNorm(48, 10*nmix, 1)                                      image_decoders/resnet.py:85         (act = 0)
+ *     ColorImageDecoder.reconstruct_error                                   color_image_decoder.py:91-125
+ *   hidden [B*ns, C, HW] fp32 NCHW: the input of that last layer (before its ELU when act = 1);
+ *   weight [10*nmix, C] row-major: the EFFECTIVE weights (weight normalisation g * v / |v| applied by the caller,
+ *   weight_norm.py) in the reference's channel order; bias [10*nmix] (nullable); x [B, 3, HW] in [-1, 1].
+ *   err [B*ns] = -log p(x | z) summed over pixels.  draw (nullable) [B*ns, 10*nmix, HW] = g_mul * d err / d raw for the
+ *   convolution's backward (plain library GEMMs on the caller's side); the raw tensor itself is never written.
+ *   supported(C, nmix, HW): nmix = 10 with C in {48, 64, 96}, nmix = 5 with C = 64; HW a multiple of 128.
+ * ---------------------------------------------------------------------------------------------- */
+int mae_dmol_head_supported(int64_t C, int64_t nmix, int64_t HW);
+int64_t mae_dmol_head_workspace_bytes(int64_t N, int64_t HW);
+int mae_dmol_head(const float* hidden, const float* weight, const float* bias, const float* x, int64_t B, int64_t ns,
+                  int64_t nmix, int64_t C, int64_t HW, int act, float g_mul, float* err, float* draw,
+                  void* workspace, int64_t workspace_bytes, mae_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * A5 / A6  Gaussian log densities
  *   replaces GaussianEncoder.log_probability_prior     (gaussian_encoder.py:231-260, lines 256-258)
  *            GaussianEncoder.log_probability_posterior (gaussian_encoder.py:262-301, lines 297-299)

@@ -40,6 +40,7 @@ SIGNATURES = {
     "mae_loss_assemble_bwd": [_P, _P, _P, _I64, _I64, _I64, _F, _F, _F, _F, _P, _P, _P, _P, _P],
     "mae_dmol_fwd_bwd": [_P, _P, _F, _I64, _I64, _I64, _I64, _P, _P, _P],
     "mae_scale_inplace": [_P, _I64, _P, _P],
+    "mae_dmol_head": [_P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _I, _F, _P, _P, _P, _I64, _P],
     "mae_comm_alloc": [_I64, _P],
     "mae_comm_free": [_P],
     "mae_comm_get_handle": [_P, _P],
@@ -67,6 +68,8 @@ PLAIN = {
     "mae_rows_scratch_bytes": (c_int64, []),
     "mae_kl_mpd_rows_fused_supported": (c_int, [_I64, _I64, _I64]),
     "mae_dmol_err_chunks": (c_int64, [_I64, _I64, _I64, _I64]),
+    "mae_dmol_head_supported": (c_int, [_I64, _I64, _I64]),
+    "mae_dmol_head_workspace_bytes": (c_int64, [_I64, _I64]),
 }
 ALL_SYMBOLS = sorted(list(SIGNATURES) + list(PLAIN))
 

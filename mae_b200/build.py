@@ -16,7 +16,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libmae_b200.so")
-SOURCES = ["api.cu", "reparam_kl.cu", "mpd.cu", "mpd_fused.cu", "mpd_rows_fused.cu", "bernoulli.cu", "dmol.cu", "logprob_iw.cu", "assemble.cu", "p2p_gather.cu", "microbench.cu"]
+SOURCES = ["api.cu", "reparam_kl.cu", "mpd.cu", "mpd_fused.cu", "mpd_rows_fused.cu", "bernoulli.cu", "dmol.cu", "dmol_head.cu", "logprob_iw.cu", "assemble.cu", "p2p_gather.cu", "microbench.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr",

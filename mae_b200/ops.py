@@ -704,6 +704,89 @@ def dmol_recon_error(raw: torch.Tensor, x: torch.Tensor, ns: int, nmix: int) -> 
 
 
 # ------------------------------------------------------------------------------------------------
+# N2: final 1x1 convolution + A4b + A4c in one tcgen05 kernel (csrc/dmol_head.cu)
+# ------------------------------------------------------------------------------------------------
+def dmol_head_supported(hidden: torch.Tensor, nmix: int) -> bool:
+    """True when the fused kernel covers this shape (hidden [N, C, H, W] fp32 on a CUDA device)."""
+    if not (hidden.is_cuda and hidden.dtype == torch.float32 and hidden.dim() == 4):
+        return False
+    return bool(_lib_().mae_dmol_head_supported(hidden.size(1), int(nmix), hidden.size(2) * hidden.size(3)))
+
+
+@_guarded
+def _dmol_head_launch(hidden_c, weight_c, bias_c, x_c, b, ns, nmix, act, g_mul, want_grad):
+    n, c = hidden_c.size(0), hidden_c.size(1)
+    hw = hidden_c.size(2) * hidden_c.size(3)
+    lib = _lib_()
+    ws = _pool.take(max(int(lib.mae_dmol_head_workspace_bytes(n, hw)), 256), hidden_c.device)
+    err = torch.empty(b, ns, device=hidden_c.device, dtype=torch.float32)
+    draw = torch.empty(n, 10 * nmix, hidden_c.size(2), hidden_c.size(3), device=hidden_c.device, dtype=torch.float32) if want_grad else None
+    _lib.check(lib.mae_dmol_head(hidden_c.data_ptr(), weight_c.data_ptr(), _ptr(bias_c), x_c.data_ptr(), b, ns, nmix, c, hw,
+                                 1 if act else 0, float(g_mul), err.data_ptr(), _ptr(draw), ws.data_ptr(), ws.numel(), _stream()),
+               "mae_dmol_head")
+    _count()
+    _pool.give(ws)
+    return err, draw
+
+
+class _DmolHead(torch.autograd.Function):
+    """(hidden, weight, bias, x) -> err [B, ns].  When any input needs a gradient the same launch also emits d err / d raw
+    (unit upstream gradient); the convolution's own backward (d hidden, d weight, d bias) is then three library GEMM-shaped
+    contractions on it - the raw tensor is never materialised in either direction."""
+
+    @staticmethod
+    def forward(ctx, hidden, weight, bias, x, ns, nmix, act):
+        _req_cuda(hidden, weight, bias, x)
+        n, c = hidden.size(0), hidden.size(1)
+        b = x.size(0)
+        if hidden.dim() != 4 or weight.shape != (10 * nmix, c) or n != b * ns or x.size(1) != 3 or x.shape[2:] != hidden.shape[2:]:
+            raise RuntimeError("dmol_head: hidden %s / weight %s / x %s inconsistent with ns=%d nmix=%d"
+                               % (tuple(hidden.shape), tuple(weight.shape), tuple(x.shape), ns, nmix))
+        if not dmol_head_supported(hidden, nmix):
+            raise RuntimeError("dmol_head: unsupported shape C=%d nmix=%d HW=%d (see mae_dmol_head_supported)"
+                               % (c, nmix, hidden.size(2) * hidden.size(3)))
+        need = any(ctx.needs_input_grad[:3])
+        hidden_c, weight_c, x_c = hidden.contiguous(), weight.contiguous(), x.contiguous()
+        bias_c = bias.contiguous() if bias is not None else None
+        err, draw = _dmol_head_launch(hidden_c, weight_c, bias_c, x_c, b, ns, nmix, act, 1.0, need)
+        if need:
+            ctx.save_for_backward(hidden_c, weight_c, draw)
+        ctx.meta = (b, ns, nmix, act, bias is not None)
+        return err
+
+    @staticmethod
+    def backward(ctx, g):
+        hidden_c, weight_c, draw = ctx.saved_tensors
+        b, ns, nmix, act, has_bias = ctx.meta
+        n, c = hidden_c.size(0), hidden_c.size(1)
+        graw = (draw.view(n, 10 * nmix, -1) * g.reshape(n, 1, 1)).view_as(draw) if g is not None else draw
+        g3 = graw.view(n, 10 * nmix, -1)
+        h3 = hidden_c.view(n, c, -1)
+        a3 = torch.nn.functional.elu(h3) if act else h3
+        gw = gb = gh = None
+        if ctx.needs_input_grad[1]:
+            gw = torch.einsum("nop,ncp->oc", g3, a3)
+        if has_bias and ctx.needs_input_grad[2]:
+            gb = g3.sum(dim=(0, 2))
+        if ctx.needs_input_grad[0]:
+            ga = torch.matmul(weight_c.t().unsqueeze(0), g3)            # [n, c, hw]
+            if act:
+                ga = ga * torch.where(h3 > 0, torch.ones_like(h3), a3 + 1.0)   # ELU'(h) = 1 (h > 0), exp(h) = ELU(h) + 1
+            gh = ga.view_as(hidden_c)
+        return gh, gw, gb, None, None, None, None
+
+
+def dmol_head_recon_error(hidden: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], x: torch.Tensor,
+                          ns: int, nmix: int, act: bool) -> torch.Tensor:
+    """Reconstruction error [B, ns] straight from the INPUT of the decoder's last 1x1 convolution.
+
+    hidden [B*ns, C, H, W] (before the ELU in front of that convolution when ``act``), weight [10*nmix, C] / bias [10*nmix]
+    the effective (weight-normalised) parameters of the convolution, x [B, 3, H, W] in [-1, 1].
+    Reference: image_decoders/pixelcnnpp.py:32-34 / resnet.py:85 followed by color_image_decoder.py:91-125."""
+    return _DmolHead.apply(hidden, weight, bias, x, int(ns), int(nmix), bool(act))
+
+
+# ------------------------------------------------------------------------------------------------
 # A5 / A6
 # ------------------------------------------------------------------------------------------------
 class _LogPrior(torch.autograd.Function):
