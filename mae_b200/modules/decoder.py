@@ -139,9 +139,31 @@ class ColorImageDecoder(Decoder):
         x_expand = x.repeat_interleave(ns, dim=0) if ns > 1 else x
         return self(x_expand, z.view(b * ns, *size[2:]))
 
+    def head_parts(self):
+        """Sub-classes whose conv stack ends in a 1x1 ``Conv2dWeightNorm`` return ``(trunk, last, act)``: ``trunk(x, z)`` is
+        the stack up to the INPUT of that convolution (before the ELU in front of it when ``act``) and ``last`` the
+        convolution module; the likelihood kernel then contracts with ``last``'s weights itself and the raw parameter tensor
+        is never materialised.  ``None``: no such split (the default)."""
+        return None
+
     def reconstruct_error(self, x, z):
         """x [B,3,H,W] in [-1,1], z [B,ns,*z] -> [B,ns].  Reference: color_image_decoder.py:91-125."""
-        return ops.dmol_recon_error(self.likelihood_input(x, z), x, z.size(1), self.nmix)
+        ns = z.size(1)
+        mode = ops.dmol_head_mode()
+        parts = self.head_parts() if mode != "off" else None
+        if parts is not None and (mode == "always" or not self._needs_grad(z)):
+            trunk, last, act = parts
+            size = z.size()
+            x_expand = x.repeat_interleave(ns, dim=0) if ns > 1 else x
+            hidden = trunk(x_expand, z.view(size[0] * ns, *size[2:]))
+            if ops.dmol_head_supported(hidden, self.nmix):
+                return ops.dmol_head_recon_error(hidden, last.conv.weight().flatten(1), last.conv.bias, x, ns, self.nmix, act)
+            raw = last(F.elu(hidden) if act else hidden)
+            return ops.dmol_recon_error(raw, x, ns, self.nmix)
+        return ops.dmol_recon_error(self.likelihood_input(x, z), x, ns, self.nmix)
+
+    def _needs_grad(self, z) -> bool:
+        return torch.is_grad_enabled() and (z.requires_grad or any(p.requires_grad for p in self.parameters()))
 
     def log_probability(self, x, z):
         return self.reconstruct_error(x, z) * -1.

@@ -110,6 +110,8 @@ class MAE(nn.Module):
             return False
         if type(enc).encode is not GaussianEncoder.encode:
             return False
+        if isinstance(dec, ColorImageDecoder) and ops.dmol_head_mode() == "always" and dec.head_parts() is not None:
+            return False      # the decoder's last convolution runs inside the likelihood kernel: reconstruct_error path
         for base in (BinaryImageDecoder, ColorImageDecoder):
             if isinstance(dec, base):
                 return type(dec).reconstruct_error is base.reconstruct_error

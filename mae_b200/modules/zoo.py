@@ -166,6 +166,13 @@ class ResnetDecoderColorImage32x32(ColorImageDecoder):
     def forward(self, x, z):
         return self.core(z)
 
+    def head_parts(self):
+        """image_decoders/resnet.py:85: the stack ends in Conv2dWeightNorm(48, 10*nmix, 1) on the last DeResNet's output."""
+        if isinstance(self.core, nn.DataParallel):
+            return None
+        core = self.core
+        return (lambda x, z: core[:-1](z)), core[-1], False
+
     def initialize(self, x, z, init_scale=1.0):
         return _run(_unwrap(self.core), z, True, init_scale)
 
@@ -420,6 +427,11 @@ class _PixelCNNPPCore(nn.Module):
     def forward(self, x, z):
         return self._pass(x, z, False, 1.0)
 
+    def trunk(self, x, z):
+        """Everything up to the input of the last ELU -> 1x1 convolution pair (image_decoders/pixelcnnpp.py:28-34)."""
+        h = self.z_transform(z)
+        return self.output[1](self.output[0](self.core(x, h=h)))
+
     def initialize(self, x, z, init_scale=1.0):
         return self._pass(x, z, True, init_scale)
 
@@ -444,6 +456,11 @@ class PixelCNNPPDecoderColorImage32x32(ColorImageDecoder):
 
     def forward(self, x, z):
         return self.core(x, z)
+
+    def head_parts(self):
+        if isinstance(self.core, nn.DataParallel):
+            return None
+        return self.core.trunk, self.core.output[3], True
 
     def decode(self, z, random_sample):
         """Ancestral sampling, one pixel per network evaluation (image_decoders/pixelcnnpp.py:101-123)."""

@@ -17,7 +17,7 @@ from . import _lib
 __all__ = [
     "reparam_kl", "mpd", "mpd_forward_only", "bernoulli_recon_error", "dmol_recon_error", "log_prob_prior",
     "log_prob_posterior", "iw_nll", "assemble_loss", "kl_mpd", "loss_tail", "loss_head", "encode_head", "kl_mpd_reg_fused", "kl_mpd_reg", "mpd_rows_loss_backward", "reg_rows_fused", "reg_rows_cluster", "rows_cluster_supported", "reparam_fwd",
-    "reparam_reg_bwd", "fused_reg_supported", "set_pdl", "set_unit_loss_grad", "join_side", "launch_count", "reset_launch_count",
+    "reparam_reg_bwd", "fused_reg_supported", "set_pdl", "set_unit_loss_grad", "set_dmol_head", "dmol_head_mode", "dmol_head_supported", "dmol_head_recon_error", "join_side", "launch_count", "reset_launch_count",
 ]
 
 _launches = 0  # number of kernels of ours enqueued since the last reset (bench.py reports it)
@@ -706,6 +706,25 @@ def dmol_recon_error(raw: torch.Tensor, x: torch.Tensor, ns: int, nmix: int) -> 
 # ------------------------------------------------------------------------------------------------
 # N2: final 1x1 convolution + A4b + A4c in one tcgen05 kernel (csrc/dmol_head.cu)
 # ------------------------------------------------------------------------------------------------
+_dmol_head_mode = os.environ.get("MAE_DMOL_HEAD", "eval")
+
+
+def set_dmol_head(mode: str) -> str:
+    """When the colour decoders fuse their last 1x1 convolution into the likelihood kernel (csrc/dmol_head.cu):
+    ``"eval"`` (default) - whenever no gradient is needed (``MAE.nll``, evaluation under ``no_grad``): the K-sample raw tensor
+    (210 MB per CIFAR image at K = 512) is never written; ``"always"`` - in training too (the kernel then also emits
+    d err / d raw and the convolution's backward is three library contractions); ``"off"`` - never.  Returns the previous mode."""
+    global _dmol_head_mode
+    if mode not in ("off", "eval", "always"):
+        raise ValueError("mode must be 'off', 'eval' or 'always'")
+    prev, _dmol_head_mode = _dmol_head_mode, mode
+    return prev
+
+
+def dmol_head_mode() -> str:
+    return _dmol_head_mode
+
+
 def dmol_head_supported(hidden: torch.Tensor, nmix: int) -> bool:
     """True when the fused kernel covers this shape (hidden [N, C, H, W] fp32 on a CUDA device)."""
     if not (hidden.is_cuda and hidden.dtype == torch.float32 and hidden.dim() == 4):

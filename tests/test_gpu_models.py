@@ -34,10 +34,15 @@ def _no_tf32():
     torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
 
 
-@pytest.mark.parametrize("name", ["binary_image_json", "color_resnet", "color_image32x32_json"])
-def test_full_model_loss_grads_and_nll_match_reference(fixtures, name, monkeypatch):
-    from mae_b200 import synth
+@pytest.mark.parametrize("name,head_mode", [
+    ("binary_image_json", "eval"), ("color_resnet", "eval"), ("color_image32x32_json", "eval"),
+    # N2: "always" also trains through the fused last-convolution + likelihood kernel (loss 7-tuple and every parameter
+    # gradient against the live reference); "off" keeps the raw tensor in evaluation as well
+    ("color_resnet", "always"), ("color_image32x32_json", "always"), ("color_resnet", "off"), ("color_image32x32_json", "off")])
+def test_full_model_loss_grads_and_nll_match_reference(fixtures, name, head_mode, monkeypatch):
+    from mae_b200 import ops, synth
     from mae_b200.modules import MAE, GaussianEncoder
+    monkeypatch.setattr(ops, "_dmol_head_mode", head_mode)
     c = fixtures[name]
     r64, r32 = c["ref64"], c["ref32"]
     model = synth.fill_state(MAE.from_params(copy.deepcopy(c["params"]))).to(DEV)
