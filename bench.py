@@ -470,6 +470,7 @@ def bench_ours(args):
             peaks = P.measure(dev)
         barrier()
         extra.update(bench_c4(dev, hbm_gbs, world))                       # every rank: its shard of the evaluation
+        extra.update(bench_n2(dev, hbm_gbs, world))
         if peaks is not None and "c4_iw_nll_eval" in extra:
             extra["c4_iw_nll_eval"]["roofline"]["sfu_coroof"] = c4_sfu_coroof(peaks)
         ffma_peak = [peaks["ffma_tflops"] if peaks else 0.0]
@@ -576,6 +577,108 @@ def bench_c4(dev, hbm_gbs, world=1):
     del graphs, outs
     del slabs
     torch.cuda.empty_cache()
+    return res
+
+
+def bench_n2(dev, hbm_gbs, world=1):
+    """N2: the colour decoder's last 1x1 convolution fused with the DMOL likelihood (csrc/dmol_head.cu: TMA ->
+    3xTF32 tcgen05.mma with the operand and the accumulators in TMEM -> DMOL epilogue).  Evaluation shape of C4: 8 images x
+    K = 512 samples of the PixelCNN++ CIFAR decoder (hidden 96 channels, image_decoders/pixelcnnpp.py:28-34), inputs are
+    the INPUT of the last ELU -> Conv2dWeightNorm(96, 100, 1) pair.  Beside it: the same work unfused (ATen ELU + cuDNN/cuBLAS
+    1x1 convolution writing the raw tensor, then this repo's DMOL forward kernel reading it), and the training shape of C3
+    (batch 64, kernel also emits d err / d raw)."""
+    import torch.distributed as dist
+    import torch.nn.functional as F
+    from mae_b200 import ops
+    res = {}
+    stream = torch.cuda.current_stream()
+    k, nimg, c, nmix = 512, 8, 96, 10
+    g = torch.Generator(device=dev).manual_seed(8191)
+    w = torch.randn(100, c, device=dev, generator=g) * (0.5 / c ** 0.5)
+    bias = torch.randn(100, device=dev, generator=g) * 0.1
+    slabs = []
+    for i in range(3):       # 3 x 1.61 GB of hidden > L2
+        hid = torch.randn(nimg * k, c, 32, 32, device=dev, generator=g)
+        x = (torch.randint(0, 256, (nimg, 3, 32, 32), device=dev, generator=g).float() / 127.5 - 1.0)
+        slabs.append((hid, x))
+
+    def fused(i):
+        hid, x = slabs[i % 3]
+        return ops.dmol_head_recon_error(hid, w, bias, x, k, nmix, True)
+
+    w4 = w.view(100, c, 1, 1)
+
+    def unfused(i):
+        hid, x = slabs[i % 3]
+        return ops.dmol_recon_error(F.conv2d(F.elu(hid), w4, bias), x, k, nmix)
+
+    with torch.no_grad():
+        a, b_ = fused(0), unfused(0)
+        torch.cuda.synchronize()
+        agree = float((a - b_).abs().max() / b_.abs().max())
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+        t_f = time_kernel(fused, 12, stream, 3)
+        t_u = time_kernel(unfused, 6, stream, 3)
+        if world > 1:
+            tt = torch.tensor([t_f, t_u], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            t_f, t_u = float(tt[0]), float(tt[1])
+    px = nimg * k * 1024
+    bytes_fused = 4 * (px * c + nimg * 3 * 1024 + nimg * k)
+    bytes_unfused = 4 * (px * (2 * c) + px * (c + 100) + px * 100 + nimg * 3 * 1024 + nimg * k)   # ELU r+w, conv r+w, DMOL r
+    mma_flop = px * 2.0 * 112 * (c + 8) * 3                                   # executed: 3 tf32 products, N padded to 112
+    res["n2_fused_head_eval"] = {
+        "metric": "fused_conv1x1_dmol_eval_images_per_s", "value": world * nimg / t_f, "unit": "images/s", "n_gpus": world,
+        "config": "PixelCNN++ CIFAR head: hidden [8 x 512, 96, 32, 32] fp32 -> ELU -> 1x1 conv (100) -> DMOL nmix=10, ring of 3 slabs (4.8 GB) > L2",
+        "us_per_image": t_f / nimg * 1e6, "ms_per_launch": t_f * 1e3,
+        "unfused": {"what": "ATen ELU + cuDNN 1x1 convolution (raw tensor written) + this repo's DMOL forward kernel",
+                    "images_per_s": world * nimg / t_u, "ms_per_launch": t_u * 1e3, "speedup_fused": t_u / t_f,
+                    "hbm_bytes_per_image": bytes_unfused // nimg},
+        "hbm_bytes_per_image": bytes_fused // nimg, "hbm_bytes_saved_per_image": (bytes_unfused - bytes_fused) // nimg,
+        "fused_vs_unfused_rel_diff": agree,
+        "roofline": {"bound": "issue / SFU (epilogue) over hbm", "achieved_per_gpu": bytes_fused / t_f / 1e9, "peak": hbm_gbs,
+                     "frac": bytes_fused / t_f / 1e9 / hbm_gbs, "tf32_mma_tflops_executed": mma_flop / t_f / 1e12,
+                     "note": "per 128-pixel tile: 38 tcgen05.mma (128 x 112 x 8, 3xTF32) = 2.1 k tensor-pipe cycles, ~13 k warp "
+                             "instructions (9.2 k DMOL epilogue, 3.3 k ELU + split) = 3.3 k issue cycles at 4 IPC, 24 k + 12 k SFU "
+                             "ops = 2.3 k cycles; profiles/README.md has the per-role cycle breakdown"}}
+    del slabs
+    torch.cuda.empty_cache()
+
+    # training shape (C3): batch 64, one sample; the kernel also writes d err / d raw (26 MB)
+    if world == 1:
+        bt = 64
+        hid = [torch.randn(bt, c, 32, 32, device=dev, generator=g) for _ in range(8)]      # 8 x 25 MB
+        x = (torch.randint(0, 256, (bt, 3, 32, 32), device=dev, generator=g).float() / 127.5 - 1.0)
+        lib = ops._lib_()
+        err = torch.empty(bt, 1, device=dev)
+        draws = [torch.empty(bt, 100, 32, 32, device=dev) for _ in range(8)]
+        ws = torch.zeros(int(lib.mae_dmol_head_workspace_bytes(bt, 1024)) + 256, dtype=torch.uint8, device=dev)
+        raws = [F.conv2d(F.elu(h), w4, bias) for h in hid]
+        chunks = int(lib.mae_dmol_err_chunks(bt, 1, nmix, 1024))
+        errp = torch.empty(bt, 1, chunks, device=dev)
+
+        def fused_train(i):
+            lib.mae_dmol_head(hid[i % 8].data_ptr(), w.data_ptr(), bias.data_ptr(), x.data_ptr(), bt, 1, nmix, c, 1024, 1, 1.0 / bt,
+                              err.data_ptr(), draws[i % 8].data_ptr(), ws.data_ptr(), ws.numel(), stream.cuda_stream)
+
+        def dmol_train(i):
+            lib.mae_dmol_fwd_bwd(raws[i % 8].data_ptr(), x.data_ptr(), 1.0 / bt, bt, 1, nmix, 1024, errp.data_ptr(),
+                                 draws[i % 8].data_ptr(), stream.cuda_stream)
+
+        def conv_only(i):
+            F.conv2d(F.elu(hid[i % 8]), w4, bias)
+
+        with torch.no_grad():
+            t_ft = time_kernel(fused_train, 50, stream, 5)
+            t_dt = time_kernel(dmol_train, 50, stream, 5)
+            t_cv = time_kernel(conv_only, 50, stream, 5)
+        res["n2_fused_head_train_c3"] = {
+            "config": "batch 64 x 32 x 32, hidden 96: last conv + DMOL forward + d err/d raw in one launch", "us_fused": t_ft * 1e6,
+            "us_unfused": (t_dt + t_cv) * 1e6, "us_unfused_parts": {"elu_conv1x1": t_cv * 1e6, "dmol_fwd_bwd": t_dt * 1e6},
+            "note": "at 512 tiles (3.5 per SM) the persistent pipeline has no depth: training keeps the raw-tensor kernels by "
+                    "default (ops.set_dmol_head('eval')), the fused head is the evaluation path"}
     return res
 
 
