@@ -52,6 +52,9 @@ int mae_abi_version(void);
  * process (the batch-sharded head does: at 8 GPUs early-placed successors cost 8 us per step while ranks wait for each
  * other's rows); MAE_NO_PDL=1 in the environment has the same effect.  Returns the previous setting. */
 int mae_set_pdl(int enabled);
+/* Tensor-core tiles of the MPD regulariser (3xTF32 tcgen05.mma, csrc/mpd_tc.cuh) for padded batches >= 2048: on by default
+ * (MAE_MPD_TC=0 in the environment starts with them off); off = the FP32 FFMA tile kernels.  Returns the previous setting. */
+int mae_set_mpd_tensor_cores(int enabled);
 const char* mae_strerror(int code);
 /* SM count / compute capability of the current device; used by the host layer to refuse non-sm_100 parts. */
 int mae_device_info(int* sm_count, int* cc_major, int* cc_minor);

@@ -56,6 +56,7 @@ SIGNATURES = {
 PLAIN = {
     "mae_abi_version": (c_int, []),
     "mae_set_pdl": (c_int, [c_int]),
+    "mae_set_mpd_tensor_cores": (c_int, [c_int]),
     "mae_strerror": (c_char_p, [c_int]),
     "mae_device_info": (c_int, [_P, _P, _P]),
     "mae_mpd_workspace_bytes": (c_int64, [_I64, _I64, _I]),

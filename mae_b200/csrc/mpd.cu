@@ -28,6 +28,7 @@
 
 #include "common.cuh"
 #include "mpd_math.cuh"
+#include "tc5.cuh"
 
 namespace mae {
 namespace {
@@ -877,11 +878,31 @@ mpd_bwd_tile_kernel(const float* __restrict__ mu, int64_t mu_stride, const float
     }
 }
 
+#include "mpd_tc.cuh"
+
+int g_mpd_tc = []() { const char* e = getenv("MAE_MPD_TC"); return (e && atoi(e) == 0) ? 0 : 1; }();
+
 // Stored-KL buffers of a row block [row0, row0 + nrows): only the rows [base, base + rows_pad) of KL (= KL_ij, own i) and
 // of KL^T (= KL_ji, own i) are kept, base a multiple of the largest tile edge.  The full batch keeps Bp rows (base 0).
 struct KlGeom {
     int64_t base, rows_pad, kl_off, klt_off, total;
+    int64_t tc_split, gp_off, rs_off;   // tensor-core backward: partner splits, partial G1 / G2 sums, partial row sums
 };
+// partner splits of the tensor-core backward: enough CTAs (row tiles x column chunks x splits) for ~2 per SM
+int64_t tc_splits(int64_t row_tiles, int64_t col_chunks, int64_t partner_tiles) {
+    int64_t s = ceil_div(2 * 148, row_tiles * col_chunks);
+    if (s > 8) s = 8;
+    if (s > partner_tiles) s = partner_tiles;
+    return s < 1 ? 1 : s;
+}
+// chunks of 32 partners per TMEM accumulation of the tensor-core backward (default 16 = 512 partners = 192 accumulating
+// MMAs): the tensor core's accumulator does not round to nearest, so the error of a running sum grows with its length
+// (measured against the FFMA path at B = 32768: 7e-5 of the gradient scale with one accumulation over all partners, 9e-6
+// with 2048 partners per accumulation, 2e-6 with 512, independent of B); the groups are added in fp32 by the row owners
+int tc_group_chunks() {
+    static const int v = []() { const char* e = getenv("MAE_MPD_TC_GROUP"); const int g = e ? atoi(e) : 16; return g < 1 ? 1 : g; }();
+    return v;
+}
 KlGeom kl_geom(const Layout& L, int64_t B, int64_t row0, int64_t nrows) {
     KlGeom g;
     if (row0 == 0 && nrows == B) {
@@ -896,6 +917,14 @@ KlGeom kl_geom(const Layout& L, int64_t B, int64_t row0, int64_t nrows) {
     g.kl_off = L.kl;
     g.klt_off = L.kl + round_up(g.rows_pad * L.Bp * 4, 256);
     g.total = g.klt_off + round_up(g.rows_pad * L.Bp * 4, 256);
+    g.tc_split = 0;
+    g.gp_off = g.rs_off = g.total;
+    if (L.Bp >= kBigTileRows && L.Kp % 128 == 0 && L.Kp <= 512) {
+        g.tc_split = tc_splits(g.rows_pad / 128, L.Kp / 128, L.Bp / 128);
+        g.gp_off = g.total;
+        g.rs_off = g.gp_off + round_up(2 * g.tc_split * g.rows_pad * L.Kp * 4, 256);
+        g.total = g.rs_off + round_up(2 * g.tc_split * g.rows_pad * 4, 256);
+    }
     return g;
 }
 
@@ -911,10 +940,16 @@ int check_common(int64_t B, int64_t D, const void* ws, int64_t ws_bytes, Layout&
 }  // namespace
 }  // namespace mae
 
+extern "C" int mae_set_mpd_tensor_cores(int enabled) {
+    const int before = mae::g_mpd_tc;
+    mae::g_mpd_tc = enabled ? 1 : 0;
+    return before;
+}
+
 extern "C" int64_t mae_mpd_workspace_bytes(int64_t B, int64_t D, int store_kl) {
     if (B < 2 || D < 1) return 0;
     const mae::Layout L = mae::make_layout(B, D);
-    return store_kl ? L.total : L.total_nokl;
+    return store_kl ? mae::kl_geom(L, B, 0, B).total : L.total_nokl;
 }
 
 extern "C" int64_t mae_mpd_workspace_bytes_rows(int64_t B, int64_t D, int64_t row0, int64_t nrows) {
@@ -978,6 +1013,32 @@ extern "C" int mae_mpd_fwd(void* workspace, int64_t workspace_bytes, int64_t B, 
                 (int)L.Bp, nullptr, nullptr, tcb, (int)kg.base);
         }
     };
+    if (g_mpd_tc && L.Bp >= kBigTileRows && L.Kp % kTcKC == 0 && L.Kp <= 512) {   // K = 2D <= 512: <= 192 accumulating MMAs
+        // tensor-core tiles (3xTF32 tcgen05.mma): one persistent CTA per SM
+        static const cudaError_t attr = cudaFuncSetAttribute(mpd_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                             FwdTcSmem::kBytes);
+        if (attr != cudaSuccess) return (int)attr;
+        const int T = kTcT;
+        const int tr0 = (int)(row0 / T);
+        const int ntr = (int)(ceil_div(row0 + nrows, T) - tr0);
+        const int ntc = (int)(L.Bp / T);
+        const int64_t ntiles = (int64_t)ntr * ntc;
+        const int grid = (int)(ntiles < sm_count() ? ntiles : sm_count());
+        launch_pdl(mpd_fwd_tc_kernel, dim3((unsigned)grid), dim3(kFwdTcThreads), (size_t)FwdTcSmem::kBytes, as_stream(stream),
+            at<float>(workspace, L.xp), at<float>(workspace, L.yp), at<float>(workspace, L.c), at<float>(workspace, L.l),
+            at<Hdr>(workspace, L.hdr), at<double>(workspace, L.part_fwd), (int)B, (int)L.Kp, (int)row0, (int)(row0 + nrows), tr0,
+            ntr, ntc, klp, full ? kltp : nullptr, (int)L.Bp, sumsq, S, 0, (int)kg.base);
+        if (store_kl && !full) {
+            const int tcb = (int)(kg.base / T), ntcb = (int)(kg.rows_pad / T), ntra = (int)(L.Bp / T);
+            const int64_t nt2 = (int64_t)ntra * ntcb;
+            const int grid2 = (int)(nt2 < sm_count() ? nt2 : sm_count());
+            mpd_fwd_tc_kernel<<<grid2, kFwdTcThreads, FwdTcSmem::kBytes, as_stream(stream)>>>(
+                at<float>(workspace, L.xp), at<float>(workspace, L.yp), at<float>(workspace, L.c), at<float>(workspace, L.l),
+                at<Hdr>(workspace, L.hdr), at<double>(workspace, L.part_fwd), (int)B, (int)L.Kp, 0, 0, 0, ntra, ntcb, nullptr, kltp,
+                (int)L.Bp, nullptr, nullptr, tcb, (int)kg.base);
+        }
+        return launch_status();
+    }
     const int tm_env = []() { const char* e = getenv("MAE_MPD_FWD_TM"); return e ? atoi(e) : 0; }();   // tuning only
     const int64_t small_limit = tm_env == 2 ? 1024 : (tm_env == 4 ? 256 : kSmallTileRows);
     if (L.Bp <= small_limit) launch(std::integral_constant<int, 2>{});   // small batches: 32 x 32 tiles, more CTAs, less latency
@@ -1026,6 +1087,31 @@ extern "C" int mae_mpd_bwd(const float* mu, int64_t mu_stride, const float* logv
         if (B > 256 && items <= 4096) launch(std::integral_constant<int, 8>{});
         else if (B > 96 && items <= 8192) launch(std::integral_constant<int, 4>{});
         else launch(std::integral_constant<int, 1>{});
+        return launch_status();
+    }
+    if (path == 3 && g_mpd_tc && kg.tc_split > 0) {
+        // tensor-core partner contractions (3xTF32 tcgen05.mma) + the closed-form finish
+        static const cudaError_t attr = cudaFuncSetAttribute(mpd_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                             BwdTcSmem::kBytes);
+        if (attr != cudaSuccess) return (int)attr;
+        const int tr0t = (int)(row0 / kTcT);
+        const int ntrt = (int)(ceil_div(row0 + nrows, kTcT) - tr0t);
+        const int ntc = (int)(L.Bp / kTcT);
+        const int nsplit = (int)kg.tc_split;
+        const int tps = (int)ceil_div(ntc, nsplit);
+        float* gp = at<float>(workspace, kg.gp_off);
+        float* rsp = at<float>(workspace, kg.rs_off);
+        dim3 grid((unsigned)ntrt, (unsigned)(L.Kp / kTcT), (unsigned)nsplit);
+        launch_pdl(mpd_bwd_tc_kernel, grid, dim3(kBwdTcThreads), (size_t)BwdTcSmem::kBytes, as_stream(stream),
+            at<float>(workspace, L.xp), at<float>(workspace, L.yp), at<Hdr>(workspace, L.hdr), (int)B, (int)L.Kp, (int)row0,
+            (int)(row0 + nrows), tr0t, ntc, tps, at<float>(workspace, kg.kl_off) - kg.base * L.Bp,
+            at<float>(workspace, kg.klt_off) - kg.base * L.Bp, (int)L.Bp, gp, rsp, (int)kg.rows_pad, (int)kg.base,
+            tc_group_chunks());
+        const int64_t n = nrows * D;
+        mpd_bwd_tc_finish_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, as_stream(stream)>>>(
+            mu, mu_stride, logvar, logvar_stride, at<float4>(workspace, L.vp), at<double>(workspace, L.colstats),
+            at<double>(workspace, L.pivots), g_m, g_S, S, gkl, (int)B, (int)D, (int)L.Kp, (int)row0, (int)nrows, nsplit, gp, rsp,
+            (int)kg.rows_pad, (int)kg.base, dmu, dlogvar, accumulate);
         return launch_status();
     }
     const int tr0 = (int)(row0 / kT);

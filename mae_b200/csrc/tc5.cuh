@@ -161,11 +161,13 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
 }
 
 // ---------------------------------------------------------------------------------------------------- 3xTF32 split
+// (hi and lo may alias v: the input is read before either is written)
 __device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
     uint32_t h, l;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
-    hi = __uint_as_float(h);
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(v - hi));
+    const float hf = __uint_as_float(h);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(v - hf));
+    hi = hf;
     lo = __uint_as_float(l);
 }
 

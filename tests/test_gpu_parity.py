@@ -154,6 +154,85 @@ def test_mpd_large_backward_vs_chunked_oracle(ops, O):
     assert ops._mpd_pick_path(b, d, 0) == 3
 
 
+@pytest.fixture
+def mpd_tc():
+    """switch the tensor-core MPD tiles on / off for one test (mae_set_mpd_tensor_cores), restoring the previous setting"""
+    from mae_b200 import _lib
+    lib = _lib.load()
+    prev = lib.mae_set_mpd_tensor_cores(1)
+    lib.mae_set_mpd_tensor_cores(prev)
+
+    def set_(on):
+        lib.mae_set_mpd_tensor_cores(1 if on else 0)
+
+    yield set_
+    lib.mae_set_mpd_tensor_cores(prev)
+
+
+@pytest.mark.parametrize("regime", ["random", "collapse", "offset"])
+def test_mpd_tensor_core_tiles_vs_chunked_oracle(ops, O, mpd_tc, regime):
+    """C5 tiles on the tensor cores (3xTF32 tcgen05.mma, csrc/mpd_tc.cuh; padded batch >= 2048, K = 2D a multiple of 128):
+    forward (m_d, S) and both backward paths against autograd through the row-chunked fp64 oracle, with the fp32 oracle as
+    the measure of what fp32 resolves; beside it the FP32 FFMA tiles on the same inputs.  Regimes: random posteriors,
+    posterior collapse (every posterior within 1e-3 of the same one: the reference's A + B - C - 1 cancels) and a common
+    offset of 30 sigma (hard part 3)."""
+    from mae_b200 import synth
+    b, d = 2304, 64
+    mu0, lv0 = synth.posterior_params(b, (d,), seed=31)
+    if regime == "collapse":
+        mu0, lv0 = 0.3 + 1e-3 * mu0, -0.5 + 1e-3 * lv0
+    elif regime == "offset":
+        mu0 = mu0 + 30.0
+    ref = {}
+    for key, dt in (("r64", torch.float64), ("r32", torch.float32)):
+        a, c = mu0.to(dt).clone().requires_grad_(), lv0.to(dt).clone().requires_grad_()
+        m_ref, s_ref = O.post_kl_chunked(a, c, rows_per_chunk=128)
+        (-0.7 * torch.nn.functional.logsigmoid(m_ref).sum() + 1.3 * s_ref).backward()
+        ref[key] = (m_ref.detach(), s_ref.detach(), a.grad, c.grad)
+    worst = {}
+    for tc in (1, 0):
+        mpd_tc(tc)
+        for path in (3, 2):
+            mu, lv = cu(mu0).requires_grad_(), cu(lv0).requires_grad_()
+            m_d, s = ops.mpd(mu, lv, bwd_path=path)
+            (-0.7 * torch.nn.functional.logsigmoid(m_d).sum() + 1.3 * s).backward()
+            got = (m_d, s, mu.grad, lv.grad)
+            for i, nm in enumerate(("m_d", "S", "dmu", "dlv")):
+                e = check_close(got[i], ref["r64"][i], ref["r32"][i], what="%s %s tc=%d path=%d" % (regime, nm, tc, path))
+                worst[(tc, nm)] = max(worst.get((tc, nm), 0.0), e)
+    print("MPD %s B=%d D=%d, error / tensor scale vs fp64: " % (regime, b, d)
+          + ", ".join("%s %s %.1e" % ("tensor" if tc else "FFMA", nm, e) for (tc, nm), e in sorted(worst.items())))
+
+
+def test_mpd_tensor_core_row_blocks(ops, mpd_tc):
+    """row blocks (the sharded decomposition) through the tensor-core tiles: partial sums add up to the full batch's, the
+    stored KL_ij / KL_ji rows of a block give the same own-row gradients as the full batch"""
+    from mae_b200 import synth
+    b, d = 2560, 64
+    mu0, lv0 = synth.posterior_params(b, (d,), seed=33)
+    mu, lv = cu(mu0).requires_grad_(), cu(lv0).requires_grad_()
+    mpd_tc(1)
+    m_full, s_full = ops.mpd(mu, lv, bwd_path=3)
+    (-torch.nn.functional.logsigmoid(m_full).sum() + s_full).backward()
+    parts = []
+    for r0, n in ((0, 640), (640, 1000), (1640, 920)):
+        m_p, ss, kl_all, state = ops.mpd_rows_forward(mu.detach(), lv.detach(), r0, n, full=False)
+        assert torch.equal(m_p, m_full.detach()) and state.path == 3
+        parts.append(ss.double())
+        ops._pool.give(state.ws)
+    tot = torch.stack(parts).sum()
+    s2 = ops.mpd_finalize(tot.reshape(1), b)
+    check_close(s2, s_full.detach().double(), rel=2e-6, what="S from row-block partial sums")
+    # own-row gradients of a block, upstream gradients as in the full run
+    g_m = -torch.sigmoid(-m_full.detach()).reshape(-1)
+    for r0, n in ((640, 1000),):
+        m_p, ss, kl_all, state = ops.mpd_rows_forward(mu.detach(), lv.detach(), r0, n, full=False)
+        state.s = s_full.detach().reshape(1)
+        dmu, dlv = ops.mpd_rows_backward(state, r0, n, g_m.contiguous(), torch.ones(1, device=DEV), None)
+        check_close(dmu, mu.grad[r0:r0 + n].double(), rel=1e-5, what="row-block dmu")
+        check_close(dlv, lv.grad[r0:r0 + n].double(), rel=1e-5, what="row-block dlv")
+
+
 def test_mpd_row_blocks_add_up_and_deterministic(ops):
     """sum of row-block partial sums == full sum (the multi-GPU decomposition); bitwise repeatability."""
     from mae_b200 import synth
