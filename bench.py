@@ -50,6 +50,15 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measured_bf16_tflops():
+    """sustained dense bf16 tensor throughput of this pool's B200s (MEASURED_PEAKS.json; fallback of the profiling guide)"""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["bf16_tflops_sustained"])
+    except Exception:
+        return 1400.0
+
+
 def ncu_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the benched kernel (dmol_bwd_kernel<10,1024,5,true>, 160
     threads) from the committed ncu --set full capture; None if no capture of THAT kernel is committed."""
@@ -471,6 +480,7 @@ def bench_ours(args):
         barrier()
         extra.update(bench_c4(dev, hbm_gbs, world))                       # every rank: its shard of the evaluation
         extra.update(bench_n2(dev, hbm_gbs, world))
+        extra.update(bench_n3(dev, world, rank))
         if peaks is not None and "c4_iw_nll_eval" in extra:
             extra["c4_iw_nll_eval"]["roofline"]["sfu_coroof"] = c4_sfu_coroof(peaks)
         ffma_peak = [peaks["ffma_tflops"] if peaks else 0.0]
@@ -481,6 +491,7 @@ def bench_ours(args):
         extra.update(bench_c5(dev, world, rank, dist_ctx, ffma_peak[0], quick=args.quick))
         if world == 1:
             extra.update(bench_c1(dev, hbm_gbs))
+            extra.update(bench_full_model(dev))
             extra["gpu_eager_baseline"] = gpu_eager_baseline(dev, value_ours=batch * args.steps / dt)
     out = None
     if rank == 0:
@@ -682,6 +693,103 @@ def bench_n2(dev, hbm_gbs, world=1):
     return res
 
 
+def bench_full_model(dev):
+    """The caller's view (experiments/color_image.py:153-160, binary_image.py:150-160): whole ``MAE.loss`` + backward of the two
+    shipped configurations (encoder / decoder conv stacks in PyTorch, loss head on this repo's kernels), eagerly and as one
+    CUDA graph (mae_b200.graph.capture_step).  Configurations come from tests/golden/models.pt (the reference's JSON files with
+    one replica and dropout 0), weights from synth.fill_state; batch sizes are the training scripts' defaults."""
+    import copy
+    from mae_b200 import graph, ops, synth
+    from mae_b200.modules import MAE
+    res = {}
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tests", "golden", "models.pt")
+    if not os.path.exists(path):
+        return {"full_model_step": {"unavailable": "tests/golden/models.pt not found"}}
+    fixtures = torch.load(path, weights_only=False)
+    stream = torch.cuda.current_stream()
+    for name, batch in (("binary_image_json", 100), ("color_image32x32_json", 64)):
+        try:
+            c = fixtures[name]
+            model = synth.fill_state(MAE.from_params(copy.deepcopy(c["params"]))).to(dev).train()
+            shape = (batch,) + tuple(c["x"].shape[1:])
+            g = torch.Generator(device=dev).manual_seed(17)
+            if shape[1] == 1:
+                x = (torch.rand(shape, device=dev, generator=g) < 0.2).float()
+            else:
+                x = torch.randint(0, 256, shape, device=dev, generator=g).float() / 127.5 - 1.0
+            args = dict(eta=1.0, gamma=1.0, free_bits=0.0)
+
+            def eager(i):
+                for p_ in model.parameters():
+                    p_.grad = None
+                model.loss(x, 1, **args)[0].backward()
+
+            n0 = ops.launch_count()
+            eager(0)
+            n_ours = ops.launch_count() - n0
+            t_eager = time_kernel(eager, 5, stream, 3)
+            step = graph.capture_step(model, x, 1, **args)
+            t_graph = time_kernel(lambda i: step(x), 10, stream, 3)
+            res["full_model_step_" + name] = {
+                "config": "%s, batch %d, nsamples 1, eta = gamma = 1: MAE.loss + backward (no optimizer)" % (name, batch),
+                "ms_eager": t_eager * 1e3, "ms_cuda_graph": t_graph * 1e3, "speedup_graph": t_eager / t_graph,
+                "samples_per_s_cuda_graph": batch / t_graph, "launches_of_ours_per_step": n_ours,
+                "parameters": sum(p_.numel() for p_ in model.parameters())}
+            del step, model
+            torch.cuda.empty_cache()
+        except Exception as e:      # never lose the headline line over a secondary workload
+            res["full_model_step_" + name] = {"error": "%s: %s" % (type(e).__name__, str(e)[:200])}
+    return res
+
+
+def bench_n3(dev, world, rank):
+    """N3: ``evaluate.calc_nll`` - the reference's test loop (experiments/color_image.py:252-277: one image per
+    MAE.nll call) batched (8 images x K = 512 per call), sharded over ranks with one final all-reduce, the per-batch body
+    replayed as a CUDA graph - through a REAL decoder: the ResNet colour configuration of tests/golden/models.pt (ResNet
+    encoder / decoder conv stacks in PyTorch, last 1x1 convolution fused into the likelihood kernel).  A bounded sample of 64
+    images per rank; the figure includes the final all-reduce and the host read of the result."""
+    import copy
+    import torch.distributed as dist
+    from mae_b200 import evaluate, synth
+    from mae_b200.modules import MAE
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tests", "golden", "models.pt")
+    if not os.path.exists(path):
+        return {"n3_calc_nll": {"unavailable": "tests/golden/models.pt not found"}}
+    try:
+        c = torch.load(path, weights_only=False)["color_resnet"]
+        model = synth.fill_state(MAE.from_params(copy.deepcopy(c["params"]))).to(dev)
+        per_rank, k = 64, 512
+        g = torch.Generator().manual_seed(23)
+        data = torch.randint(0, 256, (per_rank * world, 3, 32, 32), generator=g).float() / 127.5 - 1.0
+        head = None
+        if world > 1:
+            from mae_b200.distributed import ShardedHead
+            head = ShardedHead(check_every=0, overlap=False)
+        out = {}
+        for label, use_graph in (("eager", False), ("cuda_graph", True)):
+            evaluate.calc_nll(model, data[:24 * world], k, images_per_step=8, sharded=head, cuda_graph=use_graph)    # warm-up
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            res = evaluate.calc_nll(model, data, k, images_per_step=8, sharded=head, cuda_graph=use_graph)
+            torch.cuda.synchronize()
+            t = time.perf_counter() - t0
+            if world > 1:
+                tt = torch.tensor([t], device=dev, dtype=torch.float64)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                t = float(tt)
+            out[label] = {"images_per_s": per_rank * world / t, "s": t, "bits_per_dim": res[2]}
+        return {"n3_calc_nll": {
+            "metric": "calc_nll_images_per_s", "value": out["cuda_graph"]["images_per_s"], "unit": "images/s", "n_gpus": world,
+            "config": "ResNet colour MAE (tests/golden/models.pt color_resnet), K = 512, 8 images per MAE.nll call, %d images per rank, "
+                      "wall clock incl. the final all-reduce and host read" % per_rank,
+            "eager_images_per_s": out["eager"]["images_per_s"], "graph_speedup": out["eager"]["s"] / out["cuda_graph"]["s"],
+            "bits_per_dim": out["cuda_graph"]["bits_per_dim"]}}
+    except Exception as e:
+        return {"n3_calc_nll": {"error": "%s: %s" % (type(e).__name__, str(e)[:200])}}
+
+
 def bench_c1(dev, hbm_gbs):
     """C1/C2 (binary head, B = 100, D = 64): launch-latency-bound (1.57 MB / 10 MFLOP per step)."""
     from mae_b200 import heads, ops, synth
@@ -779,11 +887,25 @@ def bench_c5(dev, world, rank, dist_ctx, ffma_peak_tflops, quick=False):
                                             if extra <= ops.MPD_KL_BUDGET_BYTES else "recompute backward")
         else:
             path = "stored-KL backward" if ops._mpd_pick_path(b5, d5, 0) != 2 else "recompute backward"
-        res["c5_mpd_b%d_d%d" % (b5, d5)] = {
-            "metric": "mpd_fwd_bwd_pairs_per_s", "value": b5 * b5 / t, "unit": "pairs/s", "n_gpus": world, "scaling": "strong",
-            "ms": t * 1e3, "tflops_algorithmic": flop / t / 1e12, "path": path,
-            "roofline": {"bound": "fp32 ffma", "peak_tflops_measured": ffma_peak_tflops * world,
-                         "frac": (flop / t / 1e12 / (ffma_peak_tflops * world)) if ffma_peak_tflops > 0 else None}}
+        # tensor-core tiles (3xTF32 tcgen05.mma, csrc/mpd_tc.cuh) serve padded batches >= 2048 with K = 2D a multiple of 128, <= 512
+        tc_prev = ops._lib_().mae_set_mpd_tensor_cores(1)
+        ops._lib_().mae_set_mpd_tensor_cores(tc_prev)
+        tensor = bool(tc_prev) and b5 >= 2048 and (2 * d5) % 128 == 0 and 2 * d5 <= 512 and "stored" in path
+        entry = {"metric": "mpd_fwd_bwd_pairs_per_s", "value": b5 * b5 / t, "unit": "pairs/s", "n_gpus": world, "scaling": "strong",
+                 "ms": t * 1e3, "tflops_algorithmic": flop / t / 1e12, "path": path + (", tensor-core tiles (3xTF32 tcgen05)" if tensor else ", FP32 FFMA tiles")}
+        if tensor:
+            # executed tensor work: 3 tf32 products per algorithmic product; forward 2 B^2 D MACs (x2 for a row block's transposed
+            # pass), stored-KL backward 4 B^2 D MACs.  tf32 dense peak = half the measured bf16 peak (MEASURED_PEAKS.json).
+            macs = (2.0 * (2 if world > 1 else 1) + 4.0) * b5 * b5 * d5
+            tf32_peak = 0.5 * measured_bf16_tflops() * world
+            entry["roofline"] = {"bound": "tf32 tensor (3xTF32)", "tensor_tflops_executed": 3 * 2 * macs / t / 1e12,
+                                 "peak_tflops": tf32_peak, "peak_source": "0.5 x measured bf16 dense (MEASURED_PEAKS.json)",
+                                 "frac": 3 * 2 * macs / t / 1e12 / tf32_peak,
+                                 "vs_ffma_peak": (flop / t / 1e12 / (ffma_peak_tflops * world)) if ffma_peak_tflops > 0 else None}
+        else:
+            entry["roofline"] = {"bound": "fp32 ffma", "peak_tflops_measured": ffma_peak_tflops * world,
+                                 "frac": (flop / t / 1e12 / (ffma_peak_tflops * world)) if ffma_peak_tflops > 0 else None}
+        res["c5_mpd_b%d_d%d" % (b5, d5)] = entry
         del enc, mu5, lv5
         torch.cuda.empty_cache()
     if head is not None:

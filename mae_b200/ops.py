@@ -469,6 +469,7 @@ def mpd_rows_forward(mu_all: torch.Tensor, logvar_all: torch.Tensor, row0: int, 
         if store:
             _count()      # the transposed tile pass
     state = MpdRowsState(ws, mu2, ms, lv2, ls, b, d, s if full else None, path)
+    state.outs = outs       # the tile kernel writes its fp64 sum into outs[2]: alive as long as the state (side-stream callers)
     return m_d, (s if full else sumsq), kl_all, state
 
 
@@ -1252,7 +1253,11 @@ def kl_mpd_reg(mu: torch.Tensor, logvar: torch.Tensor, eta: float, gamma: float,
                                         grads[1].data_ptr() if want_grad else None, state.path, _stream()), "mae_mpd_loss_bwd")
         _count(2 if want_grad else 1)
         _pool.give(ws)
-    return kl, m_d.view(mu.shape[1:]), s_, reg, grads, (mu2, lv2)
+    # ``keep``: every buffer the launch stream's kernels touch that is not among the results (the tile kernel writes its fp64
+    # sum into outs[2]).  The caller must hold it until the launch stream has been joined: a block freed earlier goes back to
+    # the CURRENT stream's free list and is handed to the next small allocation (e.g. a weight-norm temporary of the decoder)
+    # while the side-stream kernel that writes it is still pending.
+    return kl, m_d.view(mu.shape[1:]), s_, reg, grads, (mu2, lv2, outs)
 
 
 class _EncodeHead(torch.autograd.Function):
@@ -1287,8 +1292,8 @@ class _EncodeHead(torch.autograd.Function):
                                                   z.data_ptr(), None, _stream()), "mae_reparam_kl_fwd")
             _count()
 
-        kl, m_d, s, reg, grads, _ = kl_mpd_reg(mu2, lv2, eta, gamma, free_bits, None if with_kl else 0.0, want_grad,
-                                               launch_stream=ss)
+        kl, m_d, s, reg, grads, keep = kl_mpd_reg(mu2, lv2, eta, gamma, free_bits, None if with_kl else 0.0, want_grad,
+                                                  launch_stream=ss)
         m_d = m_d.view(mu.shape[1:])
         if z_side:
             # the caller's next main-stream kernel does not consume z (heads.*: the decoder output is an input): z is
@@ -1302,7 +1307,7 @@ class _EncodeHead(torch.autograd.Function):
         ev.record(ss)
         if z_side:
             holder["z_event"] = ev
-        _pending_join[idx] = (ev, (prev, kl, m_d, s, reg, grads, mu2, lv2, z, eps_c))
+        _pending_join[idx] = (ev, (prev, kl, m_d, s, reg, grads, mu2, lv2, z, eps_c, keep))
         if not z_side:
             reparam()
         ctx.save_for_backward(mu2, lv2, eps_c)

@@ -37,3 +37,20 @@ def golden():
         return cache[name]
 
     return load
+
+
+def pytest_terminal_summary(terminalreporter):
+    """element-wise relative errors recorded by tolerance.check_close (entries with |ref| >= 1e-3 of the tensor scale)"""
+    try:
+        import tolerance
+    except ImportError:
+        return
+    rows = sorted(tolerance.ELEMENTWISE, reverse=True)[:12]
+    if not rows:
+        return
+    terminalreporter.write_line("")
+    terminalreporter.write_line("element-wise relative error of the %d checked tensors (entries >= 1e-3 of the tensor scale): worst 12"
+                                % len(tolerance.ELEMENTWISE))
+    terminalreporter.write_line("   max elementwise   99.9 %         norm-wise    tensor")
+    for mx, q, nw, what in rows:
+        terminalreporter.write_line("   %.2e          %.2e      %.2e     %s" % (mx, q, nw, what[:90]))

@@ -233,3 +233,62 @@ def test_sharded_model_gradients_all_reduced(tmp_path, world, flows):
     print("sharded MAE.loss world=%d flows=%s: worst parameter-gradient error %.1e of the parameter's own scale "
           "(parameters above 1e-3 of the largest gradient), %.1e of the largest gradient (all parameters)"
           % (world, flows, worst, worst_global))
+
+
+# ------------------------------------------------------------------------------------------------- N3: sharded evaluation
+def _nll_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        import stubs
+        from mae_b200 import distributed as D, evaluate
+        from mae_b200.modules import MAE, GaussianEncoder
+        torch.manual_seed(0)
+        model = MAE(GaussianEncoder(stubs.LinearCore(48, 6, True)), stubs.ColorLinearDecoder(6, 3, 4, 4)).to(dev)
+        data = torch.rand(23, 3, 4, 4, generator=torch.Generator().manual_seed(2)) * 2 - 1
+        k = 32
+        noise = torch.randn(23, k, 6, generator=torch.Generator().manual_seed(1))     # one row of noise per IMAGE
+        head = D.ShardedHead()
+        lo, hi = head.shard(23)
+        cursor = {"i": lo}
+
+        def draw(mu, ns):
+            b = mu.size(0)
+            e = noise[cursor["i"]:cursor["i"] + b]
+            cursor["i"] += b
+            return e.to(mu.device)
+
+        GaussianEncoder._draw_eps = staticmethod(draw)
+        got = evaluate.calc_nll(model, data, k, images_per_step=4, sharded=head)
+        res = {"got": got, "shard": (lo, hi)}
+        if rank == 0:
+            cursor["i"] = 0
+            res["ref"] = evaluate.calc_nll(model, data, k, images_per_step=4)
+        torch.save(res, out % rank)
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_calc_nll_two_gpus(tmp_path):
+    """evaluate.calc_nll with a ShardedHead (images split over ranks, one final all-reduce) == the single-GPU evaluation of
+    all images under the same per-image noise; every rank returns the global averages
+    (experiments/color_image.py:252-277 is the loop being sharded)."""
+    world = 2
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    import torch.multiprocessing as mp
+    out = str(tmp_path / "n%d.pt")
+    mp.spawn(_nll_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    res = [torch.load(out % r, weights_only=False) for r in range(world)]
+    flat = lambda r: (r[0][0], r[0][1], r[0][2], r[1], r[2])
+    ref = flat(res[0]["ref"])
+    assert res[0]["shard"][1] == res[1]["shard"][0] and res[1]["shard"][1] == 23
+    for r in range(world):
+        for a, b in zip(flat(res[r]["got"]), ref):
+            assert abs(a - b) <= 2e-6 * max(1.0, abs(b)), (r, a, b)

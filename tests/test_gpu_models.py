@@ -113,3 +113,22 @@ def test_batched_calc_nll_equals_per_image_loop(monkeypatch):
     for a, b in ((e1, e3), (r1, r3), (k1, k3), (iw1, iw3), (bpd1, bpd3)):
         assert abs(a - b) <= 1e-5 * max(1.0, abs(a)), (a, b)
     assert model.training
+
+
+def test_calc_nll_cuda_graph_equals_eager(monkeypatch):
+    """evaluate.calc_nll(cuda_graph=True): the captured per-batch body (decoder, log densities, fused IW kernel, running
+    sums) replayed over the full batches + the eager ragged tail == the eager loop.  Noise is pinned to zero so that both
+    see the same samples (a replay draws fresh Philox noise otherwise)."""
+    import stubs
+    from mae_b200 import evaluate
+    from mae_b200.modules import MAE, GaussianEncoder
+    torch.manual_seed(0)
+    model = MAE(GaussianEncoder(stubs.LinearCore(48, 6, True)), stubs.ColorLinearDecoder(6, 3, 4, 4)).to(DEV)
+    data = torch.rand(26, 3, 4, 4) * 2 - 1
+    k = 16
+    monkeypatch.setattr(GaussianEncoder, "_draw_eps", staticmethod(lambda mu, ns: mu.new_zeros(mu.size(0), ns, *mu.shape[1:])))
+    ref = evaluate.calc_nll(model, data, k, images_per_step=4)
+    got = evaluate.calc_nll(model, data, k, images_per_step=4, cuda_graph=True)
+    flat = lambda r: (r[0][0], r[0][1], r[0][2], r[1], r[2])
+    for a, b in zip(flat(got), flat(ref)):
+        assert abs(a - b) <= 1e-6 * max(1.0, abs(b)), (a, b)
