@@ -22,6 +22,8 @@ oracle standing in for the CUDA kernels.
 """
 from __future__ import annotations
 
+import os
+
 from typing import Optional
 
 import torch
@@ -32,6 +34,10 @@ SMALL_GLOBAL_BATCH = 2048   # <= : every rank evaluates the whole MPD forward re
 # (C5: up to 16 MB per rank) are bandwidth-bound and go through the library all-gather.
 PEER_SLOT_FLOATS = 1 << 18
 ROWS_SLOT_FLOATS = 64 * 128      # one-launch sharded regulariser: b_loc <= 64 rows of 2 D <= 128 floats
+# Largest world size that takes the one-launch exchange + regulariser kernel (mae_kl_mpd_rows_fused).  Measured on one box
+# (C3 step, batch 64 per GPU): world 2 43.6-45.7 us vs 46-48 us for gather -> cluster kernel, world 4 54.5 vs 56 us, but
+# world 8 68.5 us vs 60.5 us for the gather -> prepare -> tiles -> backward chain: its 16 CTAs then serve 512 global rows.
+ROWS_CLUSTER_MAX_WORLD = int(os.environ.get("MAE_ROWS_CLUSTER_MAX_WORLD", "4"))
 
 
 def _packed_parent(mu, logvar, b_loc, d):
@@ -273,6 +279,8 @@ class ShardedHead:
         depends on shapes, on the collectively created buffers and on the ``rows_cluster`` switch only)."""
         eng = self.engine
         if not (self.rows_cluster and self.use_p2p and like.is_cuda and self.world > 1 and hasattr(eng, "reg_rows_cluster")):
+            return False
+        if self.world > ROWS_CLUSTER_MAX_WORLD:
             return False
         if (b_loc * 2 * d) % 4 != 0 or b_loc * 2 * d > ROWS_SLOT_FLOATS or not eng.rows_cluster_supported(self.world, b_loc, d, like.device):
             return False

@@ -92,7 +92,7 @@ def post_kl_chunked(mu: torch.Tensor, logvar: torch.Tensor, rows_per_chunk: int 
     nb, nd = mu.shape
     var = logvar.exp()
     denom = var + EPS
-    acc_d = torch.zeros(nd, dtype=torch.float64)
+    acc_d = torch.zeros(nd, dtype=torch.float64, device=mu.device)
     row_totals = []
     for r0 in range(0, nb, rows_per_chunk):
         r1 = min(nb, r0 + rows_per_chunk)
@@ -100,14 +100,14 @@ def post_kl_chunked(mu: torch.Tensor, logvar: torch.Tensor, rows_per_chunk: int 
         gap = (mu[r0:r1, None, :] - mu[None, :, :]).pow(2) / denom[None, :, :]
         lgap = logvar[r0:r1, None, :] - logvar[None, :, :]
         pair = (ratio + gap - lgap - 1) * 0.5
-        idx = torch.arange(r0, r1)
+        idx = torch.arange(r0, r1, device=mu.device)
         pair[idx - r0, idx, :] = 0.0
         acc_d += pair.sum(dim=(0, 1))
         row_totals.append(pair.sum(dim=2))
     cc = nb / (nb - 1.0)
     m_d = acc_d / float(nb * nb) * cc
     total = torch.cat(row_totals, dim=0)
-    total = total + torch.eye(nb, dtype=torch.float64) * m_d.sum()
+    total = total + torch.eye(nb, dtype=torch.float64, device=mu.device) * m_d.sum()
     dd = math.sqrt((nb ** 2 - 1) / (nb ** 2 - nb - 1.0))
     return m_d, total.std() * dd
 

@@ -63,6 +63,8 @@ def _worker(rank, world, port, case, small_limit, rows_cluster, out):
         from mae_b200 import distributed as D, heads
         if small_limit is not None:
             D.SMALL_GLOBAL_BATCH = small_limit
+        if rows_cluster:
+            D.ROWS_CLUSTER_MAX_WORLD = world  # the one-launch kernel is a policy choice up to world 4; test it at every size
         head = D.ShardedHead(check_equal_batches=True)
         head.rows_cluster = rows_cluster      # False: peer gather + cluster / general kernel chain (row0 != 0)
         kind, b_loc, d, (mu_g, lv_g, eps_g, dec_g, x_g) = _case_inputs(case, world)
@@ -113,7 +115,11 @@ def _run(tmp_path, world, case, small_limit=None, rows_cluster=True):
         sl = slice(r * b_loc, (r + 1) * b_loc)
         for rep in ("rep0", "rep1"):
             got = res[r][rep]
-            for key, rel in (("loss", 2e-6), ("dmu", 1e-5), ("dlv", 1e-5), ("ddec", 1e-6), ("kl", 1e-6), ("recon", 1e-6)):
+            # ddec / recon: a rank evaluates its 64 images with the training-shape DMOL kernel (components split over 5 warps),
+            # the single-GPU reference on world * 64 images picks the variant for its pixel count (2 warps / vectorised at
+            # world >= 4): the same arithmetic in a different association, i.e. fp32 rounding (measured 7.7e-7 / 1.0e-6 /
+            # 1.7e-6 of the tensor scale at world 2 / 4 / 8), well inside north_star's 1e-5
+            for key, rel in (("loss", 2e-6), ("dmu", 1e-5), ("dlv", 1e-5), ("ddec", 5e-6), ("kl", 1e-6), ("recon", 5e-6)):
                 want = ref[key] if key == "loss" else ref[key][sl]
                 e = check_close(got[key], want.double(), rel=rel, what="world %d %s rank %d %s %s" % (world, case, r, rep, key))
                 worst[key] = max(worst.get(key, 0.0), e)
