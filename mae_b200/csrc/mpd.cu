@@ -77,6 +77,7 @@ struct Layout {
     int64_t Bp, Kp, nblk;
     int64_t prep_rows, prep_grid;  // rows per CTA / CTAs of mpd_prepare_kernel
     int64_t hdr, colstats, pivots, c, l, xp, yp, vp, part_prep, part_fwd, lossg, kl, klt, total, total_nokl;
+    int64_t tp, tp_mat;   // tensor-core path: 8 tiled, pre-split panel copies of tp_mat floats each (0: not eligible)
 };
 
 constexpr int64_t kBigTileRows = 2048;  // padded batch from which the forward uses 128 x 128 tiles
@@ -112,6 +113,8 @@ Layout make_layout(int64_t B, int64_t D) {
     L.part_prep = take(L.prep_grid * kStats * D * 8);
     L.part_fwd = take(kMaxFwdCtas * 8);
     L.lossg = take((D + B + 8) * 4);   // mae_mpd_loss_bwd: g_m[D] | g_S | pad[7] | gkl[B]
+    L.tp_mat = (L.Bp >= kBigTileRows && L.Kp % 32 == 0 && L.Kp <= 512) ? L.Bp * L.Kp : 0;   // see mpd_tc.cuh
+    L.tp = take(8 * L.tp_mat * 4);
     L.total_nokl = off;           // everything the forward needs when the KL tiles are not kept
     L.kl = take(L.Bp * L.Bp * 4);  // optional tail: KL[Bp][Bp] and its transpose (stored-KL backward paths)
     L.klt = take(L.Bp * L.Bp * 4);
@@ -919,7 +922,7 @@ KlGeom kl_geom(const Layout& L, int64_t B, int64_t row0, int64_t nrows) {
     g.total = g.klt_off + round_up(g.rows_pad * L.Bp * 4, 256);
     g.tc_split = 0;
     g.gp_off = g.rs_off = g.total;
-    if (L.Bp >= kBigTileRows && L.Kp % 128 == 0 && L.Kp <= 512) {
+    if (L.tp_mat > 0 && L.Kp % 128 == 0) {
         g.tc_split = tc_splits(g.rows_pad / 128, L.Kp / 128, L.Bp / 128);
         g.gp_off = g.total;
         g.rs_off = g.gp_off + round_up(2 * g.tc_split * g.rows_pad * L.Kp * 4, 256);
@@ -973,6 +976,13 @@ extern "C" int mae_mpd_prepare(const float* mu, int64_t mu_stride, const float* 
         at<float4>(workspace, L.vp), at<float>(workspace, L.c), at<float>(workspace, L.l), at<double>(workspace, L.part_prep),
         at<double>(workspace, L.colstats), at<double>(workspace, L.pivots), at<Hdr>(workspace, L.hdr), m_d, kl,
         0.5 / ((double)B * ((double)B - 1.0)));
+    if (g_mpd_tc && L.tp_mat > 0) {
+        // tensor-core tiles: pre-split copies of the panels in the K-major canonical tile layout (mpd_tc.cuh)
+        const int64_t n = L.Bp * (L.Kp / 4);
+        mpd_tile_panels_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, as_stream(stream)>>>(
+            at<float>(workspace, L.xp), at<float>(workspace, L.yp), (int)L.Bp, (int)L.Kp, at<float>(workspace, L.tp), L.tp_mat,
+            L.Kp % 128 == 0 ? 1 : 0);
+    }
     return launch_status();
 }
 
@@ -1013,7 +1023,7 @@ extern "C" int mae_mpd_fwd(void* workspace, int64_t workspace_bytes, int64_t B, 
                 (int)L.Bp, nullptr, nullptr, tcb, (int)kg.base);
         }
     };
-    if (g_mpd_tc && L.Bp >= kBigTileRows && L.Kp % kTcKC == 0 && L.Kp <= 512) {   // K = 2D <= 512: <= 192 accumulating MMAs
+    if (g_mpd_tc && L.tp_mat > 0) {   // padded batch >= 2048, K = 2D <= 512 (<= 192 accumulating MMAs)
         // tensor-core tiles (3xTF32 tcgen05.mma): one persistent CTA per SM
         static const cudaError_t attr = cudaFuncSetAttribute(mpd_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                              FwdTcSmem::kBytes);
@@ -1025,7 +1035,7 @@ extern "C" int mae_mpd_fwd(void* workspace, int64_t workspace_bytes, int64_t B, 
         const int64_t ntiles = (int64_t)ntr * ntc;
         const int grid = (int)(ntiles < sm_count() ? ntiles : sm_count());
         launch_pdl(mpd_fwd_tc_kernel, dim3((unsigned)grid), dim3(kFwdTcThreads), (size_t)FwdTcSmem::kBytes, as_stream(stream),
-            at<float>(workspace, L.xp), at<float>(workspace, L.yp), at<float>(workspace, L.c), at<float>(workspace, L.l),
+            at<float>(workspace, L.tp), L.tp_mat, at<float>(workspace, L.c), at<float>(workspace, L.l),
             at<Hdr>(workspace, L.hdr), at<double>(workspace, L.part_fwd), (int)B, (int)L.Kp, (int)row0, (int)(row0 + nrows), tr0,
             ntr, ntc, klp, full ? kltp : nullptr, (int)L.Bp, sumsq, S, 0, (int)kg.base);
         if (store_kl && !full) {
@@ -1033,7 +1043,7 @@ extern "C" int mae_mpd_fwd(void* workspace, int64_t workspace_bytes, int64_t B, 
             const int64_t nt2 = (int64_t)ntra * ntcb;
             const int grid2 = (int)(nt2 < sm_count() ? nt2 : sm_count());
             mpd_fwd_tc_kernel<<<grid2, kFwdTcThreads, FwdTcSmem::kBytes, as_stream(stream)>>>(
-                at<float>(workspace, L.xp), at<float>(workspace, L.yp), at<float>(workspace, L.c), at<float>(workspace, L.l),
+                at<float>(workspace, L.tp), L.tp_mat, at<float>(workspace, L.c), at<float>(workspace, L.l),
                 at<Hdr>(workspace, L.hdr), at<double>(workspace, L.part_fwd), (int)B, (int)L.Kp, 0, 0, 0, ntra, ntcb, nullptr, kltp,
                 (int)L.Bp, nullptr, nullptr, tcb, (int)kg.base);
         }
@@ -1103,7 +1113,7 @@ extern "C" int mae_mpd_bwd(const float* mu, int64_t mu_stride, const float* logv
         float* rsp = at<float>(workspace, kg.rs_off);
         dim3 grid((unsigned)ntrt, (unsigned)(L.Kp / kTcT), (unsigned)nsplit);
         launch_pdl(mpd_bwd_tc_kernel, grid, dim3(kBwdTcThreads), (size_t)BwdTcSmem::kBytes, as_stream(stream),
-            at<float>(workspace, L.xp), at<float>(workspace, L.yp), at<Hdr>(workspace, L.hdr), (int)B, (int)L.Kp, (int)row0,
+            at<float>(workspace, L.tp), L.tp_mat, at<Hdr>(workspace, L.hdr), (int)B, (int)L.Kp, (int)row0,
             (int)(row0 + nrows), tr0t, ntc, tps, at<float>(workspace, kg.kl_off) - kg.base * L.Bp,
             at<float>(workspace, kg.klt_off) - kg.base * L.Bp, (int)L.Bp, gp, rsp, (int)kg.rows_pad, (int)kg.base,
             tc_group_chunks());

@@ -6,11 +6,12 @@
 // accumulation in TMEM; tc5.cuh).  Included by mpd.cu inside namespace mae::{anonymous} (shares Hdr / Layout).
 //
 // Both kernels are warp-specialised, one persistent CTA per SM:
-//   A side     thread = tile row = TMEM lane: loads its 128 contiguous bytes of the chunk from global (L2-resident panels or
-//              the stored KL rows), splits, tcgen05.st into a TMEM operand stage -> the tensor core reads only B from smem
-//              (with K = 8 per tf32 instruction an SS-mode MMA re-reads 8 KB of operands per 64 cycles: the shared-memory
-//              bandwidth, measured in dmol_head.cu)
-//   B side     loads + splits the column panel chunk into the K-major canonical shared-memory layout
+//   A side     thread = tile row = TMEM lane: loads its part of the chunk from global (the pre-split tiled panel, or the stored
+//              KL rows which it turns into weights and splits), tcgen05.st into a TMEM operand stage -> the tensor core
+//              reads only B from smem (with K = 8 per tf32 instruction an SS-mode MMA re-reads 8 KB of operands per 64
+//              cycles: the shared-memory bandwidth, measured in dmol_head.cu)
+//   B side     one thread: cp.async.bulk of the chunk's 16 KB halves from the tiled panels (written by
+//              mpd_tile_panels_kernel already split and already in the K-major canonical shared-memory layout)
 //   MMA        one thread: 3 tcgen05.mma (128 x 128 x 8) per k-step, tcgen05.commit -> mbarriers
 //   epilogue   thread = row: tcgen05.ld of the accumulator, KL / weights arithmetic, stores
 #pragma once
@@ -20,26 +21,67 @@
 constexpr int kTcT = 128;            // tile edge (rows = TMEM lanes, columns = MMA N)
 constexpr int kTcKC = 32;            // contraction elements per pipeline stage
 constexpr int kTcLbo = 16 * 128;     // canonical layout: 128 rows x 16 B per k-group
-constexpr int kTcStageB = 2 * kTcT * kTcKC * 4;   // B_hi | B_lo of one stage
-constexpr int kTcStages = 2;
+constexpr int kTcHalf = kTcT * kTcKC * 4;         // one of hi / lo of an operand chunk: 16 KB, contiguous in the tiled panels
+constexpr int kTcStageB = 2 * kTcHalf;            // B_hi | B_lo of one stage
 
+// Tiled, pre-split copies of the panels (workspace region L.tp, 8 matrices of Bp x Kp floats; written once per forward by
+// mpd_tile_panels_kernel, read by both tensor-core kernels).  "Row" tilings 0..3 = X_hi, X_lo, Y_hi, Y_lo hold element
+// (row r, k) at  ((r / 128 * (Kp / 4) + k / 4) * 128 + r % 128) * 4 + k % 4 : a chunk of 32 k of a 128-row tile is 16 KB of
+// CONTIGUOUS memory that already is the K-major canonical UMMA layout (one cp.async.bulk per operand half, or coalesced
+// 16-byte loads with thread = row).  "Partner" tilings 4..7 = Y_hi, Y_lo, X_hi, X_lo hold element (n = k, K = partner j) of
+// the backward's B operands at  ((((j / 128 * (Kp / 128) + k / 128) * 32 + j % 128 / 4) * 128 + k % 128) * 4 + j % 4 : a chunk
+// of 32 partners x 128 gradient columns is again 16 KB contiguous in canonical layout.
+__global__ void __launch_bounds__(256)
+mpd_tile_panels_kernel(const float* __restrict__ Xp, const float* __restrict__ Yp, int Bp, int Kp, float* __restrict__ tp,
+                       int64_t mat, int with_partner) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int kq = Kp / 4;
+    if (idx >= (int64_t)Bp * kq) return;
+    const int r = (int)(idx % Bp), g = (int)(idx / Bp);      // consecutive threads: consecutive rows -> coalesced stores
+    const float4 x = *reinterpret_cast<const float4*>(Xp + (int64_t)r * Kp + 4 * g);
+    const float4 y = *reinterpret_cast<const float4*>(Yp + (int64_t)r * Kp + 4 * g);
+    float4 xh, xl, yh, yl;
+    tc5::split_tf32(x.x, xh.x, xl.x); tc5::split_tf32(x.y, xh.y, xl.y); tc5::split_tf32(x.z, xh.z, xl.z); tc5::split_tf32(x.w, xh.w, xl.w);
+    tc5::split_tf32(y.x, yh.x, yl.x); tc5::split_tf32(y.y, yh.y, yl.y); tc5::split_tf32(y.z, yh.z, yl.z); tc5::split_tf32(y.w, yh.w, yl.w);
+    const int64_t o = (((int64_t)(r / 128) * kq + g) * 128 + r % 128) * 4;
+    *reinterpret_cast<float4*>(tp + 0 * mat + o) = xh;
+    *reinterpret_cast<float4*>(tp + 1 * mat + o) = xl;
+    *reinterpret_cast<float4*>(tp + 2 * mat + o) = yh;
+    *reinterpret_cast<float4*>(tp + 3 * mat + o) = yl;
+    if (with_partner) {
+        const int nc = (4 * g) / 128, kk = (4 * g) % 128;
+        const int64_t ob = ((((int64_t)(r / 128) * (Kp / 128) + nc) * 32 + (r % 128) / 4) * 128 + kk) * 4 + r % 4;
+        const float yhv[4] = {yh.x, yh.y, yh.z, yh.w}, ylv[4] = {yl.x, yl.y, yl.z, yl.w};
+        const float xhv[4] = {xh.x, xh.y, xh.z, xh.w}, xlv[4] = {xl.x, xl.y, xl.z, xl.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            tp[4 * mat + ob + 4 * e] = yhv[e];
+            tp[5 * mat + ob + 4 * e] = ylv[e];
+            tp[6 * mat + ob + 4 * e] = xhv[e];
+            tp[7 * mat + ob + 4 * e] = xlv[e];
+        }
+    }
+}
+
+constexpr int kFwdAStages = 3;       // TMEM operand stages (A = x~ rows)
+constexpr int kFwdBStages = 4;       // shared-memory stages (B = y~ rows, filled by the bulk-copy engine)
 struct FwdTcSmem {
     static constexpr int kBOff = 0;
-    static constexpr int kFOff = kTcStages * kTcStageB;            // f_j of the current tile, one copy per epilogue warpgroup
+    static constexpr int kFOff = kFwdBStages * kTcStageB;          // f_j of the current tile, one copy per epilogue warpgroup
     static constexpr int kBarOff = kFOff + 2 * kTcT * 4;
-    static constexpr int kNumBars = 3 * kTcStages + 4;             // afull, bfull, sempty per stage; tfull, tempty per accumulator
+    static constexpr int kNumBars = 2 * kFwdAStages + 2 * kFwdBStages + 4;
     static constexpr int kSlotOff = kBarOff + kNumBars * 8;
     static constexpr int kRedOff = kSlotOff + 16;
     static constexpr int kBytes = kRedOff + 8 * 8 + 16;
 };
-constexpr int kFwdTcThreads = (8 + 4 + 4 + 1) * 32;   // 2 epilogue warpgroups, A producer, B producer, MMA warp
+constexpr int kFwdTcThreads = (8 + 8 + 1 + 1) * 32;   // 2 epilogue warpgroups, 2 A warpgroups, MMA warp, loader warp
 
 // TMEM columns: accumulators at 0 and 128, A operand stages (hi | lo, kTcKC columns each) behind them
 constexpr int kFwdTcACol = 256;
 constexpr int kFwdTcTmemCols = 512;
 
 __global__ void __launch_bounds__(kFwdTcThreads, 1)
-mpd_fwd_tc_kernel(const float* __restrict__ Xp, const float* __restrict__ Yp, const float* __restrict__ evec,
+mpd_fwd_tc_kernel(const float* __restrict__ tp, int64_t mat, const float* __restrict__ evec,
                   const float* __restrict__ fvec, Hdr* hdr, double* part, int B, int Kp, int row0, int row1, int tr0, int ntr,
                   int ntc, float* __restrict__ KL, float* __restrict__ KLT, int Bp, double* __restrict__ sumsq_out,
                   float* __restrict__ S_out, int tc0, int kl_base) {
@@ -48,9 +90,10 @@ mpd_fwd_tc_kernel(const float* __restrict__ Xp, const float* __restrict__ Yp, co
     uint8_t* bst = smem + SM::kBOff;
     float* fs = reinterpret_cast<float*>(smem + SM::kFOff);
     uint64_t* afull = reinterpret_cast<uint64_t*>(smem + SM::kBarOff);
-    uint64_t* bfull = afull + kTcStages;
-    uint64_t* sempty = bfull + kTcStages;
-    uint64_t* tfull = sempty + kTcStages;
+    uint64_t* aempty = afull + kFwdAStages;
+    uint64_t* bfull = aempty + kFwdAStages;
+    uint64_t* bempty = bfull + kFwdBStages;
+    uint64_t* tfull = bempty + kFwdBStages;
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM::kSlotOff);
     double* red = reinterpret_cast<double*>(smem + SM::kRedOff);
@@ -59,14 +102,20 @@ mpd_fwd_tc_kernel(const float* __restrict__ Xp, const float* __restrict__ Yp, co
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ntiles = ntr * ntc;
     const int nchunk = Kp / kTcKC;
-    pdl_wait();                // panels, E / F and m come from mpd_prepare_kernel
+    const int kq = Kp / 4;
+    const int my_tiles = (int)blockIdx.x < ntiles ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int total = my_tiles * nchunk;         // chunks of this CTA, in (tile, k) order
+    pdl_wait();                // tiled panels, E / F and m come from the kernels before this one
     pdl_launch_dependents();
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kTcStages; ++s) {
+        for (int s = 0; s < kFwdAStages; ++s) {
             tc5::mbar_init(&afull[s], 4);
-            tc5::mbar_init(&bfull[s], 4);
-            tc5::mbar_init(&sempty[s], 1);
+            tc5::mbar_init(&aempty[s], 1);
+        }
+        for (int s = 0; s < kFwdBStages; ++s) {
+            tc5::mbar_init(&bfull[s], 1);
+            tc5::mbar_init(&bempty[s], 1);
         }
         for (int a = 0; a < 2; ++a) {
             tc5::mbar_init(&tfull[a], 1);
@@ -87,7 +136,7 @@ mpd_fwd_tc_kernel(const float* __restrict__ Xp, const float* __restrict__ Yp, co
         const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(wg * kTcT);
         float* fw = fs + wg * kTcT;
         const float m = (float)hdr->m;
-        double total = 0.0;
+        double tot = 0.0;
         int it = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             if ((it & 1) != wg) continue;
@@ -105,11 +154,12 @@ mpd_fwd_tc_kernel(const float* __restrict__ Xp, const float* __restrict__ Yp, co
             float psum = 0.f;
             float* klrow = KL != nullptr ? KL + (int64_t)(i - kl_base) * Bp + tj * kTcT : nullptr;
             float* kltcol = KLT != nullptr ? KLT + (int64_t)(tj * kTcT - kl_base) * Bp + ti * kTcT + t : nullptr;
+            float v[16], w[16];
+            tc5::tmem_ld16(tacc, v);
+            tc5::tmem_ld_wait();
 #pragma unroll 1
             for (int c0 = 0; c0 < kTcT; c0 += 16) {
-                float v[16];
-                tc5::tmem_ld16(tacc + c0, v);
-                tc5::tmem_ld_wait();
+                if (c0 + 16 < kTcT) tc5::tmem_ld16(tacc + c0 + 16, w);     // in flight while this batch is evaluated
 #pragma unroll
                 for (int c = 0; c < 16; ++c) {
                     const float kl = 0.5f * (v[c] + ei + fw[c0 + c]);
@@ -128,19 +178,22 @@ mpd_fwd_tc_kernel(const float* __restrict__ Xp, const float* __restrict__ Yp, co
 #pragma unroll
                     for (int c = 0; c < 16; ++c) kltcol[(int64_t)(c0 + c) * Bp] = v[c];      // lanes = consecutive i: coalesced
                 }
+                tc5::tmem_ld_wait();
+#pragma unroll
+                for (int c = 0; c < 16; ++c) v[c] = w[c];
             }
             tc5::fence_before_sync();
             __syncwarp();
             if (lane == 0) tc5::mbar_arrive(&tempty[wg]);
-            total += (double)psum;
+            tot += (double)psum;
         }
         // CTA total over the 256 epilogue threads, fixed order
-        total = warp_sum(total);
-        if (lane == 0) red[warp] = total;
+        tot = warp_sum(tot);
+        if (lane == 0) red[warp] = tot;
         tc5::named_sync(3, 256);
         if (sumsq_out != nullptr && threadIdx.x == 0) {
             double s = 0.0;
-            for (int w = 0; w < 8; ++w) s += red[w];
+            for (int w8 = 0; w8 < 8; ++w8) s += red[w8];
             if (gridDim.x == 1) {
                 is_last = true;
                 part[0] = s;
@@ -167,39 +220,27 @@ mpd_fwd_tc_kernel(const float* __restrict__ Xp, const float* __restrict__ Yp, co
                 hdr->ticket_fwd = 0u;
             }
         }
-    } else if (warp < 12) {
-        // ------------------------------------------------------------ A producer: x~ rows -> hi / lo -> TMEM operand stage
+    } else if (warp < 16) {
+        // ------------------------------------------------------------ A: pre-split x~ rows -> TMEM operand stage; the two
+        // warpgroups take alternate chunks, so one has its 16 loads in flight while the other stores
+        const int pw = (warp - 8) >> 2;
         const int t = ((warp & 3) << 5) | lane;
         const uint32_t ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)kFwdTcACol;
-        const int my_tiles = blockIdx.x < ntiles ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-        const int total = my_tiles * nchunk;
-        // chunk g of this CTA's sequence -> the 128 bytes of this thread's row; the loads of chunk g + 1 are in flight while
-        // chunk g is split and stored (the panels are L2-resident: latency, not bandwidth)
-        auto src_of = [&](int g) {
-            const int tile = blockIdx.x + (g / nchunk) * gridDim.x;
-            return Xp + (int64_t)((tr0 + tile / ntc) * kTcT + t) * Kp + (g % nchunk) * kTcKC;
-        };
-        float4 nxt[kTcKC / 4];
-        if (total > 0) {
-            const float* p = src_of(0);
-#pragma unroll
-            for (int g4 = 0; g4 < kTcKC / 4; ++g4) nxt[g4] = __ldg(reinterpret_cast<const float4*>(p + 4 * g4));
-        }
-        for (int qn = 0; qn < total; ++qn) {
+        const float* xh = tp, * xl = tp + mat;
+        for (int qn = pw; qn < total; qn += 2) {
+            const int tile = blockIdx.x + (qn / nchunk) * gridDim.x;
+            const int ti = tr0 + tile / ntc, kc = qn % nchunk;
+            const int64_t o = (((int64_t)ti * kq + kc * 8) * 128 + t) * 4;
             float h[kTcKC], l[kTcKC];
 #pragma unroll
-            for (int g4 = 0; g4 < kTcKC / 4; ++g4) {
-                h[4 * g4] = nxt[g4].x; h[4 * g4 + 1] = nxt[g4].y; h[4 * g4 + 2] = nxt[g4].z; h[4 * g4 + 3] = nxt[g4].w;
+            for (int g = 0; g < 8; ++g) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(xh + o + g * 512));
+                const float4 b = __ldg(reinterpret_cast<const float4*>(xl + o + g * 512));
+                h[4 * g] = a.x; h[4 * g + 1] = a.y; h[4 * g + 2] = a.z; h[4 * g + 3] = a.w;
+                l[4 * g] = b.x; l[4 * g + 1] = b.y; l[4 * g + 2] = b.z; l[4 * g + 3] = b.w;
             }
-            if (qn + 1 < total) {
-                const float* p = src_of(qn + 1);
-#pragma unroll
-                for (int g4 = 0; g4 < kTcKC / 4; ++g4) nxt[g4] = __ldg(reinterpret_cast<const float4*>(p + 4 * g4));
-            }
-#pragma unroll
-            for (int j = 0; j < kTcKC; ++j) tc5::split_tf32(h[j], h[j], l[j]);     // both parts ROUNDED: a truncated lo biases long contractions
-            const int s = qn % kTcStages;
-            tc5::mbar_wait(&sempty[s], ((uint32_t)(qn / kTcStages) & 1u) ^ 1u);
+            const int s = qn % kFwdAStages;
+            tc5::mbar_wait(&aempty[s], ((uint32_t)(qn / kFwdAStages) & 1u) ^ 1u);
             tc5::fence_after_sync();
             const uint32_t tas = ta + (uint32_t)(s * 2 * kTcKC);
 #pragma unroll
@@ -212,48 +253,20 @@ mpd_fwd_tc_kernel(const float* __restrict__ Xp, const float* __restrict__ Yp, co
             __syncwarp();
             if (lane == 0) tc5::mbar_arrive(&afull[s]);
         }
-    } else if (warp < 16) {
-        // ------------------------------------------------------------ B producer: y~ rows -> hi / lo -> canonical smem
-        const int t = ((warp & 3) << 5) | lane;
-        const int my_tiles = blockIdx.x < ntiles ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-        const int total = my_tiles * nchunk;
-        auto src_of = [&](int g) {
-            const int tile = blockIdx.x + (g / nchunk) * gridDim.x;
-            return Yp + (int64_t)((tc0 + tile % ntc) * kTcT + t) * Kp + (g % nchunk) * kTcKC;
-        };
-        float4 nxt[kTcKC / 4];
-        if (total > 0) {
-            const float* p = src_of(0);
-#pragma unroll
-            for (int g4 = 0; g4 < kTcKC / 4; ++g4) nxt[g4] = __ldg(reinterpret_cast<const float4*>(p + 4 * g4));
-        }
-        for (int qn = 0; qn < total; ++qn) {
-            float4 v[kTcKC / 4];
-#pragma unroll
-            for (int g4 = 0; g4 < kTcKC / 4; ++g4) v[g4] = nxt[g4];
-            if (qn + 1 < total) {
-                const float* p = src_of(qn + 1);
-#pragma unroll
-                for (int g4 = 0; g4 < kTcKC / 4; ++g4) nxt[g4] = __ldg(reinterpret_cast<const float4*>(p + 4 * g4));
+    } else if (warp == 17) {
+        // ------------------------------------------------------------ loader: B = y~ chunk, two contiguous 16 KB bulk copies
+        if (lane == 0) {
+            const float* yh = tp + 2 * mat, * yl = tp + 3 * mat;
+            for (int qn = 0; qn < total; ++qn) {
+                const int tile = blockIdx.x + (qn / nchunk) * gridDim.x;
+                const int tj = tc0 + tile % ntc, kc = qn % nchunk;
+                const int64_t o = (((int64_t)tj * kq + kc * 8) * 128) * 4;
+                const int s = qn % kFwdBStages;
+                tc5::mbar_wait(&bempty[s], ((uint32_t)(qn / kFwdBStages) & 1u) ^ 1u);
+                tc5::mbar_expect_tx(&bfull[s], kTcStageB);
+                tc5::bulk_g2s(bst + s * kTcStageB, yh + o, kTcHalf, &bfull[s]);
+                tc5::bulk_g2s(bst + s * kTcStageB + kTcHalf, yl + o, kTcHalf, &bfull[s]);
             }
-            const int s = qn % kTcStages;
-            tc5::mbar_wait(&sempty[s], ((uint32_t)(qn / kTcStages) & 1u) ^ 1u);
-            tc5::fence_after_sync();
-            uint8_t* b_hi = bst + s * kTcStageB + t * 16;
-            uint8_t* b_lo = b_hi + kTcStageB / 2;
-#pragma unroll
-            for (int g4 = 0; g4 < kTcKC / 4; ++g4) {
-                float4 h, l;
-                tc5::split_tf32(v[g4].x, h.x, l.x);
-                tc5::split_tf32(v[g4].y, h.y, l.y);
-                tc5::split_tf32(v[g4].z, h.z, l.z);
-                tc5::split_tf32(v[g4].w, h.w, l.w);
-                *reinterpret_cast<float4*>(b_hi + g4 * kTcLbo) = h;
-                *reinterpret_cast<float4*>(b_lo + g4 * kTcLbo) = l;
-            }
-            tc5::fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) tc5::mbar_arrive(&bfull[s]);
         }
     } else if (lane == 0) {
         // ------------------------------------------------------------ MMA issuer
@@ -266,13 +279,12 @@ mpd_fwd_tc_kernel(const float* __restrict__ Xp, const float* __restrict__ Yp, co
             tc5::fence_after_sync();
             const uint32_t d = tmem_base + (uint32_t)(a * kTcT);
             for (int kc = 0; kc < nchunk; ++kc, ++qn) {
-                const int s = qn % kTcStages;
-                const uint32_t ph = (uint32_t)(qn / kTcStages) & 1u;
-                tc5::mbar_wait(&afull[s], ph);
-                tc5::mbar_wait(&bfull[s], ph);
+                const int sa = qn % kFwdAStages, sb = qn % kFwdBStages;
+                tc5::mbar_wait(&afull[sa], (uint32_t)(qn / kFwdAStages) & 1u);
+                tc5::mbar_wait(&bfull[sb], (uint32_t)(qn / kFwdBStages) & 1u);
                 tc5::fence_after_sync();
-                const uint32_t a_hi = tmem_base + (uint32_t)(kFwdTcACol + s * 2 * kTcKC), a_lo = a_hi + kTcKC;
-                const uint32_t b_hi = b_a + s * kTcStageB, b_lo = b_hi + kTcStageB / 2;
+                const uint32_t a_hi = tmem_base + (uint32_t)(kFwdTcACol + sa * 2 * kTcKC), a_lo = a_hi + kTcKC;
+                const uint32_t b_hi = b_a + sb * kTcStageB, b_lo = b_hi + kTcHalf;
 #pragma unroll
                 for (int j = 0; j < kTcKC / 8; ++j) {
                     const uint64_t bh = tc5::smem_desc(b_hi + 2 * j * kTcLbo, kTcLbo, 128);
@@ -281,7 +293,8 @@ mpd_fwd_tc_kernel(const float* __restrict__ Xp, const float* __restrict__ Yp, co
                     tc5::mma_tf32_ts(d, a_hi + 8 * j, bl, idesc, 1u);
                     tc5::mma_tf32_ts(d, a_hi + 8 * j, bh, idesc, 1u);
                 }
-                tc5::mma_commit(&sempty[s]);
+                tc5::mma_commit(&aempty[sa]);
+                tc5::mma_commit(&bempty[sb]);
             }
             tc5::mma_commit(&tfull[a]);
         }
@@ -301,35 +314,35 @@ mpd_fwd_tc_kernel(const float* __restrict__ Xp, const float* __restrict__ Yp, co
 // G2 at 128, weight stages W1 (hi | lo) at 256 + 64 s, W2 at 384 + 64 s.  The weights of a row are formed by the thread that
 // owns the row (= TMEM lane) straight from the stored KL rows (128 contiguous bytes per chunk, streamed once per column
 // chunk), so A never touches shared memory; B = the partner panels transposed on the fly into [k][j] (K-major) tiles.
-constexpr int kBwdTcLbo = 16 * 128 + 16;          // +16 B: the transposing 4-byte stores of 32 partners hit 32 banks
-constexpr int kBwdTcMat = (kTcKC / 4) * kBwdTcLbo;   // one of Y_hi, Y_lo, X_hi, X_lo of a stage
-constexpr int kBwdTcStageB = 4 * kBwdTcMat;
+constexpr int kBwdWStages = 2;                     // TMEM weight stages per W (hi | lo, 64 columns each)
+constexpr int kBwdPStages = 3;                     // shared-memory panel stages: Y_hi | Y_lo | X_hi | X_lo, 16 KB each
+constexpr int kBwdTcStageB = 4 * kTcHalf;
 struct BwdTcSmem {
-    static constexpr int kBarOff = kTcStages * kBwdTcStageB;
-    static constexpr int kNumBars = 5 * kTcStages + 2;    // w1full, w2full, yfull, xfull, sempty per stage; gfull, gdrained
+    static constexpr int kBarOff = kBwdPStages * kBwdTcStageB;
+    static constexpr int kNumBars = 3 * kBwdWStages + 2 * kBwdPStages + 2;   // w1full, w2full, wempty; pfull, pempty; gfull, gdrained
     static constexpr int kSlotOff = kBarOff + kNumBars * 8;
     static constexpr int kBytes = kSlotOff + 32;
 };
-constexpr int kBwdTcThreads = (4 + 4 + 4 + 4 + 1) * 32;   // W1 rows, W2 rows, Y panel, X panel, MMA warp
+constexpr int kBwdTcThreads = (4 + 4 + 1 + 1) * 32;   // W1 rows, W2 rows, MMA warp, loader warp
 
 __global__ void __launch_bounds__(kBwdTcThreads, 1)
-mpd_bwd_tc_kernel(const float* __restrict__ Xp, const float* __restrict__ Yp, const Hdr* __restrict__ hdr, int B, int Kp,
+mpd_bwd_tc_kernel(const float* __restrict__ tp, int64_t mat, const Hdr* __restrict__ hdr, int B, int Kp,
                   int row0, int row1, int tr0, int ntc, int tiles_per_split, const float* __restrict__ KL,
                   const float* __restrict__ KLT, int Bp, float* __restrict__ gpart, float* __restrict__ rspart, int rows_pad,
                   int gbase, int group_chunks) {
+    // KL / KLT: pre-offset so that global row i is at [i * Bp] (row blocks keep only their rows).  gpart
+    // [split][2][rows_pad][Kp], rspart [split][2][rows_pad], local row = i - gbase.
     // group_chunks: chunks of 32 partners per TMEM accumulation.  The tensor core's accumulator does not round to nearest, so
     // the error of a running sum grows with its length; after every group the owners of the rows add the accumulator to the
     // CTA's fp32 partial sums in global memory (round to nearest) and the next group starts from zero.
-    // KL / KLT: pre-offset so that global row i is at [i * Bp] (row blocks keep only their rows).  gpart
-    // [split][2][rows_pad][Kp], rspart [split][2][rows_pad], local row = i - gbase.
     using SM = BwdTcSmem;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* w1full = reinterpret_cast<uint64_t*>(smem + SM::kBarOff);
-    uint64_t* w2full = w1full + kTcStages;
-    uint64_t* yfull = w2full + kTcStages;
-    uint64_t* xfull = yfull + kTcStages;
-    uint64_t* sempty = xfull + kTcStages;
-    uint64_t* gfull = sempty + kTcStages;
+    uint64_t* w2full = w1full + kBwdWStages;
+    uint64_t* wempty = w2full + kBwdWStages;
+    uint64_t* pfull = wempty + kBwdWStages;
+    uint64_t* pempty = pfull + kBwdPStages;
+    uint64_t* gfull = pempty + kBwdPStages;
     uint64_t* gdrained = gfull + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM::kSlotOff);
 
@@ -343,18 +356,20 @@ mpd_bwd_tc_kernel(const float* __restrict__ Xp, const float* __restrict__ Yp, co
     pdl_wait();
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kTcStages; ++s) {
+        for (int s = 0; s < kBwdWStages; ++s) {
             tc5::mbar_init(&w1full[s], 4);
             tc5::mbar_init(&w2full[s], 4);
-            tc5::mbar_init(&yfull[s], 4);
-            tc5::mbar_init(&xfull[s], 4);
-            tc5::mbar_init(&sempty[s], 1);
+            tc5::mbar_init(&wempty[s], 1);
+        }
+        for (int s = 0; s < kBwdPStages; ++s) {
+            tc5::mbar_init(&pfull[s], 1);
+            tc5::mbar_init(&pempty[s], 1);
         }
         tc5::mbar_init(gfull, 1);
         tc5::mbar_init(gdrained, 8);
         tc5::fence_barrier_init();
     }
-    if (warp == 16) tc5::tmem_alloc(tmem_slot, 512);
+    if (warp == 8) tc5::tmem_alloc(tmem_slot, 512);
     tc5::fence_before_sync();
     __syncthreads();
     tc5::fence_after_sync();
@@ -377,7 +392,7 @@ mpd_bwd_tc_kernel(const float* __restrict__ Xp, const float* __restrict__ Yp, co
         float4 nxt[kTcKC / 4];
         if (total > 0) {
 #pragma unroll
-            for (int g4 = 0; g4 < kTcKC / 4; ++g4) nxt[g4] = __ldcs(reinterpret_cast<const float4*>(krow + tj0 * kTcT + 4 * g4));
+            for (int g4 = 0; g4 < kTcKC / 4; ++g4) nxt[g4] = __ldg(reinterpret_cast<const float4*>(krow + tj0 * kTcT + 4 * g4));
         }
         for (int qn = 0; qn < total; ++qn) {
             float h[kTcKC], l[kTcKC];
@@ -388,7 +403,7 @@ mpd_bwd_tc_kernel(const float* __restrict__ Xp, const float* __restrict__ Yp, co
             const int j0 = tj0 * kTcT + qn * kTcKC;
             if (qn + 1 < total) {
 #pragma unroll
-                for (int g4 = 0; g4 < kTcKC / 4; ++g4) nxt[g4] = __ldcs(reinterpret_cast<const float4*>(krow + j0 + kTcKC + 4 * g4));
+                for (int g4 = 0; g4 < kTcKC / 4; ++g4) nxt[g4] = __ldg(reinterpret_cast<const float4*>(krow + j0 + kTcKC + 4 * g4));
             }
             const bool plain = row_ok && (j0 + kTcKC <= B) && (i < j0 || i >= j0 + kTcKC);
 #pragma unroll
@@ -398,8 +413,8 @@ mpd_bwd_tc_kernel(const float* __restrict__ Xp, const float* __restrict__ Yp, co
                 rs += w;
                 tc5::split_tf32(w, h[j], l[j]);
             }
-            const int s = qn % kTcStages;
-            tc5::mbar_wait(&sempty[s], ((uint32_t)(qn / kTcStages) & 1u) ^ 1u);
+            const int s = qn % kBwdWStages;
+            tc5::mbar_wait(&wempty[s], ((uint32_t)(qn / kBwdWStages) & 1u) ^ 1u);
             tc5::fence_after_sync();
             const uint32_t tws = tw + (uint32_t)(s * 2 * kTcKC);
 #pragma unroll
@@ -441,76 +456,47 @@ mpd_bwd_tc_kernel(const float* __restrict__ Xp, const float* __restrict__ Yp, co
         if (total == 0) {
             for (int c0 = 0; c0 < kTcT; c0 += 4) *reinterpret_cast<float4*>(dst + c0) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-    } else if (warp < 16) {
-        // ------------------------------------------------------------ panels: lane = partner j of the chunk, transposed store
-        const int which = (warp - 8) >> 2;                  // 0: Y panel (pairs with W1), 1: X panel (pairs with W2)
-        const int w4 = warp & 3;
-        const float* P = which == 0 ? Yp : Xp;
-        uint64_t* pfull = which == 0 ? yfull : xfull;
-        float4 nxt[8];
-        auto load = [&](int qn, float4* dstv) {
-            const float* src = P + (int64_t)(tj0 * kTcT + qn * kTcKC + lane) * Kp + kbase + w4 * 32;
+    } else if (warp == 9) {
+        // ------------------------------------------------------------ loader: the four 16 KB operand halves of a chunk
+        if (lane == 0) {
+            const int ncn = Kp / 128;
+            for (int qn = 0; qn < total; ++qn) {
+                const int tj = tj0 + qn / (kTcT / kTcKC), jc = qn % (kTcT / kTcKC);
+                const int64_t o = ((((int64_t)tj * ncn + blockIdx.y) * 32 + jc * 8) * 128) * 4;
+                const int s = qn % kBwdPStages;
+                tc5::mbar_wait(&pempty[s], ((uint32_t)(qn / kBwdPStages) & 1u) ^ 1u);
+                tc5::mbar_expect_tx(&pfull[s], kBwdTcStageB);
+                uint8_t* st = smem + s * kBwdTcStageB;
 #pragma unroll
-            for (int it = 0; it < 8; ++it) dstv[it] = __ldg(reinterpret_cast<const float4*>(src + 4 * it));
-        };
-        if (total > 0) load(0, nxt);
-        for (int qn = 0; qn < total; ++qn) {
-            float4 v[8];
-#pragma unroll
-            for (int it = 0; it < 8; ++it) v[it] = nxt[it];
-            if (qn + 1 < total) load(qn + 1, nxt);
-            const int s = qn % kTcStages;
-            tc5::mbar_wait(&sempty[s], ((uint32_t)(qn / kTcStages) & 1u) ^ 1u);
-            tc5::fence_after_sync();
-            // element (n = k, K = j): (j / 4) * LBO + n * 16 + (j % 4) * 4
-            uint8_t* hi = smem + s * kBwdTcStageB + which * 2 * kBwdTcMat + (lane >> 2) * kBwdTcLbo + (lane & 3) * 4;
-            uint8_t* lo = hi + kBwdTcMat;
-#pragma unroll
-            for (int it = 0; it < 8; ++it) {
-                const int n = w4 * 32 + 4 * it;
-                float h4[4], l4[4];
-                tc5::split_tf32(v[it].x, h4[0], l4[0]);
-                tc5::split_tf32(v[it].y, h4[1], l4[1]);
-                tc5::split_tf32(v[it].z, h4[2], l4[2]);
-                tc5::split_tf32(v[it].w, h4[3], l4[3]);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    *reinterpret_cast<float*>(hi + (n + e) * 16) = h4[e];
-                    *reinterpret_cast<float*>(lo + (n + e) * 16) = l4[e];
-                }
+                for (int q4 = 0; q4 < 4; ++q4) tc5::bulk_g2s(st + q4 * kTcHalf, tp + (4 + q4) * mat + o, kTcHalf, &pfull[s]);
             }
-            tc5::fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) tc5::mbar_arrive(&pfull[s]);
         }
-    } else if (lane == 0) {
+    } else if (warp == 8 && lane == 0) {
         // ------------------------------------------------------------ MMA issuer
         constexpr uint32_t idesc = tc5::idesc_tf32(kTcT, kTcT);
         const uint32_t st_a = tc5::smem_u32(smem);
         const uint32_t dG1 = tmem_base, dG2 = tmem_base + kTcT;
         for (int qn = 0; qn < total; ++qn) {
-            const int s = qn % kTcStages;
-            const uint32_t ph = (uint32_t)(qn / kTcStages) & 1u;
+            const int sw = qn % kBwdWStages, sp = qn % kBwdPStages;
             const int gq = qn % group_chunks;
             if (gq == 0 && qn > 0) {       // the previous group's sums have been read out of the accumulators
                 tc5::mbar_wait(gdrained, (uint32_t)(qn / group_chunks - 1) & 1u);
                 tc5::fence_after_sync();
             }
-            tc5::mbar_wait(&w1full[s], ph);
-            tc5::mbar_wait(&w2full[s], ph);
-            tc5::mbar_wait(&yfull[s], ph);
-            tc5::mbar_wait(&xfull[s], ph);
+            tc5::mbar_wait(&w1full[sw], (uint32_t)(qn / kBwdWStages) & 1u);
+            tc5::mbar_wait(&w2full[sw], (uint32_t)(qn / kBwdWStages) & 1u);
+            tc5::mbar_wait(&pfull[sp], (uint32_t)(qn / kBwdPStages) & 1u);
             tc5::fence_after_sync();
-            const uint32_t w1h = tmem_base + (uint32_t)(256 + s * 2 * kTcKC), w1l = w1h + kTcKC;
-            const uint32_t w2h = tmem_base + (uint32_t)(384 + s * 2 * kTcKC), w2l = w2h + kTcKC;
-            const uint32_t yh = st_a + s * kBwdTcStageB, yl = yh + kBwdTcMat, xh = yl + kBwdTcMat, xl = xh + kBwdTcMat;
+            const uint32_t w1h = tmem_base + (uint32_t)(256 + sw * 2 * kTcKC), w1l = w1h + kTcKC;
+            const uint32_t w2h = tmem_base + (uint32_t)(384 + sw * 2 * kTcKC), w2l = w2h + kTcKC;
+            const uint32_t yh = st_a + sp * kBwdTcStageB, yl = yh + kTcHalf, xh = yl + kTcHalf, xl = xh + kTcHalf;
 #pragma unroll
             for (int j = 0; j < kTcKC / 8; ++j) {
                 const uint32_t acc = (gq | j) != 0;
-                const uint64_t dyh = tc5::smem_desc(yh + 2 * j * kBwdTcLbo, kBwdTcLbo, 128);
-                const uint64_t dyl = tc5::smem_desc(yl + 2 * j * kBwdTcLbo, kBwdTcLbo, 128);
-                const uint64_t dxh = tc5::smem_desc(xh + 2 * j * kBwdTcLbo, kBwdTcLbo, 128);
-                const uint64_t dxl = tc5::smem_desc(xl + 2 * j * kBwdTcLbo, kBwdTcLbo, 128);
+                const uint64_t dyh = tc5::smem_desc(yh + 2 * j * kTcLbo, kTcLbo, 128);
+                const uint64_t dyl = tc5::smem_desc(yl + 2 * j * kTcLbo, kTcLbo, 128);
+                const uint64_t dxh = tc5::smem_desc(xh + 2 * j * kTcLbo, kTcLbo, 128);
+                const uint64_t dxl = tc5::smem_desc(xl + 2 * j * kTcLbo, kTcLbo, 128);
                 tc5::mma_tf32_ts(dG1, w1l + 8 * j, dyh, idesc, acc);
                 tc5::mma_tf32_ts(dG1, w1h + 8 * j, dyl, idesc, 1u);
                 tc5::mma_tf32_ts(dG1, w1h + 8 * j, dyh, idesc, 1u);
@@ -518,13 +504,14 @@ mpd_bwd_tc_kernel(const float* __restrict__ Xp, const float* __restrict__ Yp, co
                 tc5::mma_tf32_ts(dG2, w2h + 8 * j, dxl, idesc, 1u);
                 tc5::mma_tf32_ts(dG2, w2h + 8 * j, dxh, idesc, 1u);
             }
-            tc5::mma_commit(&sempty[s]);
+            tc5::mma_commit(&wempty[sw]);
+            tc5::mma_commit(&pempty[sp]);
             if (gq + 1 == group_chunks || qn + 1 == total) tc5::mma_commit(gfull);
         }
     }
     tc5::fence_before_sync();
     __syncthreads();
-    if (warp == 16) {
+    if (warp == 8) {
         tc5::fence_after_sync();
         tc5::tmem_dealloc(tmem_base, 512);
     }
