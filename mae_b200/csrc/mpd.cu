@@ -943,6 +943,11 @@ int check_common(int64_t B, int64_t D, const void* ws, int64_t ws_bytes, Layout&
 }  // namespace
 }  // namespace mae
 
+// development aid (not part of include/mae_b200.h): per-role cycle counters of the last profiled tensor-core forward
+extern "C" int mae_debug_mpd_prof(long long* host_out) {
+    return (int)cudaMemcpyFromSymbol(host_out, mae::g_mpd_prof, sizeof(long long) * 32);
+}
+
 extern "C" int mae_set_mpd_tensor_cores(int enabled) {
     const int before = mae::g_mpd_tc;
     mae::g_mpd_tc = enabled ? 1 : 0;
@@ -1034,10 +1039,17 @@ extern "C" int mae_mpd_fwd(void* workspace, int64_t workspace_bytes, int64_t B, 
         const int ntc = (int)(L.Bp / T);
         const int64_t ntiles = (int64_t)ntr * ntc;
         const int grid = (int)(ntiles < sm_count() ? ntiles : sm_count());
+        // profiling runs (MAE_MPD_PROF=1): per-role cycle counters of CTA 0 in the (unused) second half of the per-CTA partials
+        static const bool want_prof = getenv("MAE_MPD_PROF") != nullptr;
+        long long* prof = nullptr;
+        if (want_prof) {
+            cudaGetSymbolAddress(reinterpret_cast<void**>(&prof), g_mpd_prof);
+            cudaMemsetAsync(prof, 0, sizeof(long long) * 32, as_stream(stream));
+        }
         launch_pdl(mpd_fwd_tc_kernel, dim3((unsigned)grid), dim3(kFwdTcThreads), (size_t)FwdTcSmem::kBytes, as_stream(stream),
             at<float>(workspace, L.tp), L.tp_mat, at<float>(workspace, L.c), at<float>(workspace, L.l),
             at<Hdr>(workspace, L.hdr), at<double>(workspace, L.part_fwd), (int)B, (int)L.Kp, (int)row0, (int)(row0 + nrows), tr0,
-            ntr, ntc, klp, full ? kltp : nullptr, (int)L.Bp, sumsq, S, 0, (int)kg.base);
+            ntr, ntc, klp, full ? kltp : nullptr, (int)L.Bp, sumsq, S, 0, (int)kg.base, prof);
         if (store_kl && !full) {
             const int tcb = (int)(kg.base / T), ntcb = (int)(kg.rows_pad / T), ntra = (int)(L.Bp / T);
             const int64_t nt2 = (int64_t)ntra * ntcb;
@@ -1045,7 +1057,7 @@ extern "C" int mae_mpd_fwd(void* workspace, int64_t workspace_bytes, int64_t B, 
             mpd_fwd_tc_kernel<<<grid2, kFwdTcThreads, FwdTcSmem::kBytes, as_stream(stream)>>>(
                 at<float>(workspace, L.tp), L.tp_mat, at<float>(workspace, L.c), at<float>(workspace, L.l),
                 at<Hdr>(workspace, L.hdr), at<double>(workspace, L.part_fwd), (int)B, (int)L.Kp, 0, 0, 0, ntra, ntcb, nullptr, kltp,
-                (int)L.Bp, nullptr, nullptr, tcb, (int)kg.base);
+                (int)L.Bp, nullptr, nullptr, tcb, (int)kg.base, nullptr);
         }
         return launch_status();
     }

@@ -63,6 +63,8 @@ mpd_tile_panels_kernel(const float* __restrict__ Xp, const float* __restrict__ Y
     }
 }
 
+__device__ long long g_mpd_prof[32];     // MAE_MPD_PROF=1: per-role cycle counters (development aid)
+
 constexpr int kFwdAStages = 3;       // TMEM operand stages (A = x~ rows)
 constexpr int kFwdBStages = 4;       // shared-memory stages (B = y~ rows, filled by the bulk-copy engine)
 struct FwdTcSmem {
@@ -84,8 +86,27 @@ __global__ void __launch_bounds__(kFwdTcThreads, 1)
 mpd_fwd_tc_kernel(const float* __restrict__ tp, int64_t mat, const float* __restrict__ evec,
                   const float* __restrict__ fvec, Hdr* hdr, double* part, int B, int Kp, int row0, int row1, int tr0, int ntr,
                   int ntc, float* __restrict__ KL, float* __restrict__ KLT, int Bp, double* __restrict__ sumsq_out,
-                  float* __restrict__ S_out, int tc0, int kl_base) {
+                  float* __restrict__ S_out, int tc0, int kl_base, long long* prof) {
     using SM = FwdTcSmem;
+    // prof != nullptr (MAE_MPD_PROF=1, profiling runs): CTA 0 reports per role the cycles of its loop and of its barrier waits
+    long long pw0 = 0, pw1 = 0;
+    auto wait = [&](uint64_t* bar, uint32_t parity, long long& acc) {
+        if (prof != nullptr) {
+            const long long t0 = clock64();
+            tc5::mbar_wait(bar, parity);
+            acc += clock64() - t0;
+        } else {
+            tc5::mbar_wait(bar, parity);
+        }
+    };
+    const long long t_start = prof != nullptr ? clock64() : 0;
+    auto report = [&](int slot) {
+        if (prof != nullptr && blockIdx.x == 0) {
+            prof[slot] = clock64() - t_start;
+            prof[slot + 1] = pw0;
+            prof[slot + 2] = pw1;
+        }
+    };
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* bst = smem + SM::kBOff;
     float* fs = reinterpret_cast<float*>(smem + SM::kFOff);
@@ -149,7 +170,7 @@ mpd_fwd_tc_kernel(const float* __restrict__ tp, int64_t mat, const float* __rest
             tc5::named_sync(1 + wg, 128);
             const bool row_ok = (i >= row0) && (i < row1);
             const bool plain = (ti != tj) && (tj * kTcT + kTcT <= B);      // no diagonal, no padded columns
-            tc5::mbar_wait(&tfull[wg], use & 1);
+            wait(&tfull[wg], use & 1, pw0);
             tc5::fence_after_sync();
             float psum = 0.f;
             float* klrow = KL != nullptr ? KL + (int64_t)(i - kl_base) * Bp + tj * kTcT : nullptr;
@@ -160,14 +181,29 @@ mpd_fwd_tc_kernel(const float* __restrict__ tp, int64_t mat, const float* __rest
 #pragma unroll 1
             for (int c0 = 0; c0 < kTcT; c0 += 16) {
                 if (c0 + 16 < kTcT) tc5::tmem_ld16(tacc + c0 + 16, w);     // in flight while this batch is evaluated
+                if (plain && row_ok) {       // interior tile: no masks; f_j by 16-byte broadcast loads
 #pragma unroll
-                for (int c = 0; c < 16; ++c) {
-                    const float kl = 0.5f * (v[c] + ei + fw[c0 + c]);
-                    v[c] = kl;
-                    const float dev = kl - m;
-                    const int j = tj * kTcT + c0 + c;
-                    const bool ok = row_ok && (plain || (j < B && j != i));
-                    psum = ok ? fmaf(dev, dev, psum) : psum;
+                    for (int g4 = 0; g4 < 4; ++g4) {
+                        const float4 f4 = *reinterpret_cast<const float4*>(fw + c0 + 4 * g4);
+                        const float ff[4] = {f4.x, f4.y, f4.z, f4.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float kl = 0.5f * (v[4 * g4 + e] + (ei + ff[e]));
+                            v[4 * g4 + e] = kl;
+                            const float dev = kl - m;
+                            psum = fmaf(dev, dev, psum);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) {
+                        const float kl = 0.5f * (v[c] + (ei + fw[c0 + c]));
+                        v[c] = kl;
+                        const float dev = kl - m;
+                        const int j = tj * kTcT + c0 + c;
+                        const bool ok = row_ok && j < B && j != i;
+                        psum = ok ? fmaf(dev, dev, psum) : psum;
+                    }
                 }
                 if (klrow != nullptr) {
 #pragma unroll
@@ -187,6 +223,7 @@ mpd_fwd_tc_kernel(const float* __restrict__ tp, int64_t mat, const float* __rest
             if (lane == 0) tc5::mbar_arrive(&tempty[wg]);
             tot += (double)psum;
         }
+        if (t == 0) report(4 * wg);
         // CTA total over the 256 epilogue threads, fixed order
         tot = warp_sum(tot);
         if (lane == 0) red[warp] = tot;
@@ -240,7 +277,7 @@ mpd_fwd_tc_kernel(const float* __restrict__ tp, int64_t mat, const float* __rest
                 l[4 * g] = b.x; l[4 * g + 1] = b.y; l[4 * g + 2] = b.z; l[4 * g + 3] = b.w;
             }
             const int s = qn % kFwdAStages;
-            tc5::mbar_wait(&aempty[s], ((uint32_t)(qn / kFwdAStages) & 1u) ^ 1u);
+            wait(&aempty[s], ((uint32_t)(qn / kFwdAStages) & 1u) ^ 1u, pw0);
             tc5::fence_after_sync();
             const uint32_t tas = ta + (uint32_t)(s * 2 * kTcKC);
 #pragma unroll
@@ -253,6 +290,7 @@ mpd_fwd_tc_kernel(const float* __restrict__ tp, int64_t mat, const float* __rest
             __syncwarp();
             if (lane == 0) tc5::mbar_arrive(&afull[s]);
         }
+        if (t == 0) report(8 + 4 * pw);
     } else if (warp == 17) {
         // ------------------------------------------------------------ loader: B = y~ chunk, two contiguous 16 KB bulk copies
         if (lane == 0) {
@@ -262,11 +300,12 @@ mpd_fwd_tc_kernel(const float* __restrict__ tp, int64_t mat, const float* __rest
                 const int tj = tc0 + tile % ntc, kc = qn % nchunk;
                 const int64_t o = (((int64_t)tj * kq + kc * 8) * 128) * 4;
                 const int s = qn % kFwdBStages;
-                tc5::mbar_wait(&bempty[s], ((uint32_t)(qn / kFwdBStages) & 1u) ^ 1u);
+                wait(&bempty[s], ((uint32_t)(qn / kFwdBStages) & 1u) ^ 1u, pw0);
                 tc5::mbar_expect_tx(&bfull[s], kTcStageB);
                 tc5::bulk_g2s(bst + s * kTcStageB, yh + o, kTcHalf, &bfull[s]);
                 tc5::bulk_g2s(bst + s * kTcStageB + kTcHalf, yl + o, kTcHalf, &bfull[s]);
             }
+            report(16);
         }
     } else if (lane == 0) {
         // ------------------------------------------------------------ MMA issuer
@@ -275,13 +314,13 @@ mpd_fwd_tc_kernel(const float* __restrict__ tp, int64_t mat, const float* __rest
         int qn = 0, it = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const int a = it & 1, use = it >> 1;
-            tc5::mbar_wait(&tempty[a], ((uint32_t)use & 1u) ^ 1u);
+            wait(&tempty[a], ((uint32_t)use & 1u) ^ 1u, pw0);
             tc5::fence_after_sync();
             const uint32_t d = tmem_base + (uint32_t)(a * kTcT);
             for (int kc = 0; kc < nchunk; ++kc, ++qn) {
                 const int sa = qn % kFwdAStages, sb = qn % kFwdBStages;
-                tc5::mbar_wait(&afull[sa], (uint32_t)(qn / kFwdAStages) & 1u);
-                tc5::mbar_wait(&bfull[sb], (uint32_t)(qn / kFwdBStages) & 1u);
+                wait(&afull[sa], (uint32_t)(qn / kFwdAStages) & 1u, pw1);
+                { long long tmpw = 0; wait(&bfull[sb], (uint32_t)(qn / kFwdBStages) & 1u, tmpw); pw1 += tmpw; if (prof) prof[31] += tmpw; }
                 tc5::fence_after_sync();
                 const uint32_t a_hi = tmem_base + (uint32_t)(kFwdTcACol + sa * 2 * kTcKC), a_lo = a_hi + kTcKC;
                 const uint32_t b_hi = b_a + sb * kTcStageB, b_lo = b_hi + kTcHalf;
@@ -298,6 +337,7 @@ mpd_fwd_tc_kernel(const float* __restrict__ tp, int64_t mat, const float* __rest
             }
             tc5::mma_commit(&tfull[a]);
         }
+        report(20);
     }
     tc5::fence_before_sync();
     __syncthreads();
@@ -315,7 +355,7 @@ mpd_fwd_tc_kernel(const float* __restrict__ tp, int64_t mat, const float* __rest
 // owns the row (= TMEM lane) straight from the stored KL rows (128 contiguous bytes per chunk, streamed once per column
 // chunk), so A never touches shared memory; B = the partner panels transposed on the fly into [k][j] (K-major) tiles.
 constexpr int kBwdWStages = 2;                     // TMEM weight stages per W (hi | lo, 64 columns each)
-constexpr int kBwdPStages = 3;                     // shared-memory panel stages: Y_hi | Y_lo | X_hi | X_lo, 16 KB each
+constexpr int kBwdPStages = 2;                     // shared-memory panel stages: Y_hi | Y_lo | X_hi | X_lo, 16 KB each
 constexpr int kBwdTcStageB = 4 * kTcHalf;
 struct BwdTcSmem {
     static constexpr int kBarOff = kBwdPStages * kBwdTcStageB;

@@ -13,3 +13,15 @@ for _ in range(2):
     (-torch.nn.functional.logsigmoid(m_d).sum() + s).backward()
 torch.cuda.synchronize()
 print("done", float(s))
+import ctypes, os
+if os.environ.get("MAE_MPD_PROF"):
+    lib = _lib.load()
+    out = (ctypes.c_longlong * 32)()
+    lib.mae_debug_mpd_prof(out)
+    ntile = ((b + 127) // 128) ** 2
+    per = -(-ntile // 148)
+    names = {0: "epilogue wg0 (wait tfull)", 4: "epilogue wg1", 8: "A producer wg0 (wait aempty)", 12: "A producer wg1", 16: "loader (wait bempty)", 20: "mma issuer (wait tempty, wait afull+bfull)"}
+    for k, nm in names.items():
+        tot = max(out[k], 1)
+        print("%-44s total %9d cyc (%6.0f / tile)  wait0 %5.1f %%  wait1 %5.1f %%" % (nm, out[k], out[k] / per, 100.0 * out[k + 1] / tot, 100.0 * out[k + 2] / tot))
+    print("   of the mma issuer's wait1, waiting for B (bulk copies): %.1f %% of its loop" % (100.0 * out[31] / max(out[20], 1)))
