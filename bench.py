@@ -492,6 +492,7 @@ def bench_ours(args):
         if world == 1:
             extra.update(bench_c1(dev, hbm_gbs))
             extra.update(bench_full_model(dev))
+            extra.update(bench_n4(dev))
             extra["gpu_eager_baseline"] = gpu_eager_baseline(dev, value_ours=batch * args.steps / dt)
     out = None
     if rank == 0:
@@ -801,6 +802,50 @@ def bench_n3(dev, world, rank):
             "bits_per_dim": out["cuda_graph"]["bits_per_dim"]}}
     except Exception as e:
         return {"n3_calc_nll": {"error": "%s: %s" % (type(e).__name__, str(e)[:200])}}
+
+
+def bench_n4(dev):
+    """N4: where the time of one ``MAE.nll`` call goes for the shipped CIFAR configuration (8 images x K = 512):
+    encoder, prior-flow inverse on [B K, 16, 8, 8] (``prior_flow.backward``, gaussian_encoder.py:254: 4 AF2d-MADE blocks whose
+    masked convolutions are re-normalised per call, networks/masked.py:102-106), decoder trunk (PixelCNN++), and this path's
+    kernels (fused last convolution + DMOL, IW-NLL).  Shows which callers of the path dominate evaluation."""
+    import copy
+    from mae_b200 import ops, synth
+    from mae_b200.modules import MAE
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tests", "golden", "models.pt")
+    if not os.path.exists(path):
+        return {"n4_nll_breakdown": {"unavailable": "tests/golden/models.pt not found"}}
+    try:
+        c = torch.load(path, weights_only=False)["color_image32x32_json"]
+        model = synth.fill_state(MAE.from_params(copy.deepcopy(c["params"]))).to(dev).eval()
+        b, k = 2, 128            # 256 decoder evaluations per call (the PixelCNN++ trunk holds ~100 MB of activations per 64)
+        g = torch.Generator(device=dev).manual_seed(29)
+        x = torch.randint(0, 256, (b, 3, 32, 32), device=dev, generator=g).float() / 127.5 - 1.0
+        enc, dec = model.encoder, model.decoder
+        stream = torch.cuda.current_stream()
+        with torch.no_grad():
+            z, (mu, logvar, z_normal, logdet) = model.sample_from_posterior(x, nsamples=k)
+            zf = z.view(b * k, *enc.prior_flow.input_size())
+            zd = z.view(b, k, *dec.z_shape())
+            trunk, last, act = dec.head_parts()
+            xe = x.repeat_interleave(k, dim=0)
+            hidden = trunk(xe, zd.view(b * k, *dec.z_shape()))
+            w, bias = last.conv.weight().flatten(1).contiguous(), last.conv.bias
+            t = {
+                "encoder_and_sampling": time_kernel(lambda i: model.sample_from_posterior(x, nsamples=k), 3, stream, 3),
+                "prior_flow_backward": time_kernel(lambda i: enc.prior_flow.backward(zf), 3, stream, 3),
+                "decoder_trunk_pixelcnnpp": time_kernel(lambda i: trunk(xe, zd.view(b * k, *dec.z_shape())), 2, stream, 3),
+                "fused_last_conv_dmol (ours)": time_kernel(lambda i: ops.dmol_head_recon_error(hidden, w, bias, x, k, dec.nmix, act), 5, stream, 3),
+                "whole_nll_call": time_kernel(lambda i: model.nll(x, k), 2, stream, 3),
+            }
+        tot = t["whole_nll_call"]
+        return {"n4_nll_breakdown": {
+            "config": "color_image32x32.json, %d images x K = %d per MAE.nll call" % (b, k),
+            "ms": {kk: v * 1e3 for kk, v in t.items()}, "share_of_call": {kk: v / tot for kk, v in t.items() if kk != "whole_nll_call"},
+            "note": "the prior-flow inverse and the PixelCNN++ trunk are PyTorch conv stacks (callers of the path, SURVEY 8f N4 / N1); "
+                    "the path's own kernels are the last entry"}}
+    except Exception as e:
+        return {"n4_nll_breakdown": {"error": "%s: %s" % (type(e).__name__, str(e)[:200])}}
 
 
 def bench_c1(dev, hbm_gbs):
