@@ -15,7 +15,7 @@ assemble_fwd_kernel(const float* __restrict__ err, const float* __restrict__ kl,
                     const float* __restrict__ S, const float* __restrict__ ext_sums, int B, int ns, int D, int kl_count,
                     int err_chunks, float eta, float gamma, float free_bits, float inv_batch, float* __restrict__ scalars,
                     float* __restrict__ recon) {
-    __shared__ float scratch[32];
+    __shared__ float scratch4[4][32];
     float s_rec = 0.f, s_kl = 0.f, s_m = 0.f, s_ls = 0.f;
     const float inv_ns = 1.0f / (float)ns;
     for (int b = threadIdx.x; b < B; b += kThreads) {
@@ -34,10 +34,31 @@ assemble_fwd_kernel(const float* __restrict__ err, const float* __restrict__ kl,
             s_ls += logsigmoid(v);
         }
     }
-    s_rec = block_sum(s_rec, scratch);
-    s_kl = block_sum(s_kl, scratch);
-    s_m = block_sum(s_m, scratch);
-    s_ls = block_sum(s_ls, scratch);
+    // the four sums in ONE barrier phase (this kernel sits on the join of every training step: four block_sum calls cost
+    // eight barriers and four dependent shuffle trees); fixed order -> deterministic
+    {
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+        s_rec = warp_sum(s_rec);
+        s_kl = warp_sum(s_kl);
+        s_m = warp_sum(s_m);
+        s_ls = warp_sum(s_ls);
+        if (lane == 0) {
+            scratch4[0][w] = s_rec;
+            scratch4[1][w] = s_kl;
+            scratch4[2][w] = s_m;
+            scratch4[3][w] = s_ls;
+        }
+        __syncthreads();
+        if (w == 0) {
+            constexpr int nw = kThreads / 32;
+            float a = lane < nw ? scratch4[0][lane] : 0.f, b = lane < nw ? scratch4[1][lane] : 0.f;
+            float c = lane < nw ? scratch4[2][lane] : 0.f, d = lane < nw ? scratch4[3][lane] : 0.f;
+            s_rec = warp_sum(a);
+            s_kl = warp_sum(b);
+            s_m = warp_sum(c);
+            s_ls = warp_sum(d);
+        }
+    }
     if (threadIdx.x == 0) {
         if (ext_sums != nullptr) {
             s_rec += ext_sums[0];
