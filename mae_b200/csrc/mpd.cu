@@ -945,7 +945,7 @@ int check_common(int64_t B, int64_t D, const void* ws, int64_t ws_bytes, Layout&
 
 // development aid (not part of include/mae_b200.h): per-role cycle counters of the last profiled tensor-core forward
 extern "C" int mae_debug_mpd_prof(long long* host_out) {
-    return (int)cudaMemcpyFromSymbol(host_out, mae::g_mpd_prof, sizeof(long long) * 32);
+    return (int)cudaMemcpyFromSymbol(host_out, mae::g_mpd_prof, sizeof(long long) * 64);
 }
 
 extern "C" int mae_set_mpd_tensor_cores(int enabled) {
@@ -1049,7 +1049,9 @@ extern "C" int mae_mpd_fwd(void* workspace, int64_t workspace_bytes, int64_t B, 
         launch_pdl(mpd_fwd_tc_kernel, dim3((unsigned)grid), dim3(kFwdTcThreads), (size_t)FwdTcSmem::kBytes, as_stream(stream),
             at<float>(workspace, L.tp), L.tp_mat, at<float>(workspace, L.c), at<float>(workspace, L.l),
             at<Hdr>(workspace, L.hdr), at<double>(workspace, L.part_fwd), (int)B, (int)L.Kp, (int)row0, (int)(row0 + nrows), tr0,
-            ntr, ntc, klp, full ? kltp : nullptr, (int)L.Bp, sumsq, S, 0, (int)kg.base, prof);
+            ntr, ntc, klp, (full && kg.tc_split == 0) ? kltp : nullptr, (int)L.Bp, sumsq, S, 0, (int)kg.base, prof);
+        // (full batch with the tensor-core backward: no KL^T, mpd_bwd_tc_kernel reads KL_ji from the columns of KL; K = 2D not a
+        //  multiple of 128: the FFMA stored-KL backward follows and wants both matrices)
         if (store_kl && !full) {
             const int tcb = (int)(kg.base / T), ntcb = (int)(kg.rows_pad / T), ntra = (int)(L.Bp / T);
             const int64_t nt2 = (int64_t)ntra * ntcb;
@@ -1116,6 +1118,7 @@ extern "C" int mae_mpd_bwd(const float* mu, int64_t mu_stride, const float* logv
         static const cudaError_t attr = cudaFuncSetAttribute(mpd_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                              BwdTcSmem::kBytes);
         if (attr != cudaSuccess) return (int)attr;
+        const bool full_rows = row0 == 0 && nrows == B;     // then the forward kept KL only: KL_ji is read from its columns
         const int tr0t = (int)(row0 / kTcT);
         const int ntrt = (int)(ceil_div(row0 + nrows, kTcT) - tr0t);
         const int ntc = (int)(L.Bp / kTcT);
@@ -1124,11 +1127,17 @@ extern "C" int mae_mpd_bwd(const float* mu, int64_t mu_stride, const float* logv
         float* gp = at<float>(workspace, kg.gp_off);
         float* rsp = at<float>(workspace, kg.rs_off);
         dim3 grid((unsigned)ntrt, (unsigned)(L.Kp / kTcT), (unsigned)nsplit);
+        static const bool want_bprof = getenv("MAE_MPD_PROF") != nullptr;
+        long long* bprof = nullptr;
+        if (want_bprof) {
+            cudaGetSymbolAddress(reinterpret_cast<void**>(&bprof), g_mpd_prof);
+            bprof += 32;
+        }
         launch_pdl(mpd_bwd_tc_kernel, grid, dim3(kBwdTcThreads), (size_t)BwdTcSmem::kBytes, as_stream(stream),
             at<float>(workspace, L.tp), L.tp_mat, at<Hdr>(workspace, L.hdr), (int)B, (int)L.Kp, (int)row0,
             (int)(row0 + nrows), tr0t, ntc, tps, at<float>(workspace, kg.kl_off) - kg.base * L.Bp,
-            at<float>(workspace, kg.klt_off) - kg.base * L.Bp, (int)L.Bp, gp, rsp, (int)kg.rows_pad, (int)kg.base,
-            tc_group_chunks());
+            full_rows ? nullptr : at<float>(workspace, kg.klt_off) - kg.base * L.Bp, (int)L.Bp, gp, rsp, (int)kg.rows_pad, (int)kg.base,
+            tc_group_chunks(), bprof);
         const int64_t n = nrows * D;
         mpd_bwd_tc_finish_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, as_stream(stream)>>>(
             mu, mu_stride, logvar, logvar_stride, at<float4>(workspace, L.vp), at<double>(workspace, L.colstats),

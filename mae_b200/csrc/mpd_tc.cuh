@@ -63,7 +63,7 @@ mpd_tile_panels_kernel(const float* __restrict__ Xp, const float* __restrict__ Y
     }
 }
 
-__device__ long long g_mpd_prof[32];     // MAE_MPD_PROF=1: per-role cycle counters (development aid)
+__device__ long long g_mpd_prof[64];     // MAE_MPD_PROF=1: per-role cycle counters (development aid)
 
 constexpr int kFwdAStages = 3;       // TMEM operand stages (A = x~ rows)
 constexpr int kFwdBStages = 4;       // shared-memory stages (B = y~ rows, filled by the bulk-copy engine)
@@ -369,8 +369,29 @@ __global__ void __launch_bounds__(kBwdTcThreads, 1)
 mpd_bwd_tc_kernel(const float* __restrict__ tp, int64_t mat, const Hdr* __restrict__ hdr, int B, int Kp,
                   int row0, int row1, int tr0, int ntc, int tiles_per_split, const float* __restrict__ KL,
                   const float* __restrict__ KLT, int Bp, float* __restrict__ gpart, float* __restrict__ rspart, int rows_pad,
-                  int gbase, int group_chunks) {
-    // KL / KLT: pre-offset so that global row i is at [i * Bp] (row blocks keep only their rows).  gpart
+                  int gbase, int group_chunks, long long* prof) {
+    long long pw0 = 0, pw1 = 0, pw2 = 0;
+    auto wait = [&](uint64_t* bar, uint32_t parity, long long& acc) {
+        if (prof != nullptr) {
+            const long long t0 = clock64();
+            tc5::mbar_wait(bar, parity);
+            acc += clock64() - t0;
+        } else {
+            tc5::mbar_wait(bar, parity);
+        }
+    };
+    const long long t_start = prof != nullptr ? clock64() : 0;
+    auto report = [&](int slot) {
+        if (prof != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+            prof[slot] = clock64() - t_start;
+            prof[slot + 1] = pw0;
+            prof[slot + 2] = pw1;
+            prof[slot + 3] = pw2;
+        }
+    };
+    // KL / KLT: pre-offset so that global row i is at [i * Bp] (row blocks keep only their rows).  KLT == nullptr (full
+    // batch): KL_ji of row i is read from COLUMN i of KL - for a fixed partner j the 32 lanes of a warp (= 32 consecutive
+    // rows i) read one 128-byte line, so the transposed matrix is neither written by the forward nor needed here.  gpart
     // [split][2][rows_pad][Kp], rspart [split][2][rows_pad], local row = i - gbase.
     // group_chunks: chunks of 32 partners per TMEM accumulation.  The tensor core's accumulator does not round to nearest, so
     // the error of a running sum grows with its length; after every group the owners of the rows add the accumulator to the
@@ -422,29 +443,35 @@ mpd_bwd_tc_kernel(const float* __restrict__ tp, int64_t mat, const Hdr* __restri
         const int i = ti * kTcT + t;
         const bool row_ok = (i >= row0) && (i < row1);
         const float m = (float)hdr->m;
-        const float* krow = (which == 0 ? KL : KLT) + (int64_t)i * Bp;
+        const bool by_col = which == 1 && KLT == nullptr;
+        const float* krow = by_col ? KL + i : (which == 0 ? KL : KLT) + (int64_t)i * Bp;
         uint64_t* wfull = which == 0 ? w1full : w2full;
         const uint32_t tw = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(256 + which * 128);
         float rs = 0.f;
         const int lrow = i - gbase;
         const uint32_t tacc = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(which * kTcT);
         float* dst = gpart + (((int64_t)split * 2 + which) * rows_pad + lrow) * Kp + kbase;
-        float4 nxt[kTcKC / 4];
-        if (total > 0) {
+        float nxt[kTcKC];
+        auto load = [&](int j0) {      // the 32 values KL_ij (row-wise, 16-byte loads) or KL_ji (column-wise, coalesced 4-byte loads)
+            if (by_col) {
 #pragma unroll
-            for (int g4 = 0; g4 < kTcKC / 4; ++g4) nxt[g4] = __ldg(reinterpret_cast<const float4*>(krow + tj0 * kTcT + 4 * g4));
-        }
+                for (int j = 0; j < kTcKC; ++j) nxt[j] = __ldg(krow + (int64_t)(j0 + j) * Bp);
+            } else {
+                const float* src = krow + j0;
+#pragma unroll
+                for (int g4 = 0; g4 < kTcKC / 4; ++g4) {
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(src + 4 * g4));
+                    nxt[4 * g4] = v.x; nxt[4 * g4 + 1] = v.y; nxt[4 * g4 + 2] = v.z; nxt[4 * g4 + 3] = v.w;
+                }
+            }
+        };
+        if (total > 0) load(tj0 * kTcT);
         for (int qn = 0; qn < total; ++qn) {
             float h[kTcKC], l[kTcKC];
 #pragma unroll
-            for (int g4 = 0; g4 < kTcKC / 4; ++g4) {
-                h[4 * g4] = nxt[g4].x; h[4 * g4 + 1] = nxt[g4].y; h[4 * g4 + 2] = nxt[g4].z; h[4 * g4 + 3] = nxt[g4].w;
-            }
+            for (int j = 0; j < kTcKC; ++j) h[j] = nxt[j];
             const int j0 = tj0 * kTcT + qn * kTcKC;
-            if (qn + 1 < total) {
-#pragma unroll
-                for (int g4 = 0; g4 < kTcKC / 4; ++g4) nxt[g4] = __ldg(reinterpret_cast<const float4*>(krow + j0 + kTcKC + 4 * g4));
-            }
+            if (qn + 1 < total) load(j0 + kTcKC);
             const bool plain = row_ok && (j0 + kTcKC <= B) && (i < j0 || i >= j0 + kTcKC);
 #pragma unroll
             for (int j = 0; j < kTcKC; ++j) {
@@ -454,7 +481,7 @@ mpd_bwd_tc_kernel(const float* __restrict__ tp, int64_t mat, const Hdr* __restri
                 tc5::split_tf32(w, h[j], l[j]);
             }
             const int s = qn % kBwdWStages;
-            tc5::mbar_wait(&wempty[s], ((uint32_t)(qn / kBwdWStages) & 1u) ^ 1u);
+            wait(&wempty[s], ((uint32_t)(qn / kBwdWStages) & 1u) ^ 1u, pw0);
             tc5::fence_after_sync();
             const uint32_t tws = tw + (uint32_t)(s * 2 * kTcKC);
 #pragma unroll
@@ -469,7 +496,7 @@ mpd_bwd_tc_kernel(const float* __restrict__ tp, int64_t mat, const Hdr* __restri
             if ((qn + 1) % group_chunks == 0 || qn + 1 == total) {
                 // end of an accumulation group: this warpgroup's accumulator (G1 or G2) -> fp32 partial sums in global memory
                 const int g = qn / group_chunks;
-                tc5::mbar_wait(gfull, (uint32_t)g & 1u);
+                wait(gfull, (uint32_t)g & 1u, pw1);
                 tc5::fence_after_sync();
 #pragma unroll 1
                 for (int c0 = 0; c0 < kTcT; c0 += 16) {
@@ -492,6 +519,7 @@ mpd_bwd_tc_kernel(const float* __restrict__ tp, int64_t mat, const Hdr* __restri
                 if (lane == 0) tc5::mbar_arrive(gdrained);
             }
         }
+        if (t == 0) report(4 * which);
         if (blockIdx.y == 0) rspart[((int64_t)split * 2 + which) * rows_pad + lrow] = rs;
         if (total == 0) {
             for (int c0 = 0; c0 < kTcT; c0 += 4) *reinterpret_cast<float4*>(dst + c0) = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -504,12 +532,13 @@ mpd_bwd_tc_kernel(const float* __restrict__ tp, int64_t mat, const Hdr* __restri
                 const int tj = tj0 + qn / (kTcT / kTcKC), jc = qn % (kTcT / kTcKC);
                 const int64_t o = ((((int64_t)tj * ncn + blockIdx.y) * 32 + jc * 8) * 128) * 4;
                 const int s = qn % kBwdPStages;
-                tc5::mbar_wait(&pempty[s], ((uint32_t)(qn / kBwdPStages) & 1u) ^ 1u);
+                wait(&pempty[s], ((uint32_t)(qn / kBwdPStages) & 1u) ^ 1u, pw0);
                 tc5::mbar_expect_tx(&pfull[s], kBwdTcStageB);
                 uint8_t* st = smem + s * kBwdTcStageB;
 #pragma unroll
                 for (int q4 = 0; q4 < 4; ++q4) tc5::bulk_g2s(st + q4 * kTcHalf, tp + (4 + q4) * mat + o, kTcHalf, &pfull[s]);
             }
+            report(8);
         }
     } else if (warp == 8 && lane == 0) {
         // ------------------------------------------------------------ MMA issuer
@@ -520,12 +549,12 @@ mpd_bwd_tc_kernel(const float* __restrict__ tp, int64_t mat, const Hdr* __restri
             const int sw = qn % kBwdWStages, sp = qn % kBwdPStages;
             const int gq = qn % group_chunks;
             if (gq == 0 && qn > 0) {       // the previous group's sums have been read out of the accumulators
-                tc5::mbar_wait(gdrained, (uint32_t)(qn / group_chunks - 1) & 1u);
+                wait(gdrained, (uint32_t)(qn / group_chunks - 1) & 1u, pw2);
                 tc5::fence_after_sync();
             }
-            tc5::mbar_wait(&w1full[sw], (uint32_t)(qn / kBwdWStages) & 1u);
-            tc5::mbar_wait(&w2full[sw], (uint32_t)(qn / kBwdWStages) & 1u);
-            tc5::mbar_wait(&pfull[sp], (uint32_t)(qn / kBwdPStages) & 1u);
+            wait(&w1full[sw], (uint32_t)(qn / kBwdWStages) & 1u, pw0);
+            wait(&w2full[sw], (uint32_t)(qn / kBwdWStages) & 1u, pw0);
+            wait(&pfull[sp], (uint32_t)(qn / kBwdPStages) & 1u, pw1);
             tc5::fence_after_sync();
             const uint32_t w1h = tmem_base + (uint32_t)(256 + sw * 2 * kTcKC), w1l = w1h + kTcKC;
             const uint32_t w2h = tmem_base + (uint32_t)(384 + sw * 2 * kTcKC), w2l = w2h + kTcKC;
@@ -548,6 +577,7 @@ mpd_bwd_tc_kernel(const float* __restrict__ tp, int64_t mat, const Hdr* __restri
             tc5::mma_commit(&pempty[sp]);
             if (gq + 1 == group_chunks || qn + 1 == total) tc5::mma_commit(gfull);
         }
+        report(12);
     }
     tc5::fence_before_sync();
     __syncthreads();

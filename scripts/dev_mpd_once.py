@@ -16,7 +16,7 @@ print("done", float(s))
 import ctypes, os
 if os.environ.get("MAE_MPD_PROF"):
     lib = _lib.load()
-    out = (ctypes.c_longlong * 32)()
+    out = (ctypes.c_longlong * 64)()
     lib.mae_debug_mpd_prof(out)
     ntile = ((b + 127) // 128) ** 2
     per = -(-ntile // 148)
@@ -25,3 +25,8 @@ if os.environ.get("MAE_MPD_PROF"):
         tot = max(out[k], 1)
         print("%-44s total %9d cyc (%6.0f / tile)  wait0 %5.1f %%  wait1 %5.1f %%" % (nm, out[k], out[k] / per, 100.0 * out[k + 1] / tot, 100.0 * out[k + 2] / tot))
     print("   of the mma issuer's wait1, waiting for B (bulk copies): %.1f %% of its loop" % (100.0 * out[31] / max(out[20], 1)))
+    nchunk = ((b + 127) // 128) * 4
+    print("backward CTA (0,0,0): chunks of 32 partners =", nchunk, "(divided by the partner splits)")
+    for k, nm in {32: "W1 rows (wait wempty, wait gfull)", 36: "W2 rows", 40: "loader (wait pempty)", 44: "mma issuer (wait w1+w2 full, wait pfull, wait gdrained)"}.items():
+        tot = max(out[k], 1)
+        print("%-58s total %9d cyc  wait0 %5.1f %%  wait1 %5.1f %%  wait2 %5.1f %%" % (nm, out[k], 100.0 * out[k + 1] / tot, 100.0 * out[k + 2] / tot, 100.0 * out[k + 3] / tot))
