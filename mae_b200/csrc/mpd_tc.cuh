@@ -65,7 +65,7 @@ mpd_tile_panels_kernel(const float* __restrict__ Xp, const float* __restrict__ Y
 
 __device__ long long g_mpd_prof[64];     // MAE_MPD_PROF=1: per-role cycle counters (development aid)
 
-constexpr int kFwdAStages = 3;       // TMEM operand stages (A = x~ rows)
+constexpr int kFwdAStages = 4;       // TMEM operand stages (A = x~ rows): 256 + 4 * 64 = all 512 columns
 constexpr int kFwdBStages = 4;       // shared-memory stages (B = y~ rows, filled by the bulk-copy engine)
 struct FwdTcSmem {
     static constexpr int kBOff = 0;
@@ -317,8 +317,11 @@ mpd_fwd_tc_kernel(const float* __restrict__ tp, int64_t mat, const float* __rest
             wait(&tempty[a], ((uint32_t)use & 1u) ^ 1u, pw0);
             tc5::fence_after_sync();
             const uint32_t d = tmem_base + (uint32_t)(a * kTcT);
-            for (int kc = 0; kc < nchunk; ++kc, ++qn) {
-                const int sa = qn % kFwdAStages, sb = qn % kFwdBStages;
+            // one chunk: wait for both operands, 4 k-steps x 3 products, release the stages.  With K = 2D a multiple of 128
+            // the chunk count per tile is a multiple of the stage count, so the stage index is the unroll index and every
+            // descriptor is loop-invariant (the issuing thread's uniform-datapath arithmetic was on the critical path:
+            // 75 % busy at 2.2x the tensor pipe's 64 cycles per MMA)
+            auto chunk = [&](int kc, int sa, int sb) {
                 wait(&afull[sa], (uint32_t)(qn / kFwdAStages) & 1u, pw1);
                 { long long tmpw = 0; wait(&bfull[sb], (uint32_t)(qn / kFwdBStages) & 1u, tmpw); pw1 += tmpw; if (prof) prof[31] += tmpw; }
                 tc5::fence_after_sync();
@@ -334,6 +337,18 @@ mpd_fwd_tc_kernel(const float* __restrict__ tp, int64_t mat, const float* __rest
                 }
                 tc5::mma_commit(&aempty[sa]);
                 tc5::mma_commit(&bempty[sb]);
+                ++qn;
+            };
+            static_assert(kFwdAStages == 4 && kFwdBStages == 4, "the unrolled issue loop assumes four stages of each operand");
+            if ((nchunk & 3) == 0) {
+                for (int kc = 0; kc < nchunk; kc += 4) {
+                    chunk(kc, 0, 0);
+                    chunk(kc + 1, 1, 1);
+                    chunk(kc + 2, 2, 2);
+                    chunk(kc + 3, 3, 3);
+                }
+            } else {
+                for (int kc = 0; kc < nchunk; ++kc) chunk(kc, qn % kFwdAStages, qn % kFwdBStages);
             }
             tc5::mma_commit(&tfull[a]);
         }
