@@ -926,7 +926,7 @@ KlGeom kl_geom(const Layout& L, int64_t B, int64_t row0, int64_t nrows) {
         g.tc_split = tc_splits(g.rows_pad / 128, L.Kp / 128, L.Bp / 128);
         g.gp_off = g.total;
         g.rs_off = g.gp_off + round_up(2 * g.tc_split * g.rows_pad * L.Kp * 4, 256);
-        g.total = g.rs_off + round_up(2 * g.tc_split * g.rows_pad * 4, 256);
+        g.total = g.rs_off + round_up(4 * g.tc_split * g.rows_pad * 4, 256);
     }
     return g;
 }

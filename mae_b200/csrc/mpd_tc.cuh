@@ -378,7 +378,7 @@ struct BwdTcSmem {
     static constexpr int kSlotOff = kBarOff + kNumBars * 8;
     static constexpr int kBytes = kSlotOff + 32;
 };
-constexpr int kBwdTcThreads = (4 + 4 + 1 + 1) * 32;   // W1 rows, W2 rows, MMA warp, loader warp
+constexpr int kBwdTcThreads = (16 + 1 + 1) * 32;   // two pairs of (W1 rows, W2 rows) warpgroups, MMA warp, loader warp
 
 __global__ void __launch_bounds__(kBwdTcThreads, 1)
 mpd_bwd_tc_kernel(const float* __restrict__ tp, int64_t mat, const Hdr* __restrict__ hdr, int B, int Kp,
@@ -404,6 +404,7 @@ mpd_bwd_tc_kernel(const float* __restrict__ tp, int64_t mat, const Hdr* __restri
             prof[slot + 3] = pw2;
         }
     };
+    // rspart [split][2][2 pairs][rows_pad].
     // KL / KLT: pre-offset so that global row i is at [i * Bp] (row blocks keep only their rows).  KLT == nullptr (full
     // batch): KL_ji of row i is read from COLUMN i of KL - for a fixed partner j the 32 lanes of a warp (= 32 consecutive
     // rows i) read one 128-byte line, so the transposed matrix is neither written by the forward nor needed here.  gpart
@@ -442,18 +443,21 @@ mpd_bwd_tc_kernel(const float* __restrict__ tp, int64_t mat, const Hdr* __restri
             tc5::mbar_init(&pempty[s], 1);
         }
         tc5::mbar_init(gfull, 1);
-        tc5::mbar_init(gdrained, 8);
+        tc5::mbar_init(gdrained, 16);
         tc5::fence_barrier_init();
     }
-    if (warp == 8) tc5::tmem_alloc(tmem_slot, 512);
+    if (warp == 16) tc5::tmem_alloc(tmem_slot, 512);
     tc5::fence_before_sync();
     __syncthreads();
     tc5::fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp < 8) {
-        // ------------------------------------------------------------ weights: thread = row i, which = 0: KL_ij, 1: KL_ji
-        const int which = warp >> 2;
+    if (warp < 16) {
+        // ------------------------------------------------------------ weights: thread = row i; which = 0: KL_ij, 1: KL_ji;
+        // two PAIRS of (W1, W2) warpgroups take alternate chunks (pair p owns TMEM weight stage p): while one pair waits for
+        // its 32 loads from HBM the other forms, splits and stores its weights - latency is hidden by the second pair instead
+        // of a register prefetch (a single pair was busy 95 % and the MMA issuer waited 29-50 % for it)
+        const int pair = warp >> 3, which = (warp >> 2) & 1;
         const int t = ((warp & 3) << 5) | lane;
         const int i = ti * kTcT + t;
         const bool row_ok = (i >= row0) && (i < row1);
@@ -461,85 +465,83 @@ mpd_bwd_tc_kernel(const float* __restrict__ tp, int64_t mat, const Hdr* __restri
         const bool by_col = which == 1 && KLT == nullptr;
         const float* krow = by_col ? KL + i : (which == 0 ? KL : KLT) + (int64_t)i * Bp;
         uint64_t* wfull = which == 0 ? w1full : w2full;
-        const uint32_t tw = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(256 + which * 128);
+        const uint32_t tws = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(256 + which * 128 + pair * 2 * kTcKC);
         float rs = 0.f;
         const int lrow = i - gbase;
-        const uint32_t tacc = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(which * kTcT);
-        float* dst = gpart + (((int64_t)split * 2 + which) * rows_pad + lrow) * Kp + kbase;
-        float nxt[kTcKC];
-        auto load = [&](int j0) {      // the 32 values KL_ij (row-wise, 16-byte loads) or KL_ji (column-wise, coalesced 4-byte loads)
-            if (by_col) {
+        // this pair drains columns [64 pair, 64 pair + 64) of its accumulator
+        const uint32_t tacc = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(which * kTcT + pair * 64);
+        float* dst = gpart + (((int64_t)split * 2 + which) * rows_pad + lrow) * Kp + kbase + pair * 64;
+        const int ngroups = (total + group_chunks - 1) / group_chunks;
+        int use = 0;       // chunks this pair has produced (parity of its stage's empty barrier)
+        for (int g = 0; g < ngroups; ++g) {
+            const int q_end = min(total, (g + 1) * group_chunks);
+            int q0 = g * group_chunks;
+            q0 += ((q0 & 1) != pair) ? 1 : 0;
+            for (int qn = q0; qn < q_end; qn += 2, ++use) {
+                const int j0 = tj0 * kTcT + qn * kTcKC;
+                float v[kTcKC];
+                if (by_col) {        // KL_ji from column i of KL: for a fixed j the lanes (consecutive i) read one 128-byte line
 #pragma unroll
-                for (int j = 0; j < kTcKC; ++j) nxt[j] = __ldg(krow + (int64_t)(j0 + j) * Bp);
-            } else {
-                const float* src = krow + j0;
+                    for (int j = 0; j < kTcKC; ++j) v[j] = __ldg(krow + (int64_t)(j0 + j) * Bp);
+                } else {
 #pragma unroll
-                for (int g4 = 0; g4 < kTcKC / 4; ++g4) {
-                    const float4 v = __ldg(reinterpret_cast<const float4*>(src + 4 * g4));
-                    nxt[4 * g4] = v.x; nxt[4 * g4 + 1] = v.y; nxt[4 * g4 + 2] = v.z; nxt[4 * g4 + 3] = v.w;
-                }
-            }
-        };
-        if (total > 0) load(tj0 * kTcT);
-        for (int qn = 0; qn < total; ++qn) {
-            float h[kTcKC], l[kTcKC];
-#pragma unroll
-            for (int j = 0; j < kTcKC; ++j) h[j] = nxt[j];
-            const int j0 = tj0 * kTcT + qn * kTcKC;
-            if (qn + 1 < total) load(j0 + kTcKC);
-            const bool plain = row_ok && (j0 + kTcKC <= B) && (i < j0 || i >= j0 + kTcKC);
-#pragma unroll
-            for (int j = 0; j < kTcKC; ++j) {
-                const bool ok = plain || (row_ok && (j0 + j) < B && (j0 + j) != i);
-                const float w = ok ? h[j] - m : 0.f;
-                rs += w;
-                tc5::split_tf32(w, h[j], l[j]);
-            }
-            const int s = qn % kBwdWStages;
-            wait(&wempty[s], ((uint32_t)(qn / kBwdWStages) & 1u) ^ 1u, pw0);
-            tc5::fence_after_sync();
-            const uint32_t tws = tw + (uint32_t)(s * 2 * kTcKC);
-#pragma unroll
-            for (int j = 0; j < kTcKC; j += 16) {
-                tc5::tmem_st16(tws + j, h + j);
-                tc5::tmem_st16(tws + kTcKC + j, l + j);
-            }
-            tc5::tmem_st_wait();
-            tc5::fence_before_sync();
-            __syncwarp();
-            if (lane == 0) tc5::mbar_arrive(&wfull[s]);
-            if ((qn + 1) % group_chunks == 0 || qn + 1 == total) {
-                // end of an accumulation group: this warpgroup's accumulator (G1 or G2) -> fp32 partial sums in global memory
-                const int g = qn / group_chunks;
-                wait(gfull, (uint32_t)g & 1u, pw1);
-                tc5::fence_after_sync();
-#pragma unroll 1
-                for (int c0 = 0; c0 < kTcT; c0 += 16) {
-                    float v[16];
-                    tc5::tmem_ld16(tacc + c0, v);
-                    tc5::tmem_ld_wait();
-#pragma unroll
-                    for (int g4 = 0; g4 < 4; ++g4) {
-                        float4* p = reinterpret_cast<float4*>(dst + c0 + 4 * g4);
-                        float4 o = make_float4(v[4 * g4], v[4 * g4 + 1], v[4 * g4 + 2], v[4 * g4 + 3]);
-                        if (g > 0) {
-                            const float4 b = *p;
-                            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-                        }
-                        *p = o;
+                    for (int g4 = 0; g4 < kTcKC / 4; ++g4) {
+                        const float4 q4 = __ldg(reinterpret_cast<const float4*>(krow + j0 + 4 * g4));
+                        v[4 * g4] = q4.x; v[4 * g4 + 1] = q4.y; v[4 * g4 + 2] = q4.z; v[4 * g4 + 3] = q4.w;
                     }
                 }
+                const bool plain = row_ok && (j0 + kTcKC <= B) && (i < j0 || i >= j0 + kTcKC);
+                wait(&wempty[pair], ((uint32_t)use & 1u) ^ 1u, pw0);
+                tc5::fence_after_sync();
+#pragma unroll
+                for (int h0 = 0; h0 < kTcKC; h0 += 16) {
+                    float h[16], l[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const bool ok = plain || (row_ok && (j0 + h0 + j) < B && (j0 + h0 + j) != i);
+                        const float w = ok ? v[h0 + j] - m : 0.f;
+                        rs += w;
+                        tc5::split_tf32(w, h[j], l[j]);
+                    }
+                    tc5::tmem_st16(tws + h0, h);
+                    tc5::tmem_st16(tws + kTcKC + h0, l);
+                }
+                tc5::tmem_st_wait();
                 tc5::fence_before_sync();
                 __syncwarp();
-                if (lane == 0) tc5::mbar_arrive(gdrained);
+                if (lane == 0) tc5::mbar_arrive(&wfull[pair]);
             }
+            // end of an accumulation group: this warpgroup's half of its accumulator (G1 or G2) -> fp32 partial sums
+            wait(gfull, (uint32_t)g & 1u, pw1);
+            tc5::fence_after_sync();
+            const long long td0 = prof != nullptr ? clock64() : 0;
+#pragma unroll 1
+            for (int c0 = 0; c0 < 64; c0 += 16) {
+                float a16[16];
+                tc5::tmem_ld16(tacc + c0, a16);
+                tc5::tmem_ld_wait();
+#pragma unroll
+                for (int g4 = 0; g4 < 4; ++g4) {
+                    float4* p = reinterpret_cast<float4*>(dst + c0 + 4 * g4);
+                    float4 o = make_float4(a16[4 * g4], a16[4 * g4 + 1], a16[4 * g4 + 2], a16[4 * g4 + 3]);
+                    if (g > 0) {
+                        const float4 bsum = *p;
+                        o.x += bsum.x; o.y += bsum.y; o.z += bsum.z; o.w += bsum.w;
+                    }
+                    *p = o;
+                }
+            }
+            tc5::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc5::mbar_arrive(gdrained);
+            if (prof != nullptr) pw2 += clock64() - td0;
         }
-        if (t == 0) report(4 * which);
-        if (blockIdx.y == 0) rspart[((int64_t)split * 2 + which) * rows_pad + lrow] = rs;
+        if (t == 0 && pair == 0) report(4 * which);
+        if (blockIdx.y == 0) rspart[(((int64_t)split * 2 + which) * 2 + pair) * rows_pad + lrow] = rs;
         if (total == 0) {
-            for (int c0 = 0; c0 < kTcT; c0 += 4) *reinterpret_cast<float4*>(dst + c0) = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int c0 = 0; c0 < 64; c0 += 4) *reinterpret_cast<float4*>(dst + c0) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-    } else if (warp == 9) {
+    } else if (warp == 17) {
         // ------------------------------------------------------------ loader: the four 16 KB operand halves of a chunk
         if (lane == 0) {
             const int ncn = Kp / 128;
@@ -555,7 +557,7 @@ mpd_bwd_tc_kernel(const float* __restrict__ tp, int64_t mat, const Hdr* __restri
             }
             report(8);
         }
-    } else if (warp == 8 && lane == 0) {
+    } else if (warp == 16 && lane == 0) {
         // ------------------------------------------------------------ MMA issuer
         constexpr uint32_t idesc = tc5::idesc_tf32(kTcT, kTcT);
         const uint32_t st_a = tc5::smem_u32(smem);
@@ -596,7 +598,7 @@ mpd_bwd_tc_kernel(const float* __restrict__ tp, int64_t mat, const Hdr* __restri
     }
     tc5::fence_before_sync();
     __syncthreads();
-    if (warp == 8) {
+    if (warp == 16) {
         tc5::fence_after_sync();
         tc5::tmem_dealloc(tmem_base, 512);
     }
@@ -621,8 +623,8 @@ mpd_bwd_tc_finish_kernel(const float* __restrict__ mu, int64_t mu_stride, const 
             const float2 a = *reinterpret_cast<const float2*>(gpart + (((int64_t)sp * 2 + 0) * rows_pad + lrow) * Kp + 2 * d);
             const float2 b = *reinterpret_cast<const float2*>(gpart + (((int64_t)sp * 2 + 1) * rows_pad + lrow) * Kp + 2 * d);
             g1r += a.x; g1m += a.y; g2x += b.x; g2m += b.y;
-            rs1 += rspart[((int64_t)sp * 2 + 0) * rows_pad + lrow];
-            rs2 += rspart[((int64_t)sp * 2 + 1) * rows_pad + lrow];
+            rs1 += rspart[(((int64_t)sp * 2 + 0) * 2 + 0) * rows_pad + lrow] + rspart[(((int64_t)sp * 2 + 0) * 2 + 1) * rows_pad + lrow];
+            rs2 += rspart[(((int64_t)sp * 2 + 1) * 2 + 0) * rows_pad + lrow] + rspart[(((int64_t)sp * 2 + 1) * 2 + 1) * rows_pad + lrow];
         }
         g1r *= beta; g1m *= beta; g2x *= beta; g2m *= beta; rs1 *= beta; rs2 *= beta;
     }
