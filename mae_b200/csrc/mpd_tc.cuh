@@ -404,7 +404,7 @@ mpd_bwd_tc_kernel(const float* __restrict__ tp, int64_t mat, const Hdr* __restri
             prof[slot + 3] = pw2;
         }
     };
-    // rspart [split][2][2 pairs][rows_pad].
+    // gpart [split][2][Kp][rows_pad] (column-major per matrix), rspart [split][2][2 pairs][rows_pad].
     // KL / KLT: pre-offset so that global row i is at [i * Bp] (row blocks keep only their rows).  KLT == nullptr (full
     // batch): KL_ji of row i is read from COLUMN i of KL - for a fixed partner j the 32 lanes of a warp (= 32 consecutive
     // rows i) read one 128-byte line, so the transposed matrix is neither written by the forward nor needed here.  gpart
@@ -470,7 +470,7 @@ mpd_bwd_tc_kernel(const float* __restrict__ tp, int64_t mat, const Hdr* __restri
         const int lrow = i - gbase;
         // this pair drains columns [64 pair, 64 pair + 64) of its accumulator
         const uint32_t tacc = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(which * kTcT + pair * 64);
-        float* dst = gpart + (((int64_t)split * 2 + which) * rows_pad + lrow) * Kp + kbase + pair * 64;
+        float* dst = gpart + (((int64_t)split * 2 + which) * Kp + kbase + pair * 64) * rows_pad + lrow;   // [k][row], see the drain
         const int ngroups = (total + group_chunks - 1) / group_chunks;
         int use = 0;       // chunks this pair has produced (parity of its stage's empty barrier)
         for (int g = 0; g < ngroups; ++g) {
@@ -515,20 +515,30 @@ mpd_bwd_tc_kernel(const float* __restrict__ tp, int64_t mat, const Hdr* __restri
             wait(gfull, (uint32_t)g & 1u, pw1);
             tc5::fence_after_sync();
             const long long td0 = prof != nullptr ? clock64() : 0;
+            // gpart is COLUMN-major per (split, which): [k][row].  The owner of row i holds one accumulator row (TMEM lane), so
+            // for a fixed column the 32 lanes of a warp touch 32 consecutive floats = one 128-byte line: every load and store
+            // of the drain is fully coalesced.  (Row-major partial sums - 16-byte accesses 512 bytes apart, 32 half-used
+            // sectors per request - made the drains 0.28 ms of a 1.25 ms kernel; serialised loads were not the cause.)
+            if (g > 0) {
 #pragma unroll 1
-            for (int c0 = 0; c0 < 64; c0 += 16) {
-                float a16[16];
-                tc5::tmem_ld16(tacc + c0, a16);
-                tc5::tmem_ld_wait();
+                for (int c0 = 0; c0 < 64; c0 += 16) {
+                    float old[16];
 #pragma unroll
-                for (int g4 = 0; g4 < 4; ++g4) {
-                    float4* p = reinterpret_cast<float4*>(dst + c0 + 4 * g4);
-                    float4 o = make_float4(a16[4 * g4], a16[4 * g4 + 1], a16[4 * g4 + 2], a16[4 * g4 + 3]);
-                    if (g > 0) {
-                        const float4 bsum = *p;
-                        o.x += bsum.x; o.y += bsum.y; o.z += bsum.z; o.w += bsum.w;
-                    }
-                    *p = o;
+                    for (int c = 0; c < 16; ++c) old[c] = __ldcg(dst + (int64_t)(c0 + c) * rows_pad);
+                    float a16[16];
+                    tc5::tmem_ld16(tacc + c0, a16);
+                    tc5::tmem_ld_wait();
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) dst[(int64_t)(c0 + c) * rows_pad] = a16[c] + old[c];
+                }
+            } else {
+#pragma unroll 1
+                for (int c0 = 0; c0 < 64; c0 += 16) {
+                    float a16[16];
+                    tc5::tmem_ld16(tacc + c0, a16);
+                    tc5::tmem_ld_wait();
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) dst[(int64_t)(c0 + c) * rows_pad] = a16[c];
                 }
             }
             tc5::fence_before_sync();
@@ -539,7 +549,7 @@ mpd_bwd_tc_kernel(const float* __restrict__ tp, int64_t mat, const Hdr* __restri
         if (t == 0 && pair == 0) report(4 * which);
         if (blockIdx.y == 0) rspart[(((int64_t)split * 2 + which) * 2 + pair) * rows_pad + lrow] = rs;
         if (total == 0) {
-            for (int c0 = 0; c0 < 64; c0 += 4) *reinterpret_cast<float4*>(dst + c0) = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int c = 0; c < 64; ++c) dst[(int64_t)c * rows_pad] = 0.f;
         }
     } else if (warp == 17) {
         // ------------------------------------------------------------ loader: the four 16 KB operand halves of a chunk
@@ -614,15 +624,15 @@ mpd_bwd_tc_finish_kernel(const float* __restrict__ mu, int64_t mu_stride, const 
                          float* __restrict__ dmu, float* __restrict__ dlv, int accumulate) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (int64_t)nrows * D) return;
-    const int i = row0 + (int)(idx / D), d = (int)(idx % D);
+    const int i = row0 + (int)(idx % nrows), d = (int)(idx / nrows);     // rows fastest: the [k][row] partial sums are read coalesced
     const int lrow = i - gbase;
     const float beta = weight_scale(g_S, S, B);
     float g1r = 0.f, g1m = 0.f, g2x = 0.f, g2m = 0.f, rs1 = 0.f, rs2 = 0.f;
     if (beta != 0.f) {
         for (int sp = 0; sp < nsplit; ++sp) {
-            const float2 a = *reinterpret_cast<const float2*>(gpart + (((int64_t)sp * 2 + 0) * rows_pad + lrow) * Kp + 2 * d);
-            const float2 b = *reinterpret_cast<const float2*>(gpart + (((int64_t)sp * 2 + 1) * rows_pad + lrow) * Kp + 2 * d);
-            g1r += a.x; g1m += a.y; g2x += b.x; g2m += b.y;
+            const float* p1 = gpart + (((int64_t)sp * 2 + 0) * Kp + 2 * d) * rows_pad + lrow;
+            const float* p2 = gpart + (((int64_t)sp * 2 + 1) * Kp + 2 * d) * rows_pad + lrow;
+            g1r += p1[0]; g1m += p1[rows_pad]; g2x += p2[0]; g2m += p2[rows_pad];
             rs1 += rspart[(((int64_t)sp * 2 + 0) * 2 + 0) * rows_pad + lrow] + rspart[(((int64_t)sp * 2 + 0) * 2 + 1) * rows_pad + lrow];
             rs2 += rspart[(((int64_t)sp * 2 + 1) * 2 + 0) * rows_pad + lrow] + rspart[(((int64_t)sp * 2 + 1) * 2 + 1) * rows_pad + lrow];
         }
