@@ -721,6 +721,52 @@ def test_fused_head_under_cuda_graph(ops, O):
     assert torch.equal(mu.grad, ref_gmu) and torch.equal(raw.grad, ref_graw)
 
 
+@pytest.mark.parametrize("one_node", [True, False])
+@pytest.mark.parametrize("order", ["ab", "ba", "read_first"])
+def test_two_heads_interleaved_with_deferred_join(ops, order, one_node, monkeypatch):
+    """Two models on one device whose loss() calls interleave (mae and mae_shadow of experiments/binary_image.py:106-108,304)
+    share the per-device side stream and its join bookkeeping (ops._pending_join / _grads_ready).  Every side-stream launch
+    of a device is ordered on ONE stream, so a join on the latest event covers all earlier work, and a popped or foreign
+    'gradients ready' event falls back to a full stream wait: interleaved deferred heads must reproduce, bit for bit, what
+    each head gives alone."""
+    from mae_b200 import heads, synth
+    monkeypatch.setattr(heads, "ONE_NODE", one_node)
+
+    def inputs(seed, b, d):
+        mu0, lv0 = synth.posterior_params(b, (d,), seed=seed, clamp=True)
+        inp = synth.color_head(b, 1, 10, 16, 16, seed=seed + 1)
+        return [cu(mu0), cu(lv0), cu(synth.noise(b, 1, (d,), seed=seed)), cu(inp["raw"]), cu(inp["x"])]
+
+    def fresh(t):
+        return [t[0].clone().requires_grad_(), t[1].clone().requires_grad_(), t[2], t[3].clone().requires_grad_(), t[4]]
+
+    def alone(t):
+        a = fresh(t)
+        out = heads.loss_head_color(*a, 10, 1.0, 1.0, 0.0, defer_join=False)
+        out[0].backward()
+        torch.cuda.synchronize()
+        return [o.detach().clone() for o in (out[0], out[1], out[2], out[3][0])] + [a[0].grad, a[1].grad, a[3].grad]
+
+    ta, tb = inputs(21, 48, 32), inputs(23, 200, 70)        # cluster-kernel shape and general-chain shape
+    ref_a, ref_b = alone(ta), alone(tb)
+    a, b = fresh(ta), fresh(tb)
+    out_a = heads.loss_head_color(*a, 10, 1.0, 1.0, 0.0, defer_join=True)
+    out_b = heads.loss_head_color(*b, 10, 1.0, 1.0, 0.0, defer_join=True)
+    if order == "read_first":           # values read before any backward: the caller joins explicitly
+        ops.join_side(DEV)
+        early = [o.detach().clone() for o in (out_a[0], out_b[0])]
+        torch.cuda.synchronize()
+        assert torch.equal(early[0], ref_a[0]) and torch.equal(early[1], ref_b[0])
+    for which in ("ab" if order == "read_first" else order):
+        (out_a if which == "a" else out_b)[0].backward()
+    ops.join_side(DEV)
+    torch.cuda.synchronize()
+    for out, t, ref, nm in ((out_a, a, ref_a, "A"), (out_b, b, ref_b, "B")):
+        got = [out[0].detach(), out[1].detach(), out[2].detach(), out[3][0].detach(), t[0].grad, t[1].grad, t[3].grad]
+        for g, r, what in zip(got, ref, ("loss", "recon", "kl", "postKL", "dmu", "dlogvar", "draw")):
+            assert torch.equal(g, r), "head %s %s differs when interleaved (%s)" % (nm, what, order)
+
+
 # --------------------------------------------------------------------------------- drop-in: whole MAE
 def _build(case, name):
     import stubs
