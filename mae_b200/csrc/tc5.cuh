@@ -131,6 +131,15 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// one lane of a converged warp (elect.sync).  A single-thread role entered through this predicate lets the compiler issue the
+// uniform-datapath instructions (UTCHMMA, UTCBAR, UBLKCP) directly; behind a plain `lane == 0` test it wraps each of them in
+// an ELECT / BRA.U.ANY loop over the possibly-divergent active mask (5 dependent instructions per MMA on the issuing thread).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+    return pred != 0;
+}
+
 // ---------------------------------------------------------------------------------------------------- MMA
 // shared-memory matrix descriptor: K-major, no swizzle, descriptor version 1 (Blackwell)
 __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
