@@ -125,7 +125,19 @@ mpd_fwd_tc_kernel(const float* __restrict__ tp, int64_t mat, const float* __rest
     const int ntiles = ntr * ntc;
     const int nchunk = Kp / kTcKC;
     const int kq = Kp / 4;
-    const int my_tiles = (int)blockIdx.x < ntiles ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    // a CTA takes a CONTIGUOUS range of tiles in row-major order, so consecutive tiles share the row tile.  With K = 2D = 128
+    // the four A stages in TMEM hold the whole pre-split row operand: it is stored once per run of equal row tiles and every
+    // tile of the run reads it in place ("resident").  Why it matters: L2 delivers ~43 B/clk to an SM (~6300 B/clk chip-wide),
+    // a 128 x 128 tile at the MMA floor (48 MMAs x 64 cycles) would need 83 B/clk when both operands are re-read per tile
+    // (profiles/r2_mma_rate.txt); with A resident only B streams: 43 B/clk.
+    // Otherwise (K > 128) the tiles are dealt round-robin: the CTAs then work on neighbouring tiles of one row at a time and
+    // share its A operand in L2 (contiguous ranges measured 30 % slower there).
+    const bool resident = (nchunk == kFwdAStages);
+    const int per_cta = (ntiles + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int t_begin = resident ? min(ntiles, (int)blockIdx.x * per_cta) : (int)blockIdx.x;
+    const int t_step = resident ? 1 : (int)gridDim.x;
+    const int my_tiles = resident ? min(ntiles, t_begin + per_cta) - t_begin
+                                  : ((int)blockIdx.x < ntiles ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0);
     const int total = my_tiles * nchunk;         // chunks of this CTA, in (tile, k) order
     pdl_wait();                // tiled panels, E / F and m come from the kernels before this one
     pdl_launch_dependents();
@@ -159,8 +171,8 @@ mpd_fwd_tc_kernel(const float* __restrict__ tp, int64_t mat, const float* __rest
         float* fw = fs + wg * kTcT;
         const float m = (float)hdr->m;
         double tot = 0.0;
-        int it = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        for (int it = 0; it < my_tiles; ++it) {
+            const int tile = t_begin + it * t_step;
             if ((it & 1) != wg) continue;
             const int use = it >> 1;
             const int ti = tr0 + tile / ntc, tj = tc0 + tile % ntc;
@@ -265,9 +277,7 @@ mpd_fwd_tc_kernel(const float* __restrict__ tp, int64_t mat, const float* __rest
         const int t = ((warp & 3) << 5) | lane;
         const uint32_t ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)kFwdTcACol;
         const float* xh = tp, * xl = tp + mat;
-        for (int qn = pw; qn < total; qn += 2) {
-            const int tile = blockIdx.x + (qn / nchunk) * gridDim.x;
-            const int ti = tr0 + tile / ntc, kc = qn % nchunk;
+        auto produce = [&](int ti, int kc, int s, uint32_t empty_parity) {
             const int64_t o = (((int64_t)ti * kq + kc * 8) * 128 + t) * 4;
             float h[kTcKC], l[kTcKC];
 #pragma unroll
@@ -277,8 +287,7 @@ mpd_fwd_tc_kernel(const float* __restrict__ tp, int64_t mat, const float* __rest
                 h[4 * g] = a.x; h[4 * g + 1] = a.y; h[4 * g + 2] = a.z; h[4 * g + 3] = a.w;
                 l[4 * g] = b.x; l[4 * g + 1] = b.y; l[4 * g + 2] = b.z; l[4 * g + 3] = b.w;
             }
-            const int s = qn % kFwdAStages;
-            wait(&aempty[s], ((uint32_t)(qn / kFwdAStages) & 1u) ^ 1u, pw0);
+            wait(&aempty[s], empty_parity, pw0);
             tc5::fence_after_sync();
             const uint32_t tas = ta + (uint32_t)(s * 2 * kTcKC);
 #pragma unroll
@@ -290,6 +299,21 @@ mpd_fwd_tc_kernel(const float* __restrict__ tp, int64_t mat, const float* __rest
             tc5::fence_before_sync();
             __syncwarp();
             if (lane == 0) tc5::mbar_arrive(&afull[s]);
+        };
+        if (resident) {
+            int run = 0, prev_ti = -1;
+            for (int it = 0; it < my_tiles; ++it) {
+                const int ti = tr0 + (t_begin + it) / ntc;
+                if (ti == prev_ti) continue;
+                prev_ti = ti;           // a new row tile: refill the four stages once the previous run's MMAs are done
+                for (int kc = pw; kc < nchunk; kc += 2) produce(ti, kc, kc, ((uint32_t)run & 1u) ^ 1u);
+                ++run;
+            }
+        } else {
+            for (int qn = pw; qn < total; qn += 2) {
+                const int tile = t_begin + (qn / nchunk) * t_step;
+                produce(tr0 + tile / ntc, qn % nchunk, qn % kFwdAStages, ((uint32_t)(qn / kFwdAStages) & 1u) ^ 1u);
+            }
         }
         if (t == 0) report(8 + 4 * pw);
     } else if (warp == 17) {
@@ -297,7 +321,7 @@ mpd_fwd_tc_kernel(const float* __restrict__ tp, int64_t mat, const float* __rest
         if (tc5::elect_one()) {
             const float* yh = tp + 2 * mat, * yl = tp + 3 * mat;
             for (int qn = 0; qn < total; ++qn) {
-                const int tile = blockIdx.x + (qn / nchunk) * gridDim.x;
+                const int tile = t_begin + (qn / nchunk) * t_step;
                 const int tj = tc0 + tile % ntc, kc = qn % nchunk;
                 const int64_t o = (((int64_t)tj * kq + kc * 8) * 128) * 4;
                 const int s = qn % kFwdBStages;
@@ -312,9 +336,14 @@ mpd_fwd_tc_kernel(const float* __restrict__ tp, int64_t mat, const float* __rest
         // ------------------------------------------------------------ MMA issuer
         constexpr uint32_t idesc = tc5::idesc_tf32(kTcT, kTcT);
         const uint32_t b_a = tc5::smem_u32(bst);
-        int qn = 0, it = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        int qn = 0, run = -1, prev_ti = -1;
+        for (int it = 0; it < my_tiles; ++it) {
+            const int tile = t_begin + it * t_step;
             const int a = it & 1, use = it >> 1;
+            const int ti = tr0 + tile / ntc;
+            const bool new_row = resident && ti != prev_ti;                    // wait for the row operand once per run ...
+            const bool run_ends = resident && (it + 1 == my_tiles || tr0 + (tile + 1) / ntc != ti);    // ... release it after the last tile
+            if (new_row) { ++run; prev_ti = ti; }
             wait(&tempty[a], ((uint32_t)use & 1u) ^ 1u, pw0);
             tc5::fence_after_sync();
             const uint32_t d = tmem_base + (uint32_t)(a * kTcT);
@@ -323,7 +352,8 @@ mpd_fwd_tc_kernel(const float* __restrict__ tp, int64_t mat, const float* __rest
             // descriptor is loop-invariant (the issuing thread's uniform-datapath arithmetic was on the critical path:
             // 75 % busy at 2.2x the tensor pipe's 64 cycles per MMA)
             auto chunk = [&](int kc, int sa, int sb) {
-                wait(&afull[sa], (uint32_t)(qn / kFwdAStages) & 1u, pw1);
+                if (!resident) wait(&afull[sa], (uint32_t)(qn / kFwdAStages) & 1u, pw1);
+                else if (new_row) wait(&afull[sa], (uint32_t)run & 1u, pw1);
                 { long long tmpw = 0; wait(&bfull[sb], (uint32_t)(qn / kFwdBStages) & 1u, tmpw); pw1 += tmpw; if (prof) prof[31] += tmpw; }
                 tc5::fence_after_sync();
                 const uint32_t a_hi = tmem_base + (uint32_t)(kFwdTcACol + sa * 2 * kTcKC), a_lo = a_hi + kTcKC;
@@ -336,7 +366,7 @@ mpd_fwd_tc_kernel(const float* __restrict__ tp, int64_t mat, const float* __rest
                     tc5::mma_tf32_ts(d, a_hi + 8 * j, bl, idesc, 1u);
                     tc5::mma_tf32_ts(d, a_hi + 8 * j, bh, idesc, 1u);
                 }
-                tc5::mma_commit(&aempty[sa]);
+                if (!resident || run_ends) tc5::mma_commit(&aempty[sa]);
                 tc5::mma_commit(&bempty[sb]);
                 ++qn;
             };
