@@ -68,14 +68,16 @@ __device__ long long g_mpd_prof[64];     // MAE_MPD_PROF=1: per-role cycle count
 constexpr int kFwdAStages = 4;       // TMEM operand stages (A = x~ rows): 256 + 4 * 64 = all 512 columns
 constexpr int kFwdBStages = 4;       // shared-memory stages (B = y~ rows, filled by the bulk-copy engine); six stages with run-time
                                      // stage indices in the issuer measured slower (0.475 vs 0.443 ms at B = 16384 / D = 64)
+constexpr int kStagePitch = 36;      // floats per row of a 32 x 32 staging tile (16-byte aligned, bank-conflict-free)
 struct FwdTcSmem {
     static constexpr int kBOff = 0;
-    static constexpr int kFOff = kFwdBStages * kTcStageB;          // f_j of the current tile, one copy per epilogue warpgroup
-    static constexpr int kBarOff = kFOff + 2 * kTcT * 4;
+    static constexpr int kFOff = kFwdBStages * kTcStageB;          // f_j of the current tile, one copy per epilogue / helper warpgroup
+    static constexpr int kBarOff = kFOff + 4 * kTcT * 4;
     static constexpr int kNumBars = 2 * kFwdAStages + 2 * kFwdBStages + 4;
     static constexpr int kSlotOff = kBarOff + kNumBars * 8;
     static constexpr int kRedOff = kSlotOff + 16;
-    static constexpr int kBytes = kRedOff + 8 * 8 + 16;
+    static constexpr int kStageOff = (kRedOff + 16 * 8 + 16 + 15) / 16 * 16;     // per-warp KL staging tiles (16 warps)
+    static constexpr int kBytes = kStageOff + 16 * 32 * kStagePitch * 4;
 };
 constexpr int kFwdTcThreads = (8 + 8 + 1 + 1) * 32;   // 2 epilogue warpgroups, 2 A warpgroups, MMA warp, loader warp
 
@@ -153,7 +155,7 @@ mpd_fwd_tc_kernel(const float* __restrict__ tp, int64_t mat, const float* __rest
         }
         for (int a = 0; a < 2; ++a) {
             tc5::mbar_init(&tfull[a], 1);
-            tc5::mbar_init(&tempty[a], 4);
+            tc5::mbar_init(&tempty[a], resident ? 8 : 4);      // one arrival per epilogue (and helper) warp
         }
         tc5::fence_barrier_init();
     }
@@ -163,87 +165,104 @@ mpd_fwd_tc_kernel(const float* __restrict__ tp, int64_t mat, const float* __rest
     tc5::fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp < 8) {
-        // ------------------------------------------------------------ epilogue: thread = row of the tile
-        const int wg = warp >> 2, q = warp & 3;
+    // ---------------------------------------------------------------- epilogue of one tile: thread = row of the tile, columns
+    // [c_lo, c_hi) of accumulator `acc`.  Run by the epilogue warpgroup that owns the accumulator and, in resident mode, by the
+    // otherwise idle A warpgroup of the same parity on the other half of the columns (8 warps per tile instead of 4).
+    const float m_piv = (float)hdr->m;
+    auto epilogue_tile = [&](int it, int acc, int q, int c_lo, int c_hi, float* fw, int bar_id, double& tot, long long& pwacc) {
         const int t = (q << 5) | lane;
-        const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(wg * kTcT);
-        float* fw = fs + wg * kTcT;
-        const float m = (float)hdr->m;
-        double tot = 0.0;
-        for (int it = 0; it < my_tiles; ++it) {
-            const int tile = t_begin + it * t_step;
-            if ((it & 1) != wg) continue;
-            const int use = it >> 1;
-            const int ti = tr0 + tile / ntc, tj = tc0 + tile % ntc;
-            const int i = ti * kTcT + t;
-            const float ei = evec[i];
-            tc5::named_sync(1 + wg, 128);                 // the previous tile's readers of fw are done
-            fw[t] = fvec[tj * kTcT + t];
-            tc5::named_sync(1 + wg, 128);
-            const bool row_ok = (i >= row0) && (i < row1);
-            const bool plain = (ti != tj) && (tj * kTcT + kTcT <= B);      // no diagonal, no padded columns
-            wait(&tfull[wg], use & 1, pw0);
-            tc5::fence_after_sync();
-            float psum = 0.f;
-            float* klrow = KL != nullptr ? KL + (int64_t)(i - kl_base) * Bp + tj * kTcT : nullptr;
-            float* kltcol = KLT != nullptr ? KLT + (int64_t)(tj * kTcT - kl_base) * Bp + ti * kTcT + t : nullptr;
-            float v[16], w[16];
-            tc5::tmem_ld16(tacc, v);
-            tc5::tmem_ld_wait();
+        const int tile = t_begin + it * t_step;
+        const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kTcT);
+        const int use = it >> 1;
+        const int ti = tr0 + tile / ntc, tj = tc0 + tile % ntc;
+        const int i = ti * kTcT + t;
+        const float ei = evec[i];
+        const float m = m_piv;
+        tc5::named_sync(bar_id, 128);                 // the previous tile's readers of fw are done
+        fw[t] = fvec[tj * kTcT + t];
+        tc5::named_sync(bar_id, 128);
+        const bool row_ok = (i >= row0) && (i < row1);
+        const bool plain = (ti != tj) && (tj * kTcT + kTcT <= B);      // no diagonal, no padded columns
+        wait(&tfull[acc], use & 1, pwacc);
+        tc5::fence_after_sync();
+        float psum = 0.f;
+        float* klrow = KL != nullptr ? KL + (int64_t)(i - kl_base) * Bp + tj * kTcT : nullptr;
+        float* kltcol = KLT != nullptr ? KLT + (int64_t)(tj * kTcT - kl_base) * Bp + ti * kTcT + t : nullptr;
+        float* stage = reinterpret_cast<float*>(smem + SM::kStageOff) + warp * (32 * kStagePitch);
+        float v[16], w[16];
+        tc5::tmem_ld16(tacc + c_lo, v);
+        tc5::tmem_ld_wait();
 #pragma unroll 1
-            for (int c0 = 0; c0 < kTcT; c0 += 16) {
-                if (c0 + 16 < kTcT) tc5::tmem_ld16(tacc + c0 + 16, w);     // in flight while this batch is evaluated
-                if (plain && row_ok) {       // interior tile: no masks; f_j by 16-byte broadcast loads
+        for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
+            if (c0 + 16 < c_hi) tc5::tmem_ld16(tacc + c0 + 16, w);     // in flight while this batch is evaluated
+            if (plain && row_ok) {       // interior tile: no masks; f_j by 16-byte broadcast loads
 #pragma unroll
-                    for (int g4 = 0; g4 < 4; ++g4) {
-                        const float4 f4 = *reinterpret_cast<const float4*>(fw + c0 + 4 * g4);
-                        const float ff[4] = {f4.x, f4.y, f4.z, f4.w};
+                for (int g4 = 0; g4 < 4; ++g4) {
+                    const float4 f4 = *reinterpret_cast<const float4*>(fw + c0 + 4 * g4);
+                    const float ff[4] = {f4.x, f4.y, f4.z, f4.w};
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const float kl = 0.5f * (v[4 * g4 + e] + (ei + ff[e]));
-                            v[4 * g4 + e] = kl;
-                            const float dev = kl - m;
-                            psum = fmaf(dev, dev, psum);
-                        }
-                    }
-                } else {
-#pragma unroll
-                    for (int c = 0; c < 16; ++c) {
-                        const float kl = 0.5f * (v[c] + (ei + fw[c0 + c]));
-                        v[c] = kl;
+                    for (int e = 0; e < 4; ++e) {
+                        const float kl = 0.5f * (v[4 * g4 + e] + (ei + ff[e]));
+                        v[4 * g4 + e] = kl;
                         const float dev = kl - m;
-                        const int j = tj * kTcT + c0 + c;
-                        const bool ok = row_ok && j < B && j != i;
-                        psum = ok ? fmaf(dev, dev, psum) : psum;
+                        psum = fmaf(dev, dev, psum);
                     }
                 }
-                if (klrow != nullptr) {
+            } else {
 #pragma unroll
-                    for (int g4 = 0; g4 < 4; ++g4)
-                        *reinterpret_cast<float4*>(klrow + c0 + 4 * g4) = make_float4(v[4 * g4], v[4 * g4 + 1], v[4 * g4 + 2], v[4 * g4 + 3]);
+                for (int c = 0; c < 16; ++c) {
+                    const float kl = 0.5f * (v[c] + (ei + fw[c0 + c]));
+                    v[c] = kl;
+                    const float dev = kl - m;
+                    const int j = tj * kTcT + c0 + c;
+                    const bool ok = row_ok && j < B && j != i;
+                    psum = ok ? fmaf(dev, dev, psum) : psum;
                 }
-                if (kltcol != nullptr) {
-#pragma unroll
-                    for (int c = 0; c < 16; ++c) kltcol[(int64_t)(c0 + c) * Bp] = v[c];      // lanes = consecutive i: coalesced
-                }
-                tc5::tmem_ld_wait();
-#pragma unroll
-                for (int c = 0; c < 16; ++c) v[c] = w[c];
             }
-            tc5::fence_before_sync();
-            __syncwarp();
-            if (lane == 0) tc5::mbar_arrive(&tempty[wg]);
-            tot += (double)psum;
+            if (klrow != nullptr) {
+                // KL rows leave through a per-warp staging tile (32 rows x 32 columns, pitch 36 floats: conflict-free for the
+                // 16-byte row writes and for the 16-byte reads below), so that one store instruction writes four complete
+                // 128-byte lines.  Thread = row storing 16 bytes of its own row touched 32 lines per instruction: 4096 L1
+                // wavefronts per tile, on the data path the MMA reads its B operand through (issuer blocked at 131 cycles / MMA).
+                float* strow = stage + lane * kStagePitch + (c0 & 16);
+#pragma unroll
+                for (int g4 = 0; g4 < 4; ++g4)
+                    *reinterpret_cast<float4*>(strow + 4 * g4) = make_float4(v[4 * g4], v[4 * g4 + 1], v[4 * g4 + 2], v[4 * g4 + 3]);
+                if (c0 & 16) {
+                    __syncwarp();
+                    const int cb = c0 - 16;                    // first column of the staged 32
+                    float* gdst = KL + (int64_t)(ti * kTcT + q * 32 - kl_base) * Bp + tj * kTcT + cb + (lane & 7) * 4;
+#pragma unroll
+                    for (int r4 = 0; r4 < 8; ++r4) {
+                        const int r = r4 * 4 + (lane >> 3);
+                        const float4 x4 = *reinterpret_cast<const float4*>(stage + r * kStagePitch + (lane & 7) * 4);
+                        *reinterpret_cast<float4*>(gdst + (int64_t)r * Bp) = x4;
+                    }
+                    __syncwarp();
+                }
+            }
+            if (kltcol != nullptr) {
+#pragma unroll
+                for (int c = 0; c < 16; ++c) kltcol[(int64_t)(c0 + c) * Bp] = v[c];      // lanes = consecutive i: coalesced
+            }
+            tc5::tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 16; ++c) v[c] = w[c];
         }
-        if (t == 0) report(4 * wg);
-        // CTA total over the 256 epilogue threads, fixed order
+        tc5::fence_before_sync();
+        __syncwarp();
+        if (lane == 0) tc5::mbar_arrive(&tempty[acc]);
+        tot += (double)psum;
+    };
+    // CTA total of the squared deviations over the warps that ran epilogues, fixed order; the last CTA adds the CTA totals
+    const int nred = resident ? 16 : 8;
+    auto reduce_total = [&](double tot) {
         tot = warp_sum(tot);
         if (lane == 0) red[warp] = tot;
-        tc5::named_sync(3, 256);
+        tc5::named_sync(3, nred * 32);
         if (sumsq_out != nullptr && threadIdx.x == 0) {
             double s = 0.0;
-            for (int w8 = 0; w8 < 8; ++w8) s += red[w8];
+            for (int w8 = 0; w8 < nred; ++w8) s += red[w8];
             if (gridDim.x == 1) {
                 is_last = true;
                 part[0] = s;
@@ -254,7 +273,7 @@ mpd_fwd_tc_kernel(const float* __restrict__ tp, int64_t mat, const float* __rest
                 is_last = (tk == gridDim.x - 1);
             }
         }
-        tc5::named_sync(3, 256);
+        tc5::named_sync(3, nred * 32);
         if (sumsq_out != nullptr && is_last && warp == 0) {
             __threadfence();
             double s = 0.0;
@@ -270,6 +289,16 @@ mpd_fwd_tc_kernel(const float* __restrict__ tp, int64_t mat, const float* __rest
                 hdr->ticket_fwd = 0u;
             }
         }
+    };
+
+    if (warp < 8) {
+        // ------------------------------------------------------------ epilogue warpgroups: accumulator wg, tiles of parity wg
+        const int wg = warp >> 2, q = warp & 3;
+        const int c_hi = resident ? kTcT / 2 : kTcT;
+        double tot = 0.0;
+        for (int it = wg; it < my_tiles; it += 2) epilogue_tile(it, wg, q, 0, c_hi, fs + wg * kTcT, 1 + wg, tot, pw0);
+        if (((q << 5) | lane) == 0) report(4 * wg);
+        reduce_total(tot);
     } else if (warp < 16) {
         // ------------------------------------------------------------ A: pre-split x~ rows -> TMEM operand stage; the two
         // warpgroups take alternate chunks, so one has its 16 loads in flight while the other stores
@@ -301,21 +330,28 @@ mpd_fwd_tc_kernel(const float* __restrict__ tp, int64_t mat, const float* __rest
             if (lane == 0) tc5::mbar_arrive(&afull[s]);
         };
         if (resident) {
+            // per tile, in order: refill the four stages when a new row tile starts (once the previous run's MMAs are done),
+            // then help the epilogue warpgroup of this parity with the upper half of the columns
             int run = 0, prev_ti = -1;
+            double tot = 0.0;
             for (int it = 0; it < my_tiles; ++it) {
                 const int ti = tr0 + (t_begin + it) / ntc;
-                if (ti == prev_ti) continue;
-                prev_ti = ti;           // a new row tile: refill the four stages once the previous run's MMAs are done
-                for (int kc = pw; kc < nchunk; kc += 2) produce(ti, kc, kc, ((uint32_t)run & 1u) ^ 1u);
-                ++run;
+                if (ti != prev_ti) {
+                    prev_ti = ti;
+                    for (int kc = pw; kc < nchunk; kc += 2) produce(ti, kc, kc, ((uint32_t)run & 1u) ^ 1u);
+                    ++run;
+                }
+                if ((it & 1) == pw) epilogue_tile(it, pw, warp & 3, kTcT / 2, kTcT, fs + (2 + pw) * kTcT, 4 + pw, tot, pw1);
             }
+            if (t == 0) report(8 + 4 * pw);
+            reduce_total(tot);
         } else {
             for (int qn = pw; qn < total; qn += 2) {
                 const int tile = t_begin + (qn / nchunk) * t_step;
                 produce(tr0 + tile / ntc, qn % nchunk, qn % kFwdAStages, ((uint32_t)(qn / kFwdAStages) & 1u) ^ 1u);
             }
+            if (t == 0) report(8 + 4 * pw);
         }
-        if (t == 0) report(8 + 4 * pw);
     } else if (warp == 17) {
         // ------------------------------------------------------------ loader: B = y~ chunk, two contiguous 16 KB bulk copies
         if (tc5::elect_one()) {
