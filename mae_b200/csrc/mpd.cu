@@ -891,12 +891,24 @@ struct KlGeom {
     int64_t base, rows_pad, kl_off, klt_off, total;
     int64_t tc_split, gp_off, rs_off;   // tensor-core backward: partner splits, partial G1 / G2 sums, partial row sums
 };
-// partner splits of the tensor-core backward: enough CTAs (row tiles x column chunks x splits) for ~2 per SM
+// partner splits of the tensor-core backward.  The kernel runs one CTA per SM (131 KB of shared memory, 576 threads), so its
+// time is whole rounds of 148 CTAs: pick the split count whose CTA count (row tiles x column chunks x splits) fills its last
+// round best (B = 16384 / D = 64: 3 splits = 2.6 rounds -> 8 splits = 6.9 rounds; D = 256: 1 split = 3.5 rounds -> 2 splits =
+// 6.9), the smaller count on a tie.  A split keeps at least one accumulation group (4 partner tiles).
 int64_t tc_splits(int64_t row_tiles, int64_t col_chunks, int64_t partner_tiles) {
-    int64_t s = ceil_div(2 * 148, row_tiles * col_chunks);
-    if (s > 8) s = 8;
-    if (s > partner_tiles) s = partner_tiles;
-    return s < 1 ? 1 : s;
+    const int64_t base = row_tiles * col_chunks;
+    int64_t best = 1;
+    double best_eff = 0.0;
+    for (int64_t s = 1; s <= 8 && s <= partner_tiles; ++s) {
+        if (s > 1 && ceil_div(partner_tiles, s) < 4) break;
+        const int64_t ctas = base * s, rounds = ceil_div(ctas, 148);
+        const double eff = (double)ctas / (double)(rounds * 148);
+        if (eff > best_eff + 0.02) {
+            best_eff = eff;
+            best = s;
+        }
+    }
+    return best;
 }
 // chunks of 32 partners per TMEM accumulation of the tensor-core backward (default 16 = 512 partners = 192 accumulating
 // MMAs): the tensor core's accumulator does not round to nearest, so the error of a running sum grows with its length
