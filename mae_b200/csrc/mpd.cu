@@ -1138,7 +1138,7 @@ extern "C" int mae_mpd_bwd(const float* mu, int64_t mu_stride, const float* logv
         const int tps = (int)ceil_div(ntc, nsplit);
         float* gp = at<float>(workspace, kg.gp_off);
         float* rsp = at<float>(workspace, kg.rs_off);
-        dim3 grid((unsigned)ntrt, (unsigned)(L.Kp / kTcT), (unsigned)nsplit);
+        dim3 grid((unsigned)(L.Kp / kTcT), (unsigned)ntrt, (unsigned)nsplit);
         static const bool want_bprof = getenv("MAE_MPD_PROF") != nullptr;
         long long* bprof = nullptr;
         if (want_bprof) {

@@ -491,8 +491,11 @@ mpd_bwd_tc_kernel(const float* __restrict__ tp, int64_t mat, const Hdr* __restri
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM::kSlotOff);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ti = tr0 + blockIdx.x;
-    const int kbase = blockIdx.y * kTcT;
+    // grid = (column chunks, row tiles, splits): the CTAs that share the KL rows of one row tile (one per 128 gradient columns)
+    // are launched next to each other and run in step, so the rows come from HBM once and from L2 for the other chunks
+    const int ti = tr0 + blockIdx.y;
+    const int cchunk = blockIdx.x;
+    const int kbase = cchunk * kTcT;
     const int split = blockIdx.z;
     const int tj0 = split * tiles_per_split;
     const int tj1 = min(ntc, tj0 + tiles_per_split);
@@ -614,7 +617,7 @@ mpd_bwd_tc_kernel(const float* __restrict__ tp, int64_t mat, const Hdr* __restri
             if (prof != nullptr) pw2 += clock64() - td0;
         }
         if (t == 0 && pair == 0) report(4 * which);
-        if (blockIdx.y == 0) rspart[(((int64_t)split * 2 + which) * 2 + pair) * rows_pad + lrow] = rs;
+        if (cchunk == 0) rspart[(((int64_t)split * 2 + which) * 2 + pair) * rows_pad + lrow] = rs;
         if (total == 0) {
             for (int c = 0; c < 64; ++c) dst[(int64_t)c * rows_pad] = 0.f;
         }
@@ -624,7 +627,7 @@ mpd_bwd_tc_kernel(const float* __restrict__ tp, int64_t mat, const Hdr* __restri
             const int ncn = Kp / 128;
             for (int qn = 0; qn < total; ++qn) {
                 const int tj = tj0 + qn / (kTcT / kTcKC), jc = qn % (kTcT / kTcKC);
-                const int64_t o = ((((int64_t)tj * ncn + blockIdx.y) * 32 + jc * 8) * 128) * 4;
+                const int64_t o = ((((int64_t)tj * ncn + cchunk) * 32 + jc * 8) * 128) * 4;
                 const int s = qn % kBwdPStages;
                 wait(&pempty[s], ((uint32_t)(qn / kBwdPStages) & 1u) ^ 1u, pw0);
                 tc5::mbar_expect_tx(&pfull[s], kBwdTcStageB);
