@@ -896,6 +896,8 @@ struct KlGeom {
 // round best (B = 16384 / D = 64: 3 splits = 2.6 rounds -> 8 splits = 6.9 rounds; D = 256: 1 split = 3.5 rounds -> 2 splits =
 // 6.9), the smaller count on a tie.  A split keeps at least one accumulation group (4 partner tiles).
 int64_t tc_splits(int64_t row_tiles, int64_t col_chunks, int64_t partner_tiles) {
+    static const int forced = []() { const char* e = getenv("MAE_MPD_TC_SPLIT"); return e ? atoi(e) : 0; }();   // tuning aid
+    if (forced > 0) return forced > partner_tiles ? partner_tiles : forced;
     const int64_t base = row_tiles * col_chunks;
     int64_t best = 1;
     double best_eff = 0.0;
