@@ -561,8 +561,8 @@ mpd_bwd_tc_kernel(const float* __restrict__ tp, int64_t mat, const Hdr* __restri
                     }
                 }
                 const bool plain = row_ok && (j0 + kTcKC <= B) && (i < j0 || i >= j0 + kTcKC);
-                wait(&wempty[pair], ((uint32_t)use & 1u) ^ 1u, pw0);
-                tc5::fence_after_sync();
+                // the first half of the chunk is split BEFORE the wait for the free stage: less work between the MMA's release
+                // of the stage and this pair's 'full' arrival (that interval is on the issuer's critical path)
 #pragma unroll
                 for (int h0 = 0; h0 < kTcKC; h0 += 16) {
                     float h[16], l[16];
@@ -572,6 +572,10 @@ mpd_bwd_tc_kernel(const float* __restrict__ tp, int64_t mat, const Hdr* __restri
                         const float w = ok ? v[h0 + j] - m : 0.f;
                         rs += w;
                         tc5::split_tf32(w, h[j], l[j]);
+                    }
+                    if (h0 == 0) {
+                        wait(&wempty[pair], ((uint32_t)use & 1u) ^ 1u, pw0);
+                        tc5::fence_after_sync();
                     }
                     tc5::tmem_st16(tws + h0, h);
                     tc5::tmem_st16(tws + kTcKC + h0, l);
