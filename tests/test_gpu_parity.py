@@ -204,6 +204,29 @@ def test_mpd_tensor_core_tiles_vs_chunked_oracle(ops, O, mpd_tc, regime):
           + ", ".join("%s %s %.1e" % ("tensor" if tc else "FFMA", nm, e) for (tc, nm), e in sorted(worst.items())))
 
 
+@pytest.mark.parametrize("b,d", [(2500, 64), (3000, 32), (2200, 96), (2100, 256)])
+def test_mpd_tensor_core_ragged_sizes(ops, O, mpd_tc, b, d):
+    """batches that are not a multiple of the 128-row tile (padded rows and columns are masked in the epilogue and in the
+    weights) at every contraction length the tensor-core kernels treat differently: K = 2D = 128 (row operand resident in
+    TMEM, contiguous tile ranges, column-half helpers), K = 64 (two chunks per tile, generic issue loop), K = 192 and 512
+    (streamed row operand, round-robin tiles, several column chunks in the backward)."""
+    from mae_b200 import synth
+    mu0, lv0 = synth.posterior_params(b, (d,), seed=37)
+    ref = {}
+    for key, dt in (("r64", torch.float64), ("r32", torch.float32)):
+        a, c = cu(mu0).to(dt).requires_grad_(), cu(lv0).to(dt).requires_grad_()
+        m_ref, s_ref = O.post_kl_chunked(a, c, rows_per_chunk=256)
+        (-0.7 * torch.nn.functional.logsigmoid(m_ref).sum() + 1.3 * s_ref).backward()
+        ref[key] = (m_ref.detach(), s_ref.detach(), a.grad, c.grad)
+    mpd_tc(1)
+    for path in (3, 2):
+        mu, lv = cu(mu0).requires_grad_(), cu(lv0).requires_grad_()
+        m_d, s = ops.mpd(mu, lv, bwd_path=path)
+        (-0.7 * torch.nn.functional.logsigmoid(m_d).sum() + 1.3 * s).backward()
+        for got, i, nm in ((m_d, 0, "m_d"), (s, 1, "S"), (mu.grad, 2, "dmu"), (lv.grad, 3, "dlv")):
+            check_close(got, ref["r64"][i], ref["r32"][i], what="B=%d D=%d %s path=%d" % (b, d, nm, path))
+
+
 def test_mpd_tensor_core_row_blocks(ops, mpd_tc):
     """row blocks (the sharded decomposition) through the tensor-core tiles: partial sums add up to the full batch's, the
     stored KL_ij / KL_ji rows of a block give the same own-row gradients as the full batch"""
