@@ -543,12 +543,14 @@ mpd_bwd_tc_kernel(const float* __restrict__ tp, int64_t mat, const Hdr* __restri
         float* dst = gpart + (((int64_t)split * 2 + which) * Kp + kbase + pair * 64) * rows_pad + lrow;   // [k][row], see the drain
         const int ngroups = (total + group_chunks - 1) / group_chunks;
         int use = 0;       // chunks this pair has produced (parity of its stage's empty barrier)
+        long long ph_load = 0, ph_store = 0, ph_split2 = 0, ph_stwait = 0, tp1 = 0;      // profiling runs: where a weight warp's time goes
         for (int g = 0; g < ngroups; ++g) {
             const int q_end = min(total, (g + 1) * group_chunks);
             int q0 = g * group_chunks;
             q0 += ((q0 & 1) != pair) ? 1 : 0;
             for (int qn = q0; qn < q_end; qn += 2, ++use) {
                 const int j0 = tj0 * kTcT + qn * kTcKC;
+                const long long tp0 = prof != nullptr ? clock64() : 0;
                 float v[kTcKC];
                 if (by_col) {        // KL_ji from column i of KL: for a fixed j the lanes (consecutive i) read one 128-byte line
 #pragma unroll
@@ -563,29 +565,59 @@ mpd_bwd_tc_kernel(const float* __restrict__ tp, int64_t mat, const Hdr* __restri
                 const bool plain = row_ok && (j0 + kTcKC <= B) && (i < j0 || i >= j0 + kTcKC);
                 // the first half of the chunk is split BEFORE the wait for the free stage: less work between the MMA's release
                 // of the stage and this pair's 'full' arrival (that interval is on the issuer's critical path)
+                // interior chunks (no diagonal, no padded partners or rows: warp-uniform test) take a branch-free loop of 7
+                // instructions per element; per-element mask branches left ~20 instructions per element with no overlap
+                // between elements (1 450 cycles for 16 elements, the critical resource of this kernel)
+                const bool all_plain = __all_sync(0xffffffffu, plain);
 #pragma unroll
                 for (int h0 = 0; h0 < kTcKC; h0 += 16) {
                     float h[16], l[16];
+                    if (all_plain) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const bool ok = plain || (row_ok && (j0 + h0 + j) < B && (j0 + h0 + j) != i);
-                        const float w = ok ? v[h0 + j] - m : 0.f;
-                        rs += w;
-                        tc5::split_tf32(w, h[j], l[j]);
+                        for (int j = 0; j < 16; ++j) {
+                            const float w = v[h0 + j] - m;
+                            rs += w;
+                            tc5::split_tf32_fast(w, h[j], l[j]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const bool ok = row_ok && (j0 + h0 + j) < B && (j0 + h0 + j) != i;
+                            const float w = ok ? v[h0 + j] - m : 0.f;
+                            rs += w;
+                            tc5::split_tf32_fast(w, h[j], l[j]);
+                        }
                     }
                     if (h0 == 0) {
+                        if (prof != nullptr) ph_load += clock64() - tp0;      // loads landed + first half split
                         wait(&wempty[pair], ((uint32_t)use & 1u) ^ 1u, pw0);
                         tc5::fence_after_sync();
+                        if (prof != nullptr) tp1 = clock64();
                     }
                     tc5::tmem_st16(tws + h0, h);
                     tc5::tmem_st16(tws + kTcKC + h0, l);
                 }
+                const long long tp2 = prof != nullptr ? clock64() : 0;
                 tc5::tmem_st_wait();
+                const long long tp3 = prof != nullptr ? clock64() : 0;
                 tc5::fence_before_sync();
                 __syncwarp();
                 if (lane == 0) tc5::mbar_arrive(&wfull[pair]);
+                if (prof != nullptr) { ph_store += clock64() - tp1; ph_split2 += tp2 - tp1; ph_stwait += tp3 - tp2; }             // second half split + TMEM stores + arrive
             }
-            // end of an accumulation group: this warpgroup's half of its accumulator (G1 or G2) -> fp32 partial sums
+            // end of an accumulation group: this warpgroup's half of its accumulator (G1 or G2) -> fp32 partial sums.
+            // The drain keeps these warps from loading ahead, so the KL lines of this pair's first chunk of the next group are
+            // pulled into L2 now: after the drain its loads cost an L2 hit instead of an HBM round trip while the issuer waits.
+            {
+                int qp = (g + 1) * group_chunks;
+                qp += ((qp & 1) != pair) ? 1 : 0;
+                if (qp < total) {
+                    const int jp = tj0 * kTcT + qp * kTcKC;
+                    const float* pf = by_col ? krow + (int64_t)(jp + lane) * Bp - lane      // line of partner jp + lane, this warp's rows
+                                             : krow + jp;                                   // this row's 128 bytes
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+                }
+            }
             wait(gfull, (uint32_t)g & 1u, pw1);
             tc5::fence_after_sync();
             const long long td0 = prof != nullptr ? clock64() : 0;
@@ -621,6 +653,12 @@ mpd_bwd_tc_kernel(const float* __restrict__ tp, int64_t mat, const Hdr* __restri
             if (prof != nullptr) pw2 += clock64() - td0;
         }
         if (t == 0 && pair == 0) report(4 * which);
+        if (prof != nullptr && t == 0 && pair == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+            prof[16 + 2 * which] = ph_load;
+            prof[17 + 2 * which] = ph_store;
+            prof[20 + 2 * which] = ph_split2;
+            prof[21 + 2 * which] = ph_stwait;
+        }
         if (cchunk == 0) rspart[(((int64_t)split * 2 + which) * 2 + pair) * rows_pad + lrow] = rs;
         if (total == 0) {
             for (int c = 0; c < 64; ++c) dst[(int64_t)c * rows_pad] = 0.f;

@@ -180,5 +180,16 @@ __device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
     lo = __uint_as_float(l);
 }
 
+// The same split for operands formed on the fly in a hot loop: round-to-nearest (ties away, = cvt.rna) by adding half a tf32
+// ulp to the bit pattern and clearing the 13 low bits - two integer instructions per rounding and no branches.
+// cvt.rna.tf32.f32 compiles to the same add-and-mask plus an |x| < inf test and a select per rounding; identical results for
+// finite inputs (callers pass finite values: KL - m, activations).
+__device__ __forceinline__ void split_tf32_fast(float v, float& hi, float& lo) {
+    const float hf = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u);
+    const float r = v - hf;
+    hi = hf;
+    lo = __uint_as_float((__float_as_uint(r) + 0x1000u) & 0xFFFFE000u);
+}
+
 }  // namespace tc5
 }  // namespace mae

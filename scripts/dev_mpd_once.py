@@ -35,3 +35,7 @@ if os.environ.get("MAE_MPD_PROF"):
     for k, nm in {32: "W1 rows (wait wempty, wait gfull)", 36: "W2 rows", 40: "loader (wait pempty)", 44: "mma issuer (wait w1+w2 full, wait pfull, wait gdrained)"}.items():
         tot = max(out[k], 1)
         print("%-58s total %9d cyc  wait0 %5.1f %%  wait1 %5.1f %%  wait2 %5.1f %%" % (nm, out[k], 100.0 * out[k + 1] / tot, 100.0 * out[k + 2] / tot, 100.0 * out[k + 3] / tot))
+    print("weight warps of pair 0, cycles per own chunk: W1 loads+first-half split %.0f, second half+TMEM stores+arrive %.0f;  W2 %.0f, %.0f"
+          % tuple(out[48 + k] / max(1, nchunk // 8 // 2) for k in range(4)))
+    print("   of the second part: second-half split + store issue %.0f, tcgen05.wait::st %.0f (W1);  %.0f, %.0f (W2)"
+          % tuple(out[52 + k] / max(1, nchunk // 8 // 2) for k in range(4)))
