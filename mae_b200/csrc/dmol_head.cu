@@ -290,7 +290,7 @@ dmol_head_kernel(const __grid_constant__ CUtensorMap hid_map, const float* __res
                 for (int j = 0; j < G::kKC; ++j) {
                     float u = h[j];
                     if (act) u = u > 0.f ? u : hm::fast_ex2(hm::kLog2e * u) - 1.0f;   // ELU(alpha = 1)
-                    tc5::split_tf32(u, h[j], l[j]);      // both parts rounded to tf32 (a truncated lo would bias the sum)
+                    tc5::split_tf32_fast(u, h[j], l[j]);      // both parts rounded to tf32 (a truncated lo would bias the sum)
                 }
                 wait(&aempty[pw], ((uint32_t)(qn / G::kConvWG) & 1u) ^ 1u, pw1);   // the MMAs that read this stage are done
                 tc5::fence_after_sync();
