@@ -962,6 +962,12 @@ extern "C" int mae_debug_mpd_prof(long long* host_out) {
     return (int)cudaMemcpyFromSymbol(host_out, mae::g_mpd_prof, sizeof(long long) * 64);
 }
 
+// development aid (not part of include/mae_b200.h): the partner-split count the tensor-core backward would use (host logic
+// only, callable without a GPU; tests/test_boundary_cpu.py checks the whole-round property)
+extern "C" long long mae_debug_mpd_tc_splits(long long row_tiles, long long col_chunks, long long partner_tiles) {
+    return mae::tc_splits(row_tiles, col_chunks, partner_tiles);
+}
+
 extern "C" int mae_set_mpd_tensor_cores(int enabled) {
     const int before = mae::g_mpd_tc;
     mae::g_mpd_tc = enabled ? 1 : 0;

@@ -57,6 +57,32 @@ def test_argument_validation_without_gpu(lib):
     assert lib.mae_dmol_workspace_bytes(64, 1024) >= 64 * 4 * 4
 
 
+def test_tensor_core_backward_splits_fill_whole_rounds(lib):
+    """host logic of the tensor-core MPD backward (csrc/mpd.cu tc_splits): one CTA per SM, so the CTA count
+    row tiles x column chunks x splits should fill its last round of 148; the chosen split must be at least as good as
+    every smaller one (ties go to the smaller count) and keep >= 4 partner tiles (one accumulation group) per split."""
+    f = lib.mae_debug_mpd_tc_splits
+    f.restype = ctypes.c_longlong
+    f.argtypes = [ctypes.c_longlong] * 3
+
+    def eff(ctas):
+        return ctas / (-(-ctas // 148) * 148)
+
+    for b in (2048, 4096, 8192, 16384, 32768, 65536):
+        for d in (64, 128, 192, 256):
+            for world in (1, 2, 4, 8):
+                row_tiles, cols, partners = b // 128 // world, 2 * d // 128, b // 128
+                if row_tiles == 0:
+                    continue
+                s = f(row_tiles, cols, partners)
+                assert 1 <= s <= 8 and s <= partners
+                assert s == 1 or -(-partners // s) >= 4
+                for smaller in range(1, s):
+                    assert eff(row_tiles * cols * s) > eff(row_tiles * cols * smaller), (b, d, world, s, smaller)
+    # the cases quoted in DESIGN.md 4
+    assert f(128, 1, 128) == 8 and f(128, 4, 128) == 2 and f(64, 1, 64) == 2
+
+
 def test_ops_refuse_cpu_tensors(lib):
     from mae_b200 import ops
     mu, lv, eps = torch.zeros(2, 3), torch.zeros(2, 3), torch.zeros(2, 1, 3)
