@@ -135,6 +135,9 @@ mpd_fwd_tc_kernel(const float* __restrict__ tp, int64_t mat, const float* __rest
     // Otherwise (K > 128) the tiles are dealt round-robin: the CTAs then work on neighbouring tiles of one row at a time and
     // share its A operand in L2 (contiguous ranges measured 30 % slower there).
     const bool resident = (nchunk == kFwdAStages);
+    // the idle A warpgroups help with the epilogue only when KL rows are stored (the evaluation-only forward is MMA-bound with
+    // four epilogue warps per tile; eight measured 4 % slower there)
+    const bool helpers = resident && KL != nullptr;
     const int per_cta = (ntiles + (int)gridDim.x - 1) / (int)gridDim.x;
     const int t_begin = resident ? min(ntiles, (int)blockIdx.x * per_cta) : (int)blockIdx.x;
     const int t_step = resident ? 1 : (int)gridDim.x;
@@ -155,7 +158,7 @@ mpd_fwd_tc_kernel(const float* __restrict__ tp, int64_t mat, const float* __rest
         }
         for (int a = 0; a < 2; ++a) {
             tc5::mbar_init(&tfull[a], 1);
-            tc5::mbar_init(&tempty[a], resident ? 8 : 4);      // one arrival per epilogue (and helper) warp
+            tc5::mbar_init(&tempty[a], helpers ? 8 : 4);      // one arrival per epilogue (and helper) warp
         }
         tc5::fence_barrier_init();
     }
@@ -255,7 +258,7 @@ mpd_fwd_tc_kernel(const float* __restrict__ tp, int64_t mat, const float* __rest
         tot += (double)psum;
     };
     // CTA total of the squared deviations over the warps that ran epilogues, fixed order; the last CTA adds the CTA totals
-    const int nred = resident ? 16 : 8;
+    const int nred = helpers ? 16 : 8;
     auto reduce_total = [&](double tot) {
         tot = warp_sum(tot);
         if (lane == 0) red[warp] = tot;
@@ -294,7 +297,7 @@ mpd_fwd_tc_kernel(const float* __restrict__ tp, int64_t mat, const float* __rest
     if (warp < 8) {
         // ------------------------------------------------------------ epilogue warpgroups: accumulator wg, tiles of parity wg
         const int wg = warp >> 2, q = warp & 3;
-        const int c_hi = resident ? kTcT / 2 : kTcT;
+        const int c_hi = helpers ? kTcT / 2 : kTcT;
         double tot = 0.0;
         for (int it = wg; it < my_tiles; it += 2) epilogue_tile(it, wg, q, 0, c_hi, fs + wg * kTcT, 1 + wg, tot, pw0);
         if (((q << 5) | lane) == 0) report(4 * wg);
@@ -341,10 +344,10 @@ mpd_fwd_tc_kernel(const float* __restrict__ tp, int64_t mat, const float* __rest
                     for (int kc = pw; kc < nchunk; kc += 2) produce(ti, kc, kc, ((uint32_t)run & 1u) ^ 1u);
                     ++run;
                 }
-                if ((it & 1) == pw) epilogue_tile(it, pw, warp & 3, kTcT / 2, kTcT, fs + (2 + pw) * kTcT, 4 + pw, tot, pw1);
+                if (helpers && (it & 1) == pw) epilogue_tile(it, pw, warp & 3, kTcT / 2, kTcT, fs + (2 + pw) * kTcT, 4 + pw, tot, pw1);
             }
             if (t == 0) report(8 + 4 * pw);
-            reduce_total(tot);
+            if (helpers) reduce_total(tot);
         } else {
             for (int qn = pw; qn < total; qn += 2) {
                 const int tile = t_begin + (qn / nchunk) * t_step;
