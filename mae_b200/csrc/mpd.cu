@@ -1158,8 +1158,8 @@ extern "C" int mae_mpd_bwd(const float* mu, int64_t mu_stride, const float* logv
             (int)(row0 + nrows), tr0t, ntc, tps, at<float>(workspace, kg.kl_off) - kg.base * L.Bp,
             full_rows ? nullptr : at<float>(workspace, kg.klt_off) - kg.base * L.Bp, (int)L.Bp, gp, rsp, (int)kg.rows_pad, (int)kg.base,
             tc_group_chunks(), bprof);
-        const int64_t n = nrows * D;
-        mpd_bwd_tc_finish_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, as_stream(stream)>>>(
+        const dim3 fgrid((unsigned)ceil_div(nrows, kFinRows), (unsigned)ceil_div(D, kFinDims));
+        mpd_bwd_tc_finish_kernel<<<fgrid, kFinRows * kFinDims, 0, as_stream(stream)>>>(
             mu, mu_stride, logvar, logvar_stride, at<float4>(workspace, L.vp), at<double>(workspace, L.colstats),
             at<double>(workspace, L.pivots), g_m, g_S, S, gkl, (int)B, (int)D, (int)L.Kp, (int)row0, (int)nrows, nsplit, gp, rsp,
             (int)kg.rows_pad, (int)kg.base, dmu, dlogvar, accumulate);
